@@ -1,0 +1,152 @@
+/* lrzgpu.h -- C ABI of liblrzgpu.so: a B200 (sm_100a) implementation of lrzip-next's compress hot
+ * path (rzip long-range pre-processor -> stream/block framing -> per-block backend), writing
+ * lrzip-next v0.14 archives.
+ *
+ * lrzip-next has no library ABI of its own (its liblrzip was abandoned, src/libdemo/README); the
+ * seams this header replaces are internal C functions.  Each entry point names the reference
+ * interface it stands in for (paths relative to the lrzip-next tree):
+ *
+ *   lrzgpu_compress / _file / _device   rzip_fd()            src/include/rzip.h:12, src/rzip.c:922
+ *                                       + write_magic()      src/lrzip.c:131 (called from
+ *                                                            compress_file(), src/lrzip.c:1549-1553)
+ *   lrzgpu_compress_chunk               one pass of the chunk loop src/rzip.c:1041-1186
+ *                                       (rzip_chunk :873 + close_stream_out, src/stream.c:2253)
+ *   lrzgpu_rzip_chunk                   hash_search()        src/rzip.c:586 with the scan primitives
+ *                                       full_tag/next_tag/match_len, lrzip_private.h:573-576
+ *   lrzgpu_tag_scan                     single_full_tag()/single_next_tag()  src/rzip.c:385-416
+ *   lrzgpu_crc32                        cksum_update()/cksumthread()  src/rzip.c:564-584, 713-757
+ *   lrzgpu_sizing                       setup_overhead/setup_ram src/util.c:103-188,
+ *                                       open_stream_out sizing  src/stream.c:1169-1331
+ *   lrzgpu_block_compress               lzma_compress_buf()/zstd_compress_buf()  src/stream.c:429/167
+ *                                       (struct compress_thread {s_buf,c_type,s_len,c_len}, :67-76)
+ *   lrzgpu_lz4_gate                     lz4_compresses()     src/stream.c:2325-2380
+ *
+ * Conventions: plain pointers and sizes, caller-owned inputs, outputs allocated by the library and
+ * released with lrzgpu_free(); every function returns 0 on success or a negative LRZGPU_E* code and
+ * never calls exit() (the reference calls fatal(), src/include/util.h:34-46).  A context is bound to
+ * one CUDA device and is not thread-safe; use one context per thread / per GPU.
+ * There is no CPU fallback: without a CUDA device lrzgpu_create() fails with LRZGPU_ENODEV.
+ */
+#ifndef LRZGPU_H
+#define LRZGPU_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+enum {
+	LRZGPU_OK = 0,
+	LRZGPU_EINVAL = -1,
+	LRZGPU_ENOMEM = -2,
+	LRZGPU_ECUDA = -3,
+	LRZGPU_ENODEV = -4,
+	LRZGPU_EIO = -5,
+	LRZGPU_EINTERNAL = -6,
+	LRZGPU_EUNSUPPORTED = -7,
+};
+
+/* c_type byte of a block header, src/include/lrzip_private.h:287-295 */
+enum { LRZGPU_CTYPE_NONE = 3, LRZGPU_CTYPE_LZMA = 6, LRZGPU_CTYPE_ZSTD = 10 };
+
+/* backend selector (the reference's FLAG_NO_COMPRESS / default lzma / FLAG_ZSTD_COMPRESS) */
+enum { LRZGPU_BACKEND_NONE = 0, LRZGPU_BACKEND_LZMA = 1, LRZGPU_BACKEND_ZSTD = 4 };
+
+/* Every option that changes archive bytes (rzip_control fields, src/include/lrzip_private.h:472-581). */
+typedef struct lrzgpu_params {
+	int level;        /* -L 1..9 (compression_level), default 7 */
+	int rzip_level;   /* -R, 0 = same as level (rzip_compression_level) */
+	int backend;      /* LRZGPU_BACKEND_* */
+	int threads;      /* -p (control->threads before prepare_streamout_threads) */
+	int window;       /* -w, units of 100 MiB, 0 = unset */
+	int unlimited;    /* -U */
+	int64_t ramsize;  /* control->ramsize in bytes (-m N  => N * 100 MiB) */
+	int page_size;    /* control->page_size, 4096 */
+	int processors;   /* sysconf(_SC_NPROCESSORS_ONLN) of the machine being reproduced */
+	int threshold;    /* lz4 gate: 0 = off (-T), else percent (default 100) */
+	int nobemt;       /* --nobemt (does not change bytes; kept for symmetry) */
+} lrzgpu_params;
+
+typedef struct lrzgpu_sizing_t {
+	int threads;        /* after prepare_streamout_threads / open_stream_out */
+	uint32_t dict_size; /* lzma dictionary after possible reduction (magic byte 18) */
+	int64_t overhead;
+	int64_t bufsize;    /* stream block size (stream_bufsize) */
+	int64_t max_chunk;  /* rzip window */
+} lrzgpu_sizing_t;
+
+/* rzip statistics, src/rzip.c:1238-1246, summed over chunks, plus stage timings */
+typedef struct lrzgpu_stats {
+	int64_t matches, match_bytes, literals, literal_bytes;
+	int64_t tag_hits, tag_misses, inserts, lookups;
+	int64_t chain_evictions, sweeps, displacements;
+	int64_t hash_count, final_min_mask, final_tag_mask; /* of the last chunk */
+	int64_t chunks, blocks, blocks_stored;
+	int64_t stream0_bytes, stream1_bytes;
+	uint32_t crc32;      /* of the last chunk */
+	uint32_t pad;
+	double ms_h2d, ms_rzip, ms_emit, ms_backend, ms_d2h, ms_md5, ms_total;
+	int64_t kernel_launches;
+} lrzgpu_stats;
+
+typedef struct lrzgpu_ctx lrzgpu_ctx;
+
+int lrzgpu_create(int device, lrzgpu_ctx **ctx);
+void lrzgpu_destroy(lrzgpu_ctx *ctx);
+const char *lrzgpu_last_error(const lrzgpu_ctx *ctx);
+void lrzgpu_free(void *p);
+const char *lrzgpu_version(void);
+
+/* Host-side sizing only (no device work): block size, threads, dictionary, window. */
+int lrzgpu_sizing(const lrzgpu_params *p, int64_t st_size, lrzgpu_sizing_t *out);
+
+/* Whole file, host buffers: in[0..n) -> malloc'ed .lrz archive. */
+int lrzgpu_compress(lrzgpu_ctx *ctx, const lrzgpu_params *p, const uint8_t *in, int64_t n,
+		    uint8_t **out, int64_t *out_len, lrzgpu_stats *stats);
+/* Whole file, file -> file. */
+int lrzgpu_compress_file(lrzgpu_ctx *ctx, const lrzgpu_params *p, const char *in_path, const char *out_path,
+			 lrzgpu_stats *stats);
+/* Whole file, input already resident in device memory: d_in must be 16-byte aligned, preceded by
+ * at least 32 readable bytes and followed by at least 8192 readable bytes.  The trailing MD5 is
+ * computed by a host thread from a device->host stream of the input unless md5 is given. */
+int lrzgpu_compress_device(lrzgpu_ctx *ctx, const lrzgpu_params *p, const void *d_in, int64_t n,
+			   const uint8_t *md5_or_null, uint8_t **out, int64_t *out_len, lrzgpu_stats *stats);
+
+/* One chunk (window) -> its position-independent blob (chunk preamble, stream headers, blocks), the
+ * unit that is sharded across GPUs.  chunk_bytes/eof as in src/rzip.c:1129-1143; victim_round carries
+ * the reference's static counter (src/rzip.c:308) in and out; *chain_evictions reports whether it was
+ * consulted. */
+int lrzgpu_compress_chunk(lrzgpu_ctx *ctx, const lrzgpu_params *p, const lrzgpu_sizing_t *sz,
+			  const uint8_t *in, int64_t n, int eof, int64_t *victim_round,
+			  uint8_t **blob, int64_t *blob_len, lrzgpu_stats *stats);
+
+/* rzip of one chunk -> stream 0 / stream 1 bytes (malloc'ed). */
+int lrzgpu_rzip_chunk(lrzgpu_ctx *ctx, const uint8_t *in, int64_t n, int rzip_level, int chunk_bytes,
+		      int64_t *victim_round, uint8_t **s0, int64_t *s0_len, uint8_t **s1, int64_t *s1_len,
+		      lrzgpu_stats *stats);
+
+/* Tag scan of positions [pos_lo, pos_hi) of in[0..n): candidates with (tag & mask) == mask, in
+ * position order, into caller arrays of capacity cap; *count receives the total found. */
+int lrzgpu_tag_scan(lrzgpu_ctx *ctx, const uint8_t *in, int64_t n, int64_t pos_lo, int64_t pos_hi, int64_t mask,
+		    int64_t *out_pos, int64_t *out_tag, int64_t cap, int64_t *count);
+
+int lrzgpu_crc32(lrzgpu_ctx *ctx, const uint8_t *in, int64_t n, uint32_t *crc);
+
+/* One stream block through a backend: out (malloc'ed) holds the payload as it would be written
+ * after the block header; *c_type is LRZGPU_CTYPE_NONE when the block is left stored. */
+int lrzgpu_block_compress(lrzgpu_ctx *ctx, const lrzgpu_params *p, uint32_t dict_size, const uint8_t *in,
+			  int64_t u_len, uint8_t **out, int64_t *c_len, int *c_type);
+/* lz4 compressibility gate: *compressible = lz4_compresses() result. */
+int lrzgpu_lz4_gate(lrzgpu_ctx *ctx, const uint8_t *in, int64_t len, int threshold, int *compressible);
+
+/* ---- measurement hooks (bench.py): kernels on caller-provided device buffers and stream ------- */
+/* K1 over a device-resident chunk: d_cand needs 16 * round_up(n, 4096) bytes, d_tile_count
+ * 4 * ceil(n / 4096) bytes.  `stream` is a cudaStream_t (0 = default stream). */
+int lrzgpu_k1_launch(lrzgpu_ctx *ctx, const void *d_buf, int64_t n, int64_t mask, void *d_cand,
+		     void *d_tile_count, void *stream);
+int lrzgpu_crc32_launch(lrzgpu_ctx *ctx, const void *d_buf, int64_t n, void *d_crc, void *stream);
+int lrzgpu_sm_count(const lrzgpu_ctx *ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,33 @@
+// backend.h -- per-block backends (device side).  A backend takes the stream blocks of one chunk,
+// already resident in HBM, and produces for each a c_type, a compressed length and a device payload.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <vector>
+#include "../../include/lrzgpu.h"
+
+namespace lrz {
+
+struct BlockJob {
+	const uint8_t *d_src; // block bytes in HBM (inside stream 0 / stream 1)
+	int64_t u_len;
+	int stream;
+	// results
+	int c_type;           // LRZGPU_CTYPE_*
+	int64_t c_len;
+	const uint8_t *d_payload; // == d_src when stored
+};
+
+struct BackendCtx; // opaque per-context scratch, owned by lrzgpu_ctx
+
+BackendCtx *backend_create();
+void backend_destroy(BackendCtx *b);
+// Runs the lz4 gate (when threshold != 0) and the backend on every job with u_len >= 64
+// (src/stream.c:1633), synchronously on `stream`.  Jobs left stored keep c_type NONE / c_len u_len.
+int backend_encode_blocks(BackendCtx *b, const lrzgpu_params &p, const lrzgpu_sizing_t &sz, std::vector<BlockJob> &jobs,
+			  int num_sms, cudaStream_t stream, int64_t *launches, char *err, size_t errlen);
+// lz4_compresses() of src/stream.c:2325-2380 on a device-resident buffer.
+int backend_lz4_gate(BackendCtx *b, const uint8_t *d_src, int64_t len, int threshold, int *result, cudaStream_t stream,
+		     int64_t *launches);
+
+} // namespace lrz

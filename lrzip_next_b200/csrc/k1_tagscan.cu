@@ -1,0 +1,232 @@
+// k1_tagscan.cu -- K1: rzip rolling-tag scan + candidate compaction (sm_100a).
+//
+// Replaces, for a whole window segment at once, the per-position work of the reference's hash_search
+// loop head: next_tag / full_tag (src/rzip.c:385-416) and the tag-mask gate (src/rzip.c:658).
+//
+//   tag(p) = XOR_{i<31} hash_index[buf[p+i]]                      (src/rzip.c:405-416)
+//
+// Every position p in [1, n-31] whose tag satisfies (tag & mask) == mask becomes one 16-byte
+// candidate record {pos, tag} (layout of struct hash_entry, src/rzip.c:61-64).  Records of tile
+// T (positions [T*4096, (T+1)*4096)) are written, in position order, to the tile-strided region
+// cand[T*4096 ...] and their number to tile_count[T]; no cross-CTA dependency exists.
+//
+// HBM traffic (the algorithmic bytes of SURVEY.md 8(d)): 1 byte read per position + 16 bytes
+// written per candidate = 1 + 16 * 2^-initial_freq bytes per input byte (9 B/B at rzip level 7).
+//
+// Structure (persistent CTAs, 256 threads, one 4096-position tile per iteration):
+//   * the input tile (+32 B halo) is staged global -> shared by the TMA engine (cp.async.bulk with
+//     an mbarrier transaction count), double buffered, so the load of tile i+1 overlaps tile i;
+//   * phase A: thread t owns the 16 bytes of slot t, XOR-accumulates hash_index over them through a
+//     16-way replicated 64-bit table in shared memory (lanes l and l+16 are in different 64-bit
+//     phases, so lookups are bank-conflict free) and publishes the 16 running XORs xs[k][t];
+//   * phase B: transposed -- lane l of a warp takes position 32*j + l, so that the survivors of one
+//     ballot are consecutive positions and their 16-byte records form one contiguous run in HBM:
+//       tag = (X_s[15] ^ X_s[k-1]) ^ X_{s+1}[15] ^ X_{s+2}[k-2]     (s = slot, k = position & 15)
+//   * warp ballots + a CTA prefix place every record; stores are 16 B per lane, contiguous per warp.
+#include "kernels.h"
+
+#include <cuda_runtime.h>
+
+namespace lrz {
+
+__constant__ int64_t c_hash_index[256];
+
+static constexpr int K1_THREADS = 256;
+static constexpr int K1_WARPS = K1_THREADS / 32;
+static constexpr int K1_SLOTS = 273;                 // = 1 (mod 16): column reads are conflict free
+static constexpr int K1_IN_BYTES = kTile + 32;       // tile + halo, multiple of 16
+static constexpr int K1_SMEM_TABLE = 256 * 16 * 8;
+static constexpr int K1_SMEM_XS = 16 * K1_SLOTS * 8;
+static constexpr int K1_SMEM_IN = 2 * K1_IN_BYTES;
+static constexpr int K1_OFF_XS = K1_SMEM_TABLE;
+static constexpr int K1_OFF_IN = K1_OFF_XS + K1_SMEM_XS;
+static constexpr int K1_OFF_WSUM = K1_OFF_IN + K1_SMEM_IN;
+static constexpr int K1_OFF_BAR = K1_OFF_WSUM + 64;
+static constexpr int K1_SMEM = K1_OFF_BAR + 32;
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, unsigned count)
+{
+	asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, unsigned bytes)
+{
+	asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, unsigned parity)
+{
+	asm volatile("{\n\t.reg .pred p;\n\tWAIT_%=:\n\t"
+		     "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+		     "@p bra DONE_%=;\n\tbra WAIT_%=;\n\tDONE_%=:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+
+// TMA bulk copy global -> shared (SASS: UBLKCP), completion counted on the mbarrier.
+__device__ __forceinline__ void tma_load_1d(void *dst, const void *src, unsigned bytes, uint64_t *bar)
+{
+	asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+		     ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
+__device__ __forceinline__ void st_cand(Cand *dst, int64_t pos, int64_t tag)
+{
+	asm volatile("st.global.cs.v2.u64 [%0], {%1,%2};" ::"l"(dst), "l"(pos), "l"(tag) : "memory");
+}
+
+__global__ void __launch_bounds__(K1_THREADS, 2)
+k1_tagscan_kernel(const uint8_t *__restrict__ buf, int64_t n, int64_t pos_lo, int64_t pos_hi, int64_t mask_arg,
+		  const ScanState *__restrict__ state, Cand *__restrict__ cand, uint32_t *__restrict__ tile_count,
+		  int64_t first_tile, int64_t num_tiles)
+{
+	extern __shared__ __align__(128) uint8_t smem[];
+	uint64_t *tab = reinterpret_cast<uint64_t *>(smem);                 // tab[b * 16 + (lane & 15)]
+	uint64_t *xs = reinterpret_cast<uint64_t *>(smem + K1_OFF_XS);      // xs[k * K1_SLOTS + slot]
+	uint8_t *in = smem + K1_OFF_IN;
+	uint32_t *wsum = reinterpret_cast<uint32_t *>(smem + K1_OFF_WSUM);
+	uint64_t *bar = reinterpret_cast<uint64_t *>(smem + K1_OFF_BAR);
+
+	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+	int64_t mask = mask_arg;
+	if (state) {
+		mask = state->min_mask;
+		if (state->scan_pos + 1 >= pos_hi) { // the scan already jumped past this segment
+			for (int64_t t = blockIdx.x * (int64_t)K1_THREADS + tid; t < num_tiles; t += (int64_t)gridDim.x * K1_THREADS)
+				tile_count[t] = 0;
+			return;
+		}
+	}
+
+	for (int i = tid; i < 256 * 16; i += K1_THREADS)
+		tab[i] = (uint64_t)c_hash_index[i >> 4];
+	if (tid == 0) {
+		mbar_init(&bar[0], 1);
+		mbar_init(&bar[1], 1);
+		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+	}
+	__syncthreads();
+
+	const int64_t end = n - kMinMatch; // last examined position (src/rzip.c:622, 631-634)
+	const uint64_t *my_tab = tab + (lane & 15);
+	const int k = lane & 15, half = lane >> 4;
+	// row indices of the three partial XORs of a 31-byte window that starts at offset k of its slot
+	const int row_b = (k >= 1) ? (k - 1) : 0;
+	const int row_c = (k == 0) ? 14 : 15;
+	const int row_d = (k >= 2) ? (k - 2) : 0;
+
+	int64_t t = blockIdx.x;
+	if (t < num_tiles && tid == 0) {
+		mbar_expect_tx(&bar[0], K1_IN_BYTES);
+		tma_load_1d(in, buf + (first_tile + t) * (int64_t)kTile, K1_IN_BYTES, &bar[0]);
+	}
+	for (int it = 0; t < num_tiles; t += gridDim.x, it++) {
+		const int stage = it & 1;
+		const unsigned parity = (it >> 1) & 1;
+		const int64_t tile = first_tile + t;
+		const int64_t base = tile * (int64_t)kTile;
+		if (tid == 0 && t + gridDim.x < num_tiles) { // prefetch the next tile into the other stage
+			mbar_expect_tx(&bar[stage ^ 1], K1_IN_BYTES);
+			tma_load_1d(in + (stage ^ 1) * K1_IN_BYTES, buf + (tile + gridDim.x) * (int64_t)kTile, K1_IN_BYTES,
+				    &bar[stage ^ 1]);
+		}
+		mbar_wait(&bar[stage], parity);
+
+		// ---- phase A: per-slot running XORs
+		{
+			const uint4 v = *reinterpret_cast<const uint4 *>(in + stage * K1_IN_BYTES + tid * 16);
+			const uint32_t w[4] = { v.x, v.y, v.z, v.w };
+			uint64_t acc = 0;
+#pragma unroll
+			for (int j = 0; j < 16; j++) {
+				const uint32_t b = (w[j >> 2] >> ((j & 3) * 8)) & 0xffu;
+				acc ^= my_tab[b * 16];
+				xs[j * K1_SLOTS + tid] = acc;
+			}
+			if (tid < 2) { // halo slots 256, 257
+				const uint4 hv = *reinterpret_cast<const uint4 *>(in + stage * K1_IN_BYTES + (K1_THREADS + tid) * 16);
+				const uint32_t hw[4] = { hv.x, hv.y, hv.z, hv.w };
+				uint64_t hacc = 0;
+#pragma unroll
+				for (int j = 0; j < 16; j++) {
+					const uint32_t b = (hw[j >> 2] >> ((j & 3) * 8)) & 0xffu;
+					hacc ^= my_tab[b * 16];
+					xs[j * K1_SLOTS + K1_THREADS + tid] = hacc;
+				}
+			}
+		}
+		__syncthreads();
+
+		// ---- phase B: tags of positions base + warp*512 + 32*j + lane
+		uint64_t tags[16];
+		uint32_t ballots[16];
+		uint32_t wtotal = 0;
+		const int64_t q0 = base + warp * 512 + lane;
+#pragma unroll
+		for (int j = 0; j < 16; j++) {
+			const int s = warp * 32 + 2 * j + half;
+			uint64_t tg = xs[15 * K1_SLOTS + s] ^ xs[row_c * K1_SLOTS + s + 1];
+			if (k >= 1)
+				tg ^= xs[row_b * K1_SLOTS + s];
+			if (k >= 2)
+				tg ^= xs[row_d * K1_SLOTS + s + 2];
+			tags[j] = tg;
+			const int64_t p = q0 + 32 * j;
+			const bool ok = p >= pos_lo && p < pos_hi && p >= 1 && p <= end && (tg & (uint64_t)mask) == (uint64_t)mask;
+			ballots[j] = __ballot_sync(0xffffffffu, ok);
+			wtotal += __popc(ballots[j]);
+		}
+		if (lane == 0)
+			wsum[warp] = wtotal;
+		__syncthreads(); // also: every read of xs / in[stage] is done before they are overwritten
+		uint32_t woff = 0, total = 0;
+#pragma unroll
+		for (int w = 0; w < K1_WARPS; w++) {
+			const uint32_t sm = wsum[w];
+			woff += (w < warp) ? sm : 0;
+			total += sm;
+		}
+		Cand *dst = cand + t * (int64_t)kTile + woff;
+		const uint32_t lt = (1u << lane) - 1;
+#pragma unroll
+		for (int j = 0; j < 16; j++) {
+			const uint32_t bm = ballots[j];
+			if ((bm >> lane) & 1)
+				st_cand(dst + __popc(bm & lt), q0 + 32 * j, (int64_t)tags[j]);
+			dst += __popc(bm);
+		}
+		if (tid == 0)
+			tile_count[t] = total;
+		__syncthreads(); // wsum reuse
+	}
+}
+
+int k1_init_tables()
+{
+	int64_t hi[256];
+	make_hash_index(hi);
+	cudaError_t e = cudaMemcpyToSymbol(c_hash_index, hi, sizeof(hi));
+	if (e != cudaSuccess)
+		return -1;
+	e = cudaFuncSetAttribute(k1_tagscan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, K1_SMEM);
+	return e == cudaSuccess ? 0 : -1;
+}
+
+int k1_launch(const uint8_t *d_buf, int64_t n, int64_t pos_lo, int64_t pos_hi, int64_t mask,
+	      const ScanState *d_state, Cand *d_cand, uint32_t *d_tile_count, int num_sms, cudaStream_t stream)
+{
+	if (pos_hi <= pos_lo)
+		return 0;
+	const int64_t first_tile = pos_lo / kTile;
+	const int64_t last_tile = (pos_hi - 1) / kTile;
+	const int64_t num_tiles = last_tile - first_tile + 1;
+	int64_t grid = (int64_t)num_sms * 2;
+	if (grid > num_tiles)
+		grid = num_tiles;
+	k1_tagscan_kernel<<<(unsigned)grid, K1_THREADS, K1_SMEM, stream>>>(
+		d_buf, n, pos_lo, pos_hi, mask, d_state, d_cand, d_tile_count, first_tile, num_tiles);
+	return cudaGetLastError() == cudaSuccess ? 0 : -1;
+}
+
+} // namespace lrz

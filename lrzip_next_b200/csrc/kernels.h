@@ -1,0 +1,39 @@
+// kernels.h -- host launchers of the sm_100a kernels (one .cu file per kernel family).
+#pragma once
+#include <cuda_runtime.h>
+#include "lrz_common.h"
+
+namespace lrz {
+
+// ---- K1 tag scan (k1_tagscan.cu) ------------------------------------------------------------
+int k1_init_tables();
+// Scan positions [pos_lo, pos_hi) (pos_lo tile-aligned) of the n-byte chunk at d_buf (followed by at
+// least kInputPad readable bytes) and write the candidates with (tag & mask) == mask, tile-strided:
+// candidates of tile T (positions [T*4096, (T+1)*4096)) start at d_cand[(T - pos_lo/4096) * 4096].
+// When d_state is non-null the mask is read on the device from d_state->min_mask (so the launch
+// needs no host round trip) and the launch is skipped if the scan already moved past pos_hi.
+int k1_launch(const uint8_t *d_buf, int64_t n, int64_t pos_lo, int64_t pos_hi, int64_t mask,
+	      const ScanState *d_state, Cand *d_cand, uint32_t *d_tile_count, int num_sms, cudaStream_t stream);
+
+// ---- K2 commit (k2_commit.cu) ---------------------------------------------------------------
+int k2_launch(const uint8_t *d_buf, ScanState *d_state, HEntry *d_tab, const Cand *d_cand,
+	      const uint32_t *d_tile_count, int64_t pos_lo, int64_t pos_hi, MatchRec *d_recs, bool last_segment,
+	      cudaStream_t stream);
+
+// ---- K4 emit + CRC (k4_emit.cu) -------------------------------------------------------------
+int k4_init_tables();
+// CRC-32 (IEEE, as gcrypt GCRY_MD_CRC32 / zlib) of d_buf[0..n): *d_crc must be zeroed by the caller
+// (crc32_launch does it on `stream`); the finished value is *d_crc ^ 0xFFFFFFFF, applied by k4.
+int crc32_launch(const uint8_t *d_buf, int64_t n, uint32_t *d_crc, int num_sms, cudaStream_t stream);
+// Stream 0 (record headers, terminator, CRC) from the match records.
+int k4_headers_launch(const MatchRec *d_recs, int64_t n_rec, int chunk_bytes, const uint32_t *d_crc,
+		      uint8_t *d_s0, cudaStream_t stream);
+// Stream 1 (literal bytes) gathered from the chunk.
+int k4_literals_launch(const uint8_t *d_buf, const MatchRec *d_recs, int64_t n_rec, int64_t s1_len,
+		       uint8_t *d_s1, int num_sms, cudaStream_t stream);
+// For each stream-0 block boundary j (byte offset (j+1)*bufsize), the number of stream-1 bytes that
+// had been written when that byte was written: decides the global flush order of blocks.
+int k4_flush_order_launch(const MatchRec *d_recs, int64_t n_rec, int chunk_bytes, int64_t bufsize,
+			  int64_t n_bounds, int64_t *d_w1, cudaStream_t stream);
+
+} // namespace lrz

@@ -1,0 +1,832 @@
+// lrzgpu.cu -- the C ABI (include/lrzgpu.h): context, device arenas, the per-chunk pipeline
+//   H2D -> [K1 tag scan || K2 commit, segment-pipelined on two streams] || CRC-32 -> K4 emit ->
+//   block plan -> backend -> framing -> D2H
+// and whole-file orchestration (window loop src/rzip.c:1041-1186, magic src/lrzip.c:131-208, MD5).
+#include "../../include/lrzgpu.h"
+
+#include <cuda_runtime.h>
+#include <errno.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <chrono>
+#include <thread>
+#include <vector>
+
+#include "backend.h"
+#include "k2_commit.cuh"
+#include "kernels.h"
+#include "lrz_host.h"
+
+using namespace lrz;
+
+namespace {
+
+constexpr int64_t kFrontPad = 256;
+constexpr int64_t kSegment = 16ll << 20; // positions per K1/K2 segment (tile multiple)
+constexpr int kCtypeNone = LRZGPU_CTYPE_NONE;
+
+struct DevBuf {
+	void *p = nullptr;
+	size_t cap = 0;
+	cudaError_t ensure(size_t n)
+	{
+		if (n <= cap)
+			return cudaSuccess;
+		if (p)
+			cudaFree(p);
+		p = nullptr;
+		cap = 0;
+		const size_t want = n + (n >> 4) + 4096;
+		cudaError_t e = cudaMalloc(&p, want);
+		if (e == cudaSuccess)
+			cap = want;
+		return e;
+	}
+	void release()
+	{
+		if (p)
+			cudaFree(p);
+		p = nullptr;
+		cap = 0;
+	}
+};
+
+double now_ms()
+{
+	return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
+} // namespace
+
+struct lrzgpu_ctx {
+	int device = 0, sms = 148;
+	char err[512] = { 0 };
+	cudaStream_t sA = nullptr, sB = nullptr, sC = nullptr, sD = nullptr;
+	cudaEvent_t evK1[2] = { nullptr, nullptr }, evK2[2] = { nullptr, nullptr }, evInit = nullptr, evCrc = nullptr;
+	DevBuf in, tab, state, cand[2], tc[2], recs, s0, s1, crc, w1;
+	ScanState *h_state = nullptr; // pinned
+	uint8_t *h_pin[2] = { nullptr, nullptr }; // pinned staging for the MD5 stream of device inputs
+	size_t h_pin_cap = 0;
+	BackendCtx *backend = nullptr;
+	int64_t launches = 0;
+};
+
+namespace {
+
+int fail(lrzgpu_ctx *c, int code, const char *fmt, ...)
+{
+	if (c) {
+		va_list ap;
+		va_start(ap, fmt);
+		vsnprintf(c->err, sizeof(c->err), fmt, ap);
+		va_end(ap);
+	}
+	return code;
+}
+
+#define CU(c, call)                                                                                          \
+	do {                                                                                                 \
+		cudaError_t e_ = (call);                                                                     \
+		if (e_ != cudaSuccess)                                                                       \
+			return fail(c, e_ == cudaErrorMemoryAllocation ? LRZGPU_ENOMEM : LRZGPU_ECUDA, "%s: %s", #call, \
+				    cudaGetErrorString(e_));                                                 \
+	} while (0)
+
+struct ChunkResult {
+	int64_t s0_len = 0, s1_len = 0, n_rec = 0;
+	ScanState st;
+};
+
+// rzip of one chunk that is resident in HBM at d_chunk (16-byte aligned, readable kFrontPad before and
+// kInputPad after).  Leaves stream 0 / stream 1 in c->s0 / c->s1.
+int rzip_chunk_device(lrzgpu_ctx *c, const uint8_t *d_chunk, int64_t n, int rzip_level, int cb, int64_t victim_round,
+		      ChunkResult &res, lrzgpu_stats *stats)
+{
+	const double t0 = now_ms();
+	const RzipLevel &lv = kLevels[rzip_level];
+	const size_t tab_bytes = (size_t)lv.mb_used << 20;
+	const int64_t rec_cap = n / kMinMatch + 8;
+	const int64_t seg = kSegment < ((n + kTile - 1) / kTile) * kTile ? kSegment : ((n + kTile - 1) / kTile) * kTile;
+	CU(c, c->tab.ensure(tab_bytes));
+	CU(c, c->state.ensure(sizeof(ScanState)));
+	CU(c, c->recs.ensure((size_t)rec_cap * sizeof(MatchRec)));
+	CU(c, c->crc.ensure(16));
+	for (int b = 0; b < 2; b++) {
+		CU(c, c->cand[b].ensure((size_t)seg * sizeof(Cand)));
+		CU(c, c->tc[b].ensure((size_t)(seg / kTile + 1) * sizeof(uint32_t)));
+	}
+	ScanState *d_state = (ScanState *)c->state.p;
+	k2_init_state(c->h_state, n, rzip_level, cb, victim_round, rec_cap);
+	CU(c, cudaMemcpyAsync(d_state, c->h_state, sizeof(ScanState), cudaMemcpyHostToDevice, c->sA));
+	CU(c, cudaMemsetAsync(c->tab.p, 0, tab_bytes, c->sA)); // src/rzip.c:599-600
+	CU(c, cudaEventRecord(c->evInit, c->sA));
+	CU(c, cudaStreamWaitEvent(c->sB, c->evInit, 0));
+	CU(c, cudaStreamWaitEvent(c->sC, c->evInit, 0));
+	if (crc32_launch(d_chunk, n, (uint32_t *)c->crc.p, c->sms, c->sC))
+		return fail(c, LRZGPU_ECUDA, "crc32 launch: %s", cudaGetErrorString(cudaGetLastError()));
+	CU(c, cudaEventRecord(c->evCrc, c->sC));
+	c->launches += 1;
+
+	const int64_t nseg = (n + seg - 1) / seg;
+	for (int64_t i = 0; i < nseg; i++) {
+		const int b = (int)(i & 1);
+		const int64_t lo = i * seg, hi = (lo + seg < n) ? lo + seg : n;
+		if (i >= 2)
+			CU(c, cudaStreamWaitEvent(c->sB, c->evK2[b], 0)); // cand[b] consumed, newer mask visible
+		if (k1_launch(d_chunk, n, lo, hi, 0, d_state, (Cand *)c->cand[b].p, (uint32_t *)c->tc[b].p, c->sms, c->sB))
+			return fail(c, LRZGPU_ECUDA, "k1 launch: %s", cudaGetErrorString(cudaGetLastError()));
+		CU(c, cudaEventRecord(c->evK1[b], c->sB));
+		CU(c, cudaStreamWaitEvent(c->sA, c->evK1[b], 0));
+		if (k2_launch(d_chunk, d_state, (HEntry *)c->tab.p, (const Cand *)c->cand[b].p, (const uint32_t *)c->tc[b].p, lo,
+			      hi, (MatchRec *)c->recs.p, i == nseg - 1, c->sA))
+			return fail(c, LRZGPU_ECUDA, "k2 launch: %s", cudaGetErrorString(cudaGetLastError()));
+		CU(c, cudaEventRecord(c->evK2[b], c->sA));
+		c->launches += 2;
+	}
+	CU(c, cudaMemcpyAsync(c->h_state, d_state, sizeof(ScanState), cudaMemcpyDeviceToHost, c->sA));
+	CU(c, cudaStreamSynchronize(c->sA));
+	CU(c, cudaStreamSynchronize(c->sB));
+	res.st = *c->h_state;
+	if (res.st.status != kStatusChunkDone)
+		return fail(c, LRZGPU_EINTERNAL, "rzip commit ended with status %d at position %lld", res.st.status,
+			    (long long)res.st.scan_pos);
+	res.s0_len = res.st.s0_len;
+	res.s1_len = res.st.s1_len;
+	res.n_rec = res.st.n_rec;
+	const double t1 = now_ms();
+
+	CU(c, c->s0.ensure((size_t)res.s0_len + 64));
+	CU(c, c->s1.ensure((size_t)res.s1_len + 64));
+	CU(c, cudaStreamWaitEvent(c->sA, c->evCrc, 0));
+	if (k4_headers_launch((const MatchRec *)c->recs.p, res.n_rec, cb, (const uint32_t *)c->crc.p, (uint8_t *)c->s0.p, c->sA) ||
+	    k4_literals_launch(d_chunk, (const MatchRec *)c->recs.p, res.n_rec, res.s1_len, (uint8_t *)c->s1.p, c->sms, c->sA))
+		return fail(c, LRZGPU_ECUDA, "k4 launch: %s", cudaGetErrorString(cudaGetLastError()));
+	c->launches += 2;
+	uint32_t crc_acc = 0;
+	CU(c, cudaMemcpyAsync(&crc_acc, c->crc.p, 4, cudaMemcpyDeviceToHost, c->sA));
+	CU(c, cudaStreamSynchronize(c->sA));
+	const double t2 = now_ms();
+	if (stats) {
+		stats->matches += res.st.st_matches;
+		stats->match_bytes += res.st.st_match_bytes;
+		stats->literals += res.st.st_literals;
+		stats->literal_bytes += res.st.st_literal_bytes;
+		stats->tag_hits += res.st.st_tag_hits;
+		stats->tag_misses += res.st.st_tag_misses;
+		stats->inserts += res.st.st_inserts;
+		stats->lookups += res.st.st_lookups;
+		stats->chain_evictions += res.st.st_evictions;
+		stats->sweeps += res.st.st_sweeps;
+		stats->displacements += res.st.st_displacements;
+		stats->hash_count = res.st.hash_count;
+		stats->final_min_mask = res.st.min_mask;
+		stats->final_tag_mask = res.st.tag_mask;
+		stats->chunks += 1;
+		stats->stream0_bytes += res.s0_len;
+		stats->stream1_bytes += res.s1_len;
+		stats->crc32 = crc_acc ^ 0xffffffffu;
+		stats->ms_rzip += t1 - t0;
+		stats->ms_emit += t2 - t1;
+	}
+	return LRZGPU_OK;
+}
+
+struct OutBuf {
+	uint8_t *p = nullptr;
+	int64_t len = 0, cap = 0;
+	int reserve(int64_t extra)
+	{
+		if (len + extra <= cap)
+			return 0;
+		int64_t nc = cap ? cap : 65536;
+		while (nc < len + extra)
+			nc += nc / 2 + 4096;
+		uint8_t *np = (uint8_t *)realloc(p, (size_t)nc);
+		if (!np)
+			return -1;
+		p = np;
+		cap = nc;
+		return 0;
+	}
+};
+
+// One chunk: rzip on the device, then blocks -> backend -> framed blob appended to `out`
+// (src/stream.c:1722-1821: chunk preamble, two initial stream headers, blocks with next_head patching).
+int compress_chunk_device(lrzgpu_ctx *c, const lrzgpu_params &p, const lrzgpu_sizing_t &sz, const uint8_t *d_chunk,
+			  int64_t n, int eof, int64_t *victim_round, OutBuf &out, lrzgpu_stats *stats)
+{
+	const int rzl = p.rzip_level ? p.rzip_level : p.level;
+	const int cb = chunk_bytes_for(n);
+	ChunkResult res;
+	int rc = rzip_chunk_device(c, d_chunk, n, rzl, cb, *victim_round, res, stats);
+	if (rc)
+		return rc;
+	*victim_round = res.st.victim_round;
+
+	const double t0 = now_ms();
+	const int64_t nb0 = res.s0_len / sz.bufsize;
+	std::vector<int64_t> w1((size_t)nb0 + 1, 0);
+	if (nb0 > 0) {
+		CU(c, c->w1.ensure((size_t)nb0 * 8));
+		if (k4_flush_order_launch((const MatchRec *)c->recs.p, res.n_rec, cb, sz.bufsize, nb0, (int64_t *)c->w1.p, c->sA))
+			return fail(c, LRZGPU_ECUDA, "flush order launch failed");
+		c->launches += 1;
+		CU(c, cudaMemcpyAsync(w1.data(), c->w1.p, (size_t)nb0 * 8, cudaMemcpyDeviceToHost, c->sA));
+		CU(c, cudaStreamSynchronize(c->sA));
+	}
+	std::vector<BlockPlan> plan;
+	plan_blocks(res.s0_len, res.s1_len, sz.bufsize, w1.data(), plan);
+
+	std::vector<BlockJob> jobs(plan.size());
+	for (size_t i = 0; i < plan.size(); i++) {
+		jobs[i].d_src = (const uint8_t *)(plan[i].stream ? c->s1.p : c->s0.p) + plan[i].off;
+		jobs[i].u_len = plan[i].u_len;
+		jobs[i].stream = plan[i].stream;
+		jobs[i].c_type = kCtypeNone;
+		jobs[i].c_len = plan[i].u_len;
+		jobs[i].d_payload = jobs[i].d_src;
+	}
+	if (p.backend != LRZGPU_BACKEND_NONE) {
+		rc = backend_encode_blocks(c->backend, p, sz, jobs, c->sms, c->sA, &c->launches, c->err, sizeof(c->err));
+		if (rc)
+			return rc;
+	}
+	const double t1 = now_ms();
+
+	const int64_t hdr = 1 + 3 * cb;
+	int64_t total = 2 + cb + 2 * hdr;
+	for (auto &j : jobs)
+		total += hdr + j.c_len;
+	if (out.reserve(total))
+		return fail(c, LRZGPU_ENOMEM, "out of host memory for %lld byte blob", (long long)total);
+	uint8_t *w = out.p + out.len;
+	const int64_t size_field = n < p.page_size ? p.page_size : n; // src/stream.c:1150-1152
+	*w++ = (uint8_t)cb;
+	*w++ = (uint8_t)eof;
+	put_le(w, size_field, cb);
+	w += cb;
+	uint8_t *initial = w;
+	int64_t cur_pos = 0, last_head[2];
+	for (int s = 0; s < 2; s++) {
+		last_head[s] = cur_pos + 1 + 2 * cb;
+		*w++ = kCtypeNone;
+		memset(w, 0, (size_t)(3 * cb));
+		w += 3 * cb;
+		cur_pos += hdr;
+	}
+	for (auto &j : jobs) {
+		put_le(initial + last_head[j.stream], cur_pos, cb); // patch the previous header's next_head
+		last_head[j.stream] = cur_pos + 1 + 2 * cb;
+		*w++ = (uint8_t)j.c_type;
+		put_le(w, j.c_len, cb);
+		put_le(w + cb, j.u_len, cb);
+		put_le(w + 2 * cb, 0, cb);
+		w += 3 * cb;
+		if (j.c_len)
+			CU(c, cudaMemcpyAsync(w, j.d_payload, (size_t)j.c_len, cudaMemcpyDeviceToHost, c->sA));
+		w += j.c_len;
+		cur_pos += hdr + j.c_len;
+		if (stats) {
+			stats->blocks++;
+			if (j.c_type == kCtypeNone)
+				stats->blocks_stored++;
+		}
+	}
+	CU(c, cudaStreamSynchronize(c->sA));
+	out.len += total;
+	const double t2 = now_ms();
+	if (stats) {
+		stats->ms_backend += t1 - t0;
+		stats->ms_d2h += t2 - t1;
+	}
+	return LRZGPU_OK;
+}
+
+// Upload a host buffer behind a zeroed front pad and in front of a zeroed tail pad.
+int upload(lrzgpu_ctx *c, const uint8_t *in, int64_t n, uint8_t **d_data)
+{
+	CU(c, c->in.ensure((size_t)(kFrontPad + n + kInputPad)));
+	uint8_t *base = (uint8_t *)c->in.p;
+	CU(c, cudaMemsetAsync(base, 0, kFrontPad, c->sA));
+	CU(c, cudaMemsetAsync(base + kFrontPad + n, 0, kInputPad, c->sA));
+	if (n)
+		CU(c, cudaMemcpyAsync(base + kFrontPad, in, (size_t)n, cudaMemcpyHostToDevice, c->sA));
+	*d_data = base + kFrontPad;
+	return LRZGPU_OK;
+}
+
+int check_params(lrzgpu_ctx *c, const lrzgpu_params *p, int64_t n)
+{
+	if (!c || !p)
+		return LRZGPU_EINVAL;
+	if (n <= 0)
+		return fail(c, LRZGPU_EINVAL, "empty input is not supported");
+	return LRZGPU_OK;
+}
+
+// Whole file whose bytes are at d_in in HBM; md5 either given or produced by md5_thread.
+int compress_resident(lrzgpu_ctx *c, const lrzgpu_params &p, const uint8_t *d_in, int64_t n, OutBuf &out,
+		      lrzgpu_sizing_t &sz, lrzgpu_stats *stats)
+{
+	int rc = compute_sizing(p, n, sz);
+	if (rc)
+		return fail(c, rc, "unsupported parameters");
+	if (out.reserve(21))
+		return fail(c, LRZGPU_ENOMEM, "out of host memory");
+	memset(out.p, 0, 21);
+	out.len = 21;
+	int64_t left = n, victim_round = 0;
+	while (left > 0) { // src/rzip.c:1041
+		const int64_t offset = n - left;
+		const int64_t chunk = sz.max_chunk < left ? sz.max_chunk : left;
+		rc = compress_chunk_device(c, p, sz, d_in + offset, chunk, chunk == left, &victim_round, out, stats);
+		if (rc)
+			return rc;
+		left -= chunk;
+	}
+	return LRZGPU_OK;
+}
+
+} // namespace
+
+extern "C" {
+
+const char *lrzgpu_version(void) { return "lrzgpu 0.1 (lrzip-next 0.14 archive format, sm_100a)"; }
+
+int lrzgpu_create(int device, lrzgpu_ctx **out)
+{
+	if (!out)
+		return LRZGPU_EINVAL;
+	*out = nullptr;
+	int count = 0;
+	if (cudaGetDeviceCount(&count) != cudaSuccess || count <= 0 || device < 0 || device >= count)
+		return LRZGPU_ENODEV; // no CPU fallback
+	if (cudaSetDevice(device) != cudaSuccess)
+		return LRZGPU_ECUDA;
+	lrzgpu_ctx *c = new (std::nothrow) lrzgpu_ctx();
+	if (!c)
+		return LRZGPU_ENOMEM;
+	c->device = device;
+	cudaDeviceProp prop;
+	if (cudaGetDeviceProperties(&prop, device) == cudaSuccess)
+		c->sms = prop.multiProcessorCount;
+	bool ok = cudaStreamCreateWithFlags(&c->sA, cudaStreamNonBlocking) == cudaSuccess &&
+		  cudaStreamCreateWithFlags(&c->sB, cudaStreamNonBlocking) == cudaSuccess &&
+		  cudaStreamCreateWithFlags(&c->sC, cudaStreamNonBlocking) == cudaSuccess &&
+		  cudaStreamCreateWithFlags(&c->sD, cudaStreamNonBlocking) == cudaSuccess;
+	for (int i = 0; i < 2 && ok; i++)
+		ok = cudaEventCreateWithFlags(&c->evK1[i], cudaEventDisableTiming) == cudaSuccess &&
+		     cudaEventCreateWithFlags(&c->evK2[i], cudaEventDisableTiming) == cudaSuccess;
+	ok = ok && cudaEventCreateWithFlags(&c->evInit, cudaEventDisableTiming) == cudaSuccess &&
+	     cudaEventCreateWithFlags(&c->evCrc, cudaEventDisableTiming) == cudaSuccess;
+	ok = ok && cudaHostAlloc((void **)&c->h_state, sizeof(ScanState), cudaHostAllocDefault) == cudaSuccess;
+	ok = ok && k1_init_tables() == 0 && k4_init_tables() == 0;
+	if (ok) {
+		c->backend = backend_create();
+		ok = c->backend != nullptr;
+	}
+	if (!ok) {
+		lrzgpu_destroy(c);
+		return LRZGPU_ECUDA;
+	}
+	*out = c;
+	return LRZGPU_OK;
+}
+
+void lrzgpu_destroy(lrzgpu_ctx *c)
+{
+	if (!c)
+		return;
+	cudaSetDevice(c->device);
+	cudaDeviceSynchronize();
+	if (c->backend)
+		backend_destroy(c->backend);
+	DevBuf *bufs[] = { &c->in, &c->tab, &c->state, &c->cand[0], &c->cand[1], &c->tc[0], &c->tc[1], &c->recs, &c->s0, &c->s1,
+			   &c->crc, &c->w1 };
+	for (DevBuf *b : bufs)
+		b->release();
+	if (c->h_state)
+		cudaFreeHost(c->h_state);
+	for (int i = 0; i < 2; i++) {
+		if (c->h_pin[i])
+			cudaFreeHost(c->h_pin[i]);
+		if (c->evK1[i])
+			cudaEventDestroy(c->evK1[i]);
+		if (c->evK2[i])
+			cudaEventDestroy(c->evK2[i]);
+	}
+	if (c->evInit)
+		cudaEventDestroy(c->evInit);
+	if (c->evCrc)
+		cudaEventDestroy(c->evCrc);
+	cudaStream_t ss[] = { c->sA, c->sB, c->sC, c->sD };
+	for (cudaStream_t s : ss)
+		if (s)
+			cudaStreamDestroy(s);
+	delete c;
+}
+
+const char *lrzgpu_last_error(const lrzgpu_ctx *c) { return c ? c->err : "no context"; }
+void lrzgpu_free(void *p) { free(p); }
+int lrzgpu_sm_count(const lrzgpu_ctx *c) { return c ? c->sms : 0; }
+
+int lrzgpu_sizing(const lrzgpu_params *p, int64_t st_size, lrzgpu_sizing_t *out)
+{
+	if (!p || !out)
+		return LRZGPU_EINVAL;
+	return compute_sizing(*p, st_size, *out);
+}
+
+int lrzgpu_compress(lrzgpu_ctx *c, const lrzgpu_params *p, const uint8_t *in, int64_t n, uint8_t **out,
+		    int64_t *out_len, lrzgpu_stats *stats)
+{
+	int rc = check_params(c, p, n);
+	if (rc)
+		return rc;
+	if (!in || !out || !out_len)
+		return LRZGPU_EINVAL;
+	cudaSetDevice(c->device);
+	if (stats)
+		memset(stats, 0, sizeof(*stats));
+	const int64_t launches0 = c->launches;
+	const double t0 = now_ms();
+	uint8_t md5[16];
+	double md5_ms = 0;
+	std::thread hasher([&] { // whole-file MD5 in file order, overlapped with the GPU (src/rzip.c:1195-1218)
+		const double a = now_ms();
+		Md5 m;
+		for (int64_t o = 0; o < n; o += (64 << 20))
+			m.update(in + o, (size_t)((n - o < (64 << 20)) ? n - o : (64 << 20)));
+		m.final(md5);
+		md5_ms = now_ms() - a;
+	});
+	uint8_t *d_in = nullptr;
+	OutBuf ob;
+	lrzgpu_sizing_t sz;
+	rc = upload(c, in, n, &d_in);
+	if (!rc) {
+		cudaStreamSynchronize(c->sA);
+		if (stats)
+			stats->ms_h2d = now_ms() - t0;
+		rc = compress_resident(c, *p, d_in, n, ob, sz, stats);
+	}
+	hasher.join();
+	if (!rc && ob.reserve(16))
+		rc = fail(c, LRZGPU_ENOMEM, "out of host memory");
+	if (rc) {
+		free(ob.p);
+		return rc;
+	}
+	memcpy(ob.p + ob.len, md5, 16);
+	ob.len += 16;
+	make_magic(ob.p, *p, sz, n);
+	*out = ob.p;
+	*out_len = ob.len;
+	if (stats) {
+		stats->ms_md5 = md5_ms;
+		stats->ms_total = now_ms() - t0;
+		stats->kernel_launches = c->launches - launches0;
+	}
+	return LRZGPU_OK;
+}
+
+int lrzgpu_compress_device(lrzgpu_ctx *c, const lrzgpu_params *p, const void *d_in_v, int64_t n,
+			   const uint8_t *md5_or_null, uint8_t **out, int64_t *out_len, lrzgpu_stats *stats)
+{
+	int rc = check_params(c, p, n);
+	if (rc)
+		return rc;
+	if (!d_in_v || !out || !out_len || ((uintptr_t)d_in_v & 15))
+		return LRZGPU_EINVAL;
+	cudaSetDevice(c->device);
+	if (stats)
+		memset(stats, 0, sizeof(*stats));
+	const int64_t launches0 = c->launches;
+	const double t0 = now_ms();
+	const uint8_t *d_in = (const uint8_t *)d_in_v;
+	uint8_t md5[16];
+	double md5_ms = 0;
+	int md5_rc = 0;
+	std::thread hasher;
+	if (md5_or_null)
+		memcpy(md5, md5_or_null, 16);
+	else {
+		const size_t slice = 32u << 20;
+		if (c->h_pin_cap < slice) {
+			for (int i = 0; i < 2; i++) {
+				if (c->h_pin[i])
+					cudaFreeHost(c->h_pin[i]);
+				if (cudaHostAlloc((void **)&c->h_pin[i], slice, cudaHostAllocDefault) != cudaSuccess)
+					return fail(c, LRZGPU_ENOMEM, "pinned staging allocation failed");
+			}
+			c->h_pin_cap = slice;
+		}
+		hasher = std::thread([&, slice] { // stream the input back to the host for the MD5, double buffered
+			const double a = now_ms();
+			cudaSetDevice(c->device);
+			Md5 m;
+			cudaEvent_t ev[2];
+			cudaEventCreateWithFlags(&ev[0], cudaEventDisableTiming);
+			cudaEventCreateWithFlags(&ev[1], cudaEventDisableTiming);
+			const int64_t nsl = (n + (int64_t)slice - 1) / (int64_t)slice;
+			auto issue = [&](int64_t i) {
+				const int64_t o = i * (int64_t)slice;
+				const size_t len = (size_t)((n - o < (int64_t)slice) ? n - o : (int64_t)slice);
+				if (cudaMemcpyAsync(c->h_pin[i & 1], d_in + o, len, cudaMemcpyDeviceToHost, c->sD) != cudaSuccess)
+					md5_rc = -1;
+				cudaEventRecord(ev[i & 1], c->sD);
+			};
+			issue(0);
+			for (int64_t i = 0; i < nsl; i++) {
+				if (i + 1 < nsl)
+					issue(i + 1);
+				if (cudaEventSynchronize(ev[i & 1]) != cudaSuccess)
+					md5_rc = -1;
+				const int64_t o = i * (int64_t)slice;
+				m.update(c->h_pin[i & 1], (size_t)((n - o < (int64_t)slice) ? n - o : (int64_t)slice));
+			}
+			m.final(md5);
+			cudaEventDestroy(ev[0]);
+			cudaEventDestroy(ev[1]);
+			md5_ms = now_ms() - a;
+		});
+	}
+	OutBuf ob;
+	lrzgpu_sizing_t sz;
+	rc = compress_resident(c, *p, d_in, n, ob, sz, stats);
+	if (hasher.joinable())
+		hasher.join();
+	if (!rc && md5_rc)
+		rc = fail(c, LRZGPU_ECUDA, "device->host MD5 stream failed");
+	if (!rc && ob.reserve(16))
+		rc = fail(c, LRZGPU_ENOMEM, "out of host memory");
+	if (rc) {
+		free(ob.p);
+		return rc;
+	}
+	memcpy(ob.p + ob.len, md5, 16);
+	ob.len += 16;
+	make_magic(ob.p, *p, sz, n);
+	*out = ob.p;
+	*out_len = ob.len;
+	if (stats) {
+		stats->ms_md5 = md5_ms;
+		stats->ms_total = now_ms() - t0;
+		stats->kernel_launches = c->launches - launches0;
+	}
+	return LRZGPU_OK;
+}
+
+int lrzgpu_compress_file(lrzgpu_ctx *c, const lrzgpu_params *p, const char *in_path, const char *out_path,
+			 lrzgpu_stats *stats)
+{
+	if (!c || !p || !in_path || !out_path)
+		return LRZGPU_EINVAL;
+	FILE *f = fopen(in_path, "rb");
+	if (!f)
+		return fail(c, LRZGPU_EIO, "cannot open %s: %s", in_path, strerror(errno));
+	fseeko(f, 0, SEEK_END);
+	const int64_t n = (int64_t)ftello(f);
+	fseeko(f, 0, SEEK_SET);
+	uint8_t *buf = nullptr;
+	if (n > 0 && cudaHostAlloc((void **)&buf, (size_t)n, cudaHostAllocDefault) != cudaSuccess) {
+		fclose(f);
+		return fail(c, LRZGPU_ENOMEM, "cannot allocate %lld bytes of pinned memory", (long long)n);
+	}
+	const bool read_ok = n > 0 && fread(buf, 1, (size_t)n, f) == (size_t)n;
+	fclose(f);
+	if (!read_ok) {
+		if (buf)
+			cudaFreeHost(buf);
+		return fail(c, n > 0 ? LRZGPU_EIO : LRZGPU_EINVAL, "cannot read %s", in_path);
+	}
+	uint8_t *out = nullptr;
+	int64_t out_len = 0;
+	int rc = lrzgpu_compress(c, p, buf, n, &out, &out_len, stats);
+	cudaFreeHost(buf);
+	if (rc)
+		return rc;
+	FILE *g = fopen(out_path, "wb");
+	if (!g || fwrite(out, 1, (size_t)out_len, g) != (size_t)out_len) {
+		if (g)
+			fclose(g);
+		free(out);
+		return fail(c, LRZGPU_EIO, "cannot write %s: %s", out_path, strerror(errno));
+	}
+	fclose(g);
+	free(out);
+	return LRZGPU_OK;
+}
+
+int lrzgpu_compress_chunk(lrzgpu_ctx *c, const lrzgpu_params *p, const lrzgpu_sizing_t *sz, const uint8_t *in,
+			  int64_t n, int eof, int64_t *victim_round, uint8_t **blob, int64_t *blob_len,
+			  lrzgpu_stats *stats)
+{
+	int rc = check_params(c, p, n);
+	if (rc)
+		return rc;
+	if (!sz || !in || !victim_round || !blob || !blob_len)
+		return LRZGPU_EINVAL;
+	cudaSetDevice(c->device);
+	if (stats)
+		memset(stats, 0, sizeof(*stats));
+	const int64_t launches0 = c->launches;
+	const double t0 = now_ms();
+	uint8_t *d_in = nullptr;
+	rc = upload(c, in, n, &d_in);
+	if (rc)
+		return rc;
+	OutBuf ob;
+	rc = compress_chunk_device(c, *p, *sz, d_in, n, eof, victim_round, ob, stats);
+	if (rc) {
+		free(ob.p);
+		return rc;
+	}
+	*blob = ob.p;
+	*blob_len = ob.len;
+	if (stats) {
+		stats->ms_total = now_ms() - t0;
+		stats->kernel_launches = c->launches - launches0;
+	}
+	return LRZGPU_OK;
+}
+
+int lrzgpu_rzip_chunk(lrzgpu_ctx *c, const uint8_t *in, int64_t n, int rzip_level, int chunk_bytes,
+		      int64_t *victim_round, uint8_t **s0, int64_t *s0_len, uint8_t **s1, int64_t *s1_len,
+		      lrzgpu_stats *stats)
+{
+	if (!c || !in || n <= 0 || rzip_level < 0 || rzip_level > 9 || chunk_bytes < 1 || chunk_bytes > 8 || !s0 || !s0_len ||
+	    !s1 || !s1_len)
+		return LRZGPU_EINVAL;
+	cudaSetDevice(c->device);
+	if (stats)
+		memset(stats, 0, sizeof(*stats));
+	const int64_t launches0 = c->launches;
+	uint8_t *d_in = nullptr;
+	int rc = upload(c, in, n, &d_in);
+	if (rc)
+		return rc;
+	ChunkResult res;
+	rc = rzip_chunk_device(c, d_in, n, rzip_level, chunk_bytes, victim_round ? *victim_round : 0, res, stats);
+	if (rc)
+		return rc;
+	if (victim_round)
+		*victim_round = res.st.victim_round;
+	uint8_t *h0 = (uint8_t *)malloc((size_t)res.s0_len + 1), *h1 = (uint8_t *)malloc((size_t)res.s1_len + 1);
+	if (!h0 || !h1) {
+		free(h0);
+		free(h1);
+		return fail(c, LRZGPU_ENOMEM, "out of host memory");
+	}
+	CU(c, cudaMemcpy(h0, c->s0.p, (size_t)res.s0_len, cudaMemcpyDeviceToHost));
+	if (res.s1_len)
+		CU(c, cudaMemcpy(h1, c->s1.p, (size_t)res.s1_len, cudaMemcpyDeviceToHost));
+	*s0 = h0;
+	*s0_len = res.s0_len;
+	*s1 = h1;
+	*s1_len = res.s1_len;
+	if (stats)
+		stats->kernel_launches = c->launches - launches0;
+	return LRZGPU_OK;
+}
+
+int lrzgpu_tag_scan(lrzgpu_ctx *c, const uint8_t *in, int64_t n, int64_t pos_lo, int64_t pos_hi, int64_t mask,
+		    int64_t *out_pos, int64_t *out_tag, int64_t cap, int64_t *count)
+{
+	if (!c || !in || n <= 0 || pos_lo < 0 || pos_hi > n || !count)
+		return LRZGPU_EINVAL;
+	cudaSetDevice(c->device);
+	uint8_t *d_in = nullptr;
+	int rc = upload(c, in, n, &d_in);
+	if (rc)
+		return rc;
+	const int64_t seg = 1 << 20;
+	CU(c, c->cand[0].ensure((size_t)seg * sizeof(Cand)));
+	CU(c, c->tc[0].ensure((size_t)(seg / kTile + 1) * 4));
+	std::vector<Cand> hc((size_t)seg);
+	std::vector<uint32_t> ht((size_t)(seg / kTile + 1));
+	int64_t total = 0;
+	for (int64_t lo = pos_lo - pos_lo % kTile; lo < pos_hi; lo += seg) {
+		const int64_t a = lo < pos_lo ? pos_lo : lo, b = lo + seg < pos_hi ? lo + seg : pos_hi;
+		// pos_lo of a launch must be tile aligned for the tile-strided layout: scan from `lo`, filter to [a,b)
+		if (k1_launch(d_in, n, lo, b, mask, nullptr, (Cand *)c->cand[0].p, (uint32_t *)c->tc[0].p, c->sms, c->sA))
+			return fail(c, LRZGPU_ECUDA, "k1 launch failed");
+		c->launches++;
+		const int64_t ntiles = (b - 1) / kTile - lo / kTile + 1;
+		CU(c, cudaMemcpyAsync(ht.data(), c->tc[0].p, (size_t)ntiles * 4, cudaMemcpyDeviceToHost, c->sA));
+		CU(c, cudaMemcpyAsync(hc.data(), c->cand[0].p, (size_t)ntiles * kTile * sizeof(Cand), cudaMemcpyDeviceToHost, c->sA));
+		CU(c, cudaStreamSynchronize(c->sA));
+		for (int64_t t = 0; t < ntiles; t++)
+			for (uint32_t i = 0; i < ht[(size_t)t]; i++) {
+				const Cand &cd = hc[(size_t)(t * kTile + i)];
+				if (cd.pos < a || cd.pos >= b)
+					continue;
+				if (total < cap && out_pos && out_tag) {
+					out_pos[total] = cd.pos;
+					out_tag[total] = cd.tag;
+				}
+				total++;
+			}
+	}
+	*count = total;
+	return LRZGPU_OK;
+}
+
+int lrzgpu_crc32(lrzgpu_ctx *c, const uint8_t *in, int64_t n, uint32_t *crc)
+{
+	if (!c || !in || n <= 0 || !crc)
+		return LRZGPU_EINVAL;
+	cudaSetDevice(c->device);
+	uint8_t *d_in = nullptr;
+	int rc = upload(c, in, n, &d_in);
+	if (rc)
+		return rc;
+	CU(c, c->crc.ensure(16));
+	if (crc32_launch(d_in, n, (uint32_t *)c->crc.p, c->sms, c->sA))
+		return fail(c, LRZGPU_ECUDA, "crc32 launch failed");
+	c->launches++;
+	uint32_t acc = 0;
+	CU(c, cudaMemcpyAsync(&acc, c->crc.p, 4, cudaMemcpyDeviceToHost, c->sA));
+	CU(c, cudaStreamSynchronize(c->sA));
+	*crc = acc ^ 0xffffffffu;
+	return LRZGPU_OK;
+}
+
+int lrzgpu_block_compress(lrzgpu_ctx *c, const lrzgpu_params *p, uint32_t dict_size, const uint8_t *in, int64_t u_len,
+			  uint8_t **out, int64_t *c_len, int *c_type)
+{
+	if (!c || !p || !in || u_len <= 0 || !out || !c_len || !c_type)
+		return LRZGPU_EINVAL;
+	cudaSetDevice(c->device);
+	uint8_t *d_in = nullptr;
+	int rc = upload(c, in, u_len, &d_in);
+	if (rc)
+		return rc;
+	lrzgpu_sizing_t sz;
+	memset(&sz, 0, sizeof(sz));
+	sz.dict_size = dict_size;
+	sz.bufsize = u_len;
+	sz.threads = p->threads;
+	std::vector<BlockJob> jobs(1);
+	jobs[0].d_src = d_in;
+	jobs[0].u_len = u_len;
+	jobs[0].stream = 1;
+	jobs[0].c_type = kCtypeNone;
+	jobs[0].c_len = u_len;
+	jobs[0].d_payload = d_in;
+	if (p->backend != LRZGPU_BACKEND_NONE && u_len >= 64) {
+		rc = backend_encode_blocks(c->backend, *p, sz, jobs, c->sms, c->sA, &c->launches, c->err, sizeof(c->err));
+		if (rc)
+			return rc;
+	}
+	uint8_t *h = (uint8_t *)malloc((size_t)jobs[0].c_len + 1);
+	if (!h)
+		return fail(c, LRZGPU_ENOMEM, "out of host memory");
+	CU(c, cudaMemcpy(h, jobs[0].d_payload, (size_t)jobs[0].c_len, cudaMemcpyDeviceToHost));
+	*out = h;
+	*c_len = jobs[0].c_len;
+	*c_type = jobs[0].c_type;
+	return LRZGPU_OK;
+}
+
+int lrzgpu_lz4_gate(lrzgpu_ctx *c, const uint8_t *in, int64_t len, int threshold, int *compressible)
+{
+	if (!c || !in || len <= 0 || !compressible)
+		return LRZGPU_EINVAL;
+	cudaSetDevice(c->device);
+	uint8_t *d_in = nullptr;
+	int rc = upload(c, in, len, &d_in);
+	if (rc)
+		return rc;
+	rc = backend_lz4_gate(c->backend, d_in, len, threshold, compressible, c->sA, &c->launches);
+	if (rc)
+		return fail(c, rc, "lz4 gate failed");
+	return LRZGPU_OK;
+}
+
+int lrzgpu_k1_launch(lrzgpu_ctx *c, const void *d_buf, int64_t n, int64_t mask, void *d_cand, void *d_tile_count,
+		     void *stream)
+{
+	if (!c || !d_buf || n <= 0 || !d_cand || !d_tile_count)
+		return LRZGPU_EINVAL;
+	if (k1_launch((const uint8_t *)d_buf, n, 0, n, mask, nullptr, (Cand *)d_cand, (uint32_t *)d_tile_count, c->sms,
+		      (cudaStream_t)stream))
+		return fail(c, LRZGPU_ECUDA, "k1 launch: %s", cudaGetErrorString(cudaGetLastError()));
+	c->launches++;
+	return LRZGPU_OK;
+}
+
+int lrzgpu_crc32_launch(lrzgpu_ctx *c, const void *d_buf, int64_t n, void *d_crc, void *stream)
+{
+	if (!c || !d_buf || n <= 0 || !d_crc)
+		return LRZGPU_EINVAL;
+	if (crc32_launch((const uint8_t *)d_buf, n, (uint32_t *)d_crc, c->sms, (cudaStream_t)stream))
+		return fail(c, LRZGPU_ECUDA, "crc32 launch failed");
+	c->launches++;
+	return LRZGPU_OK;
+}
+
+} // extern "C"

@@ -343,6 +343,10 @@ int rzo_compress(const rzo_params *p, const uint8_t *in, int64_t n, rzo_block_fn
 			sum->tag_hits += st.tag_hits; sum->tag_misses += st.tag_misses;
 			sum->inserts += st.inserts; sum->lookups += st.lookups;
 			sum->chain_evictions += st.chain_evictions; sum->sweeps += st.sweeps;
+			sum->displacements += st.displacements; sum->insert_probes += st.insert_probes;
+			sum->lookup_probes += st.lookup_probes; sum->probes_ge32 += st.probes_ge32;
+			if (st.max_depth > sum->max_depth) sum->max_depth = st.max_depth;
+			if (st.max_probe > sum->max_probe) sum->max_probe = st.max_probe;
 		}
 		if (plan_blocks(s0, s0_len, s1_len, cb, sz.bufsize, &blocks, &nb))
 			return -3;

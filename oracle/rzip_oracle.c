@@ -113,7 +113,9 @@ static inline int lesser_bitness(int64_t a, int64_t b)
 }
 
 /* src/rzip.c:304-353 insert_hash */
-static void insert_hash(rz *z, int64_t t, int64_t offset)
+static void insert_hash_d(rz *z, int64_t t, int64_t offset, int depth);
+static void insert_hash(rz *z, int64_t t, int64_t offset) { insert_hash_d(z, t, offset, 0); }
+static void insert_hash_d(rz *z, int64_t t, int64_t offset, int depth)
 {
 	const int64_t mask = ((int64_t)1 << z->bits) - 1;
 	const int64_t better = (z->min_mask << 1) | 1; /* :284-291 minimum_bitness */
@@ -126,7 +128,10 @@ static void insert_hash(rz *z, int64_t t, int64_t offset)
 			break;
 		}
 		if (lesser_bitness(he->t, t)) { /* re-home the weaker occupant, take its slot (:324-328) */
-			insert_hash(z, he->t, he->offset);
+			z->st.displacements++;
+			if (depth + 1 > z->st.max_depth)
+				z->st.max_depth = depth + 1;
+			insert_hash_d(z, he->t, he->offset, depth + 1);
 			break;
 		}
 		if (he->t == t) { /* equal-tag chain cap with round-robin victim (:332-343) */
@@ -144,6 +149,7 @@ static void insert_hash(rz *z, int64_t t, int64_t offset)
 		}
 		h = (h + 1) & mask;
 		he = &z->tab[h];
+		z->st.insert_probes++;
 	}
 	he->t = t;
 	he->offset = offset;
@@ -202,7 +208,7 @@ static int64_t match_len(const rz *z, int64_t p0, int64_t op, int64_t end, int64
 static int64_t find_best_match(rz *z, int64_t t, int64_t p, int64_t end, int64_t *offset, int64_t *reverse)
 {
 	const int64_t mask = ((int64_t)1 << z->bits) - 1;
-	int64_t h = t & mask, length = 0, rev = 0;
+	int64_t h = t & mask, length = 0, rev = 0, nprobe = 0;
 	const hentry *he = &z->tab[h];
 
 	*reverse = 0;
@@ -221,7 +227,13 @@ static int64_t find_best_match(rz *z, int64_t t, int64_t p, int64_t end, int64_t
 		}
 		h = (h + 1) & mask;
 		he = &z->tab[h];
+		nprobe++;
 	}
+	z->st.lookup_probes += nprobe;
+	if (nprobe > z->st.max_probe)
+		z->st.max_probe = nprobe;
+	if (nprobe >= 32)
+		z->st.probes_ge32++;
 	return length;
 }
 

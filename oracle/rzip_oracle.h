@@ -13,6 +13,7 @@ typedef struct rzo_stats {
 	int64_t matches, match_bytes, literals, literal_bytes; /* src/rzip.c:1238-1241 */
 	int64_t tag_hits, tag_misses, inserts;                 /* src/rzip.c:1242-1244 */
 	int64_t lookups, chain_evictions, sweeps;
+	int64_t displacements, max_depth, insert_probes, lookup_probes, max_probe, probes_ge32;
 	int64_t hash_count, final_min_mask, final_tag_mask;
 	uint32_t crc32;
 } rzo_stats;

@@ -21,7 +21,8 @@ BACKEND_NONE, BACKEND_LZMA, BACKEND_ZSTD = 0, 1, 4
 class Stats(C.Structure):
     _fields_ = [(n, C.c_int64) for n in (
         "matches", "match_bytes", "literals", "literal_bytes", "tag_hits", "tag_misses", "inserts",
-        "lookups", "chain_evictions", "sweeps", "hash_count", "final_min_mask", "final_tag_mask")] + [("crc32", C.c_uint32)]
+        "lookups", "chain_evictions", "sweeps",
+        "displacements", "max_depth", "insert_probes", "lookup_probes", "max_probe", "probes_ge32", "hash_count", "final_min_mask", "final_tag_mask")] + [("crc32", C.c_uint32)]
 
     def as_dict(self):
         return {n: getattr(self, n) for n, _ in self._fields_}

@@ -1,0 +1,105 @@
+"""GPU parity tests for the rzip path (K1 tag scan, K2 commit, K4 emit, CRC) through the C ABI.
+
+Every comparison is bit-exact against the CPU oracle (oracle/liboracle.so), which is itself pinned to
+the unmodified reference (tests/test_oracle_vs_ref.py, tests/golden/)."""
+import hashlib
+import zlib
+
+import numpy as np
+import pytest
+
+import oracle
+from lrzip_next_b200 import BACKEND_NONE, make_params
+from lrzip_next_b200 import datagen
+
+pytestmark = pytest.mark.gpu
+
+
+def _first_diff(a: bytes, b: bytes):
+    n = min(len(a), len(b))
+    x = np.frombuffer(a[:n], dtype=np.uint8) != np.frombuffer(b[:n], dtype=np.uint8)
+    nz = np.flatnonzero(x)
+    return int(nz[0]) if nz.size else (n if len(a) != len(b) else None)
+
+
+@pytest.mark.parametrize("n", [1, 31, 32, 4095, 4096, 4097, 100_000, (1 << 20) + 77])
+def test_crc32_matches_zlib(ctx, n):
+    d = np.random.default_rng(n).integers(0, 256, size=n, dtype=np.uint8)
+    assert ctx.crc32(d) == zlib.crc32(d.tobytes())
+
+
+@pytest.mark.parametrize("kind,n,mask", [("text", 300_000, 1), ("rep", 1 << 20, 1), ("text", 70_000, 15),
+                                         ("randzero", 200_000, 3), ("text", 40, 1), ("text", 31, 1), ("text", 5000, 0)])
+def test_tag_scan_matches_full_tag(ctx, kind, n, mask):
+    d = datagen.generate(kind, n)
+    pos, tag = ctx.tag_scan(d, mask)
+    hi = oracle.hash_index()
+    # reference tags by prefix XOR (src/rzip.c:405-416)
+    x = np.concatenate(([0], np.bitwise_xor.accumulate(hi[d])))
+    end = n - 31
+    if end < 1:
+        assert pos.size == 0
+        return
+    p = np.arange(1, end + 1)
+    t = x[p + 31] ^ x[p]
+    keep = (t & mask) == mask
+    assert np.array_equal(pos, p[keep])
+    assert np.array_equal(tag, t[keep])
+
+
+CASES = [
+    ("rep", 8 << 20, 7), ("text", 6 << 20, 7), ("text", 3 << 20, 3), ("mix", 8 << 20, 7), ("vm", 8 << 20, 7),
+    ("trees", 8 << 20, 9), ("randzero", 4 << 20, 1), ("text", 1000, 7), ("text", 20, 7), ("text", 31, 7),
+    ("text", 32, 7), ("text", 24 << 20, 1), ("trees", 40 << 20, 7), ("rep", 33 << 20, 5),
+]
+
+
+@pytest.mark.parametrize("kind,n,level", CASES)
+def test_rzip_chunk_streams_bit_exact(ctx, kind, n, level):
+    d = datagen.generate(kind, n)
+    o0, o1, ost, ovr = oracle.rzip_chunk(d, level)
+    s0, s1, st, vr = ctx.rzip_chunk(d, level)
+    for k in ("inserts", "lookups", "tag_hits", "tag_misses", "chain_evictions", "sweeps", "hash_count",
+              "final_min_mask", "final_tag_mask", "matches", "match_bytes", "literals", "literal_bytes"):
+        assert st[k] == ost[k], (k, st[k], ost[k])
+    assert st["crc32"] == ost["crc32"]
+    assert len(s0) == len(o0) and _first_diff(s0, o0) is None, _first_diff(s0, o0)
+    assert len(s1) == len(o1) and _first_diff(s1, o1) is None, _first_diff(s1, o1)
+    assert vr == ovr
+
+
+def test_rzip_victim_round_carried(ctx):
+    # a periodic input whose tag passes the mask builds equal-tag chains that hit max_chain_len
+    blk = np.frombuffer(b"abcdefg" * 5, dtype=np.uint8)
+    d = np.tile(blk, (2 << 20) // blk.size + 1)[:2 << 20].copy()
+    rnd = np.random.default_rng(5).integers(0, 256, size=d.size // 8, dtype=np.uint8)
+    d[::8] ^= (rnd & 1)  # break most long matches, keep many equal windows
+    for vr_in in (0, 3):
+        o0, o1, ost, ovr = oracle.rzip_chunk(d, 7, victim_round=vr_in)
+        s0, s1, st, vr = ctx.rzip_chunk(d, 7, victim_round=vr_in)
+        assert (s0, s1, vr) == (o0, o1, ovr)
+        assert st["chain_evictions"] == ost["chain_evictions"]
+
+
+@pytest.mark.parametrize("kind,n,kw", [
+    ("rep", 12 << 20, {}), ("text", 5 << 20, {}), ("mix", 8 << 20, {}),
+    ("text", 30 << 20, dict(window=1, ramsize=3 * 100 * 1048576)),   # several chunks (windows)
+    ("vm", 25 << 20, dict(level=9)),
+])
+def test_archive_stored_bit_identical_to_oracle(ctx, kind, n, kw):
+    d = datagen.generate(kind, n)
+    p = make_params(backend=BACKEND_NONE, threads=1, **kw)
+    op = oracle.make_params(backend=oracle.BACKEND_NONE, threads=1, **kw)
+    want, _ = oracle.compress(d, op)
+    got = ctx.compress(d, p)
+    assert len(got) == len(want) and _first_diff(got, want) is None, _first_diff(got, want)
+    assert got[-16:] == hashlib.md5(d.tobytes()).digest()
+
+
+@pytest.mark.skipif(not oracle.have_ref(), reason="compiled reference (oracle/_ref) not present")
+def test_archive_verifies_with_reference_binary(ctx):
+    d = datagen.generate("trees", 16 << 20)
+    p = make_params(backend=BACKEND_NONE, threads=1)
+    got = ctx.compress(d, p)
+    assert oracle.ref_test(got)
+    assert oracle.ref_decompress(got) == d.tobytes()
