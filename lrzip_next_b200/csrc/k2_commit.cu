@@ -8,8 +8,15 @@
 //     (find_best_match src/rzip.c:511-531, insert_hash :313-349, clean_one_from_hash :363-378)
 //   * match extension: 512 bytes per step forwards and backwards, 16 B per lane, first mismatch by
 //     ballot + ffs/clz (single_match_len src/rzip.c:441-454)
-//   * candidate fetch: 32 {pos,tag} records per load, mask filter by ballot, table lines of the
-//     upcoming candidates prefetched into L1
+//   * candidate fetch: 32 {pos,tag} records per load, mask filter by ballot
+//
+// The commit warp is latency bound: every candidate costs a chain of dependent loads (probe window,
+// then the bytes at the matching offsets).  Seven helper warps of the same CTA therefore run a bounded
+// distance AHEAD of it over the same candidate list and do read-only "dry" lookups, one candidate per
+// lane: they walk the probe chain and touch the window bytes of equal-tag entries, which pulls those
+// lines into the SM's L1 (shared by all warps of the CTA).  Helpers never write and never decide
+// anything, so exactness rests on the commit warp alone; they only turn its HBM/L2 round trips into
+// L1 hits.  Progress is exchanged through two volatile shared-memory words.
 #include "k2_commit.cuh"
 #include "kernels.h"
 
@@ -49,7 +56,14 @@ __device__ __forceinline__ int nth_set_bit(uint32_t m, int k)
 	return __ffs(m) - 1;
 }
 
+struct Progress { // shared memory, written by the commit warp, polled by the helpers
+	volatile long long pos;
+	volatile long long min_mask;
+	volatile int done;
+};
+
 struct WarpPrim {
+	Progress *prog;
 	const uint8_t *buf;
 	HEntry *tab;
 	int64_t hmask;
@@ -65,6 +79,13 @@ struct WarpPrim {
 	uint32_t bmask;
 
 	__device__ __forceinline__ bool leader() const { return lane == 0; }
+	__device__ __forceinline__ void publish(int64_t p, int64_t mask)
+	{
+		if (lane == 0) {
+			prog->pos = p;
+			prog->min_mask = mask;
+		}
+	}
 	__device__ __forceinline__ void store_rec(MatchRec *dst, const MatchRec &r)
 	{
 		if (lane == 0)
@@ -115,18 +136,47 @@ struct WarpPrim {
 			const uint32_t i = idx + lane;
 			const bool v = i < cnt;
 			if (v) {
-				const longlong2 c = __ldcs(reinterpret_cast<const longlong2 *>(cand + tile * (int64_t)kTile + i));
+				const longlong2 c = *reinterpret_cast<const longlong2 *>(cand + tile * (int64_t)kTile + i);
 				bpos = c.x;
 				btag = c.y;
-				if ((btag & min_mask) == min_mask && bpos > after) {
-					const HEntry *w = tab + (btag & hmask);
-					asm volatile("prefetch.global.L1 [%0];" ::"l"(w));
-					asm volatile("prefetch.global.L1 [%0];" ::"l"(w + 8));
-				}
 			}
 			bmask = __ballot_sync(FULL, v);
 			idx += 32;
 		}
+	}
+
+	// Next 32 records of the K1 list (one per lane, `valid` false past the tile's count); false when
+	// the segment's list is exhausted.  Tiles that lie wholly at or before `after` are skipped.
+	__device__ bool load_window(int64_t after, int64_t &pos, int64_t &tag, bool &valid)
+	{
+		const int64_t want = (after + 1) / kTile - first_tile;
+		if (want > tile) {
+			tile = want;
+			idx = 0;
+			cnt_valid = false;
+		}
+		for (;;) {
+			if (tile >= num_tiles)
+				return false;
+			if (!cnt_valid) {
+				cnt = __ldg(tile_count + tile);
+				cnt_valid = true;
+			}
+			if (idx < cnt)
+				break;
+			tile++;
+			idx = 0;
+			cnt_valid = false;
+		}
+		const uint32_t i = idx + lane;
+		valid = i < cnt;
+		if (valid) {
+			const longlong2 c = *reinterpret_cast<const longlong2 *>(cand + tile * (int64_t)kTile + i);
+			pos = c.x;
+			tag = c.y;
+		}
+		idx += 32;
+		return true;
 	}
 
 	// src/rzip.c:431-461 single_match_len, 512 bytes per step
@@ -278,28 +328,646 @@ struct WarpPrim {
 	}
 };
 
-__global__ void __launch_bounds__(32, 1)
+static constexpr int K2_HELPERS = 7;
+static constexpr int K2_THREADS = 32 * (1 + K2_HELPERS);
+static constexpr int K2_LOOKAHEAD = 64;  // candidates the helpers may run ahead of the commit warp
+static constexpr int K2_MAXW = 4;        // insert writes one lane may carry (displacement depth 3)
+static constexpr unsigned K2_MAXWALK = 192;
+
+struct FastShared {
+	long long qpos[64], qtag[64]; // queue of upcoming candidates that pass the current gate
+	unsigned dslot[32];           // sweep deletions of the current batch, in order
+	Progress prog;
+};
+
+__device__ __forceinline__ void touch_line(const void *p)
+{
+	unsigned v;
+	asm volatile("ld.global.ca.u32 %0, [%1];" : "=r"(v) : "l"((uintptr_t)p & ~(uintptr_t)3) : "memory");
+	asm volatile("" ::"r"(v));
+}
+
+// Helper warp `hw` (0-based): dry lookups for batches b of every tile with (tile + b) % K2_HELPERS == hw.
+__device__ void k2_helper(Progress *prog, const uint8_t *__restrict__ buf, const HEntry *tab, int64_t hmask,
+			  const Cand *__restrict__ cand, const uint32_t *__restrict__ tile_count, int64_t first_tile,
+			  int64_t num_tiles, int64_t n, int hw, int lane)
+{
+	for (int64_t t = 0; t < num_tiles; t++) {
+		if (prog->done)
+			return;
+		if ((first_tile + t + 1) * (int64_t)kTile <= prog->pos)
+			continue; // the scan is already past this tile
+		const uint32_t cnt = tile_count[t];
+		for (uint32_t b = (uint32_t)((hw + K2_HELPERS - (t % K2_HELPERS)) % K2_HELPERS); b * 32 < cnt; b += K2_HELPERS) {
+			const uint32_t i = b * 32 + lane;
+			int64_t pos = 0, tag = 0;
+			const bool v = i < cnt;
+			if (v) {
+				const longlong2 c = *reinterpret_cast<const longlong2 *>(cand + t * (int64_t)kTile + i);
+				pos = c.x;
+				tag = c.y;
+			}
+			const int64_t first_pos = __shfl_sync(FULL, pos, 0);
+			// stay within K2_LOOKAHEAD candidates (at the current density) of the commit warp
+			for (;;) {
+				if (prog->done)
+					return;
+				const int64_t ahead = (int64_t)K2_LOOKAHEAD << __popcll(prog->min_mask);
+				if (first_pos <= prog->pos + ahead)
+					break;
+				__nanosleep(2000);
+			}
+			const int64_t mm = prog->min_mask, mp = prog->pos;
+			if (v && pos > mp && (tag & mm) == mm) {
+				touch_line(buf + pos);
+				int64_t h = tag & hmask;
+				for (int step = 0; step < 8; step++) { // 4 slots per step, up to 32 slots
+					HEntry e[4];
+#pragma unroll
+					for (int k = 0; k < 4; k++)
+						e[k] = ld_entry(tab + ((h + k) & hmask));
+					bool stop = false;
+#pragma unroll
+					for (int k = 0; k < 4; k++) {
+						if (stop)
+							break;
+						if (!(e[k].offset | e[k].tag)) {
+							stop = true;
+							break;
+						}
+						if (e[k].tag == tag && e[k].offset < pos && e[k].offset >= 0 && e[k].offset < n)
+							touch_line(buf + e[k].offset);
+					}
+					if (stop)
+						break;
+					h += 4;
+				}
+			}
+			__syncwarp();
+		}
+	}
+}
+
+// ---- batched commit ---------------------------------------------------------------------------------
+// The reference's loop is serial, but consecutive candidates almost never interact: a candidate reads
+// its probe chain [home, first empty slot] and writes one or a few slots.  The commit warp therefore
+// evaluates up to 32 queued candidates at once, ONE PER LANE, against the table as it stands at the
+// start of the batch, and then validates in order that no candidate read a slot written (inserted into
+// or swept) by an earlier candidate of the same batch.  The longest conflict-free prefix is committed
+// with exactly the effects the serial loop would have had; the first candidate that needs anything
+// beyond the simple cases -- a real match (anything that touches the pending-match / emit logic), an
+// equal-tag chain reaching max_chain_len (victim_round), a displacement chain deeper than 3, a sweep
+// that wraps (mask promotion), a write inside the stretch of table the sweep is about to visit -- is
+// handed to the serial k2_step(), which is also used while a match is pending.  The batch therefore
+// never decides anything the serial code would decide differently.
+
+struct LaneEval {
+	unsigned wslot[K2_MAXW + 1]; // insert writes, then (optionally) the sweep deletion
+	long long wtag[K2_MAXW], woff[K2_MAXW];
+	unsigned rlo[K2_MAXW], rlen[K2_MAXW]; // probe ranges read (start slot, length), modulo the table size
+	int nw, nr, net, ins, miss;
+	bool cx;
+};
+
+// Could the equal-tag entry at `op` give a match of >= 31 bytes at p0?  (single_match_len, bounded.)
+__device__ __forceinline__ bool could_match(const uint8_t *__restrict__ buf, int64_t p0, int64_t op, int64_t end,
+					    int64_t last_match)
+{
+	if (op >= p0)
+		return false;
+	int fwd = 0;
+	while (fwd < kMinMatch && p0 + fwd < end && __ldg(buf + p0 + fwd) == __ldg(buf + op + fwd))
+		fwd++;
+	if (fwd >= kMinMatch)
+		return true;
+	const int need = kMinMatch - fwd;
+	const int64_t lo = last_match > 0 ? last_match : 0;
+	int rev = 0;
+	while (rev < need && p0 - rev > lo && op - rev > 0 && __ldg(buf + op - rev - 1) == __ldg(buf + p0 - rev - 1))
+		rev++;
+	return rev >= need;
+}
+
+__device__ __forceinline__ void prefetch_l1(const void *p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+
+static constexpr int K2_MAXEQ = 16; // equal-tag entries one lane may meet in its chain
+static constexpr int K2_WIDE = 8; // slots fetched per step of a lane's private probe walk (independent loads)
+
+__device__ void lane_eval(const uint8_t *__restrict__ buf, const HEntry *tab, unsigned hmask, int64_t p, int64_t t,
+			  int64_t tag_mask, int64_t better, int max_chain, int64_t end, int64_t last_match, LaneEval &L)
+{
+	L.nw = L.nr = L.net = L.ins = L.miss = 0;
+	L.cx = false;
+	const bool do_insert = (t & tag_mask) == tag_mask;
+	const unsigned h = (unsigned)t & hmask;
+	const int my_ones = tz_ones(t);
+	bool stop = !do_insert;
+	int kind = -1, round = 0;
+	unsigned sslot = 0, s = 0;
+	HEntry occ;
+	occ.offset = occ.tag = 0;
+	int64_t eq_off[K2_MAXEQ]; // offsets of the equal-tag entries met on the way, compared after the walk
+	int neq = 0;
+	prefetch_l1(buf + p);
+	for (bool done = false; !done;) {
+		if (s >= K2_MAXWALK) {
+			L.cx = true;
+			return;
+		}
+		HEntry e[K2_WIDE];
+#pragma unroll
+		for (int k = 0; k < K2_WIDE; k++)
+			e[k] = ld_entry(tab + ((h + s + k) & hmask));
+#pragma unroll
+		for (int k = 0; k < K2_WIDE; k++)
+			if (e[k].tag == t && e[k].offset > 0 && e[k].offset < p)
+				prefetch_l1(buf + e[k].offset);
+#pragma unroll
+		for (int k = 0; k < K2_WIDE; k++) {
+			if (done)
+				break;
+			const unsigned slot = (h + s) & hmask;
+			if (!(e[k].offset | e[k].tag)) {
+				if (!stop) {
+					kind = kProbeEmpty;
+					sslot = slot;
+				}
+				done = true;
+				break;
+			}
+			if (!stop) {
+				if ((e[k].tag & better) != better) {
+					kind = kProbeDue;
+					sslot = slot;
+					stop = true;
+				} else if (tz_ones(e[k].tag) < my_ones) {
+					kind = kProbeDisplace;
+					occ = e[k];
+					sslot = slot;
+					stop = true;
+				} else if (e[k].tag == t && ++round == max_chain) {
+					L.cx = true; // chain cap: victim_round logic stays serial
+					return;
+				}
+			}
+			if (e[k].tag == t) {
+				if (neq == K2_MAXEQ) {
+					L.cx = true;
+					return;
+				}
+				eq_off[neq++] = e[k].offset;
+			}
+			s++;
+		}
+	}
+	// all lanes compare their q-th equal-tag entry at the same time, so the misses overlap
+	for (int q = 0; q < neq; q++) {
+		if (could_match(buf, p, eq_off[q], end, last_match)) {
+			L.cx = true;
+			return;
+		}
+		L.miss++;
+	}
+	L.rlo[0] = h;
+	L.rlen[0] = s + 1;
+	L.nr = 1;
+	if (!do_insert)
+		return;
+	L.ins = 1;
+	int64_t ct = t, coff = p;
+	for (;;) {
+		L.wslot[L.nw] = sslot;
+		L.wtag[L.nw] = ct;
+		L.woff[L.nw] = coff;
+		L.nw++;
+		if (kind != kProbeDisplace) {
+			L.net = (kind == kProbeEmpty) ? 1 : 0;
+			return;
+		}
+		if (L.nw == K2_MAXW) {
+			L.cx = true;
+			return;
+		}
+		// re-home the displaced occupant (the reference recurses before it overwrites the slot)
+		ct = occ.tag;
+		coff = occ.offset;
+		const unsigned h2 = (unsigned)ct & hmask;
+		const int ones2 = tz_ones(ct);
+		round = 0;
+		kind = -1;
+		unsigned s2 = 0;
+		for (bool done = false; !done;) {
+			if (s2 >= K2_MAXWALK) {
+				L.cx = true;
+				return;
+			}
+			HEntry e[K2_WIDE];
+#pragma unroll
+			for (int k = 0; k < K2_WIDE; k++)
+				e[k] = ld_entry(tab + ((h2 + s2 + k) & hmask));
+#pragma unroll
+			for (int k = 0; k < K2_WIDE; k++) {
+				if (done)
+					break;
+				sslot = (h2 + s2) & hmask;
+				if (!(e[k].offset | e[k].tag)) {
+					kind = kProbeEmpty;
+					done = true;
+					break;
+				}
+				if ((e[k].tag & better) != better) {
+					kind = kProbeDue;
+					done = true;
+					break;
+				}
+				if (tz_ones(e[k].tag) < ones2) {
+					kind = kProbeDisplace;
+					occ = e[k];
+					done = true;
+					break;
+				}
+				if (e[k].tag == ct && ++round == max_chain) {
+					L.cx = true;
+					return;
+				}
+				s2++;
+			}
+		}
+		L.rlo[L.nr] = h2;
+		L.rlen[L.nr] = s2 + 1;
+		L.nr++;
+	}
+}
+
+__device__ __forceinline__ int warp_sum(int v)
+{
+#pragma unroll
+	for (int o = 16; o; o >>= 1)
+		v += __shfl_xor_sync(FULL, v, o);
+	return v;
+}
+
+__device__ void k2_commit_segment_batched(WarpPrim &prim, FastShared *sh, ScanState *st, MatchRec *recs, bool last_segment)
+{
+	CommitRegs r;
+	CommitConst c;
+	CommitCounters n;
+	k2_load_regs(st, r, c);
+	int status = st->status;
+	const int lane = prim.lane;
+	const unsigned lt = (1u << lane) - 1;
+	const unsigned hmask = (unsigned)prim.hmask;
+	const int64_t tsize = prim.hmask + 1;
+	int qn = 0;
+	bool list_done = false, again = false;
+	int64_t again_p = 0, again_t = 0;
+	int64_t n_disp = 0;
+	int64_t dbg[12] = { 0 };
+	const long long clk_start = clock64();
+
+	// drop queue entries the scan has moved past or that fail the (possibly tightened) gate
+	auto filter_queue = [&]() {
+		__syncwarp();
+		long long p0 = 0, t0 = 0, p1 = 0, t1 = 0;
+		bool k0 = false, k1 = false;
+		if (lane < qn) {
+			p0 = sh->qpos[lane];
+			t0 = sh->qtag[lane];
+			k0 = p0 > r.p && (t0 & r.min_mask) == r.min_mask;
+		}
+		if (lane + 32 < qn) {
+			p1 = sh->qpos[lane + 32];
+			t1 = sh->qtag[lane + 32];
+			k1 = p1 > r.p && (t1 & r.min_mask) == r.min_mask;
+		}
+		const unsigned b0 = __ballot_sync(FULL, k0), b1 = __ballot_sync(FULL, k1);
+		__syncwarp();
+		if (k0) {
+			const int d = __popc(b0 & lt);
+			sh->qpos[d] = p0;
+			sh->qtag[d] = t0;
+		}
+		if (k1) {
+			const int d = __popc(b0) + __popc(b1 & lt);
+			sh->qpos[d] = p1;
+			sh->qtag[d] = t1;
+		}
+		qn = __popc(b0) + __popc(b1);
+		__syncwarp();
+	};
+	auto pop_front = [&](int k) {
+		__syncwarp();
+		long long p0 = 0, t0 = 0, p1 = 0, t1 = 0;
+		const int i0 = lane + k, i1 = lane + 32 + k;
+		if (i0 < qn) {
+			p0 = sh->qpos[i0];
+			t0 = sh->qtag[i0];
+		}
+		if (i1 < qn) {
+			p1 = sh->qpos[i1];
+			t1 = sh->qtag[i1];
+		}
+		__syncwarp();
+		if (i0 < qn) {
+			sh->qpos[lane] = p0;
+			sh->qtag[lane] = t0;
+		}
+		if (i1 < qn) {
+			sh->qpos[lane + 32] = p1;
+			sh->qtag[lane + 32] = t1;
+		}
+		qn -= k;
+		__syncwarp();
+	};
+
+	while (status == kStatusRunning) {
+		if (again) { // re-examine the candidate a match emission jumped back over (see k2_step)
+			again = false;
+			if ((again_t & r.min_mask) == r.min_mask) {
+				again = k2_step(prim, st, r, c, n, recs, again_p, again_t, status);
+				filter_queue();
+			} else
+				r.p = again_p;
+			continue;
+		}
+		while (qn < 32 && !list_done) { // refill from the K1 list
+			int64_t wp = 0, wt = 0;
+			bool wv = false;
+			if (!prim.load_window(r.p, wp, wt, wv)) {
+				list_done = true;
+				break;
+			}
+			const bool keep = wv && wp > r.p && wp < prim.seg_hi && (wt & r.min_mask) == r.min_mask;
+			const unsigned bm = __ballot_sync(FULL, keep);
+			if (keep) {
+				const int d = qn + __popc(bm & lt);
+				sh->qpos[d] = wp;
+				sh->qtag[d] = wt;
+			}
+			qn += __popc(bm);
+			__syncwarp();
+		}
+		if (qn == 0)
+			break;
+		if (r.cur_len > 0) { // a match is pending: strictly serial until it is emitted
+			const int64_t p = sh->qpos[0], t = sh->qtag[0];
+			pop_front(1);
+			const long long c0 = clock64();
+			again = k2_step(prim, st, r, c, n, recs, p, t, status);
+			dbg[9] += clock64() - c0;
+			dbg[2]++;
+			again_p = p;
+			again_t = t;
+			filter_queue();
+			continue;
+		}
+
+		// ---- evaluate up to 32 candidates, one per lane, on the table as it stands
+		const int nb = qn < 32 ? qn : 32;
+		const int64_t better = (r.min_mask << 1) | 1;
+		LaneEval L;
+		L.nw = L.nr = L.net = L.ins = L.miss = 0;
+		L.cx = false;
+		int64_t myp = 0, myt = 0;
+		dbg[0]++;
+		const long long ce0 = clock64();
+		if (lane < nb) {
+			myp = sh->qpos[lane];
+			myt = sh->qtag[lane];
+			lane_eval(prim.buf, prim.tab, hmask, myp, myt, r.tag_mask, better, c.max_chain, c.end, r.last_match, L);
+		}
+		__syncwarp();
+		dbg[8] += clock64() - ce0;
+		if (L.cx)
+			L.net = 0;
+		// sweep deletions (clean_one_from_hash): the k-th insert that overfills the table removes the
+		// k-th entry, in table order from tag_clean_ptr, that lacks the next-stricter mask
+		const unsigned netm = __ballot_sync(FULL, L.net != 0);
+		bool cl = L.net && (r.hash_count + __popc(netm & (lt | (1u << lane))) > c.hash_limit);
+		const unsigned clm = __ballot_sync(FULL, cl);
+		const int ncl = __popc(clm), crank = __popc(clm & lt);
+		int found = 0;
+		unsigned dmax = 0;
+		if (ncl) {
+			for (int64_t cp = r.clean_ptr; found < ncl && cp < tsize; cp += 32) {
+				const int64_t k = cp + lane;
+				bool q = false;
+				if (k < tsize) {
+					const HEntry e = ld_entry(prim.tab + k);
+					q = (e.offset | e.tag) && (e.tag & better) != better;
+				}
+				const unsigned bm = __ballot_sync(FULL, q);
+				if (q) {
+					const int rk = found + __popc(bm & lt);
+					if (rk < ncl)
+						sh->dslot[rk] = (unsigned)k;
+				}
+				found += __popc(bm);
+			}
+			if (found > ncl)
+				found = ncl;
+			__syncwarp();
+			if (found)
+				dmax = sh->dslot[found - 1];
+		}
+		// flags of one lane after an evaluation: `stopper` = must go through the serial step
+		bool stopper = false;
+		unsigned del = 0;
+		int nwt = 0;
+		auto classify = [&]() {
+			stopper = L.cx;
+			del = 0;
+			if (cl) {
+				if (crank >= found)
+					stopper = true; // the sweep has to wrap first (mask promotion)
+				else
+					del = sh->dslot[crank];
+			}
+			if (found && !stopper) // a write inside the stretch the sweep visits in this batch changes the sweep
+				for (int w = 0; w < L.nw; w++)
+					if ((int64_t)L.wslot[w] >= r.clean_ptr && L.wslot[w] <= dmax)
+						stopper = true;
+			nwt = L.nw;
+			if (cl && !stopper)
+				L.wslot[nwt++] = del;
+		};
+		classify();
+		// ---- ordered validation: cmask bit j = this lane read a slot that lane j (< lane) writes
+		unsigned cmask = 0;
+		auto check_against = [&](int j) {
+			const int nwj = __shfl_sync(FULL, nwt, j);
+#pragma unroll
+			for (int w = 0; w < K2_MAXW + 1; w++) {
+				if (w >= nwj)
+					break;
+				const unsigned sl = __shfl_sync(FULL, L.wslot[w], j);
+				if (lane > j) {
+#pragma unroll
+					for (int q = 0; q < K2_MAXW; q++)
+						if (q < L.nr && ((sl - L.rlo[q]) & hmask) < L.rlen[q])
+							cmask |= 1u << j;
+				}
+			}
+		};
+		for (int j = 0; j + 1 < nb; j++)
+			check_against(j);
+
+		// ---- commit in order; a lane that only conflicts is re-evaluated alone on the updated table
+		int base = 0;
+		bool serial_next = false;
+		const int64_t tag_mask0 = r.tag_mask;
+		for (;;) {
+			const unsigned stopm = __ballot_sync(FULL, lane >= base && lane < nb && (stopper || cmask != 0));
+			int k = stopm ? (__ffs(stopm) - 1) : nb;
+			bool gate_cut = false;
+			if (r.tag_mask != better) { // the first sweep deletion of a phase tightens the insert gate:
+				const unsigned lo_m = (base >= 32) ? 0u : (FULL << base); // later lanes used the old gate
+				const unsigned km0 = (k >= 32) ? FULL : ((1u << k) - 1);
+				const unsigned first_cl = clm & lo_m & km0;
+				if (first_cl) {
+					const int f = __ffs(first_cl) - 1;
+					if (f + 1 < k) {
+						k = f + 1;
+						gate_cut = true;
+					}
+				}
+			}
+			const bool mine = lane >= base && lane < k;
+			if (mine) {
+				for (int w = 0; w < L.nw; w++)
+					*reinterpret_cast<longlong2 *>(prim.tab + L.wslot[w]) = make_longlong2(L.woff[w], L.wtag[w]);
+				if (cl)
+					*reinterpret_cast<longlong2 *>(prim.tab + del) = make_longlong2(0, 0);
+			}
+			__syncwarp();
+			if (k > base) {
+				const unsigned km = ((k >= 32) ? FULL : ((1u << k) - 1)) & ((base >= 32) ? 0u : (FULL << base));
+				const int s_ins = warp_sum(mine ? L.ins : 0), s_miss = warp_sum(mine ? L.miss : 0);
+				const int s_disp = warp_sum(mine && L.nw > 1 ? L.nw - 1 : 0);
+				const unsigned ck = clm & km;
+				n.lookups += k - base;
+				n.inserts += s_ins;
+				n.misses += s_miss;
+				n_disp += s_disp;
+				r.hash_count += __popc(netm & km) - __popc(ck);
+				if (ck) {
+					r.clean_ptr = sh->dslot[__popc(clm & ((k >= 32) ? FULL : ((1u << k) - 1))) - 1];
+					r.tag_mask = better;
+				}
+				r.p = sh->qpos[k - 1];
+			}
+			dbg[1] += k - base;
+			base = k;
+			if (gate_cut)
+				dbg[6]++;
+			if (k >= nb || gate_cut || r.tag_mask != tag_mask0)
+				break;
+			if (__shfl_sync(FULL, (int)stopper, k)) {
+				serial_next = true;
+				dbg[__shfl_sync(FULL, (int)L.cx, k) ? 3 : 4]++;
+				break;
+			}
+			// lane k only conflicts with committed lanes: evaluate it again, alone, on the current table
+			const int old_net = __shfl_sync(FULL, L.net, k);
+			const int old_cl = __shfl_sync(FULL, (int)cl, k);
+			dbg[5]++;
+			const long long ce1 = clock64();
+			if (lane == k) {
+				lane_eval(prim.buf, prim.tab, hmask, myp, myt, r.tag_mask, better, c.max_chain, c.end, r.last_match, L);
+				if (L.cx)
+					L.net = 0;
+				cmask = 0;
+			}
+			__syncwarp();
+			dbg[8] += clock64() - ce1;
+			const int new_net = __shfl_sync(FULL, L.net, k);
+			const int new_cx = __shfl_sync(FULL, (int)L.cx, k);
+			if (new_cx) {
+				serial_next = true;
+				dbg[3]++;
+				break;
+			}
+			if (new_net != old_net || (new_net && (r.hash_count + 1 > c.hash_limit) != (old_cl != 0))) {
+				dbg[7]++;
+				break; // sweep ranks of the later lanes would shift: start a fresh batch
+			}
+			if (lane == k)
+				classify();
+			__syncwarp();
+			if (__shfl_sync(FULL, (int)stopper, k)) {
+				serial_next = true;
+				dbg[4]++;
+				break;
+			}
+			if (lane > k)
+				cmask &= ~(1u << k);
+			check_against(k);
+		}
+		if (base > 0) {
+			prim.publish(r.p, r.min_mask);
+			pop_front(base);
+		}
+		if (serial_next) { // serial step for the candidate that needs it
+			const int64_t p = sh->qpos[0], t = sh->qtag[0];
+			pop_front(1);
+			const long long c0 = clock64();
+			again = k2_step(prim, st, r, c, n, recs, p, t, status);
+			dbg[9] += clock64() - c0;
+			again_p = p;
+			again_t = t;
+			filter_queue();
+		}
+	}
+	if (status == kStatusRunning && last_segment)
+		k2_close_chunk(prim, st, r, c, recs, status);
+	if (lane == 0) {
+		dbg[10] = clock64() - clk_start;
+		for (int i = 0; i < 12; i++)
+			st->dbg[i] += dbg[i];
+		st->st_displacements += n_disp;
+		k2_store_regs(st, r, n, status);
+	}
+}
+
+__global__ void __launch_bounds__(K2_THREADS, 1)
 k2_commit_kernel(const uint8_t *__restrict__ buf, ScanState *st, HEntry *tab, const Cand *cand,
 		 const uint32_t *tile_count, int64_t first_tile, int64_t num_tiles, int64_t seg_hi, MatchRec *recs,
 		 int last_segment)
 {
+	__shared__ FastShared sh;
+	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+	if (threadIdx.x == 0) {
+		sh.prog.pos = st->scan_pos;
+		sh.prog.min_mask = st->min_mask;
+		sh.prog.done = (st->status != kStatusRunning) ? 1 : 0;
+	}
+	__syncthreads();
+	const int64_t hmask = ((int64_t)1 << st->hash_bits) - 1;
+	if (warp != 0) {
+		k2_helper(&sh.prog, buf, tab, hmask, cand, tile_count, first_tile, num_tiles, st->n, warp - 1, lane);
+		return;
+	}
 	WarpPrim prim;
+	prim.prog = &sh.prog;
 	prim.buf = buf;
 	prim.tab = tab;
-	prim.hmask = ((int64_t)1 << st->hash_bits) - 1;
+	prim.hmask = hmask;
 	prim.cand = cand;
 	prim.tile_count = tile_count;
 	prim.first_tile = first_tile;
 	prim.num_tiles = num_tiles;
 	prim.seg_hi = seg_hi;
-	prim.lane = threadIdx.x;
+	prim.lane = lane;
 	prim.tile = 0;
 	prim.idx = 0;
 	prim.cnt = 0;
 	prim.cnt_valid = false;
 	prim.bpos = prim.btag = 0;
 	prim.bmask = 0;
-	k2_commit_segment(prim, st, recs, last_segment != 0);
+	k2_commit_segment_batched(prim, &sh, st, recs, last_segment != 0);
+	__syncwarp();
+	if (lane == 0)
+		sh.prog.done = 1;
 }
 
 int k2_launch(const uint8_t *d_buf, ScanState *d_state, HEntry *d_tab, const Cand *d_cand,
@@ -311,7 +979,7 @@ int k2_launch(const uint8_t *d_buf, ScanState *d_state, HEntry *d_tab, const Can
 		first_tile = pos_lo / kTile;
 		num_tiles = (pos_hi - 1) / kTile - first_tile + 1;
 	}
-	k2_commit_kernel<<<1, 32, 0, stream>>>(d_buf, d_state, d_tab, d_cand, d_tile_count, first_tile, num_tiles,
+	k2_commit_kernel<<<1, K2_THREADS, 0, stream>>>(d_buf, d_state, d_tab, d_cand, d_tile_count, first_tile, num_tiles,
 					       pos_hi, d_recs, last_segment ? 1 : 0);
 	return cudaGetLastError() == cudaSuccess ? 0 : -1;
 }

@@ -31,6 +31,9 @@ struct ProbeResult {
 
 LRZ_HD int tz_ones(int64_t t) // ffsll(~t): 1 + number of trailing one bits (src/rzip.c:295-300)
 {
+#if defined(__CUDA_ARCH__)
+	return __ffsll(~(long long)t);
+#endif
 	uint64_t v = ~(uint64_t)t;
 	int n = 1;
 	if (!v)
@@ -85,16 +88,16 @@ template <class P>
 LRZ_HD void k2_insert(P &prim, ScanState *st, CommitRegs &r, int64_t t, int64_t off, int max_chain)
 {
 	const int64_t better = (r.min_mask << 1) | 1;
-	int64_t slots[50], tags[50], offs[50];
+	int64_t slots[48], tags[48], offs[48]; // bitness strictly decreases along a displacement chain: depth <= 47
 	int depth = 0;
 	for (;;) {
 		ProbeResult pr;
 		prim.probe(t, better, r.victim_round, max_chain, pr);
-		slots[depth] = pr.slot;
-		tags[depth] = t;
-		offs[depth] = off;
-		depth++;
 		if (pr.kind == kProbeDisplace) {
+			slots[depth] = pr.slot;
+			tags[depth] = t;
+			offs[depth] = off;
+			depth++;
 			t = pr.occ.tag;
 			off = pr.occ.offset;
 			if (prim.leader())
@@ -110,6 +113,7 @@ LRZ_HD void k2_insert(P &prim, ScanState *st, CommitRegs &r, int64_t t, int64_t 
 			if (prim.leader())
 				st->st_evictions++;
 		}
+		prim.store_entry(pr.slot, t, off); // the deepest insert lands first
 		break;
 	}
 	while (depth--)
@@ -137,11 +141,17 @@ LRZ_HD int64_t k2_clean_one(P &prim, ScanState *st, CommitRegs &r, int hash_bits
 	}
 }
 
-// Process the candidates of one segment.  `last_segment` closes the chunk when the candidates run out.
-template <class P>
-LRZ_HD void k2_commit_segment(P &prim, ScanState *st, MatchRec *recs, bool last_segment)
+struct CommitConst {
+	int64_t end, n, hash_limit, rec_cap;
+	int max_chain, hash_bits, cb;
+};
+
+struct CommitCounters {
+	int64_t lookups = 0, inserts = 0, hits = 0, misses = 0;
+};
+
+LRZ_HD void k2_load_regs(const ScanState *st, CommitRegs &r, CommitConst &c)
 {
-	CommitRegs r;
 	r.hash_count = st->hash_count;
 	r.min_mask = st->min_mask;
 	r.tag_mask = st->tag_mask;
@@ -155,16 +165,99 @@ LRZ_HD void k2_commit_segment(P &prim, ScanState *st, MatchRec *recs, bool last_
 	r.n_rec = st->n_rec;
 	r.s0_len = st->s0_len;
 	r.s1_len = st->s1_len;
-	const int64_t end = st->end, n = st->n, hash_limit = st->hash_limit, rec_cap = st->rec_cap;
-	const int max_chain = st->max_chain, hash_bits = st->hash_bits, cb = st->chunk_bytes;
-	int status = st->status;
-	int64_t n_lookups = 0, n_inserts = 0, n_hits = 0, n_misses = 0;
+	c.end = st->end;
+	c.n = st->n;
+	c.hash_limit = st->hash_limit;
+	c.rec_cap = st->rec_cap;
+	c.max_chain = st->max_chain;
+	c.hash_bits = st->hash_bits;
+	c.cb = st->chunk_bytes;
+}
 
+LRZ_HD void k2_store_regs(ScanState *st, const CommitRegs &r, const CommitCounters &n, int status)
+{
+	st->hash_count = r.hash_count;
+	st->min_mask = r.min_mask;
+	st->tag_mask = r.tag_mask;
+	st->clean_ptr = r.clean_ptr;
+	st->victim_round = r.victim_round;
+	st->last_match = r.last_match;
+	st->cur_p = r.cur_p;
+	st->cur_ofs = r.cur_ofs;
+	st->cur_len = r.cur_len;
+	st->scan_pos = r.p;
+	st->n_rec = r.n_rec;
+	st->s0_len = r.s0_len;
+	st->s1_len = r.s1_len;
+	st->status = status;
+	st->st_lookups += n.lookups;
+	st->st_inserts += n.inserts;
+	st->st_tag_hits += n.hits;
+	st->st_tag_misses += n.misses;
+}
+
+// One iteration of the reference's loop body at candidate (p, t): src/rzip.c:660-688.
+// Returns true when p must be examined again: a match is emitted at the first candidate p that lies
+// 31 positions past its start; when the match ends before p the reference's loop variable moves
+// BACKWARDS to the end of the match (src/rzip.c:685) and walks up to p again, so p itself is looked up
+// and inserted a second time (no other candidate can lie in between).
+template <class P>
+LRZ_HD bool k2_step(P &prim, ScanState *st, CommitRegs &r, const CommitConst &c, CommitCounters &n, MatchRec *recs,
+		    int64_t p, int64_t t, int &status)
+{
+	int64_t mlen = 0, offset = 0, reverse = 0;
+	bool again = false;
+	r.p = p;
+	prim.publish(p, r.min_mask);
+	n.lookups++;
+	prim.lookup(t, p, c.end, r.last_match, mlen, offset, reverse, n.hits, n.misses);
+	if ((t & r.tag_mask) == r.tag_mask) {
+		n.inserts++;
+		r.hash_count++;
+		k2_insert(prim, st, r, t, p, c.max_chain);
+		if (r.hash_count > c.hash_limit)
+			r.tag_mask = k2_clean_one(prim, st, r, c.hash_bits);
+	}
+	if (mlen > r.cur_len) {
+		r.cur_p = p - reverse;
+		r.cur_len = mlen;
+		r.cur_ofs = offset;
+	}
+	if ((r.cur_len >= kGreatMatch || p >= r.cur_p + kMinMatch) && r.cur_len >= kMinMatch) {
+		if (r.n_rec + 2 > c.rec_cap) {
+			status = kStatusRecOverflow;
+			return false;
+		}
+		k2_emit_record(prim, st, r, recs, r.cur_p, r.cur_ofs, r.cur_len, c.cb, false);
+		r.last_match = r.cur_p + r.cur_len;
+		r.cur_p = r.p = r.last_match;
+		r.cur_len = 0;
+		again = r.last_match < p;
+		prim.publish(r.p, r.min_mask);
+	}
+	return again;
+}
+
+// src/rzip.c:710-711 tail literal, :759-760 terminator + CRC
+template <class P>
+LRZ_HD void k2_close_chunk(P &prim, ScanState *st, CommitRegs &r, const CommitConst &c, MatchRec *recs, int &status)
+{
+	k2_emit_record(prim, st, r, recs, c.n, 0, 0, c.cb, true);
+	r.last_match = c.n;
+	status = kStatusChunkDone;
+}
+
+// Process the candidates of one segment, strictly one after the other.  `last_segment` closes the
+// chunk when the candidates run out.
+template <class P>
+LRZ_HD void k2_commit_segment(P &prim, ScanState *st, MatchRec *recs, bool last_segment)
+{
+	CommitRegs r;
+	CommitConst c;
+	CommitCounters n;
+	k2_load_regs(st, r, c);
+	int status = st->status;
 	if (status == kStatusRunning) {
-		// A match is emitted at the first candidate p that lies 31 positions past its start; when the
-		// match ends before p the reference's loop variable moves BACKWARDS to the end of the match
-		// (src/rzip.c:685) and walks up to p again, so p itself is examined -- looked up and inserted --
-		// a second time (no other candidate can lie in between).  `again` replays it from registers.
 		int64_t p = 0, t = 0;
 		bool again = false;
 		for (;;) {
@@ -176,62 +269,15 @@ LRZ_HD void k2_commit_segment(P &prim, ScanState *st, MatchRec *recs, bool last_
 				}
 			} else if (!prim.next(r.p, r.min_mask, p, t))
 				break;
-			int64_t mlen = 0, offset = 0, reverse = 0;
-			r.p = p;
-			n_lookups++;
-			prim.lookup(t, p, end, r.last_match, mlen, offset, reverse, n_hits, n_misses);
-			if ((t & r.tag_mask) == r.tag_mask) {
-				n_inserts++;
-				r.hash_count++;
-				k2_insert(prim, st, r, t, p, max_chain);
-				if (r.hash_count > hash_limit)
-					r.tag_mask = k2_clean_one(prim, st, r, hash_bits);
-			}
-			if (mlen > r.cur_len) {
-				r.cur_p = p - reverse;
-				r.cur_len = mlen;
-				r.cur_ofs = offset;
-			}
-			if ((r.cur_len >= kGreatMatch || p >= r.cur_p + kMinMatch) && r.cur_len >= kMinMatch) {
-				if (r.n_rec + 2 > rec_cap) {
-					status = kStatusRecOverflow;
-					break;
-				}
-				k2_emit_record(prim, st, r, recs, r.cur_p, r.cur_ofs, r.cur_len, cb, false);
-				r.last_match = r.cur_p + r.cur_len;
-				r.cur_p = r.p = r.last_match;
-				r.cur_len = 0;
-				again = r.last_match < p;
-			}
+			again = k2_step(prim, st, r, c, n, recs, p, t, status);
+			if (status != kStatusRunning)
+				break;
 		}
-		if (status == kStatusRunning && last_segment) {
-			// src/rzip.c:710-711 tail literal, :759-760 terminator + CRC
-			k2_emit_record(prim, st, r, recs, n, 0, 0, cb, true);
-			r.last_match = n;
-			status = kStatusChunkDone;
-		}
+		if (status == kStatusRunning && last_segment)
+			k2_close_chunk(prim, st, r, c, recs, status);
 	}
-
-	if (prim.leader()) {
-		st->hash_count = r.hash_count;
-		st->min_mask = r.min_mask;
-		st->tag_mask = r.tag_mask;
-		st->clean_ptr = r.clean_ptr;
-		st->victim_round = r.victim_round;
-		st->last_match = r.last_match;
-		st->cur_p = r.cur_p;
-		st->cur_ofs = r.cur_ofs;
-		st->cur_len = r.cur_len;
-		st->scan_pos = r.p;
-		st->n_rec = r.n_rec;
-		st->s0_len = r.s0_len;
-		st->s1_len = r.s1_len;
-		st->status = status;
-		st->st_lookups += n_lookups;
-		st->st_inserts += n_inserts;
-		st->st_tag_hits += n_hits;
-		st->st_tag_misses += n_misses;
-	}
+	if (prim.leader())
+		k2_store_regs(st, r, n, status);
 }
 
 // Initial state for a chunk (src/rzip.c:590-626).
@@ -270,6 +316,7 @@ struct ScalarPrim {
 	int64_t tile, idx;
 
 	bool leader() const { return true; }
+	void publish(int64_t, int64_t) {}
 	void store_rec(MatchRec *dst, const MatchRec &r) { *dst = r; }
 	void store_entry(int64_t slot, int64_t t, int64_t off)
 	{

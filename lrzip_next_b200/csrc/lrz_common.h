@@ -101,6 +101,10 @@ struct ScanState {
 	int64_t st_inserts, st_tag_hits, st_tag_misses, st_lookups;
 	int64_t st_matches, st_match_bytes, st_literals, st_literal_bytes;
 	int64_t st_evictions, st_sweeps, st_displacements;
+	// commit-kernel bookkeeping: 0 batch rounds, 1 lanes committed in batches, 2 serial steps (pending match),
+	// 3 serial (needs serial logic), 4 serial (sweep wrap / window), 5 single-lane re-evaluations, 6 gate cuts,
+	// 7 rank-shift restarts, 8 clock cycles in lane evaluation, 9 cycles in serial steps, 10 total cycles
+	int64_t dbg[12];
 };
 
 enum { kStatusRunning = 0, kStatusChunkDone = 2, kStatusRecOverflow = -1 };

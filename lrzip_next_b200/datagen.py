@@ -58,16 +58,14 @@ def gen_text(size: int, seed: int = 7, nwords: int = 50000, zipf_a: float = 1.05
         ends = np.cumsum(tl)
         starts = ends - tl
         total = int(ends[-1])
-        buf = np.empty(total, dtype=np.uint8)
-        # scatter words then separators with a flat index trick
-        idx = np.arange(total, dtype=np.int64)
-        tok = np.searchsorted(ends, idx, side="right")
-        within = idx - starts[tok]
-        is_word = within < wl[tok]
-        src_w = offs[w[tok]] + within
-        src_s = sep_offs[s[tok]] + (within - wl[tok])
-        buf[is_word] = letters[src_w[is_word]]
-        buf[~is_word] = sep_cat[src_s[~is_word]]
+        # per-byte token index and offset inside the token, then gather letters / separator bytes
+        tok = np.repeat(np.arange(batch, dtype=np.int64), tl)
+        within = np.arange(total, dtype=np.int64) - np.repeat(starts, tl)
+        wl_b = np.repeat(wl, tl)
+        is_word = within < wl_b
+        src = np.where(is_word, np.repeat(offs[w], tl) + within, np.repeat(sep_offs[s], tl) + (within - wl_b))
+        buf = np.where(is_word, letters[np.minimum(src, len(letters) - 1)], sep_cat[np.minimum(src, len(sep_cat) - 1)])
+        del tok
         n = min(total, size - pos)
         out[pos:pos + n] = buf[:n]
         pos += n
@@ -144,6 +142,27 @@ def gen_vm(size: int, seed: int = 5) -> np.ndarray:
         elif k == 3:
             seg[:] = rng.integers(0, 256, size=ext, dtype=np.uint8)
     return out[:size].copy()
+
+
+def _text_block(args):
+    size, seed = args
+    return gen_text(size, seed=seed)
+
+
+def gen_text_blocks(size: int, seed: int = 7, block: int = 64 << 20, workers: int | None = None) -> np.ndarray:
+    """C2 at full size: `size` bytes of enwik-style text as independent `block`-byte pieces (seed,
+    seed+1, ...) generated in parallel worker processes -- same bytes for any worker count."""
+    import multiprocessing as mp
+    import os
+    nb = -(-size // block)
+    jobs = [(min(block, size - i * block), seed + i) for i in range(nb)]
+    workers = workers or min(nb, max(1, (os.cpu_count() or 2) - 1), 32)
+    if workers <= 1 or nb == 1:
+        parts = [_text_block(j) for j in jobs]
+    else:
+        with mp.get_context("fork").Pool(workers) as pool:
+            parts = pool.map(_text_block, jobs)
+    return np.concatenate(parts)
 
 
 GENERATORS = {
