@@ -18,10 +18,12 @@
 //     an mbarrier transaction count), double buffered, so the load of tile i+1 overlaps tile i;
 //   * phase A: thread t owns the 16 bytes of slot t, XOR-accumulates hash_index over them through a
 //     16-way replicated 64-bit table in shared memory (lanes l and l+16 are in different 64-bit
-//     phases, so lookups are bank-conflict free) and publishes the 16 running XORs xs[k][t];
+//     phases, so lookups are bank-conflict free); a shuffle XOR-scan over the slot totals turns the
+//     local prefixes into the tile-wide running XOR Z[i] = XOR_{b < i} hash_index[byte b], stored
+//     with one pad word per 16 entries so that both phases are conflict free;
 //   * phase B: transposed -- lane l of a warp takes position 32*j + l, so that the survivors of one
 //     ballot are consecutive positions and their 16-byte records form one contiguous run in HBM:
-//       tag = (X_s[15] ^ X_s[k-1]) ^ X_{s+1}[15] ^ X_{s+2}[k-2]     (s = slot, k = position & 15)
+//       tag(q) = Z[q + 31] ^ Z[q]                                   (two shared-memory reads)
 //   * warp ballots + a CTA prefix place every record; stores are 16 B per lane, contiguous per warp.
 #include "kernels.h"
 
@@ -33,15 +35,16 @@ __constant__ int64_t c_hash_index[256];
 
 static constexpr int K1_THREADS = 256;
 static constexpr int K1_WARPS = K1_THREADS / 32;
-static constexpr int K1_SLOTS = 273;                 // = 1 (mod 16): column reads are conflict free
 static constexpr int K1_IN_BYTES = kTile + 32;       // tile + halo, multiple of 16
+static constexpr int K1_Z = kTile + 32 + 1;          // running XORs Z[0..4128], Z[0] = 0
+static constexpr int K1_ZPAD = K1_Z + K1_Z / 16 + 2; // one pad word per 16 entries: conflict-free columns
 static constexpr int K1_SMEM_TABLE = 256 * 16 * 8;
-static constexpr int K1_SMEM_XS = 16 * K1_SLOTS * 8;
+static constexpr int K1_SMEM_Z = ((K1_ZPAD * 8 + 127) / 128) * 128;
 static constexpr int K1_SMEM_IN = 2 * K1_IN_BYTES;
-static constexpr int K1_OFF_XS = K1_SMEM_TABLE;
-static constexpr int K1_OFF_IN = K1_OFF_XS + K1_SMEM_XS;
+static constexpr int K1_OFF_Z = K1_SMEM_TABLE;
+static constexpr int K1_OFF_IN = K1_OFF_Z + K1_SMEM_Z;
 static constexpr int K1_OFF_WSUM = K1_OFF_IN + K1_SMEM_IN;
-static constexpr int K1_OFF_BAR = K1_OFF_WSUM + 64;
+static constexpr int K1_OFF_BAR = K1_OFF_WSUM + 128;
 static constexpr int K1_SMEM = K1_OFF_BAR + 32;
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -70,9 +73,47 @@ __device__ __forceinline__ void tma_load_1d(void *dst, const void *src, unsigned
 		     ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
 
-__device__ __forceinline__ void st_cand(Cand *dst, int64_t pos, int64_t tag)
+__device__ __forceinline__ void st_cand(Cand *dst, int64_t pos, uint32_t tlo, uint32_t thi)
 {
-	asm volatile("st.global.cs.v2.u64 [%0], {%1,%2};" ::"l"(dst), "l"(pos), "l"(tag) : "memory");
+	asm volatile("{\n\t.reg .b64 t;\n\tmov.b64 t, {%2,%3};\n\tst.global.cs.v2.u64 [%0], {%1,t};\n\t}"
+		     ::"l"(dst), "l"(pos), "r"(tlo), "r"(thi) : "memory");
+}
+
+__device__ __forceinline__ uint64_t shfl_up64(uint64_t v, int d)
+{
+	const uint32_t lo = __shfl_up_sync(0xffffffffu, (uint32_t)v, d);
+	const uint32_t hi = __shfl_up_sync(0xffffffffu, (uint32_t)(v >> 32), d);
+	return ((uint64_t)hi << 32) | lo;
+}
+
+__device__ __forceinline__ int zidx(int j) { return j + (j >> 4); }
+
+// tag(q) = Z[q + 31] ^ Z[q] with Z the running XOR of hash_index over the tile's bytes (Z[0] = 0).
+template <bool kInterior>
+__device__ __forceinline__ void k1_phase_b(const uint64_t *__restrict__ z, int warp, int lane, int64_t base, int64_t lo,
+					   int64_t hi, uint32_t mlo, uint32_t mhi, uint32_t tags_lo[16], uint32_t tags_hi[16],
+					   uint32_t ballots[16], uint32_t &wtotal)
+{
+	const int q0 = warp * 512 + lane;
+	const uint64_t *za = z + zidx(q0), *zb = z + zidx(q0 + 31);
+	// lo / hi as offsets inside the tile (only used when the tile straddles the valid range)
+	const int l0 = (int)(lo - base), h0 = (int)(hi - base);
+	wtotal = 0;
+#pragma unroll
+	for (int j = 0; j < 16; j++) {
+		// 32 positions further = 34 padded words further
+		const uint64_t tg = za[34 * j] ^ zb[34 * j];
+		const uint32_t tl = (uint32_t)tg, th = (uint32_t)(tg >> 32);
+		tags_lo[j] = tl;
+		tags_hi[j] = th;
+		bool ok = (tl & mlo) == mlo && (th & mhi) == mhi;
+		if (!kInterior) {
+			const int q = q0 + 32 * j;
+			ok = ok && q >= l0 && q < h0;
+		}
+		ballots[j] = __ballot_sync(0xffffffffu, ok);
+		wtotal += __popc(ballots[j]);
+	}
 }
 
 __global__ void __launch_bounds__(K1_THREADS, 2)
@@ -81,10 +122,11 @@ k1_tagscan_kernel(const uint8_t *__restrict__ buf, int64_t n, int64_t pos_lo, in
 		  int64_t first_tile, int64_t num_tiles)
 {
 	extern __shared__ __align__(128) uint8_t smem[];
-	uint64_t *tab = reinterpret_cast<uint64_t *>(smem);                 // tab[b * 16 + (lane & 15)]
-	uint64_t *xs = reinterpret_cast<uint64_t *>(smem + K1_OFF_XS);      // xs[k * K1_SLOTS + slot]
+	uint64_t *tab = reinterpret_cast<uint64_t *>(smem);                // tab[b * 16 + (lane & 15)]
+	uint64_t *z = reinterpret_cast<uint64_t *>(smem + K1_OFF_Z);       // padded running XORs
 	uint8_t *in = smem + K1_OFF_IN;
-	uint32_t *wsum = reinterpret_cast<uint32_t *>(smem + K1_OFF_WSUM);
+	uint64_t *wxor = reinterpret_cast<uint64_t *>(smem + K1_OFF_WSUM); // per-warp XOR totals (8) + halo (2)
+	uint32_t *wsum = reinterpret_cast<uint32_t *>(smem + K1_OFF_WSUM + 96);
 	uint64_t *bar = reinterpret_cast<uint64_t *>(smem + K1_OFF_BAR);
 
 	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -98,23 +140,22 @@ k1_tagscan_kernel(const uint8_t *__restrict__ buf, int64_t n, int64_t pos_lo, in
 			return;
 		}
 	}
+	const uint32_t mlo = (uint32_t)mask, mhi = (uint32_t)((uint64_t)mask >> 32);
 
 	for (int i = tid; i < 256 * 16; i += K1_THREADS)
 		tab[i] = (uint64_t)c_hash_index[i >> 4];
 	if (tid == 0) {
+		z[0] = 0;
 		mbar_init(&bar[0], 1);
 		mbar_init(&bar[1], 1);
 		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 	}
 	__syncthreads();
 
-	const int64_t end = n - kMinMatch; // last examined position (src/rzip.c:622, 631-634)
+	// valid positions: [max(pos_lo, 1), min(pos_hi, n - 31 + 1))   (src/rzip.c:622, 631-634)
+	const int64_t vlo = pos_lo > 1 ? pos_lo : 1;
+	const int64_t vhi = (pos_hi < n - kMinMatch + 1) ? pos_hi : n - kMinMatch + 1;
 	const uint64_t *my_tab = tab + (lane & 15);
-	const int k = lane & 15, half = lane >> 4;
-	// row indices of the three partial XORs of a 31-byte window that starts at offset k of its slot
-	const int row_b = (k >= 1) ? (k - 1) : 0;
-	const int row_c = (k == 0) ? 14 : 15;
-	const int row_d = (k >= 2) ? (k - 2) : 0;
 
 	int64_t t = blockIdx.x;
 	if (t < num_tiles && tid == 0) {
@@ -133,7 +174,8 @@ k1_tagscan_kernel(const uint8_t *__restrict__ buf, int64_t n, int64_t pos_lo, in
 		}
 		mbar_wait(&bar[stage], parity);
 
-		// ---- phase A: per-slot running XORs
+		// ---- phase A: running XOR of hash_index over the tile (+ halo): local prefix, CTA scan, publish
+		uint64_t x[16];
 		{
 			const uint4 v = *reinterpret_cast<const uint4 *>(in + stage * K1_IN_BYTES + tid * 16);
 			const uint32_t w[4] = { v.x, v.y, v.z, v.w };
@@ -142,44 +184,66 @@ k1_tagscan_kernel(const uint8_t *__restrict__ buf, int64_t n, int64_t pos_lo, in
 			for (int j = 0; j < 16; j++) {
 				const uint32_t b = (w[j >> 2] >> ((j & 3) * 8)) & 0xffu;
 				acc ^= my_tab[b * 16];
-				xs[j * K1_SLOTS + tid] = acc;
+				x[j] = acc;
 			}
-			if (tid < 2) { // halo slots 256, 257
-				const uint4 hv = *reinterpret_cast<const uint4 *>(in + stage * K1_IN_BYTES + (K1_THREADS + tid) * 16);
-				const uint32_t hw[4] = { hv.x, hv.y, hv.z, hv.w };
-				uint64_t hacc = 0;
+		}
+		uint64_t hx[16]; // halo slots 256, 257 (threads 0, 1)
+		if (tid < 2) {
+			const uint4 hv = *reinterpret_cast<const uint4 *>(in + stage * K1_IN_BYTES + (K1_THREADS + tid) * 16);
+			const uint32_t hw[4] = { hv.x, hv.y, hv.z, hv.w };
+			uint64_t hacc = 0;
 #pragma unroll
-				for (int j = 0; j < 16; j++) {
-					const uint32_t b = (hw[j >> 2] >> ((j & 3) * 8)) & 0xffu;
-					hacc ^= my_tab[b * 16];
-					xs[j * K1_SLOTS + K1_THREADS + tid] = hacc;
-				}
+			for (int j = 0; j < 16; j++) {
+				const uint32_t b = (hw[j >> 2] >> ((j & 3) * 8)) & 0xffu;
+				hacc ^= my_tab[b * 16];
+				hx[j] = hacc;
 			}
+			wxor[K1_WARPS + tid] = hacc;
+		}
+		uint64_t incl = x[15]; // inclusive XOR scan of the slot totals inside the warp
+#pragma unroll
+		for (int d = 1; d < 32; d <<= 1) {
+			const uint64_t o = shfl_up64(incl, d);
+			if (lane >= d)
+				incl ^= o;
+		}
+		if (lane == 31)
+			wxor[warp] = incl;
+		__syncthreads();
+		uint64_t off = incl ^ x[15]; // exclusive
+#pragma unroll
+		for (int w = 0; w < K1_WARPS; w++)
+			if (w < warp)
+				off ^= wxor[w];
+		{
+			uint64_t *dst = z + 1 + tid * 16;
+			const int pad = (tid * 16 + 1) >> 4; // = tid
+#pragma unroll
+			for (int j = 0; j < 16; j++)
+				dst[pad + (j == 15 ? 1 : 0) + j] = off ^ x[j];
+		}
+		if (tid < 2) {
+			uint64_t hoff = 0;
+#pragma unroll
+			for (int w = 0; w < K1_WARPS; w++)
+				hoff ^= wxor[w];
+			if (tid == 1)
+				hoff ^= wxor[K1_WARPS];
+#pragma unroll
+			for (int j = 0; j < 16; j++)
+				z[zidx(1 + (K1_THREADS + tid) * 16 + j)] = hoff ^ hx[j];
 		}
 		__syncthreads();
 
-		// ---- phase B: tags of positions base + warp*512 + 32*j + lane
-		uint64_t tags[16];
-		uint32_t ballots[16];
-		uint32_t wtotal = 0;
-		const int64_t q0 = base + warp * 512 + lane;
-#pragma unroll
-		for (int j = 0; j < 16; j++) {
-			const int s = warp * 32 + 2 * j + half;
-			uint64_t tg = xs[15 * K1_SLOTS + s] ^ xs[row_c * K1_SLOTS + s + 1];
-			if (k >= 1)
-				tg ^= xs[row_b * K1_SLOTS + s];
-			if (k >= 2)
-				tg ^= xs[row_d * K1_SLOTS + s + 2];
-			tags[j] = tg;
-			const int64_t p = q0 + 32 * j;
-			const bool ok = p >= pos_lo && p < pos_hi && p >= 1 && p <= end && (tg & (uint64_t)mask) == (uint64_t)mask;
-			ballots[j] = __ballot_sync(0xffffffffu, ok);
-			wtotal += __popc(ballots[j]);
-		}
+		// ---- phase B: tags of positions base + warp*512 + 32*j + lane, survivors by ballot
+		uint32_t tags_lo[16], tags_hi[16], ballots[16], wtotal;
+		if (base >= vlo && base + kTile <= vhi)
+			k1_phase_b<true>(z, warp, lane, base, vlo, vhi, mlo, mhi, tags_lo, tags_hi, ballots, wtotal);
+		else
+			k1_phase_b<false>(z, warp, lane, base, vlo, vhi, mlo, mhi, tags_lo, tags_hi, ballots, wtotal);
 		if (lane == 0)
 			wsum[warp] = wtotal;
-		__syncthreads(); // also: every read of xs / in[stage] is done before they are overwritten
+		__syncthreads(); // also: every read of z / in[stage] is done before they are overwritten
 		uint32_t woff = 0, total = 0;
 #pragma unroll
 		for (int w = 0; w < K1_WARPS; w++) {
@@ -189,16 +253,16 @@ k1_tagscan_kernel(const uint8_t *__restrict__ buf, int64_t n, int64_t pos_lo, in
 		}
 		Cand *dst = cand + t * (int64_t)kTile + woff;
 		const uint32_t lt = (1u << lane) - 1;
+		const int64_t q0 = base + warp * 512 + lane;
 #pragma unroll
 		for (int j = 0; j < 16; j++) {
 			const uint32_t bm = ballots[j];
 			if ((bm >> lane) & 1)
-				st_cand(dst + __popc(bm & lt), q0 + 32 * j, (int64_t)tags[j]);
+				st_cand(dst + __popc(bm & lt), q0 + 32 * j, tags_lo[j], tags_hi[j]);
 			dst += __popc(bm);
 		}
 		if (tid == 0)
 			tile_count[t] = total;
-		__syncthreads(); // wsum reuse
 	}
 }
 
