@@ -1,0 +1,1368 @@
+// lzma_enc.cuh -- LZMA block encoder for the lrzip-next LZMA backend, one encoder instance per
+// stream block (src/stream.c:429-494 lzma_compress_buf -> src/lzma/C/LzmaLib.c:12 LzmaCompress).
+//
+// Bit-exactness target: the raw LZMA stream LzmaCompress() writes for (level, dictSize, lc3 lp0 pb2,
+// fb, numThreads = 2), i.e. the vendored 7-Zip SDK 24.07 encoder in "optimal" mode (levels 5-9)
+// over its two-thread match finder.  What is restated here, piece by piece:
+//
+//   match finder    binary tree over 4-byte hashes with cut value mc        LzFind.c:962-1029
+//                   driven per position like the BT thread does             LzFindMt.c:571-729
+//                   2/3-byte hash candidates mixed in front of the tree's   LzFindMt.c:1093-1131,
+//                   pairs only when nearer than the first tree match          1274-1317, 1340-1350
+//                   (LzFindOpt.c's long-match shortcut is equivalent to the plain tree step)
+//   range coder     32-bit range, 11-bit adaptive probabilities, shift 5    LzmaEnc.c:685-826
+//   price tables    4-bit fixed-point prices, refreshed every 64 matches /  LzmaEnc.c:830-1065,
+//                   64 rep lengths                                            2202-2319, 2645-2657
+//   optimal parser  price-based DP over up to 2048 positions, 4 reps,       LzmaEnc.c:1219-1968
+//                   12-state machine, LIT/REP/MATCH + "x : LIT : REP0" trials
+//   block loop      first byte literal, symbol coding, flush of 5 bytes     LzmaEnc.c:2383-2680
+//
+// The same source is compiled for the device (product: one encoder per CUDA block, see
+// backend_lzma.cu) and for the host (tests/hostsim only: lets the CPU-only container check the
+// restatement against the reference's own LzmaCompress before a GPU is involved).
+#pragma once
+#include <stdint.h>
+#include <string.h>
+#include <stddef.h>
+
+#if defined(__CUDACC__)
+#define LZ_FN __host__ __device__
+#define LZ_INL __host__ __device__ __forceinline__
+#else
+#define LZ_FN
+#define LZ_INL inline
+#endif
+
+namespace lrz {
+namespace lzma {
+
+constexpr uint32_t kNumReps = 4;
+constexpr uint32_t kNumOpts = 1u << 11;
+constexpr uint32_t kNumStates = 12;
+constexpr uint32_t kMatchMin = 2;
+constexpr uint32_t kMatchMax = 273;
+constexpr uint32_t kNumPosStatesMax = 16;
+constexpr uint32_t kLenLow = 8, kLenHigh = 256, kLenTotal = kLenLow * 2 + kLenHigh;
+constexpr uint32_t kNumLenToPos = 4;
+constexpr uint32_t kNumAlignBits = 4, kAlignSize = 16, kAlignMask = 15;
+constexpr uint32_t kStartPosModel = 4, kEndPosModel = 14, kNumFullDist = 1u << (kEndPosModel >> 1); // 128
+constexpr uint32_t kDistTableMax = 64;
+constexpr uint32_t kBitModelTotal = 1u << 11;
+constexpr uint32_t kProbInit = kBitModelTotal >> 1;
+constexpr uint32_t kMoveBits = 5;
+constexpr uint32_t kMoveReducingBits = 4;
+constexpr uint32_t kPriceShift = 4;
+constexpr uint32_t kInfinity = 1u << 30;
+constexpr uint32_t kTopValue = 1u << 24;
+constexpr uint32_t kMarkLit = 0xFFFFFFFFu;
+constexpr int kRepLenCount = 64;
+constexpr uint32_t kHash2Size = 1u << 10, kHash3Size = 1u << 16;
+
+typedef uint16_t Prob;
+
+struct LenProbs {
+	Prob low[kNumPosStatesMax << 4]; // per posState: 16 probs (choice bits live in low[0], low[8])
+	Prob high[kLenHigh];
+};
+
+struct LenPrices {
+	uint32_t tableSize;
+	uint32_t prices[kNumPosStatesMax][kLenTotal];
+};
+
+struct Opt {
+	uint32_t price;
+	uint16_t state;
+	uint16_t extra; // 0 normal, 1 LIT : MATCH, >1 MATCH(extra-1) : LIT : REP0(len)
+	uint32_t len;
+	uint32_t dist;
+	uint32_t reps[kNumReps];
+};
+
+// Everything one block encoder owns besides the match-finder arrays; lives in HBM (device) / heap (host).
+struct Enc {
+	// ---- configuration
+	const uint8_t *src;
+	uint32_t n;
+	uint32_t fb, mc, historySize, cyclicSize, hashMask, bigHash, distTableSize;
+	uint32_t pbMask, lpMask, lc;
+	// ---- match finder (positions are 1-based: byte i has pos i + 1; 0 = empty)
+	uint32_t *hash2, *hash3, *hash4, *son;
+	uint32_t pos;       // position the match finder will hand out next
+	uint32_t cycPos;
+	uint32_t crc[256];
+	// ---- range coder
+	uint64_t low, cacheSize;
+	uint32_t range, cache;
+	uint8_t *out;
+	uint64_t outPos, outCap;
+	int overflow;
+	// ---- coder state
+	uint32_t state, reps[kNumReps];
+	uint32_t optCur, optEnd, longestMatchLen, numPairs, numAvail, additionalOffset, backRes, matchPriceCount;
+	int repLenCounter;
+	uint32_t probPrices[kBitModelTotal >> kMoveReducingBits];
+	uint32_t matches[kMatchMax * 2 + 2];
+	uint32_t alignPrices[kAlignSize];
+	uint32_t posSlotPrices[kNumLenToPos][kDistTableMax];
+	uint32_t distPrices[kNumLenToPos][kNumFullDist];
+	Prob posAlign[kAlignSize];
+	Prob isRep[kNumStates], isRepG0[kNumStates], isRepG1[kNumStates], isRepG2[kNumStates];
+	Prob isMatch[kNumStates][kNumPosStatesMax], isRep0Long[kNumStates][kNumPosStatesMax];
+	Prob posSlot[kNumLenToPos][64];
+	Prob posEnc[kNumFullDist];
+	LenProbs lenProbs, repLenProbs;
+	LenPrices lenPrices, repLenPrices;
+	Prob lit[0x300 << 4]; // lc + lp <= 4 supported (lrzip-next uses lc3 lp0)
+	Opt opt[kNumOpts];
+};
+
+// ---------------------------------------------------------------------------------------------------
+// small helpers
+LZ_INL uint32_t top_bit(uint32_t v)
+{
+#if defined(__CUDA_ARCH__)
+	return 31u - (uint32_t)__clz((int)v);
+#else
+	return 31u - (uint32_t)__builtin_clz(v);
+#endif
+}
+
+LZ_INL uint32_t pos_slot(uint32_t d) // GetPosSlot (LzmaEnc.c:167-246): 2*log2 + next bit
+{
+	if (d < 2)
+		return d;
+	const uint32_t b = top_bit(d);
+	return 2 * b + ((d >> (b - 1)) & 1);
+}
+
+LZ_INL bool is_lit_state(uint32_t s) { return s < 7; }
+LZ_INL uint32_t st_lit(uint32_t s) { return s < 4 ? 0 : (s < 10 ? s - 3 : s - 6); }   // kLiteralNextStates
+LZ_INL uint32_t st_match(uint32_t s) { return s < 7 ? 7 : 10; }                         // kMatchNextStates
+LZ_INL uint32_t st_rep(uint32_t s) { return s < 7 ? 8 : 11; }                           // kRepNextStates
+LZ_INL uint32_t st_shortrep(uint32_t s) { return s < 7 ? 9 : 11; }                      // kShortRepNextStates
+
+LZ_INL uint32_t price_bit(const Enc *e, uint32_t prob, uint32_t bit)
+{
+	return e->probPrices[(prob ^ ((0u - bit) & (kBitModelTotal - 1))) >> kMoveReducingBits];
+}
+LZ_INL uint32_t price0(const Enc *e, uint32_t prob) { return e->probPrices[prob >> kMoveReducingBits]; }
+LZ_INL uint32_t price1(const Enc *e, uint32_t prob) { return e->probPrices[(prob ^ (kBitModelTotal - 1)) >> kMoveReducingBits]; }
+
+// ---------------------------------------------------------------------------------------------------
+// range coder (LzmaEnc.c:685-760)
+LZ_INL void rc_put(Enc *e, uint8_t b)
+{
+	if (e->outPos < e->outCap)
+		e->out[e->outPos] = b;
+	else
+		e->overflow = 1;
+	e->outPos++;
+}
+
+LZ_FN inline void rc_shift_low(Enc *e)
+{
+	const uint32_t low = (uint32_t)e->low;
+	const uint32_t high = (uint32_t)(e->low >> 32);
+	e->low = (uint32_t)(low << 8);
+	if (low < 0xFF000000u || high != 0) {
+		rc_put(e, (uint8_t)(e->cache + high));
+		e->cache = low >> 24;
+		if (e->cacheSize == 0)
+			return;
+		const uint8_t fill = (uint8_t)(high + 0xFF);
+		do
+			rc_put(e, fill);
+		while (--e->cacheSize);
+		return;
+	}
+	e->cacheSize++;
+}
+
+LZ_INL void rc_norm(Enc *e)
+{
+	if (e->range < kTopValue) {
+		e->range <<= 8;
+		rc_shift_low(e);
+	}
+}
+
+LZ_INL void rc_bit(Enc *e, Prob *prob, uint32_t bit)
+{
+	const uint32_t p = *prob;
+	const uint32_t bound = (e->range >> 11) * p;
+	if (bit == 0) {
+		e->range = bound;
+		*prob = (Prob)(p + ((kBitModelTotal - p) >> kMoveBits));
+	} else {
+		e->low += bound;
+		e->range -= bound;
+		*prob = (Prob)(p - (p >> kMoveBits));
+	}
+	rc_norm(e);
+}
+
+LZ_INL void rc_direct(Enc *e, uint32_t value, uint32_t nbits) // most significant bit first
+{
+	while (nbits--) {
+		e->range >>= 1;
+		if ((value >> nbits) & 1)
+			e->low += e->range;
+		rc_norm(e);
+	}
+}
+
+LZ_FN inline void lit_encode(Enc *e, Prob *probs, uint32_t sym)
+{
+	sym |= 0x100;
+	do {
+		rc_bit(e, probs + (sym >> 8), (sym >> 7) & 1);
+		sym <<= 1;
+	} while (sym < 0x10000);
+}
+
+LZ_FN inline void lit_encode_matched(Enc *e, Prob *probs, uint32_t sym, uint32_t matchByte)
+{
+	uint32_t offs = 0x100;
+	sym |= 0x100;
+	do {
+		matchByte <<= 1;
+		Prob *prob = probs + (offs + (matchByte & offs) + (sym >> 8));
+		const uint32_t bit = (sym >> 7) & 1;
+		sym <<= 1;
+		offs &= ~(matchByte ^ sym);
+		rc_bit(e, prob, bit);
+	} while (sym < 0x10000);
+}
+
+LZ_FN inline void rc_reverse(Enc *e, Prob *probs, uint32_t nbits, uint32_t sym)
+{
+	uint32_t m = 1;
+	do {
+		const uint32_t bit = sym & 1;
+		sym >>= 1;
+		rc_bit(e, probs + m, bit);
+		m = (m << 1) | bit;
+	} while (--nbits);
+}
+
+// LenEnc_Encode (LzmaEnc.c:928-960)
+LZ_FN inline void len_encode(Enc *e, LenProbs *lp, uint32_t sym, uint32_t posState)
+{
+	Prob *probs = lp->low;
+	if (sym >= kLenLow) {
+		rc_bit(e, probs, 1);
+		probs += kLenLow;
+		if (sym >= kLenLow * 2) {
+			rc_bit(e, probs, 1);
+			lit_encode(e, lp->high, sym - kLenLow * 2);
+			return;
+		}
+		sym -= kLenLow;
+	}
+	rc_bit(e, probs, 0);
+	probs += posState << 4;
+	uint32_t bit = sym >> 2;
+	rc_bit(e, probs + 1, bit);
+	uint32_t m = 2 + bit;
+	bit = (sym >> 1) & 1;
+	rc_bit(e, probs + m, bit);
+	m = (m << 1) + bit;
+	rc_bit(e, probs + m, sym & 1);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// prices
+LZ_FN inline void init_prob_prices(uint32_t *pp) // LzmaEnc_InitPriceTables (LzmaEnc.c:830-852)
+{
+	for (uint32_t i = 0; i < (kBitModelTotal >> kMoveReducingBits); i++) {
+		uint32_t w = (i << kMoveReducingBits) + (1u << (kMoveReducingBits - 1));
+		uint32_t bits = 0;
+		for (uint32_t j = 0; j < kPriceShift; j++) {
+			w = w * w;
+			bits <<= 1;
+			while (w >= (1u << 16)) {
+				w >>= 1;
+				bits++;
+			}
+		}
+		pp[i] = (11u << kPriceShift) - 15 - bits;
+	}
+}
+
+LZ_FN inline uint32_t lit_price(const Enc *e, const Prob *probs, uint32_t sym)
+{
+	uint32_t price = 0;
+	sym |= 0x100;
+	do {
+		const uint32_t bit = sym & 1;
+		sym >>= 1;
+		price += price_bit(e, probs[sym], bit);
+	} while (sym >= 2);
+	return price;
+}
+
+LZ_FN inline uint32_t lit_price_matched(const Enc *e, const Prob *probs, uint32_t sym, uint32_t matchByte)
+{
+	uint32_t price = 0, offs = 0x100;
+	sym |= 0x100;
+	do {
+		matchByte <<= 1;
+		price += price_bit(e, probs[offs + (matchByte & offs) + (sym >> 8)], (sym >> 7) & 1);
+		sym <<= 1;
+		offs &= ~(matchByte ^ sym);
+	} while (sym < 0x10000);
+	return price;
+}
+
+LZ_INL const Prob *lit_probs(const Enc *e, uint32_t pos, uint32_t prevByte)
+{
+	return e->lit + 3u * ((((pos << 8) + prevByte) & e->lpMask) << e->lc);
+}
+
+LZ_FN inline void set_prices_3(const Enc *e, const Prob *probs, uint32_t start, uint32_t *prices)
+{
+	for (uint32_t i = 0; i < 8; i += 2) {
+		uint32_t price = start;
+		price += price_bit(e, probs[1], i >> 2);
+		price += price_bit(e, probs[2 + (i >> 2)], (i >> 1) & 1);
+		const uint32_t prob = probs[4 + (i >> 1)];
+		prices[i] = price + price0(e, prob);
+		prices[i + 1] = price + price1(e, prob);
+	}
+}
+
+// LenPriceEnc_UpdateTables (LzmaEnc.c:979-1065)
+LZ_FN inline void len_update_prices(const Enc *e, LenPrices *lp, uint32_t numPosStates, const LenProbs *enc)
+{
+	uint32_t b;
+	{
+		const uint32_t prob = enc->low[0];
+		b = price1(e, prob);
+		const uint32_t a = price0(e, prob);
+		const uint32_t c = b + price0(e, enc->low[kLenLow]);
+		for (uint32_t ps = 0; ps < numPosStates; ps++) {
+			uint32_t *prices = lp->prices[ps];
+			const Prob *probs = enc->low + (ps << 4);
+			set_prices_3(e, probs, a, prices);
+			set_prices_3(e, probs + kLenLow, c, prices + kLenLow);
+		}
+	}
+	uint32_t i = lp->tableSize;
+	if (i > kLenLow * 2) {
+		const Prob *probs = enc->high;
+		uint32_t *prices = lp->prices[0] + kLenLow * 2;
+		i -= kLenLow * 2 - 1;
+		i >>= 1;
+		b += price1(e, enc->low[kLenLow]);
+		do {
+			uint32_t sym = --i + (1u << 7);
+			uint32_t price = b;
+			do {
+				const uint32_t bit = sym & 1;
+				sym >>= 1;
+				price += price_bit(e, probs[sym], bit);
+			} while (sym >= 2);
+			const uint32_t prob = probs[i + (1u << 7)];
+			prices[i * 2] = price + price0(e, prob);
+			prices[i * 2 + 1] = price + price1(e, prob);
+		} while (i);
+		const uint32_t num = lp->tableSize - kLenLow * 2;
+		for (uint32_t ps = 1; ps < numPosStates; ps++)
+			for (uint32_t k = 0; k < num; k++)
+				lp->prices[ps][kLenLow * 2 + k] = lp->prices[0][kLenLow * 2 + k];
+	}
+}
+
+LZ_FN inline void fill_align_prices(Enc *e) // LzmaEnc.c:2202-2222
+{
+	const Prob *probs = e->posAlign;
+	for (uint32_t i = 0; i < kAlignSize / 2; i++) {
+		uint32_t price = 0, sym = i, m = 1, bit;
+		for (int k = 0; k < 3; k++) {
+			bit = sym & 1;
+			sym >>= 1;
+			price += price_bit(e, probs[m], bit);
+			m = (m << 1) + bit;
+		}
+		const uint32_t prob = probs[m];
+		e->alignPrices[i] = price + price0(e, prob);
+		e->alignPrices[i + 8] = price + price1(e, prob);
+	}
+}
+
+LZ_FN inline void fill_distance_prices(Enc *e) // LzmaEnc.c:2225-2319
+{
+	uint32_t temp[kNumFullDist];
+	e->matchPriceCount = 0;
+	for (uint32_t i = kStartPosModel / 2; i < kNumFullDist / 2; i++) {
+		const uint32_t slot = pos_slot(i);
+		uint32_t footer = (slot >> 1) - 1;
+		uint32_t base = (2 | (slot & 1)) << footer;
+		const Prob *probs = e->posEnc + (size_t)base * 2;
+		uint32_t price = 0, m = 1, sym = i;
+		const uint32_t offset = 1u << footer;
+		base += i;
+		while (footer) {
+			const uint32_t bit = sym & 1;
+			sym >>= 1;
+			price += price_bit(e, probs[m], bit);
+			m = (m << 1) + bit;
+			footer--;
+		}
+		const uint32_t prob = probs[m];
+		temp[base] = price + price0(e, prob);
+		temp[base + offset] = price + price1(e, prob);
+	}
+	for (uint32_t lps = 0; lps < kNumLenToPos; lps++) {
+		const uint32_t half = (e->distTableSize + 1) >> 1;
+		uint32_t *sp = e->posSlotPrices[lps];
+		const Prob *probs = e->posSlot[lps];
+		for (uint32_t slot = 0; slot < half; slot++) {
+			uint32_t sym = slot + (1u << 5), price = 0;
+			for (int k = 0; k < 5; k++) {
+				const uint32_t bit = sym & 1;
+				sym >>= 1;
+				price += price_bit(e, probs[sym], bit);
+			}
+			const uint32_t prob = probs[slot + (1u << 5)];
+			sp[slot * 2] = price + price0(e, prob);
+			sp[slot * 2 + 1] = price + price1(e, prob);
+		}
+		uint32_t delta = ((kEndPosModel / 2 - 1) - kNumAlignBits) << kPriceShift;
+		for (uint32_t slot = kEndPosModel / 2; slot < half; slot++) {
+			sp[slot * 2] += delta;
+			sp[slot * 2 + 1] += delta;
+			delta += 1u << kPriceShift;
+		}
+		uint32_t *dp = e->distPrices[lps];
+		dp[0] = sp[0];
+		dp[1] = sp[1];
+		dp[2] = sp[2];
+		dp[3] = sp[3];
+		for (uint32_t i = 4; i < kNumFullDist; i += 2) {
+			const uint32_t slotPrice = sp[pos_slot(i)];
+			dp[i] = slotPrice + temp[i];
+			dp[i + 1] = slotPrice + temp[i + 1];
+		}
+	}
+}
+
+// ---------------------------------------------------------------------------------------------------
+// match finder
+LZ_INL const uint8_t *mf_cur(const Enc *e) { return e->src + (e->pos - 1); }
+LZ_INL uint32_t mf_avail(const Enc *e) { return e->n - (e->pos - 1); }
+
+// One step of the binary tree for the position e->pos (GetMatchesSpec1 with maxLen = 3): returns the
+// number of uint32 written to d (pairs len, dist-1; len >= 4, strictly increasing).
+LZ_FN inline uint32_t mf_tree_step(Enc *e, uint32_t *d)
+{
+	const uint32_t avail = mf_avail(e);
+	if (avail < 4)
+		return 0; // the last three positions are not searched and not inserted (LzFindMt.c:627-642)
+	const uint8_t *cur = mf_cur(e);
+	const uint32_t pos = e->pos;
+	uint32_t hv;
+	if (e->bigHash) // GetHeads4b (LzFindMt.c:386-394)
+		hv = (e->crc[cur[0]] & e->hashMask) ^ ((uint32_t)cur[1] | ((uint32_t)cur[2] << 8) | ((uint32_t)cur[3] << 16));
+	else            // GetHeads4 (LzFindMt.c:368-384) == HASH4_CALC (LzFind.c:49)
+		hv = (e->crc[cur[0]] ^ cur[1] ^ ((uint32_t)cur[2] << 8) ^ (e->crc[cur[3]] << 5)) & e->hashMask;
+	uint32_t curMatch = e->hash4[hv];
+	e->hash4[hv] = pos;
+	const uint32_t lenLimit = avail < e->fb ? avail : e->fb;
+	const uint32_t cyc = e->cycPos, cbs = e->cyclicSize;
+	uint32_t *son = e->son;
+	uint32_t *ptr0 = son + ((size_t)cyc << 1) + 1, *ptr1 = son + ((size_t)cyc << 1);
+	uint32_t len0 = 0, len1 = 0, maxLen = 3, cut = e->mc, nd = 0;
+	const uint32_t cmCheck = pos <= cbs ? 0 : pos - cbs;
+	if (cmCheck < curMatch) {
+		do {
+			const uint32_t delta = pos - curMatch;
+			uint32_t *pair = son + ((size_t)(cyc - delta + (delta > cyc ? cbs : 0)) << 1);
+			const uint8_t *pb = cur - delta;
+			uint32_t len = len0 < len1 ? len0 : len1;
+			const uint32_t pair0 = pair[0];
+			if (pb[len] == cur[len]) {
+				while (++len != lenLimit)
+					if (pb[len] != cur[len])
+						break;
+				if (maxLen < len) {
+					maxLen = len;
+					d[nd++] = len;
+					d[nd++] = delta - 1;
+					if (len == lenLimit) {
+						*ptr1 = pair0;
+						*ptr0 = pair[1];
+						return nd;
+					}
+				}
+			}
+			if (pb[len] < cur[len]) {
+				*ptr1 = curMatch;
+				curMatch = pair[1];
+				ptr1 = pair + 1;
+				len1 = len;
+			} else {
+				*ptr0 = curMatch;
+				curMatch = pair0;
+				ptr0 = pair;
+				len0 = len;
+			}
+		} while (--cut && cmCheck < curMatch);
+	}
+	*ptr0 = *ptr1 = 0;
+	return nd;
+}
+
+LZ_INL void mf_advance(Enc *e)
+{
+	e->pos++;
+	if (++e->cycPos == e->cyclicSize)
+		e->cycPos = 0;
+}
+
+LZ_INL void mf_hash23(const Enc *e, const uint8_t *cur, uint32_t &h2, uint32_t &h3)
+{
+	const uint32_t t = e->crc[cur[0]] ^ cur[1];
+	h2 = t & (kHash2Size - 1);
+	h3 = (t ^ ((uint32_t)cur[2] << 8)) & (kHash3Size - 1);
+}
+
+// MatchFinderMt_GetMatches + MixMatches3 (LzFindMt.c:1274-1317, 1093-1131)
+LZ_FN inline uint32_t mf_get_matches(Enc *e, uint32_t *d)
+{
+	uint32_t bt[2 * (kMatchMax + 1)];
+	const uint32_t nbt = mf_tree_step(e, bt);
+	const uint32_t availAfter = mf_avail(e) - 1;
+	const uint8_t *cur = mf_cur(e);
+	const uint32_t m = e->pos;
+	uint32_t nd = 0;
+	bool mix = false;
+	uint32_t minPos = 0;
+	if (nbt == 0) {
+		if (availAfter >= 3) {
+			mix = true;
+			minPos = m > e->historySize ? m - e->historySize : 1;
+		}
+	} else {
+		mix = true;
+		minPos = m - bt[1];
+	}
+	if (mix) {
+		uint32_t h2, h3;
+		mf_hash23(e, cur, h2, h3);
+		const uint32_t c2 = e->hash2[h2], c3 = e->hash3[h3];
+		e->hash2[h2] = m;
+		e->hash3[h3] = m;
+		bool done = false;
+		if (c2 >= minPos && cur[(ptrdiff_t)c2 - (ptrdiff_t)m] == cur[0]) {
+			d[nd + 1] = m - c2 - 1;
+			if (cur[(ptrdiff_t)c2 - (ptrdiff_t)m + 2] == cur[2]) {
+				d[nd] = 3;
+				nd += 2;
+				done = true;
+			} else {
+				d[nd] = 2;
+				nd += 2;
+			}
+		}
+		if (!done && c3 >= minPos && cur[(ptrdiff_t)c3 - (ptrdiff_t)m] == cur[0]) {
+			d[nd++] = 3;
+			d[nd++] = m - c3 - 1;
+		}
+	}
+	for (uint32_t i = 0; i < nbt; i++)
+		d[nd++] = bt[i];
+	mf_advance(e);
+	return nd;
+}
+
+// MatchFinderMt3_Skip (LzFindMt.c:1340-1350): the tree still sees every position
+LZ_FN inline void mf_skip(Enc *e, uint32_t num)
+{
+	uint32_t scratch[2 * (kMatchMax + 1)];
+	while (num--) {
+		mf_tree_step(e, scratch);
+		if (mf_avail(e) >= 3) {
+			uint32_t h2, h3;
+			mf_hash23(e, mf_cur(e), h2, h3);
+			e->hash2[h2] = e->pos;
+			e->hash3[h3] = e->pos;
+		}
+		mf_advance(e);
+	}
+}
+
+// ReadMatchDistances (LzmaEnc.c:1083-1126)
+LZ_FN inline uint32_t read_matches(Enc *e, uint32_t *numPairsRes)
+{
+	e->additionalOffset++;
+	e->numAvail = mf_avail(e);
+	const uint32_t numPairs = mf_get_matches(e, e->matches);
+	*numPairsRes = numPairs;
+	if (numPairs == 0)
+		return 0;
+	const uint32_t len = e->matches[numPairs - 2];
+	if (len != e->fb)
+		return len;
+	uint32_t numAvail = e->numAvail;
+	if (numAvail > kMatchMax)
+		numAvail = kMatchMax;
+	const uint8_t *p1 = mf_cur(e) - 1;
+	const ptrdiff_t dif = (ptrdiff_t)-1 - (ptrdiff_t)e->matches[numPairs - 1];
+	uint32_t l = len;
+	while (l != numAvail && p1[l] == p1[(ptrdiff_t)l + dif])
+		l++;
+	return l;
+}
+
+LZ_INL void move_pos(Enc *e, uint32_t num)
+{
+	e->additionalOffset += num;
+	mf_skip(e, num);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// optimal parser
+LZ_INL uint32_t price_short_rep(const Enc *e, uint32_t state, uint32_t posState)
+{
+	return price0(e, e->isRepG0[state]) + price0(e, e->isRep0Long[state][posState]);
+}
+
+LZ_INL uint32_t price_rep0(const Enc *e, uint32_t state, uint32_t posState) // GetPrice_Rep_0
+{
+	return price1(e, e->isMatch[state][posState]) + price1(e, e->isRep0Long[state][posState]) + price1(e, e->isRep[state]) +
+	       price0(e, e->isRepG0[state]);
+}
+
+LZ_FN inline uint32_t price_pure_rep(const Enc *e, uint32_t repIndex, uint32_t state, uint32_t posState)
+{
+	uint32_t price, prob = e->isRepG0[state];
+	if (repIndex == 0) {
+		price = price0(e, prob);
+		price += price1(e, e->isRep0Long[state][posState]);
+	} else {
+		price = price1(e, prob);
+		prob = e->isRepG1[state];
+		if (repIndex == 1)
+			price += price0(e, prob);
+		else {
+			price += price1(e, prob);
+			price += price_bit(e, e->isRepG2[state], repIndex - 2);
+		}
+	}
+	return price;
+}
+
+LZ_INL uint32_t len_price(const LenPrices *lp, uint32_t posState, uint32_t len) { return lp->prices[posState][len - kMatchMin]; }
+
+// Backward (LzmaEnc.c:1167-1211)
+LZ_FN inline uint32_t backward(Enc *e, uint32_t cur)
+{
+	uint32_t wr = cur + 1;
+	e->optEnd = wr;
+	for (;;) {
+		uint32_t dist = e->opt[cur].dist;
+		uint32_t len = e->opt[cur].len;
+		const uint32_t extra = e->opt[cur].extra;
+		cur -= len;
+		if (extra) {
+			wr--;
+			e->opt[wr].len = len;
+			cur -= extra;
+			len = extra;
+			if (extra == 1) {
+				e->opt[wr].dist = dist;
+				dist = kMarkLit;
+			} else {
+				e->opt[wr].dist = 0;
+				len--;
+				wr--;
+				e->opt[wr].dist = kMarkLit;
+				e->opt[wr].len = 1;
+			}
+		}
+		if (cur == 0) {
+			e->backRes = dist;
+			e->optCur = wr;
+			return len;
+		}
+		wr--;
+		e->opt[wr].dist = dist;
+		e->opt[wr].len = len;
+	}
+}
+
+LZ_INL void opt_set(Opt *o, uint32_t price, uint32_t len, uint32_t dist, uint32_t extra)
+{
+	o->price = price;
+	o->len = len;
+	o->dist = dist;
+	o->extra = (uint16_t)extra;
+}
+
+// GetOptimum (LzmaEnc.c:1219-1968)
+LZ_FN inline uint32_t get_optimum(Enc *e, uint32_t position)
+{
+	uint32_t last, cur;
+	uint32_t reps[kNumReps], repLens[kNumReps];
+	uint32_t *matches = e->matches;
+	const uint32_t fb = e->fb;
+	{
+		uint32_t numAvail, numPairs, mainLen, repMaxIndex, i, posState, matchPrice, repMatchPrice;
+		e->optCur = e->optEnd = 0;
+		if (e->additionalOffset == 0)
+			mainLen = read_matches(e, &numPairs);
+		else {
+			mainLen = e->longestMatchLen;
+			numPairs = e->numPairs;
+		}
+		numAvail = e->numAvail;
+		if (numAvail < 2) {
+			e->backRes = kMarkLit;
+			return 1;
+		}
+		if (numAvail > kMatchMax)
+			numAvail = kMatchMax;
+		const uint8_t *data = mf_cur(e) - 1;
+		repMaxIndex = 0;
+		for (i = 0; i < kNumReps; i++) {
+			reps[i] = e->reps[i];
+			const uint8_t *data2 = data - reps[i];
+			if (data[0] != data2[0] || data[1] != data2[1]) {
+				repLens[i] = 0;
+				continue;
+			}
+			uint32_t len = 2;
+			while (len < numAvail && data[len] == data2[len])
+				len++;
+			repLens[i] = len;
+			if (len > repLens[repMaxIndex])
+				repMaxIndex = i;
+			if (len == kMatchMax)
+				break;
+		}
+		// NB: when the loop above stops early at kMatchMax the remaining repLens are not read below,
+		// because that rep is >= fb and is returned right away.
+		if (repLens[repMaxIndex] >= fb) {
+			e->backRes = repMaxIndex;
+			const uint32_t len = repLens[repMaxIndex];
+			move_pos(e, len - 1);
+			return len;
+		}
+		if (mainLen >= fb) {
+			e->backRes = matches[numPairs - 1] + kNumReps;
+			move_pos(e, mainLen - 1);
+			return mainLen;
+		}
+		const uint8_t curByte = *data, matchByte = *(data - reps[0]);
+		last = repLens[repMaxIndex];
+		if (last <= mainLen)
+			last = mainLen;
+		if (last < 2 && curByte != matchByte) {
+			e->backRes = kMarkLit;
+			return 1;
+		}
+		e->opt[0].state = (uint16_t)e->state;
+		posState = position & e->pbMask;
+		{
+			const Prob *probs = lit_probs(e, position, *(data - 1));
+			e->opt[1].price = price0(e, e->isMatch[e->state][posState]) +
+					  (!is_lit_state(e->state) ? lit_price_matched(e, probs, curByte, matchByte) : lit_price(e, probs, curByte));
+		}
+		e->opt[1].dist = kMarkLit;
+		e->opt[1].extra = 0;
+		matchPrice = price1(e, e->isMatch[e->state][posState]);
+		repMatchPrice = matchPrice + price1(e, e->isRep[e->state]);
+		if (matchByte == curByte && repLens[0] == 0) {
+			const uint32_t shortRepPrice = repMatchPrice + price_short_rep(e, e->state, posState);
+			if (shortRepPrice < e->opt[1].price) {
+				e->opt[1].price = shortRepPrice;
+				e->opt[1].dist = 0;
+				e->opt[1].extra = 0;
+			}
+			if (last < 2) {
+				e->backRes = e->opt[1].dist;
+				return 1;
+			}
+		}
+		e->opt[1].len = 1;
+		for (i = 0; i < kNumReps; i++)
+			e->opt[0].reps[i] = reps[i];
+
+		for (i = 0; i < kNumReps; i++) { // REP
+			uint32_t repLen = repLens[i];
+			if (repLen < 2)
+				continue;
+			const uint32_t price = repMatchPrice + price_pure_rep(e, i, e->state, posState);
+			do {
+				const uint32_t price2 = price + len_price(&e->repLenPrices, posState, repLen);
+				Opt *o = &e->opt[repLen];
+				if (price2 < o->price)
+					opt_set(o, price2, repLen, i, 0);
+			} while (--repLen >= 2);
+		}
+		{ // MATCH
+			uint32_t len = repLens[0] + 1;
+			if (len <= mainLen) {
+				uint32_t offs = 0;
+				const uint32_t normalMatchPrice = matchPrice + price0(e, e->isRep[e->state]);
+				if (len < 2)
+					len = 2;
+				else
+					while (len > matches[offs])
+						offs += 2;
+				for (;; len++) {
+					const uint32_t dist = matches[offs + 1];
+					uint32_t price = normalMatchPrice + len_price(&e->lenPrices, posState, len);
+					const uint32_t l2p = len < kNumLenToPos + 1 ? len - 2 : kNumLenToPos - 1;
+					if (dist < kNumFullDist)
+						price += e->distPrices[l2p][dist & (kNumFullDist - 1)];
+					else
+						price += e->alignPrices[dist & kAlignMask] + e->posSlotPrices[l2p][pos_slot(dist)];
+					Opt *o = &e->opt[len];
+					if (price < o->price)
+						opt_set(o, price, len, dist + kNumReps, 0);
+					if (len == matches[offs]) {
+						offs += 2;
+						if (offs == numPairs)
+							break;
+					}
+				}
+			}
+		}
+		cur = 0;
+	}
+
+	for (;;) {
+		uint32_t numAvail, numAvailFull, newLen, numPairs, prev, state, posState, startLen;
+		uint32_t litPrice, matchPrice, repMatchPrice;
+		bool nextIsLit;
+		if (++cur == last)
+			break;
+		if (cur >= kNumOpts - 64) {
+			uint32_t best = cur, price = e->opt[cur].price;
+			for (uint32_t j = cur + 1; j <= last; j++) {
+				const uint32_t price2 = e->opt[j].price;
+				if (price >= price2) {
+					price = price2;
+					best = j;
+				}
+			}
+			const uint32_t delta = best - cur;
+			if (delta != 0)
+				move_pos(e, delta);
+			cur = best;
+			break;
+		}
+		newLen = read_matches(e, &numPairs);
+		if (newLen >= fb) {
+			e->numPairs = numPairs;
+			e->longestMatchLen = newLen;
+			break;
+		}
+		Opt *curOpt = &e->opt[cur];
+		position++;
+		prev = cur - curOpt->len;
+		if (curOpt->len == 1) {
+			state = e->opt[prev].state;
+			state = curOpt->dist == 0 ? st_shortrep(state) : st_lit(state);
+		} else {
+			const uint32_t dist = curOpt->dist;
+			if (curOpt->extra) {
+				prev -= curOpt->extra;
+				state = 8; // kState_RepAfterLit
+				if (curOpt->extra == 1)
+					state = dist < kNumReps ? 8 : 7; // RepAfterLit : MatchAfterLit
+			} else {
+				state = e->opt[prev].state;
+				state = dist < kNumReps ? st_rep(state) : st_match(state);
+			}
+			const Opt *prevOpt = &e->opt[prev];
+			uint32_t b0 = prevOpt->reps[0];
+			if (dist < kNumReps) {
+				if (dist == 0) {
+					reps[0] = b0;
+					reps[1] = prevOpt->reps[1];
+					reps[2] = prevOpt->reps[2];
+					reps[3] = prevOpt->reps[3];
+				} else {
+					reps[1] = b0;
+					b0 = prevOpt->reps[1];
+					if (dist == 1) {
+						reps[0] = b0;
+						reps[2] = prevOpt->reps[2];
+						reps[3] = prevOpt->reps[3];
+					} else {
+						reps[2] = b0;
+						reps[0] = prevOpt->reps[dist];
+						reps[3] = prevOpt->reps[dist ^ 1];
+					}
+				}
+			} else {
+				reps[0] = dist - kNumReps + 1;
+				reps[1] = b0;
+				reps[2] = prevOpt->reps[1];
+				reps[3] = prevOpt->reps[2];
+			}
+		}
+		curOpt->state = (uint16_t)state;
+		for (uint32_t i = 0; i < kNumReps; i++)
+			curOpt->reps[i] = reps[i];
+
+		const uint8_t *data = mf_cur(e) - 1;
+		const uint8_t curByte = *data, matchByte = *(data - reps[0]);
+		posState = position & e->pbMask;
+		{
+			const uint32_t curPrice = curOpt->price;
+			const uint32_t prob = e->isMatch[state][posState];
+			matchPrice = curPrice + price1(e, prob);
+			litPrice = curPrice + price0(e, prob);
+		}
+		Opt *nextOpt = &e->opt[cur + 1];
+		nextIsLit = false;
+		if ((nextOpt->price < kInfinity && matchByte == curByte) || litPrice > nextOpt->price)
+			litPrice = 0;
+		else {
+			const Prob *probs = lit_probs(e, position, *(data - 1));
+			litPrice += !is_lit_state(state) ? lit_price_matched(e, probs, curByte, matchByte) : lit_price(e, probs, curByte);
+			if (litPrice < nextOpt->price) {
+				opt_set(nextOpt, litPrice, 1, kMarkLit, 0);
+				nextIsLit = true;
+			}
+		}
+		repMatchPrice = matchPrice + price1(e, e->isRep[state]);
+		numAvailFull = e->numAvail;
+		{
+			const uint32_t temp = kNumOpts - 1 - cur;
+			if (numAvailFull > temp)
+				numAvailFull = temp;
+		}
+		// SHORT_REP
+		if (is_lit_state(state) && matchByte == curByte && repMatchPrice < nextOpt->price &&
+		    (nextOpt->len < 2 || nextOpt->dist != 0)) {
+			const uint32_t shortRepPrice = repMatchPrice + price_short_rep(e, state, posState);
+			if (shortRepPrice < nextOpt->price) {
+				opt_set(nextOpt, shortRepPrice, 1, 0, 0);
+				nextIsLit = false;
+			}
+		}
+		if (numAvailFull < 2)
+			continue;
+		numAvail = numAvailFull <= fb ? numAvailFull : fb;
+
+		// LIT : REP_0
+		if (!nextIsLit && litPrice != 0 && matchByte != curByte && numAvailFull > 2) {
+			const uint8_t *data2 = data - reps[0];
+			if (data[1] == data2[1] && data[2] == data2[2]) {
+				uint32_t len, limit = fb + 1;
+				if (limit > numAvailFull)
+					limit = numAvailFull;
+				for (len = 3; len < limit && data[len] == data2[len]; len++) {
+				}
+				const uint32_t state2 = st_lit(state), posState2 = (position + 1) & e->pbMask;
+				const uint32_t price = litPrice + price_rep0(e, state2, posState2);
+				const uint32_t offset = cur + len;
+				if (last < offset)
+					last = offset;
+				len--;
+				const uint32_t price2 = price + len_price(&e->repLenPrices, posState2, len);
+				Opt *o = &e->opt[offset];
+				if (price2 < o->price)
+					opt_set(o, price2, len, 0, 1);
+			}
+		}
+		startLen = 2;
+		// REP
+		for (uint32_t repIndex = 0; repIndex < kNumReps; repIndex++) {
+			const uint8_t *data2 = data - reps[repIndex];
+			if (data[0] != data2[0] || data[1] != data2[1])
+				continue;
+			uint32_t len = 2;
+			while (len < numAvail && data[len] == data2[len])
+				len++;
+			if (last < cur + len)
+				last = cur + len;
+			uint32_t price = repMatchPrice + price_pure_rep(e, repIndex, state, posState);
+			{
+				uint32_t len2 = len;
+				do {
+					const uint32_t price2 = price + len_price(&e->repLenPrices, posState, len2);
+					Opt *o = &e->opt[cur + len2];
+					if (price2 < o->price)
+						opt_set(o, price2, len2, repIndex, 0);
+				} while (--len2 >= 2);
+			}
+			if (repIndex == 0)
+				startLen = len + 1;
+			// REP : LIT : REP_0
+			uint32_t len2 = len + 1, limit = len2 + fb;
+			if (limit > numAvailFull)
+				limit = numAvailFull;
+			len2 += 2;
+			if (len2 <= limit && data[len2 - 2] == data2[len2 - 2] && data[len2 - 1] == data2[len2 - 1]) {
+				uint32_t state2 = st_rep(state), posState2 = (position + len) & e->pbMask;
+				price += len_price(&e->repLenPrices, posState, len) + price0(e, e->isMatch[state2][posState2]) +
+					 lit_price_matched(e, lit_probs(e, position + len, data[len - 1]), data[len], data2[len]);
+				state2 = 5; // kState_LitAfterRep
+				posState2 = (posState2 + 1) & e->pbMask;
+				price += price_rep0(e, state2, posState2);
+				while (len2 < limit && data[len2] == data2[len2])
+					len2++;
+				len2 -= len;
+				const uint32_t offset = cur + len + len2;
+				if (last < offset)
+					last = offset;
+				len2--;
+				const uint32_t price2 = price + len_price(&e->repLenPrices, posState2, len2);
+				Opt *o = &e->opt[offset];
+				if (price2 < o->price)
+					opt_set(o, price2, len2, repIndex, len + 1);
+			}
+		}
+		// MATCH
+		if (newLen > numAvail) {
+			newLen = numAvail;
+			for (numPairs = 0; newLen > matches[numPairs]; numPairs += 2) {
+			}
+			matches[numPairs] = newLen;
+			numPairs += 2;
+		}
+		if (newLen >= startLen) {
+			const uint32_t normalMatchPrice = matchPrice + price0(e, e->isRep[state]);
+			if (last < cur + newLen)
+				last = cur + newLen;
+			uint32_t offs = 0;
+			while (startLen > matches[offs])
+				offs += 2;
+			uint32_t dist = matches[offs + 1];
+			uint32_t slot = pos_slot(dist);
+			for (uint32_t len = startLen;; len++) {
+				uint32_t price = normalMatchPrice + len_price(&e->lenPrices, posState, len);
+				{
+					uint32_t lenNorm = len - 2;
+					lenNorm = lenNorm < kNumLenToPos - 1 ? lenNorm : kNumLenToPos - 1;
+					if (dist < kNumFullDist)
+						price += e->distPrices[lenNorm][dist & (kNumFullDist - 1)];
+					else
+						price += e->posSlotPrices[lenNorm][slot] + e->alignPrices[dist & kAlignMask];
+					Opt *o = &e->opt[cur + len];
+					if (price < o->price)
+						opt_set(o, price, len, dist + kNumReps, 0);
+				}
+				if (len == matches[offs]) {
+					// MATCH : LIT : REP_0
+					const uint8_t *data2 = data - dist - 1;
+					uint32_t len2 = len + 1, limit = len2 + fb;
+					if (limit > numAvailFull)
+						limit = numAvailFull;
+					len2 += 2;
+					if (len2 <= limit && data[len2 - 2] == data2[len2 - 2] && data[len2 - 1] == data2[len2 - 1]) {
+						while (len2 < limit && data[len2] == data2[len2])
+							len2++;
+						len2 -= len;
+						uint32_t state2 = st_match(state), posState2 = (position + len) & e->pbMask;
+						price += price0(e, e->isMatch[state2][posState2]);
+						price += lit_price_matched(e, lit_probs(e, position + len, data[len - 1]), data[len], data2[len]);
+						state2 = 4; // kState_LitAfterMatch
+						posState2 = (posState2 + 1) & e->pbMask;
+						price += price_rep0(e, state2, posState2);
+						const uint32_t offset = cur + len + len2;
+						if (last < offset)
+							last = offset;
+						len2--;
+						const uint32_t price2 = price + len_price(&e->repLenPrices, posState2, len2);
+						Opt *o = &e->opt[offset];
+						if (price2 < o->price)
+							opt_set(o, price2, len2, dist + kNumReps, len + 1);
+					}
+					offs += 2;
+					if (offs == numPairs)
+						break;
+					dist = matches[offs + 1];
+					slot = pos_slot(dist);
+				}
+			}
+		}
+	}
+	do
+		e->opt[last].price = kInfinity;
+	while (--last);
+	return backward(e, cur);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// block driver
+struct Config {
+	uint32_t dictSize, fb, mc, lc, lp, pb;
+	uint32_t historySize, cyclicSize, hashMask, bigHash, distTableSize;
+	uint64_t sonEntries, hash4Entries; // allocation sizes (uint32 counts)
+};
+
+// MatchFinder_GetHashMask (LzFind.c:347-373) for numHashBytes == 4
+inline uint32_t hash_mask_for(uint32_t hs)
+{
+	if (hs != 0)
+		hs--;
+	hs |= hs >> 1;
+	hs |= hs >> 2;
+	hs |= hs >> 4;
+	hs |= hs >> 8;
+	hs >>= 1;
+	if (hs >= (1u << 24))
+		hs >>= 1;
+	hs |= (1u << 16) - 1;
+	return hs;
+}
+
+// LzmaEncProps_Normalize / LzmaEnc_SetProps / LzmaEnc_Alloc / MatchFinder_Create for the parameters
+// lzma_compress_buf passes (src/stream.c:450-456): level, dictSize, lc3 lp0 pb2, fb, numThreads 2.
+inline bool make_config(int level, uint32_t dictSize, uint32_t fb, uint64_t srcLen, Config &c)
+{
+	if (level < 5 || srcLen == 0 || srcLen >= 0xFFFF0000ull)
+		return false; // fast mode (levels 1-4, hc5) is not built yet
+	if (fb < 5)
+		fb = 5;
+	if (fb > kMatchMax)
+		fb = kMatchMax;
+	c.dictSize = dictSize;
+	c.fb = fb;
+	c.mc = 16 + (fb >> 1);
+	c.lc = 3;
+	c.lp = 0;
+	c.pb = 2;
+	uint32_t hist = dictSize;
+	if (hist == (2u << 30) || hist == (3u << 30))
+		hist -= 1;
+	c.historySize = hist;
+	c.cyclicSize = hist + 1;
+	const uint32_t hs = hash_mask_for(hist);
+	uint32_t cur = hs;
+	if (srcLen < hist) {
+		cur = hash_mask_for((uint32_t)srcLen);
+		if (cur > hs)
+			cur = hs;
+	}
+	c.hashMask = cur;
+	c.bigHash = cur >= 0xFFFFFFu ? 1 : 0; // LzmaEnc.c:2752 (two-thread match finder)
+	uint32_t i;
+	for (i = kEndPosModel / 2; i < 32; i++)
+		if (dictSize <= (1u << i))
+			break;
+	c.distTableSize = i * 2;
+	c.hash4Entries = (uint64_t)cur + 1;
+	// a block shorter than the dictionary never wraps the cyclic buffer: only the first entries are touched
+	const uint64_t need = srcLen + 2;
+	c.sonEntries = 2 * (need < c.cyclicSize ? need : (uint64_t)c.cyclicSize);
+	return true;
+}
+
+// LzmaEnc_Init + LzmaEnc_InitPrices (LzmaEnc.c:2769-2852); hash arrays must be zeroed by the caller.
+LZ_FN inline void enc_init(Enc *e, const Config &c, const uint8_t *src, uint32_t n, uint8_t *out, uint64_t outCap,
+			   uint32_t *hash2, uint32_t *hash3, uint32_t *hash4, uint32_t *son)
+{
+	e->src = src;
+	e->n = n;
+	e->fb = c.fb;
+	e->mc = c.mc;
+	e->historySize = c.historySize;
+	e->cyclicSize = c.cyclicSize;
+	e->hashMask = c.hashMask;
+	e->bigHash = c.bigHash;
+	e->distTableSize = c.distTableSize;
+	e->lc = c.lc;
+	e->pbMask = (1u << c.pb) - 1;
+	e->lpMask = (0x100u << c.lp) - (0x100u >> c.lc);
+	e->hash2 = hash2;
+	e->hash3 = hash3;
+	e->hash4 = hash4;
+	e->son = son;
+	e->pos = 1;
+	e->cycPos = 1;
+	for (uint32_t i = 0; i < 256; i++) {
+		uint32_t r = i;
+		for (int j = 0; j < 8; j++)
+			r = (r >> 1) ^ (0xEDB88320u & (0u - (r & 1)));
+		e->crc[i] = r;
+	}
+	e->low = 0;
+	e->cacheSize = 0;
+	e->range = 0xFFFFFFFFu;
+	e->cache = 0;
+	e->out = out;
+	e->outPos = 0;
+	e->outCap = outCap;
+	e->overflow = 0;
+	e->state = 0;
+	for (uint32_t i = 0; i < kNumReps; i++)
+		e->reps[i] = 1;
+	for (uint32_t i = 0; i < kAlignSize; i++)
+		e->posAlign[i] = kProbInit;
+	for (uint32_t i = 0; i < kNumStates; i++) {
+		for (uint32_t j = 0; j < kNumPosStatesMax; j++) {
+			e->isMatch[i][j] = kProbInit;
+			e->isRep0Long[i][j] = kProbInit;
+		}
+		e->isRep[i] = e->isRepG0[i] = e->isRepG1[i] = e->isRepG2[i] = kProbInit;
+	}
+	for (uint32_t i = 0; i < kNumLenToPos; i++)
+		for (uint32_t j = 0; j < 64; j++)
+			e->posSlot[i][j] = kProbInit;
+	for (uint32_t i = 0; i < kNumFullDist; i++)
+		e->posEnc[i] = kProbInit;
+	for (uint32_t i = 0; i < (0x300u << (c.lc + c.lp)); i++)
+		e->lit[i] = kProbInit;
+	for (uint32_t i = 0; i < (kNumPosStatesMax << 4); i++)
+		e->lenProbs.low[i] = e->repLenProbs.low[i] = kProbInit;
+	for (uint32_t i = 0; i < kLenHigh; i++)
+		e->lenProbs.high[i] = e->repLenProbs.high[i] = kProbInit;
+	e->optEnd = e->optCur = 0;
+	for (uint32_t i = 0; i < kNumOpts; i++)
+		e->opt[i].price = kInfinity;
+	e->additionalOffset = 0;
+	e->longestMatchLen = e->numPairs = e->numAvail = e->backRes = 0;
+	init_prob_prices(e->probPrices);
+	fill_distance_prices(e);
+	fill_align_prices(e);
+	e->lenPrices.tableSize = e->repLenPrices.tableSize = c.fb + 1 - kMatchMin;
+	e->repLenCounter = kRepLenCount;
+	len_update_prices(e, &e->lenPrices, 1u << c.pb, &e->lenProbs);
+	len_update_prices(e, &e->repLenPrices, 1u << c.pb, &e->repLenProbs);
+}
+
+// LzmaEnc_CodeOneBlock (LzmaEnc.c:2383-2680) run to the end of the block, then Flush (:2191-2200).
+// Returns the number of output bytes (valid when !e->overflow).
+LZ_FN inline uint64_t enc_run(Enc *e)
+{
+	uint32_t nowPos = 0;
+	if (e->n == 0) {
+		for (int i = 0; i < 5; i++)
+			rc_shift_low(e);
+		return e->outPos;
+	}
+	{
+		uint32_t numPairs;
+		read_matches(e, &numPairs);
+		rc_bit(e, &e->isMatch[0][0], 0);
+		const uint8_t curByte = *(mf_cur(e) - e->additionalOffset);
+		lit_encode(e, e->lit, curByte);
+		e->additionalOffset--;
+		nowPos++;
+	}
+	if (mf_avail(e) != 0) {
+		for (;;) {
+			uint32_t len;
+			{
+				const uint32_t oci = e->optCur;
+				if (e->optEnd == oci)
+					len = get_optimum(e, nowPos);
+				else {
+					const Opt *o = &e->opt[oci];
+					len = o->len;
+					e->backRes = o->dist;
+					e->optCur = oci + 1;
+				}
+			}
+			const uint32_t posState = nowPos & e->pbMask;
+			uint32_t dist = e->backRes;
+			Prob *pm = &e->isMatch[e->state][posState];
+			if (dist == kMarkLit) {
+				rc_bit(e, pm, 0);
+				const uint8_t *data = mf_cur(e) - e->additionalOffset;
+				Prob *probs = (Prob *)lit_probs(e, nowPos, *(data - 1));
+				const uint32_t state = e->state;
+				e->state = st_lit(state);
+				if (is_lit_state(state))
+					lit_encode(e, probs, *data);
+				else
+					lit_encode_matched(e, probs, *data, *(data - e->reps[0]));
+			} else {
+				rc_bit(e, pm, 1);
+				if (dist < kNumReps) {
+					rc_bit(e, &e->isRep[e->state], 1);
+					if (dist == 0) {
+						rc_bit(e, &e->isRepG0[e->state], 0);
+						rc_bit(e, &e->isRep0Long[e->state][posState], len != 1 ? 1 : 0);
+						if (len == 1)
+							e->state = st_shortrep(e->state);
+					} else {
+						rc_bit(e, &e->isRepG0[e->state], 1);
+						if (dist == 1) {
+							rc_bit(e, &e->isRepG1[e->state], 0);
+							dist = e->reps[1];
+						} else {
+							rc_bit(e, &e->isRepG1[e->state], 1);
+							rc_bit(e, &e->isRepG2[e->state], dist - 2);
+							if (dist == 2)
+								dist = e->reps[2];
+							else {
+								dist = e->reps[3];
+								e->reps[3] = e->reps[2];
+							}
+							e->reps[2] = e->reps[1];
+						}
+						e->reps[1] = e->reps[0];
+						e->reps[0] = dist;
+					}
+					if (len != 1) {
+						len_encode(e, &e->repLenProbs, len - kMatchMin, posState);
+						--e->repLenCounter;
+						e->state = st_rep(e->state);
+					}
+				} else {
+					rc_bit(e, &e->isRep[e->state], 0);
+					e->state = st_match(e->state);
+					len_encode(e, &e->lenProbs, len - kMatchMin, posState);
+					dist -= kNumReps;
+					e->reps[3] = e->reps[2];
+					e->reps[2] = e->reps[1];
+					e->reps[1] = e->reps[0];
+					e->reps[0] = dist + 1;
+					e->matchPriceCount++;
+					const uint32_t slot = pos_slot(dist);
+					{
+						uint32_t sym = slot + 64;
+						Prob *probs = e->posSlot[len < kNumLenToPos + 1 ? len - 2 : kNumLenToPos - 1];
+						do {
+							Prob *prob = probs + (sym >> 6);
+							const uint32_t bit = (sym >> 5) & 1;
+							sym <<= 1;
+							rc_bit(e, prob, bit);
+						} while (sym < (1u << 12));
+					}
+					if (dist >= kStartPosModel) {
+						const uint32_t footer = (slot >> 1) - 1;
+						if (dist < kNumFullDist) {
+							const uint32_t base = (2 | (slot & 1)) << footer;
+							rc_reverse(e, e->posEnc + base, footer, dist);
+						} else {
+							rc_direct(e, (dist & ((1u << footer) - 1)) >> kNumAlignBits, footer - kNumAlignBits);
+							rc_reverse(e, e->posAlign, kNumAlignBits, dist & kAlignMask);
+						}
+					}
+				}
+			}
+			nowPos += len;
+			e->additionalOffset -= len;
+			if (e->additionalOffset == 0) {
+				if (e->matchPriceCount >= 64) {
+					fill_align_prices(e);
+					fill_distance_prices(e);
+					len_update_prices(e, &e->lenPrices, e->pbMask + 1, &e->lenProbs);
+				}
+				if (e->repLenCounter <= 0) {
+					e->repLenCounter = kRepLenCount;
+					len_update_prices(e, &e->repLenPrices, e->pbMask + 1, &e->repLenProbs);
+				}
+				if (mf_avail(e) == 0)
+					break;
+			}
+		}
+	}
+	for (int i = 0; i < 5; i++) // RangeEnc_FlushData; no end marker (writeEndMark = 0)
+		rc_shift_low(e);
+	return e->outPos;
+}
+
+} // namespace lzma
+} // namespace lrz
