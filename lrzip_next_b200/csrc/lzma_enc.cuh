@@ -103,6 +103,7 @@ struct Enc {
 	int repLenCounter;
 	uint32_t probPrices[kBitModelTotal >> kMoveReducingBits];
 	uint32_t matches[kMatchMax * 2 + 2];
+	uint32_t btTmp[kMatchMax * 2 + 2]; // tree pairs of the current position before the 2/3-byte hash mix
 	uint32_t alignPrices[kAlignSize];
 	uint32_t posSlotPrices[kNumLenToPos][kDistTableMax];
 	uint32_t distPrices[kNumLenToPos][kNumFullDist];
@@ -531,7 +532,7 @@ LZ_INL void mf_hash23(const Enc *e, const uint8_t *cur, uint32_t &h2, uint32_t &
 // MatchFinderMt_GetMatches + MixMatches3 (LzFindMt.c:1274-1317, 1093-1131)
 LZ_FN inline uint32_t mf_get_matches(Enc *e, uint32_t *d)
 {
-	uint32_t bt[2 * (kMatchMax + 1)];
+	uint32_t *bt = e->btTmp;
 	const uint32_t nbt = mf_tree_step(e, bt);
 	const uint32_t availAfter = mf_avail(e) - 1;
 	const uint8_t *cur = mf_cur(e);
@@ -580,9 +581,8 @@ LZ_FN inline uint32_t mf_get_matches(Enc *e, uint32_t *d)
 // MatchFinderMt3_Skip (LzFindMt.c:1340-1350): the tree still sees every position
 LZ_FN inline void mf_skip(Enc *e, uint32_t num)
 {
-	uint32_t scratch[2 * (kMatchMax + 1)];
 	while (num--) {
-		mf_tree_step(e, scratch);
+		mf_tree_step(e, e->btTmp);
 		if (mf_avail(e) >= 3) {
 			uint32_t h2, h3;
 			mf_hash23(e, mf_cur(e), h2, h3);

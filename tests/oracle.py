@@ -218,3 +218,69 @@ def ref_decompress(archive: bytes) -> bytes:
                        stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
         with open(o, "rb") as fh:
             return fh.read()
+
+
+# ---- lz4 gate reference: lz4_compresses() of src/stream.c:2325-2380 over the system liblz4 ----------
+_lz4 = None
+
+
+def _liblz4():
+    global _lz4
+    if _lz4 is None:
+        for name in ("liblz4.so.1", "/lib/x86_64-linux-gnu/liblz4.so.1"):
+            try:
+                _lz4 = C.CDLL(name)
+                break
+            except OSError:
+                continue
+        if _lz4 is None:
+            raise RuntimeError("liblz4.so.1 not found")
+        _lz4.LZ4_compress_default.argtypes = [C.c_char_p, C.c_char_p, C.c_int, C.c_int]
+    return _lz4
+
+
+def have_lz4() -> bool:
+    try:
+        _liblz4()
+        return True
+    except RuntimeError:
+        return False
+
+
+def ref_lz4_gate(data: bytes, threshold: int = 100) -> int:
+    L = _liblz4()
+    s_len = len(data)
+    test_len = s_len
+    in_len = min(test_len, 100 * 1048576)
+    buftest = in_len
+    pct = 101.0
+    dst = C.create_string_buffer(in_len + 2)
+    while test_len > 0:
+        ret = L.LZ4_compress_default(data, dst, in_len, in_len + 1)
+        if ret > 0:
+            pct = 100 * (ret / in_len)
+            if ret < in_len * (threshold / 100):
+                break
+        test_len -= in_len
+        if test_len > 0:
+            buftest += in_len
+            if buftest < 10 * 1048576:
+                buftest <<= 1
+            in_len = min(test_len, buftest)
+            dst = C.create_string_buffer(in_len + 2)
+    return 0 if pct > threshold else (int(pct + 1) if pct < 1 else int(pct))
+
+
+def lzma_block_fn(level: int, dict_size: int, threshold: int = 100):
+    """Block callback for oracle.compress(): lz4 gate + the reference's LzmaCompress."""
+    def fn(user, src, u_len, stream, out, out_cap, c_len, c_type):
+        data = C.string_at(src, u_len)
+        if threshold and have_lz4() and not ref_lz4_gate(data, threshold):
+            return 0
+        payload = ref_lzma_block(data, level, dict_size, 2)
+        if payload is not None:
+            C.memmove(out, payload, len(payload))
+            c_len[0] = len(payload)
+            c_type[0] = 6
+        return 0
+    return fn
