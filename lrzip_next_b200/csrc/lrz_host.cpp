@@ -116,6 +116,8 @@ int compute_sizing(const lrzgpu_params &p, int64_t st_size, lrzgpu_sizing_t &o)
 			exponent = save_exponent; // last tried dictionary stays in place until the next reduction
 		}
 	}
+	if (threads < 1)
+		return LRZGPU_EINVAL; // not even one encoder fits the RAM budget: the reference divides by zero here
 	if (st_size > 0 && st_size < limit)
 		limit = st_size > kStreamBufsize ? st_size : kStreamBufsize;
 	else if (limit > chunk_limit)

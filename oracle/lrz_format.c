@@ -180,6 +180,8 @@ retry_lzma:
 			}
 		}
 	}
+	if (threads < 1)
+		return -1; /* the reference would divide by zero at src/stream.c:1316 */
 	if (st_size > 0 && st_size < limit) /* src/stream.c:1286-1290 */
 		limit = st_size > STREAM_BUFSIZE ? st_size : STREAM_BUFSIZE;
 	else if (limit > chunk_limit)

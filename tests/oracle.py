@@ -64,6 +64,7 @@ def lib():
         L.rzo_hash_index.argtypes = [C.c_void_p]
         L.rzo_full_tag.argtypes = [C.c_void_p, C.c_int64]
         L.rzo_full_tag.restype = C.c_int64
+        L.rzo_sizing_compute.restype = C.c_int
         L.rzo_sizing_compute.argtypes = [C.POINTER(Params), C.c_int64, C.POINTER(Sizing)]
         L.rzo_compress.argtypes = [C.POINTER(Params), C.c_void_p, C.c_int64, BLOCK_FN, C.c_void_p,
                                    C.POINTER(C.c_void_p), C.POINTER(C.c_int64), C.POINTER(Stats)]
@@ -117,7 +118,8 @@ def make_params(level=7, rzip_level=0, backend=BACKEND_NONE, threads=1, window=0
 
 def sizing(params: Params, st_size: int) -> Sizing:
     s = Sizing()
-    lib().rzo_sizing_compute(C.byref(params), st_size, C.byref(s))
+    if lib().rzo_sizing_compute(C.byref(params), st_size, C.byref(s)):
+        raise ValueError("no encoder fits the RAM budget (the reference would crash)")
     return s
 
 

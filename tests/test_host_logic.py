@@ -1,0 +1,150 @@
+"""CPU tests of the product's host-side logic and of the host builds of its device code
+(tests/hostsim): commit control logic, LZMA block encoder, LZ4 size emulation, sizing rules, C ABI."""
+import ctypes as C
+import hashlib
+import json
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+import oracle
+from lrzip_next_b200 import api, datagen, make_params, sizing
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+with open(os.path.join(HERE, "golden", "golden.json")) as fh:
+    GOLDEN = json.load(fh)
+
+
+@pytest.fixture(scope="module")
+def hostsim():
+    subprocess.run(["make", "-s", "-C", os.path.join(HERE, "hostsim"), "all"], check=True)
+    H = C.CDLL(os.path.join(HERE, "hostsim", "libhostsim.so"))
+    H.hostsim_rzip_chunk.argtypes = [C.c_void_p, C.c_int64, C.c_int, C.c_int, C.POINTER(C.c_int64), C.c_int64,
+                                     C.POINTER(C.c_void_p), C.POINTER(C.c_int64), C.POINTER(C.c_void_p),
+                                     C.POINTER(C.c_int64), C.c_void_p]
+    Z = C.CDLL(os.path.join(HERE, "hostsim", "liblzmahost.so"))
+    Z.hostsim_lzma_encode.argtypes = [C.c_void_p, C.c_int64, C.c_int, C.c_uint32, C.c_uint32, C.c_void_p, C.c_int64,
+                                      C.POINTER(C.c_int64)]
+    L = C.CDLL(os.path.join(HERE, "hostsim", "liblz4host.so"))
+    L.hostsim_lz4_size.argtypes = [C.c_char_p, C.c_int, C.c_int]
+    L.hostsim_lz4_gate.argtypes = [C.c_char_p, C.c_int64, C.c_int]
+    return H, Z, L
+
+
+def _commit(H, data, level, seg, vr=0):
+    data = np.ascontiguousarray(data, dtype=np.uint8)
+    v, s0, s1, l0, l1 = C.c_int64(vr), C.c_void_p(), C.c_void_p(), C.c_int64(), C.c_int64()
+    rc = H.hostsim_rzip_chunk(data.ctypes.data, data.size, level, oracle.chunk_bytes_for(data.size), C.byref(v), seg,
+                              C.byref(s0), C.byref(l0), C.byref(s1), C.byref(l1), None)
+    assert rc == 0
+    a, b = C.string_at(s0, l0.value), C.string_at(s1, l1.value)
+    H.hostsim_free(s0)
+    H.hostsim_free(s1)
+    return a, b, v.value
+
+
+@pytest.mark.parametrize("kind,n,level,seg", [
+    ("rep", 4 << 20, 7, 1 << 20), ("text", 4 << 20, 7, 1 << 19), ("text", 3 << 20, 3, 4096), ("mix", 4 << 20, 7, 12288),
+    ("vm", 4 << 20, 9, 1 << 20), ("text", 12 << 20, 1, 1 << 20), ("text", 100, 7, 4096), ("text", 20, 7, 4096),
+])
+def test_commit_control_logic_matches_oracle(hostsim, kind, n, level, seg):
+    d = datagen.generate(kind, n)
+    o0, o1, _, ovr = oracle.rzip_chunk(d, level)
+    assert _commit(hostsim[0], d, level, seg) == (o0, o1, ovr)
+
+
+def _lzma(Z, data, level, dic):
+    n = len(data)
+    cap = int(n * 1.02)
+    cap += (-cap) % 4096
+    out, ol = C.create_string_buffer(max(cap, 1)), C.c_int64()
+    rc = Z.hostsim_lzma_encode(data, n, level, dic, 32 if level < 7 else 64, out, cap, C.byref(ol))
+    return None if (rc != 0 or ol.value >= n) else out.raw[:ol.value]
+
+
+def test_lzma_encoder_matches_golden(hostsim):
+    for g in GOLDEN["lzma_blocks"]:
+        d = datagen.generate(g["kind"], g["n"]).tobytes()
+        got = _lzma(hostsim[1], d, g["level"], g["dict"])
+        assert (None if got is None else len(got)) == g["len"]
+        if got is not None:
+            assert hashlib.sha256(got).hexdigest() == g["sha256"]
+
+
+@pytest.mark.skipif(not oracle.have_ref(), reason="oracle/_ref not built")
+def test_lzma_encoder_matches_reference_lzmacompress(hostsim):
+    rng = np.random.default_rng(5)
+    cases = [datagen.gen_text(400_000).tobytes(), bytes(300_000), rng.integers(0, 256, 50_000, dtype=np.uint8).tobytes(),
+             datagen.gen_vm(1 << 20).tobytes(), datagen.gen_rep(1 << 20, block=1 << 14).tobytes(), b"ab" * 40,
+             rng.integers(0, 4, 200_000, dtype=np.uint8).tobytes()]
+    for d in cases:
+        for level, dic in ((7, 1 << 25), (5, 1 << 24), (9, 1 << 27), (7, 1 << 16)):
+            assert _lzma(hostsim[1], d, level, dic) == oracle.ref_lzma_block(d, level, dic, 2)
+
+
+@pytest.mark.skipif(not oracle.have_lz4(), reason="system liblz4 not present")
+def test_lz4_size_matches_liblz4(hostsim):
+    L = hostsim[2]
+    lz4 = oracle._liblz4()
+    rng = np.random.default_rng(3)
+    text = datagen.gen_text(400_000).tobytes()
+    for n in list(range(0, 30)) + [64, 1000, 65535, 65546, 65547, 65548, 400_000]:
+        for d in (text[:n], bytes(n), rng.integers(0, 256, n, dtype=np.uint8).tobytes()):
+            for cap in (n + 1, max(1, n // 2)):
+                dst = C.create_string_buffer(max(cap, 1))
+                assert L.hostsim_lz4_size(d, n, cap) == lz4.LZ4_compress_default(d, dst, n, cap)
+    for d in (text, bytes(100_000), rng.integers(0, 256, 100_000, dtype=np.uint8).tobytes()):
+        for th in (100, 40, 5):
+            assert L.hostsim_lz4_gate(d, len(d), th) == oracle.ref_lz4_gate(d, th)
+
+
+def test_sizing_matches_oracle_sweep():
+    for backend in (0, 1, 4):
+        for threads in (1, 2, 8, 33, 128):
+            for ram in (8, 60, 600):
+                for level in (3, 7, 9):
+                    for window, unlimited in ((0, 0), (1, 0), (13, 0), (0, 1)):
+                        for n in (1000, 20 << 20, 300 << 20, 5 << 30):
+                            kw = dict(level=level, backend=backend, threads=threads, window=window, unlimited=unlimited,
+                                      ramsize=ram * 100 * 1048576, processors=16)
+                            try:
+                                b = oracle.sizing(oracle.make_params(**kw), n)
+                            except ValueError:
+                                with pytest.raises(api.LrzGpuError):
+                                    sizing(make_params(**kw), n)
+                                continue
+                            a = sizing(make_params(**kw), n)
+                            assert (a.threads, a.dict_size, a.overhead, a.bufsize, a.max_chunk) == \
+                                   (b.threads, b.dict_size, b.overhead, b.bufsize, b.max_chunk), kw
+
+
+def test_abi_exports_every_declared_symbol():
+    with open(os.path.join(ROOT, "include", "lrzgpu.h")) as fh:
+        declared = set(re.findall(r"\b(lrzgpu_[a-z0-9_]+)\s*\(", fh.read()))
+    L = api.load_library()
+    missing = [s for s in sorted(declared) if not hasattr(L, s)]
+    assert not missing, missing
+    assert declared == set(api.EXPORTS)
+    assert b"lrzip-next 0.14" in L.lrzgpu_version()
+
+
+def test_no_cpu_fallback_without_device():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a CUDA device is present")
+    with pytest.raises(api.LrzGpuError) as e:
+        api.Context(0)
+    assert e.value.code == -4  # LRZGPU_ENODEV
+
+
+def test_product_does_not_link_the_oracle():
+    out = subprocess.run(["nm", "-D", "--undefined-only", api.lib_path()], capture_output=True, text=True).stdout
+    assert "rzo_" not in out
+    for src in os.listdir(os.path.join(ROOT, "lrzip_next_b200", "csrc")):
+        if src.endswith((".cu", ".cuh", ".h", ".cpp")):
+            with open(os.path.join(ROOT, "lrzip_next_b200", "csrc", src)) as fh:
+                assert "oracle/" not in fh.read().replace("the oracle", ""), src
