@@ -21,6 +21,7 @@
 
 #include "lz4_size.cuh"
 #include "lzma_enc.cuh"
+#include "lzma_mf.h"
 
 namespace lrz {
 
@@ -74,17 +75,21 @@ struct LzmaJob {
 	uint8_t *out;
 	uint64_t outCap;
 	lzma::Enc *enc;
-	uint32_t *h2, *h3, *h4, *son;
+	const uint64_t *rec;  // match lists of the data-parallel finder (lzma_mf.cu)
+	const uint32_t *pool;
 	lzma::Config cfg;
 	uint64_t outLen;
 	int overflow;
 };
 
+// K7b: optimal parser + range coder, one block per CTA, over the precomputed match lists.
 __global__ void __launch_bounds__(32) lzma_block_kernel(LzmaJob *jobs)
 {
 	if (threadIdx.x == 0) {
 		LzmaJob &j = jobs[blockIdx.x];
-		lzma::enc_init(j.enc, j.cfg, j.src, j.n, j.out, j.outCap, j.h2, j.h3, j.h4, j.son);
+		lzma::enc_init(j.enc, j.cfg, j.src, j.n, j.out, j.outCap, nullptr, nullptr, nullptr, nullptr);
+		j.enc->preRec = j.rec;
+		j.enc->prePool = j.pool;
 		j.outLen = lzma::enc_run(j.enc);
 		j.overflow = j.enc->overflow;
 	}
@@ -134,7 +139,7 @@ int64_t round_up_page(int64_t v, int page) { return v % page ? v + page - v % pa
 } // namespace
 
 struct BackendCtx {
-	DevBuf jobs, work, out, flags, offs;
+	DevBuf jobs, work, out, flags, offs, scratch;
 };
 
 BackendCtx *backend_create() { return new BackendCtx(); }
@@ -148,6 +153,7 @@ void backend_destroy(BackendCtx *b)
 	b->out.release();
 	b->flags.release();
 	b->offs.release();
+	b->scratch.release();
 	delete b;
 }
 
@@ -197,78 +203,171 @@ int backend_lz4_gate(BackendCtx *b, const uint8_t *d_src, int64_t len, int thres
 
 static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
+// All LZMA blocks of a chunk: K7a (match finder, data-parallel over positions and buckets) then K7b
+// (parser + range coder, one CTA per block).  Work arrays are laid out per block in one arena; blocks
+// are taken in waves when the arena does not fit in free HBM.  Payloads of all waves stay in b->out.
 static int run_lzma(BackendCtx *b, const lrzgpu_params &p, const lrzgpu_sizing_t &sz, std::vector<BlockJob> &jobs,
 		    const std::vector<int> &idx, cudaStream_t stream, int64_t *launches, char *err, size_t errlen)
 {
 	const uint32_t fb = p.level < 7 ? 32 : 64; // src/stream.c:455
+	if (lzma::mf_init_tables()) {
+		snprintf(err, errlen, "LZMA match finder tables: %s", cudaGetErrorString(cudaGetLastError()));
+		return LRZGPU_ECUDA;
+	}
+	// payload area for every block of the chunk
+	std::vector<size_t> oofs(idx.size());
+	std::vector<lzma::Config> cfgs(idx.size());
+	size_t osum = 0;
+	uint32_t maxCount = 0;
+	for (size_t k = 0; k < idx.size(); k++) {
+		const BlockJob &bj = jobs[idx[k]];
+		if (!lzma::make_config(p.level, sz.dict_size, fb, (uint64_t)bj.u_len, cfgs[k]) || fb > lzma::kMfMaxFb) {
+			snprintf(err, errlen, "LZMA level %d / block of %lld bytes is not supported by the device encoder", p.level,
+				 (long long)bj.u_len);
+			return LRZGPU_EUNSUPPORTED;
+		}
+		oofs[k] = osum;
+		osum += align_up((size_t)round_up_page((int64_t)((double)bj.u_len * 1.02), p.page_size), 256);
+		const uint32_t count = bj.u_len >= 4 ? (uint32_t)bj.u_len - 3 : 0;
+		if (count > maxCount)
+			maxCount = count;
+	}
+	const size_t scratch_bytes = align_up(lzma::mf_sort_scratch_bytes(maxCount), 256);
+	if (b->out.ensure(osum) != cudaSuccess || b->scratch.ensure(scratch_bytes) != cudaSuccess) {
+		snprintf(err, errlen, "out of device memory for LZMA payloads / sort scratch (%zu MiB)", (osum + scratch_bytes) >> 20);
+		return LRZGPU_ENOMEM;
+	}
 	size_t free_b = 0, total_b = 0;
 	cudaMemGetInfo(&free_b, &total_b);
-	const size_t budget = free_b + b->work.cap + b->out.cap - (1ull << 30);
+	const size_t budget = free_b + b->work.cap > (2ull << 30) ? free_b + b->work.cap - (1ull << 30) : free_b + b->work.cap;
 
+	struct Lay {
+		size_t enc, son, c2, c3, sorted, ctl, rec, pool, end;
+		uint64_t poolCap;
+	};
 	size_t at = 0;
+	unsigned poolMul = 12; // uint32 of match-list pool per input byte; text needs ~6-9, raised on overflow
 	while (at < idx.size()) {
-		// one wave = as many blocks as fit the memory budget
-		std::vector<LzmaJob> lj;
-		std::vector<size_t> wofs, oofs;
-		size_t wsum = 0, osum = 0, first = at;
+		std::vector<Lay> lay;
+		size_t wsum = 0, first = at;
 		for (; at < idx.size(); at++) {
-			const BlockJob &bj = jobs[idx[at]];
-			LzmaJob j;
-			memset(&j, 0, sizeof(j));
-			if (!lzma::make_config(p.level, sz.dict_size, fb, (uint64_t)bj.u_len, j.cfg)) {
-				snprintf(err, errlen, "LZMA level %d / block of %lld bytes is not supported by the device encoder",
-					 p.level, (long long)bj.u_len);
-				return LRZGPU_EUNSUPPORTED;
-			}
-			const size_t wneed = align_up(sizeof(lzma::Enc), 256) + align_up((lzma::kHash2Size + lzma::kHash3Size) * 4, 256) +
-					     align_up(j.cfg.hash4Entries * 4, 256) + align_up(j.cfg.sonEntries * 4, 256);
-			const size_t oneed = align_up((size_t)round_up_page((int64_t)((double)bj.u_len * 1.02), p.page_size), 256);
-			if (!lj.empty() && wsum + osum + wneed + oneed > budget)
+			const size_t n = (size_t)jobs[idx[at]].u_len, count = n >= 4 ? n - 3 : 0;
+			Lay L;
+			size_t o = wsum;
+			L.enc = o;
+			o += align_up(sizeof(lzma::Enc), 256);
+			L.son = o;
+			o += align_up(8 * (n + 2), 256);
+			L.c2 = o;
+			o += align_up(4 * count + 4, 256);
+			L.c3 = o;
+			o += align_up(4 * count + 4, 256);
+			L.sorted = o;
+			o += align_up(4 * count + 4, 256);
+			L.ctl = o; // cursor, overflow flag; zeroed together with rec
+			o += 256;
+			L.rec = o;
+			o += align_up(8 * n, 256);
+			L.pool = o;
+			L.poolCap = (uint64_t)poolMul * n + 65536;
+			o += align_up(4 * L.poolCap, 256);
+			L.end = o;
+			if (!lay.empty() && o > budget)
 				break;
-			j.src = bj.d_src;
-			j.n = (uint32_t)bj.u_len;
-			j.outCap = (uint64_t)round_up_page((int64_t)((double)bj.u_len * 1.02), p.page_size);
-			lj.push_back(j);
-			wofs.push_back(wsum);
-			oofs.push_back(osum);
-			wsum += wneed;
-			osum += oneed;
+			lay.push_back(L);
+			wsum = o;
 		}
-		if (b->work.ensure(wsum) != cudaSuccess || b->out.ensure(osum) != cudaSuccess ||
-		    b->jobs.ensure(lj.size() * sizeof(LzmaJob)) != cudaSuccess) {
-			snprintf(err, errlen, "out of device memory for %zu LZMA block encoders (%zu MiB)", lj.size(),
-				 (wsum + osum) >> 20);
+		if (b->work.ensure(wsum) != cudaSuccess || b->jobs.ensure(lay.size() * (sizeof(LzmaJob) + sizeof(lzma::MfBlock) + 8) + 64) != cudaSuccess) {
+			snprintf(err, errlen, "out of device memory for %zu LZMA block encoders (%zu MiB)", lay.size(), wsum >> 20);
 			return LRZGPU_ENOMEM;
 		}
-		for (size_t i = 0; i < lj.size(); i++) {
-			uint8_t *w = (uint8_t *)b->work.p + wofs[i];
-			lj[i].enc = (lzma::Enc *)w;
-			w += align_up(sizeof(lzma::Enc), 256);
-			lj[i].h2 = (uint32_t *)w;
-			lj[i].h3 = lj[i].h2 + lzma::kHash2Size;
-			w += align_up((lzma::kHash2Size + lzma::kHash3Size) * 4, 256);
-			lj[i].h4 = (uint32_t *)w;
-			w += align_up(lj[i].cfg.hash4Entries * 4, 256);
-			lj[i].son = (uint32_t *)w;
-			lj[i].out = (uint8_t *)b->out.p + oofs[i];
-			// MatchFinder_Init_HighHash / _LowHash: hash heads start empty (son entries are written before use)
-			const size_t hz = align_up((lzma::kHash2Size + lzma::kHash3Size) * 4, 256) + lj[i].cfg.hash4Entries * 4;
-			if (cudaMemsetAsync(lj[i].h2, 0, hz, stream) != cudaSuccess)
+		uint8_t *W = (uint8_t *)b->work.p;
+		std::vector<LzmaJob> lj(lay.size());
+		std::vector<lzma::MfBlock> mb(lay.size());
+		std::vector<uint64_t> seg(lay.size() + 1, 0);
+		for (size_t i = 0; i < lay.size(); i++) {
+			const BlockJob &bj = jobs[idx[first + i]];
+			const Lay &L = lay[i];
+			const lzma::Config &c = cfgs[first + i];
+			lzma::MfBlock &B = mb[i];
+			B.src = bj.d_src;
+			B.P.n = (uint32_t)bj.u_len;
+			B.P.fb = c.fb;
+			B.P.mc = c.mc;
+			B.P.hashMask = c.hashMask;
+			B.P.bigHash = c.bigHash;
+			B.P.historySize = c.historySize;
+			B.P.cyclicSize = c.cyclicSize;
+			B.count = bj.u_len >= 4 ? (uint32_t)bj.u_len - 3 : 0;
+			B.son = (uint32_t *)(W + L.son);
+			B.c2 = (uint32_t *)(W + L.c2);
+			B.c3 = (uint32_t *)(W + L.c3);
+			B.sorted = (uint32_t *)(W + L.sorted);
+			B.cursor = (unsigned long long *)(W + L.ctl);
+			B.overflow = (int *)(W + L.ctl + 8);
+			B.rec = (uint64_t *)(W + L.rec);
+			B.pool = (uint32_t *)(W + L.pool);
+			B.poolCap = L.poolCap;
+			seg[i + 1] = seg[i] + B.count;
+			LzmaJob &j = lj[i];
+			memset(&j, 0, sizeof(j));
+			j.src = bj.d_src;
+			j.n = (uint32_t)bj.u_len;
+			j.out = (uint8_t *)b->out.p + oofs[first + i];
+			j.outCap = (uint64_t)round_up_page((int64_t)((double)bj.u_len * 1.02), p.page_size);
+			j.enc = (lzma::Enc *)(W + L.enc);
+			j.rec = B.rec;
+			j.pool = B.pool;
+			j.cfg = c;
+			if (cudaMemsetAsync(W + L.ctl, 0, 256 + 8 * (size_t)bj.u_len, stream) != cudaSuccess)
 				return LRZGPU_ECUDA;
+			if (lzma::mf_prepare_block(B, b->scratch.p, stream, launches)) {
+				snprintf(err, errlen, "LZMA match finder sort: %s", cudaGetErrorString(cudaGetLastError()));
+				return LRZGPU_ECUDA;
+			}
 		}
-		if (cudaMemcpyAsync(b->jobs.p, lj.data(), lj.size() * sizeof(LzmaJob), cudaMemcpyHostToDevice, stream) != cudaSuccess)
+		// job table: [LzmaJob x m][MfBlock x m][segBase x (m + 1)]
+		uint8_t *J = (uint8_t *)b->jobs.p;
+		const size_t o_mb = lay.size() * sizeof(LzmaJob), o_seg = o_mb + lay.size() * sizeof(lzma::MfBlock);
+		if (cudaMemcpyAsync(J, lj.data(), o_mb, cudaMemcpyHostToDevice, stream) != cudaSuccess ||
+		    cudaMemcpyAsync(J + o_mb, mb.data(), lay.size() * sizeof(lzma::MfBlock), cudaMemcpyHostToDevice, stream) != cudaSuccess ||
+		    cudaMemcpyAsync(J + o_seg, seg.data(), seg.size() * 8, cudaMemcpyHostToDevice, stream) != cudaSuccess)
 			return LRZGPU_ECUDA;
-		lzma_block_kernel<<<(unsigned)lj.size(), 32, 0, stream>>>((LzmaJob *)b->jobs.p);
+		if (lzma::mf_walk_launch((const lzma::MfBlock *)(J + o_mb), (int)lay.size(), (const uint64_t *)(J + o_seg), seg.back(),
+					 stream, launches)) {
+			snprintf(err, errlen, "LZMA match finder walk: %s", cudaGetErrorString(cudaGetLastError()));
+			return LRZGPU_ECUDA;
+		}
+		// pool overflow check before the parser consumes the lists
+		std::vector<int> ovf(lay.size(), 0);
+		for (size_t i = 0; i < lay.size(); i++)
+			if (cudaMemcpyAsync(&ovf[i], mb[i].overflow, 4, cudaMemcpyDeviceToHost, stream) != cudaSuccess)
+				return LRZGPU_ECUDA;
+		cudaError_t ce = cudaStreamSynchronize(stream);
+		if (ce != cudaSuccess) {
+			snprintf(err, errlen, "LZMA match finder failed: %s", cudaGetErrorString(ce));
+			return LRZGPU_ECUDA;
+		}
+		bool any_ovf = false;
+		for (int v : ovf)
+			any_ovf = any_ovf || v;
+		if (any_ovf) { // redo this wave with a larger pool (worst case 2 * (fb - 3) + 4 words per position)
+			if (poolMul >= 2 * fb)
+				return LRZGPU_EINTERNAL;
+			poolMul = poolMul < 40 ? 40 : 2 * fb;
+			at = first;
+			continue;
+		}
+		lzma_block_kernel<<<(unsigned)lj.size(), 32, 0, stream>>>((LzmaJob *)J);
 		if (launches)
 			(*launches)++;
-		if (cudaMemcpyAsync(lj.data(), b->jobs.p, lj.size() * sizeof(LzmaJob), cudaMemcpyDeviceToHost, stream) != cudaSuccess)
+		if (cudaMemcpyAsync(lj.data(), J, o_mb, cudaMemcpyDeviceToHost, stream) != cudaSuccess)
 			return LRZGPU_ECUDA;
-		cudaError_t ce = cudaStreamSynchronize(stream);
+		ce = cudaStreamSynchronize(stream);
 		if (ce != cudaSuccess) {
 			snprintf(err, errlen, "LZMA kernel failed: %s", cudaGetErrorString(ce));
 			return LRZGPU_ECUDA;
 		}
-		const bool more_waves = at < idx.size();
 		for (size_t i = 0; i < lj.size(); i++) {
 			BlockJob &bj = jobs[idx[first + i]];
 			// src/stream.c:482-487: kept only when smaller; SZ_ERROR_OUTPUT_EOF leaves the block stored
@@ -277,11 +376,6 @@ static int run_lzma(BackendCtx *b, const lrzgpu_params &p, const lrzgpu_sizing_t
 				bj.c_len = (int64_t)lj[i].outLen;
 				bj.d_payload = lj[i].out;
 			}
-		}
-		if (more_waves) {
-			snprintf(err, errlen, "LZMA blocks of this chunk do not fit in device memory at once (%zu of %zu)", lj.size(),
-				 idx.size());
-			return LRZGPU_ENOMEM; // payloads of a wave would be overwritten by the next one
 		}
 	}
 	return LRZGPU_OK;

@@ -88,6 +88,9 @@ struct Enc {
 	uint32_t pbMask, lpMask, lc;
 	// ---- match finder (positions are 1-based: byte i has pos i + 1; 0 = empty)
 	uint32_t *hash2, *hash3, *hash4, *son;
+	// precomputed match lists (lzma_mf.cu): when preRec is set the serial finder above is not used
+	const uint64_t *preRec;
+	const uint32_t *prePool;
 	uint32_t pos;       // position the match finder will hand out next
 	uint32_t cycPos;
 	uint32_t crc[256];
@@ -532,6 +535,15 @@ LZ_INL void mf_hash23(const Enc *e, const uint8_t *cur, uint32_t &h2, uint32_t &
 // MatchFinderMt_GetMatches + MixMatches3 (LzFindMt.c:1274-1317, 1093-1131)
 LZ_FN inline uint32_t mf_get_matches(Enc *e, uint32_t *d)
 {
+	if (e->preRec) { // the data-parallel pre-pass already produced this position's list
+		const uint64_t rec = e->preRec[e->pos - 1];
+		const uint32_t nd = (uint32_t)rec & 1023u;
+		const uint32_t *s = e->prePool + (rec >> 10);
+		for (uint32_t i = 0; i < nd; i++)
+			d[i] = s[i];
+		e->pos++;
+		return nd;
+	}
 	uint32_t *bt = e->btTmp;
 	const uint32_t nbt = mf_tree_step(e, bt);
 	const uint32_t availAfter = mf_avail(e) - 1;
@@ -581,6 +593,10 @@ LZ_FN inline uint32_t mf_get_matches(Enc *e, uint32_t *d)
 // MatchFinderMt3_Skip (LzFindMt.c:1340-1350): the tree still sees every position
 LZ_FN inline void mf_skip(Enc *e, uint32_t num)
 {
+	if (e->preRec) {
+		e->pos += num;
+		return;
+	}
 	while (num--) {
 		mf_tree_step(e, e->btTmp);
 		if (mf_avail(e) >= 3) {
@@ -1173,6 +1189,8 @@ LZ_FN inline void enc_init(Enc *e, const Config &c, const uint8_t *src, uint32_t
 	e->lc = c.lc;
 	e->pbMask = (1u << c.pb) - 1;
 	e->lpMask = (0x100u << c.lp) - (0x100u >> c.lc);
+	e->preRec = nullptr;
+	e->prePool = nullptr;
 	e->hash2 = hash2;
 	e->hash3 = hash3;
 	e->hash4 = hash4;

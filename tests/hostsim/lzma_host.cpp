@@ -32,3 +32,73 @@ extern "C" int hostsim_lzma_encode(const uint8_t *src, int64_t n, int level, uin
 	*out_len = (int64_t)len;
 	return ovf ? 1 : 0;
 }
+
+// The same encoder over the match lists of the data-parallel pre-pass (lzma_mf.cuh), computed here the
+// way lzma_mf.cu does it -- positions grouped by hash, buckets processed one after another in HASH order
+// (not in position order) -- to check on the CPU that bucket-wise insertion reproduces the serial finder.
+#include <algorithm>
+#include <chrono>
+#include <numeric>
+#include <vector>
+
+#include "../../lrzip_next_b200/csrc/lzma_mf.cuh"
+
+extern "C" {
+double hostsim_last_parse_seconds = 0; // parser + range coder alone (development aid)
+}
+
+extern "C" int hostsim_lzma_encode_pre(const uint8_t *src, int64_t n, int level, uint32_t dict, uint32_t fb, uint8_t *out,
+				       int64_t cap, int64_t *out_len, int64_t *pool_words)
+{
+	Config c;
+	if (!make_config(level, dict, fb, (uint64_t)n, c))
+		return -1;
+	uint32_t crc[256];
+	for (uint32_t i = 0; i < 256; i++)
+		crc[i] = mf_crc_entry(i);
+	MfParams P = { (uint32_t)n, c.fb, c.mc, c.hashMask, c.bigHash, c.historySize, c.cyclicSize };
+	const uint32_t count = n >= 4 ? (uint32_t)n - 3 : 0;
+	std::vector<uint32_t> c2(count), c3(count), order(count), son(2 * ((size_t)n + 2));
+	std::vector<uint64_t> rec((size_t)n, 0);
+	std::vector<uint32_t> pool;
+	auto prev_by = [&](auto keyf, std::vector<uint32_t> &dst) {
+		std::iota(order.begin(), order.end(), 0u);
+		std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return keyf(a) < keyf(b); });
+		for (uint32_t s = 0; s < count; s++)
+			dst[order[s]] = (s > 0 && keyf(order[s - 1]) == keyf(order[s])) ? order[s - 1] + 1 : 0;
+	};
+	prev_by([&](uint32_t i) { return mf_hash2(crc, src + i); }, c2);
+	prev_by([&](uint32_t i) { return mf_hash3(crc, src + i); }, c3);
+	auto h4 = [&](uint32_t i) { return mf_hash4(crc, src + i, P.hashMask, P.bigHash); };
+	std::iota(order.begin(), order.end(), 0u);
+	std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return h4(a) < h4(b); });
+	uint32_t d[2 * 273 + 8];
+	for (uint32_t s = 0; s < count;) {
+		const uint32_t hv = h4(order[s]);
+		uint32_t prev = 0;
+		for (; s < count && h4(order[s]) == hv; s++) {
+			const uint32_t i = order[s], pos = i + 1;
+			const uint32_t nbt = mf_bt_insert(src, P, son.data(), pos, prev, d + 4);
+			const uint32_t nd = mf_mix(src, P, pos, c2[i], c3[i], d, nbt);
+			rec[i] = ((uint64_t)pool.size() << kMfCountBits) | nd;
+			pool.insert(pool.end(), d, d + nd);
+			prev = pos;
+		}
+	}
+	if (pool_words)
+		*pool_words = (int64_t)pool.size();
+	pool.push_back(0);
+	Enc *e = (Enc *)malloc(sizeof(Enc));
+	if (!e)
+		return -2;
+	enc_init(e, c, src, (uint32_t)n, out, (uint64_t)cap, nullptr, nullptr, nullptr, nullptr);
+	e->preRec = rec.data();
+	e->prePool = pool.data();
+	const auto t0 = std::chrono::steady_clock::now();
+	const uint64_t len = enc_run(e);
+	hostsim_last_parse_seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+	const int ovf = e->overflow;
+	free(e);
+	*out_len = (int64_t)len;
+	return ovf ? 1 : 0;
+}

@@ -29,6 +29,7 @@ def hostsim():
     Z = C.CDLL(os.path.join(HERE, "hostsim", "liblzmahost.so"))
     Z.hostsim_lzma_encode.argtypes = [C.c_void_p, C.c_int64, C.c_int, C.c_uint32, C.c_uint32, C.c_void_p, C.c_int64,
                                       C.POINTER(C.c_int64)]
+    Z.hostsim_lzma_encode_pre.argtypes = Z.hostsim_lzma_encode.argtypes + [C.POINTER(C.c_int64)]
     L = C.CDLL(os.path.join(HERE, "hostsim", "liblz4host.so"))
     L.hostsim_lz4_size.argtypes = [C.c_char_p, C.c_int, C.c_int]
     L.hostsim_lz4_gate.argtypes = [C.c_char_p, C.c_int64, C.c_int]
@@ -64,6 +65,31 @@ def _lzma(Z, data, level, dic):
     out, ol = C.create_string_buffer(max(cap, 1)), C.c_int64()
     rc = Z.hostsim_lzma_encode(data, n, level, dic, 32 if level < 7 else 64, out, cap, C.byref(ol))
     return None if (rc != 0 or ol.value >= n) else out.raw[:ol.value]
+
+
+def _lzma_pre(Z, data, level, dic):
+    n = len(data)
+    cap = int(n * 1.02)
+    cap += (-cap) % 4096
+    out, ol, pw = C.create_string_buffer(max(cap, 1)), C.c_int64(), C.c_int64()
+    rc = Z.hostsim_lzma_encode_pre(data, n, level, dic, 32 if level < 7 else 64, out, cap, C.byref(ol), C.byref(pw))
+    return (None if (rc != 0 or ol.value >= n) else out.raw[:ol.value]), pw.value
+
+
+def test_lzma_bucketwise_match_finder_equals_serial(hostsim):
+    """The data-parallel pre-pass (positions grouped by hash, one bucket at a time) must hand the encoder
+    exactly what the serial two-thread finder does -- including when the block is longer than the
+    dictionary (cyclic buffer wraps in the reference, flat tree array here)."""
+    rng = np.random.default_rng(9)
+    cases = [datagen.gen_text(600_000).tobytes(), bytes(200_000), rng.integers(0, 256, 50_000, dtype=np.uint8).tobytes(),
+             datagen.gen_vm(1 << 20).tobytes(), datagen.gen_rep(1 << 20, block=1 << 14).tobytes(), b"ab" * 40, b"abc",
+             rng.integers(0, 4, 200_000, dtype=np.uint8).tobytes(), datagen.gen_trees(700_000).tobytes()]
+    for d in cases:
+        for level, dic in ((7, 1 << 25), (5, 1 << 24), (7, 1 << 16), (9, 1 << 12)):
+            got, words = _lzma_pre(hostsim[1], d, level, dic)
+            assert got == _lzma(hostsim[1], d, level, dic), (len(d), level, dic)
+            assert words <= (2 * 61 + 4) * len(d)
+            print(len(d), level, dic, words / max(1, len(d)))
 
 
 def test_lzma_encoder_matches_golden(hostsim):
