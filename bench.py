@@ -300,8 +300,8 @@ def main():
     if rank == 0:
         rl = params.rzip_level or params.level
         initial_freq = [4, 4, 4, 4, 4, 4, 2, 1, 1, 1][rl]
-        tiles = (size + 4095) // 4096
-        cand = torch.empty(tiles * 4096 * 2, dtype=torch.int64, device=dev)
+        tiles = (size + 511) // 512
+        cand = torch.empty(tiles * 512 * 2, dtype=torch.int64, device=dev)
         tcnt = torch.empty(tiles, dtype=torch.int32, device=dev)
         stream = torch.cuda.current_stream().cuda_stream
         mask = (1 << initial_freq) - 1

@@ -139,8 +139,8 @@ int lrzgpu_block_compress(lrzgpu_ctx *ctx, const lrzgpu_params *p, uint32_t dict
 int lrzgpu_lz4_gate(lrzgpu_ctx *ctx, const uint8_t *in, int64_t len, int threshold, int *compressible);
 
 /* ---- measurement hooks (bench.py): kernels on caller-provided device buffers and stream ------- */
-/* K1 over a device-resident chunk: d_cand needs 16 * round_up(n, 4096) bytes, d_tile_count
- * 4 * ceil(n / 4096) bytes.  `stream` is a cudaStream_t (0 = default stream). */
+/* K1 over a device-resident chunk: d_cand needs 16 * round_up(n, 512) bytes, d_tile_count
+ * 4 * ceil(n / 512) bytes (candidate tiles are 512 positions).  `stream` is a cudaStream_t (0 = default stream). */
 int lrzgpu_k1_launch(lrzgpu_ctx *ctx, const void *d_buf, int64_t n, int64_t mask, void *d_cand,
 		     void *d_tile_count, void *stream);
 int lrzgpu_crc32_launch(lrzgpu_ctx *ctx, const void *d_buf, int64_t n, void *d_crc, void *stream);

@@ -15,7 +15,10 @@
 #include "backend.h"
 
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
+
+#include <chrono>
 
 #include <vector>
 
@@ -82,16 +85,24 @@ struct LzmaJob {
 	int overflow;
 };
 
-// K7b: optimal parser + range coder, one block per CTA, over the precomputed match lists.
-__global__ void __launch_bounds__(32) lzma_block_kernel(LzmaJob *jobs)
+// K7b: optimal parser + range coder, one block per CTA = one warp, over the precomputed match lists.
+// The whole encoder state (probabilities, price tables, the 2048-cell parse table: 135 KB) lives in the
+// SM's shared memory; the warp runs the encoder cooperatively (lzma_enc.cuh: replicated scalar code,
+// lane-split loops).
+__global__ void __launch_bounds__(32, 1) lzma_block_kernel(LzmaJob *jobs)
 {
+	extern __shared__ __align__(16) uint8_t lzma_smem[];
+	lzma::Enc *e = reinterpret_cast<lzma::Enc *>(lzma_smem);
+	LzmaJob &j = jobs[blockIdx.x];
+	lzma::enc_init(e, j.cfg, j.src, j.n, j.out, j.outCap, nullptr, nullptr, nullptr, nullptr);
+	e->preRec = j.rec;
+	e->prePool = j.pool;
+	__syncwarp();
+	const uint64_t len = lzma::enc_run(e);
+	__syncwarp();
 	if (threadIdx.x == 0) {
-		LzmaJob &j = jobs[blockIdx.x];
-		lzma::enc_init(j.enc, j.cfg, j.src, j.n, j.out, j.outCap, nullptr, nullptr, nullptr, nullptr);
-		j.enc->preRec = j.rec;
-		j.enc->prePool = j.pool;
-		j.outLen = lzma::enc_run(j.enc);
-		j.overflow = j.enc->overflow;
+		j.outLen = len;
+		j.overflow = e->overflow;
 	}
 }
 
@@ -250,6 +261,7 @@ static int run_lzma(BackendCtx *b, const lrzgpu_params &p, const lrzgpu_sizing_t
 	while (at < idx.size()) {
 		std::vector<Lay> lay;
 		size_t wsum = 0, first = at;
+		const auto t_wave = std::chrono::steady_clock::now();
 		for (; at < idx.size(); at++) {
 			const size_t n = (size_t)jobs[idx[at]].u_len, count = n >= 4 ? n - 3 : 0;
 			Lay L;
@@ -348,6 +360,7 @@ static int run_lzma(BackendCtx *b, const lrzgpu_params &p, const lrzgpu_sizing_t
 			snprintf(err, errlen, "LZMA match finder failed: %s", cudaGetErrorString(ce));
 			return LRZGPU_ECUDA;
 		}
+		const auto t_mf = std::chrono::steady_clock::now();
 		bool any_ovf = false;
 		for (int v : ovf)
 			any_ovf = any_ovf || v;
@@ -358,7 +371,11 @@ static int run_lzma(BackendCtx *b, const lrzgpu_params &p, const lrzgpu_sizing_t
 			at = first;
 			continue;
 		}
-		lzma_block_kernel<<<(unsigned)lj.size(), 32, 0, stream>>>((LzmaJob *)J);
+		if (cudaFuncSetAttribute(lzma_block_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(lzma::Enc)) != cudaSuccess) {
+			snprintf(err, errlen, "LZMA encoder state (%zu bytes) does not fit in shared memory", sizeof(lzma::Enc));
+			return LRZGPU_ECUDA;
+		}
+		lzma_block_kernel<<<(unsigned)lj.size(), 32, sizeof(lzma::Enc), stream>>>((LzmaJob *)J);
 		if (launches)
 			(*launches)++;
 		if (cudaMemcpyAsync(lj.data(), J, o_mb, cudaMemcpyDeviceToHost, stream) != cudaSuccess)
@@ -367,6 +384,13 @@ static int run_lzma(BackendCtx *b, const lrzgpu_params &p, const lrzgpu_sizing_t
 		if (ce != cudaSuccess) {
 			snprintf(err, errlen, "LZMA kernel failed: %s", cudaGetErrorString(ce));
 			return LRZGPU_ECUDA;
+		}
+		if (getenv("LRZGPU_DEBUG")) {
+			const auto t_end = std::chrono::steady_clock::now();
+			fprintf(stderr, "[lrzgpu] lzma wave: %zu blocks, %llu positions, arena %zu MiB, match finder %.1f ms, parser %.1f ms\n",
+				lj.size(), (unsigned long long)seg.back(), wsum >> 20,
+				std::chrono::duration<double, std::milli>(t_mf - t_wave).count(),
+				std::chrono::duration<double, std::milli>(t_end - t_mf).count());
 		}
 		for (size_t i = 0; i < lj.size(); i++) {
 			BlockJob &bj = jobs[idx[first + i]];

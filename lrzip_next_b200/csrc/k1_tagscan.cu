@@ -7,24 +7,25 @@
 //
 // Every position p in [1, n-31] whose tag satisfies (tag & mask) == mask becomes one 16-byte
 // candidate record {pos, tag} (layout of struct hash_entry, src/rzip.c:61-64).  Records of tile
-// T (positions [T*4096, (T+1)*4096)) are written, in position order, to the tile-strided region
-// cand[T*4096 ...] and their number to tile_count[T]; no cross-CTA dependency exists.
+// T (positions [T*512, (T+1)*512)) are written, in position order, to the tile-strided region
+// cand[T*512 ...] and their number to tile_count[T]; no cross-CTA (or cross-warp) dependency exists.
 //
 // HBM traffic (the algorithmic bytes of SURVEY.md 8(d)): 1 byte read per position + 16 bytes
 // written per candidate = 1 + 16 * 2^-initial_freq bytes per input byte (9 B/B at rzip level 7).
 //
-// Structure (persistent CTAs, 256 threads, one 4096-position tile per iteration):
-//   * the input tile (+32 B halo) is staged global -> shared by the TMA engine (cp.async.bulk with
-//     an mbarrier transaction count), double buffered, so the load of tile i+1 overlaps tile i;
+// Structure (persistent CTAs, 256 threads = 8 warps, one 4096-byte step per iteration; a candidate
+// tile is 512 positions = one warp's share of the step, so tiles never need a cross-warp prefix):
+//   * the step's bytes (+32 B halo) are staged global -> shared by the TMA engine (cp.async.bulk with
+//     an mbarrier transaction count), double buffered, so the load of step i+1 overlaps step i;
 //   * phase A: thread t owns the 16 bytes of slot t, XOR-accumulates hash_index over them through a
 //     16-way replicated 64-bit table in shared memory (lanes l and l+16 are in different 64-bit
-//     phases, so lookups are bank-conflict free); a shuffle XOR-scan over the slot totals turns the
-//     local prefixes into the tile-wide running XOR Z[i] = XOR_{b < i} hash_index[byte b], stored
-//     with one pad word per 16 entries so that both phases are conflict free;
-//   * phase B: transposed -- lane l of a warp takes position 32*j + l, so that the survivors of one
-//     ballot are consecutive positions and their 16-byte records form one contiguous run in HBM:
-//       tag(q) = Z[q + 31] ^ Z[q]                                   (two shared-memory reads)
-//   * warp ballots + a CTA prefix place every record; stores are 16 B per lane, contiguous per warp.
+//     phases, so lookups are bank-conflict free); a shuffle XOR-scan inside the warp turns the local
+//     prefixes into the WARP-relative running XOR Z[i] = XOR_{512w <= b < i} hash_index[byte b],
+//     stored with one pad word per 16 entries so that both phases are conflict free;
+//   * phase B, fused with the output: lane l of warp w takes position 512w + 32j + l, so that the
+//     survivors of one ballot are consecutive positions and their 16-byte records form one contiguous
+//     run in HBM:   tag(q) = Z[q + 31] ^ Z[q]  (^ the warp's total when q + 31 is in the next warp's
+//     share); ballot, 16 B store per surviving lane at the warp's running count.
 #include "kernels.h"
 
 #include <cuda_runtime.h>
@@ -35,17 +36,18 @@ __constant__ int64_t c_hash_index[256];
 
 static constexpr int K1_THREADS = 256;
 static constexpr int K1_WARPS = K1_THREADS / 32;
-static constexpr int K1_IN_BYTES = kTile + 32;       // tile + halo, multiple of 16
-static constexpr int K1_Z = kTile + 32 + 1;          // running XORs Z[0..4128], Z[0] = 0
+static constexpr int K1_STEP = K1_WARPS * kTile;     // 4096 bytes per CTA iteration
+static constexpr int K1_IN_BYTES = K1_STEP + 32;     // step + halo, multiple of 16
+static constexpr int K1_Z = K1_STEP + 32 + 1;        // running XORs Z[0..4128]
 static constexpr int K1_ZPAD = K1_Z + K1_Z / 16 + 2; // one pad word per 16 entries: conflict-free columns
 static constexpr int K1_SMEM_TABLE = 256 * 16 * 8;
 static constexpr int K1_SMEM_Z = ((K1_ZPAD * 8 + 127) / 128) * 128;
 static constexpr int K1_SMEM_IN = 2 * K1_IN_BYTES;
 static constexpr int K1_OFF_Z = K1_SMEM_TABLE;
 static constexpr int K1_OFF_IN = K1_OFF_Z + K1_SMEM_Z;
-static constexpr int K1_OFF_WSUM = K1_OFF_IN + K1_SMEM_IN;
-static constexpr int K1_OFF_BAR = K1_OFF_WSUM + 128;
+static constexpr int K1_OFF_BAR = ((K1_OFF_IN + K1_SMEM_IN + 15) / 16) * 16;
 static constexpr int K1_SMEM = K1_OFF_BAR + 32;
+static_assert(kTile == 512, "one candidate tile per warp and step");
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -73,10 +75,9 @@ __device__ __forceinline__ void tma_load_1d(void *dst, const void *src, unsigned
 		     ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
 
-__device__ __forceinline__ void st_cand(Cand *dst, int64_t pos, uint32_t tlo, uint32_t thi)
+__device__ __forceinline__ void st_cand(Cand *dst, uint32_t plo, uint32_t phi, uint32_t tlo, uint32_t thi)
 {
-	asm volatile("{\n\t.reg .b64 t;\n\tmov.b64 t, {%2,%3};\n\tst.global.cs.v2.u64 [%0], {%1,t};\n\t}"
-		     ::"l"(dst), "l"(pos), "r"(tlo), "r"(thi) : "memory");
+	asm volatile("st.global.cs.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(dst), "r"(plo), "r"(phi), "r"(tlo), "r"(thi) : "memory");
 }
 
 __device__ __forceinline__ uint64_t shfl_up64(uint64_t v, int d)
@@ -88,45 +89,51 @@ __device__ __forceinline__ uint64_t shfl_up64(uint64_t v, int d)
 
 __device__ __forceinline__ int zidx(int j) { return j + (j >> 4); }
 
-// tag(q) = Z[q + 31] ^ Z[q] with Z the running XOR of hash_index over the tile's bytes (Z[0] = 0).
+// Phase B for one warp: tags of positions base + 32 j + lane (base = start of the warp's tile), survivors
+// stored in position order at dst; returns their number.  z points at the padded Z entry of the tile start.
 template <bool kInterior>
-__device__ __forceinline__ void k1_phase_b(const uint64_t *__restrict__ z, int warp, int lane, int64_t base, int64_t lo,
-					   int64_t hi, uint32_t mlo, uint32_t mhi, uint32_t tags_lo[16], uint32_t tags_hi[16],
-					   uint32_t ballots[16], uint32_t &wtotal)
+__device__ __forceinline__ uint32_t k1_phase_b(const uint64_t *__restrict__ z, int zq0, int lane, int64_t base, int64_t lo,
+					       int64_t hi, uint32_t mlo, uint32_t mhi, Cand *__restrict__ dst)
 {
-	const int q0 = warp * 512 + lane;
-	const uint64_t *za = z + zidx(q0), *zb = z + zidx(q0 + 31);
-	// lo / hi as offsets inside the tile (only used when the tile straddles the valid range)
+	const uint64_t *za = z + zidx(zq0 + lane), *zb = z + zidx(zq0 + lane + 31);
+	const uint64_t wtot = z[zidx(zq0 + kTile)]; // XOR over the warp's whole share
 	const int l0 = (int)(lo - base), h0 = (int)(hi - base);
-	wtotal = 0;
+	const uint32_t lt = (1u << lane) - 1;
+	const uint32_t pos_hi = (uint32_t)((uint64_t)base >> 32), pos_lo = (uint32_t)base + (uint32_t)lane;
+	uint32_t cnt = 0;
 #pragma unroll
 	for (int j = 0; j < 16; j++) {
 		// 32 positions further = 34 padded words further
-		const uint64_t tg = za[34 * j] ^ zb[34 * j];
+		uint64_t a = za[34 * j];
+		const uint64_t b = zb[34 * j];
+		if (j == 0 && lane == 0)
+			a = 0; // Z at the tile start holds the previous warp's total
+		uint64_t tg = a ^ b;
+		if (j == 15 && lane >= 2)
+			tg ^= wtot; // q + 31 lies in the next warp's share, whose Z restarts at 0
 		const uint32_t tl = (uint32_t)tg, th = (uint32_t)(tg >> 32);
-		tags_lo[j] = tl;
-		tags_hi[j] = th;
 		bool ok = (tl & mlo) == mlo && (th & mhi) == mhi;
 		if (!kInterior) {
-			const int q = q0 + 32 * j;
+			const int q = 32 * j + lane;
 			ok = ok && q >= l0 && q < h0;
 		}
-		ballots[j] = __ballot_sync(0xffffffffu, ok);
-		wtotal += __popc(ballots[j]);
+		const uint32_t bm = __ballot_sync(0xffffffffu, ok);
+		if (ok)
+			st_cand(dst + cnt + __popc(bm & lt), pos_lo + 32 * j, pos_hi, tl, th);
+		cnt += __popc(bm);
 	}
+	return cnt;
 }
 
-__global__ void __launch_bounds__(K1_THREADS, 2)
+__global__ void __launch_bounds__(K1_THREADS, 3)
 k1_tagscan_kernel(const uint8_t *__restrict__ buf, int64_t n, int64_t pos_lo, int64_t pos_hi, int64_t mask_arg,
 		  const ScanState *__restrict__ state, Cand *__restrict__ cand, uint32_t *__restrict__ tile_count,
-		  int64_t first_tile, int64_t num_tiles)
+		  int64_t first_tile, int64_t num_tiles, int64_t first_step, int64_t num_steps)
 {
 	extern __shared__ __align__(128) uint8_t smem[];
 	uint64_t *tab = reinterpret_cast<uint64_t *>(smem);                // tab[b * 16 + (lane & 15)]
-	uint64_t *z = reinterpret_cast<uint64_t *>(smem + K1_OFF_Z);       // padded running XORs
+	uint64_t *z = reinterpret_cast<uint64_t *>(smem + K1_OFF_Z);       // padded warp-relative running XORs
 	uint8_t *in = smem + K1_OFF_IN;
-	uint64_t *wxor = reinterpret_cast<uint64_t *>(smem + K1_OFF_WSUM); // per-warp XOR totals (8) + halo (2)
-	uint32_t *wsum = reinterpret_cast<uint32_t *>(smem + K1_OFF_WSUM + 96);
 	uint64_t *bar = reinterpret_cast<uint64_t *>(smem + K1_OFF_BAR);
 
 	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -145,7 +152,6 @@ k1_tagscan_kernel(const uint8_t *__restrict__ buf, int64_t n, int64_t pos_lo, in
 	for (int i = tid; i < 256 * 16; i += K1_THREADS)
 		tab[i] = (uint64_t)c_hash_index[i >> 4];
 	if (tid == 0) {
-		z[0] = 0;
 		mbar_init(&bar[0], 1);
 		mbar_init(&bar[1], 1);
 		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -157,26 +163,25 @@ k1_tagscan_kernel(const uint8_t *__restrict__ buf, int64_t n, int64_t pos_lo, in
 	const int64_t vhi = (pos_hi < n - kMinMatch + 1) ? pos_hi : n - kMinMatch + 1;
 	const uint64_t *my_tab = tab + (lane & 15);
 
-	int64_t t = blockIdx.x;
-	if (t < num_tiles && tid == 0) {
+	int64_t s = blockIdx.x;
+	if (s < num_steps && tid == 0) {
 		mbar_expect_tx(&bar[0], K1_IN_BYTES);
-		tma_load_1d(in, buf + (first_tile + t) * (int64_t)kTile, K1_IN_BYTES, &bar[0]);
+		tma_load_1d(in, buf + (first_step + s) * (int64_t)K1_STEP, K1_IN_BYTES, &bar[0]);
 	}
-	for (int it = 0; t < num_tiles; t += gridDim.x, it++) {
+	for (int it = 0; s < num_steps; s += gridDim.x, it++) {
 		const int stage = it & 1;
 		const unsigned parity = (it >> 1) & 1;
-		const int64_t tile = first_tile + t;
-		const int64_t base = tile * (int64_t)kTile;
-		if (tid == 0 && t + gridDim.x < num_tiles) { // prefetch the next tile into the other stage
+		const int64_t step = first_step + s;
+		if (tid == 0 && s + gridDim.x < num_steps) { // prefetch the next step into the other stage
 			mbar_expect_tx(&bar[stage ^ 1], K1_IN_BYTES);
-			tma_load_1d(in + (stage ^ 1) * K1_IN_BYTES, buf + (tile + gridDim.x) * (int64_t)kTile, K1_IN_BYTES,
+			tma_load_1d(in + (stage ^ 1) * K1_IN_BYTES, buf + (step + gridDim.x) * (int64_t)K1_STEP, K1_IN_BYTES,
 				    &bar[stage ^ 1]);
 		}
 		mbar_wait(&bar[stage], parity);
 
-		// ---- phase A: running XOR of hash_index over the tile (+ halo): local prefix, CTA scan, publish
-		uint64_t x[16];
+		// ---- phase A: warp-relative running XOR of hash_index over the step (+ halo)
 		{
+			uint64_t x[16];
 			const uint4 v = *reinterpret_cast<const uint4 *>(in + stage * K1_IN_BYTES + tid * 16);
 			const uint32_t w[4] = { v.x, v.y, v.z, v.w };
 			uint64_t acc = 0;
@@ -186,83 +191,47 @@ k1_tagscan_kernel(const uint8_t *__restrict__ buf, int64_t n, int64_t pos_lo, in
 				acc ^= my_tab[b * 16];
 				x[j] = acc;
 			}
-		}
-		uint64_t hx[16]; // halo slots 256, 257 (threads 0, 1)
-		if (tid < 2) {
-			const uint4 hv = *reinterpret_cast<const uint4 *>(in + stage * K1_IN_BYTES + (K1_THREADS + tid) * 16);
-			const uint32_t hw[4] = { hv.x, hv.y, hv.z, hv.w };
-			uint64_t hacc = 0;
+			uint64_t incl = acc; // inclusive XOR scan of the slot totals inside the warp
 #pragma unroll
-			for (int j = 0; j < 16; j++) {
-				const uint32_t b = (hw[j >> 2] >> ((j & 3) * 8)) & 0xffu;
-				hacc ^= my_tab[b * 16];
-				hx[j] = hacc;
+			for (int d = 1; d < 32; d <<= 1) {
+				const uint64_t o = shfl_up64(incl, d);
+				if (lane >= d)
+					incl ^= o;
 			}
-			wxor[K1_WARPS + tid] = hacc;
-		}
-		uint64_t incl = x[15]; // inclusive XOR scan of the slot totals inside the warp
-#pragma unroll
-		for (int d = 1; d < 32; d <<= 1) {
-			const uint64_t o = shfl_up64(incl, d);
-			if (lane >= d)
-				incl ^= o;
-		}
-		if (lane == 31)
-			wxor[warp] = incl;
-		__syncthreads();
-		uint64_t off = incl ^ x[15]; // exclusive
-#pragma unroll
-		for (int w = 0; w < K1_WARPS; w++)
-			if (w < warp)
-				off ^= wxor[w];
-		{
+			const uint64_t off = incl ^ acc; // exclusive
 			uint64_t *dst = z + 1 + tid * 16;
 			const int pad = (tid * 16 + 1) >> 4; // = tid
 #pragma unroll
 			for (int j = 0; j < 16; j++)
 				dst[pad + (j == 15 ? 1 : 0) + j] = off ^ x[j];
 		}
-		if (tid < 2) {
-			uint64_t hoff = 0;
+		if (warp == K1_WARPS - 1) { // halo: one byte per lane, XOR scan, Z relative to the end of the step
+			const uint32_t b = in[stage * K1_IN_BYTES + K1_STEP + lane];
+			uint64_t incl = my_tab[b * 16];
 #pragma unroll
-			for (int w = 0; w < K1_WARPS; w++)
-				hoff ^= wxor[w];
-			if (tid == 1)
-				hoff ^= wxor[K1_WARPS];
-#pragma unroll
-			for (int j = 0; j < 16; j++)
-				z[zidx(1 + (K1_THREADS + tid) * 16 + j)] = hoff ^ hx[j];
+			for (int d = 1; d < 32; d <<= 1) {
+				const uint64_t o = shfl_up64(incl, d);
+				if (lane >= d)
+					incl ^= o;
+			}
+			z[zidx(K1_STEP + 1 + lane)] = incl;
 		}
 		__syncthreads();
 
-		// ---- phase B: tags of positions base + warp*512 + 32*j + lane, survivors by ballot
-		uint32_t tags_lo[16], tags_hi[16], ballots[16], wtotal;
-		if (base >= vlo && base + kTile <= vhi)
-			k1_phase_b<true>(z, warp, lane, base, vlo, vhi, mlo, mhi, tags_lo, tags_hi, ballots, wtotal);
-		else
-			k1_phase_b<false>(z, warp, lane, base, vlo, vhi, mlo, mhi, tags_lo, tags_hi, ballots, wtotal);
-		if (lane == 0)
-			wsum[warp] = wtotal;
-		__syncthreads(); // also: every read of z / in[stage] is done before they are overwritten
-		uint32_t woff = 0, total = 0;
-#pragma unroll
-		for (int w = 0; w < K1_WARPS; w++) {
-			const uint32_t sm = wsum[w];
-			woff += (w < warp) ? sm : 0;
-			total += sm;
+		// ---- phase B: warp w owns candidate tile step * 8 + w
+		const int64_t t = step * K1_WARPS + warp - first_tile;
+		if (t >= 0 && t < num_tiles) {
+			const int64_t base = (first_tile + t) * (int64_t)kTile;
+			Cand *dst = cand + t * (int64_t)kTile;
+			uint32_t cnt;
+			if (base >= vlo && base + kTile <= vhi)
+				cnt = k1_phase_b<true>(z, warp * kTile, lane, base, vlo, vhi, mlo, mhi, dst);
+			else
+				cnt = k1_phase_b<false>(z, warp * kTile, lane, base, vlo, vhi, mlo, mhi, dst);
+			if (lane == 0)
+				tile_count[t] = cnt;
 		}
-		Cand *dst = cand + t * (int64_t)kTile + woff;
-		const uint32_t lt = (1u << lane) - 1;
-		const int64_t q0 = base + warp * 512 + lane;
-#pragma unroll
-		for (int j = 0; j < 16; j++) {
-			const uint32_t bm = ballots[j];
-			if ((bm >> lane) & 1)
-				st_cand(dst + __popc(bm & lt), q0 + 32 * j, tags_lo[j], tags_hi[j]);
-			dst += __popc(bm);
-		}
-		if (tid == 0)
-			tile_count[t] = total;
+		__syncthreads(); // every read of z / in[stage] is done before they are overwritten
 	}
 }
 
@@ -285,11 +254,13 @@ int k1_launch(const uint8_t *d_buf, int64_t n, int64_t pos_lo, int64_t pos_hi, i
 	const int64_t first_tile = pos_lo / kTile;
 	const int64_t last_tile = (pos_hi - 1) / kTile;
 	const int64_t num_tiles = last_tile - first_tile + 1;
-	int64_t grid = (int64_t)num_sms * 2;
-	if (grid > num_tiles)
-		grid = num_tiles;
+	const int64_t first_step = pos_lo / K1_STEP;
+	const int64_t num_steps = (pos_hi - 1) / K1_STEP - first_step + 1;
+	int64_t grid = (int64_t)num_sms * 3;
+	if (grid > num_steps)
+		grid = num_steps;
 	k1_tagscan_kernel<<<(unsigned)grid, K1_THREADS, K1_SMEM, stream>>>(
-		d_buf, n, pos_lo, pos_hi, mask, d_state, d_cand, d_tile_count, first_tile, num_tiles);
+		d_buf, n, pos_lo, pos_hi, mask, d_state, d_cand, d_tile_count, first_tile, num_tiles, first_step, num_steps);
 	return cudaGetLastError() == cudaSuccess ? 0 : -1;
 }
 

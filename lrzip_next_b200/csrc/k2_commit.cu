@@ -454,12 +454,17 @@ static constexpr int K2_MAXEQ = 16; // equal-tag entries one lane may meet in it
 static constexpr int K2_WIDE = 8; // slots fetched per step of a lane's private probe walk (independent loads)
 
 __device__ void lane_eval(const uint8_t *__restrict__ buf, const HEntry *tab, unsigned hmask, int64_t p, int64_t t,
-			  int64_t tag_mask, int64_t better, int max_chain, int64_t end, int64_t last_match, LaneEval &L)
+			  int64_t tag_mask, int64_t better, int max_chain, int64_t end, int64_t last_match, int pf_lines,
+			  LaneEval &L)
 {
 	L.nw = L.nr = L.net = L.ins = L.miss = 0;
 	L.cx = false;
 	const bool do_insert = (t & tag_mask) == tag_mask;
 	const unsigned h = (unsigned)t & hmask;
+	// inserted tags have all gate bits set, so homes cluster every 2^bits slots and a probe chain is about
+	// 2/3 * 2^bits slots long: pull the expected span of the chain into L1 before walking it
+	for (int l = 1; l <= pf_lines; l++)
+		prefetch_l1(tab + ((h + 8u * (unsigned)l) & hmask));
 	const int my_ones = tz_ones(t);
 	bool stop = !do_insert;
 	int kind = -1, round = 0;
@@ -475,6 +480,7 @@ __device__ void lane_eval(const uint8_t *__restrict__ buf, const HEntry *tab, un
 			return;
 		}
 		HEntry e[K2_WIDE];
+		prefetch_l1(tab + ((h + s + 8u * (unsigned)(pf_lines + 1)) & hmask));
 #pragma unroll
 		for (int k = 0; k < K2_WIDE; k++)
 			e[k] = ld_entry(tab + ((h + s + k) & hmask));
@@ -556,12 +562,15 @@ __device__ void lane_eval(const uint8_t *__restrict__ buf, const HEntry *tab, un
 		round = 0;
 		kind = -1;
 		unsigned s2 = 0;
+		for (int l = 1; l <= pf_lines; l++)
+			prefetch_l1(tab + ((h2 + 8u * (unsigned)l) & hmask));
 		for (bool done = false; !done;) {
 			if (s2 >= K2_MAXWALK) {
 				L.cx = true;
 				return;
 			}
 			HEntry e[K2_WIDE];
+			prefetch_l1(tab + ((h2 + s2 + 8u * (unsigned)(pf_lines + 1)) & hmask));
 #pragma unroll
 			for (int k = 0; k < K2_WIDE; k++)
 				e[k] = ld_entry(tab + ((h2 + s2 + k) & hmask));
@@ -622,7 +631,7 @@ __device__ void k2_commit_segment_batched(WarpPrim &prim, FastShared *sh, ScanSt
 	bool list_done = false, again = false;
 	int64_t again_p = 0, again_t = 0;
 	int64_t n_disp = 0;
-	int64_t dbg[12] = { 0 };
+	int64_t dbg[16] = { 0 };
 	const long long clk_start = clock64();
 
 	// drop queue entries the scan has moved past or that fail the (possibly tightened) gate
@@ -690,6 +699,7 @@ __device__ void k2_commit_segment_batched(WarpPrim &prim, FastShared *sh, ScanSt
 				r.p = again_p;
 			continue;
 		}
+		const long long cr0 = clock64();
 		while (qn < 32 && !list_done) { // refill from the K1 list
 			int64_t wp = 0, wt = 0;
 			bool wv = false;
@@ -707,6 +717,7 @@ __device__ void k2_commit_segment_batched(WarpPrim &prim, FastShared *sh, ScanSt
 			qn += __popc(bm);
 			__syncwarp();
 		}
+		dbg[11] += clock64() - cr0;
 		if (qn == 0)
 			break;
 		if (r.cur_len > 0) { // a match is pending: strictly serial until it is emitted
@@ -725,6 +736,14 @@ __device__ void k2_commit_segment_batched(WarpPrim &prim, FastShared *sh, ScanSt
 		// ---- evaluate up to 32 candidates, one per lane, on the table as it stands
 		const int nb = qn < 32 ? qn : 32;
 		const int64_t better = (r.min_mask << 1) | 1;
+		int pf_lines;
+		{
+			const int bits = __popcll(r.tag_mask);
+			const int64_t span = bits >= 9 ? 384 : (((int64_t)2 << bits) / 3 + 8); // slots
+			pf_lines = (int)((span + 7) >> 3);
+			if (pf_lines > 24)
+				pf_lines = 24;
+		}
 		LaneEval L;
 		L.nw = L.nr = L.net = L.ins = L.miss = 0;
 		L.cx = false;
@@ -734,12 +753,13 @@ __device__ void k2_commit_segment_batched(WarpPrim &prim, FastShared *sh, ScanSt
 		if (lane < nb) {
 			myp = sh->qpos[lane];
 			myt = sh->qtag[lane];
-			lane_eval(prim.buf, prim.tab, hmask, myp, myt, r.tag_mask, better, c.max_chain, c.end, r.last_match, L);
+			lane_eval(prim.buf, prim.tab, hmask, myp, myt, r.tag_mask, better, c.max_chain, c.end, r.last_match, pf_lines, L);
 		}
 		__syncwarp();
 		dbg[8] += clock64() - ce0;
 		if (L.cx)
 			L.net = 0;
+		const long long cs0 = clock64();
 		// sweep deletions (clean_one_from_hash): the k-th insert that overfills the table removes the
 		// k-th entry, in table order from tag_clean_ptr, that lacks the next-stricter mask
 		const unsigned netm = __ballot_sync(FULL, L.net != 0);
@@ -792,6 +812,8 @@ __device__ void k2_commit_segment_batched(WarpPrim &prim, FastShared *sh, ScanSt
 				L.wslot[nwt++] = del;
 		};
 		classify();
+		dbg[12] += clock64() - cs0;
+		const long long cv0 = clock64();
 		// ---- ordered validation: cmask bit j = this lane read a slot that lane j (< lane) writes
 		unsigned cmask = 0;
 		auto check_against = [&](int j) {
@@ -811,6 +833,8 @@ __device__ void k2_commit_segment_batched(WarpPrim &prim, FastShared *sh, ScanSt
 		};
 		for (int j = 0; j + 1 < nb; j++)
 			check_against(j);
+		dbg[13] += clock64() - cv0;
+		const long long cc0 = clock64();
 
 		// ---- commit in order; a lane that only conflicts is re-evaluated alone on the updated table
 		int base = 0;
@@ -873,7 +897,7 @@ __device__ void k2_commit_segment_batched(WarpPrim &prim, FastShared *sh, ScanSt
 			dbg[5]++;
 			const long long ce1 = clock64();
 			if (lane == k) {
-				lane_eval(prim.buf, prim.tab, hmask, myp, myt, r.tag_mask, better, c.max_chain, c.end, r.last_match, L);
+				lane_eval(prim.buf, prim.tab, hmask, myp, myt, r.tag_mask, better, c.max_chain, c.end, r.last_match, pf_lines, L);
 				if (L.cx)
 					L.net = 0;
 				cmask = 0;
@@ -907,6 +931,7 @@ __device__ void k2_commit_segment_batched(WarpPrim &prim, FastShared *sh, ScanSt
 			prim.publish(r.p, r.min_mask);
 			pop_front(base);
 		}
+		dbg[14] += clock64() - cc0;
 		if (serial_next) { // serial step for the candidate that needs it
 			const int64_t p = sh->qpos[0], t = sh->qtag[0];
 			pop_front(1);
@@ -922,7 +947,7 @@ __device__ void k2_commit_segment_batched(WarpPrim &prim, FastShared *sh, ScanSt
 		k2_close_chunk(prim, st, r, c, recs, status);
 	if (lane == 0) {
 		dbg[10] = clock64() - clk_start;
-		for (int i = 0; i < 12; i++)
+		for (int i = 0; i < 16; i++)
 			st->dbg[i] += dbg[i];
 		st->st_displacements += n_disp;
 		k2_store_regs(st, r, n, status);

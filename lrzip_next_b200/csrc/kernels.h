@@ -7,9 +7,9 @@ namespace lrz {
 
 // ---- K1 tag scan (k1_tagscan.cu) ------------------------------------------------------------
 int k1_init_tables();
-// Scan positions [pos_lo, pos_hi) (pos_lo tile-aligned) of the n-byte chunk at d_buf (followed by at
+// Scan positions [pos_lo, pos_hi) (pos_lo tile-aligned, kTile = 512) of the n-byte chunk at d_buf (followed by at
 // least kInputPad readable bytes) and write the candidates with (tag & mask) == mask, tile-strided:
-// candidates of tile T (positions [T*4096, (T+1)*4096)) start at d_cand[(T - pos_lo/4096) * 4096].
+// candidates of tile T (positions [T*512, (T+1)*512)) start at d_cand[(T - pos_lo/512) * 512].
 // When d_state is non-null the mask is read on the device from d_state->min_mask (so the launch
 // needs no host round trip) and the launch is skipped if the scan already moved past pos_hi.
 int k1_launch(const uint8_t *d_buf, int64_t n, int64_t pos_lo, int64_t pos_hi, int64_t mask,

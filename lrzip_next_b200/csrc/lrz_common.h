@@ -15,7 +15,7 @@ namespace lrz {
 
 constexpr int kMinMatch = 31;        // MINIMUM_MATCH (reference src/include/lrzip_private.h)
 constexpr int kGreatMatch = 1024;    // GREAT_MATCH
-constexpr int kTile = 4096;          // positions per tag-scan tile; candidate regions are tile-strided
+constexpr int kTile = 512;           // positions per candidate tile (one warp of a K1 step); candidate regions are tile-strided
 constexpr int kInputPad = 8192;      // zero padding after the chunk in HBM (tile / vector over-reads)
 
 // One candidate position that passed the tag mask: same 16-byte layout as the reference's
@@ -103,8 +103,9 @@ struct ScanState {
 	int64_t st_evictions, st_sweeps, st_displacements;
 	// commit-kernel bookkeeping: 0 batch rounds, 1 lanes committed in batches, 2 serial steps (pending match),
 	// 3 serial (needs serial logic), 4 serial (sweep wrap / window), 5 single-lane re-evaluations, 6 gate cuts,
-	// 7 rank-shift restarts, 8 clock cycles in lane evaluation, 9 cycles in serial steps, 10 total cycles
-	int64_t dbg[12];
+	// 7 rank-shift restarts, 8 clock cycles in lane evaluation, 9 cycles in serial steps, 10 total cycles,
+	// 11 cycles in queue refill, 12 sweep scan + classify, 13 validation, 14 commit loop (incl. re-evaluations)
+	int64_t dbg[16];
 };
 
 enum { kStatusRunning = 0, kStatusChunkDone = 2, kStatusRecOverflow = -1 };

@@ -155,7 +155,7 @@ int rzip_chunk_device(lrzgpu_ctx *c, const uint8_t *d_chunk, int64_t n, int rzip
 			    (long long)res.st.scan_pos);
 	if (getenv("LRZGPU_DEBUG")) {
 		fprintf(stderr, "[lrzgpu] commit: n=%lld lookups=%lld", (long long)n, (long long)res.st.st_lookups);
-		for (int i = 0; i < 12; i++)
+		for (int i = 0; i < 16; i++)
 			fprintf(stderr, " d%d=%lld", i, (long long)res.st.dbg[i]);
 		fprintf(stderr, "\n");
 	}

@@ -36,6 +36,45 @@
 namespace lrz {
 namespace lzma {
 
+// ---------------------------------------------------------------------------------------------------
+// Warp-cooperative execution model of the encoder (device): ALL 32 lanes of the block's warp run the
+// encoder's scalar code in lockstep on identical values ("replicated": every lane computes and stores the
+// same thing, so no broadcast is needed and a lane always sees its own stores), and the loops whose
+// iterations are independent -- price-table rows, literal-price bits, the cells one position updates in the
+// optimal-parse table, byte compares, the candidates of one position -- are split across lanes:
+//     LZ_PFOR(i, n) { body(i) }   lane l runs i = l, l + 32, ...;  results go to memory (shared);
+//     lz_sync()                   makes them visible to the whole warp and re-converges it.
+// On the host the warp has one lane (LZ_W == 1), so the very same source degenerates to the serial
+// algorithm -- which is what tests/hostsim checks against the reference's LzmaCompress.
+#if defined(__CUDA_ARCH__)
+#define LZ_W 32u
+LZ_INL uint32_t lz_lane() { return threadIdx.x & 31u; }
+LZ_INL void lz_sync() { __syncwarp(); }
+LZ_INL uint32_t lz_ballot(bool p) { return __ballot_sync(0xffffffffu, p); }
+LZ_INL uint32_t lz_ffs(uint32_t m) { return (uint32_t)__ffs((int)m); }
+LZ_INL void lz_prefetch(const void *p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+#else
+#define LZ_W 1u
+LZ_INL uint32_t lz_lane() { return 0; }
+LZ_INL void lz_sync() {}
+LZ_INL uint32_t lz_ballot(bool p) { return p ? 1u : 0u; }
+LZ_INL uint32_t lz_ffs(uint32_t m) { return m ? (uint32_t)__builtin_ffs((int)m) : 0; }
+LZ_INL void lz_prefetch(const void *) {}
+#endif
+#define LZ_PFOR(i, n) for (uint32_t i = lz_lane(); i < (uint32_t)(n); i += LZ_W)
+
+// First index in [from, limit] at which a and b differ (limit if they agree up to there); from <= limit.
+LZ_FN inline uint32_t lz_extend(const uint8_t *a, const uint8_t *b, uint32_t from, uint32_t limit)
+{
+	for (;;) {
+		const uint32_t i = from + lz_lane();
+		const uint32_t m = lz_ballot(i >= limit || a[i] != b[i]);
+		if (m)
+			return from + lz_ffs(m) - 1;
+		from += LZ_W;
+	}
+}
+
 constexpr uint32_t kNumReps = 4;
 constexpr uint32_t kNumOpts = 1u << 11;
 constexpr uint32_t kNumStates = 12;
@@ -119,6 +158,11 @@ struct Enc {
 	LenPrices lenPrices, repLenPrices;
 	Prob lit[0x300 << 4]; // lc + lp <= 4 supported (lrzip-next uses lc3 lp0)
 	Opt opt[kNumOpts];
+	// scratch the lanes of the warp exchange results through (see LZ_PFOR)
+	uint32_t tmpDist[kNumFullDist];
+	uint32_t xLit[8];
+	uint32_t xRepLen[kNumReps], xRepLen2[kNumReps];
+	uint32_t xPairLen2[kMatchMax + 2], xPairPrice[kMatchMax + 2];
 };
 
 // ---------------------------------------------------------------------------------------------------
@@ -294,7 +338,8 @@ LZ_FN inline void init_prob_prices(uint32_t *pp) // LzmaEnc_InitPriceTables (Lzm
 	}
 }
 
-LZ_FN inline uint32_t lit_price(const Enc *e, const Prob *probs, uint32_t sym)
+// Serial forms (used inside LZ_PFOR bodies, where a lane prices a literal on its own).
+LZ_FN inline uint32_t lit_price_1(const Enc *e, const Prob *probs, uint32_t sym)
 {
 	uint32_t price = 0;
 	sym |= 0x100;
@@ -306,7 +351,7 @@ LZ_FN inline uint32_t lit_price(const Enc *e, const Prob *probs, uint32_t sym)
 	return price;
 }
 
-LZ_FN inline uint32_t lit_price_matched(const Enc *e, const Prob *probs, uint32_t sym, uint32_t matchByte)
+LZ_FN inline uint32_t lit_price_matched_1(const Enc *e, const Prob *probs, uint32_t sym, uint32_t matchByte)
 {
 	uint32_t price = 0, offs = 0x100;
 	sym |= 0x100;
@@ -316,6 +361,39 @@ LZ_FN inline uint32_t lit_price_matched(const Enc *e, const Prob *probs, uint32_
 		sym <<= 1;
 		offs &= ~(matchByte ^ sym);
 	} while (sym < 0x10000);
+	return price;
+}
+
+// Warp forms: the 8 binary decisions of a literal are priced by 8 lanes at once.  Decision k (most
+// significant bit first) uses the node reached by the k bits above it, which is known from the symbol.
+LZ_FN inline uint32_t lit_price(Enc *e, const Prob *probs, uint32_t sym)
+{
+	lz_sync();
+	LZ_PFOR(k, 8) {
+		const uint32_t node = (0x100u | sym) >> (8 - k);
+		e->xLit[k] = price_bit(e, probs[node], (sym >> (7 - k)) & 1);
+	}
+	lz_sync();
+	uint32_t price = 0;
+	for (uint32_t k = 0; k < 8; k++)
+		price += e->xLit[k];
+	return price;
+}
+
+LZ_FN inline uint32_t lit_price_matched(Enc *e, const Prob *probs, uint32_t sym, uint32_t matchByte)
+{
+	lz_sync();
+	LZ_PFOR(k, 8) {
+		// offs stays 0x100 while the bits above agree with the match byte's (LitEnc_MatchedEncode, LzmaEnc.c:800-826)
+		const uint32_t offs = (((matchByte ^ sym) >> (8 - k)) == 0) ? 0x100u : 0u;
+		const uint32_t node = (0x100u | sym) >> (8 - k);
+		const uint32_t mb = ((matchByte >> (7 - k)) & 1) << 8;
+		e->xLit[k] = price_bit(e, probs[offs + (mb & offs) + node], (sym >> (7 - k)) & 1);
+	}
+	lz_sync();
+	uint32_t price = 0;
+	for (uint32_t k = 0; k < 8; k++)
+		price += e->xLit[k];
 	return price;
 }
 
@@ -340,27 +418,30 @@ LZ_FN inline void set_prices_3(const Enc *e, const Prob *probs, uint32_t start, 
 LZ_FN inline void len_update_prices(const Enc *e, LenPrices *lp, uint32_t numPosStates, const LenProbs *enc)
 {
 	uint32_t b;
+	lz_sync();
 	{
 		const uint32_t prob = enc->low[0];
 		b = price1(e, prob);
 		const uint32_t a = price0(e, prob);
 		const uint32_t c = b + price0(e, enc->low[kLenLow]);
-		for (uint32_t ps = 0; ps < numPosStates; ps++) {
+		LZ_PFOR(q, numPosStates * 2) { // one lane per (posState, low | mid) group of 8 prices
+			const uint32_t ps = q >> 1;
 			uint32_t *prices = lp->prices[ps];
 			const Prob *probs = enc->low + (ps << 4);
-			set_prices_3(e, probs, a, prices);
-			set_prices_3(e, probs + kLenLow, c, prices + kLenLow);
+			if (q & 1)
+				set_prices_3(e, probs + kLenLow, c, prices + kLenLow);
+			else
+				set_prices_3(e, probs, a, prices);
 		}
 	}
-	uint32_t i = lp->tableSize;
-	if (i > kLenLow * 2) {
+	const uint32_t ts = lp->tableSize;
+	if (ts > kLenLow * 2) {
 		const Prob *probs = enc->high;
 		uint32_t *prices = lp->prices[0] + kLenLow * 2;
-		i -= kLenLow * 2 - 1;
-		i >>= 1;
+		const uint32_t cnt = (ts - (kLenLow * 2 - 1)) >> 1;
 		b += price1(e, enc->low[kLenLow]);
-		do {
-			uint32_t sym = --i + (1u << 7);
+		LZ_PFOR(i, cnt) {
+			uint32_t sym = i + (1u << 7);
 			uint32_t price = b;
 			do {
 				const uint32_t bit = sym & 1;
@@ -370,18 +451,22 @@ LZ_FN inline void len_update_prices(const Enc *e, LenPrices *lp, uint32_t numPos
 			const uint32_t prob = probs[i + (1u << 7)];
 			prices[i * 2] = price + price0(e, prob);
 			prices[i * 2 + 1] = price + price1(e, prob);
-		} while (i);
-		const uint32_t num = lp->tableSize - kLenLow * 2;
-		for (uint32_t ps = 1; ps < numPosStates; ps++)
-			for (uint32_t k = 0; k < num; k++)
-				lp->prices[ps][kLenLow * 2 + k] = lp->prices[0][kLenLow * 2 + k];
+		}
+		lz_sync();
+		const uint32_t num = ts - kLenLow * 2;
+		LZ_PFOR(q, (numPosStates - 1) * num) {
+			const uint32_t ps = 1 + q / num, k = q % num;
+			lp->prices[ps][kLenLow * 2 + k] = lp->prices[0][kLenLow * 2 + k];
+		}
 	}
+	lz_sync();
 }
 
 LZ_FN inline void fill_align_prices(Enc *e) // LzmaEnc.c:2202-2222
 {
 	const Prob *probs = e->posAlign;
-	for (uint32_t i = 0; i < kAlignSize / 2; i++) {
+	lz_sync();
+	LZ_PFOR(i, kAlignSize / 2) {
 		uint32_t price = 0, sym = i, m = 1, bit;
 		for (int k = 0; k < 3; k++) {
 			bit = sym & 1;
@@ -393,13 +478,16 @@ LZ_FN inline void fill_align_prices(Enc *e) // LzmaEnc.c:2202-2222
 		e->alignPrices[i] = price + price0(e, prob);
 		e->alignPrices[i + 8] = price + price1(e, prob);
 	}
+	lz_sync();
 }
 
 LZ_FN inline void fill_distance_prices(Enc *e) // LzmaEnc.c:2225-2319
 {
-	uint32_t temp[kNumFullDist];
+	uint32_t *temp = e->tmpDist;
 	e->matchPriceCount = 0;
-	for (uint32_t i = kStartPosModel / 2; i < kNumFullDist / 2; i++) {
+	lz_sync();
+	LZ_PFOR(q, kNumFullDist / 2 - kStartPosModel / 2) {
+		const uint32_t i = q + kStartPosModel / 2;
 		const uint32_t slot = pos_slot(i);
 		uint32_t footer = (slot >> 1) - 1;
 		uint32_t base = (2 | (slot & 1)) << footer;
@@ -418,38 +506,31 @@ LZ_FN inline void fill_distance_prices(Enc *e) // LzmaEnc.c:2225-2319
 		temp[base] = price + price0(e, prob);
 		temp[base + offset] = price + price1(e, prob);
 	}
-	for (uint32_t lps = 0; lps < kNumLenToPos; lps++) {
-		const uint32_t half = (e->distTableSize + 1) >> 1;
+	const uint32_t half = (e->distTableSize + 1) >> 1;
+	LZ_PFOR(q, kNumLenToPos * half) { // slot prices; slots >= kEndPosModel also carry their direct bits
+		const uint32_t lps = q / half, slot = q % half;
 		uint32_t *sp = e->posSlotPrices[lps];
 		const Prob *probs = e->posSlot[lps];
-		for (uint32_t slot = 0; slot < half; slot++) {
-			uint32_t sym = slot + (1u << 5), price = 0;
-			for (int k = 0; k < 5; k++) {
-				const uint32_t bit = sym & 1;
-				sym >>= 1;
-				price += price_bit(e, probs[sym], bit);
-			}
-			const uint32_t prob = probs[slot + (1u << 5)];
-			sp[slot * 2] = price + price0(e, prob);
-			sp[slot * 2 + 1] = price + price1(e, prob);
+		uint32_t sym = slot + (1u << 5), price = 0;
+		for (int k = 0; k < 5; k++) {
+			const uint32_t bit = sym & 1;
+			sym >>= 1;
+			price += price_bit(e, probs[sym], bit);
 		}
-		uint32_t delta = ((kEndPosModel / 2 - 1) - kNumAlignBits) << kPriceShift;
-		for (uint32_t slot = kEndPosModel / 2; slot < half; slot++) {
-			sp[slot * 2] += delta;
-			sp[slot * 2 + 1] += delta;
-			delta += 1u << kPriceShift;
-		}
-		uint32_t *dp = e->distPrices[lps];
-		dp[0] = sp[0];
-		dp[1] = sp[1];
-		dp[2] = sp[2];
-		dp[3] = sp[3];
-		for (uint32_t i = 4; i < kNumFullDist; i += 2) {
-			const uint32_t slotPrice = sp[pos_slot(i)];
-			dp[i] = slotPrice + temp[i];
-			dp[i + 1] = slotPrice + temp[i + 1];
-		}
+		const uint32_t prob = probs[slot + (1u << 5)];
+		uint32_t delta = 0;
+		if (slot >= kEndPosModel / 2)
+			delta = (((kEndPosModel / 2 - 1) - kNumAlignBits) + (slot - kEndPosModel / 2)) << kPriceShift;
+		sp[slot * 2] = price + price0(e, prob) + delta;
+		sp[slot * 2 + 1] = price + price1(e, prob) + delta;
 	}
+	lz_sync();
+	LZ_PFOR(q, kNumLenToPos * kNumFullDist) {
+		const uint32_t lps = q / kNumFullDist, i = q % kNumFullDist;
+		const uint32_t *sp = e->posSlotPrices[lps];
+		e->distPrices[lps][i] = i < 4 ? sp[i] : sp[pos_slot(i)] + temp[i];
+	}
+	lz_sync();
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -536,11 +617,18 @@ LZ_INL void mf_hash23(const Enc *e, const uint8_t *cur, uint32_t &h2, uint32_t &
 LZ_FN inline uint32_t mf_get_matches(Enc *e, uint32_t *d)
 {
 	if (e->preRec) { // the data-parallel pre-pass already produced this position's list
-		const uint64_t rec = e->preRec[e->pos - 1];
+		const uint32_t i0 = e->pos - 1;
+		const uint64_t rec = e->preRec[i0];
 		const uint32_t nd = (uint32_t)rec & 1023u;
 		const uint32_t *s = e->prePool + (rec >> 10);
-		for (uint32_t i = 0; i < nd; i++)
+		if (i0 + 6 < e->n) { // lists sit in the pool in bucket order: pull the ones needed next towards L1
+			lz_prefetch(e->prePool + (e->preRec[i0 + 3] >> 10));
+			lz_prefetch(e->preRec + i0 + 6);
+		}
+		lz_sync();
+		LZ_PFOR(i, nd)
 			d[i] = s[i];
+		lz_sync();
 		e->pos++;
 		return nd;
 	}
@@ -626,10 +714,7 @@ LZ_FN inline uint32_t read_matches(Enc *e, uint32_t *numPairsRes)
 		numAvail = kMatchMax;
 	const uint8_t *p1 = mf_cur(e) - 1;
 	const ptrdiff_t dif = (ptrdiff_t)-1 - (ptrdiff_t)e->matches[numPairs - 1];
-	uint32_t l = len;
-	while (l != numAvail && p1[l] == p1[(ptrdiff_t)l + dif])
-		l++;
-	return l;
+	return lz_extend(p1 + dif, p1, len, numAvail);
 }
 
 LZ_INL void move_pos(Enc *e, uint32_t num)
@@ -717,7 +802,62 @@ LZ_INL void opt_set(Opt *o, uint32_t price, uint32_t len, uint32_t dist, uint32_
 	o->extra = (uint16_t)extra;
 }
 
-// GetOptimum (LzmaEnc.c:1219-1968)
+// price of a normal match (len, dist) given the price of reaching it (LzmaEnc.c:1402-1416, 1856-1872)
+LZ_INL uint32_t match_price(const Enc *e, uint32_t normalMatchPrice, uint32_t posState, uint32_t len, uint32_t dist)
+{
+	uint32_t price = normalMatchPrice + len_price(&e->lenPrices, posState, len);
+	uint32_t lenNorm = len - 2;
+	lenNorm = lenNorm < kNumLenToPos - 1 ? lenNorm : kNumLenToPos - 1;
+	if (dist < kNumFullDist)
+		price += e->distPrices[lenNorm][dist & (kNumFullDist - 1)];
+	else
+		price += e->posSlotPrices[lenNorm][pos_slot(dist)] + e->alignPrices[dist & kAlignMask];
+	return price;
+}
+
+// The cells [base + lo, base + hi] of the parse table get the rep-match price for their length.
+LZ_FN inline void opt_rep_cells(Enc *e, uint32_t base, uint32_t lo, uint32_t hi, uint32_t price, uint32_t posState,
+				uint32_t repIndex)
+{
+	lz_sync();
+	LZ_PFOR(q, hi + 1 - lo) {
+		const uint32_t len2 = lo + q;
+		const uint32_t price2 = price + len_price(&e->repLenPrices, posState, len2);
+		Opt *o = &e->opt[base + len2];
+		if (price2 < o->price)
+			opt_set(o, price2, len2, repIndex, 0);
+	}
+	lz_sync();
+}
+
+// The cells [base + startLen, base + newLen] get the price of the shortest-distance match that reaches them.
+LZ_FN inline void opt_match_cells(Enc *e, uint32_t base, uint32_t startLen, uint32_t newLen, uint32_t normalMatchPrice,
+				  uint32_t posState)
+{
+	const uint32_t *matches = e->matches;
+	lz_sync();
+	uint32_t offs = 0;
+	LZ_PFOR(q, newLen + 1 - startLen) {
+		const uint32_t len = startLen + q;
+		while (len > matches[offs])
+			offs += 2;
+		const uint32_t dist = matches[offs + 1];
+		const uint32_t price = match_price(e, normalMatchPrice, posState, len, dist);
+		Opt *o = &e->opt[base + len];
+		if (price < o->price)
+			opt_set(o, price, len, dist + kNumReps, 0);
+	}
+	lz_sync();
+}
+
+// GetOptimum (LzmaEnc.c:1219-1968).
+//
+// Order of updates: the reference interleaves, per position, "cell" updates (a rep or match of every
+// length) with "x : LIT : REP_0" trials that write one cell further on.  Updates only replace a cell when
+// strictly cheaper, so what must be kept is, per cell, the order of the updates that reach it.  A trial of
+// rep i / pair k lands beyond that rep's / pair's own length, hence for any one cell the trials that reach
+// it come before the normal match update of that cell and in pair order; reps are kept strictly in index
+// order (cells, then trial).  Everything else (the cells of one loop are distinct) runs across lanes.
 LZ_FN inline uint32_t get_optimum(Enc *e, uint32_t position)
 {
 	uint32_t last, cur;
@@ -741,25 +881,29 @@ LZ_FN inline uint32_t get_optimum(Enc *e, uint32_t position)
 		if (numAvail > kMatchMax)
 			numAvail = kMatchMax;
 		const uint8_t *data = mf_cur(e) - 1;
+		for (i = 0; i < kNumReps; i++)
+			reps[i] = e->reps[i];
+		lz_sync();
+		LZ_PFOR(q, kNumReps) { // the four first-two-bytes checks at once (four cache misses overlap)
+			const uint8_t *data2 = data - e->reps[q];
+			e->xRepLen[q] = (data[0] == data2[0] && data[1] == data2[1]) ? 2 : 0;
+		}
+		lz_sync();
 		repMaxIndex = 0;
 		for (i = 0; i < kNumReps; i++) {
-			reps[i] = e->reps[i];
-			const uint8_t *data2 = data - reps[i];
-			if (data[0] != data2[0] || data[1] != data2[1]) {
-				repLens[i] = 0;
+			repLens[i] = 0;
+			if (e->xRepLen[i] == 0)
 				continue;
-			}
-			uint32_t len = 2;
-			while (len < numAvail && data[len] == data2[len])
-				len++;
+			const uint32_t len = lz_extend(data - reps[i], data, 2, numAvail);
 			repLens[i] = len;
 			if (len > repLens[repMaxIndex])
 				repMaxIndex = i;
-			if (len == kMatchMax)
+			if (len == kMatchMax) {
+				for (uint32_t j = i + 1; j < kNumReps; j++)
+					repLens[j] = 0; // not read: this rep is >= fb and is returned right away
 				break;
+			}
 		}
-		// NB: when the loop above stops early at kMatchMax the remaining repLens are not read below,
-		// because that rep is >= fb and is returned right away.
 		if (repLens[repMaxIndex] >= fb) {
 			e->backRes = repMaxIndex;
 			const uint32_t len = repLens[repMaxIndex];
@@ -783,8 +927,8 @@ LZ_FN inline uint32_t get_optimum(Enc *e, uint32_t position)
 		posState = position & e->pbMask;
 		{
 			const Prob *probs = lit_probs(e, position, *(data - 1));
-			e->opt[1].price = price0(e, e->isMatch[e->state][posState]) +
-					  (!is_lit_state(e->state) ? lit_price_matched(e, probs, curByte, matchByte) : lit_price(e, probs, curByte));
+			const uint32_t lp = !is_lit_state(e->state) ? lit_price_matched(e, probs, curByte, matchByte) : lit_price(e, probs, curByte);
+			e->opt[1].price = price0(e, e->isMatch[e->state][posState]) + lp;
 		}
 		e->opt[1].dist = kMarkLit;
 		e->opt[1].extra = 0;
@@ -807,44 +951,19 @@ LZ_FN inline uint32_t get_optimum(Enc *e, uint32_t position)
 			e->opt[0].reps[i] = reps[i];
 
 		for (i = 0; i < kNumReps; i++) { // REP
-			uint32_t repLen = repLens[i];
+			const uint32_t repLen = repLens[i];
 			if (repLen < 2)
 				continue;
 			const uint32_t price = repMatchPrice + price_pure_rep(e, i, e->state, posState);
-			do {
-				const uint32_t price2 = price + len_price(&e->repLenPrices, posState, repLen);
-				Opt *o = &e->opt[repLen];
-				if (price2 < o->price)
-					opt_set(o, price2, repLen, i, 0);
-			} while (--repLen >= 2);
+			opt_rep_cells(e, 0, 2, repLen, price, posState, i);
 		}
 		{ // MATCH
 			uint32_t len = repLens[0] + 1;
 			if (len <= mainLen) {
-				uint32_t offs = 0;
 				const uint32_t normalMatchPrice = matchPrice + price0(e, e->isRep[e->state]);
 				if (len < 2)
 					len = 2;
-				else
-					while (len > matches[offs])
-						offs += 2;
-				for (;; len++) {
-					const uint32_t dist = matches[offs + 1];
-					uint32_t price = normalMatchPrice + len_price(&e->lenPrices, posState, len);
-					const uint32_t l2p = len < kNumLenToPos + 1 ? len - 2 : kNumLenToPos - 1;
-					if (dist < kNumFullDist)
-						price += e->distPrices[l2p][dist & (kNumFullDist - 1)];
-					else
-						price += e->alignPrices[dist & kAlignMask] + e->posSlotPrices[l2p][pos_slot(dist)];
-					Opt *o = &e->opt[len];
-					if (price < o->price)
-						opt_set(o, price, len, dist + kNumReps, 0);
-					if (len == matches[offs]) {
-						offs += 2;
-						if (offs == numPairs)
-							break;
-					}
-				}
+				opt_match_cells(e, 0, len, mainLen, normalMatchPrice, posState);
 			}
 		}
 		cur = 0;
@@ -927,6 +1046,46 @@ LZ_FN inline uint32_t get_optimum(Enc *e, uint32_t position)
 			curOpt->reps[i] = reps[i];
 
 		const uint8_t *data = mf_cur(e) - 1;
+		numAvailFull = e->numAvail;
+		{
+			const uint32_t temp = kNumOpts - 1 - cur;
+			if (numAvailFull > temp)
+				numAvailFull = temp;
+		}
+		numAvail = numAvailFull <= fb ? numAvailFull : fb;
+		// MATCH list clipped to what is available (LzmaEnc.c:1830-1838; independent of the REP section)
+		if (numAvailFull >= 2 && newLen > numAvail) {
+			newLen = numAvail;
+			for (numPairs = 0; newLen > matches[numPairs]; numPairs += 2) {
+			}
+			matches[numPairs] = newLen;
+			numPairs += 2;
+		}
+		// ---- one pass over everything that needs bytes from far back in the block, so that the cache
+		// misses overlap: first two bytes of each rep, and for each pair the bytes after a one-literal gap
+		lz_sync();
+		LZ_PFOR(q, kNumReps + (numAvailFull >= 2 ? (numPairs >> 1) : 0)) {
+			if (q < kNumReps) {
+				const uint8_t *data2 = data - curOpt->reps[q];
+				e->xRepLen[q] = (numAvailFull >= 2 && data[0] == data2[0] && data[1] == data2[1]) ? 2 : 0;
+			} else {
+				// MATCH : LIT : REP_0 reach of pair k (LzmaEnc.c:1876-1893)
+				const uint32_t k = q - kNumReps, len = matches[2 * k];
+				const uint8_t *data2 = data - matches[2 * k + 1] - 1;
+				uint32_t len2 = len + 1, limit = len2 + fb, res = 0;
+				if (limit > numAvailFull)
+					limit = numAvailFull;
+				len2 += 2;
+				if (len2 <= limit && data[len2 - 2] == data2[len2 - 2] && data[len2 - 1] == data2[len2 - 1]) {
+					while (len2 < limit && data[len2] == data2[len2])
+						len2++;
+					res = len2 - len;
+				}
+				e->xPairLen2[k] = res;
+			}
+		}
+		lz_sync();
+
 		const uint8_t curByte = *data, matchByte = *(data - reps[0]);
 		posState = position & e->pbMask;
 		{
@@ -948,12 +1107,6 @@ LZ_FN inline uint32_t get_optimum(Enc *e, uint32_t position)
 			}
 		}
 		repMatchPrice = matchPrice + price1(e, e->isRep[state]);
-		numAvailFull = e->numAvail;
-		{
-			const uint32_t temp = kNumOpts - 1 - cur;
-			if (numAvailFull > temp)
-				numAvailFull = temp;
-		}
 		// SHORT_REP
 		if (is_lit_state(state) && matchByte == curByte && repMatchPrice < nextOpt->price &&
 		    (nextOpt->len < 2 || nextOpt->dist != 0)) {
@@ -965,7 +1118,6 @@ LZ_FN inline uint32_t get_optimum(Enc *e, uint32_t position)
 		}
 		if (numAvailFull < 2)
 			continue;
-		numAvail = numAvailFull <= fb ? numAvailFull : fb;
 
 		// LIT : REP_0
 		if (!nextIsLit && litPrice != 0 && matchByte != curByte && numAvailFull > 2) {
@@ -974,8 +1126,7 @@ LZ_FN inline uint32_t get_optimum(Enc *e, uint32_t position)
 				uint32_t len, limit = fb + 1;
 				if (limit > numAvailFull)
 					limit = numAvailFull;
-				for (len = 3; len < limit && data[len] == data2[len]; len++) {
-				}
+				len = lz_extend(data2, data, 3, limit);
 				const uint32_t state2 = st_lit(state), posState2 = (position + 1) & e->pbMask;
 				const uint32_t price = litPrice + price_rep0(e, state2, posState2);
 				const uint32_t offset = cur + len;
@@ -991,24 +1142,14 @@ LZ_FN inline uint32_t get_optimum(Enc *e, uint32_t position)
 		startLen = 2;
 		// REP
 		for (uint32_t repIndex = 0; repIndex < kNumReps; repIndex++) {
-			const uint8_t *data2 = data - reps[repIndex];
-			if (data[0] != data2[0] || data[1] != data2[1])
+			if (e->xRepLen[repIndex] == 0)
 				continue;
-			uint32_t len = 2;
-			while (len < numAvail && data[len] == data2[len])
-				len++;
+			const uint8_t *data2 = data - reps[repIndex];
+			const uint32_t len = lz_extend(data2, data, 2, numAvail);
 			if (last < cur + len)
 				last = cur + len;
 			uint32_t price = repMatchPrice + price_pure_rep(e, repIndex, state, posState);
-			{
-				uint32_t len2 = len;
-				do {
-					const uint32_t price2 = price + len_price(&e->repLenPrices, posState, len2);
-					Opt *o = &e->opt[cur + len2];
-					if (price2 < o->price)
-						opt_set(o, price2, len2, repIndex, 0);
-				} while (--len2 >= 2);
-			}
+			opt_rep_cells(e, cur, 2, len, price, posState, repIndex);
 			if (repIndex == 0)
 				startLen = len + 1;
 			// REP : LIT : REP_0
@@ -1023,8 +1164,7 @@ LZ_FN inline uint32_t get_optimum(Enc *e, uint32_t position)
 				state2 = 5; // kState_LitAfterRep
 				posState2 = (posState2 + 1) & e->pbMask;
 				price += price_rep0(e, state2, posState2);
-				while (len2 < limit && data[len2] == data2[len2])
-					len2++;
+				len2 = lz_extend(data2, data, len2, limit);
 				len2 -= len;
 				const uint32_t offset = cur + len + len2;
 				if (last < offset)
@@ -1037,73 +1177,48 @@ LZ_FN inline uint32_t get_optimum(Enc *e, uint32_t position)
 			}
 		}
 		// MATCH
-		if (newLen > numAvail) {
-			newLen = numAvail;
-			for (numPairs = 0; newLen > matches[numPairs]; numPairs += 2) {
-			}
-			matches[numPairs] = newLen;
-			numPairs += 2;
-		}
 		if (newLen >= startLen) {
 			const uint32_t normalMatchPrice = matchPrice + price0(e, e->isRep[state]);
 			if (last < cur + newLen)
 				last = cur + newLen;
-			uint32_t offs = 0;
-			while (startLen > matches[offs])
-				offs += 2;
-			uint32_t dist = matches[offs + 1];
-			uint32_t slot = pos_slot(dist);
-			for (uint32_t len = startLen;; len++) {
-				uint32_t price = normalMatchPrice + len_price(&e->lenPrices, posState, len);
-				{
-					uint32_t lenNorm = len - 2;
-					lenNorm = lenNorm < kNumLenToPos - 1 ? lenNorm : kNumLenToPos - 1;
-					if (dist < kNumFullDist)
-						price += e->distPrices[lenNorm][dist & (kNumFullDist - 1)];
-					else
-						price += e->posSlotPrices[lenNorm][slot] + e->alignPrices[dist & kAlignMask];
-					Opt *o = &e->opt[cur + len];
-					if (price < o->price)
-						opt_set(o, price, len, dist + kNumReps, 0);
-				}
-				if (len == matches[offs]) {
-					// MATCH : LIT : REP_0
-					const uint8_t *data2 = data - dist - 1;
-					uint32_t len2 = len + 1, limit = len2 + fb;
-					if (limit > numAvailFull)
-						limit = numAvailFull;
-					len2 += 2;
-					if (len2 <= limit && data[len2 - 2] == data2[len2 - 2] && data[len2 - 1] == data2[len2 - 1]) {
-						while (len2 < limit && data[len2] == data2[len2])
-							len2++;
-						len2 -= len;
-						uint32_t state2 = st_match(state), posState2 = (position + len) & e->pbMask;
-						price += price0(e, e->isMatch[state2][posState2]);
-						price += lit_price_matched(e, lit_probs(e, position + len, data[len - 1]), data[len], data2[len]);
-						state2 = 4; // kState_LitAfterMatch
-						posState2 = (posState2 + 1) & e->pbMask;
-						price += price_rep0(e, state2, posState2);
-						const uint32_t offset = cur + len + len2;
-						if (last < offset)
-							last = offset;
-						len2--;
-						const uint32_t price2 = price + len_price(&e->repLenPrices, posState2, len2);
-						Opt *o = &e->opt[offset];
-						if (price2 < o->price)
-							opt_set(o, price2, len2, dist + kNumReps, len + 1);
-					}
-					offs += 2;
-					if (offs == numPairs)
-						break;
-					dist = matches[offs + 1];
-					slot = pos_slot(dist);
-				}
+			// MATCH : LIT : REP_0 of every pair that is long enough: prices across lanes, then applied in pair order
+			const uint32_t np = numPairs >> 1;
+			lz_sync();
+			LZ_PFOR(k, np) {
+				const uint32_t len = matches[2 * k], l2 = e->xPairLen2[k];
+				if (len < startLen || l2 == 0)
+					continue;
+				const uint32_t dist = matches[2 * k + 1];
+				const uint8_t *data2 = data - dist - 1;
+				uint32_t price = match_price(e, normalMatchPrice, posState, len, dist);
+				uint32_t state2 = st_match(state), posState2 = (position + len) & e->pbMask;
+				price += price0(e, e->isMatch[state2][posState2]);
+				price += lit_price_matched_1(e, lit_probs(e, position + len, data[len - 1]), data[len], data2[len]);
+				state2 = 4; // kState_LitAfterMatch
+				posState2 = (posState2 + 1) & e->pbMask;
+				price += price_rep0(e, state2, posState2);
+				e->xPairPrice[k] = price + len_price(&e->repLenPrices, posState2, l2 - 1);
 			}
+			lz_sync();
+			for (uint32_t k = 0; k < np; k++) {
+				const uint32_t len = matches[2 * k], l2 = e->xPairLen2[k];
+				if (len < startLen || l2 == 0)
+					continue;
+				const uint32_t offset = cur + len + l2;
+				if (last < offset)
+					last = offset;
+				Opt *o = &e->opt[offset];
+				const uint32_t price2 = e->xPairPrice[k];
+				if (price2 < o->price)
+					opt_set(o, price2, l2 - 1, matches[2 * k + 1] + kNumReps, len + 1);
+			}
+			opt_match_cells(e, cur, startLen, newLen, normalMatchPrice, posState);
 		}
 	}
-	do
-		e->opt[last].price = kInfinity;
-	while (--last);
+	lz_sync();
+	LZ_PFOR(q, last)
+		e->opt[1 + q].price = kInfinity;
+	lz_sync();
 	return backward(e, cur);
 }
 
@@ -1228,15 +1343,16 @@ LZ_FN inline void enc_init(Enc *e, const Config &c, const uint8_t *src, uint32_t
 			e->posSlot[i][j] = kProbInit;
 	for (uint32_t i = 0; i < kNumFullDist; i++)
 		e->posEnc[i] = kProbInit;
-	for (uint32_t i = 0; i < (0x300u << (c.lc + c.lp)); i++)
+	LZ_PFOR(i, 0x300u << (c.lc + c.lp))
 		e->lit[i] = kProbInit;
 	for (uint32_t i = 0; i < (kNumPosStatesMax << 4); i++)
 		e->lenProbs.low[i] = e->repLenProbs.low[i] = kProbInit;
 	for (uint32_t i = 0; i < kLenHigh; i++)
 		e->lenProbs.high[i] = e->repLenProbs.high[i] = kProbInit;
 	e->optEnd = e->optCur = 0;
-	for (uint32_t i = 0; i < kNumOpts; i++)
+	LZ_PFOR(i, kNumOpts)
 		e->opt[i].price = kInfinity;
+	lz_sync();
 	e->additionalOffset = 0;
 	e->longestMatchLen = e->numPairs = e->numAvail = e->backRes = 0;
 	init_prob_prices(e->probPrices);

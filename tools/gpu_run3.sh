@@ -1,0 +1,5 @@
+set -x
+mkdir -p gpurun_out
+timeout 600 python -m pytest tests/test_gpu_rzip.py -x -q 2>&1 | tail -15 > gpurun_out/pytest_rzip.log; tail -5 gpurun_out/pytest_rzip.log
+LRZGPU_DEBUG=1 timeout 300 python tools/prof_small.py 64 > gpurun_out/k2_debug2.log 2>&1; cat gpurun_out/k2_debug2.log
+timeout 300 python tools/perf_probe.py 256 > gpurun_out/perf_probe2.log 2>&1; head -4 gpurun_out/perf_probe2.log

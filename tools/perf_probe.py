@@ -21,8 +21,8 @@ for mb in sizes:
     d = torch.zeros(n + 8192 + 256, dtype=torch.uint8, device="cuda")
     d[256:256 + n] = torch.from_numpy(h).cuda()
     base = d.data_ptr() + 256
-    cand = torch.empty(((n + 4095) // 4096) * 4096 * 2, dtype=torch.int64, device="cuda")
-    tc = torch.empty((n + 4095) // 4096, dtype=torch.int32, device="cuda")
+    cand = torch.empty(((n + 511) // 512) * 512 * 2, dtype=torch.int64, device="cuda")
+    tc = torch.empty((n + 511) // 512, dtype=torch.int32, device="cuda")
     crc = torch.zeros(4, dtype=torch.int32, device="cuda")
     st = torch.cuda.current_stream().cuda_stream
     for mask in (1, 15, 255):
