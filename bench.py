@@ -38,6 +38,10 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 import numpy as np  # noqa: E402
 
 MB = 1e6
+# Warm-up steps run the whole path on a prefix of the workload (module load, arena growth, clocks); the
+# timed steps always run the full workload.  A full C2 step is minutes of serial commit + LZMA work, so
+# full-size warm-ups would not let the default run finish "within minutes".
+WARM_BYTES = 64 << 20
 WORKLOADS = {
     # name: (generator, per-GPU bytes, backend, level, description)
     "c1": ("rep", 100 << 20, "none", 7, "C1: 100 MiB repeated 1 MiB random block, rzip-only (-n)"),
@@ -150,7 +154,8 @@ def cpu_sample_bytes(backend: str, cores: int) -> int:
     # roughly 0.7 MB/s per core
     if backend == "none":
         return 256 << 20
-    return min(1 << 30, max(32 << 20, (cores * 3) << 20))
+    # at least one 10 MiB stream block per host core, so that every core has a backend block to work on
+    return min(1 << 30, max(64 << 20, (cores * 12) << 20))
 
 
 def main():
@@ -172,13 +177,17 @@ def main():
     if a.size_mb:
         size = a.size_mb << 20
     cores = os.cpu_count() or 1
-    threads = a.threads or cores
+    # -p: stream blocks are limit/threads but never below 10 MiB (src/stream.c:1140-1348), and one block is
+    # the unit of backend parallelism on both arms.  -p 160 gives the 10 MiB minimum for 1 GiB at -m 600
+    # (105 threads after the reference's own memory-driven reduction); it is passed to both arms.
+    threads = a.threads or max(cores, 160)
     ram_units = 600  # -m 600 = 60 GB, pinned for both arms
     window = 0 if world == 1 else size // (100 << 20)
     if world > 1 and size % (100 << 20):
         size = window * (100 << 20)
     config = {"workload": desc, "per_gpu_bytes": size, "backend": backend, "level": level, "threads_p": threads,
               "ram_m": ram_units, "window_w": window, "l2": "inputs larger than L2 (126 MB); no flush needed",
+              "warmup_bytes": min(size, WARM_BYTES),
               "sharding": "one rzip window per GPU, blobs gathered to rank 0" if world > 1 else "single window"}
 
     if a.impl == "reference":
@@ -280,8 +289,10 @@ def main():
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms.item()), launches0
 
+    warm = min(size, WARM_BYTES)
     for _ in range(a.warmup):
-        step_device()
+        out, ol, st = ctx.compress_device_raw(d_in, warm, params)
+        ctx.free(out)
     sampler = ClockSampler(local_rank)
     sampler.start()
     ms, launches = timed(step_device, a.steps)
@@ -290,7 +301,6 @@ def main():
     out_len = last["out_len"]
     stats = last["stats"]
 
-    step_e2e()  # warm the host-buffer path (allocations)
     e2e_ms, _ = timed(step_e2e, a.steps)
     e2e_value = total * a.steps / (e2e_ms / 1e3) / MB
     e2e_out = last["out_len"]
@@ -319,8 +329,18 @@ def main():
         alg = size * (1 + 16 * 2.0 ** -initial_freq)
         peak, how = peaks()
         ach = alg / (k1_ms / 1e3) / 1e9
+        traffic, traffic_src = None, None
+        tpath = os.path.join(ROOT, "profiles", "k1_traffic.json")
+        if os.path.exists(tpath):  # dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` capture
+            with open(tpath) as fh:
+                tj = json.load(fh)
+            if tj.get("initial_freq") == initial_freq:
+                traffic = tj["dram_bytes"] * size / tj["n"]
+                traffic_src = (f"{tj['source']}: {tj['dram_bytes']} B for a launch over {tj['n']} input bytes, "
+                               f"scaled linearly to this launch")
         roofline = {"kernel": "k1_tagscan_kernel", "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s",
-                    "frac": ach / peak, "traffic": None, "peak_source": how, "ms_per_launch": k1_ms,
+                    "frac": ach / peak, "traffic": traffic, "traffic_source": traffic_src, "peak_source": how,
+                    "ms_per_launch": k1_ms,
                     "algorithmic_bytes_per_launch": alg,
                     "note": "K2 commit / LZMA block encoders are serial, latency-bound stages: no roofline fraction"}
         del cand, tcnt

@@ -334,11 +334,31 @@ static constexpr int K2_LOOKAHEAD = 64;  // candidates the helpers may run ahead
 static constexpr int K2_MAXW = 4;        // insert writes one lane may carry (displacement depth 3)
 static constexpr unsigned K2_MAXWALK = 192;
 
+struct LaneEval {
+	unsigned wslot[K2_MAXW + 1]; // insert writes, then (optionally) the sweep deletion
+	long long wtag[K2_MAXW], woff[K2_MAXW];
+	unsigned rlo[K2_MAXW], rlen[K2_MAXW]; // probe ranges read (start slot, length), modulo the table size
+	int nw, nr, net, ins, miss;
+	bool cx;
+};
+
+static constexpr int K2_MAXEQ = 16; // equal-tag entries one candidate may meet in its chain
+
 struct FastShared {
 	long long qpos[64], qtag[64]; // queue of upcoming candidates that pass the current gate
 	unsigned dslot[32];           // sweep deletions of the current batch, in order
+	LaneEval ev[32];              // evaluation results of the batch, written by the 8-lane groups
+	long long eq_off[8][4][K2_MAXEQ]; // per warp and group: offsets of the equal-tag entries met on the walk
+	// batch evaluation command, written by the commit warp before barrier 1 (see k2_eval_worker)
+	long long cmd_tag_mask, cmd_better, cmd_end, cmd_last_match;
+	int cmd_nb, cmd_max_chain, cmd_exit;
 	Progress prog;
 };
+
+// Named barriers of the commit CTA: all 8 warps meet at K2_BAR_GO when the commit warp has queued a batch
+// (or wants the workers to leave), and at K2_BAR_DONE when every warp has evaluated its four candidates.
+static constexpr int K2_BAR_GO = 1, K2_BAR_DONE = 2;
+__device__ __forceinline__ void k2_bar(int id) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(256) : "memory"); }
 
 __device__ __forceinline__ void touch_line(const void *p)
 {
@@ -421,14 +441,6 @@ __device__ void k2_helper(Progress *prog, const uint8_t *__restrict__ buf, const
 // handed to the serial k2_step(), which is also used while a match is pending.  The batch therefore
 // never decides anything the serial code would decide differently.
 
-struct LaneEval {
-	unsigned wslot[K2_MAXW + 1]; // insert writes, then (optionally) the sweep deletion
-	long long wtag[K2_MAXW], woff[K2_MAXW];
-	unsigned rlo[K2_MAXW], rlen[K2_MAXW]; // probe ranges read (start slot, length), modulo the table size
-	int nw, nr, net, ins, miss;
-	bool cx;
-};
-
 // Could the equal-tag entry at `op` give a match of >= 31 bytes at p0?  (single_match_len, bounded.)
 __device__ __forceinline__ bool could_match(const uint8_t *__restrict__ buf, int64_t p0, int64_t op, int64_t end,
 					    int64_t last_match)
@@ -450,7 +462,6 @@ __device__ __forceinline__ bool could_match(const uint8_t *__restrict__ buf, int
 
 __device__ __forceinline__ void prefetch_l1(const void *p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 
-static constexpr int K2_MAXEQ = 16; // equal-tag entries one lane may meet in its chain
 static constexpr int K2_WIDE = 8; // slots fetched per step of a lane's private probe walk (independent loads)
 
 __device__ void lane_eval(const uint8_t *__restrict__ buf, const HEntry *tab, unsigned hmask, int64_t p, int64_t t,
@@ -608,6 +619,269 @@ __device__ void lane_eval(const uint8_t *__restrict__ buf, const HEntry *tab, un
 	}
 }
 
+
+// ---- cooperative evaluation -------------------------------------------------------------------------
+// lane_eval above walks a candidate's probe chain with ONE lane: a long serial instruction stream, and the
+// warp pays the slowest of its 32 lanes.  group_eval gives each candidate 8 lanes instead: one probe step is
+// one 128-byte load of 8 consecutive slots, classified by ballot (empty / due / lesser-bitness / equal tag),
+// so the per-candidate critical path is a handful of warp instructions per step.  Four candidates are
+// evaluated per call (one per 8-lane group); results go to sh->ev[candidate].  The meaning of the result is
+// exactly lane_eval's; `cx` (hand the candidate to the serial step) may only ever be set MORE often.
+
+// could_match() with the group's 8 lanes: 4 bytes per lane forwards, then backwards.
+__device__ __forceinline__ bool group_could_match(const uint8_t *__restrict__ buf, int64_t p0, int64_t op, int64_t end,
+						  int64_t last_match, bool act, unsigned gshift, int gl)
+{
+	act = act && op < p0;
+	int c = 0;
+	bool stopf = false;
+	if (act) {
+#pragma unroll
+		for (int k = 0; k < 4; k++) {
+			const int i = 4 * gl + k;
+			if (stopf)
+				break;
+			if (i >= kMinMatch || p0 + i >= end || __ldg(buf + p0 + i) != __ldg(buf + op + i))
+				stopf = true;
+			else
+				c++;
+		}
+	}
+	unsigned m = (__ballot_sync(FULL, stopf) >> gshift) & 0xffu;
+	int fl = m ? __ffs(m) - 1 : 7;
+	const int fwd = 4 * fl + __shfl_sync(FULL, c, (int)(gshift + fl));
+	// no early exit: the other groups of the warp still need every lane at the ballots below
+	const bool fwd_ok = fwd >= kMinMatch;
+	const int need = kMinMatch - fwd;
+	const int64_t lo = last_match > 0 ? last_match : 0;
+	c = 0;
+	stopf = false;
+	if (act && !fwd_ok) {
+#pragma unroll
+		for (int k = 0; k < 4; k++) {
+			const int j = 4 * gl + k;
+			if (stopf)
+				break;
+			if (j >= need || p0 - j <= lo || op - j <= 0 || __ldg(buf + op - j - 1) != __ldg(buf + p0 - j - 1))
+				stopf = true;
+			else
+				c++;
+		}
+	}
+	m = (__ballot_sync(FULL, stopf) >> gshift) & 0xffu;
+	fl = m ? __ffs(m) - 1 : 7;
+	const int rev = 4 * fl + __shfl_sync(FULL, c, (int)(gshift + fl));
+	if (fwd_ok)
+		return act;
+	return act && rev >= need;
+}
+
+// cand_idx: index into sh->qpos / sh->qtag / sh->ev of this lane's GROUP's candidate, or -1 (group idle).
+__device__ void group_eval(const uint8_t *__restrict__ buf, const HEntry *tab, unsigned hmask, FastShared *sh, int cand_idx,
+			   int64_t tag_mask, int64_t better, int max_chain, int64_t end, int64_t last_match, int lane, int warp)
+{
+	const int g = lane >> 3, gl = lane & 7;
+	long long *eq_list = sh->eq_off[warp][g];
+	const unsigned gshift = (unsigned)g * 8u;
+	const unsigned ltg = (1u << gl) - 1;
+	const bool active = cand_idx >= 0;
+	int64_t p = 0, t = 0;
+	if (active) {
+		p = sh->qpos[cand_idx];
+		t = sh->qtag[cand_idx];
+	}
+	LaneEval *R = &sh->ev[active ? cand_idx : 0];
+	const bool do_insert = (t & tag_mask) == tag_mask;
+	int nw = 0, nr = 0, net = 0, miss = 0;
+	bool cx = false;
+
+	// ---- walk 1: the lookup chain [home, first empty slot], and on the way the insert target
+	const unsigned h = (unsigned)t & hmask;
+	const int my_ones = tz_ones(t);
+	unsigned s = 0, sslot = 0;
+	bool stop = !do_insert, done = !active;
+	int kind = -1, round = 0, neq = 0;
+	int64_t occ_off = 0, occ_tag = 0;
+	while (__any_sync(FULL, !done)) {
+		HEntry e;
+		e.offset = e.tag = 0;
+		if (!done)
+			e = ld_entry(tab + ((h + s + (unsigned)gl) & hmask));
+		const bool emp = !(e.offset | e.tag);
+		const bool due = !emp && (e.tag & better) != better;
+		const bool les = !emp && !due && tz_ones(e.tag) < my_ones;
+		const bool eq = !emp && e.tag == t;
+		if (eq && e.offset > 0 && e.offset < p)
+			prefetch_l1(buf + e.offset);
+		const unsigned em = (__ballot_sync(FULL, emp) >> gshift) & 0xffu;
+		const unsigned dm = (__ballot_sync(FULL, due) >> gshift) & 0xffu;
+		const unsigned lm = (__ballot_sync(FULL, les) >> gshift) & 0xffu;
+		const unsigned qm = (__ballot_sync(FULL, eq) >> gshift) & 0xffu;
+		const int fe = em ? __ffs(em) - 1 : 8;
+		const unsigned valid = (1u << fe) - 1;
+		const unsigned sc = (dm | lm) & valid;
+		const int fs = sc ? __ffs(sc) - 1 : 8;
+		const int src = (int)gshift + (fs & 7);
+		const int64_t oo = __shfl_sync(FULL, e.offset, src), ot = __shfl_sync(FULL, e.tag, src);
+		if (!done) {
+			if (!stop) {
+				const unsigned before = valid & ((1u << fs) - 1);
+				round += __popc(qm & before);
+				if (round >= max_chain)
+					cx = true; // chain cap: victim_round logic stays serial
+				if (sc) {
+					stop = true;
+					sslot = (h + s + (unsigned)fs) & hmask;
+					kind = ((dm >> fs) & 1) ? kProbeDue : kProbeDisplace;
+					occ_off = oo;
+					occ_tag = ot;
+				} else if (em) {
+					kind = kProbeEmpty;
+					sslot = (h + s + (unsigned)fe) & hmask;
+				}
+			}
+			const unsigned eqv = qm & valid;
+			if (neq + __popc(eqv) > K2_MAXEQ)
+				cx = true;
+			else {
+				if ((eqv >> gl) & 1)
+					eq_list[neq + __popc(eqv & ltg)] = e.offset;
+				neq += __popc(eqv);
+			}
+			if (em) {
+				s += (unsigned)fe;
+				done = true;
+			} else {
+				s += 8;
+				if (s >= K2_MAXWALK)
+					cx = true;
+			}
+			if (cx)
+				done = true;
+		}
+	}
+	__syncwarp();
+	// ---- equal-tag entries: would any of them give a match?  (then the serial step must decide)
+	for (int q = 0; __any_sync(FULL, active && !cx && q < neq); q++) {
+		const bool act = active && !cx && q < neq;
+		const int64_t op = act ? eq_list[q] : 0;
+		const bool cm = group_could_match(buf, p, op, end, last_match, act, gshift, gl);
+		if (act) {
+			if (cm)
+				cx = true;
+			else
+				miss++;
+		}
+	}
+	if (active && gl == 0) {
+		R->rlo[0] = h;
+		R->rlen[0] = s + 1;
+	}
+	nr = 1;
+	// ---- the insert and the re-homing of displaced occupants (all probing on the unmodified table)
+	bool chain = active && !cx && do_insert;
+	const int ins = chain ? 1 : 0;
+	int64_t wt = t, wo = p;
+	while (__any_sync(FULL, chain)) {
+		unsigned h2 = 0, s2 = 0;
+		int ones2 = 0;
+		bool wdone = true;
+		if (chain) {
+			if (gl == 0) {
+				R->wslot[nw] = sslot;
+				R->wtag[nw] = wt;
+				R->woff[nw] = wo;
+			}
+			nw++;
+			if (kind != kProbeDisplace) {
+				net = (kind == kProbeEmpty) ? 1 : 0;
+				chain = false;
+			} else if (nw == K2_MAXW) {
+				cx = true;
+				chain = false;
+			} else { // re-home the displaced occupant (the reference recurses before it overwrites the slot)
+				wt = occ_tag;
+				wo = occ_off;
+				h2 = (unsigned)wt & hmask;
+				ones2 = tz_ones(wt);
+				round = 0;
+				kind = -1;
+				wdone = false;
+			}
+		}
+		while (__any_sync(FULL, !wdone)) {
+			HEntry e;
+			e.offset = e.tag = 0;
+			if (!wdone)
+				e = ld_entry(tab + ((h2 + s2 + (unsigned)gl) & hmask));
+			const bool emp = !(e.offset | e.tag);
+			const bool due = !emp && (e.tag & better) != better;
+			const bool les = !emp && !due && tz_ones(e.tag) < ones2;
+			const bool eq = !emp && e.tag == wt;
+			const unsigned em = (__ballot_sync(FULL, emp) >> gshift) & 0xffu;
+			const unsigned dm = (__ballot_sync(FULL, due) >> gshift) & 0xffu;
+			const unsigned lm = (__ballot_sync(FULL, les) >> gshift) & 0xffu;
+			const unsigned qm = (__ballot_sync(FULL, eq) >> gshift) & 0xffu;
+			const unsigned xm = em | dm | lm;
+			const int fx = xm ? __ffs(xm) - 1 : 8;
+			const int src = (int)gshift + (fx & 7);
+			const int64_t oo = __shfl_sync(FULL, e.offset, src), ot = __shfl_sync(FULL, e.tag, src);
+			if (!wdone) {
+				round += __popc(qm & ((1u << fx) - 1));
+				if (round >= max_chain) {
+					cx = true;
+					wdone = true;
+					chain = false;
+				} else if (xm) {
+					sslot = (h2 + s2 + (unsigned)fx) & hmask;
+					kind = ((em >> fx) & 1) ? kProbeEmpty : (((dm >> fx) & 1) ? kProbeDue : kProbeDisplace);
+					occ_off = oo;
+					occ_tag = ot;
+					s2 += (unsigned)fx;
+					wdone = true;
+					if (gl == 0) {
+						R->rlo[nr] = h2;
+						R->rlen[nr] = s2 + 1;
+					}
+					nr++;
+				} else {
+					s2 += 8;
+					if (s2 >= K2_MAXWALK) {
+						cx = true;
+						wdone = true;
+						chain = false;
+					}
+				}
+			}
+		}
+	}
+	if (active && gl == 0) {
+		R->nw = nw;
+		R->nr = nr;
+		R->net = cx ? 0 : net;
+		R->ins = ins;
+		R->miss = miss;
+		R->cx = cx;
+	}
+	__syncwarp();
+}
+
+// Warps 1..7 of the commit CTA: evaluate candidates 4*warp .. 4*warp+3 of every batch the commit warp queues.
+__device__ void k2_eval_worker(const uint8_t *__restrict__ buf, const HEntry *tab, unsigned hmask, FastShared *sh, int warp,
+			       int lane)
+{
+	for (;;) {
+		k2_bar(K2_BAR_GO);
+		if (sh->cmd_exit)
+			return;
+		const int ci = warp * 4 + (lane >> 3);
+		if (warp * 4 < sh->cmd_nb)
+			group_eval(buf, tab, hmask, sh, ci < sh->cmd_nb ? ci : -1, sh->cmd_tag_mask, sh->cmd_better, sh->cmd_max_chain,
+				   sh->cmd_end, sh->cmd_last_match, lane, warp);
+		k2_bar(K2_BAR_DONE);
+	}
+}
+
 __device__ __forceinline__ int warp_sum(int v)
 {
 #pragma unroll
@@ -750,12 +1024,78 @@ __device__ void k2_commit_segment_batched(WarpPrim &prim, FastShared *sh, ScanSt
 		int64_t myp = 0, myt = 0;
 		dbg[0]++;
 		const long long ce0 = clock64();
-		if (lane < nb) {
+		if (lane < nb) { // pull each candidate's home line(s) and window bytes towards L1 before the passes
 			myp = sh->qpos[lane];
 			myt = sh->qtag[lane];
-			lane_eval(prim.buf, prim.tab, hmask, myp, myt, r.tag_mask, better, c.max_chain, c.end, r.last_match, pf_lines, L);
+			const unsigned hh = (unsigned)myt & hmask;
+			prefetch_l1(prim.buf + myp);
+			for (int l = 0; l <= pf_lines; l++)
+				prefetch_l1(prim.tab + ((hh + 8u * (unsigned)l) & hmask));
 		}
+		if (lane == 0) { // all 8 warps of the CTA evaluate four candidates each
+			sh->cmd_tag_mask = r.tag_mask;
+			sh->cmd_better = better;
+			sh->cmd_end = c.end;
+			sh->cmd_last_match = r.last_match;
+			sh->cmd_nb = nb;
+			sh->cmd_max_chain = c.max_chain;
+		}
+		k2_bar(K2_BAR_GO);
+		{
+			const int ci = lane >> 3;
+			group_eval(prim.buf, prim.tab, hmask, sh, ci < nb ? ci : -1, r.tag_mask, better, c.max_chain, c.end,
+				   r.last_match, lane, 0);
+		}
+		k2_bar(K2_BAR_DONE);
+		if (lane < nb)
+			L = sh->ev[lane];
 		__syncwarp();
+#ifdef K2_CROSSCHECK
+		{ // development aid: the single-lane evaluator must agree with the cooperative one
+			bool bad = false;
+			LaneEval L2;
+			L2.nw = L2.nr = L2.net = L2.ins = L2.miss = 0;
+			L2.cx = false;
+			if (lane < nb) {
+				lane_eval(prim.buf, prim.tab, hmask, myp, myt, r.tag_mask, better, c.max_chain, c.end, r.last_match, 0, L2);
+				if (L2.cx)
+					L2.net = 0;
+				if (L.cx != L2.cx)
+					bad = !L.cx; // the cooperative form may only be stricter
+				else if (!L.cx) {
+					bad = L.nw != L2.nw || L.nr != L2.nr || L.net != L2.net || L.ins != L2.ins || L.miss != L2.miss;
+					for (int w = 0; w < L.nw && !bad; w++)
+						bad = L.wslot[w] != L2.wslot[w] || L.wtag[w] != L2.wtag[w] || L.woff[w] != L2.woff[w];
+					for (int q = 0; q < L.nr && !bad; q++)
+						bad = L.rlo[q] != L2.rlo[q] || L.rlen[q] != L2.rlen[q];
+				}
+			}
+			const unsigned bm = __ballot_sync(FULL, bad);
+			if (bm) {
+				if (lane == __ffs(bm) - 1) {
+					st->dbg[0] = myp;
+					st->dbg[1] = myt;
+					st->dbg[2] = ((int64_t)L.cx << 32) | (unsigned)L2.cx;
+					st->dbg[3] = ((int64_t)L.nw << 32) | (unsigned)L2.nw;
+					st->dbg[4] = ((int64_t)L.nr << 32) | (unsigned)L2.nr;
+					st->dbg[5] = ((int64_t)L.net << 32) | (unsigned)L2.net;
+					st->dbg[6] = ((int64_t)L.wslot[0] << 32) | L2.wslot[0];
+					st->dbg[7] = ((int64_t)L.wslot[1] << 32) | L2.wslot[1];
+					st->dbg[8] = ((int64_t)L.rlo[0] << 32) | L2.rlo[0];
+					st->dbg[9] = ((int64_t)L.rlen[0] << 32) | L2.rlen[0];
+					st->dbg[10] = ((int64_t)L.rlen[1] << 32) | L2.rlen[1];
+					st->dbg[11] = ((int64_t)L.miss << 32) | (unsigned)L2.miss;
+					st->dbg[12] = L.wtag[0];
+					st->dbg[13] = L2.wtag[0];
+					st->dbg[14] = r.tag_mask;
+					st->dbg[15] = ((int64_t)lane << 32) | (unsigned)nb;
+					st->status = -9;
+				}
+				status = -9;
+				break;
+			}
+		}
+#endif
 		dbg[8] += clock64() - ce0;
 		if (L.cx)
 			L.net = 0;
@@ -896,10 +1236,10 @@ __device__ void k2_commit_segment_batched(WarpPrim &prim, FastShared *sh, ScanSt
 			const int old_cl = __shfl_sync(FULL, (int)cl, k);
 			dbg[5]++;
 			const long long ce1 = clock64();
+			group_eval(prim.buf, prim.tab, hmask, sh, lane < 8 ? k : -1, r.tag_mask, better, c.max_chain, c.end,
+				   r.last_match, lane, 0);
 			if (lane == k) {
-				lane_eval(prim.buf, prim.tab, hmask, myp, myt, r.tag_mask, better, c.max_chain, c.end, r.last_match, pf_lines, L);
-				if (L.cx)
-					L.net = 0;
+				L = sh->ev[k];
 				cmask = 0;
 			}
 			__syncwarp();
@@ -945,7 +1285,7 @@ __device__ void k2_commit_segment_batched(WarpPrim &prim, FastShared *sh, ScanSt
 	}
 	if (status == kStatusRunning && last_segment)
 		k2_close_chunk(prim, st, r, c, recs, status);
-	if (lane == 0) {
+	if (lane == 0 && status != -9) {
 		dbg[10] = clock64() - clk_start;
 		for (int i = 0; i < 16; i++)
 			st->dbg[i] += dbg[i];
@@ -965,11 +1305,13 @@ k2_commit_kernel(const uint8_t *__restrict__ buf, ScanState *st, HEntry *tab, co
 		sh.prog.pos = st->scan_pos;
 		sh.prog.min_mask = st->min_mask;
 		sh.prog.done = (st->status != kStatusRunning) ? 1 : 0;
+		sh.cmd_exit = 0;
+		sh.cmd_nb = 0;
 	}
 	__syncthreads();
 	const int64_t hmask = ((int64_t)1 << st->hash_bits) - 1;
 	if (warp != 0) {
-		k2_helper(&sh.prog, buf, tab, hmask, cand, tile_count, first_tile, num_tiles, st->n, warp - 1, lane);
+		k2_eval_worker(buf, tab, (unsigned)hmask, &sh, warp, lane);
 		return;
 	}
 	WarpPrim prim;
@@ -991,8 +1333,12 @@ k2_commit_kernel(const uint8_t *__restrict__ buf, ScanState *st, HEntry *tab, co
 	prim.bmask = 0;
 	k2_commit_segment_batched(prim, &sh, st, recs, last_segment != 0);
 	__syncwarp();
-	if (lane == 0)
+	if (lane == 0) {
 		sh.prog.done = 1;
+		sh.cmd_exit = 1;
+	}
+	__syncwarp();
+	k2_bar(K2_BAR_GO); // releases the workers
 }
 
 int k2_launch(const uint8_t *d_buf, ScanState *d_state, HEntry *d_tab, const Cand *d_cand,

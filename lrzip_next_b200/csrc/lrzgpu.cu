@@ -150,15 +150,15 @@ int rzip_chunk_device(lrzgpu_ctx *c, const uint8_t *d_chunk, int64_t n, int rzip
 	CU(c, cudaStreamSynchronize(c->sA));
 	CU(c, cudaStreamSynchronize(c->sB));
 	res.st = *c->h_state;
-	if (res.st.status != kStatusChunkDone)
-		return fail(c, LRZGPU_EINTERNAL, "rzip commit ended with status %d at position %lld", res.st.status,
-			    (long long)res.st.scan_pos);
 	if (getenv("LRZGPU_DEBUG")) {
 		fprintf(stderr, "[lrzgpu] commit: n=%lld lookups=%lld", (long long)n, (long long)res.st.st_lookups);
 		for (int i = 0; i < 16; i++)
 			fprintf(stderr, " d%d=%lld", i, (long long)res.st.dbg[i]);
 		fprintf(stderr, "\n");
 	}
+	if (res.st.status != kStatusChunkDone)
+		return fail(c, LRZGPU_EINTERNAL, "rzip commit ended with status %d at position %lld", res.st.status,
+			    (long long)res.st.scan_pos);
 	res.s0_len = res.st.s0_len;
 	res.s1_len = res.st.s1_len;
 	res.n_rec = res.st.n_rec;
