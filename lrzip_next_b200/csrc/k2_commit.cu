@@ -332,7 +332,7 @@ static constexpr int K2_HELPERS = 7;
 static constexpr int K2_THREADS = 32 * (1 + K2_HELPERS);
 static constexpr int K2_LOOKAHEAD = 64;  // candidates the helpers may run ahead of the commit warp
 static constexpr int K2_MAXW = 4;        // insert writes one lane may carry (displacement depth 3)
-static constexpr unsigned K2_MAXWALK = 192;
+static constexpr unsigned K2_MAXWALK = 2048; // slots one candidate may walk before it is handed to the serial step
 
 struct LaneEval {
 	unsigned wslot[K2_MAXW + 1]; // insert writes, then (optionally) the sweep deletion
@@ -351,7 +351,7 @@ struct FastShared {
 	long long eq_off[8][4][K2_MAXEQ]; // per warp and group: offsets of the equal-tag entries met on the walk
 	// batch evaluation command, written by the commit warp before barrier 1 (see k2_eval_worker)
 	long long cmd_tag_mask, cmd_better, cmd_end, cmd_last_match;
-	int cmd_nb, cmd_max_chain, cmd_exit;
+	int cmd_nb, cmd_max_chain, cmd_exit, cmd_mode;
 	Progress prog;
 };
 
@@ -630,12 +630,14 @@ __device__ void lane_eval(const uint8_t *__restrict__ buf, const HEntry *tab, un
 
 // could_match() with the group's 8 lanes: 4 bytes per lane forwards, then backwards.
 __device__ __forceinline__ bool group_could_match(const uint8_t *__restrict__ buf, int64_t p0, int64_t op, int64_t end,
-						  int64_t last_match, bool act, unsigned gshift, int gl)
+						  int64_t last_match, bool act, bool part, unsigned gshift, int gl)
 {
+	// act: the group has a pair to test (group-uniform); part: this lane is one of the 8 that compare bytes
 	act = act && op < p0;
+	part = part && act;
 	int c = 0;
 	bool stopf = false;
-	if (act) {
+	if (part) {
 #pragma unroll
 		for (int k = 0; k < 4; k++) {
 			const int i = 4 * gl + k;
@@ -656,7 +658,7 @@ __device__ __forceinline__ bool group_could_match(const uint8_t *__restrict__ bu
 	const int64_t lo = last_match > 0 ? last_match : 0;
 	c = 0;
 	stopf = false;
-	if (act && !fwd_ok) {
+	if (part && !fwd_ok) {
 #pragma unroll
 		for (int k = 0; k < 4; k++) {
 			const int j = 4 * gl + k;
@@ -676,13 +678,30 @@ __device__ __forceinline__ bool group_could_match(const uint8_t *__restrict__ bu
 	return act && rev >= need;
 }
 
-// cand_idx: index into sh->qpos / sh->qtag / sh->ev of this lane's GROUP's candidate, or -1 (group idle).
-__device__ void group_eval(const uint8_t *__restrict__ buf, const HEntry *tab, unsigned hmask, FastShared *sh, int cand_idx,
-			   int64_t tag_mask, int64_t better, int max_chain, int64_t end, int64_t last_match, int lane, int warp)
+__device__ __forceinline__ unsigned low_mask(int n) { return n >= 32 ? 0xffffffffu : ((1u << n) - 1u); }
+
+// Evaluation modes: the probe chain of a candidate is about 2/3 * 2^bits slots long (bits = number of gate
+// bits: inserted tags have them all set, so homes fall on every 2^bits-th slot and the entries between two
+// homes pile up behind the first).  Short chains: 8 lanes per candidate, one 8-slot window per step.  Long
+// chains (tight gates, i.e. large inputs): the whole warp per candidate and P windows of 32 slots loaded AT
+// ONCE per step, so that a chain of hundreds of slots costs one L2 round trip instead of one per window.
+enum { K2_MODE_NARROW = 0, K2_MODE_WIDE2 = 1, K2_MODE_WIDE8 = 2 };
+__device__ __forceinline__ int k2_mode_for(int64_t tag_mask)
 {
-	const int g = lane >> 3, gl = lane & 7;
+	const int bits = __popcll(tag_mask);
+	return bits <= 4 ? K2_MODE_NARROW : (bits <= 6 ? K2_MODE_WIDE2 : K2_MODE_WIDE8);
+}
+
+// cand_idx: index into sh->qpos / sh->qtag / sh->ev of this lane's GROUP's candidate, or -1 (group idle).
+// G lanes per candidate (8 or 32), P windows of G slots in flight per step.
+template <int G, int P>
+__device__ void group_eval_t(const uint8_t *__restrict__ buf, const HEntry *tab, unsigned hmask, FastShared *sh, int cand_idx,
+			     int64_t tag_mask, int64_t better, int max_chain, int64_t end, int64_t last_match, int lane, int warp)
+{
+	constexpr unsigned GM = (G == 32) ? 0xffffffffu : ((1u << G) - 1u);
+	const int g = lane / G, gl = lane % G;
 	long long *eq_list = sh->eq_off[warp][g];
-	const unsigned gshift = (unsigned)g * 8u;
+	const unsigned gshift = (unsigned)(g * G);
 	const unsigned ltg = (1u << gl) - 1;
 	const bool active = cand_idx >= 0;
 	int64_t p = 0, t = 0;
@@ -703,61 +722,68 @@ __device__ void group_eval(const uint8_t *__restrict__ buf, const HEntry *tab, u
 	int kind = -1, round = 0, neq = 0;
 	int64_t occ_off = 0, occ_tag = 0;
 	while (__any_sync(FULL, !done)) {
-		HEntry e;
-		e.offset = e.tag = 0;
-		if (!done)
-			e = ld_entry(tab + ((h + s + (unsigned)gl) & hmask));
-		const bool emp = !(e.offset | e.tag);
-		const bool due = !emp && (e.tag & better) != better;
-		const bool les = !emp && !due && tz_ones(e.tag) < my_ones;
-		const bool eq = !emp && e.tag == t;
-		if (eq && e.offset > 0 && e.offset < p)
-			prefetch_l1(buf + e.offset);
-		const unsigned em = (__ballot_sync(FULL, emp) >> gshift) & 0xffu;
-		const unsigned dm = (__ballot_sync(FULL, due) >> gshift) & 0xffu;
-		const unsigned lm = (__ballot_sync(FULL, les) >> gshift) & 0xffu;
-		const unsigned qm = (__ballot_sync(FULL, eq) >> gshift) & 0xffu;
-		const int fe = em ? __ffs(em) - 1 : 8;
-		const unsigned valid = (1u << fe) - 1;
-		const unsigned sc = (dm | lm) & valid;
-		const int fs = sc ? __ffs(sc) - 1 : 8;
-		const int src = (int)gshift + (fs & 7);
-		const int64_t oo = __shfl_sync(FULL, e.offset, src), ot = __shfl_sync(FULL, e.tag, src);
-		if (!done) {
-			if (!stop) {
-				const unsigned before = valid & ((1u << fs) - 1);
-				round += __popc(qm & before);
-				if (round >= max_chain)
-					cx = true; // chain cap: victim_round logic stays serial
-				if (sc) {
-					stop = true;
-					sslot = (h + s + (unsigned)fs) & hmask;
-					kind = ((dm >> fs) & 1) ? kProbeDue : kProbeDisplace;
-					occ_off = oo;
-					occ_tag = ot;
-				} else if (em) {
-					kind = kProbeEmpty;
-					sslot = (h + s + (unsigned)fe) & hmask;
+		HEntry ew[P];
+#pragma unroll
+		for (int i = 0; i < P; i++) {
+			ew[i].offset = ew[i].tag = 0;
+			if (!done)
+				ew[i] = ld_entry(tab + ((h + s + (unsigned)(i * G + gl)) & hmask));
+		}
+#pragma unroll
+		for (int i = 0; i < P; i++) {
+			const HEntry e = ew[i];
+			const bool emp = !(e.offset | e.tag);
+			const bool due = !emp && (e.tag & better) != better;
+			const bool les = !emp && !due && tz_ones(e.tag) < my_ones;
+			const bool eq = !emp && e.tag == t;
+			if (eq && !done && e.offset > 0 && e.offset < p)
+				prefetch_l1(buf + e.offset);
+			const unsigned em = (__ballot_sync(FULL, emp) >> gshift) & GM;
+			const unsigned dm = (__ballot_sync(FULL, due) >> gshift) & GM;
+			const unsigned lm = (__ballot_sync(FULL, les) >> gshift) & GM;
+			const unsigned qm = (__ballot_sync(FULL, eq) >> gshift) & GM;
+			const int fe = em ? __ffs(em) - 1 : G;
+			const unsigned valid = low_mask(fe);
+			const unsigned sc = (dm | lm) & valid;
+			const int fs = sc ? __ffs(sc) - 1 : G;
+			const int src = (int)gshift + (fs % G);
+			const int64_t oo = __shfl_sync(FULL, e.offset, src), ot = __shfl_sync(FULL, e.tag, src);
+			if (!done) {
+				if (!stop) {
+					const unsigned before = valid & low_mask(fs);
+					round += __popc(qm & before);
+					if (round >= max_chain)
+						cx = true; // chain cap: victim_round logic stays serial
+					if (sc) {
+						stop = true;
+						sslot = (h + s + (unsigned)fs) & hmask;
+						kind = ((dm >> fs) & 1) ? kProbeDue : kProbeDisplace;
+						occ_off = oo;
+						occ_tag = ot;
+					} else if (em) {
+						kind = kProbeEmpty;
+						sslot = (h + s + (unsigned)fe) & hmask;
+					}
 				}
-			}
-			const unsigned eqv = qm & valid;
-			if (neq + __popc(eqv) > K2_MAXEQ)
-				cx = true;
-			else {
-				if ((eqv >> gl) & 1)
-					eq_list[neq + __popc(eqv & ltg)] = e.offset;
-				neq += __popc(eqv);
-			}
-			if (em) {
-				s += (unsigned)fe;
-				done = true;
-			} else {
-				s += 8;
-				if (s >= K2_MAXWALK)
+				const unsigned eqv = qm & valid;
+				if (neq + __popc(eqv) > K2_MAXEQ)
 					cx = true;
+				else {
+					if ((eqv >> gl) & 1)
+						eq_list[neq + __popc(eqv & ltg)] = e.offset;
+					neq += __popc(eqv);
+				}
+				if (em) {
+					s += (unsigned)fe;
+					done = true;
+				} else {
+					s += G;
+					if (s >= K2_MAXWALK)
+						cx = true;
+				}
+				if (cx)
+					done = true;
 			}
-			if (cx)
-				done = true;
 		}
 	}
 	__syncwarp();
@@ -765,7 +791,7 @@ __device__ void group_eval(const uint8_t *__restrict__ buf, const HEntry *tab, u
 	for (int q = 0; __any_sync(FULL, active && !cx && q < neq); q++) {
 		const bool act = active && !cx && q < neq;
 		const int64_t op = act ? eq_list[q] : 0;
-		const bool cm = group_could_match(buf, p, op, end, last_match, act, gshift, gl);
+		const bool cm = group_could_match(buf, p, op, end, last_match, act, gl < 8, gshift, gl & 7);
 		if (act) {
 			if (cm)
 				cx = true;
@@ -810,46 +836,53 @@ __device__ void group_eval(const uint8_t *__restrict__ buf, const HEntry *tab, u
 			}
 		}
 		while (__any_sync(FULL, !wdone)) {
-			HEntry e;
-			e.offset = e.tag = 0;
-			if (!wdone)
-				e = ld_entry(tab + ((h2 + s2 + (unsigned)gl) & hmask));
-			const bool emp = !(e.offset | e.tag);
-			const bool due = !emp && (e.tag & better) != better;
-			const bool les = !emp && !due && tz_ones(e.tag) < ones2;
-			const bool eq = !emp && e.tag == wt;
-			const unsigned em = (__ballot_sync(FULL, emp) >> gshift) & 0xffu;
-			const unsigned dm = (__ballot_sync(FULL, due) >> gshift) & 0xffu;
-			const unsigned lm = (__ballot_sync(FULL, les) >> gshift) & 0xffu;
-			const unsigned qm = (__ballot_sync(FULL, eq) >> gshift) & 0xffu;
-			const unsigned xm = em | dm | lm;
-			const int fx = xm ? __ffs(xm) - 1 : 8;
-			const int src = (int)gshift + (fx & 7);
-			const int64_t oo = __shfl_sync(FULL, e.offset, src), ot = __shfl_sync(FULL, e.tag, src);
-			if (!wdone) {
-				round += __popc(qm & ((1u << fx) - 1));
-				if (round >= max_chain) {
-					cx = true;
-					wdone = true;
-					chain = false;
-				} else if (xm) {
-					sslot = (h2 + s2 + (unsigned)fx) & hmask;
-					kind = ((em >> fx) & 1) ? kProbeEmpty : (((dm >> fx) & 1) ? kProbeDue : kProbeDisplace);
-					occ_off = oo;
-					occ_tag = ot;
-					s2 += (unsigned)fx;
-					wdone = true;
-					if (gl == 0) {
-						R->rlo[nr] = h2;
-						R->rlen[nr] = s2 + 1;
-					}
-					nr++;
-				} else {
-					s2 += 8;
-					if (s2 >= K2_MAXWALK) {
+			HEntry ew[P];
+#pragma unroll
+			for (int i = 0; i < P; i++) {
+				ew[i].offset = ew[i].tag = 0;
+				if (!wdone)
+					ew[i] = ld_entry(tab + ((h2 + s2 + (unsigned)(i * G + gl)) & hmask));
+			}
+#pragma unroll
+			for (int i = 0; i < P; i++) {
+				const HEntry e = ew[i];
+				const bool emp = !(e.offset | e.tag);
+				const bool due = !emp && (e.tag & better) != better;
+				const bool les = !emp && !due && tz_ones(e.tag) < ones2;
+				const bool eq = !emp && e.tag == wt;
+				const unsigned em = (__ballot_sync(FULL, emp) >> gshift) & GM;
+				const unsigned dm = (__ballot_sync(FULL, due) >> gshift) & GM;
+				const unsigned lm = (__ballot_sync(FULL, les) >> gshift) & GM;
+				const unsigned qm = (__ballot_sync(FULL, eq) >> gshift) & GM;
+				const unsigned xm = em | dm | lm;
+				const int fx = xm ? __ffs(xm) - 1 : G;
+				const int src = (int)gshift + (fx % G);
+				const int64_t oo = __shfl_sync(FULL, e.offset, src), ot = __shfl_sync(FULL, e.tag, src);
+				if (!wdone) {
+					round += __popc(qm & low_mask(fx));
+					if (round >= max_chain) {
 						cx = true;
 						wdone = true;
 						chain = false;
+					} else if (xm) {
+						sslot = (h2 + s2 + (unsigned)fx) & hmask;
+						kind = ((em >> fx) & 1) ? kProbeEmpty : (((dm >> fx) & 1) ? kProbeDue : kProbeDisplace);
+						occ_off = oo;
+						occ_tag = ot;
+						s2 += (unsigned)fx;
+						wdone = true;
+						if (gl == 0) {
+							R->rlo[nr] = h2;
+							R->rlen[nr] = s2 + 1;
+						}
+						nr++;
+					} else {
+						s2 += G;
+						if (s2 >= K2_MAXWALK) {
+							cx = true;
+							wdone = true;
+							chain = false;
+						}
 					}
 				}
 			}
@@ -866,6 +899,35 @@ __device__ void group_eval(const uint8_t *__restrict__ buf, const HEntry *tab, u
 	__syncwarp();
 }
 
+// This warp's share of a batch of nb candidates (warp 0..7), in the given mode.
+__device__ void k2_eval_share(const uint8_t *__restrict__ buf, const HEntry *tab, unsigned hmask, FastShared *sh, int nb, int mode,
+			      int64_t tag_mask, int64_t better, int max_chain, int64_t end, int64_t last_match, int lane, int warp)
+{
+	if (mode == K2_MODE_NARROW) {
+		const int ci = warp * 4 + (lane >> 3);
+		if (warp * 4 < nb)
+			group_eval_t<8, 1>(buf, tab, hmask, sh, ci < nb ? ci : -1, tag_mask, better, max_chain, end, last_match, lane, warp);
+	} else if (mode == K2_MODE_WIDE2) {
+		for (int ci = warp; ci < nb; ci += 8)
+			group_eval_t<32, 2>(buf, tab, hmask, sh, ci, tag_mask, better, max_chain, end, last_match, lane, warp);
+	} else {
+		for (int ci = warp; ci < nb; ci += 8)
+			group_eval_t<32, 8>(buf, tab, hmask, sh, ci, tag_mask, better, max_chain, end, last_match, lane, warp);
+	}
+}
+
+// One candidate, by the calling warp alone (re-evaluation on the updated table).
+__device__ void k2_eval_one(const uint8_t *__restrict__ buf, const HEntry *tab, unsigned hmask, FastShared *sh, int k, int mode,
+			    int64_t tag_mask, int64_t better, int max_chain, int64_t end, int64_t last_match, int lane)
+{
+	if (mode == K2_MODE_NARROW)
+		group_eval_t<8, 1>(buf, tab, hmask, sh, lane < 8 ? k : -1, tag_mask, better, max_chain, end, last_match, lane, 0);
+	else if (mode == K2_MODE_WIDE2)
+		group_eval_t<32, 2>(buf, tab, hmask, sh, k, tag_mask, better, max_chain, end, last_match, lane, 0);
+	else
+		group_eval_t<32, 8>(buf, tab, hmask, sh, k, tag_mask, better, max_chain, end, last_match, lane, 0);
+}
+
 // Warps 1..7 of the commit CTA: evaluate candidates 4*warp .. 4*warp+3 of every batch the commit warp queues.
 __device__ void k2_eval_worker(const uint8_t *__restrict__ buf, const HEntry *tab, unsigned hmask, FastShared *sh, int warp,
 			       int lane)
@@ -874,10 +936,8 @@ __device__ void k2_eval_worker(const uint8_t *__restrict__ buf, const HEntry *ta
 		k2_bar(K2_BAR_GO);
 		if (sh->cmd_exit)
 			return;
-		const int ci = warp * 4 + (lane >> 3);
-		if (warp * 4 < sh->cmd_nb)
-			group_eval(buf, tab, hmask, sh, ci < sh->cmd_nb ? ci : -1, sh->cmd_tag_mask, sh->cmd_better, sh->cmd_max_chain,
-				   sh->cmd_end, sh->cmd_last_match, lane, warp);
+		k2_eval_share(buf, tab, hmask, sh, sh->cmd_nb, sh->cmd_mode, sh->cmd_tag_mask, sh->cmd_better, sh->cmd_max_chain,
+			      sh->cmd_end, sh->cmd_last_match, lane, warp);
 		k2_bar(K2_BAR_DONE);
 	}
 }
@@ -1018,6 +1078,7 @@ __device__ void k2_commit_segment_batched(WarpPrim &prim, FastShared *sh, ScanSt
 			if (pf_lines > 24)
 				pf_lines = 24;
 		}
+		const int mode = k2_mode_for(r.tag_mask);
 		LaneEval L;
 		L.nw = L.nr = L.net = L.ins = L.miss = 0;
 		L.cx = false;
@@ -1029,8 +1090,9 @@ __device__ void k2_commit_segment_batched(WarpPrim &prim, FastShared *sh, ScanSt
 			myt = sh->qtag[lane];
 			const unsigned hh = (unsigned)myt & hmask;
 			prefetch_l1(prim.buf + myp);
-			for (int l = 0; l <= pf_lines; l++)
-				prefetch_l1(prim.tab + ((hh + 8u * (unsigned)l) & hmask));
+			if (mode == K2_MODE_NARROW)
+				for (int l = 0; l <= pf_lines; l++)
+					prefetch_l1(prim.tab + ((hh + 8u * (unsigned)l) & hmask));
 		}
 		if (lane == 0) { // all 8 warps of the CTA evaluate four candidates each
 			sh->cmd_tag_mask = r.tag_mask;
@@ -1039,13 +1101,10 @@ __device__ void k2_commit_segment_batched(WarpPrim &prim, FastShared *sh, ScanSt
 			sh->cmd_last_match = r.last_match;
 			sh->cmd_nb = nb;
 			sh->cmd_max_chain = c.max_chain;
+			sh->cmd_mode = mode;
 		}
 		k2_bar(K2_BAR_GO);
-		{
-			const int ci = lane >> 3;
-			group_eval(prim.buf, prim.tab, hmask, sh, ci < nb ? ci : -1, r.tag_mask, better, c.max_chain, c.end,
-				   r.last_match, lane, 0);
-		}
+		k2_eval_share(prim.buf, prim.tab, hmask, sh, nb, mode, r.tag_mask, better, c.max_chain, c.end, r.last_match, lane, 0);
 		k2_bar(K2_BAR_DONE);
 		if (lane < nb)
 			L = sh->ev[lane];
@@ -1163,11 +1222,25 @@ __device__ void k2_commit_segment_batched(WarpPrim &prim, FastShared *sh, ScanSt
 				if (w >= nwj)
 					break;
 				const unsigned sl = __shfl_sync(FULL, L.wslot[w], j);
+#ifdef K2_CONFSTAT
+				const int jnw = __shfl_sync(FULL, L.nw, j);
+#endif
 				if (lane > j) {
-#pragma unroll
-					for (int q = 0; q < K2_MAXW; q++)
-						if (q < L.nr && ((sl - L.rlo[q]) & hmask) < L.rlen[q])
+					for (int q = 0; q < L.nr; q++) // almost always one range (two with a displacement)
+						if (((sl - L.rlo[q]) & hmask) < L.rlen[q]) {
 							cmask |= 1u << j;
+#ifdef K2_CONFSTAT
+							// writer kind: 0 insert target, 1 re-home target, 2 sweep deletion; reader: range q, place in range
+							const int wk = (w >= jnw) ? 2 : (w == 0 ? 0 : 1);
+							const unsigned place = (sl - L.rlo[q]) & hmask;
+							const int pk = (place == L.rlen[q] - 1) ? 0 : ((L.nw > 0 && sl == L.wslot[0]) ? 1 : 2); // end-empty, my target, interior
+							atomicAdd((unsigned long long *)&st->dbg[wk * 3 + pk], 1ull);
+							if (q > 0)
+								atomicAdd((unsigned long long *)&st->dbg[9], 1ull);
+							if (lane == j + 1)
+								atomicAdd((unsigned long long *)&st->dbg[10], 1ull);
+#endif
+						}
 				}
 			}
 		};
@@ -1236,8 +1309,7 @@ __device__ void k2_commit_segment_batched(WarpPrim &prim, FastShared *sh, ScanSt
 			const int old_cl = __shfl_sync(FULL, (int)cl, k);
 			dbg[5]++;
 			const long long ce1 = clock64();
-			group_eval(prim.buf, prim.tab, hmask, sh, lane < 8 ? k : -1, r.tag_mask, better, c.max_chain, c.end,
-				   r.last_match, lane, 0);
+			k2_eval_one(prim.buf, prim.tab, hmask, sh, k, mode, r.tag_mask, better, c.max_chain, c.end, r.last_match, lane);
 			if (lane == k) {
 				L = sh->ev[k];
 				cmask = 0;
@@ -1287,8 +1359,13 @@ __device__ void k2_commit_segment_batched(WarpPrim &prim, FastShared *sh, ScanSt
 		k2_close_chunk(prim, st, r, c, recs, status);
 	if (lane == 0 && status != -9) {
 		dbg[10] = clock64() - clk_start;
+#ifndef K2_CONFSTAT
 		for (int i = 0; i < 16; i++)
 			st->dbg[i] += dbg[i];
+#else
+		st->dbg[11] += dbg[5];
+		st->dbg[12] += dbg[1];
+#endif
 		st->st_displacements += n_disp;
 		k2_store_regs(st, r, n, status);
 	}
