@@ -168,6 +168,9 @@ def main():
     ap.add_argument("--size-mb", type=int, default=0, help="override the per-GPU input size (MiB)")
     ap.add_argument("--threads", type=int, default=0, help="-p given to both arms (default: host cores)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--verify", action="store_true",
+                    help="after timing (N=1): run the unmodified reference on the FULL workload with the same flags and "
+                         "compare archive SHA-256 (minutes of CPU time; outside every timed region)")
     a = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -270,6 +273,8 @@ def main():
         if world == 1:
             out, ol, st = ctx.compress_raw(pinned.data_ptr(), size, params)
             last.update(out_len=ol, stats=st.as_dict())
+            if a.verify:
+                last["sha256"] = hashlib.sha256(C.string_at(out, ol)).hexdigest()
             ctx.free(out)
         else:
             step_device()
@@ -358,8 +363,32 @@ def main():
             cpu_baseline = {"value": None, "unit": "MB/s", "cores": 0, "kind": "reference",
                             "sample": "oracle/_ref/lrzip-next not built"}
 
+    verified = None
+    if a.verify and rank == 0 and world == 1 and "sha256" in last:
+        ref = os.path.join(ROOT, "oracle", "_ref", "lrzip-next")
+        d = tempfile.mkdtemp(dir="/dev/shm" if os.path.isdir("/dev/shm") else None)
+        src, dst = os.path.join(d, "in.bin"), os.path.join(d, "out.lrz")
+        try:
+            host.tofile(src)
+            t0 = time.perf_counter()
+            subprocess.run([ref, *ref_flags(backend, level, threads, ram_units), "-o", dst, src], check=True,
+                           env=dict(os.environ, LRZIP="NOCONFIG"), stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+            ref_s = time.perf_counter() - t0
+            hsh = hashlib.sha256()
+            with open(dst, "rb") as fh:
+                for blk in iter(lambda: fh.read(1 << 24), b""):
+                    hsh.update(blk)
+            verified = {"identical_to_reference": hsh.hexdigest() == last["sha256"], "sha256": last["sha256"],
+                        "reference_seconds_full_workload": ref_s, "reference_MBps_full_workload": size / ref_s / MB}
+        finally:
+            for f in (src, dst):
+                if os.path.exists(f):
+                    os.unlink(f)
+            os.rmdir(d)
+
     if rank == 0:
         print(json.dumps({
+            "verified": verified,
             "metric": "compress MB/s (input bytes)", "value": value, "unit": "MB/s", "n_gpus": world, "steps": a.steps,
             "warmup": a.warmup, "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "u8", "data": "synthetic", "config": config, "clocks": clocks,

@@ -40,6 +40,42 @@ __device__ __forceinline__ void load16u(const uint8_t *p, uint64_t &lo, uint64_t
 	}
 }
 
+// Certain "no match of >= 31 bytes between p0 and the earlier offset op" from 16 bytes either side of both
+// positions (single_match_len src/rzip.c:431-461 returns 0).  The rolling tag is an XOR over the window, so it
+// is blind to byte order and to pairs of equal bytes: on text nearly every lookup meets equal-tag entries
+// whose bytes differ at once.  This test lets one lane dismiss one such entry with four independent loads;
+// false means "a match, or agreement too long to tell" and the full compare decides.
+__device__ __forceinline__ bool quick_no_match(const uint8_t *__restrict__ buf, int64_t p0, int64_t op, int64_t end,
+					       int64_t last_match)
+{
+	if (op >= p0)
+		return true;
+	uint64_t a0, a1, b0, b1, c0, c1, d0, d1;
+	load16u(buf + p0, a0, a1);
+	load16u(buf + op, b0, b1);
+	load16u(buf + p0 - 16, c0, c1);
+	load16u(buf + op - 16, d0, d1);
+	const uint64_t x0 = a0 ^ b0, x1 = a1 ^ b1;
+	const int cf = x0 ? ((__ffsll((long long)x0) - 1) >> 3) : (x1 ? 8 + ((__ffsll((long long)x1) - 1) >> 3) : 16);
+	const int64_t fwd_cap = (end - p0 < kMinMatch) ? end - p0 : kMinMatch;
+	if (cf >= 16 && fwd_cap > 16)
+		return false;
+	const int64_t fwd = cf < fwd_cap ? cf : fwd_cap;
+	const int64_t need = kMinMatch - fwd;
+	const int64_t lo = last_match > 0 ? last_match : 0;
+	int64_t rev_cap = need;
+	if (p0 - lo < rev_cap)
+		rev_cap = p0 - lo;
+	if (op < rev_cap)
+		rev_cap = op;
+	const uint64_t y0 = c0 ^ d0, y1 = c1 ^ d1;
+	const int cr = y1 ? (__clzll((long long)y1) >> 3) : (y0 ? 8 + (__clzll((long long)y0) >> 3) : 16);
+	if (cr >= 16 && rev_cap > 16)
+		return false;
+	const int64_t rev = cr < rev_cap ? cr : rev_cap;
+	return rev < need;
+}
+
 __device__ __forceinline__ HEntry ld_entry(const HEntry *p)
 {
 	const longlong2 v = *reinterpret_cast<const longlong2 *>(p);
@@ -249,6 +285,13 @@ struct WarpPrim {
 			const uint32_t em = __ballot_sync(FULL, emp);
 			const uint32_t valid = em ? ((1u << (__ffs(em) - 1)) - 1) : FULL;
 			uint32_t eq = __ballot_sync(FULL, e.tag == t) & valid;
+			if (eq) { // every lane dismisses its own equal-tag entry if its bytes differ at once
+				const bool mine = (eq >> lane) & 1;
+				const bool no = mine && quick_no_match(buf, p, e.offset, end, last_match);
+				const uint32_t nom = __ballot_sync(FULL, no);
+				misses += __popc(nom);
+				eq &= ~nom;
+			}
 			while (eq) {
 				const int l = __ffs(eq) - 1;
 				eq &= eq - 1;
@@ -348,6 +391,8 @@ struct FastShared {
 	long long qpos[64], qtag[64]; // queue of upcoming candidates that pass the current gate
 	unsigned dslot[32];           // sweep deletions of the current batch, in order
 	LaneEval ev[32];              // evaluation results of the batch, written by the 8-lane groups
+	unsigned vslot[32 * (K2_MAXW + 1)]; // validation: slots written by the batch, in lane order ...
+	unsigned char vown[32 * (K2_MAXW + 1)]; // ... and the lane that writes each
 	long long eq_off[8][4][K2_MAXEQ]; // per warp and group: offsets of the equal-tag entries met on the walk
 	// batch evaluation command, written by the commit warp before barrier 1 (see k2_eval_worker)
 	long long cmd_tag_mask, cmd_better, cmd_end, cmd_last_match;
@@ -788,15 +833,28 @@ __device__ void group_eval_t(const uint8_t *__restrict__ buf, const HEntry *tab,
 	}
 	__syncwarp();
 	// ---- equal-tag entries: would any of them give a match?  (then the serial step must decide)
-	for (int q = 0; __any_sync(FULL, active && !cx && q < neq); q++) {
-		const bool act = active && !cx && q < neq;
-		const int64_t op = act ? eq_list[q] : 0;
-		const bool cm = group_could_match(buf, p, op, end, last_match, act, gl < 8, gshift, gl & 7);
-		if (act) {
-			if (cm)
-				cx = true;
-			else
-				miss++;
+	// One lane per entry dismisses the ones whose bytes differ at once (all loads in flight together);
+	// the rare survivors get the group-wide compare.
+	for (int qb = 0; __any_sync(FULL, active && !cx && qb < neq); qb += G) {
+		const int q = qb + gl;
+		const bool have = active && !cx && q < neq;
+		const bool no = have && quick_no_match(buf, p, eq_list[q], end, last_match);
+		const unsigned nom = (__ballot_sync(FULL, no) >> gshift) & GM;
+		unsigned left = (__ballot_sync(FULL, have) >> gshift) & GM & ~nom;
+		if (active && !cx)
+			miss += __popc(nom);
+		while (__any_sync(FULL, left != 0)) {
+			const bool act = left != 0 && !cx;
+			const int b = left ? __ffs(left) - 1 : 0;
+			left &= left - 1;
+			const int64_t op = act ? eq_list[qb + b] : 0;
+			const bool cm = group_could_match(buf, p, op, end, last_match, act, gl < 8, gshift, gl & 7);
+			if (act) {
+				if (cm)
+					cx = true;
+				else
+					miss++;
+			}
 		}
 	}
 	if (active && gl == 0) {
@@ -1213,8 +1271,43 @@ __device__ void k2_commit_segment_batched(WarpPrim &prim, FastShared *sh, ScanSt
 		classify();
 		dbg[12] += clock64() - cs0;
 		const long long cv0 = clock64();
-		// ---- ordered validation: cmask bit j = this lane read a slot that lane j (< lane) writes
+		// ---- ordered validation: cmask bit j = this lane read a slot that lane j (< lane) writes.
+		// Only the lanes up to the first stopper can commit in this round, so only they are checked: their
+		// writes are gathered (in lane order) into a shared list that every reader lane scans once.
 		unsigned cmask = 0;
+		{
+			const unsigned stop0 = __ballot_sync(FULL, lane < nb && stopper);
+			const int nv = stop0 ? __ffs(stop0) : nb;
+			const int myn = lane < nv ? nwt : 0;
+			int incl = myn;
+#pragma unroll
+			for (int d = 1; d < 32; d <<= 1) {
+				const int o = __shfl_up_sync(FULL, incl, d);
+				if (lane >= d)
+					incl += o;
+			}
+			const int total = __shfl_sync(FULL, incl, 31);
+			for (int w = 0; w < myn; w++) {
+				sh->vslot[incl - myn + w] = L.wslot[w];
+				sh->vown[incl - myn + w] = (unsigned char)lane;
+			}
+			__syncwarp();
+			const int mynr = lane < nv ? L.nr : 0;
+			const unsigned rlo0 = L.rlo[0], rlen0 = L.rlen[0];
+			for (int i = 0; i < total; i++) {
+				const unsigned sl = sh->vslot[i];
+				const int ow = sh->vown[i];
+				if (ow < lane && mynr > 0) {
+					bool hit = ((sl - rlo0) & hmask) < rlen0;
+					for (int q = 1; q < mynr; q++)
+						hit = hit || ((sl - L.rlo[q]) & hmask) < L.rlen[q];
+					if (hit)
+						cmask |= 1u << ow;
+				}
+			}
+			__syncwarp();
+		}
+		// the same check against ONE writer lane (after that lane has been re-evaluated)
 		auto check_against = [&](int j) {
 			const int nwj = __shfl_sync(FULL, nwt, j);
 #pragma unroll
@@ -1222,30 +1315,12 @@ __device__ void k2_commit_segment_batched(WarpPrim &prim, FastShared *sh, ScanSt
 				if (w >= nwj)
 					break;
 				const unsigned sl = __shfl_sync(FULL, L.wslot[w], j);
-#ifdef K2_CONFSTAT
-				const int jnw = __shfl_sync(FULL, L.nw, j);
-#endif
-				if (lane > j) {
+				if (lane > j)
 					for (int q = 0; q < L.nr; q++) // almost always one range (two with a displacement)
-						if (((sl - L.rlo[q]) & hmask) < L.rlen[q]) {
+						if (((sl - L.rlo[q]) & hmask) < L.rlen[q])
 							cmask |= 1u << j;
-#ifdef K2_CONFSTAT
-							// writer kind: 0 insert target, 1 re-home target, 2 sweep deletion; reader: range q, place in range
-							const int wk = (w >= jnw) ? 2 : (w == 0 ? 0 : 1);
-							const unsigned place = (sl - L.rlo[q]) & hmask;
-							const int pk = (place == L.rlen[q] - 1) ? 0 : ((L.nw > 0 && sl == L.wslot[0]) ? 1 : 2); // end-empty, my target, interior
-							atomicAdd((unsigned long long *)&st->dbg[wk * 3 + pk], 1ull);
-							if (q > 0)
-								atomicAdd((unsigned long long *)&st->dbg[9], 1ull);
-							if (lane == j + 1)
-								atomicAdd((unsigned long long *)&st->dbg[10], 1ull);
-#endif
-						}
-				}
 			}
 		};
-		for (int j = 0; j + 1 < nb; j++)
-			check_against(j);
 		dbg[13] += clock64() - cv0;
 		const long long cc0 = clock64();
 
@@ -1359,13 +1434,8 @@ __device__ void k2_commit_segment_batched(WarpPrim &prim, FastShared *sh, ScanSt
 		k2_close_chunk(prim, st, r, c, recs, status);
 	if (lane == 0 && status != -9) {
 		dbg[10] = clock64() - clk_start;
-#ifndef K2_CONFSTAT
 		for (int i = 0; i < 16; i++)
 			st->dbg[i] += dbg[i];
-#else
-		st->dbg[11] += dbg[5];
-		st->dbg[12] += dbg[1];
-#endif
 		st->st_displacements += n_disp;
 		k2_store_regs(st, r, n, status);
 	}
