@@ -397,7 +397,7 @@ def main():
             "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu_baseline,
             "ratio": total / out_len if out_len else None, "archive_bytes": int(out_len),
             "stage_ms": {k: stats[k] for k in ("ms_h2d", "ms_rzip", "ms_emit", "ms_backend", "ms_d2h", "ms_md5", "ms_total")},
-            "rzip": {k: stats[k] for k in ("matches", "match_bytes", "literals", "literal_bytes", "inserts", "lookups")},
+            "rzip": {k: stats[k] for k in ("matches", "match_bytes", "literals", "literal_bytes", "inserts", "lookups", "chain_evictions", "sweeps")},
             "block_size": int(sz.bufsize), "blocks": int(stats["blocks"]), "blocks_stored": int(stats["blocks_stored"]),
         }))
     ctx.close()

@@ -77,7 +77,6 @@ struct LzmaJob {
 	uint32_t n;
 	uint8_t *out;
 	uint64_t outCap;
-	lzma::Enc *enc;
 	const uint64_t *rec;  // match lists of the data-parallel finder (lzma_mf.cu)
 	const uint32_t *pool;
 	lzma::Config cfg;
@@ -253,7 +252,7 @@ static int run_lzma(BackendCtx *b, const lrzgpu_params &p, const lrzgpu_sizing_t
 	const size_t budget = free_b + b->work.cap > (2ull << 30) ? free_b + b->work.cap - (1ull << 30) : free_b + b->work.cap;
 
 	struct Lay {
-		size_t enc, son, c2, c3, sorted, ctl, rec, pool, end;
+		size_t son, c2, c3, sorted, ctl, rec, pool, end;
 		uint64_t poolCap;
 	};
 	size_t at = 0;
@@ -266,8 +265,6 @@ static int run_lzma(BackendCtx *b, const lrzgpu_params &p, const lrzgpu_sizing_t
 			const size_t n = (size_t)jobs[idx[at]].u_len, count = n >= 4 ? n - 3 : 0;
 			Lay L;
 			size_t o = wsum;
-			L.enc = o;
-			o += align_up(sizeof(lzma::Enc), 256);
 			L.son = o;
 			o += align_up(8 * (n + 2), 256);
 			L.c2 = o;
@@ -327,7 +324,6 @@ static int run_lzma(BackendCtx *b, const lrzgpu_params &p, const lrzgpu_sizing_t
 			j.n = (uint32_t)bj.u_len;
 			j.out = (uint8_t *)b->out.p + oofs[first + i];
 			j.outCap = (uint64_t)round_up_page((int64_t)((double)bj.u_len * 1.02), p.page_size);
-			j.enc = (lzma::Enc *)(W + L.enc);
 			j.rec = B.rec;
 			j.pool = B.pool;
 			j.cfg = c;

@@ -1,5 +1,5 @@
 // k2_commit.cu -- warp-cooperative primitives for the serial commit stage (see k2_commit.cuh) and
-// the kernel that runs them: ONE warp owns a chunk's hash table (64 MiB at rzip level 7, resident in
+// the kernel that runs them: ONE CTA owns a chunk's hash table (64 MiB at rzip level 7, resident in
 // the 126 MB L2) and replays the candidates K1 produced, in position order.
 //
 // Data-parallel pieces, each one L2/L1 round trip wide instead of one per slot / per byte:
@@ -11,12 +11,11 @@
 //   * candidate fetch: 32 {pos,tag} records per load, mask filter by ballot
 //
 // The commit warp is latency bound: every candidate costs a chain of dependent loads (probe window,
-// then the bytes at the matching offsets).  Seven helper warps of the same CTA therefore run a bounded
-// distance AHEAD of it over the same candidate list and do read-only "dry" lookups, one candidate per
-// lane: they walk the probe chain and touch the window bytes of equal-tag entries, which pulls those
-// lines into the SM's L1 (shared by all warps of the CTA).  Helpers never write and never decide
-// anything, so exactness rests on the commit warp alone; they only turn its HBM/L2 round trips into
-// L1 hits.  Progress is exchanged through two volatile shared-memory words.
+// then the bytes at the matching offsets).  Candidates are therefore evaluated in batches of up to 32 by
+// ALL 8 warps of the CTA (group_eval_t: 8 lanes per candidate, several probe windows in flight), against
+// the table as it stands; the commit warp validates in order that no candidate read a slot an earlier one
+// of the batch writes, commits the conflict-free prefix and re-evaluates / serialises the rest, so
+// exactness rests on the serial step (k2_commit.cuh) and on the ordered validation alone.
 #include "k2_commit.cuh"
 #include "kernels.h"
 
@@ -371,9 +370,7 @@ struct WarpPrim {
 	}
 };
 
-static constexpr int K2_HELPERS = 7;
-static constexpr int K2_THREADS = 32 * (1 + K2_HELPERS);
-static constexpr int K2_LOOKAHEAD = 64;  // candidates the helpers may run ahead of the commit warp
+static constexpr int K2_THREADS = 256;   // commit warp + 7 evaluator warps
 static constexpr int K2_MAXW = 4;        // insert writes one lane may carry (displacement depth 3)
 static constexpr unsigned K2_MAXWALK = 2048; // slots one candidate may walk before it is handed to the serial step
 
@@ -405,74 +402,6 @@ struct FastShared {
 static constexpr int K2_BAR_GO = 1, K2_BAR_DONE = 2;
 __device__ __forceinline__ void k2_bar(int id) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(256) : "memory"); }
 
-__device__ __forceinline__ void touch_line(const void *p)
-{
-	unsigned v;
-	asm volatile("ld.global.ca.u32 %0, [%1];" : "=r"(v) : "l"((uintptr_t)p & ~(uintptr_t)3) : "memory");
-	asm volatile("" ::"r"(v));
-}
-
-// Helper warp `hw` (0-based): dry lookups for batches b of every tile with (tile + b) % K2_HELPERS == hw.
-__device__ void k2_helper(Progress *prog, const uint8_t *__restrict__ buf, const HEntry *tab, int64_t hmask,
-			  const Cand *__restrict__ cand, const uint32_t *__restrict__ tile_count, int64_t first_tile,
-			  int64_t num_tiles, int64_t n, int hw, int lane)
-{
-	for (int64_t t = 0; t < num_tiles; t++) {
-		if (prog->done)
-			return;
-		if ((first_tile + t + 1) * (int64_t)kTile <= prog->pos)
-			continue; // the scan is already past this tile
-		const uint32_t cnt = tile_count[t];
-		for (uint32_t b = (uint32_t)((hw + K2_HELPERS - (t % K2_HELPERS)) % K2_HELPERS); b * 32 < cnt; b += K2_HELPERS) {
-			const uint32_t i = b * 32 + lane;
-			int64_t pos = 0, tag = 0;
-			const bool v = i < cnt;
-			if (v) {
-				const longlong2 c = *reinterpret_cast<const longlong2 *>(cand + t * (int64_t)kTile + i);
-				pos = c.x;
-				tag = c.y;
-			}
-			const int64_t first_pos = __shfl_sync(FULL, pos, 0);
-			// stay within K2_LOOKAHEAD candidates (at the current density) of the commit warp
-			for (;;) {
-				if (prog->done)
-					return;
-				const int64_t ahead = (int64_t)K2_LOOKAHEAD << __popcll(prog->min_mask);
-				if (first_pos <= prog->pos + ahead)
-					break;
-				__nanosleep(2000);
-			}
-			const int64_t mm = prog->min_mask, mp = prog->pos;
-			if (v && pos > mp && (tag & mm) == mm) {
-				touch_line(buf + pos);
-				int64_t h = tag & hmask;
-				for (int step = 0; step < 8; step++) { // 4 slots per step, up to 32 slots
-					HEntry e[4];
-#pragma unroll
-					for (int k = 0; k < 4; k++)
-						e[k] = ld_entry(tab + ((h + k) & hmask));
-					bool stop = false;
-#pragma unroll
-					for (int k = 0; k < 4; k++) {
-						if (stop)
-							break;
-						if (!(e[k].offset | e[k].tag)) {
-							stop = true;
-							break;
-						}
-						if (e[k].tag == tag && e[k].offset < pos && e[k].offset >= 0 && e[k].offset < n)
-							touch_line(buf + e[k].offset);
-					}
-					if (stop)
-						break;
-					h += 4;
-				}
-			}
-			__syncwarp();
-		}
-	}
-}
-
 // ---- batched commit ---------------------------------------------------------------------------------
 // The reference's loop is serial, but consecutive candidates almost never interact: a candidate reads
 // its probe chain [home, first empty slot] and writes one or a few slots.  The commit warp therefore
@@ -486,6 +415,10 @@ __device__ void k2_helper(Progress *prog, const uint8_t *__restrict__ buf, const
 // handed to the serial k2_step(), which is also used while a match is pending.  The batch therefore
 // never decides anything the serial code would decide differently.
 
+__device__ __forceinline__ void prefetch_l1(const void *p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+
+#ifdef K2_CROSSCHECK
+// Development aid: the original one-lane evaluator, kept as an in-kernel cross-check of group_eval_t.
 // Could the equal-tag entry at `op` give a match of >= 31 bytes at p0?  (single_match_len, bounded.)
 __device__ __forceinline__ bool could_match(const uint8_t *__restrict__ buf, int64_t p0, int64_t op, int64_t end,
 					    int64_t last_match)
@@ -504,8 +437,6 @@ __device__ __forceinline__ bool could_match(const uint8_t *__restrict__ buf, int
 		rev++;
 	return rev >= need;
 }
-
-__device__ __forceinline__ void prefetch_l1(const void *p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 
 static constexpr int K2_WIDE = 8; // slots fetched per step of a lane's private probe walk (independent loads)
 
@@ -663,7 +594,7 @@ __device__ void lane_eval(const uint8_t *__restrict__ buf, const HEntry *tab, un
 		L.nr++;
 	}
 }
-
+#endif // K2_CROSSCHECK
 
 // ---- cooperative evaluation -------------------------------------------------------------------------
 // lane_eval above walks a candidate's probe chain with ONE lane: a long serial instruction stream, and the
@@ -783,6 +714,16 @@ __device__ void group_eval_t(const uint8_t *__restrict__ buf, const HEntry *tab,
 			const bool eq = !emp && e.tag == t;
 			if (eq && !done && e.offset > 0 && e.offset < p)
 				prefetch_l1(buf + e.offset);
+			// a window with nothing to act on (no empty slot, no equal tag, no insert target still wanted)
+			// only moves the cursor: the common case inside a long chain
+			if (!__any_sync(FULL, !done && (emp || eq || (!stop && (due || les))))) {
+				if (!done) {
+					s += G;
+					if (s >= K2_MAXWALK)
+						cx = done = true;
+				}
+				continue;
+			}
 			const unsigned em = (__ballot_sync(FULL, emp) >> gshift) & GM;
 			const unsigned dm = (__ballot_sync(FULL, due) >> gshift) & GM;
 			const unsigned lm = (__ballot_sync(FULL, les) >> gshift) & GM;
@@ -908,6 +849,17 @@ __device__ void group_eval_t(const uint8_t *__restrict__ buf, const HEntry *tab,
 				const bool due = !emp && (e.tag & better) != better;
 				const bool les = !emp && !due && tz_ones(e.tag) < ones2;
 				const bool eq = !emp && e.tag == wt;
+				if (!__any_sync(FULL, !wdone && (emp || due || les || eq))) {
+					if (!wdone) {
+						s2 += G;
+						if (s2 >= K2_MAXWALK) {
+							cx = true;
+							wdone = true;
+							chain = false;
+						}
+					}
+					continue;
+				}
 				const unsigned em = (__ballot_sync(FULL, emp) >> gshift) & GM;
 				const unsigned dm = (__ballot_sync(FULL, due) >> gshift) & GM;
 				const unsigned lm = (__ballot_sync(FULL, les) >> gshift) & GM;
@@ -957,21 +909,21 @@ __device__ void group_eval_t(const uint8_t *__restrict__ buf, const HEntry *tab,
 	__syncwarp();
 }
 
-// This warp's share of a batch of nb candidates (warp 0..7), in the given mode.
+// This warp's share of a batch of nb candidates (warp 0..7): four candidates at once, 8 lanes each, so that
+// their table walks and their far-byte compares overlap; tighter gates get more windows in flight per step.
 __device__ void k2_eval_share(const uint8_t *__restrict__ buf, const HEntry *tab, unsigned hmask, FastShared *sh, int nb, int mode,
 			      int64_t tag_mask, int64_t better, int max_chain, int64_t end, int64_t last_match, int lane, int warp)
 {
-	if (mode == K2_MODE_NARROW) {
-		const int ci = warp * 4 + (lane >> 3);
-		if (warp * 4 < nb)
-			group_eval_t<8, 1>(buf, tab, hmask, sh, ci < nb ? ci : -1, tag_mask, better, max_chain, end, last_match, lane, warp);
-	} else if (mode == K2_MODE_WIDE2) {
-		for (int ci = warp; ci < nb; ci += 8)
-			group_eval_t<32, 2>(buf, tab, hmask, sh, ci, tag_mask, better, max_chain, end, last_match, lane, warp);
-	} else {
-		for (int ci = warp; ci < nb; ci += 8)
-			group_eval_t<32, 8>(buf, tab, hmask, sh, ci, tag_mask, better, max_chain, end, last_match, lane, warp);
-	}
+	const int ci = warp * 4 + (lane >> 3);
+	if (warp * 4 >= nb)
+		return;
+	const int c = ci < nb ? ci : -1;
+	if (mode == K2_MODE_NARROW)
+		group_eval_t<8, 1>(buf, tab, hmask, sh, c, tag_mask, better, max_chain, end, last_match, lane, warp);
+	else if (mode == K2_MODE_WIDE2)
+		group_eval_t<8, 4>(buf, tab, hmask, sh, c, tag_mask, better, max_chain, end, last_match, lane, warp);
+	else
+		group_eval_t<8, 8>(buf, tab, hmask, sh, c, tag_mask, better, max_chain, end, last_match, lane, warp);
 }
 
 // One candidate, by the calling warp alone (re-evaluation on the updated table).
