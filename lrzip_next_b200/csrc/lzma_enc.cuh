@@ -1350,8 +1350,18 @@ LZ_FN inline void enc_init(Enc *e, const Config &c, const uint8_t *src, uint32_t
 	for (uint32_t i = 0; i < kLenHigh; i++)
 		e->lenProbs.high[i] = e->repLenProbs.high[i] = kProbInit;
 	e->optEnd = e->optCur = 0;
-	LZ_PFOR(i, kNumOpts)
-		e->opt[i].price = kInfinity;
+	// The parse table starts zeroed, like the fresh pages the reference's encoder object is allocated from
+	// (defensive: shared memory starts with whatever the previous kernel left there).
+	LZ_PFOR(i, kNumOpts) {
+		Opt *o = &e->opt[i];
+		o->price = kInfinity;
+		o->state = 0;
+		o->extra = 0;
+		o->len = 0;
+		o->dist = 0;
+		for (uint32_t k = 0; k < kNumReps; k++)
+			o->reps[k] = 0;
+	}
 	lz_sync();
 	e->additionalOffset = 0;
 	e->longestMatchLen = e->numPairs = e->numAvail = e->backRes = 0;

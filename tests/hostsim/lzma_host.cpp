@@ -21,6 +21,11 @@ extern "C" int hostsim_lzma_encode(const uint8_t *src, int64_t n, int level, uin
 	uint32_t *h4 = (uint32_t *)calloc(c.hash4Entries, 4), *son = (uint32_t *)malloc(c.sonEntries * 4);
 	if (!e || !h2 || !h3 || !h4 || !son)
 		return -2;
+	memset(e, 0xA5, sizeof(Enc)); // the device keeps this state in shared memory, which starts with stale contents
+	for (uint32_t i = 0; i < kNumOpts; i++) { // ... e.g. cells a previous block left behind as "rep0, length 5"
+		e->opt[i].len = 5;
+		e->opt[i].dist = 0;
+	}
 	enc_init(e, c, src, (uint32_t)n, out, (uint64_t)cap, h2, h3, h4, son);
 	const uint64_t len = enc_run(e);
 	const int ovf = e->overflow;
@@ -91,6 +96,7 @@ extern "C" int hostsim_lzma_encode_pre(const uint8_t *src, int64_t n, int level,
 	Enc *e = (Enc *)malloc(sizeof(Enc));
 	if (!e)
 		return -2;
+	memset(e, 0xA5, sizeof(Enc));
 	enc_init(e, c, src, (uint32_t)n, out, (uint64_t)cap, nullptr, nullptr, nullptr, nullptr);
 	e->preRec = rec.data();
 	e->prePool = pool.data();
