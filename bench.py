@@ -173,6 +173,16 @@ def main():
                          "compare archive SHA-256 (minutes of CPU time; outside every timed region)")
     a = ap.parse_args()
 
+    # The contract is ONE JSON line on stdout.  Native libraries write there too (NCCL prints its version
+    # banner at the first communicator), so everything else is sent to stderr and only emit() uses stdout.
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(obj):
+        sys.stdout.flush()
+        os.write(real_stdout, (json.dumps(obj) + "\n").encode())
+
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -203,19 +213,19 @@ def main():
         for i in range(a.warmup + a.steps):
             dt, osz = run_reference(data, flags)
             if dt is None:
-                print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/lrzip-next was not built"}))
+                emit({"impl": "reference", "unavailable": "oracle/_ref/lrzip-next was not built"})
                 return
             if i >= a.warmup:
                 times.append(dt)
         v = sample / (sum(times) / len(times)) / MB
-        print(json.dumps({
+        emit({
             "impl": "reference", "metric": "compress MB/s (input bytes)", "value": v, "unit": "MB/s", "n_gpus": a.gpus,
             "steps": a.steps, "warmup": a.warmup, "ms_per_step": 1e3 * sum(times) / len(times), "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic", "config": config,
             "cpu_baseline": {"value": v, "unit": "MB/s", "cores": min(threads, cores), "kind": "reference",
                              "sample": f"first {sample >> 20} MiB of the workload, lrzip-next {' '.join(flags)}"},
             "e2e": {"value": v, "unit": "MB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-            "ratio": sample / osz if osz else None}))
+            "ratio": sample / osz if osz else None})
         return
 
     import torch
@@ -306,7 +316,12 @@ def main():
     out_len = last["out_len"]
     stats = last["stats"]
 
-    e2e_ms, _ = timed(step_e2e, a.steps)
+    if world == 1:
+        e2e_ms, _ = timed(step_e2e, a.steps)
+    else:
+        # at N > 1 the timed step above already IS the host-buffer path: every rank's window goes through
+        # lrzgpu_compress_chunk from pinned host memory and the blobs come back to the host on rank 0
+        e2e_ms = ms
     e2e_value = total * a.steps / (e2e_ms / 1e3) / MB
     e2e_out = last["out_len"]
 
@@ -387,7 +402,7 @@ def main():
             os.rmdir(d)
 
     if rank == 0:
-        print(json.dumps({
+        emit({
             "verified": verified,
             "metric": "compress MB/s (input bytes)", "value": value, "unit": "MB/s", "n_gpus": world, "steps": a.steps,
             "warmup": a.warmup, "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak",
@@ -399,7 +414,7 @@ def main():
             "stage_ms": {k: stats[k] for k in ("ms_h2d", "ms_rzip", "ms_emit", "ms_backend", "ms_d2h", "ms_md5", "ms_total")},
             "rzip": {k: stats[k] for k in ("matches", "match_bytes", "literals", "literal_bytes", "inserts", "lookups", "chain_evictions", "sweeps")},
             "block_size": int(sz.bufsize), "blocks": int(stats["blocks"]), "blocks_stored": int(stats["blocks_stored"]),
-        }))
+        })
     ctx.close()
     if world > 1:
         dist.destroy_process_group()
