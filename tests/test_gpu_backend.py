@@ -1,6 +1,7 @@
 """GPU parity tests for the block backends through the C ABI: lz4 gate, LZMA block encoder, zstd frames,
 and whole archives against the unmodified reference binary (oracle/_ref, built from /root/reference by
 oracle/Makefile and shipped to the GPU box)."""
+import os
 import time
 
 import numpy as np
@@ -58,6 +59,10 @@ def test_lzma_block_bit_exact(ctx, level, dict_size):
 ])
 def test_lzma_archive_bit_identical_to_reference(ctx, kind, n, kw):
     d = datagen.generate(kind, n)
+    # the reference binary sizes threads / dictionary from the core count of the machine it runs on
+    # (PROCESSORS in open_stream_out, src/stream.c:1180): -p8 -m100 gives dict 32 MiB on a 16-core box and
+    # 24 MiB from 20 cores up, so both sides must be told the cores of THIS box
+    kw = dict(kw, processors=os.cpu_count() or 8)
     p = make_params(backend=BACKEND_LZMA, **kw)
     op = oracle.make_params(backend=oracle.BACKEND_LZMA, **kw)
     want = oracle.ref_compress(d, op)
