@@ -85,7 +85,7 @@ def test_lzma_bucketwise_match_finder_equals_serial(hostsim):
              datagen.gen_vm(1 << 20).tobytes(), datagen.gen_rep(1 << 20, block=1 << 14).tobytes(), b"ab" * 40, b"abc",
              rng.integers(0, 4, 200_000, dtype=np.uint8).tobytes(), datagen.gen_trees(700_000).tobytes()]
     for d in cases:
-        for level, dic in ((7, 1 << 25), (5, 1 << 24), (7, 1 << 16), (9, 1 << 12)):
+        for level, dic in ((7, 1 << 25), (5, 1 << 24), (7, 1 << 16), (9, 1 << 12), (7, 3 << 23)):
             got, words = _lzma_pre(hostsim[1], d, level, dic)
             assert got == _lzma(hostsim[1], d, level, dic), (len(d), level, dic)
             assert words <= (2 * 61 + 4) * len(d)
@@ -108,7 +108,8 @@ def test_lzma_encoder_matches_reference_lzmacompress(hostsim):
              datagen.gen_vm(1 << 20).tobytes(), datagen.gen_rep(1 << 20, block=1 << 14).tobytes(), b"ab" * 40,
              rng.integers(0, 4, 200_000, dtype=np.uint8).tobytes()]
     for d in cases:
-        for level, dic in ((7, 1 << 25), (5, 1 << 24), (9, 1 << 27), (7, 1 << 16)):
+        # 3 << 23: the 24 MiB dictionary open_stream_out falls back to on boxes with >= 20 cores at -p8 -m100
+        for level, dic in ((7, 1 << 25), (5, 1 << 24), (9, 1 << 27), (7, 1 << 16), (7, 3 << 23)):
             assert _lzma(hostsim[1], d, level, dic) == oracle.ref_lzma_block(d, level, dic, 2)
 
 
