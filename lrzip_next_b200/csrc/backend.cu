@@ -238,10 +238,13 @@ static int run_lzma(BackendCtx *b, const lrzgpu_params &p, const lrzgpu_sizing_t
 		}
 		oofs[k] = osum;
 		osum += align_up((size_t)round_up_page((int64_t)((double)bj.u_len * 1.02), p.page_size), 256);
-		const uint32_t count = bj.u_len >= 4 ? (uint32_t)bj.u_len - 3 : 0;
+		const uint32_t minAvail = cfgs[k].fastMode ? 5 : 4;
+		const uint32_t count = bj.u_len >= minAvail ? (uint32_t)bj.u_len - (minAvail - 1) : 0;
 		if (count > maxCount)
 			maxCount = count;
 	}
+	const bool hc5 = cfgs[0].fastMode != 0; // one level per call: all blocks use the same finder
+	const size_t minAvail = hc5 ? 5 : 4;
 	const size_t scratch_bytes = align_up(lzma::mf_sort_scratch_bytes(maxCount), 256);
 	if (b->out.ensure(osum) != cudaSuccess || b->scratch.ensure(scratch_bytes) != cudaSuccess) {
 		snprintf(err, errlen, "out of device memory for LZMA payloads / sort scratch (%zu MiB)", (osum + scratch_bytes) >> 20);
@@ -262,11 +265,11 @@ static int run_lzma(BackendCtx *b, const lrzgpu_params &p, const lrzgpu_sizing_t
 		size_t wsum = 0, first = at;
 		const auto t_wave = std::chrono::steady_clock::now();
 		for (; at < idx.size(); at++) {
-			const size_t n = (size_t)jobs[idx[at]].u_len, count = n >= 4 ? n - 3 : 0;
+			const size_t n = (size_t)jobs[idx[at]].u_len, count = n >= minAvail ? n - (minAvail - 1) : 0;
 			Lay L;
 			size_t o = wsum;
 			L.son = o;
-			o += align_up(8 * (n + 2), 256);
+			o += hc5 ? 256 : align_up(8 * (n + 2), 256); // the hash-chain finder keeps its links in `sorted`
 			L.c2 = o;
 			o += align_up(4 * count + 4, 256);
 			L.c3 = o;
@@ -307,7 +310,8 @@ static int run_lzma(BackendCtx *b, const lrzgpu_params &p, const lrzgpu_sizing_t
 			B.P.bigHash = c.bigHash;
 			B.P.historySize = c.historySize;
 			B.P.cyclicSize = c.cyclicSize;
-			B.count = bj.u_len >= 4 ? (uint32_t)bj.u_len - 3 : 0;
+			B.P.hc5 = c.fastMode;
+			B.count = (size_t)bj.u_len >= minAvail ? (uint32_t)bj.u_len - (uint32_t)(minAvail - 1) : 0;
 			B.son = (uint32_t *)(W + L.son);
 			B.c2 = (uint32_t *)(W + L.c2);
 			B.c3 = (uint32_t *)(W + L.c3);
@@ -342,7 +346,7 @@ static int run_lzma(BackendCtx *b, const lrzgpu_params &p, const lrzgpu_sizing_t
 		    cudaMemcpyAsync(J + o_seg, seg.data(), seg.size() * 8, cudaMemcpyHostToDevice, stream) != cudaSuccess)
 			return LRZGPU_ECUDA;
 		if (lzma::mf_walk_launch((const lzma::MfBlock *)(J + o_mb), (int)lay.size(), (const uint64_t *)(J + o_seg), seg.back(),
-					 stream, launches)) {
+					 hc5, stream, launches)) {
 			snprintf(err, errlen, "LZMA match finder walk: %s", cudaGetErrorString(cudaGetLastError()));
 			return LRZGPU_ECUDA;
 		}

@@ -3,7 +3,8 @@
 //
 // Bit-exactness target: the raw LZMA stream LzmaCompress() writes for (level, dictSize, lc3 lp0 pb2,
 // fb, numThreads = 2), i.e. the vendored 7-Zip SDK 24.07 encoder in "optimal" mode (levels 5-9)
-// over its two-thread match finder.  What is restated here, piece by piece:
+// over its two-thread match finder, and in "fast" mode (levels 1-4: GetOptimumFast, LzmaEnc.c:1970-2098,
+// over the single-threaded hc5 hash-chain finder, lzma_mf.cuh).  What is restated here, piece by piece:
 //
 //   match finder    binary tree over 4-byte hashes with cut value mc        LzFind.c:962-1029
 //                   driven per position like the BT thread does             LzFindMt.c:571-729
@@ -124,7 +125,7 @@ struct Enc {
 	const uint8_t *src;
 	uint32_t n;
 	uint32_t fb, mc, historySize, cyclicSize, hashMask, bigHash, distTableSize;
-	uint32_t pbMask, lpMask, lc;
+	uint32_t pbMask, lpMask, lc, fastMode;
 	// ---- match finder (positions are 1-based: byte i has pos i + 1; 0 = empty)
 	uint32_t *hash2, *hash3, *hash4, *son;
 	// precomputed match lists (lzma_mf.cu): when preRec is set the serial finder above is not used
@@ -1222,11 +1223,112 @@ LZ_FN inline uint32_t get_optimum(Enc *e, uint32_t position)
 	return backward(e, cur);
 }
 
+// GetOptimumFast (LzmaEnc.c:1970-2098): levels 1-4.  No price tables; greedy with one position of look-ahead.
+LZ_INL bool change_pair(uint32_t smallDist, uint32_t bigDist) { return (bigDist >> 7) > smallDist; }
+
+LZ_FN inline uint32_t get_optimum_fast(Enc *e)
+{
+	uint32_t numAvail, mainDist, mainLen, numPairs, repIndex, repLen;
+	uint32_t *matches = e->matches;
+	if (e->additionalOffset == 0)
+		mainLen = read_matches(e, &numPairs);
+	else {
+		mainLen = e->longestMatchLen;
+		numPairs = e->numPairs;
+	}
+	numAvail = e->numAvail;
+	e->backRes = kMarkLit;
+	if (numAvail < 2)
+		return 1;
+	if (numAvail > kMatchMax)
+		numAvail = kMatchMax;
+	const uint8_t *data = mf_cur(e) - 1;
+	repLen = repIndex = 0;
+	lz_sync();
+	LZ_PFOR(q, kNumReps) { // the four first-two-bytes checks at once
+		const uint8_t *data2 = data - e->reps[q];
+		e->xRepLen[q] = (data[0] == data2[0] && data[1] == data2[1]) ? 2 : 0;
+	}
+	lz_sync();
+	for (uint32_t i = 0; i < kNumReps; i++) {
+		if (e->xRepLen[i] == 0)
+			continue;
+		const uint32_t len = lz_extend(data - e->reps[i], data, 2, numAvail);
+		if (len >= e->fb) {
+			e->backRes = i;
+			move_pos(e, len - 1);
+			return len;
+		}
+		if (len > repLen) {
+			repIndex = i;
+			repLen = len;
+		}
+	}
+	if (mainLen >= e->fb) {
+		e->backRes = matches[numPairs - 1] + kNumReps;
+		move_pos(e, mainLen - 1);
+		return mainLen;
+	}
+	mainDist = 0;
+	if (mainLen >= 2) {
+		mainDist = matches[numPairs - 1];
+		while (numPairs > 2) {
+			if (mainLen != matches[numPairs - 4] + 1)
+				break;
+			const uint32_t dist2 = matches[numPairs - 3];
+			if (!change_pair(dist2, mainDist))
+				break;
+			numPairs -= 2;
+			mainLen--;
+			mainDist = dist2;
+		}
+		if (mainLen == 2 && mainDist >= 0x80)
+			mainLen = 1;
+	}
+	if (repLen >= 2)
+		if (repLen + 1 >= mainLen || (repLen + 2 >= mainLen && mainDist >= (1u << 9)) ||
+		    (repLen + 3 >= mainLen && mainDist >= (1u << 15))) {
+			e->backRes = repIndex;
+			move_pos(e, repLen - 1);
+			return repLen;
+		}
+	if (mainLen < 2 || numAvail <= 2)
+		return 1;
+	{
+		const uint32_t len1 = read_matches(e, &e->numPairs);
+		e->longestMatchLen = len1;
+		if (len1 >= 2) {
+			const uint32_t newDist = matches[e->numPairs - 1];
+			if ((len1 >= mainLen && newDist < mainDist) || (len1 == mainLen + 1 && !change_pair(mainDist, newDist)) ||
+			    (len1 > mainLen + 1) || (len1 + 1 >= mainLen && mainLen >= 3 && change_pair(newDist, mainDist)))
+				return 1;
+		}
+	}
+	data = mf_cur(e) - 1;
+	for (uint32_t i = 0; i < kNumReps; i++) {
+		const uint8_t *data2 = data - e->reps[i];
+		if (data[0] != data2[0] || data[1] != data2[1])
+			continue;
+		const uint32_t limit = mainLen - 1;
+		for (uint32_t len = 2;; len++) {
+			if (len >= limit)
+				return 1;
+			if (data[len] != data2[len])
+				break;
+		}
+	}
+	e->backRes = mainDist + kNumReps;
+	if (mainLen != 2)
+		move_pos(e, mainLen - 2);
+	return mainLen;
+}
+
 // ---------------------------------------------------------------------------------------------------
 // block driver
 struct Config {
 	uint32_t dictSize, fb, mc, lc, lp, pb;
 	uint32_t historySize, cyclicSize, hashMask, bigHash, distTableSize;
+	uint32_t fastMode; // levels 1-4: GetOptimumFast over the hc5 finder (LzmaEncProps_Normalize, LzmaEnc.c:68-108)
 	uint64_t sonEntries, hash4Entries; // allocation sizes (uint32 counts)
 };
 
@@ -1250,15 +1352,16 @@ inline uint32_t hash_mask_for(uint32_t hs)
 // lzma_compress_buf passes (src/stream.c:450-456): level, dictSize, lc3 lp0 pb2, fb, numThreads 2.
 inline bool make_config(int level, uint32_t dictSize, uint32_t fb, uint64_t srcLen, Config &c)
 {
-	if (level < 5 || srcLen == 0 || srcLen >= 0xFFFF0000ull)
-		return false; // fast mode (levels 1-4, hc5) is not built yet
+	if (level < 1 || level > 9 || srcLen == 0 || srcLen >= 0xFFFF0000ull)
+		return false;
 	if (fb < 5)
 		fb = 5;
 	if (fb > kMatchMax)
 		fb = kMatchMax;
+	c.fastMode = level < 5 ? 1 : 0; // algo 0: hc5, single-threaded finder, mc halved
 	c.dictSize = dictSize;
 	c.fb = fb;
-	c.mc = 16 + (fb >> 1);
+	c.mc = (16 + (fb >> 1)) >> (c.fastMode ? 1 : 0);
 	c.lc = 3;
 	c.lp = 0;
 	c.pb = 2;
@@ -1267,15 +1370,17 @@ inline bool make_config(int level, uint32_t dictSize, uint32_t fb, uint64_t srcL
 		hist -= 1;
 	c.historySize = hist;
 	c.cyclicSize = hist + 1;
-	const uint32_t hs = hash_mask_for(hist);
+	// numHashBytes 5 (hc5): the mask also covers the 18 bits the fifth byte's CRC is shifted into (LzFind.c:340-343)
+	const uint32_t extra = c.fastMode ? ((256u << 10) - 1) : 0;
+	const uint32_t hs = hash_mask_for(hist) | extra;
 	uint32_t cur = hs;
 	if (srcLen < hist) {
-		cur = hash_mask_for((uint32_t)srcLen);
+		cur = hash_mask_for((uint32_t)srcLen) | extra;
 		if (cur > hs)
 			cur = hs;
 	}
 	c.hashMask = cur;
-	c.bigHash = cur >= 0xFFFFFFu ? 1 : 0; // LzmaEnc.c:2752 (two-thread match finder)
+	c.bigHash = (!c.fastMode && cur >= 0xFFFFFFu) ? 1 : 0; // LzmaEnc.c:2752 (two-thread match finder)
 	uint32_t i;
 	for (i = kEndPosModel / 2; i < 32; i++)
 		if (dictSize <= (1u << i))
@@ -1301,6 +1406,7 @@ LZ_FN inline void enc_init(Enc *e, const Config &c, const uint8_t *src, uint32_t
 	e->hashMask = c.hashMask;
 	e->bigHash = c.bigHash;
 	e->distTableSize = c.distTableSize;
+	e->fastMode = c.fastMode;
 	e->lc = c.lc;
 	e->pbMask = (1u << c.pb) - 1;
 	e->lpMask = (0x100u << c.lp) - (0x100u >> c.lc);
@@ -1366,8 +1472,11 @@ LZ_FN inline void enc_init(Enc *e, const Config &c, const uint8_t *src, uint32_t
 	e->additionalOffset = 0;
 	e->longestMatchLen = e->numPairs = e->numAvail = e->backRes = 0;
 	init_prob_prices(e->probPrices);
-	fill_distance_prices(e);
-	fill_align_prices(e);
+	e->matchPriceCount = 0;
+	if (!e->fastMode) { // LzmaEnc_InitPrices (LzmaEnc.c:2833-2850)
+		fill_distance_prices(e);
+		fill_align_prices(e);
+	}
 	e->lenPrices.tableSize = e->repLenPrices.tableSize = c.fb + 1 - kMatchMin;
 	e->repLenCounter = kRepLenCount;
 	len_update_prices(e, &e->lenPrices, 1u << c.pb, &e->lenProbs);
@@ -1398,7 +1507,9 @@ LZ_FN inline uint64_t enc_run(Enc *e)
 			uint32_t len;
 			{
 				const uint32_t oci = e->optCur;
-				if (e->optEnd == oci)
+				if (e->fastMode)
+					len = get_optimum_fast(e);
+				else if (e->optEnd == oci)
 					len = get_optimum(e, nowPos);
 				else {
 					const Opt *o = &e->opt[oci];
@@ -1489,12 +1600,12 @@ LZ_FN inline uint64_t enc_run(Enc *e)
 			nowPos += len;
 			e->additionalOffset -= len;
 			if (e->additionalOffset == 0) {
-				if (e->matchPriceCount >= 64) {
+				if (!e->fastMode && e->matchPriceCount >= 64) {
 					fill_align_prices(e);
 					fill_distance_prices(e);
 					len_update_prices(e, &e->lenPrices, e->pbMask + 1, &e->lenProbs);
 				}
-				if (e->repLenCounter <= 0) {
+				if (!e->fastMode && e->repLenCounter <= 0) {
 					e->repLenCounter = kRepLenCount;
 					len_update_prices(e, &e->repLenPrices, e->pbMask + 1, &e->repLenProbs);
 				}

@@ -28,7 +28,7 @@ constexpr int RS_WARPS = RS_THREADS / 32;
 constexpr int RS_ROUNDS = 16;
 constexpr int RS_TILE = RS_THREADS * RS_ROUNDS; // 4096 keys per CTA; warp w owns keys [512 w, 512 (w+1)) of the tile
 
-enum { KEY_H4 = 0, KEY_H3 = 1, KEY_H2 = 2 };
+enum { KEY_H4 = 0, KEY_H3 = 1, KEY_H2 = 2, KEY_H5 = 3 };
 
 struct KeySrc { // first pass: keys are hashes of the block bytes, values are the positions themselves
 	const uint8_t *src;
@@ -41,6 +41,8 @@ __device__ __forceinline__ uint32_t key_of(const KeySrc &ks, uint32_t i)
 	const uint8_t *cur = ks.src + i;
 	if (ks.kind == KEY_H4)
 		return mf_hash4(c_crc, cur, ks.hashMask, ks.bigHash);
+	if (ks.kind == KEY_H5)
+		return mf_hash5(c_crc, cur, ks.hashMask);
 	if (ks.kind == KEY_H3)
 		return mf_hash3(c_crc, cur);
 	return mf_hash2(c_crc, cur);
@@ -237,6 +239,40 @@ __global__ void __launch_bounds__(128) mf_walk_kernel(const MfBlock *__restrict_
 	}
 }
 
+// Levels 1-4 (hash chains): one thread per position of the wave; nothing is carried between positions.
+// B.sorted holds c5[i] = previous position (1-based) with the same 5-byte hash, i.e. the reference's son[].
+__global__ void __launch_bounds__(128) mf_hc_kernel(const MfBlock *__restrict__ blocks, int nblocks,
+						     const uint64_t *__restrict__ segBase)
+{
+	const uint64_t g = (uint64_t)blockIdx.x * 128u + threadIdx.x;
+	int lo = 0, hi = nblocks;
+	if (g >= segBase[nblocks])
+		return;
+	while (hi - lo > 1) {
+		const int mid = (lo + hi) >> 1;
+		if (segBase[mid] <= g)
+			lo = mid;
+		else
+			hi = mid;
+	}
+	const MfBlock &B = blocks[lo];
+	const uint32_t i = (uint32_t)(g - segBase[lo]);
+	const MfParams P = B.P;
+	uint32_t d[2 * kMfMaxFb + 6];
+	const uint32_t nd = mf_hc5_matches(B.src, P, B.sorted - 1, i + 1, B.c2[i], B.c3[i], d);
+	uint64_t off = 0;
+	if (nd) {
+		off = atomicAdd(B.cursor, (unsigned long long)nd);
+		if (off + nd <= B.poolCap) {
+			uint32_t *w = B.pool + off;
+			for (uint32_t j = 0; j < nd; j++)
+				w[j] = d[j];
+		} else
+			*B.overflow = 1;
+	}
+	B.rec[i] = (off << kMfCountBits) | nd;
+}
+
 bool g_init = false;
 
 } // namespace
@@ -306,6 +342,14 @@ int mf_prepare_block(const MfBlock &B, void *scratch, cudaStream_t st, int64_t *
 	int bits = 0;
 	while (bits < 32 && (B.P.hashMask >> bits))
 		bits++;
+	if (B.P.hc5) { // hash chains: the predecessor in the 5-byte-hash order IS the chain link (son[])
+		if (sort_by(B, KEY_H5, bits, bufs, hist, &K, &V, st, launches))
+			return -1;
+		mf_prev_kernel<<<grid, 256, 0, st>>>(K, V, count, B.sorted);
+		if (launches)
+			*launches += 3;
+		return cudaGetLastError() == cudaSuccess ? 0 : -1;
+	}
 	if (sort_by(B, KEY_H4, bits, bufs, hist, &K, &V, st, launches))
 		return -1;
 	mf_copy_kernel<<<grid, 256, 0, st>>>(V, count, B.sorted);
@@ -314,15 +358,18 @@ int mf_prepare_block(const MfBlock &B, void *scratch, cudaStream_t st, int64_t *
 	return cudaGetLastError() == cudaSuccess ? 0 : -1;
 }
 
-int mf_walk_launch(const MfBlock *d_blocks, int nblocks, const uint64_t *d_segBase, uint64_t total, cudaStream_t st,
-		   int64_t *launches)
+int mf_walk_launch(const MfBlock *d_blocks, int nblocks, const uint64_t *d_segBase, uint64_t total, bool hc5,
+		   cudaStream_t st, int64_t *launches)
 {
 	if (total == 0)
 		return 0;
 	const uint64_t grid = (total + 127) / 128;
 	if (grid > 0x7fffffffull)
 		return -1;
-	mf_walk_kernel<<<(unsigned)grid, 128, 0, st>>>(d_blocks, nblocks, d_segBase);
+	if (hc5)
+		mf_hc_kernel<<<(unsigned)grid, 128, 0, st>>>(d_blocks, nblocks, d_segBase);
+	else
+		mf_walk_kernel<<<(unsigned)grid, 128, 0, st>>>(d_blocks, nblocks, d_segBase);
 	if (launches)
 		*launches += 1;
 	return cudaGetLastError() == cudaSuccess ? 0 : -1;

@@ -44,6 +44,7 @@ struct MfParams {
 	uint32_t fb, mc;      // numFastBytes (lenLimit), cutValue
 	uint32_t hashMask, bigHash;
 	uint32_t historySize, cyclicSize;
+	uint32_t hc5;         // levels 1-4: hash-chain finder over 5-byte hashes (single-threaded in the reference)
 };
 
 MF_INL uint32_t mf_crc_entry(uint32_t i) // g_CrcTable[i] (7zCrc.c), reflected 0xEDB88320
@@ -65,6 +66,12 @@ MF_INL uint32_t mf_hash2(const uint32_t *crc, const uint8_t *cur) { return (crc[
 MF_INL uint32_t mf_hash3(const uint32_t *crc, const uint8_t *cur)
 {
 	return (crc[cur[0]] ^ cur[1] ^ ((uint32_t)cur[2] << 8)) & 0xFFFFu;
+}
+
+// HASH5_CALC (LzFind.c:56-63): kLzHash_CrcShift_1 = 5, kLzHash_CrcShift_2 = 10
+MF_INL uint32_t mf_hash5(const uint32_t *crc, const uint8_t *cur, uint32_t hashMask)
+{
+	return (crc[cur[0]] ^ cur[1] ^ ((uint32_t)cur[2] << 8) ^ (crc[cur[3]] << 5) ^ (crc[cur[4]] << 10)) & hashMask;
 }
 
 // Length of the common prefix of a[len..) and b[len..), capped at limit (a = earlier copy, b = cur).
@@ -154,6 +161,79 @@ MF_FN inline uint32_t mf_mix(const uint8_t *src, const MfParams &P, uint32_t pos
 		for (uint32_t i = 0; i < nbt; i++)
 			d[nd + i] = bt[i];
 	return nd + nbt;
+}
+
+// ---- levels 1-4: Hc5_MatchFinder_GetMatches + Hc_GetMatchesSpec (LzFind.c:1431-1500, 880-960) -------------
+// The hash-chain finder is data-parallel outright: son[p] is just the previous position with the same 5-byte
+// hash, the 2- / 3-byte heads are the previous positions with the same 2- / 3-byte hash, GetMatches and Skip
+// update all of them identically, and a position's list only READS the chain.  link[q] = previous position
+// (1-based, 0 = none) with the same 5-byte hash as position q, for positions with at least 5 bytes available.
+// The reference's cyclic son[] forgets links older than cyclicBufferSize; the delta test below does the same.
+MF_FN inline uint32_t mf_hc5_matches(const uint8_t *src, const MfParams &P, const uint32_t *link, uint32_t pos, uint32_t c2,
+				     uint32_t c3, uint32_t *d)
+{
+	const uint8_t *cur = src + (pos - 1);
+	const uint32_t avail = P.n - (pos - 1);
+	const uint32_t lenLimit = avail < P.fb ? avail : P.fb;
+	const uint32_t mmm = pos < P.cyclicSize ? pos : P.cyclicSize; // SET_mmm
+	uint32_t d2 = pos - c2, d3 = pos - c3; // an empty head (0) gives d == pos, which fails d < mmm
+	uint32_t curMatch = link[pos];
+	uint32_t nd = 0, maxLen = 4;
+	for (;;) {
+		if (d2 < mmm && *(cur - d2) == *cur) {
+			d[nd] = 2;
+			d[nd + 1] = d2 - 1;
+			nd += 2;
+			if (*(cur - d2 + 2) == cur[2]) {
+			} else if (d3 < mmm && *(cur - d3) == *cur) {
+				d[nd + 1] = d3 - 1;
+				nd += 2;
+				d2 = d3;
+			} else
+				break;
+		} else if (d3 < mmm && *(cur - d3) == *cur) {
+			d[nd + 1] = d3 - 1;
+			nd += 2;
+			d2 = d3;
+		} else
+			break;
+		d[nd - 2] = 3;
+		if (*(cur - d2 + 3) != cur[3])
+			break;
+		maxLen = mf_extend(cur - d2, cur, maxLen, lenLimit); // UPDATE_maxLen
+		d[nd - 2] = maxLen;
+		if (maxLen == lenLimit)
+			return nd; // son[] gets its link all the same; no chain walk
+		break;
+	}
+	// Hc_GetMatchesSpec
+	uint32_t cut = P.mc;
+	do {
+		if (curMatch == 0)
+			break;
+		const uint32_t delta = pos - curMatch;
+		if (delta >= P.cyclicSize)
+			break;
+		const uint8_t *pb = cur - delta;
+		curMatch = link[curMatch];
+		if (cur[maxLen] == pb[maxLen]) {
+			uint32_t len = 0;
+			while (cur[len] == pb[len]) {
+				if (++len == lenLimit) {
+					d[nd] = lenLimit;
+					d[nd + 1] = delta - 1;
+					return nd + 2;
+				}
+			}
+			if (maxLen < len) {
+				maxLen = len;
+				d[nd] = len;
+				d[nd + 1] = delta - 1;
+				nd += 2;
+			}
+		}
+	} while (--cut);
+	return nd;
 }
 
 } // namespace lzma

@@ -61,8 +61,9 @@ extern "C" int hostsim_lzma_encode_pre(const uint8_t *src, int64_t n, int level,
 	uint32_t crc[256];
 	for (uint32_t i = 0; i < 256; i++)
 		crc[i] = mf_crc_entry(i);
-	MfParams P = { (uint32_t)n, c.fb, c.mc, c.hashMask, c.bigHash, c.historySize, c.cyclicSize };
-	const uint32_t count = n >= 4 ? (uint32_t)n - 3 : 0;
+	MfParams P = { (uint32_t)n, c.fb, c.mc, c.hashMask, c.bigHash, c.historySize, c.cyclicSize, c.fastMode };
+	const uint32_t minAvail = c.fastMode ? 5 : 4; // positions with fewer bytes left are neither searched nor inserted
+	const uint32_t count = n >= minAvail ? (uint32_t)n - (minAvail - 1) : 0;
 	std::vector<uint32_t> c2(count), c3(count), order(count), son(2 * ((size_t)n + 2));
 	std::vector<uint64_t> rec((size_t)n, 0);
 	std::vector<uint32_t> pool;
@@ -74,20 +75,39 @@ extern "C" int hostsim_lzma_encode_pre(const uint8_t *src, int64_t n, int level,
 	};
 	prev_by([&](uint32_t i) { return mf_hash2(crc, src + i); }, c2);
 	prev_by([&](uint32_t i) { return mf_hash3(crc, src + i); }, c3);
-	auto h4 = [&](uint32_t i) { return mf_hash4(crc, src + i, P.hashMask, P.bigHash); };
-	std::iota(order.begin(), order.end(), 0u);
-	std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return h4(a) < h4(b); });
 	uint32_t d[2 * 273 + 8];
-	for (uint32_t s = 0; s < count;) {
-		const uint32_t hv = h4(order[s]);
-		uint32_t prev = 0;
-		for (; s < count && h4(order[s]) == hv; s++) {
-			const uint32_t i = order[s], pos = i + 1;
-			const uint32_t nbt = mf_bt_insert(src, P, son.data(), pos, prev, d + 4);
-			const uint32_t nd = mf_mix(src, P, pos, c2[i], c3[i], d, nbt);
-			rec[i] = ((uint64_t)pool.size() << kMfCountBits) | nd;
-			pool.insert(pool.end(), d, d + nd);
-			prev = pos;
+	if (c.fastMode) {
+		// hash chains: link[pos] = previous position with the same 5-byte hash; then every position on its own,
+		// here in DESCENDING order to make the point that nothing is carried between positions
+		std::vector<uint32_t> prev5(count);
+		prev_by([&](uint32_t i) { return mf_hash5(crc, src + i, P.hashMask); }, prev5);
+		std::vector<uint32_t> link((size_t)n + 2, 0);
+		for (uint32_t i = 0; i < count; i++)
+			link[i + 1] = prev5[i];
+		std::vector<std::vector<uint32_t>> lists(count);
+		for (uint32_t k = count; k-- > 0;) {
+			const uint32_t nd = mf_hc5_matches(src, P, link.data(), k + 1, c2[k], c3[k], d);
+			lists[k].assign(d, d + nd);
+		}
+		for (uint32_t i = 0; i < count; i++) {
+			rec[i] = ((uint64_t)pool.size() << kMfCountBits) | lists[i].size();
+			pool.insert(pool.end(), lists[i].begin(), lists[i].end());
+		}
+	} else {
+		auto h4 = [&](uint32_t i) { return mf_hash4(crc, src + i, P.hashMask, P.bigHash); };
+		std::iota(order.begin(), order.end(), 0u);
+		std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return h4(a) < h4(b); });
+		for (uint32_t s = 0; s < count;) {
+			const uint32_t hv = h4(order[s]);
+			uint32_t prev = 0;
+			for (; s < count && h4(order[s]) == hv; s++) {
+				const uint32_t i = order[s], pos = i + 1;
+				const uint32_t nbt = mf_bt_insert(src, P, son.data(), pos, prev, d + 4);
+				const uint32_t nd = mf_mix(src, P, pos, c2[i], c3[i], d, nbt);
+				rec[i] = ((uint64_t)pool.size() << kMfCountBits) | nd;
+				pool.insert(pool.end(), d, d + nd);
+				prev = pos;
+			}
 		}
 	}
 	if (pool_words)

@@ -34,7 +34,7 @@ def test_lz4_gate_matches_liblz4(ctx, threshold):
 
 
 @pytest.mark.skipif(not oracle.have_ref(), reason="oracle/_ref not built")
-@pytest.mark.parametrize("level,dict_size", [(7, 1 << 25), (5, 1 << 24), (9, 1 << 27)])
+@pytest.mark.parametrize("level,dict_size", [(7, 1 << 25), (5, 1 << 24), (9, 1 << 27), (3, 1 << 22), (1, 1 << 18)])
 def test_lzma_block_bit_exact(ctx, level, dict_size):
     p = make_params(level=level, backend=BACKEND_LZMA, threads=8, threshold=0)
     for name, d in _inputs().items():
@@ -56,6 +56,7 @@ def test_lzma_block_bit_exact(ctx, level, dict_size):
     ("text", 1_500_000, dict(threads=8)),
     ("mix", 2_000_000, dict(threads=8)),
     ("trees", 3_000_000, dict(threads=2, level=5)),
+    ("text", 2_000_000, dict(threads=4, level=3)),
 ])
 def test_lzma_archive_bit_identical_to_reference(ctx, kind, n, kw):
     d = datagen.generate(kind, n)

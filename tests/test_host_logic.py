@@ -92,6 +92,21 @@ def test_lzma_bucketwise_match_finder_equals_serial(hostsim):
             print(len(d), level, dic, words / max(1, len(d)))
 
 
+@pytest.mark.skipif(not oracle.have_ref(), reason="oracle/_ref not built")
+def test_lzma_fast_mode_matches_reference_lzmacompress(hostsim):
+    """Levels 1-4: GetOptimumFast over the hash-chain (hc5) finder computed as a data-parallel pre-pass
+    (every position on its own, links from a stable sort by 5-byte hash) -- against the reference's own
+    single-threaded finder, including blocks much longer than the small dictionaries of these levels."""
+    rng = np.random.default_rng(21)
+    cases = [datagen.gen_text(500_000).tobytes(), bytes(200_000), rng.integers(0, 256, 50_000, dtype=np.uint8).tobytes(),
+             datagen.gen_vm(1 << 20).tobytes(), datagen.gen_rep(1 << 20, block=1 << 14).tobytes(), b"ab" * 40, b"abcd",
+             rng.integers(0, 4, 200_000, dtype=np.uint8).tobytes(), datagen.gen_trees(700_000).tobytes()]
+    for d in cases:
+        for level, dic in ((1, 1 << 18), (2, 1 << 20), (3, 1 << 22), (4, 1 << 23), (3, 1 << 16)):
+            got, _ = _lzma_pre(hostsim[1], d, level, dic)
+            assert got == oracle.ref_lzma_block(d, level, dic, 2), (len(d), level, dic)
+
+
 def test_lzma_encoder_matches_golden(hostsim):
     for g in GOLDEN["lzma_blocks"]:
         d = datagen.generate(g["kind"], g["n"]).tobytes()
