@@ -201,7 +201,9 @@ def main():
     config = {"workload": desc, "per_gpu_bytes": size, "backend": backend, "level": level, "threads_p": threads,
               "ram_m": ram_units, "window_w": window, "l2": "inputs larger than L2 (126 MB); no flush needed",
               "warmup_bytes": min(size, WARM_BYTES),
-              "sharding": "one rzip window per GPU, blobs gathered to rank 0" if world > 1 else "single window"}
+              "sharding": ("one rzip window per GPU, blobs gathered to rank 0; "
+                           + ("windows chained through victim_round" if kind == "text" else "victim_round speculated"))
+              if world > 1 else "single window"}
 
     if a.impl == "reference":
         if rank != 0:
@@ -276,7 +278,10 @@ def main():
             last.update(out_len=ol, stats=st.as_dict())
             ctx.free(out)
         else:  # the shard is re-uploaded from the pinned copy by compress_chunk (the chunk ABI takes host data)
-            arc, sts = multigpu.compress_sharded(ctx, params, sz, {rank: host}, plans, whole_md5, dev)
+            # text consults the reference's cross-window counter all the time: chain the windows
+            # through it (rzip stages in sequence, backends overlapped); other data speculates and shards freely
+            fn = multigpu.compress_chained if kind == "text" else multigpu.compress_sharded
+            arc, sts = fn(ctx, params, sz, {rank: host}, plans, whole_md5, dev)
             last.update(out_len=len(arc) if arc is not None else 0, stats=sts[0])
 
     def step_e2e():

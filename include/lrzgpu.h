@@ -10,7 +10,8 @@
  *                                       + write_magic()      src/lrzip.c:131 (called from
  *                                                            compress_file(), src/lrzip.c:1549-1553)
  *   lrzgpu_compress_chunk               one pass of the chunk loop src/rzip.c:1041-1186
- *                                       (rzip_chunk :873 + close_stream_out, src/stream.c:2253)
+ *   lrzgpu_chunk_begin / _finish        (rzip_chunk :873 + close_stream_out, src/stream.c:2253); the two-call form
+ *                                       splits it at the point where rzip_chunk returns
  *   lrzgpu_rzip_chunk                   hash_search()        src/rzip.c:586 with the scan primitives
  *                                       full_tag/next_tag/match_len, lrzip_private.h:573-576
  *   lrzgpu_tag_scan                     single_full_tag()/single_next_tag()  src/rzip.c:385-416
@@ -118,6 +119,14 @@ int lrzgpu_compress_device(lrzgpu_ctx *ctx, const lrzgpu_params *p, const void *
 int lrzgpu_compress_chunk(lrzgpu_ctx *ctx, const lrzgpu_params *p, const lrzgpu_sizing_t *sz,
 			  const uint8_t *in, int64_t n, int eof, int64_t *victim_round,
 			  uint8_t **blob, int64_t *blob_len, lrzgpu_stats *stats);
+
+/* The same window in two calls, for chained windows (multi-GPU): _begin runs the rzip stage and returns the
+ * outgoing victim_round as soon as the commit is done -- the only thing the NEXT window needs, so its rank can
+ * start while this one is still in the backend; _finish runs blocks -> backend -> framing of the pending
+ * window and returns the same blob lrzgpu_compress_chunk would.  One pending window per context. */
+int lrzgpu_chunk_begin(lrzgpu_ctx *ctx, const lrzgpu_params *p, const lrzgpu_sizing_t *sz, const uint8_t *in, int64_t n,
+		       int eof, int64_t *victim_round, lrzgpu_stats *stats);
+int lrzgpu_chunk_finish(lrzgpu_ctx *ctx, uint8_t **blob, int64_t *blob_len, lrzgpu_stats *stats);
 
 /* rzip of one chunk -> stream 0 / stream 1 bytes (malloc'ed). */
 int lrzgpu_rzip_chunk(lrzgpu_ctx *ctx, const uint8_t *in, int64_t n, int rzip_level, int chunk_bytes,

@@ -69,6 +69,7 @@ _lib = None
 EXPORTS = [
     "lrzgpu_create", "lrzgpu_destroy", "lrzgpu_last_error", "lrzgpu_free", "lrzgpu_version", "lrzgpu_sizing",
     "lrzgpu_compress", "lrzgpu_compress_file", "lrzgpu_compress_device", "lrzgpu_compress_chunk",
+    "lrzgpu_chunk_begin", "lrzgpu_chunk_finish",
     "lrzgpu_rzip_chunk", "lrzgpu_tag_scan", "lrzgpu_crc32", "lrzgpu_block_compress", "lrzgpu_lz4_gate",
     "lrzgpu_k1_launch", "lrzgpu_crc32_launch", "lrzgpu_sm_count",
 ]
@@ -98,6 +99,8 @@ def load_library():
     L.lrzgpu_compress_device.argtypes = [vp, C.POINTER(Params), vp, i64, vp, pvp, pi64, C.POINTER(Stats)]
     L.lrzgpu_compress_chunk.argtypes = [vp, C.POINTER(Params), C.POINTER(Sizing), vp, i64, C.c_int, pi64, pvp, pi64,
                                         C.POINTER(Stats)]
+    L.lrzgpu_chunk_begin.argtypes = [vp, C.POINTER(Params), C.POINTER(Sizing), vp, i64, C.c_int, pi64, C.POINTER(Stats)]
+    L.lrzgpu_chunk_finish.argtypes = [vp, pvp, pi64, C.POINTER(Stats)]
     L.lrzgpu_rzip_chunk.argtypes = [vp, vp, i64, C.c_int, C.c_int, pi64, pvp, pi64, pvp, pi64, C.POINTER(Stats)]
     L.lrzgpu_tag_scan.argtypes = [vp, vp, i64, i64, i64, i64, vp, vp, i64, pi64]
     L.lrzgpu_crc32.argtypes = [vp, vp, i64, C.POINTER(C.c_uint32)]
@@ -219,6 +222,20 @@ class Context:
         self._check(self._L.lrzgpu_compress_chunk(self._h, C.byref(params), C.byref(sz), addr, n, int(eof), C.byref(vr),
                                                   C.byref(out), C.byref(ol), C.byref(st)))
         return self._take(out, ol.value), vr.value, st.as_dict()
+
+    def chunk_begin(self, data, params: Params, sz: Sizing, eof: bool, victim_round: int = 0):
+        """rzip stage of one window -> (victim_round_out, stats); the window stays pending for chunk_finish()."""
+        addr, n, keep = _ptr(data)
+        st, vr = Stats(), C.c_int64(victim_round)
+        self._check(self._L.lrzgpu_chunk_begin(self._h, C.byref(params), C.byref(sz), addr, n, int(eof), C.byref(vr),
+                                               C.byref(st)))
+        return vr.value, st.as_dict()
+
+    def chunk_finish(self):
+        """backend + framing of the pending window -> (blob, stats)."""
+        out, ol, st = C.c_void_p(), C.c_int64(), Stats()
+        self._check(self._L.lrzgpu_chunk_finish(self._h, C.byref(out), C.byref(ol), C.byref(st)))
+        return self._take(out, ol.value), st.as_dict()
 
     # ---- scan primitives -------------------------------------------------------------------------
     def rzip_chunk(self, data, rzip_level: int = 7, chunk_bytes: int | None = None, victim_round: int = 0):

@@ -72,6 +72,14 @@ struct lrzgpu_ctx {
 	size_t h_pin_cap = 0;
 	BackendCtx *backend = nullptr;
 	int64_t launches = 0;
+	// window between lrzgpu_chunk_begin and lrzgpu_chunk_finish (rzip done, streams resident in s0 / s1)
+	struct Pending {
+		bool valid = false;
+		lrzgpu_params p;
+		lrzgpu_sizing_t sz;
+		int64_t n = 0, s0_len = 0, s1_len = 0, n_rec = 0;
+		int eof = 0, cb = 0;
+	} pending;
 };
 
 namespace {
@@ -221,6 +229,10 @@ struct OutBuf {
 
 // One chunk: rzip on the device, then blocks -> backend -> framed blob appended to `out`
 // (src/stream.c:1722-1821: chunk preamble, two initial stream headers, blocks with next_head patching).
+// Second half of a chunk: stream blocks -> backend -> framed blob, from the streams rzip left in c->s0 / c->s1.
+int finish_chunk_device(lrzgpu_ctx *c, const lrzgpu_params &p, const lrzgpu_sizing_t &sz, int64_t n, int eof, int cb,
+			const ChunkResult &res, OutBuf &out, lrzgpu_stats *stats);
+
 int compress_chunk_device(lrzgpu_ctx *c, const lrzgpu_params &p, const lrzgpu_sizing_t &sz, const uint8_t *d_chunk,
 			  int64_t n, int eof, int64_t *victim_round, OutBuf &out, lrzgpu_stats *stats)
 {
@@ -231,7 +243,13 @@ int compress_chunk_device(lrzgpu_ctx *c, const lrzgpu_params &p, const lrzgpu_si
 	if (rc)
 		return rc;
 	*victim_round = res.st.victim_round;
+	return finish_chunk_device(c, p, sz, n, eof, cb, res, out, stats);
+}
 
+int finish_chunk_device(lrzgpu_ctx *c, const lrzgpu_params &p, const lrzgpu_sizing_t &sz, int64_t n, int eof, int cb,
+			const ChunkResult &res, OutBuf &out, lrzgpu_stats *stats)
+{
+	int rc = 0;
 	const double t0 = now_ms();
 	const int64_t nb0 = res.s0_len / sz.bufsize;
 	std::vector<int64_t> w1((size_t)nb0 + 1, 0);
@@ -647,6 +665,79 @@ int lrzgpu_compress_chunk(lrzgpu_ctx *c, const lrzgpu_params *p, const lrzgpu_si
 		return rc;
 	OutBuf ob;
 	rc = compress_chunk_device(c, *p, *sz, d_in, n, eof, victim_round, ob, stats);
+	if (rc) {
+		free(ob.p);
+		return rc;
+	}
+	*blob = ob.p;
+	*blob_len = ob.len;
+	if (stats) {
+		stats->ms_total = now_ms() - t0;
+		stats->kernel_launches = c->launches - launches0;
+	}
+	return LRZGPU_OK;
+}
+
+int lrzgpu_chunk_begin(lrzgpu_ctx *c, const lrzgpu_params *p, const lrzgpu_sizing_t *sz, const uint8_t *in, int64_t n,
+		       int eof, int64_t *victim_round, lrzgpu_stats *stats)
+{
+	int rc = check_params(c, p, n);
+	if (rc)
+		return rc;
+	if (!sz || !in || !victim_round)
+		return LRZGPU_EINVAL;
+	cudaSetDevice(c->device);
+	c->pending.valid = false;
+	if (stats)
+		memset(stats, 0, sizeof(*stats));
+	const int64_t launches0 = c->launches;
+	const double t0 = now_ms();
+	uint8_t *d_in = nullptr;
+	rc = upload(c, in, n, &d_in);
+	if (rc)
+		return rc;
+	const int rzl = p->rzip_level ? p->rzip_level : p->level;
+	const int cb = chunk_bytes_for(n);
+	ChunkResult res;
+	rc = rzip_chunk_device(c, d_in, n, rzl, cb, *victim_round, res, stats);
+	if (rc)
+		return rc;
+	*victim_round = res.st.victim_round;
+	c->pending.valid = true;
+	c->pending.p = *p;
+	c->pending.sz = *sz;
+	c->pending.n = n;
+	c->pending.eof = eof;
+	c->pending.cb = cb;
+	c->pending.s0_len = res.s0_len;
+	c->pending.s1_len = res.s1_len;
+	c->pending.n_rec = res.n_rec;
+	if (stats) {
+		stats->ms_total = now_ms() - t0;
+		stats->kernel_launches = c->launches - launches0;
+	}
+	return LRZGPU_OK;
+}
+
+int lrzgpu_chunk_finish(lrzgpu_ctx *c, uint8_t **blob, int64_t *blob_len, lrzgpu_stats *stats)
+{
+	if (!c || !blob || !blob_len)
+		return LRZGPU_EINVAL;
+	if (!c->pending.valid)
+		return fail(c, LRZGPU_EINVAL, "lrzgpu_chunk_finish without a window from lrzgpu_chunk_begin");
+	cudaSetDevice(c->device);
+	if (stats)
+		memset(stats, 0, sizeof(*stats));
+	const int64_t launches0 = c->launches;
+	const double t0 = now_ms();
+	ChunkResult res;
+	res.s0_len = c->pending.s0_len;
+	res.s1_len = c->pending.s1_len;
+	res.n_rec = c->pending.n_rec;
+	c->pending.valid = false;
+	OutBuf ob;
+	const int rc = finish_chunk_device(c, c->pending.p, c->pending.sz, c->pending.n, c->pending.eof, c->pending.cb, res, ob,
+					   stats);
 	if (rc) {
 		free(ob.p);
 		return rc;

@@ -162,3 +162,53 @@ def compress_sharded(ctx, params: Params, sz: Sizing, shards: dict[int, np.ndarr
         return None, stats
     md5 = whole_md5 if whole_md5 is not None else hashlib.md5(b"").digest()
     return assemble(params, sz, sum(p.size for p in plans), got, md5), stats
+
+
+_chain_calls = 0
+
+
+def compress_chained(ctx, params: Params, sz: Sizing, shards: dict[int, np.ndarray], plans: list[ChunkPlan],
+                     whole_md5: bytes | None = None, device: torch.device | None = None):
+    """Like compress_sharded, for data that consults ``victim_round`` all the time (text: the XOR tags collide
+    and fill equal-tag chains), where speculation would re-run nearly every chunk.  The chunks form a chain
+    through that one counter, but only through the rzip stage: the owner of chunk i receives the counter from
+    the owner of chunk i-1, runs ``chunk_begin`` (rzip), passes the new counter on at once and only then runs
+    ``chunk_finish`` (blocks -> backend -> framing), so the backend phases of all chunks overlap and the
+    critical path is  sum(rzip) + one backend  instead of  sum(rzip + backend).
+    Returns (archive or None, per-rank stats list)."""
+    global _chain_calls
+    rank, world = dist.get_rank(), dist.get_world_size()
+    device = device or torch.device("cpu")
+    # The counter (one small integer per chunk) travels through the process group's key-value store: plain
+    # TCP, the same under nccl and gloo, no device work and no pairing rules to get wrong.  Every rank makes
+    # the same number of calls, so the call index keeps the keys of successive archives apart.
+    from datetime import timedelta
+    store = dist.distributed_c10d._get_default_store()
+    store.set_timeout(timedelta(hours=6))
+    _chain_calls += 1
+    tag = f"lrzgpu/victim_round/{_chain_calls}"
+    blobs, stats = {}, []
+    last_out = 0
+    for p in plans:
+        if p.rank != rank:
+            continue
+        vin = 0
+        if p.index > 0:
+            vin = last_out if plans[p.index - 1].rank == rank else int(store.get(f"{tag}/{p.index - 1}"))
+        vr_out, st_a = ctx.chunk_begin(shards[p.index], params, sz, p.eof, vin)
+        last_out = vr_out
+        if p.index + 1 < len(plans) and plans[p.index + 1].rank != rank:
+            store.set(f"{tag}/{p.index}", str(vr_out))
+        blob, st_b = ctx.chunk_finish()
+        blobs[p.index] = blob
+        merged = dict(st_b)
+        for k, v in st_a.items():  # begin holds the rzip counters and timings, finish the backend ones
+            if isinstance(v, (int, float)) and k not in ("crc32",):
+                merged[k] = merged.get(k, 0) + v
+        merged["crc32"] = st_a.get("crc32", 0)
+        stats.append(merged)
+    got = gather_blobs(blobs, device)
+    if rank != 0:
+        return None, stats
+    md5 = whole_md5 if whole_md5 is not None else hashlib.md5(b"").digest()
+    return assemble(params, sz, sum(p.size for p in plans), got, md5), stats

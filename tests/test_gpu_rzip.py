@@ -103,3 +103,17 @@ def test_archive_verifies_with_reference_binary(ctx):
     got = ctx.compress(d, p)
     assert oracle.ref_test(got)
     assert oracle.ref_decompress(got) == d.tobytes()
+
+
+def test_two_phase_chunk_equals_one_call(ctx):
+    """lrzgpu_chunk_begin + lrzgpu_chunk_finish (the chained multi-GPU form) == lrzgpu_compress_chunk."""
+    from lrzip_next_b200 import BACKEND_LZMA, sizing
+    d = np.concatenate([datagen.generate("text", 1_200_000), datagen.generate("rep", 800_000, block=1 << 16)])
+    for p in (make_params(backend=BACKEND_NONE, threads=1), make_params(backend=BACKEND_LZMA, threads=8)):
+        sz = sizing(p, d.size)
+        for vin in (0, 5):
+            blob, vr, st = ctx.compress_chunk(d, p, sz, True, vin)
+            vr2, st_a = ctx.chunk_begin(d, p, sz, True, vin)
+            blob2, st_b = ctx.chunk_finish()
+            assert (blob2, vr2) == (blob, vr)
+            assert st_a["lookups"] == st["lookups"] and st_b["blocks"] == st["blocks"]

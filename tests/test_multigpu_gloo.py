@@ -79,3 +79,60 @@ def test_magic_matches_reference_layout():
     pz = make_params(backend=api.BACKEND_ZSTD, threads=8)
     mz = multigpu.make_magic(pz, sizing(pz, 1000), 1000)
     assert (mz[17], mz[18], mz[19]) == (0x74, 0x11, 0x77)
+
+
+class ChainFakeCtx:
+    """chunk_begin / chunk_finish with a made-up but victim_round-DEPENDENT result, to test the chained
+    orchestration (who waits for whom, what is passed on, gather order) without a GPU."""
+
+    def __init__(self):
+        self.pending = None
+
+    @staticmethod
+    def _vr_out(data, vin):
+        return (vin * 5 + int(np.asarray(data[:64], dtype=np.int64).sum()) + 3) % 16
+
+    def chunk_begin(self, data, params, sz, eof, victim_round=0):
+        assert self.pending is None
+        d = np.ascontiguousarray(data, dtype=np.uint8)
+        self.pending = (d, bool(eof), victim_round)
+        return self._vr_out(d, victim_round), {"chain_evictions": 1, "lookups": int(d.size), "crc32": 7}
+
+    def chunk_finish(self):
+        d, eof, vin = self.pending
+        self.pending = None
+        blob = bytes([4, 1 if eof else 0, vin]) + hashlib.sha1(d.tobytes()).digest() + d[:1000].tobytes()
+        return blob, {"blocks": 2, "lookups": 0, "crc32": 0}
+
+
+def _chain_worker(rank, world, port, path, n, chunk):
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    d = datagen.gen_text(n)
+    params = make_params(backend=0, threads=1)
+    sz = sizing(params, n)
+    plans = multigpu.plan_chunks(n, chunk, world)
+    shards = {p.index: d[p.offset:p.offset + p.size] for p in plans if p.rank == rank}
+    arc, sts = multigpu.compress_chained(ChainFakeCtx(), params, sz, shards, plans, hashlib.md5(d.tobytes()).digest())
+    if rank == 0:
+        with open(path, "wb") as fh:
+            fh.write(arc)
+        assert all(s["lookups"] > 0 and s["blocks"] == 2 for s in sts)
+    dist.destroy_process_group()
+
+
+def test_chained_windows_pass_victim_round_along(tmp_path):
+    n, chunk = 700_000, 100_000  # 7 windows over 2 ranks: ranks alternate, each waits for its predecessor
+    path = str(tmp_path / "chain.lrz")
+    mp.spawn(_chain_worker, args=(2, 29741, path, n, chunk), nprocs=2, join=True)
+    d = datagen.gen_text(n)
+    params = make_params(backend=0, threads=1)
+    sz = sizing(params, n)
+    fake, vr, blobs = ChainFakeCtx(), 0, {}
+    for p in multigpu.plan_chunks(n, chunk, 2):  # the serial meaning: one process, chunks in order
+        vr, _ = fake.chunk_begin(d[p.offset:p.offset + p.size], params, sz, p.eof, vr)
+        blobs[p.index], _ = fake.chunk_finish()
+    want = multigpu.assemble(params, sz, n, blobs, hashlib.md5(d.tobytes()).digest())
+    with open(path, "rb") as fh:
+        assert fh.read() == want
