@@ -3,7 +3,7 @@
  * CPU restatement of the parts of lrzip-next that turn rzip's two byte streams into a .lrz
  * archive: window (chunk) policy, stream block sizing, block flush order, chunk / stream / block
  * headers with next_head patching, trailing MD5 and the 21-byte magic header.
- * Pinned against oracle/_ref archives by tests/test_oracle_vs_ref.py and tests/golden/.
+ * Pinned against oracle/_ref archives by tests/test_oracle.py and tests/golden/.
  * References are to /root/reference.
  */
 #include "rzip_oracle.h"

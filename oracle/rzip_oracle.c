@@ -8,7 +8,7 @@
  * compiled reference (oracle/_ref) is unavailable.
  *
  * PARITY PINNING: this restatement is itself checked against the unmodified reference built
- * into oracle/_ref (tests/test_oracle_vs_ref.py) and against the committed golden vectors
+ * into oracle/_ref (tests/test_oracle.py) and against the committed golden vectors
  * under tests/golden/ that were produced by that reference (tests/golden/make_golden.py).
  *
  * Every function cites the reference lines it follows (paths relative to /root/reference).

@@ -1,7 +1,7 @@
 """GPU parity tests for the rzip path (K1 tag scan, K2 commit, K4 emit, CRC) through the C ABI.
 
 Every comparison is bit-exact against the CPU oracle (oracle/liboracle.so), which is itself pinned to
-the unmodified reference (tests/test_oracle_vs_ref.py, tests/golden/)."""
+the unmodified reference (tests/test_oracle.py, tests/golden/)."""
 import hashlib
 import zlib
 

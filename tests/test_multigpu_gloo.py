@@ -1,6 +1,6 @@
 """world_size-2 gloo tests (CPU) of the window-sharded path: chunk planning, victim_round settlement,
 blob gather and archive assembly.  The per-chunk compressor is played by the oracle here (the GPU
-library cannot run on this box); on a GPU box test_gpu_multi.py runs the same path with the real one."""
+library cannot run on this box); on GPU boxes `bench.py --gpus N` runs the same paths with the real one."""
 import hashlib
 import os
 import tempfile
