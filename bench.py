@@ -41,7 +41,7 @@ MB = 1e6
 # Warm-up steps run the whole path on a prefix of the workload (module load, arena growth, clocks); the
 # timed steps always run the full workload.  A full C2 step is minutes of serial commit + LZMA work, so
 # full-size warm-ups would not let the default run finish "within minutes".
-WARM_BYTES = 64 << 20
+WARM_BYTES = 8 << 20
 WORKLOADS = {
     # name: (generator, per-GPU bytes, backend, level, description)
     "c1": ("rep", 100 << 20, "none", 7, "C1: 100 MiB repeated 1 MiB random block, rzip-only (-n)"),
