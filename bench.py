@@ -1,26 +1,32 @@
 #!/usr/bin/env python
 """bench.py -- compress MB/s of input bytes on N B200s, next to the reference's CPU path.
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c1|c2|c3|c4] [--impl reference]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--budget-s S] [--workload c1|c2|c3|c4] [--impl reference]
 
 A "step" is one whole pass of the hot path (rzip -> stream blocks -> backend -> .lrz framing) over the
-workload's input.  Workloads follow BASELINE.json `configs`; the default at N=1 is the
-configuration the metric is quoted on, C2: 1 GiB of enwik-style text, LZMA level 7.  At N>1 every
-rank owns one window (chunk) of the per-GPU size -- weak scaling -- and the only collective is the
-final gather of the finished chunk blobs to rank 0 (NCCL).
+workload's input, called through the reference-facing C ABI with HOST buffers.  Workloads follow
+BASELINE.json `configs`; the default is the configuration the metric is quoted on, C2: 1 GB
+(1000 MiB) of enwik-style text per GPU, LZMA level 7.  At N>1 every rank owns one rzip window of the same
+per-GPU size -- weak scaling -- the file is the concatenation of the windows (reference flag `-w 10`), and the
+only collective is the final gather of the finished chunk blobs to rank 0 (NCCL).
 
-value     = input bytes / time, inputs resident in HBM when the timed region starts
-e2e       = the same through the C ABI with HOST buffers (pinned H2D of the input and D2H of the
-            archive inside the timed region)
-roofline  = the K1 tag-scan kernel timed alone with CUDA events on its launch stream; algorithmic
-            bytes = N * (1 + 16 * 2^-initial_freq)  
-cpu_baseline / --impl reference = the unmodified reference binary (oracle/_ref/lrzip-next) on the
-            host cores, on a bounded sample of the same workload
+ONE timed loop produces both headline numbers (a full C2 step is tens of seconds of serial rzip commit and
+LZMA work, so the loop is also bounded by a wall-clock budget, see --budget-s):
+  e2e       = input bytes / wall time of the steps; every step does the pinned H2D copy of the input and the
+              D2H read of the finished archive inside the timed region
+  value     = the same steps with the H2D / D2H time the library measured around its copies taken out
+              (= inputs resident in HBM when the step starts)
+`steps` is the number of full-size steps actually timed, `steps_requested` what --steps asked for.
+roofline    = the K1 tag-scan kernel timed alone with CUDA events on its launch stream; algorithmic
+              bytes = N * (1 + 16 * 2^-initial_freq)  
+cpu_baseline = the unmodified reference binary (oracle/_ref/lrzip-next) on the host cores, on a bounded
+              prefix of the workload (N=1, rank 0)
+--impl reference = the unmodified reference binary on the FULL workload (N x per-GPU size, same flags, same
+              `-w`), same budget rule; both arms print `archive_sha256`, equal values = bit-identical archives.
 """
 from __future__ import annotations
 
 import argparse
-import ctypes as C
 import hashlib
 import json
 import os
@@ -31,6 +37,7 @@ import tempfile
 import threading
 import time
 
+T_START = time.perf_counter()
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
@@ -38,17 +45,18 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 import numpy as np  # noqa: E402
 
 MB = 1e6
-# Warm-up steps run the whole path on a prefix of the workload (module load, arena growth, clocks); the
-# timed steps always run the full workload.  A full C2 step is minutes of serial commit + LZMA work, so
-# full-size warm-ups would not let the default run finish "within minutes".
-WARM_BYTES = 8 << 20
+MiB = 1 << 20
+# Warm-up steps run the whole path (every kernel, arena growth, clocks) on a prefix of the workload; the timed
+# steps always run the full workload.  A full C2 step is tens of seconds, so full-size warm-ups would eat the budget.
+WARM_BYTES = 1 << 20
+REF_WARM_BYTES = 32 << 20
 WORKLOADS = {
     # name: (generator, per-GPU bytes, backend, level, description)
-    "c1": ("rep", 100 << 20, "none", 7, "C1: 100 MiB repeated 1 MiB random block, rzip-only (-n)"),
-    "c2": ("text", 1 << 30, "lzma", 7, "C2: 1 GiB enwik-style text, lzma level 7"),
-    "c2n": ("text", 1 << 30, "none", 7, "C2 input, rzip-only (-n)"),
-    "c3": ("trees", 1000 << 20, "lzma", 7, "C3 shard: 1000 MiB of duplicated source trees, lzma level 7"),
-    "c4": ("randzero", 1 << 30, "zstd", 7, "C4 scaled: 512 MiB random + 512 MiB zeros, zstd, lz4 gate on"),
+    "c1": ("rep", 100 * MiB, "none", 7, "C1: 100 MiB repeated 1 MiB random block, rzip-only (-n)"),
+    "c2": ("text", 1000 * MiB, "lzma", 7, "C2: 1 GB (1000 MiB) enwik-style text, lzma level 7"),
+    "c2n": ("text", 1000 * MiB, "none", 7, "C2 input, rzip-only (-n)"),
+    "c3": ("trees", 1000 * MiB, "lzma", 7, "C3 shard: 1000 MiB of duplicated source trees, lzma level 7"),
+    "c4": ("randzero", 1000 * MiB, "zstd", 7, "C4 scaled: 500 MiB random + 500 MiB zeros, zstd, lz4 gate on"),
 }
 
 
@@ -56,7 +64,7 @@ def peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
         with open(path) as fh:
-            return float(json.load(fh)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+            return float(json.load(fh)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs, burst copy figure: K1 is timed alone)"
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
@@ -71,7 +79,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "200", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
+                                          "-lms", "500", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
             threading.Thread(target=lambda: self.lines.extend(self.proc.stdout), daemon=True).start()
         except OSError:
             self.proc = None
@@ -123,54 +131,60 @@ def ref_flags(backend: str, level: int, threads: int, ram_units: int, window: in
     return f
 
 
-def run_reference(data: np.ndarray, flags, repeats: int = 1):
-    """Wall-clock the unmodified reference binary file -> file on tmpfs. Returns (best seconds, out size)."""
-    ref = os.path.join(ROOT, "oracle", "_ref", "lrzip-next")
-    if not os.path.exists(ref):
-        return None, None
-    env = dict(os.environ, LRZIP="NOCONFIG")
-    d = tempfile.mkdtemp(dir="/dev/shm" if os.path.isdir("/dev/shm") else None)
-    src, dst = os.path.join(d, "in.bin"), os.path.join(d, "out.lrz")
-    try:
-        data.tofile(src)
-        best, size = None, None
-        for _ in range(repeats):
-            t = time.perf_counter()
-            subprocess.run([ref, *flags, "-o", dst, src], check=True, env=env, stdout=subprocess.DEVNULL,
-                           stderr=subprocess.DEVNULL)
-            dt = time.perf_counter() - t
-            best = dt if best is None else min(best, dt)
-            size = os.path.getsize(dst)
-        return best, size
-    finally:
-        for f in (src, dst):
+class RefRunner:
+    """The unmodified reference binary, file -> file on tmpfs, wall clock around the whole run
+    (test/speedtest.sh:87-99 of the reference times the same way)."""
+
+    def __init__(self):
+        self.ref = os.path.join(ROOT, "oracle", "_ref", "lrzip-next")
+        self.dir = tempfile.mkdtemp(dir="/dev/shm" if os.path.isdir("/dev/shm") else None)
+        self.files = set()
+
+    def available(self) -> bool:
+        return os.path.exists(self.ref)
+
+    def put(self, name: str, data: np.ndarray) -> str:
+        p = os.path.join(self.dir, name)
+        data.tofile(p)
+        self.files.add(p)
+        return p
+
+    def run(self, src: str, flags) -> tuple[float, str]:
+        dst = src + ".lrz"
+        self.files.add(dst)
+        t = time.perf_counter()
+        subprocess.run([self.ref, *flags, "-o", dst, src], check=True, env=dict(os.environ, LRZIP="NOCONFIG"),
+                       stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+        return time.perf_counter() - t, dst
+
+    def close(self):
+        for f in self.files:
             if os.path.exists(f):
                 os.unlink(f)
-        os.rmdir(d)
+        os.rmdir(self.dir)
 
 
-def cpu_sample_bytes(backend: str, cores: int) -> int:
-    # ~10-30 s of reference CPU work: rzip-only runs at 10-150 MB/s on one thread, lzma/zstd level 7 at
-    # roughly 0.7 MB/s per core
-    if backend == "none":
-        return 256 << 20
-    # at least one 10 MiB stream block per host core, so that every core has a backend block to work on
-    return min(1 << 30, max(64 << 20, (cores * 12) << 20))
+def sha256_file(path: str) -> str:
+    h = hashlib.sha256()
+    with open(path, "rb") as fh:
+        for blk in iter(lambda: fh.read(1 << 24), b""):
+            h.update(blk)
+    return h.hexdigest()
 
 
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="lrzgpu", choices=["lrzgpu", "reference"])
     ap.add_argument("--workload", default=os.environ.get("LRZ_BENCH_WORKLOAD", "c2"), choices=sorted(WORKLOADS))
-    ap.add_argument("--size-mb", type=int, default=0, help="override the per-GPU input size (MiB)")
-    ap.add_argument("--threads", type=int, default=0, help="-p given to both arms (default: host cores)")
+    ap.add_argument("--size-mb", type=int, default=0, help="override the per-GPU input size (MiB, multiple of 100 at N>1)")
+    ap.add_argument("--threads", type=int, default=0, help="-p given to both arms (default: max(host cores, 160))")
+    ap.add_argument("--budget-s", type=float, default=float(os.environ.get("LRZ_BENCH_BUDGET_S", "540")),
+                    help="wall-clock budget of the whole run: full-size steps are timed until --steps are done or "
+                         "the next one would overrun it (at least one is always timed)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--verify", action="store_true",
-                    help="after timing (N=1): run the unmodified reference on the FULL workload with the same flags and "
-                         "compare archive SHA-256 (minutes of CPU time; outside every timed region)")
     a = ap.parse_args()
 
     # The contract is ONE JSON line on stdout.  Native libraries write there too (NCCL prints its version
@@ -183,51 +197,74 @@ def main():
         sys.stdout.flush()
         os.write(real_stdout, (json.dumps(obj) + "\n").encode())
 
+    def elapsed():
+        return time.perf_counter() - T_START
+
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
+    nwin = world if a.impl == "lrzgpu" else max(1, a.gpus)
     kind, size, backend, level, desc = WORKLOADS[a.workload]
     if a.size_mb:
-        size = a.size_mb << 20
+        size = a.size_mb * MiB
     cores = os.cpu_count() or 1
     # -p: stream blocks are limit/threads but never below 10 MiB (src/stream.c:1140-1348), and one block is
-    # the unit of backend parallelism on both arms.  -p 160 gives the 10 MiB minimum for 1 GiB at -m 600
-    # (105 threads after the reference's own memory-driven reduction); it is passed to both arms.
+    # the unit of backend parallelism on both arms.  -p 160 gives the 10 MiB minimum for 1 GB at -m 600
+    # (the reference itself reduces it to what fits its memory budget); it is passed to both arms.
     threads = a.threads or max(cores, 160)
     ram_units = 600  # -m 600 = 60 GB, pinned for both arms
-    window = 0 if world == 1 else size // (100 << 20)
-    if world > 1 and size % (100 << 20):
-        size = window * (100 << 20)
-    config = {"workload": desc, "per_gpu_bytes": size, "backend": backend, "level": level, "threads_p": threads,
-              "ram_m": ram_units, "window_w": window, "l2": "inputs larger than L2 (126 MB); no flush needed",
-              "warmup_bytes": min(size, WARM_BYTES),
-              "sharding": ("one rzip window per GPU, blobs gathered to rank 0; "
-                           + ("windows chained through victim_round" if kind == "text" else "victim_round speculated"))
-              if world > 1 else "single window"}
+    # the same per-GPU size at every N; N > 1 = N windows of that size (-w in units of 100 MiB)
+    window = 0 if nwin == 1 else size // (100 * MiB)
+    if nwin > 1 and size % (100 * MiB):
+        raise SystemExit("per-GPU size must be a multiple of 100 MiB at N > 1 (-w units)")
+    total = size * nwin
+    config = {"workload": desc, "per_gpu_bytes": size, "total_bytes": total, "backend": backend, "level": level,
+              "threads_p": threads, "ram_m": ram_units, "window_w": window,
+              "l2": "inputs larger than L2 (126 MB); no flush needed",
+              "budget_s": a.budget_s,
+              "sharding": "single window" if nwin == 1 else
+              f"{nwin} rzip windows of {size // MiB} MiB, one per GPU; blobs gathered to rank 0 (NCCL)"}
 
     if a.impl == "reference":
         if rank != 0:
             return
-        sample = min(size, cpu_sample_bytes(backend, cores))
-        data = gen_input(kind, sample)
-        flags = ref_flags(backend, level, threads, ram_units)
-        times = []
-        for i in range(a.warmup + a.steps):
-            dt, osz = run_reference(data, flags)
-            if dt is None:
-                emit({"impl": "reference", "unavailable": "oracle/_ref/lrzip-next was not built"})
-                return
-            if i >= a.warmup:
+        rr = RefRunner()
+        if not rr.available():
+            emit({"impl": "reference", "unavailable": "oracle/_ref/lrzip-next was not built"})
+            return
+        try:
+            data = np.concatenate([gen_input(kind, size, seed_shift=r) for r in range(nwin)]) if nwin > 1 \
+                else gen_input(kind, size)
+            flags = ref_flags(backend, level, threads, ram_units, window)
+            config["warmup_bytes"] = min(total, REF_WARM_BYTES)
+            wsrc = rr.put("warm.bin", data[:config["warmup_bytes"]])
+            for _ in range(a.warmup):
+                rr.run(wsrc, ref_flags(backend, level, threads, ram_units))
+            src = rr.put("in.bin", data)
+            del data
+            times, dst = [], None
+            while len(times) < a.steps:
+                est = max(times) if times else 0.0
+                if times and elapsed() + est > a.budget_s:
+                    break
+                dt, dst = rr.run(src, flags)
                 times.append(dt)
-        v = sample / (sum(times) / len(times)) / MB
+            osz = os.path.getsize(dst)
+            sha = sha256_file(dst)
+        finally:
+            rr.close()
+        mean = sum(times) / len(times)
+        v = total / mean / MB
         emit({
             "impl": "reference", "metric": "compress MB/s (input bytes)", "value": v, "unit": "MB/s", "n_gpus": a.gpus,
-            "steps": a.steps, "warmup": a.warmup, "ms_per_step": 1e3 * sum(times) / len(times), "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic", "config": config,
+            "steps": len(times), "steps_requested": a.steps, "warmup": a.warmup, "ms_per_step": 1e3 * mean,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+            "config": config,
             "cpu_baseline": {"value": v, "unit": "MB/s", "cores": min(threads, cores), "kind": "reference",
-                             "sample": f"first {sample >> 20} MiB of the workload, lrzip-next {' '.join(flags)}"},
+                             "sample": f"the full workload ({total // MiB} MiB), lrzip-next {' '.join(flags)}, file -> file on tmpfs"},
             "e2e": {"value": v, "unit": "MB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-            "ratio": sample / osz if osz else None})
+            "ratio": total / osz if osz else None, "archive_bytes": osz, "archive_sha256": sha,
+            "step_seconds": times, "wall_s": elapsed()})
         return
 
     import torch
@@ -240,30 +277,28 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     bk = {"none": BACKEND_NONE, "lzma": BACKEND_LZMA, "zstd": BACKEND_ZSTD}[backend]
-    total = size * world
     params = make_params(level=level, backend=bk, threads=threads, window=window, ramsize=ram_units * 100 * 1048576,
                          processors=cores)
     sz = sizing(params, total)
     ctx = Context(local_rank)
 
-    # ---- synthetic input: this rank's window, resident in HBM (16-byte aligned, padded) and pinned on the host
+    # ---- synthetic input: this rank's window in pinned host memory (the C ABI takes host buffers)
     host = gen_input(kind, size, seed_shift=rank)
     pinned = torch.from_numpy(host).pin_memory()
-    dbuf = torch.zeros(size + 8192 + 256, dtype=torch.uint8, device=dev)
-    dbuf[256:256 + size].copy_(pinned)
-    d_in = dbuf.data_ptr() + 256
-    assert d_in % 16 == 0
-    whole_md5 = None
-    if world > 1:  # rank 0 needs the whole file's MD5: collect it once, outside the timed region
-        parts = [torch.empty_like(dbuf[256:256 + size]) for _ in range(world)] if rank == 0 else None
-        dist.gather(dbuf[256:256 + size].contiguous(), parts, dst=0)
+    whole = None
+    if world > 1:
+        # rank 0 plays the process that read the file: it holds all of it on the host, because the trailing
+        # MD5 is over the whole file (src/rzip.c:1195-1218) and is hashed INSIDE every timed step, as at N=1
+        dbuf = pinned.to(dev)
+        parts = [torch.empty_like(dbuf) for _ in range(world)] if rank == 0 else None
+        dist.gather(dbuf, parts, dst=0)
         if rank == 0:
-            h = hashlib.md5()
-            for p_ in parts:
-                h.update(p_.cpu().numpy().tobytes())
-            whole_md5 = h.digest()
-            del parts
+            whole = np.concatenate([p_.cpu().numpy() for p_ in parts])
+        del parts, dbuf
+        torch.cuda.empty_cache()
     plans = multigpu.plan_chunks(total, sz.max_chunk, world) if world > 1 else None
+    if world > 1:
+        assert len(plans) == world and all(p.size == size for p in plans), "one window per GPU expected"
 
     def barrier():
         if world > 1:
@@ -272,67 +307,46 @@ def main():
 
     last = {}
 
-    def step_device():
-        if world == 1:
-            out, ol, st = ctx.compress_device_raw(d_in, size, params)
-            last.update(out_len=ol, stats=st.as_dict())
-            ctx.free(out)
-        else:  # the shard is re-uploaded from the pinned copy by compress_chunk (the chunk ABI takes host data)
-            # text consults the reference's cross-window counter all the time: chain the windows
-            # through it (rzip stages in sequence, backends overlapped); other data speculates and shards freely
-            fn = multigpu.compress_chained if kind == "text" else multigpu.compress_sharded
-            arc, sts = fn(ctx, params, sz, {rank: host}, plans, whole_md5, dev)
-            last.update(out_len=len(arc) if arc is not None else 0, stats=sts[0])
-
-    def step_e2e():
+    def step():
+        """One pass through the public API with host buffers. Returns (copy_ms, kernel_launches) of this rank."""
         if world == 1:
             out, ol, st = ctx.compress_raw(pinned.data_ptr(), size, params)
-            last.update(out_len=ol, stats=st.as_dict())
-            if a.verify:
-                last["sha256"] = hashlib.sha256(C.string_at(out, ol)).hexdigest()
-            ctx.free(out)
-        else:
-            step_device()
+            if last.get("out") is not None:
+                ctx.free(last["out"])
+            last.update(out=out, out_len=ol, stats=st.as_dict())
+            return st.ms_h2d + st.ms_d2h, int(st.kernel_launches)
+        md5_box = {}
+        th = None
+        if rank == 0:
+            th = threading.Thread(target=lambda: md5_box.update(d=hashlib.md5(whole).digest()))
+            th.start()
 
-    def timed(fn, steps):
-        barrier()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        launches0 = 0
-        e0.record()
-        for _ in range(steps):
-            fn()
-            launches0 += int(last["stats"]["kernel_launches"])
-        e1.record()
-        barrier()
-        ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-        return float(ms.item()), launches0
+        def md5():
+            th.join()
+            return md5_box["d"]
+        # text consults the reference's cross-window counter all the time (DESIGN.md 5): the windows' rzip
+        # stages are ordered through it; other data speculates the counter and shards freely
+        fn = multigpu.compress_chained if kind == "text" else multigpu.compress_sharded
+        arc, sts = fn(ctx, params, sz, {rank: pinned}, plans, md5 if rank == 0 else None, dev)
+        last.update(arc=arc, out_len=len(arc) if arc is not None else 0, stats=sts[0])
+        return sum(s["ms_h2d"] + s["ms_d2h"] for s in sts), sum(int(s["kernel_launches"]) for s in sts)
 
-    warm = min(size, WARM_BYTES)
+    # warm-up: the whole single-window path on a prefix, on every rank (no collectives)
+    config["warmup_bytes"] = min(size, WARM_BYTES)
+    warm_params = make_params(level=level, backend=bk, threads=threads, window=0, ramsize=ram_units * 100 * 1048576,
+                              processors=cores)
     for _ in range(a.warmup):
-        out, ol, st = ctx.compress_device_raw(d_in, warm, params)
-        ctx.free(out)
-    sampler = ClockSampler(local_rank)
-    sampler.start()
-    ms, launches = timed(step_device, a.steps)
-    clocks = sampler.stop()
-    value = total * a.steps / (ms / 1e3) / MB
-    out_len = last["out_len"]
-    stats = last["stats"]
+        wout, _, _ = ctx.compress_raw(pinned.data_ptr(), config["warmup_bytes"], warm_params)
+        ctx.free(wout)
 
-    if world == 1:
-        e2e_ms, _ = timed(step_e2e, a.steps)
-    else:
-        # at N > 1 the timed step above already IS the host-buffer path: every rank's window goes through
-        # lrzgpu_compress_chunk from pinned host memory and the blobs come back to the host on rank 0
-        e2e_ms = ms
-    e2e_value = total * a.steps / (e2e_ms / 1e3) / MB
-    e2e_out = last["out_len"]
-
-    # ---- roofline of the dominant HBM kernel of the rzip stage: K1 over the whole window, alone
+    # ---- roofline of the dominant HBM kernel of the rzip stage: K1 over the whole window, alone (before the
+    # long loop, so that the line can be written the moment the loop ends)
     roofline = None
     if rank == 0:
+        dbuf = torch.zeros(size + 8192 + 256, dtype=torch.uint8, device=dev)
+        dbuf[256:256 + size].copy_(pinned)
+        d_in = dbuf.data_ptr() + 256
+        assert d_in % 16 == 0
         rl = params.rzip_level or params.level
         initial_freq = [4, 4, 4, 4, 4, 4, 2, 1, 1, 1][rl]
         tiles = (size + 511) // 512
@@ -365,60 +379,88 @@ def main():
                                f"scaled linearly to this launch")
         roofline = {"kernel": "k1_tagscan_kernel", "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s",
                     "frac": ach / peak, "traffic": traffic, "traffic_source": traffic_src, "peak_source": how,
-                    "ms_per_launch": k1_ms,
-                    "algorithmic_bytes_per_launch": alg,
+                    "ms_per_launch": k1_ms, "algorithmic_bytes_per_launch": alg,
                     "note": "K2 commit / LZMA block encoders are serial, latency-bound stages: no roofline fraction"}
-        del cand, tcnt
+        del cand, tcnt, dbuf
+        torch.cuda.empty_cache()
 
     cpu_baseline = None
     if rank == 0 and world == 1 and not a.no_cpu_baseline:
-        sample = min(size, cpu_sample_bytes(backend, cores))
-        flags = ref_flags(backend, level, threads, ram_units)
-        dt, osz = run_reference(host[:sample], flags)
-        if dt is not None:
-            cpu_baseline = {"value": sample / dt / MB, "unit": "MB/s", "cores": min(threads, cores), "kind": "reference",
-                            "sample": f"first {sample >> 20} MiB of the workload, one run of lrzip-next {' '.join(flags)} on tmpfs",
-                            "ratio": sample / osz}
+        rr = RefRunner()
+        if rr.available():
+            try:
+                # ~10-30 s of reference CPU work: rzip-only runs at 10-150 MB/s on one thread, lzma level 7 at
+                # roughly 1.5 MB/s per core; at least one 10 MiB stream block per core
+                sample = min(size, 256 * MiB if backend == "none" else max(64 * MiB, min(cores, 24) * 10 * MiB))
+                flags = ref_flags(backend, level, threads, ram_units)
+                dt, dst = rr.run(rr.put("sample.bin", host[:sample]), flags)
+                cpu_baseline = {"value": sample / dt / MB, "unit": "MB/s", "cores": min(threads, cores), "kind": "reference",
+                                "sample": f"first {sample // MiB} MiB of the workload, one run of lrzip-next {' '.join(flags)} "
+                                          f"on tmpfs (the --impl reference arm runs the full workload)",
+                                "ratio": sample / os.path.getsize(dst)}
+            finally:
+                rr.close()
         else:
             cpu_baseline = {"value": None, "unit": "MB/s", "cores": 0, "kind": "reference",
                             "sample": "oracle/_ref/lrzip-next not built"}
 
-    verified = None
-    if a.verify and rank == 0 and world == 1 and "sha256" in last:
-        ref = os.path.join(ROOT, "oracle", "_ref", "lrzip-next")
-        d = tempfile.mkdtemp(dir="/dev/shm" if os.path.isdir("/dev/shm") else None)
-        src, dst = os.path.join(d, "in.bin"), os.path.join(d, "out.lrz")
-        try:
-            host.tofile(src)
-            t0 = time.perf_counter()
-            subprocess.run([ref, *ref_flags(backend, level, threads, ram_units), "-o", dst, src], check=True,
-                           env=dict(os.environ, LRZIP="NOCONFIG"), stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
-            ref_s = time.perf_counter() - t0
-            hsh = hashlib.sha256()
-            with open(dst, "rb") as fh:
-                for blk in iter(lambda: fh.read(1 << 24), b""):
-                    hsh.update(blk)
-            verified = {"identical_to_reference": hsh.hexdigest() == last["sha256"], "sha256": last["sha256"],
-                        "reference_seconds_full_workload": ref_s, "reference_MBps_full_workload": size / ref_s / MB}
-        finally:
-            for f in (src, dst):
-                if os.path.exists(f):
-                    os.unlink(f)
-            os.rmdir(d)
+    # ---- the timed loop: full-size steps until --steps are done or the budget is spent
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    step_ms, copy_ms, launches = [], 0.0, 0
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    t_loop = time.perf_counter()
+    while len(step_ms) < a.steps:
+        t0 = time.perf_counter()
+        cm, nl = step()
+        copy_ms += cm
+        launches += nl
+        step_ms.append(1e3 * (time.perf_counter() - t0))
+        # every rank must take the same decision: the slowest rank's clock decides
+        proj = torch.tensor([elapsed() + max(step_ms) / 1e3], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(proj, op=dist.ReduceOp.MAX)
+        if float(proj.item()) > a.budget_s:
+            break
+    e1.record()
+    barrier()
+    ms = torch.tensor([e0.elapsed_time(e1), e0.elapsed_time(e1) - copy_ms], dtype=torch.float64, device=dev)
+    cnt = torch.tensor([launches], dtype=torch.int64, device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
+    clocks = sampler.stop()
+    nsteps = len(step_ms)
+    e2e_ms, dev_ms = float(ms[0].item()), float(ms[1].item())
+    e2e_value = total * nsteps / (e2e_ms / 1e3) / MB
+    value = total * nsteps / (dev_ms / 1e3) / MB
+    out_len = last["out_len"]
+    stats = last["stats"]
 
     if rank == 0:
+        if world == 1:
+            import ctypes as C
+            sha = hashlib.sha256(C.string_at(last["out"], out_len)).hexdigest()
+        else:
+            sha = hashlib.sha256(last["arc"]).hexdigest()
         emit({
-            "verified": verified,
-            "metric": "compress MB/s (input bytes)", "value": value, "unit": "MB/s", "n_gpus": world, "steps": a.steps,
-            "warmup": a.warmup, "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "u8", "data": "synthetic", "config": config, "clocks": clocks,
-            "e2e": {"value": e2e_value, "unit": "MB/s", "h2d_bytes_per_step": total, "d2h_bytes_per_step": int(e2e_out),
-                    "ms_per_step": e2e_ms / a.steps},
-            "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu_baseline,
-            "ratio": total / out_len if out_len else None, "archive_bytes": int(out_len),
+            "metric": "compress MB/s (input bytes)", "value": value, "unit": "MB/s", "n_gpus": world, "steps": nsteps,
+            "steps_requested": a.steps, "warmup": a.warmup, "ms_per_step": e2e_ms / nsteps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic", "config": config, "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": "MB/s", "h2d_bytes_per_step": total, "d2h_bytes_per_step": int(out_len),
+                    "ms_per_step": e2e_ms / nsteps},
+            "value_note": "the e2e loop with the library-measured H2D/D2H copy time removed "
+                          f"({copy_ms / nsteps:.0f} ms per step on rank 0)",
+            "gpu_launches": int(cnt.item()), "roofline": roofline, "cpu_baseline": cpu_baseline,
+            "ratio": total / out_len if out_len else None, "archive_bytes": int(out_len), "archive_sha256": sha,
+            "step_ms": step_ms, "wall_s": elapsed(),
             "stage_ms": {k: stats[k] for k in ("ms_h2d", "ms_rzip", "ms_emit", "ms_backend", "ms_d2h", "ms_md5", "ms_total")},
-            "rzip": {k: stats[k] for k in ("matches", "match_bytes", "literals", "literal_bytes", "inserts", "lookups", "chain_evictions", "sweeps")},
+            "rzip": {k: stats[k] for k in ("matches", "match_bytes", "literals", "literal_bytes", "inserts", "lookups",
+                                           "chain_evictions", "sweeps")},
             "block_size": int(sz.bufsize), "blocks": int(stats["blocks"]), "blocks_stored": int(stats["blocks_stored"]),
+            "zstd_parity": "unpinned" if backend == "zstd" else None,
         })
     ctx.close()
     if world > 1:

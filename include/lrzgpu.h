@@ -61,10 +61,11 @@ typedef struct lrzgpu_params {
 	int window;       /* -w, units of 100 MiB, 0 = unset */
 	int unlimited;    /* -U */
 	int64_t ramsize;  /* control->ramsize in bytes (-m N  => N * 100 MiB) */
-	int page_size;    /* control->page_size, 4096 */
+	int page_size;    /* control->page_size, 4096 (must be a multiple of 16) */
 	int processors;   /* sysconf(_SC_NPROCESSORS_ONLN) of the machine being reproduced */
 	int threshold;    /* lz4 gate: 0 = off (-T), else percent (default 100) */
-	int nobemt;       /* --nobemt (does not change bytes; kept for symmetry) */
+	int nobemt;       /* --nobemt: with LZMA level >= 5 and threads > 1 the reference switches to the single-threaded
+			     bt4 finder (src/stream.c:456); not reproduced => LRZGPU_EUNSUPPORTED */
 } lrzgpu_params;
 
 typedef struct lrzgpu_sizing_t {

@@ -66,6 +66,14 @@ int compute_sizing(const lrzgpu_params &p, int64_t st_size, lrzgpu_sizing_t &o)
 	if (p.level < 1 || p.level > 9 || p.rzip_level < 0 || p.rzip_level > 9 || p.page_size <= 0 || p.threads < 1 ||
 	    p.ramsize <= 0)
 		return LRZGPU_EINVAL;
+	// windows after the first start at multiples of max_chunk, which is only rounded to page_size: the tag scan's
+	// TMA loads (cp.async.bulk) need 16-byte aligned sources, so the page must keep that alignment
+	if (p.page_size % 16)
+		return LRZGPU_EINVAL;
+	// --nobemt with more than one thread selects the single-threaded bt4 finder (numThreads = 1, src/stream.c:456),
+	// whose hash2/hash3 handling differs from the two-thread finder this library reproduces
+	if (p.nobemt && p.backend == LRZGPU_BACKEND_LZMA && p.level >= 5 && p.threads > 1)
+		return LRZGPU_EUNSUPPORTED;
 	if (p.backend != LRZGPU_BACKEND_NONE && p.backend != LRZGPU_BACKEND_LZMA && p.backend != LRZGPU_BACKEND_ZSTD)
 		return LRZGPU_EUNSUPPORTED;
 	const bool stored = p.backend == LRZGPU_BACKEND_NONE, lzma = p.backend == LRZGPU_BACKEND_LZMA;

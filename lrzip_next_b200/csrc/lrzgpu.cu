@@ -543,8 +543,12 @@ int lrzgpu_compress_device(lrzgpu_ctx *c, const lrzgpu_params *p, const void *d_
 			for (int i = 0; i < 2; i++) {
 				if (c->h_pin[i])
 					cudaFreeHost(c->h_pin[i]);
-				if (cudaHostAlloc((void **)&c->h_pin[i], slice, cudaHostAllocDefault) != cudaSuccess)
+				c->h_pin[i] = nullptr;
+				c->h_pin_cap = 0;
+				if (cudaHostAlloc((void **)&c->h_pin[i], slice, cudaHostAllocDefault) != cudaSuccess) {
+					c->h_pin[i] = nullptr;
 					return fail(c, LRZGPU_ENOMEM, "pinned staging allocation failed");
+				}
 			}
 			c->h_pin_cap = slice;
 		}

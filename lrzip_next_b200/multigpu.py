@@ -130,17 +130,28 @@ def assemble(params: Params, sz: Sizing, st_size: int, blobs: dict[int, bytes], 
     return make_magic(params, sz, st_size) + b"".join(blobs[i] for i in sorted(blobs)) + md5
 
 
+def _resolve_md5(whole_md5) -> bytes:
+    """The trailing MD5 is over the whole file (src/rzip.c:1195-1218) and MD5 states do not combine, so rank 0
+    must be given it: either the 16 bytes or a callable producing them (e.g. the join of a hashing thread)."""
+    md5 = whole_md5() if callable(whole_md5) else whole_md5
+    if not isinstance(md5, (bytes, bytearray)) or len(md5) != 16:
+        raise ValueError("rank 0 needs the whole file's 16-byte MD5 (bytes or a callable returning them)")
+    return bytes(md5)
+
+
 def compress_sharded(ctx, params: Params, sz: Sizing, shards: dict[int, np.ndarray], plans: list[ChunkPlan],
                      whole_md5: bytes | None = None, device: torch.device | None = None):
     """Compress this rank's chunks (``shards``: chunk index -> bytes), settle victim_round, gather.
     Returns (archive or None, per-rank stats list)."""
     rank, world = dist.get_rank(), dist.get_world_size()
     mine = [p for p in plans if p.rank == rank]
-    blobs, reports, stats = {}, {}, []
+    if rank == 0 and whole_md5 is None:
+        raise ValueError("rank 0 needs the whole file's MD5")
+    blobs, reports, stats_by = {}, {}, {}
     for p in mine:
         blob, vr_out, st = ctx.compress_chunk(shards[p.index], params, sz, p.eof, 0)
         blobs[p.index], reports[p.index] = blob, (0, st["chain_evictions"], vr_out)
-        stats.append(st)
+        stats_by[p.index] = st
     # settle the victim_round chain (a few integers per chunk; gloo/nccl all_gather_object)
     while True:
         allrep: list = [None] * world
@@ -157,11 +168,12 @@ def compress_sharded(ctx, params: Params, sz: Sizing, shards: dict[int, np.ndarr
             vin = true_incoming(ordered, i)
             blob, vr_out, st = ctx.compress_chunk(shards[i], params, sz, plans[i].eof, vin)
             blobs[i], reports[i] = blob, (vin, st["chain_evictions"], vr_out)
+            stats_by[i] = st  # the redone chunk's counters replace the speculative ones
+    stats = [stats_by[i] for i in sorted(stats_by)]
     got = gather_blobs(blobs, device)
     if rank != 0:
         return None, stats
-    md5 = whole_md5 if whole_md5 is not None else hashlib.md5(b"").digest()
-    return assemble(params, sz, sum(p.size for p in plans), got, md5), stats
+    return assemble(params, sz, sum(p.size for p in plans), got, _resolve_md5(whole_md5)), stats
 
 
 _chain_calls = 0
@@ -178,6 +190,8 @@ def compress_chained(ctx, params: Params, sz: Sizing, shards: dict[int, np.ndarr
     Returns (archive or None, per-rank stats list)."""
     global _chain_calls
     rank, world = dist.get_rank(), dist.get_world_size()
+    if rank == 0 and whole_md5 is None:
+        raise ValueError("rank 0 needs the whole file's MD5")
     device = device or torch.device("cpu")
     # The counter (one small integer per chunk) travels through the process group's key-value store: plain
     # TCP, the same under nccl and gloo, no device work and no pairing rules to get wrong.  Every rank makes
@@ -210,5 +224,4 @@ def compress_chained(ctx, params: Params, sz: Sizing, shards: dict[int, np.ndarr
     got = gather_blobs(blobs, device)
     if rank != 0:
         return None, stats
-    md5 = whole_md5 if whole_md5 is not None else hashlib.md5(b"").digest()
-    return assemble(params, sz, sum(p.size for p in plans), got, md5), stats
+    return assemble(params, sz, sum(p.size for p in plans), got, _resolve_md5(whole_md5)), stats

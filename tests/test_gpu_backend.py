@@ -57,6 +57,9 @@ def test_lzma_block_bit_exact(ctx, level, dict_size):
     ("mix", 2_000_000, dict(threads=8)),
     ("trees", 3_000_000, dict(threads=2, level=5)),
     ("text", 2_000_000, dict(threads=4, level=3)),
+    # several LZMA blocks per stream (block waves, flush order, next_head patching over compressed blocks):
+    # -p8 on 45 MiB gives the 10 MiB minimum block => 5 stream-1 blocks
+    ("text", 45 << 20, dict(threads=8)),
 ])
 def test_lzma_archive_bit_identical_to_reference(ctx, kind, n, kw):
     d = datagen.generate(kind, n)

@@ -83,8 +83,13 @@ def test_rzip_victim_round_carried(ctx):
 
 @pytest.mark.parametrize("kind,n,kw", [
     ("rep", 12 << 20, {}), ("text", 5 << 20, {}), ("mix", 8 << 20, {}),
-    ("text", 30 << 20, dict(window=1, ramsize=3 * 100 * 1048576)),   # several chunks (windows)
+    ("text", 30 << 20, dict(window=1, ramsize=3 * 100 * 1048576)),   # -w1 = 100 MiB window: still ONE chunk
     ("vm", 25 << 20, dict(level=9)),
+    # several chunks (victim_round carried between them, eof only on the last) and several blocks per stream
+    # (flush order, next_head patching); each has an oracle-vs-reference-binary twin in tests/test_oracle.py
+    ("text", 250 << 20, dict(window=1)),                              # 3 chunks of 100 / 100 / 50 MiB
+    ("text", 80 << 20, dict(ramsize=100 * 1048576)),                  # 2 chunks x 3 blocks of 33.3 MiB
+    ("mix", 70 << 20, dict(ramsize=30 * 1048576)),                    # 4 chunks of 20 MiB x 2 blocks of 10 MiB
 ])
 def test_archive_stored_bit_identical_to_oracle(ctx, kind, n, kw):
     d = datagen.generate(kind, n)
@@ -94,6 +99,45 @@ def test_archive_stored_bit_identical_to_oracle(ctx, kind, n, kw):
     got = ctx.compress(d, p)
     assert len(got) == len(want) and _first_diff(got, want) is None, _first_diff(got, want)
     assert got[-16:] == hashlib.md5(d.tobytes()).digest()
+
+
+def test_rzip_chunk_bytes_5_forced(ctx):
+    """chunk_bytes = 5 (files >= 2^32, C3/C4/C5; src/rzip.c:1129-1133) forced on a small chunk: 5-byte match
+    distances in stream 0."""
+    d = np.concatenate([datagen.generate("text", 600_000), datagen.generate("rep", 400_000, block=1 << 15)])
+    o0, o1, ost, _ = oracle.rzip_chunk(d, 7, chunk_bytes=5)
+    s0, s1, st, _ = ctx.rzip_chunk(d, 7, chunk_bytes=5)
+    assert (s0, s1) == (o0, o1)
+    o4, _, _, _ = oracle.rzip_chunk(d, 7, chunk_bytes=4)
+    assert len(s0) == len(o4) + st["matches"]  # one more distance byte per match record
+
+
+def test_c1_full_size_appendix_f_facts(ctx):
+    """BASELINE config C1 at its stated size: 100 MiB of a repeated 1 MiB block, -n -p1.  SURVEY.md Appendix F
+    records what the reference produces: 1,059,858 bytes, 1585 matches, MD5 535d79..."""
+    d = datagen.gen_rep(100 << 20)
+    got, st = ctx.compress(d, make_params(backend=BACKEND_NONE, threads=1), want_stats=True)
+    assert len(got) == 1_059_858
+    assert (st["matches"], st["match_bytes"], st["literals"], st["literal_bytes"], st["inserts"]) == \
+           (1585, 103_808_993, 19, 1_048_607, 524_840)
+    assert got[-16:].hex() == "535d792a42ccc7c552714d2a97bf158f"
+    want, _ = oracle.compress(d, oracle.make_params(backend=oracle.BACKEND_NONE, threads=1))
+    assert got == want
+
+
+def test_compress_file_equals_compress(ctx, tmp_path):
+    """lrzgpu_compress_file (the B1 seam: rzip_fd + write_magic, file -> file) writes the bytes lrzgpu_compress returns."""
+    d = np.concatenate([datagen.generate("text", 2_500_000), datagen.generate("rep", 1_500_000, block=1 << 16)])
+    src, dst = tmp_path / "in.bin", tmp_path / "out.lrz"
+    d.tofile(src)
+    p = make_params(backend=BACKEND_NONE, threads=1)
+    st = ctx.compress_file(str(src), str(dst), p)
+    got = dst.read_bytes()
+    assert got == ctx.compress(d, p)
+    assert got == oracle.compress(d, oracle.make_params(backend=oracle.BACKEND_NONE, threads=1))[0]
+    assert st["chunks"] == 1 and st["stream1_bytes"] > 0
+    with pytest.raises(Exception):
+        ctx.compress_file(str(tmp_path / "missing.bin"), str(dst), p)
 
 
 @pytest.mark.skipif(not oracle.have_ref(), reason="compiled reference (oracle/_ref) not present")

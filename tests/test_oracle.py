@@ -39,6 +39,10 @@ def test_oracle_archive_matches_golden(name):
 @pytest.mark.parametrize("kind,n,kw", [
     ("text", 3 << 20, dict(level=3)), ("trees", 5 << 20, dict(level=9)), ("randzero", 2 << 20, dict(level=1)),
     ("text", 9 << 20, dict(window=1, ramsize=100 * 1048576 * 2)), ("rep", 70_000, {}), ("text", 31, {}), ("text", 4096, {}),
+    # twins of the multi-chunk / multi-block GPU cases (tests/test_gpu_rzip.py): victim_round carried between
+    # chunks, eof on the last chunk only, flush order and next_head patching over several blocks per stream
+    ("text", 250 << 20, dict(window=1)),              # 3 chunks of 100 / 100 / 50 MiB
+    ("text", 80 << 20, dict(ramsize=100 * 1048576)),  # 2 chunks x 3 blocks
 ])
 def test_oracle_equals_reference_binary_stored(kind, n, kw):
     d = datagen.generate(kind, n)
