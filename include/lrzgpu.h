@@ -12,6 +12,8 @@
  *   lrzgpu_compress_chunk               one pass of the chunk loop src/rzip.c:1041-1186
  *   lrzgpu_chunk_begin / _finish        (rzip_chunk :873 + close_stream_out, src/stream.c:2253); the two-call form
  *                                       splits it at the point where rzip_chunk returns
+ *   lrzgpu_chunk_begin_all / _select    the same window for every value of insert_hash()'s static victim_round
+ *                                       (src/rzip.c:308), so that windows need not wait for their predecessor
  *   lrzgpu_rzip_chunk                   hash_search()        src/rzip.c:586 with the scan primitives
  *                                       full_tag/next_tag/match_len, lrzip_private.h:573-576
  *   lrzgpu_tag_scan                     single_full_tag()/single_next_tag()  src/rzip.c:385-416
@@ -128,6 +130,19 @@ int lrzgpu_compress_chunk(lrzgpu_ctx *ctx, const lrzgpu_params *p, const lrzgpu_
 int lrzgpu_chunk_begin(lrzgpu_ctx *ctx, const lrzgpu_params *p, const lrzgpu_sizing_t *sz, const uint8_t *in, int64_t n,
 		       int eof, int64_t *victim_round, lrzgpu_stats *stats);
 int lrzgpu_chunk_finish(lrzgpu_ctx *ctx, uint8_t **blob, int64_t *blob_len, lrzgpu_stats *stats);
+
+/* All-values speculation of the cross-window counter, so that the windows of one file are independent and can
+ * run on different GPUs at the same time.  insert_hash()'s function-static victim_round (src/rzip.c:308, 332-343)
+ * is the only state that leaks from one window into the next, and it takes max_chain_len values
+ * (lrzgpu_victim_values(): 16 at rzip level 7).  The commit stage of a window occupies one SM of 148, so
+ * _begin_all runs the window once per possible incoming value, concurrently, and reports victim_out[v] = the
+ * counter after the window when it started at v.  Once the true incoming value is known (from the predecessor's
+ * table: v_i = victim_out_{i-1}[v_{i-1}], v_0 = 0), _select emits the streams of that variant and
+ * lrzgpu_chunk_finish() produces the blob -- byte-identical to lrzgpu_compress_chunk(victim_round = v). */
+int lrzgpu_victim_values(const lrzgpu_params *p);
+int lrzgpu_chunk_begin_all(lrzgpu_ctx *ctx, const lrzgpu_params *p, const lrzgpu_sizing_t *sz, const uint8_t *in, int64_t n,
+			   int eof, int64_t *victim_out, int nvalues, lrzgpu_stats *stats);
+int lrzgpu_chunk_select(lrzgpu_ctx *ctx, int64_t victim_in, lrzgpu_stats *stats);
 
 /* rzip of one chunk -> stream 0 / stream 1 bytes (malloc'ed). */
 int lrzgpu_rzip_chunk(lrzgpu_ctx *ctx, const uint8_t *in, int64_t n, int rzip_level, int chunk_bytes,

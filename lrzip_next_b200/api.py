@@ -69,7 +69,7 @@ _lib = None
 EXPORTS = [
     "lrzgpu_create", "lrzgpu_destroy", "lrzgpu_last_error", "lrzgpu_free", "lrzgpu_version", "lrzgpu_sizing",
     "lrzgpu_compress", "lrzgpu_compress_file", "lrzgpu_compress_device", "lrzgpu_compress_chunk",
-    "lrzgpu_chunk_begin", "lrzgpu_chunk_finish",
+    "lrzgpu_chunk_begin", "lrzgpu_chunk_finish", "lrzgpu_victim_values", "lrzgpu_chunk_begin_all", "lrzgpu_chunk_select",
     "lrzgpu_rzip_chunk", "lrzgpu_tag_scan", "lrzgpu_crc32", "lrzgpu_block_compress", "lrzgpu_lz4_gate",
     "lrzgpu_k1_launch", "lrzgpu_crc32_launch", "lrzgpu_sm_count",
 ]
@@ -101,6 +101,10 @@ def load_library():
                                         C.POINTER(Stats)]
     L.lrzgpu_chunk_begin.argtypes = [vp, C.POINTER(Params), C.POINTER(Sizing), vp, i64, C.c_int, pi64, C.POINTER(Stats)]
     L.lrzgpu_chunk_finish.argtypes = [vp, pvp, pi64, C.POINTER(Stats)]
+    L.lrzgpu_victim_values.argtypes = [C.POINTER(Params)]
+    L.lrzgpu_chunk_begin_all.argtypes = [vp, C.POINTER(Params), C.POINTER(Sizing), vp, i64, C.c_int, pi64, C.c_int,
+                                         C.POINTER(Stats)]
+    L.lrzgpu_chunk_select.argtypes = [vp, i64, C.POINTER(Stats)]
     L.lrzgpu_rzip_chunk.argtypes = [vp, vp, i64, C.c_int, C.c_int, pi64, pvp, pi64, pvp, pi64, C.POINTER(Stats)]
     L.lrzgpu_tag_scan.argtypes = [vp, vp, i64, i64, i64, i64, vp, vp, i64, pi64]
     L.lrzgpu_crc32.argtypes = [vp, vp, i64, C.POINTER(C.c_uint32)]
@@ -119,6 +123,11 @@ def sizing(params: Params, st_size: int) -> Sizing:
     if rc:
         raise LrzGpuError(rc, "lrzgpu_sizing rejected the parameters")
     return s
+
+
+def victim_values(params: Params) -> int:
+    """Number of values the reference's cross-window counter can take (max_chain_len of the rzip level)."""
+    return load_library().lrzgpu_victim_values(C.byref(params))
 
 
 def chunk_bytes_for(n: int) -> int:
@@ -230,6 +239,23 @@ class Context:
         self._check(self._L.lrzgpu_chunk_begin(self._h, C.byref(params), C.byref(sz), addr, n, int(eof), C.byref(vr),
                                                C.byref(st)))
         return vr.value, st.as_dict()
+
+    def chunk_begin_all(self, data, params: Params, sz: Sizing, eof: bool):
+        """rzip stage of one window for EVERY incoming victim_round value at once -> (victim_out list, stats):
+        victim_out[v] is the counter after the window when it started at v.  chunk_select(v) then picks one."""
+        addr, n, keep = _ptr(data)
+        nv = victim_values(params)
+        out = (C.c_int64 * nv)()
+        st = Stats()
+        self._check(self._L.lrzgpu_chunk_begin_all(self._h, C.byref(params), C.byref(sz), addr, n, int(eof), out, nv,
+                                                   C.byref(st)))
+        return list(out), st.as_dict()
+
+    def chunk_select(self, victim_in: int) -> dict:
+        """Emit the streams of the variant that started from `victim_in`; chunk_finish() follows."""
+        st = Stats()
+        self._check(self._L.lrzgpu_chunk_select(self._h, victim_in, C.byref(st)))
+        return st.as_dict()
 
     def chunk_finish(self):
         """backend + framing of the pending window -> (blob, stats)."""

@@ -127,7 +127,7 @@ __device__ __forceinline__ uint32_t k1_phase_b(const uint64_t *__restrict__ z, i
 
 __global__ void __launch_bounds__(K1_THREADS, 3)
 k1_tagscan_kernel(const uint8_t *__restrict__ buf, int64_t n, int64_t pos_lo, int64_t pos_hi, int64_t mask_arg,
-		  const ScanState *__restrict__ state, Cand *__restrict__ cand, uint32_t *__restrict__ tile_count,
+		  const ScanState *__restrict__ state, int nstates, Cand *__restrict__ cand, uint32_t *__restrict__ tile_count,
 		  int64_t first_tile, int64_t num_tiles, int64_t first_step, int64_t num_steps)
 {
 	extern __shared__ __align__(128) uint8_t smem[];
@@ -140,8 +140,17 @@ k1_tagscan_kernel(const uint8_t *__restrict__ buf, int64_t n, int64_t pos_lo, in
 
 	int64_t mask = mask_arg;
 	if (state) {
-		mask = state->min_mask;
-		if (state->scan_pos + 1 >= pos_hi) { // the scan already jumped past this segment
+		// several scan states = the variants of one window run for every incoming victim_round value
+		// (all-values speculation): the loosest gate of them decides what is a candidate (gates are nested
+		// 2^b - 1 masks, so AND gives the loosest), each commit filters by its own gate again
+		mask = state[0].min_mask;
+		int64_t least = state[0].scan_pos;
+		for (int v = 1; v < nstates; v++) {
+			mask &= state[v].min_mask;
+			if (state[v].scan_pos < least)
+				least = state[v].scan_pos;
+		}
+		if (least + 1 >= pos_hi) { // every scan already jumped past this segment
 			for (int64_t t = blockIdx.x * (int64_t)K1_THREADS + tid; t < num_tiles; t += (int64_t)gridDim.x * K1_THREADS)
 				tile_count[t] = 0;
 			return;
@@ -247,7 +256,7 @@ int k1_init_tables()
 }
 
 int k1_launch(const uint8_t *d_buf, int64_t n, int64_t pos_lo, int64_t pos_hi, int64_t mask,
-	      const ScanState *d_state, Cand *d_cand, uint32_t *d_tile_count, int num_sms, cudaStream_t stream)
+	      const ScanState *d_state, int nstates, Cand *d_cand, uint32_t *d_tile_count, int num_sms, cudaStream_t stream)
 {
 	if (pos_hi <= pos_lo)
 		return 0;
@@ -260,7 +269,7 @@ int k1_launch(const uint8_t *d_buf, int64_t n, int64_t pos_lo, int64_t pos_hi, i
 	if (grid > num_steps)
 		grid = num_steps;
 	k1_tagscan_kernel<<<(unsigned)grid, K1_THREADS, K1_SMEM, stream>>>(
-		d_buf, n, pos_lo, pos_hi, mask, d_state, d_cand, d_tile_count, first_tile, num_tiles, first_step, num_steps);
+		d_buf, n, pos_lo, pos_hi, mask, d_state, nstates, d_cand, d_tile_count, first_tile, num_tiles, first_step, num_steps);
 	return cudaGetLastError() == cudaSuccess ? 0 : -1;
 }
 

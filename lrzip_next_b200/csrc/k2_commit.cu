@@ -379,6 +379,7 @@ struct LaneEval {
 	long long wtag[K2_MAXW], woff[K2_MAXW];
 	unsigned rlo[K2_MAXW], rlen[K2_MAXW]; // probe ranges read (start slot, length), modulo the table size
 	int nw, nr, net, ins, miss;
+	int chain; // the insert met max_chain_len equal-tag entries: the victim slot is chosen at commit time (eslot[])
 	bool cx;
 };
 
@@ -391,6 +392,7 @@ struct FastShared {
 	unsigned vslot[32 * (K2_MAXW + 1)]; // validation: slots written by the batch, in lane order ...
 	unsigned char vown[32 * (K2_MAXW + 1)]; // ... and the lane that writes each
 	long long eq_off[8][4][K2_MAXEQ]; // per warp and group: offsets of the equal-tag entries met on the walk
+	unsigned eslot[32][K2_MAXEQ];     // per candidate: the slots of those entries, in walk order (chain-cap victims)
 	// batch evaluation command, written by the commit warp before barrier 1 (see k2_eval_worker)
 	long long cmd_tag_mask, cmd_better, cmd_end, cmd_last_match;
 	int cmd_nb, cmd_max_chain, cmd_exit, cmd_mode;
@@ -738,9 +740,15 @@ __device__ void group_eval_t(const uint8_t *__restrict__ buf, const HEntry *tab,
 				if (!stop) {
 					const unsigned before = valid & low_mask(fs);
 					round += __popc(qm & before);
-					if (round >= max_chain)
-						cx = true; // chain cap: victim_round logic stays serial
-					if (sc) {
+					if (round >= max_chain) {
+						// chain cap (src/rzip.c:332-343): the max_chain_len-th equal-tag entry comes before any
+						// empty / due / lesser slot.  The insert replaces the victim_round-th of them; which one
+						// is only known at commit time (rank among the evicting candidates of the batch).
+						stop = true;
+						kind = kProbeChain;
+						if (max_chain > K2_MAXEQ)
+							cx = true;
+					} else if (sc) {
 						stop = true;
 						sslot = (h + s + (unsigned)fs) & hmask;
 						kind = ((dm >> fs) & 1) ? kProbeDue : kProbeDisplace;
@@ -755,8 +763,10 @@ __device__ void group_eval_t(const uint8_t *__restrict__ buf, const HEntry *tab,
 				if (neq + __popc(eqv) > K2_MAXEQ)
 					cx = true;
 				else {
-					if ((eqv >> gl) & 1)
+					if ((eqv >> gl) & 1) {
 						eq_list[neq + __popc(eqv & ltg)] = e.offset;
+						sh->eslot[cand_idx][neq + __popc(eqv & ltg)] = (h + s + (unsigned)gl) & hmask;
+					}
 					neq += __popc(eqv);
 				}
 				if (em) {
@@ -904,6 +914,7 @@ __device__ void group_eval_t(const uint8_t *__restrict__ buf, const HEntry *tab,
 		R->net = cx ? 0 : net;
 		R->ins = ins;
 		R->miss = miss;
+		R->chain = (!cx && ins && nw == 1 && kind == kProbeChain) ? 1 : 0;
 		R->cx = cx;
 	}
 	__syncwarp();
@@ -924,18 +935,6 @@ __device__ void k2_eval_share(const uint8_t *__restrict__ buf, const HEntry *tab
 		group_eval_t<8, 4>(buf, tab, hmask, sh, c, tag_mask, better, max_chain, end, last_match, lane, warp);
 	else
 		group_eval_t<8, 8>(buf, tab, hmask, sh, c, tag_mask, better, max_chain, end, last_match, lane, warp);
-}
-
-// One candidate, by the calling warp alone (re-evaluation on the updated table).
-__device__ void k2_eval_one(const uint8_t *__restrict__ buf, const HEntry *tab, unsigned hmask, FastShared *sh, int k, int mode,
-			    int64_t tag_mask, int64_t better, int max_chain, int64_t end, int64_t last_match, int lane)
-{
-	if (mode == K2_MODE_NARROW)
-		group_eval_t<8, 1>(buf, tab, hmask, sh, lane < 8 ? k : -1, tag_mask, better, max_chain, end, last_match, lane, 0);
-	else if (mode == K2_MODE_WIDE2)
-		group_eval_t<32, 2>(buf, tab, hmask, sh, k, tag_mask, better, max_chain, end, last_match, lane, 0);
-	else
-		group_eval_t<32, 8>(buf, tab, hmask, sh, k, tag_mask, better, max_chain, end, last_match, lane, 0);
 }
 
 // Warps 1..7 of the commit CTA: evaluate candidates 4*warp .. 4*warp+3 of every batch the commit warp queues.
@@ -974,7 +973,7 @@ __device__ void k2_commit_segment_batched(WarpPrim &prim, FastShared *sh, ScanSt
 	int qn = 0;
 	bool list_done = false, again = false;
 	int64_t again_p = 0, again_t = 0;
-	int64_t n_disp = 0;
+	int64_t n_disp = 0, n_evict = 0;
 	int64_t dbg[16] = { 0 };
 	const long long clk_start = clock64();
 
@@ -1090,7 +1089,7 @@ __device__ void k2_commit_segment_batched(WarpPrim &prim, FastShared *sh, ScanSt
 		}
 		const int mode = k2_mode_for(r.tag_mask);
 		LaneEval L;
-		L.nw = L.nr = L.net = L.ins = L.miss = 0;
+		L.nw = L.nr = L.net = L.ins = L.miss = L.chain = 0;
 		L.cx = false;
 		int64_t myp = 0, myt = 0;
 		dbg[0]++;
@@ -1130,7 +1129,7 @@ __device__ void k2_commit_segment_batched(WarpPrim &prim, FastShared *sh, ScanSt
 				if (L2.cx)
 					L2.net = 0;
 				if (L.cx != L2.cx)
-					bad = !L.cx; // the cooperative form may only be stricter
+					bad = !L.cx && !L.chain; // the cooperative form may only be stricter (chain caps: decided at commit)
 				else if (!L.cx) {
 					bad = L.nw != L2.nw || L.nr != L2.nr || L.net != L2.net || L.ins != L2.ins || L.miss != L2.miss;
 					for (int w = 0; w < L.nw && !bad; w++)
@@ -1168,6 +1167,16 @@ __device__ void k2_commit_segment_batched(WarpPrim &prim, FastShared *sh, ScanSt
 		dbg[8] += clock64() - ce0;
 		if (L.cx)
 			L.net = 0;
+		// chain-cap evictions (src/rzip.c:332-343) inside the batch: every evicting candidate advances the
+		// reference's round-robin counter by one, so the k-th evicting lane of the batch sees
+		// victim_round + k and replaces that one of the max_chain_len equal-tag entries its walk recorded.
+		// Lanes commit as a prefix, so every evicting lane before a committing lane commits as well.
+		const bool evict = lane < nb && !L.cx && L.chain != 0;
+		const unsigned evm = __ballot_sync(FULL, evict);
+		if (evict) {
+			const int vi = (int)((r.victim_round + __popc(evm & lt)) % c.max_chain);
+			L.wslot[0] = sh->eslot[lane][vi];
+		}
 		const long long cs0 = clock64();
 		// sweep deletions (clean_one_from_hash): the k-th insert that overfills the table removes the
 		// k-th entry, in table order from tag_clean_ptr, that lacks the next-stricter mask
@@ -1178,20 +1187,29 @@ __device__ void k2_commit_segment_batched(WarpPrim &prim, FastShared *sh, ScanSt
 		int found = 0;
 		unsigned dmax = 0;
 		if (ncl) {
-			for (int64_t cp = r.clean_ptr; found < ncl && cp < tsize; cp += 32) {
-				const int64_t k = cp + lane;
-				bool q = false;
-				if (k < tsize) {
-					const HEntry e = ld_entry(prim.tab + k);
-					q = (e.offset | e.tag) && (e.tag & better) != better;
+			// four windows of 32 slots in flight per step: crossing a stretch without due entries (the
+			// regions of tags that already satisfy the stricter mask) costs one L2 round trip per 128 slots
+			for (int64_t cp = r.clean_ptr; found < ncl && cp < tsize; cp += 128) {
+				HEntry e4[4];
+#pragma unroll
+				for (int u = 0; u < 4; u++) {
+					const int64_t k = cp + u * 32 + lane;
+					e4[u].offset = e4[u].tag = 0;
+					if (k < tsize)
+						e4[u] = ld_entry(prim.tab + k);
 				}
-				const unsigned bm = __ballot_sync(FULL, q);
-				if (q) {
-					const int rk = found + __popc(bm & lt);
-					if (rk < ncl)
-						sh->dslot[rk] = (unsigned)k;
+#pragma unroll
+				for (int u = 0; u < 4; u++) {
+					const int64_t k = cp + u * 32 + lane;
+					const bool q = (e4[u].offset | e4[u].tag) && (e4[u].tag & better) != better;
+					const unsigned bm = __ballot_sync(FULL, q);
+					if (q) {
+						const int rk = found + __popc(bm & lt);
+						if (rk < ncl)
+							sh->dslot[rk] = (unsigned)k;
+					}
+					found += __popc(bm);
 				}
-				found += __popc(bm);
 			}
 			if (found > ncl)
 				found = ncl;
@@ -1259,24 +1277,10 @@ __device__ void k2_commit_segment_batched(WarpPrim &prim, FastShared *sh, ScanSt
 			}
 			__syncwarp();
 		}
-		// the same check against ONE writer lane (after that lane has been re-evaluated)
-		auto check_against = [&](int j) {
-			const int nwj = __shfl_sync(FULL, nwt, j);
-#pragma unroll
-			for (int w = 0; w < K2_MAXW + 1; w++) {
-				if (w >= nwj)
-					break;
-				const unsigned sl = __shfl_sync(FULL, L.wslot[w], j);
-				if (lane > j)
-					for (int q = 0; q < L.nr; q++) // almost always one range (two with a displacement)
-						if (((sl - L.rlo[q]) & hmask) < L.rlen[q])
-							cmask |= 1u << j;
-			}
-		};
 		dbg[13] += clock64() - cv0;
 		const long long cc0 = clock64();
 
-		// ---- commit in order; a lane that only conflicts is re-evaluated alone on the updated table
+		// ---- commit the longest prefix of lanes that neither need the serial step nor read a slot an earlier lane writes
 		int base = 0;
 		bool serial_next = false;
 		const int64_t tag_mask0 = r.tag_mask;
@@ -1314,6 +1318,11 @@ __device__ void k2_commit_segment_batched(WarpPrim &prim, FastShared *sh, ScanSt
 				n.misses += s_miss;
 				n_disp += s_disp;
 				r.hash_count += __popc(netm & km) - __popc(ck);
+				const int nev = __popc(evm & km);
+				if (nev) {
+					r.victim_round = (r.victim_round + nev) % c.max_chain;
+					n_evict += nev;
+				}
 				if (ck) {
 					r.clean_ptr = sh->dslot[__popc(clm & ((k >= 32) ? FULL : ((1u << k) - 1))) - 1];
 					r.tag_mask = better;
@@ -1331,40 +1340,10 @@ __device__ void k2_commit_segment_batched(WarpPrim &prim, FastShared *sh, ScanSt
 				dbg[__shfl_sync(FULL, (int)L.cx, k) ? 3 : 4]++;
 				break;
 			}
-			// lane k only conflicts with committed lanes: evaluate it again, alone, on the current table
-			const int old_net = __shfl_sync(FULL, L.net, k);
-			const int old_cl = __shfl_sync(FULL, (int)cl, k);
+			// lane k only conflicts with committed lanes (it read a slot one of them wrote): it and everything
+			// after it go into the next full-width batch, evaluated on the updated table
 			dbg[5]++;
-			const long long ce1 = clock64();
-			k2_eval_one(prim.buf, prim.tab, hmask, sh, k, mode, r.tag_mask, better, c.max_chain, c.end, r.last_match, lane);
-			if (lane == k) {
-				L = sh->ev[k];
-				cmask = 0;
-			}
-			__syncwarp();
-			dbg[8] += clock64() - ce1;
-			const int new_net = __shfl_sync(FULL, L.net, k);
-			const int new_cx = __shfl_sync(FULL, (int)L.cx, k);
-			if (new_cx) {
-				serial_next = true;
-				dbg[3]++;
-				break;
-			}
-			if (new_net != old_net || (new_net && (r.hash_count + 1 > c.hash_limit) != (old_cl != 0))) {
-				dbg[7]++;
-				break; // sweep ranks of the later lanes would shift: start a fresh batch
-			}
-			if (lane == k)
-				classify();
-			__syncwarp();
-			if (__shfl_sync(FULL, (int)stopper, k)) {
-				serial_next = true;
-				dbg[4]++;
-				break;
-			}
-			if (lane > k)
-				cmask &= ~(1u << k);
-			check_against(k);
+			break;
 		}
 		if (base > 0) {
 			prim.publish(r.p, r.min_mask);
@@ -1389,6 +1368,7 @@ __device__ void k2_commit_segment_batched(WarpPrim &prim, FastShared *sh, ScanSt
 		for (int i = 0; i < 16; i++)
 			st->dbg[i] += dbg[i];
 		st->st_displacements += n_disp;
+		st->st_evictions += n_evict;
 		k2_store_regs(st, r, n, status);
 	}
 }
@@ -1396,9 +1376,13 @@ __device__ void k2_commit_segment_batched(WarpPrim &prim, FastShared *sh, ScanSt
 __global__ void __launch_bounds__(K2_THREADS, 1)
 k2_commit_kernel(const uint8_t *__restrict__ buf, ScanState *st, HEntry *tab, const Cand *cand,
 		 const uint32_t *tile_count, int64_t first_tile, int64_t num_tiles, int64_t seg_hi, MatchRec *recs,
-		 int last_segment)
+		 int last_segment, int64_t tab_stride, int64_t rec_stride)
 {
 	__shared__ FastShared sh;
+	// one CTA per variant of the window (all-values speculation of victim_round); a plain run has one
+	st += blockIdx.x;
+	tab += (int64_t)blockIdx.x * tab_stride;
+	recs += (int64_t)blockIdx.x * rec_stride;
 	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 	if (threadIdx.x == 0) {
 		sh.prog.pos = st->scan_pos;
@@ -1442,15 +1426,15 @@ k2_commit_kernel(const uint8_t *__restrict__ buf, ScanState *st, HEntry *tab, co
 
 int k2_launch(const uint8_t *d_buf, ScanState *d_state, HEntry *d_tab, const Cand *d_cand,
 	      const uint32_t *d_tile_count, int64_t pos_lo, int64_t pos_hi, MatchRec *d_recs, bool last_segment,
-	      cudaStream_t stream)
+	      int nvar, int64_t tab_stride, int64_t rec_stride, cudaStream_t stream)
 {
 	int64_t first_tile = 0, num_tiles = 0;
 	if (pos_hi > pos_lo) {
 		first_tile = pos_lo / kTile;
 		num_tiles = (pos_hi - 1) / kTile - first_tile + 1;
 	}
-	k2_commit_kernel<<<1, K2_THREADS, 0, stream>>>(d_buf, d_state, d_tab, d_cand, d_tile_count, first_tile, num_tiles,
-					       pos_hi, d_recs, last_segment ? 1 : 0);
+	k2_commit_kernel<<<nvar, K2_THREADS, 0, stream>>>(d_buf, d_state, d_tab, d_cand, d_tile_count, first_tile, num_tiles,
+							  pos_hi, d_recs, last_segment ? 1 : 0, tab_stride, rec_stride);
 	return cudaGetLastError() == cudaSuccess ? 0 : -1;
 }
 

@@ -10,15 +10,18 @@ int k1_init_tables();
 // Scan positions [pos_lo, pos_hi) (pos_lo tile-aligned, kTile = 512) of the n-byte chunk at d_buf (followed by at
 // least kInputPad readable bytes) and write the candidates with (tag & mask) == mask, tile-strided:
 // candidates of tile T (positions [T*512, (T+1)*512)) start at d_cand[(T - pos_lo/512) * 512].
-// When d_state is non-null the mask is read on the device from d_state->min_mask (so the launch
-// needs no host round trip) and the launch is skipped if the scan already moved past pos_hi.
+// When d_state is non-null the mask is read on the device from d_state[0..nstates)->min_mask (the loosest of
+// them; so the launch needs no host round trip) and the launch is skipped if every scan already moved past pos_hi.
 int k1_launch(const uint8_t *d_buf, int64_t n, int64_t pos_lo, int64_t pos_hi, int64_t mask,
-	      const ScanState *d_state, Cand *d_cand, uint32_t *d_tile_count, int num_sms, cudaStream_t stream);
+	      const ScanState *d_state, int nstates, Cand *d_cand, uint32_t *d_tile_count, int num_sms, cudaStream_t stream);
 
 // ---- K2 commit (k2_commit.cu) ---------------------------------------------------------------
+// nvar > 1: all-values speculation of the reference's cross-window counter (victim_round, src/rzip.c:308).  CTA v
+// commits the same candidates into its own table / state / record array (d_state[v], d_tab + v * tab_stride
+// entries, d_recs + v * rec_stride records); the variants differ only in the counter value they started from.
 int k2_launch(const uint8_t *d_buf, ScanState *d_state, HEntry *d_tab, const Cand *d_cand,
 	      const uint32_t *d_tile_count, int64_t pos_lo, int64_t pos_hi, MatchRec *d_recs, bool last_segment,
-	      cudaStream_t stream);
+	      int nvar, int64_t tab_stride, int64_t rec_stride, cudaStream_t stream);
 
 // ---- K4 emit + CRC (k4_emit.cu) -------------------------------------------------------------
 int k4_init_tables();

@@ -67,7 +67,8 @@ struct lrzgpu_ctx {
 	cudaStream_t sA = nullptr, sB = nullptr, sC = nullptr, sD = nullptr;
 	cudaEvent_t evK1[2] = { nullptr, nullptr }, evK2[2] = { nullptr, nullptr }, evInit = nullptr, evCrc = nullptr;
 	DevBuf in, tab, state, cand[2], tc[2], recs, s0, s1, crc, w1;
-	ScanState *h_state = nullptr; // pinned
+	ScanState *h_state = nullptr; // pinned, one per variant of the window being scanned
+	size_t h_state_cap = 0;
 	uint8_t *h_pin[2] = { nullptr, nullptr }; // pinned staging for the MD5 stream of device inputs
 	size_t h_pin_cap = 0;
 	BackendCtx *backend = nullptr;
@@ -77,8 +78,12 @@ struct lrzgpu_ctx {
 		bool valid = false;
 		lrzgpu_params p;
 		lrzgpu_sizing_t sz;
-		int64_t n = 0, s0_len = 0, s1_len = 0, n_rec = 0;
+		int64_t n = 0, s0_len = 0, s1_len = 0, n_rec = 0, rec_base = 0;
 		int eof = 0, cb = 0;
+		const uint8_t *d_chunk = nullptr;
+		bool selected = false; // streams emitted (always true after lrzgpu_chunk_begin)
+		std::vector<int64_t> v_s0, v_s1, v_nrec, v_base, v_out; // per variant, after lrzgpu_chunk_begin_all
+		std::vector<ScanState> v_st;
 	} pending;
 };
 
@@ -105,31 +110,67 @@ int fail(lrzgpu_ctx *c, int code, const char *fmt, ...)
 
 struct ChunkResult {
 	int64_t s0_len = 0, s1_len = 0, n_rec = 0;
+	int64_t rec_base = 0; // first record of this variant in c->recs
 	ScanState st;
 };
 
-// rzip of one chunk that is resident in HBM at d_chunk (16-byte aligned, readable kFrontPad before and
-// kInputPad after).  Leaves stream 0 / stream 1 in c->s0 / c->s1.
-int rzip_chunk_device(lrzgpu_ctx *c, const uint8_t *d_chunk, int64_t n, int rzip_level, int cb, int64_t victim_round,
-		      ChunkResult &res, lrzgpu_stats *stats)
+void account_rzip(lrzgpu_stats *stats, const ChunkResult &res)
+{
+	if (!stats)
+		return;
+	stats->matches += res.st.st_matches;
+	stats->match_bytes += res.st.st_match_bytes;
+	stats->literals += res.st.st_literals;
+	stats->literal_bytes += res.st.st_literal_bytes;
+	stats->tag_hits += res.st.st_tag_hits;
+	stats->tag_misses += res.st.st_tag_misses;
+	stats->inserts += res.st.st_inserts;
+	stats->lookups += res.st.st_lookups;
+	stats->chain_evictions += res.st.st_evictions;
+	stats->sweeps += res.st.st_sweeps;
+	stats->displacements += res.st.st_displacements;
+	stats->hash_count = res.st.hash_count;
+	stats->final_min_mask = res.st.min_mask;
+	stats->final_tag_mask = res.st.tag_mask;
+	stats->chunks += 1;
+	stats->stream0_bytes += res.s0_len;
+	stats->stream1_bytes += res.s1_len;
+}
+
+// The scan of one chunk that is resident in HBM at d_chunk (16-byte aligned, readable kFrontPad before and
+// kInputPad after): CRC-32, K1 tag scan and K2 commit, segment-pipelined on two streams.  nvar == 1 runs the
+// chunk from the given victim_round; nvar > 1 runs one commit per possible incoming value 0..nvar-1 of the
+// reference's cross-window counter (all-values speculation), each with its own table, state and
+// match records.  Leaves the match records in c->recs (variant v from res[v].rec_base).
+int rzip_scan_device(lrzgpu_ctx *c, const uint8_t *d_chunk, int64_t n, int rzip_level, int cb, int64_t victim_round,
+		     int nvar, std::vector<ChunkResult> &res, lrzgpu_stats *stats)
 {
 	const double t0 = now_ms();
 	const RzipLevel &lv = kLevels[rzip_level];
 	const size_t tab_bytes = (size_t)lv.mb_used << 20;
 	const int64_t rec_cap = n / kMinMatch + 8;
 	const int64_t seg = kSegment < ((n + kTile - 1) / kTile) * kTile ? kSegment : ((n + kTile - 1) / kTile) * kTile;
-	CU(c, c->tab.ensure(tab_bytes));
-	CU(c, c->state.ensure(sizeof(ScanState)));
-	CU(c, c->recs.ensure((size_t)rec_cap * sizeof(MatchRec)));
+	CU(c, c->tab.ensure(tab_bytes * (size_t)nvar));
+	CU(c, c->state.ensure(sizeof(ScanState) * (size_t)nvar));
+	CU(c, c->recs.ensure((size_t)rec_cap * sizeof(MatchRec) * (size_t)nvar));
 	CU(c, c->crc.ensure(16));
 	for (int b = 0; b < 2; b++) {
 		CU(c, c->cand[b].ensure((size_t)seg * sizeof(Cand)));
 		CU(c, c->tc[b].ensure((size_t)(seg / kTile + 1) * sizeof(uint32_t)));
 	}
+	if ((size_t)nvar > c->h_state_cap) {
+		if (c->h_state)
+			cudaFreeHost(c->h_state);
+		c->h_state = nullptr;
+		c->h_state_cap = 0;
+		CU(c, cudaHostAlloc((void **)&c->h_state, sizeof(ScanState) * (size_t)nvar, cudaHostAllocDefault));
+		c->h_state_cap = (size_t)nvar;
+	}
 	ScanState *d_state = (ScanState *)c->state.p;
-	k2_init_state(c->h_state, n, rzip_level, cb, victim_round, rec_cap);
-	CU(c, cudaMemcpyAsync(d_state, c->h_state, sizeof(ScanState), cudaMemcpyHostToDevice, c->sA));
-	CU(c, cudaMemsetAsync(c->tab.p, 0, tab_bytes, c->sA)); // src/rzip.c:599-600
+	for (int v = 0; v < nvar; v++)
+		k2_init_state(c->h_state + v, n, rzip_level, cb, nvar > 1 ? v : victim_round, rec_cap);
+	CU(c, cudaMemcpyAsync(d_state, c->h_state, sizeof(ScanState) * (size_t)nvar, cudaMemcpyHostToDevice, c->sA));
+	CU(c, cudaMemsetAsync(c->tab.p, 0, tab_bytes * (size_t)nvar, c->sA)); // src/rzip.c:599-600
 	CU(c, cudaEventRecord(c->evInit, c->sA));
 	CU(c, cudaStreamWaitEvent(c->sB, c->evInit, 0));
 	CU(c, cudaStreamWaitEvent(c->sC, c->evInit, 0));
@@ -144,68 +185,75 @@ int rzip_chunk_device(lrzgpu_ctx *c, const uint8_t *d_chunk, int64_t n, int rzip
 		const int64_t lo = i * seg, hi = (lo + seg < n) ? lo + seg : n;
 		if (i >= 2)
 			CU(c, cudaStreamWaitEvent(c->sB, c->evK2[b], 0)); // cand[b] consumed, newer mask visible
-		if (k1_launch(d_chunk, n, lo, hi, 0, d_state, (Cand *)c->cand[b].p, (uint32_t *)c->tc[b].p, c->sms, c->sB))
+		if (k1_launch(d_chunk, n, lo, hi, 0, d_state, nvar, (Cand *)c->cand[b].p, (uint32_t *)c->tc[b].p, c->sms, c->sB))
 			return fail(c, LRZGPU_ECUDA, "k1 launch: %s", cudaGetErrorString(cudaGetLastError()));
 		CU(c, cudaEventRecord(c->evK1[b], c->sB));
 		CU(c, cudaStreamWaitEvent(c->sA, c->evK1[b], 0));
 		if (k2_launch(d_chunk, d_state, (HEntry *)c->tab.p, (const Cand *)c->cand[b].p, (const uint32_t *)c->tc[b].p, lo,
-			      hi, (MatchRec *)c->recs.p, i == nseg - 1, c->sA))
+			      hi, (MatchRec *)c->recs.p, i == nseg - 1, nvar, (int64_t)(tab_bytes / sizeof(HEntry)), rec_cap, c->sA))
 			return fail(c, LRZGPU_ECUDA, "k2 launch: %s", cudaGetErrorString(cudaGetLastError()));
 		CU(c, cudaEventRecord(c->evK2[b], c->sA));
 		c->launches += 2;
 	}
-	CU(c, cudaMemcpyAsync(c->h_state, d_state, sizeof(ScanState), cudaMemcpyDeviceToHost, c->sA));
+	CU(c, cudaMemcpyAsync(c->h_state, d_state, sizeof(ScanState) * (size_t)nvar, cudaMemcpyDeviceToHost, c->sA));
 	CU(c, cudaStreamSynchronize(c->sA));
 	CU(c, cudaStreamSynchronize(c->sB));
-	res.st = *c->h_state;
-	if (getenv("LRZGPU_DEBUG")) {
-		fprintf(stderr, "[lrzgpu] commit: n=%lld lookups=%lld", (long long)n, (long long)res.st.st_lookups);
-		for (int i = 0; i < 16; i++)
-			fprintf(stderr, " d%d=%lld", i, (long long)res.st.dbg[i]);
-		fprintf(stderr, "\n");
+	res.assign((size_t)nvar, ChunkResult());
+	for (int v = 0; v < nvar; v++) {
+		ChunkResult &r = res[(size_t)v];
+		r.st = c->h_state[v];
+		if (getenv("LRZGPU_DEBUG")) {
+			fprintf(stderr, "[lrzgpu] commit v%d: n=%lld lookups=%lld", v, (long long)n, (long long)r.st.st_lookups);
+			for (int i = 0; i < 16; i++)
+				fprintf(stderr, " d%d=%lld", i, (long long)r.st.dbg[i]);
+			fprintf(stderr, "\n");
+		}
+		if (r.st.status != kStatusChunkDone)
+			return fail(c, LRZGPU_EINTERNAL, "rzip commit ended with status %d at position %lld", r.st.status,
+				    (long long)r.st.scan_pos);
+		r.s0_len = r.st.s0_len;
+		r.s1_len = r.st.s1_len;
+		r.n_rec = r.st.n_rec;
+		r.rec_base = (int64_t)v * rec_cap;
 	}
-	if (res.st.status != kStatusChunkDone)
-		return fail(c, LRZGPU_EINTERNAL, "rzip commit ended with status %d at position %lld", res.st.status,
-			    (long long)res.st.scan_pos);
-	res.s0_len = res.st.s0_len;
-	res.s1_len = res.st.s1_len;
-	res.n_rec = res.st.n_rec;
-	const double t1 = now_ms();
+	if (stats)
+		stats->ms_rzip += now_ms() - t0;
+	return LRZGPU_OK;
+}
 
+// K4: stream 0 / stream 1 of one scanned variant into c->s0 / c->s1.
+int rzip_emit_device(lrzgpu_ctx *c, const uint8_t *d_chunk, int cb, const ChunkResult &res, lrzgpu_stats *stats)
+{
+	const double t1 = now_ms();
+	const MatchRec *recs = (const MatchRec *)c->recs.p + res.rec_base;
 	CU(c, c->s0.ensure((size_t)res.s0_len + 64));
 	CU(c, c->s1.ensure((size_t)res.s1_len + 64));
 	CU(c, cudaStreamWaitEvent(c->sA, c->evCrc, 0));
-	if (k4_headers_launch((const MatchRec *)c->recs.p, res.n_rec, cb, (const uint32_t *)c->crc.p, (uint8_t *)c->s0.p, c->sA) ||
-	    k4_literals_launch(d_chunk, (const MatchRec *)c->recs.p, res.n_rec, res.s1_len, (uint8_t *)c->s1.p, c->sms, c->sA))
+	if (k4_headers_launch(recs, res.n_rec, cb, (const uint32_t *)c->crc.p, (uint8_t *)c->s0.p, c->sA) ||
+	    k4_literals_launch(d_chunk, recs, res.n_rec, res.s1_len, (uint8_t *)c->s1.p, c->sms, c->sA))
 		return fail(c, LRZGPU_ECUDA, "k4 launch: %s", cudaGetErrorString(cudaGetLastError()));
 	c->launches += 2;
 	uint32_t crc_acc = 0;
 	CU(c, cudaMemcpyAsync(&crc_acc, c->crc.p, 4, cudaMemcpyDeviceToHost, c->sA));
 	CU(c, cudaStreamSynchronize(c->sA));
-	const double t2 = now_ms();
+	account_rzip(stats, res);
 	if (stats) {
-		stats->matches += res.st.st_matches;
-		stats->match_bytes += res.st.st_match_bytes;
-		stats->literals += res.st.st_literals;
-		stats->literal_bytes += res.st.st_literal_bytes;
-		stats->tag_hits += res.st.st_tag_hits;
-		stats->tag_misses += res.st.st_tag_misses;
-		stats->inserts += res.st.st_inserts;
-		stats->lookups += res.st.st_lookups;
-		stats->chain_evictions += res.st.st_evictions;
-		stats->sweeps += res.st.st_sweeps;
-		stats->displacements += res.st.st_displacements;
-		stats->hash_count = res.st.hash_count;
-		stats->final_min_mask = res.st.min_mask;
-		stats->final_tag_mask = res.st.tag_mask;
-		stats->chunks += 1;
-		stats->stream0_bytes += res.s0_len;
-		stats->stream1_bytes += res.s1_len;
 		stats->crc32 = crc_acc ^ 0xffffffffu;
-		stats->ms_rzip += t1 - t0;
-		stats->ms_emit += t2 - t1;
+		stats->ms_emit += now_ms() - t1;
 	}
 	return LRZGPU_OK;
+}
+
+// rzip of one chunk from a known victim_round: scan + emit.
+int rzip_chunk_device(lrzgpu_ctx *c, const uint8_t *d_chunk, int64_t n, int rzip_level, int cb, int64_t victim_round,
+		      ChunkResult &res, lrzgpu_stats *stats)
+{
+	std::vector<ChunkResult> all;
+	int rc = rzip_scan_device(c, d_chunk, n, rzip_level, cb, victim_round, 1, all, stats);
+	if (rc)
+		return rc;
+	res = all[0];
+	return rzip_emit_device(c, d_chunk, cb, res, stats);
 }
 
 struct OutBuf {
@@ -255,7 +303,7 @@ int finish_chunk_device(lrzgpu_ctx *c, const lrzgpu_params &p, const lrzgpu_sizi
 	std::vector<int64_t> w1((size_t)nb0 + 1, 0);
 	if (nb0 > 0) {
 		CU(c, c->w1.ensure((size_t)nb0 * 8));
-		if (k4_flush_order_launch((const MatchRec *)c->recs.p, res.n_rec, cb, sz.bufsize, nb0, (int64_t *)c->w1.p, c->sA))
+		if (k4_flush_order_launch((const MatchRec *)c->recs.p + res.rec_base, res.n_rec, cb, sz.bufsize, nb0, (int64_t *)c->w1.p, c->sA))
 			return fail(c, LRZGPU_ECUDA, "flush order launch failed");
 		c->launches += 1;
 		CU(c, cudaMemcpyAsync(w1.data(), c->w1.p, (size_t)nb0 * 8, cudaMemcpyDeviceToHost, c->sA));
@@ -407,6 +455,8 @@ int lrzgpu_create(int device, lrzgpu_ctx **out)
 	ok = ok && cudaEventCreateWithFlags(&c->evInit, cudaEventDisableTiming) == cudaSuccess &&
 	     cudaEventCreateWithFlags(&c->evCrc, cudaEventDisableTiming) == cudaSuccess;
 	ok = ok && cudaHostAlloc((void **)&c->h_state, sizeof(ScanState), cudaHostAllocDefault) == cudaSuccess;
+	if (ok)
+		c->h_state_cap = 1;
 	ok = ok && k1_init_tables() == 0 && k4_init_tables() == 0;
 	if (ok) {
 		c->backend = backend_create();
@@ -667,6 +717,9 @@ int lrzgpu_compress_chunk(lrzgpu_ctx *c, const lrzgpu_params *p, const lrzgpu_si
 	rc = upload(c, in, n, &d_in);
 	if (rc)
 		return rc;
+	CU(c, cudaStreamSynchronize(c->sA));
+	if (stats)
+		stats->ms_h2d = now_ms() - t0;
 	OutBuf ob;
 	rc = compress_chunk_device(c, *p, *sz, d_in, n, eof, victim_round, ob, stats);
 	if (rc) {
@@ -700,6 +753,9 @@ int lrzgpu_chunk_begin(lrzgpu_ctx *c, const lrzgpu_params *p, const lrzgpu_sizin
 	rc = upload(c, in, n, &d_in);
 	if (rc)
 		return rc;
+	CU(c, cudaStreamSynchronize(c->sA));
+	if (stats)
+		stats->ms_h2d = now_ms() - t0;
 	const int rzl = p->rzip_level ? p->rzip_level : p->level;
 	const int cb = chunk_bytes_for(n);
 	ChunkResult res;
@@ -707,15 +763,136 @@ int lrzgpu_chunk_begin(lrzgpu_ctx *c, const lrzgpu_params *p, const lrzgpu_sizin
 	if (rc)
 		return rc;
 	*victim_round = res.st.victim_round;
-	c->pending.valid = true;
-	c->pending.p = *p;
-	c->pending.sz = *sz;
-	c->pending.n = n;
-	c->pending.eof = eof;
-	c->pending.cb = cb;
-	c->pending.s0_len = res.s0_len;
-	c->pending.s1_len = res.s1_len;
-	c->pending.n_rec = res.n_rec;
+	lrzgpu_ctx::Pending &pd = c->pending;
+	pd.valid = true;
+	pd.selected = true;
+	pd.p = *p;
+	pd.sz = *sz;
+	pd.n = n;
+	pd.eof = eof;
+	pd.cb = cb;
+	pd.d_chunk = d_in;
+	pd.s0_len = res.s0_len;
+	pd.s1_len = res.s1_len;
+	pd.n_rec = res.n_rec;
+	pd.rec_base = res.rec_base;
+	if (stats) {
+		stats->ms_total = now_ms() - t0;
+		stats->kernel_launches = c->launches - launches0;
+	}
+	return LRZGPU_OK;
+}
+
+int lrzgpu_victim_values(const lrzgpu_params *p)
+{
+	if (!p)
+		return LRZGPU_EINVAL;
+	const int rzl = p->rzip_level ? p->rzip_level : p->level;
+	if (rzl < 0 || rzl > 9)
+		return LRZGPU_EINVAL;
+	return (int)kLevels[rzl].max_chain_len;
+}
+
+int lrzgpu_chunk_begin_all(lrzgpu_ctx *c, const lrzgpu_params *p, const lrzgpu_sizing_t *sz, const uint8_t *in, int64_t n,
+			   int eof, int64_t *victim_out, int nvalues, lrzgpu_stats *stats)
+{
+	int rc = check_params(c, p, n);
+	if (rc)
+		return rc;
+	if (!sz || !in || !victim_out)
+		return LRZGPU_EINVAL;
+	const int nvar = lrzgpu_victim_values(p);
+	if (nvalues != nvar)
+		return fail(c, LRZGPU_EINVAL, "victim_out must hold lrzgpu_victim_values() = %d entries", nvar);
+	cudaSetDevice(c->device);
+	c->pending.valid = false;
+	if (stats)
+		memset(stats, 0, sizeof(*stats));
+	const int64_t launches0 = c->launches;
+	const double t0 = now_ms();
+	{ // nvar tables and record arrays must fit next to the window and the backend's work space
+		size_t free_b = 0, total_b = 0;
+		cudaMemGetInfo(&free_b, &total_b);
+		const int rzl0 = p->rzip_level ? p->rzip_level : p->level;
+		const size_t need = (size_t)nvar * (((size_t)kLevels[rzl0].mb_used << 20) + (size_t)(n / kMinMatch + 8) * sizeof(MatchRec));
+		const size_t have = free_b + c->tab.cap + c->recs.cap;
+		if (need + (size_t)n * 4 + (8ull << 30) > have)
+			return fail(c, LRZGPU_ENOMEM, "%d variants of a %lld byte window need %zu MiB of device memory", nvar,
+				    (long long)n, need >> 20);
+	}
+	uint8_t *d_in = nullptr;
+	rc = upload(c, in, n, &d_in);
+	if (rc)
+		return rc;
+	CU(c, cudaStreamSynchronize(c->sA));
+	if (stats)
+		stats->ms_h2d = now_ms() - t0;
+	const int rzl = p->rzip_level ? p->rzip_level : p->level;
+	const int cb = chunk_bytes_for(n);
+	std::vector<ChunkResult> res;
+	rc = rzip_scan_device(c, d_in, n, rzl, cb, 0, nvar, res, stats);
+	if (rc)
+		return rc;
+	lrzgpu_ctx::Pending &pd = c->pending;
+	pd.valid = true;
+	pd.selected = false;
+	pd.p = *p;
+	pd.sz = *sz;
+	pd.n = n;
+	pd.eof = eof;
+	pd.cb = cb;
+	pd.d_chunk = d_in;
+	pd.v_s0.clear();
+	pd.v_s1.clear();
+	pd.v_nrec.clear();
+	pd.v_base.clear();
+	pd.v_out.clear();
+	pd.v_st.clear();
+	for (int v = 0; v < nvar; v++) {
+		pd.v_s0.push_back(res[(size_t)v].s0_len);
+		pd.v_s1.push_back(res[(size_t)v].s1_len);
+		pd.v_nrec.push_back(res[(size_t)v].n_rec);
+		pd.v_base.push_back(res[(size_t)v].rec_base);
+		pd.v_out.push_back(res[(size_t)v].st.victim_round);
+		pd.v_st.push_back(res[(size_t)v].st);
+		victim_out[v] = res[(size_t)v].st.victim_round;
+	}
+	if (stats) {
+		stats->ms_total = now_ms() - t0;
+		stats->kernel_launches = c->launches - launches0;
+	}
+	return LRZGPU_OK;
+}
+
+int lrzgpu_chunk_select(lrzgpu_ctx *c, int64_t victim_in, lrzgpu_stats *stats)
+{
+	if (!c)
+		return LRZGPU_EINVAL;
+	lrzgpu_ctx::Pending &pd = c->pending;
+	if (!pd.valid || pd.selected)
+		return fail(c, LRZGPU_EINVAL, "lrzgpu_chunk_select without a window from lrzgpu_chunk_begin_all");
+	if (victim_in < 0 || victim_in >= (int64_t)pd.v_out.size())
+		return fail(c, LRZGPU_EINVAL, "victim_round %lld out of range", (long long)victim_in);
+	cudaSetDevice(c->device);
+	if (stats)
+		memset(stats, 0, sizeof(*stats));
+	const int64_t launches0 = c->launches;
+	const double t0 = now_ms();
+	ChunkResult res;
+	const size_t v = (size_t)victim_in;
+	res.s0_len = pd.v_s0[v];
+	res.s1_len = pd.v_s1[v];
+	res.n_rec = pd.v_nrec[v];
+	res.rec_base = pd.v_base[v];
+	res.st = pd.v_st[v];
+	int rc = rzip_emit_device(c, pd.d_chunk, pd.cb, res, stats);
+	if (rc)
+		return rc;
+	pd.selected = true;
+	pd.s0_len = res.s0_len;
+	pd.s1_len = res.s1_len;
+	pd.n_rec = res.n_rec;
+	pd.rec_base = res.rec_base;
 	if (stats) {
 		stats->ms_total = now_ms() - t0;
 		stats->kernel_launches = c->launches - launches0;
@@ -727,8 +904,8 @@ int lrzgpu_chunk_finish(lrzgpu_ctx *c, uint8_t **blob, int64_t *blob_len, lrzgpu
 {
 	if (!c || !blob || !blob_len)
 		return LRZGPU_EINVAL;
-	if (!c->pending.valid)
-		return fail(c, LRZGPU_EINVAL, "lrzgpu_chunk_finish without a window from lrzgpu_chunk_begin");
+	if (!c->pending.valid || !c->pending.selected)
+		return fail(c, LRZGPU_EINVAL, "lrzgpu_chunk_finish without a window from lrzgpu_chunk_begin / lrzgpu_chunk_select");
 	cudaSetDevice(c->device);
 	if (stats)
 		memset(stats, 0, sizeof(*stats));
@@ -738,6 +915,7 @@ int lrzgpu_chunk_finish(lrzgpu_ctx *c, uint8_t **blob, int64_t *blob_len, lrzgpu
 	res.s0_len = c->pending.s0_len;
 	res.s1_len = c->pending.s1_len;
 	res.n_rec = c->pending.n_rec;
+	res.rec_base = c->pending.rec_base;
 	c->pending.valid = false;
 	OutBuf ob;
 	const int rc = finish_chunk_device(c, c->pending.p, c->pending.sz, c->pending.n, c->pending.eof, c->pending.cb, res, ob,
@@ -813,7 +991,7 @@ int lrzgpu_tag_scan(lrzgpu_ctx *c, const uint8_t *in, int64_t n, int64_t pos_lo,
 	for (int64_t lo = pos_lo - pos_lo % kTile; lo < pos_hi; lo += seg) {
 		const int64_t a = lo < pos_lo ? pos_lo : lo, b = lo + seg < pos_hi ? lo + seg : pos_hi;
 		// pos_lo of a launch must be tile aligned for the tile-strided layout: scan from `lo`, filter to [a,b)
-		if (k1_launch(d_in, n, lo, b, mask, nullptr, (Cand *)c->cand[0].p, (uint32_t *)c->tc[0].p, c->sms, c->sA))
+		if (k1_launch(d_in, n, lo, b, mask, nullptr, 0, (Cand *)c->cand[0].p, (uint32_t *)c->tc[0].p, c->sms, c->sA))
 			return fail(c, LRZGPU_ECUDA, "k1 launch failed");
 		c->launches++;
 		const int64_t ntiles = (b - 1) / kTile - lo / kTile + 1;
@@ -913,7 +1091,7 @@ int lrzgpu_k1_launch(lrzgpu_ctx *c, const void *d_buf, int64_t n, int64_t mask, 
 {
 	if (!c || !d_buf || n <= 0 || !d_cand || !d_tile_count)
 		return LRZGPU_EINVAL;
-	if (k1_launch((const uint8_t *)d_buf, n, 0, n, mask, nullptr, (Cand *)d_cand, (uint32_t *)d_tile_count, c->sms,
+	if (k1_launch((const uint8_t *)d_buf, n, 0, n, mask, nullptr, 0, (Cand *)d_cand, (uint32_t *)d_tile_count, c->sms,
 		      (cudaStream_t)stream))
 		return fail(c, LRZGPU_ECUDA, "k1 launch: %s", cudaGetErrorString(cudaGetLastError()));
 	c->launches++;

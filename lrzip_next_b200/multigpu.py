@@ -225,3 +225,80 @@ def compress_chained(ctx, params: Params, sz: Sizing, shards: dict[int, np.ndarr
     if rank != 0:
         return None, stats
     return assemble(params, sz, sum(p.size for p in plans), got, _resolve_md5(whole_md5)), stats
+
+
+def _merge_stats(parts: list[dict]) -> dict:
+    """Sum the numeric fields of the stats of the calls that made up one window (begin / select / finish)."""
+    merged: dict = {}
+    for st in parts:
+        for k, v in st.items():
+            if isinstance(v, (int, float)) and k != "crc32":
+                merged[k] = merged.get(k, 0) + v
+    for st in parts:
+        if st.get("crc32"):
+            merged["crc32"] = st["crc32"]
+    merged.setdefault("crc32", 0)
+    return merged
+
+
+_spec_calls = 0
+
+
+def compress_speculated(ctx, params: Params, sz: Sizing, shards: dict[int, np.ndarray], plans: list[ChunkPlan],
+                        whole_md5=None, device: torch.device | None = None):
+    """All-values speculation of ``victim_round``: every window runs its rzip stage at once, on its own GPU, for
+    EVERY value the reference's cross-window counter can take (``chunk_begin_all``: one commit CTA, one table and
+    one record array per value -- the commit stage needs one SM of 148).  Only the counter's true value then
+    travels from window to window (one small integer through the process group's store, as in
+    ``compress_chained``), each owner picks the matching variant (``chunk_select``) and runs its backend.  The
+    rzip stages of all windows overlap, so the critical path is one rzip stage + one backend for any number of
+    windows, and the archive is byte-identical to the serial one.  Window 0 starts from the known value 0.
+    Falls back to waiting for the predecessor (the chained form) when the variants do not fit device memory.
+    Returns (archive or None, per-window stats list of this rank)."""
+    global _spec_calls
+    rank, world = dist.get_rank(), dist.get_world_size()
+    if rank == 0 and whole_md5 is None:
+        raise ValueError("rank 0 needs the whole file's MD5")
+    device = device or torch.device("cpu")
+    from datetime import timedelta
+    store = dist.distributed_c10d._get_default_store()
+    store.set_timeout(timedelta(hours=6))
+    _spec_calls += 1
+    tag = f"lrzgpu/victim_round_true/{_spec_calls}"
+    blobs, stats = {}, []
+    last_out = 0
+
+    def incoming(p):
+        return last_out if plans[p.index - 1].rank == rank else int(store.get(f"{tag}/{p.index - 1}"))
+
+    for p in plans:
+        if p.rank != rank:
+            continue
+        parts = []
+        if p.index == 0:
+            vr_out, st_a = ctx.chunk_begin(shards[p.index], params, sz, p.eof, 0)
+            parts.append(st_a)
+        else:
+            try:
+                table, st_a = ctx.chunk_begin_all(shards[p.index], params, sz, p.eof)
+            except Exception as e:  # LrzGpuError ENOMEM: the variants do not fit -> wait for the predecessor
+                if getattr(e, "code", None) != -2:
+                    raise
+                table = None
+            if table is None:
+                vr_out, st_a = ctx.chunk_begin(shards[p.index], params, sz, p.eof, incoming(p))
+                parts.append(st_a)
+            else:
+                vin = incoming(p)
+                parts += [st_a, ctx.chunk_select(vin)]
+                vr_out = int(table[vin])
+        last_out = vr_out
+        if p.index + 1 < len(plans) and plans[p.index + 1].rank != rank:
+            store.set(f"{tag}/{p.index}", str(vr_out))
+        blob, st_b = ctx.chunk_finish()
+        blobs[p.index] = blob
+        stats.append(_merge_stats(parts + [st_b]))
+    got = gather_blobs(blobs, device)
+    if rank != 0:
+        return None, stats
+    return assemble(params, sz, sum(p.size for p in plans), got, _resolve_md5(whole_md5)), stats

@@ -161,3 +161,36 @@ def test_two_phase_chunk_equals_one_call(ctx):
             blob2, st_b = ctx.chunk_finish()
             assert (blob2, vr2) == (blob, vr)
             assert st_a["lookups"] == st["lookups"] and st_b["blocks"] == st["blocks"]
+
+
+def test_all_values_speculation_equals_chunk_from_known_value(ctx):
+    """lrzgpu_chunk_begin_all + _select(v) + _finish == lrzgpu_compress_chunk(victim_round = v) for every tested v,
+    and the reported table of outgoing counter values agrees with the oracle's."""
+    from lrzip_next_b200 import sizing
+    from lrzip_next_b200.api import victim_values
+    blk = np.frombuffer(b"abcdefg" * 5, dtype=np.uint8)
+    d = np.tile(blk, (3 << 20) // blk.size + 1)[:3 << 20].copy()
+    rnd = np.random.default_rng(5).integers(0, 256, size=d.size // 8, dtype=np.uint8)
+    d[::8] ^= (rnd & 1)  # many equal 31-byte windows => equal-tag chains at max_chain_len => the counter matters
+    d = np.concatenate([d, datagen.generate("text", 2 << 20)])
+    p = make_params(backend=BACKEND_NONE, threads=1)
+    assert victim_values(p) == 16
+    sz = sizing(p, d.size)
+    table, st_a = ctx.chunk_begin_all(d, p, sz, True)
+    assert len(table) == 16
+    blobs = {}
+    for v in (0, 3, 15):
+        if v:
+            table2, _ = ctx.chunk_begin_all(d, p, sz, True)
+            assert table2 == table
+        st_s = ctx.chunk_select(v)
+        blob, _ = ctx.chunk_finish()
+        want, vr_out, st = ctx.compress_chunk(d, p, sz, True, v)
+        assert blob == want and table[v] == vr_out
+        assert st_s["chain_evictions"] == st["chain_evictions"] > 0
+        _, _, _, ovr = oracle.rzip_chunk(d, 7, victim_round=v)
+        assert table[v] == ovr
+        blobs[v] = blob
+    assert len(set(blobs.values())) > 1, "the input was meant to depend on the incoming counter"
+    with pytest.raises(Exception):
+        ctx.chunk_select(0)  # nothing pending any more

@@ -136,3 +136,62 @@ def test_chained_windows_pass_victim_round_along(tmp_path):
     want = multigpu.assemble(params, sz, n, blobs, hashlib.md5(d.tobytes()).digest())
     with open(path, "rb") as fh:
         assert fh.read() == want
+
+
+class SpecFakeCtx(ChainFakeCtx):
+    """Adds chunk_begin_all / chunk_select (all-values speculation) to the fake: the table of outgoing counter
+    values for every incoming one, and the pick of one variant."""
+
+    def chunk_begin_all(self, data, params, sz, eof):
+        assert self.pending is None
+        d = np.ascontiguousarray(data, dtype=np.uint8)
+        self.pending = (d, bool(eof), None)
+        return [self._vr_out(d, v) for v in range(16)], {"chain_evictions": 1, "lookups": int(d.size), "crc32": 0}
+
+    def chunk_select(self, victim_in):
+        d, eof, v = self.pending
+        assert v is None
+        self.pending = (d, eof, victim_in)
+        return {"lookups": 0, "crc32": 7}
+
+
+def _spec_worker(rank, world, port, path, n, chunk):
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    d = datagen.gen_text(n)
+    params = make_params(backend=0, threads=1)
+    sz = sizing(params, n)
+    plans = multigpu.plan_chunks(n, chunk, world)
+    shards = {p.index: d[p.offset:p.offset + p.size] for p in plans if p.rank == rank}
+    md5 = hashlib.md5(d.tobytes()).digest()
+    arc, sts = multigpu.compress_speculated(SpecFakeCtx(), params, sz, shards, plans, (lambda: md5) if rank == 0 else None)
+    if rank == 0:
+        with open(path, "wb") as fh:
+            fh.write(arc)
+        assert all(s["lookups"] > 0 and s["blocks"] == 2 and s["crc32"] == 7 for s in sts)
+    dist.destroy_process_group()
+
+
+def test_speculated_windows_equal_the_serial_chain(tmp_path):
+    n, chunk = 700_000, 100_000  # 7 windows over 2 ranks
+    path = str(tmp_path / "spec.lrz")
+    mp.spawn(_spec_worker, args=(2, 29751, path, n, chunk), nprocs=2, join=True)
+    d = datagen.gen_text(n)
+    params = make_params(backend=0, threads=1)
+    sz = sizing(params, n)
+    fake, vr, blobs = ChainFakeCtx(), 0, {}
+    for p in multigpu.plan_chunks(n, chunk, 2):
+        vr, _ = fake.chunk_begin(d[p.offset:p.offset + p.size], params, sz, p.eof, vr)
+        blobs[p.index], _ = fake.chunk_finish()
+    want = multigpu.assemble(params, sz, n, blobs, hashlib.md5(d.tobytes()).digest())
+    with open(path, "rb") as fh:
+        assert fh.read() == want
+
+
+def test_missing_md5_is_an_error():
+    with pytest.raises(ValueError):
+        multigpu._resolve_md5(None)
+    with pytest.raises(ValueError):
+        multigpu._resolve_md5(b"short")
+    assert multigpu._resolve_md5(lambda: b"0123456789abcdef") == b"0123456789abcdef"
