@@ -223,7 +223,8 @@ def main():
               "l2": "inputs larger than L2 (126 MB); no flush needed",
               "budget_s": a.budget_s,
               "sharding": "single window" if nwin == 1 else
-              f"{nwin} rzip windows of {size // MiB} MiB, one per GPU; blobs gathered to rank 0 (NCCL)"}
+              f"{nwin} rzip windows of {size // MiB} MiB, one per GPU, all-values speculation of victim_round; "
+              f"blobs gathered to rank 0 (NCCL)"}
 
     if a.impl == "reference":
         if rank != 0:
@@ -324,9 +325,10 @@ def main():
         def md5():
             th.join()
             return md5_box["d"]
-        # text consults the reference's cross-window counter all the time: the windows' rzip
-        # stages are ordered through it; other data speculates the counter and shards freely
-        fn = multigpu.compress_chained if kind == "text" else multigpu.compress_sharded
+        # text consults the reference's cross-window counter all the time: every window but the
+        # first runs its rzip stage for all 16 values of it at once and picks the true one when it arrives;
+        # other data passes the counter through unchanged and shards freely (redone only if it did not)
+        fn = multigpu.compress_speculated if kind == "text" else multigpu.compress_sharded
         arc, sts = fn(ctx, params, sz, {rank: pinned}, plans, md5 if rank == 0 else None, dev)
         last.update(arc=arc, out_len=len(arc) if arc is not None else 0, stats=sts[0])
         return sum(s["ms_h2d"] + s["ms_d2h"] for s in sts), sum(int(s["kernel_launches"]) for s in sts)

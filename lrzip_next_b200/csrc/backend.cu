@@ -84,22 +84,71 @@ struct LzmaJob {
 	int overflow;
 };
 
-// K7b: optimal parser + range coder, one block per CTA = one warp, over the precomputed match lists.
+// K7b: optimal parser + range coder, one block per CTA, over the precomputed match lists.
 // The whole encoder state (probabilities, price tables, the 2048-cell parse table: 135 KB) lives in the
-// SM's shared memory; the warp runs the encoder cooperatively (lzma_enc.cuh: replicated scalar code,
-// lane-split loops).
-__global__ void __launch_bounds__(32, 1) lzma_block_kernel(LzmaJob *jobs)
+// SM's shared memory; warp 0 runs the encoder cooperatively (lzma_enc.cuh: replicated scalar code,
+// lane-split loops).  Warp 1 is a pure look-ahead: it follows the encoder's position (e->pos in shared
+// memory) and, for the next few positions, pulls into L1 what the parser will read from far away in HBM --
+// the position's record, its match list in the pool, and for every (len, dist) pair the bytes at the end of
+// the match that the MATCH : LIT : REP0 trial compares (LzmaEnc.c:1876-1893).  It writes nothing, so it
+// cannot change the output; it only turns the parser's dependent HBM/L2 round trips into L1 hits.
+constexpr uint32_t kLzmaAhead = 6; // positions
+
+__device__ void lzma_lookahead_warp(const lzma::Enc *e, const LzmaJob &j, const volatile int *done)
+{
+	const uint32_t lane = threadIdx.x & 31u;
+	const volatile uint32_t *ppos = &e->pos;
+	const uint8_t *src = j.src;
+	const uint32_t n = j.n;
+	uint32_t upto = 0; // positions <= upto (1-based, like e->pos) are already prefetched
+	while (!*done) {
+		const uint32_t pos = *ppos;
+		uint32_t lo = pos + 1 > upto + 1 ? pos + 1 : upto + 1;
+		uint32_t hi = pos + kLzmaAhead < n ? pos + kLzmaAhead : n;
+		if (lo > hi) {
+			__nanosleep(200);
+			continue;
+		}
+		for (uint32_t q = lo; q <= hi; q++) {
+			const uint32_t i0 = q - 1;
+			const uint64_t rec = j.rec[i0];
+			const uint32_t nd = (uint32_t)rec & 1023u;
+			const uint32_t *lst = j.pool + (rec >> 10);
+			for (uint32_t k = lane; 2 * k < nd; k += 32) {
+				const uint32_t len = lst[2 * k], dist = lst[2 * k + 1];
+				if (dist < i0) {
+					const uint8_t *far = src + i0 - dist - 1;
+					lzma::lz_prefetch(far);
+					lzma::lz_prefetch(far + len + 2);
+				}
+			}
+		}
+		upto = hi;
+		__syncwarp();
+	}
+}
+
+__global__ void __launch_bounds__(64, 1) lzma_block_kernel(LzmaJob *jobs)
 {
 	extern __shared__ __align__(16) uint8_t lzma_smem[];
+	__shared__ int done;
 	lzma::Enc *e = reinterpret_cast<lzma::Enc *>(lzma_smem);
 	LzmaJob &j = jobs[blockIdx.x];
+	if (threadIdx.x >= 32) {
+		if (threadIdx.x == 32)
+			done = 0;
+		__syncthreads(); // the encoder state (e->pos) is initialised
+		lzma_lookahead_warp(e, j, &done);
+		return;
+	}
 	lzma::enc_init(e, j.cfg, j.src, j.n, j.out, j.outCap, nullptr, nullptr, nullptr, nullptr);
 	e->preRec = j.rec;
 	e->prePool = j.pool;
-	__syncwarp();
+	__syncthreads();
 	const uint64_t len = lzma::enc_run(e);
 	__syncwarp();
 	if (threadIdx.x == 0) {
+		done = 1;
 		j.outLen = len;
 		j.overflow = e->overflow;
 	}
@@ -375,7 +424,7 @@ static int run_lzma(BackendCtx *b, const lrzgpu_params &p, const lrzgpu_sizing_t
 			snprintf(err, errlen, "LZMA encoder state (%zu bytes) does not fit in shared memory", sizeof(lzma::Enc));
 			return LRZGPU_ECUDA;
 		}
-		lzma_block_kernel<<<(unsigned)lj.size(), 32, sizeof(lzma::Enc), stream>>>((LzmaJob *)J);
+		lzma_block_kernel<<<(unsigned)lj.size(), 64, sizeof(lzma::Enc), stream>>>((LzmaJob *)J);
 		if (launches)
 			(*launches)++;
 		if (cudaMemcpyAsync(lj.data(), J, o_mb, cudaMemcpyDeviceToHost, stream) != cudaSuccess)

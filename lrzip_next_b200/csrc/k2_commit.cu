@@ -380,6 +380,7 @@ struct LaneEval {
 	unsigned rlo[K2_MAXW], rlen[K2_MAXW]; // probe ranges read (start slot, length), modulo the table size
 	int nw, nr, net, ins, miss;
 	int chain; // the insert met max_chain_len equal-tag entries: the victim slot is chosen at commit time (eslot[])
+	int twin;  // evaluated as the second of two adjacent candidates with the same tag (see group_eval_t)
 	bool cx;
 };
 
@@ -389,8 +390,6 @@ struct FastShared {
 	long long qpos[64], qtag[64]; // queue of upcoming candidates that pass the current gate
 	unsigned dslot[32];           // sweep deletions of the current batch, in order
 	LaneEval ev[32];              // evaluation results of the batch, written by the 8-lane groups
-	unsigned vslot[32 * (K2_MAXW + 1)]; // validation: slots written by the batch, in lane order ...
-	unsigned char vown[32 * (K2_MAXW + 1)]; // ... and the lane that writes each
 	long long eq_off[8][4][K2_MAXEQ]; // per warp and group: offsets of the equal-tag entries met on the walk
 	unsigned eslot[32][K2_MAXEQ];     // per candidate: the slots of those entries, in walk order (chain-cap victims)
 	// batch evaluation command, written by the commit warp before barrier 1 (see k2_eval_worker)
@@ -783,6 +782,44 @@ __device__ void group_eval_t(const uint8_t *__restrict__ buf, const HEntry *tab,
 		}
 	}
 	__syncwarp();
+	// ---- twins.  The rolling tag is an XOR over the window, so positions p and p + 1 have the SAME tag whenever
+	// buf[p] == buf[p + 31] (about one position in 16 on text): the second of two such candidates reads exactly the
+	// chain the first one writes to, which used to end the batch at it.  Both walk the same chain from the same
+	// table, so this group knows what its predecessor does and evaluates its own candidate on the table as the
+	// predecessor leaves it -- for the two common cases:
+	//   predecessor appends at the chain end E and E + 1 is empty: this candidate meets one more equal-tag entry
+	//     (the predecessor's, a tag miss unless the two windows really match) and appends at E + 1, or evicts when
+	//     that entry completes the chain;
+	//   predecessor evicts from a full chain: the chain keeps its slots, this candidate evicts the next victim.
+	// The commit warp skips the predecessor's insert when it checks this lane's reads (L.twin).
+	bool tw = active && !cx && do_insert && cand_idx >= 1 && sh->qtag[cand_idx - 1] == t &&
+		  !(cand_idx >= 2 && sh->qtag[cand_idx - 2] == t);
+	if (__any_sync(FULL, tw)) {
+		const bool twE = tw && kind == kProbeEmpty, twC = tw && kind == kProbeChain;
+		HEntry nx;
+		nx.offset = nx.tag = 1;
+		if (twE)
+			nx = ld_entry(tab + ((sslot + 1) & hmask));
+		const bool ok = twC || (twE && !(nx.offset | nx.tag));
+		const bool nm = ok && quick_no_match(buf, p, sh->qpos[cand_idx - 1], end, last_match);
+		if (ok && !nm)
+			cx = true; // the two windows may really match: the serial step decides
+		if (nm && twE) {
+			miss += 1;
+			if (round + 1 >= max_chain) {
+				if (neq < K2_MAXEQ && max_chain <= K2_MAXEQ) {
+					if (gl == 0)
+						sh->eslot[cand_idx][neq] = sslot;
+					kind = kProbeChain;
+				} else
+					cx = true;
+			} else
+				sslot = (sslot + 1) & hmask;
+			s += 1; // the read range grows by the slot after the old chain end
+		}
+		tw = nm && !cx;
+	}
+	__syncwarp();
 	// ---- equal-tag entries: would any of them give a match?  (then the serial step must decide)
 	// One lane per entry dismisses the ones whose bytes differ at once (all loads in flight together);
 	// the rare survivors get the group-wide compare.
@@ -915,6 +952,7 @@ __device__ void group_eval_t(const uint8_t *__restrict__ buf, const HEntry *tab,
 		R->ins = ins;
 		R->miss = miss;
 		R->chain = (!cx && ins && nw == 1 && kind == kProbeChain) ? 1 : 0;
+		R->twin = (tw && !cx) ? 1 : 0;
 		R->cx = cx;
 	}
 	__syncwarp();
@@ -1089,7 +1127,7 @@ __device__ void k2_commit_segment_batched(WarpPrim &prim, FastShared *sh, ScanSt
 		}
 		const int mode = k2_mode_for(r.tag_mask);
 		LaneEval L;
-		L.nw = L.nr = L.net = L.ins = L.miss = L.chain = 0;
+		L.nw = L.nr = L.net = L.ins = L.miss = L.chain = L.twin = 0;
 		L.cx = false;
 		int64_t myp = 0, myt = 0;
 		dbg[0]++;
@@ -1248,34 +1286,39 @@ __device__ void k2_commit_segment_batched(WarpPrim &prim, FastShared *sh, ScanSt
 		{
 			const unsigned stop0 = __ballot_sync(FULL, lane < nb && stopper);
 			const int nv = stop0 ? __ffs(stop0) : nb;
+			constexpr unsigned NONE = 0xffffffffu;
 			const int myn = lane < nv ? nwt : 0;
-			int incl = myn;
-#pragma unroll
-			for (int d = 1; d < 32; d <<= 1) {
-				const int o = __shfl_up_sync(FULL, incl, d);
-				if (lane >= d)
-					incl += o;
-			}
-			const int total = __shfl_sync(FULL, incl, 31);
-			for (int w = 0; w < myn; w++) {
-				sh->vslot[incl - myn + w] = L.wslot[w];
-				sh->vown[incl - myn + w] = (unsigned char)lane;
-			}
-			__syncwarp();
+			// nearly every lane writes one slot (its insert) or two (and the sweep deletion it triggers): those
+			// travel by shuffle, one writer lane per step; deeper displacement chains take the extra loop below
+			const unsigned w0 = myn > 0 ? L.wslot[0] : NONE, w1 = myn > 1 ? L.wslot[1] : NONE;
+			const unsigned manym = __ballot_sync(FULL, myn > 2);
 			const int mynr = lane < nv ? L.nr : 0;
 			const unsigned rlo0 = L.rlo[0], rlen0 = L.rlen[0];
-			for (int i = 0; i < total; i++) {
-				const unsigned sl = sh->vslot[i];
-				const int ow = sh->vown[i];
-				if (ow < lane && mynr > 0) {
-					bool hit = ((sl - rlo0) & hmask) < rlen0;
-					for (int q = 1; q < mynr; q++)
-						hit = hit || ((sl - L.rlo[q]) & hmask) < L.rlen[q];
-					if (hit)
-						cmask |= 1u << ow;
+			auto reads = [&](unsigned sl) {
+				bool hit = ((sl - rlo0) & hmask) < rlen0;
+				for (int q = 1; q < mynr; q++)
+					hit = hit || ((sl - L.rlo[q]) & hmask) < L.rlen[q];
+				return hit;
+			};
+			for (int i = 0; i + 1 < nv; i++) {
+				const unsigned a0 = __shfl_sync(FULL, w0, i), a1 = __shfl_sync(FULL, w1, i);
+				if (lane > i && mynr > 0) {
+					// a twin was evaluated on the table as its predecessor's insert leaves it
+					const bool skip0 = L.twin && i == lane - 1;
+					if ((a0 != NONE && !skip0 && reads(a0)) || (a1 != NONE && reads(a1)))
+						cmask |= 1u << i;
 				}
 			}
-			__syncwarp();
+			for (unsigned mm = manym; mm; mm &= mm - 1) {
+				const int i = __ffs(mm) - 1;
+				const int ni = __shfl_sync(FULL, myn, i);
+#pragma unroll
+				for (int w = 2; w < K2_MAXW + 1; w++) {
+					const unsigned a = __shfl_sync(FULL, L.wslot[w], i);
+					if (w < ni && lane > i && mynr > 0 && reads(a))
+						cmask |= 1u << i;
+				}
+			}
 		}
 		dbg[13] += clock64() - cv0;
 		const long long cc0 = clock64();
