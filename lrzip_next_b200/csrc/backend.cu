@@ -80,8 +80,11 @@ struct LzmaJob {
 	const uint64_t *rec;  // match lists of the data-parallel finder (lzma_mf.cu)
 	const uint32_t *pool;
 	lzma::Config cfg;
+	const int *gate_result; // lz4 gate verdict of this block (device), or null when the gate is off
+	const int *mf_overflow; // the match finder ran out of pool for this block: encode it again with a larger one
 	uint64_t outLen;
 	int overflow;
+	int skipped;            // 1: gate said incompressible, 2: match-list pool overflow
 };
 
 // K7b: optimal parser + range coder, one block per CTA, over the precomputed match lists.
@@ -134,6 +137,14 @@ __global__ void __launch_bounds__(64, 1) lzma_block_kernel(LzmaJob *jobs)
 	__shared__ int done;
 	lzma::Enc *e = reinterpret_cast<lzma::Enc *>(lzma_smem);
 	LzmaJob &j = jobs[blockIdx.x];
+	{ // verdicts of the stages that ran before, read on the device so that the host never waits for them
+		const int why = (j.gate_result && *j.gate_result == 0) ? 1 : (*j.mf_overflow ? 2 : 0);
+		if (why) { // uniform over the CTA
+			if (threadIdx.x == 0)
+				j.skipped = why;
+			return;
+		}
+	}
 	if (threadIdx.x >= 32) {
 		if (threadIdx.x == 32)
 			done = 0;
@@ -197,8 +208,76 @@ int64_t round_up_page(int64_t v, int page) { return v % page ? v + page - v % pa
 
 } // namespace
 
+// ---- LZMA pipeline ------------------------------------------------------------------------------------
+// Blocks are SUBMITTED (lz4 gate, match finder, parser enqueued on the backend's own streams, no host wait)
+// and later DRAINED (wait, read verdicts and lengths).  The rzip stage submits stream-1 blocks while it is
+// still scanning (src/stream.c:1836-1875: the reference hands a block to a compthread the moment it fills);
+// the synchronous entry point is submit-everything-then-drain.
+struct SlotLay {
+	size_t son, c2, c3, sorted, ctl, rec, pool, end;
+	uint64_t poolCap;
+};
+
+static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+static SlotLay lay_for(size_t n, bool hc5, unsigned poolMul)
+{
+	const size_t minAvail = hc5 ? 5 : 4, count = n >= minAvail ? n - (minAvail - 1) : 0;
+	SlotLay L;
+	size_t o = 0;
+	L.son = o;
+	o += hc5 ? 256 : align_up(8 * (n + 2), 256); // the hash-chain finder keeps its links in `sorted`
+	L.c2 = o;
+	o += align_up(4 * count + 4, 256);
+	L.c3 = o;
+	o += align_up(4 * count + 4, 256);
+	L.sorted = o;
+	o += align_up(4 * count + 4, 256);
+	L.ctl = o; // cursor, overflow flag; zeroed together with rec
+	o += 256;
+	L.rec = o;
+	o += align_up(8 * n, 256);
+	L.pool = o;
+	L.poolCap = (uint64_t)poolMul * n + 65536;
+	o += align_up(4 * L.poolCap, 256);
+	L.end = o;
+	return L;
+}
+
+constexpr unsigned kPoolMul = 12; // uint32 of match-list pool per input byte; text needs ~6-9
+
+struct AsyncSub {
+	BlockJob job;
+	lzma::Config cfg;
+	size_t oofs = 0;     // payload offset in BackendCtx::out
+	int group = -1;
+	int index_in_group = 0;
+	bool done = false;
+};
+
+struct AsyncGroup {
+	size_t first = 0, count = 0; // subs[first .. first + count)
+	size_t meta_off = 0;         // [LzmaJob x m][MfBlock x m][segBase x (m + 1)][GateJob x m] in BackendCtx::meta
+	cudaStream_t ps = nullptr;   // parser stream
+	bool gated = false;
+};
+
 struct BackendCtx {
-	DevBuf jobs, work, out, flags, offs, scratch;
+	DevBuf jobs, work, out, flags, offs, scratch, meta, big;
+	cudaStream_t sMF = nullptr, sGate = nullptr;
+	std::vector<cudaStream_t> pstreams;
+	std::vector<cudaEvent_t> events;
+	size_t ev_next = 0;
+	// state of the chunk being encoded
+	bool active = false;
+	lrzgpu_params p;
+	lrzgpu_sizing_t sz;
+	uint32_t fb = 0;
+	size_t slot_bytes = 0, max_block = 0;
+	int nslots = 0, slots_used = 0;
+	size_t out_used = 0, meta_used = 0;
+	std::vector<AsyncSub> subs;
+	std::vector<AsyncGroup> groups; // enqueued since the last drain
 };
 
 BackendCtx *backend_create() { return new BackendCtx(); }
@@ -207,39 +286,29 @@ void backend_destroy(BackendCtx *b)
 {
 	if (!b)
 		return;
-	b->jobs.release();
-	b->work.release();
-	b->out.release();
-	b->flags.release();
-	b->offs.release();
-	b->scratch.release();
+	DevBuf *bufs[] = { &b->jobs, &b->work, &b->out, &b->flags, &b->offs, &b->scratch, &b->meta, &b->big };
+	for (DevBuf *d : bufs)
+		d->release();
+	for (cudaStream_t s : b->pstreams)
+		cudaStreamDestroy(s);
+	for (cudaEvent_t e : b->events)
+		cudaEventDestroy(e);
+	if (b->sMF)
+		cudaStreamDestroy(b->sMF);
+	if (b->sGate)
+		cudaStreamDestroy(b->sGate);
 	delete b;
 }
 
-static int run_gate(BackendCtx *b, std::vector<BlockJob> &jobs, const std::vector<int> &idx, int threshold,
-		    std::vector<int> &pass, cudaStream_t stream, int64_t *launches)
+static cudaEvent_t next_event(BackendCtx *b)
 {
-	std::vector<GateJob> g(idx.size());
-	for (size_t i = 0; i < idx.size(); i++) {
-		g[i].src = jobs[idx[i]].d_src;
-		g[i].len = jobs[idx[i]].u_len;
-		g[i].result = 0;
+	if (b->ev_next == b->events.size()) {
+		cudaEvent_t e = nullptr;
+		if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess)
+			return nullptr;
+		b->events.push_back(e);
 	}
-	if (b->jobs.ensure(g.size() * sizeof(GateJob)) != cudaSuccess)
-		return LRZGPU_ENOMEM;
-	if (cudaMemcpyAsync(b->jobs.p, g.data(), g.size() * sizeof(GateJob), cudaMemcpyHostToDevice, stream) != cudaSuccess)
-		return LRZGPU_ECUDA;
-	lz4_gate_kernel<<<(unsigned)g.size(), 32, 0, stream>>>((GateJob *)b->jobs.p, threshold);
-	if (launches)
-		(*launches)++;
-	if (cudaMemcpyAsync(g.data(), b->jobs.p, g.size() * sizeof(GateJob), cudaMemcpyDeviceToHost, stream) != cudaSuccess ||
-	    cudaStreamSynchronize(stream) != cudaSuccess)
-		return LRZGPU_ECUDA;
-	pass.clear();
-	for (size_t i = 0; i < idx.size(); i++)
-		if (g[i].result)
-			pass.push_back(idx[i]);
-	return LRZGPU_OK;
+	return b->events[b->ev_next++];
 }
 
 int backend_lz4_gate(BackendCtx *b, const uint8_t *d_src, int64_t len, int threshold, int *result, cudaStream_t stream,
@@ -260,197 +329,374 @@ int backend_lz4_gate(BackendCtx *b, const uint8_t *d_src, int64_t len, int thres
 	return LRZGPU_OK;
 }
 
-static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
-
-// All LZMA blocks of a chunk: K7a (match finder, data-parallel over positions and buckets) then K7b
-// (parser + range coder, one CTA per block).  Work arrays are laid out per block in one arena; blocks
-// are taken in waves when the arena does not fit in free HBM.  Payloads of all waves stay in b->out.
-static int run_lzma(BackendCtx *b, const lrzgpu_params &p, const lrzgpu_sizing_t &sz, std::vector<BlockJob> &jobs,
-		    const std::vector<int> &idx, cudaStream_t stream, int64_t *launches, char *err, size_t errlen)
+int backend_async_begin(BackendCtx *b, const lrzgpu_params &p, const lrzgpu_sizing_t &sz, int64_t max_block_len,
+			int64_t max_blocks, int64_t payload_bytes_upper, char *err, size_t errlen)
 {
-	const uint32_t fb = p.level < 7 ? 32 : 64; // src/stream.c:455
+	b->active = false;
+	if (p.backend != LRZGPU_BACKEND_LZMA) {
+		snprintf(err, errlen, "the block pipeline is the LZMA backend's");
+		return LRZGPU_EUNSUPPORTED;
+	}
 	if (lzma::mf_init_tables()) {
 		snprintf(err, errlen, "LZMA match finder tables: %s", cudaGetErrorString(cudaGetLastError()));
 		return LRZGPU_ECUDA;
 	}
-	// payload area for every block of the chunk
-	std::vector<size_t> oofs(idx.size());
-	std::vector<lzma::Config> cfgs(idx.size());
-	size_t osum = 0;
-	uint32_t maxCount = 0;
-	for (size_t k = 0; k < idx.size(); k++) {
-		const BlockJob &bj = jobs[idx[k]];
-		if (!lzma::make_config(p.level, sz.dict_size, fb, (uint64_t)bj.u_len, cfgs[k]) || fb > lzma::kMfMaxFb) {
-			snprintf(err, errlen, "LZMA level %d / block of %lld bytes is not supported by the device encoder", p.level,
-				 (long long)bj.u_len);
-			return LRZGPU_EUNSUPPORTED;
-		}
-		oofs[k] = osum;
-		osum += align_up((size_t)round_up_page((int64_t)((double)bj.u_len * 1.02), p.page_size), 256);
-		const uint32_t minAvail = cfgs[k].fastMode ? 5 : 4;
-		const uint32_t count = bj.u_len >= minAvail ? (uint32_t)bj.u_len - (minAvail - 1) : 0;
-		if (count > maxCount)
-			maxCount = count;
+	if (!b->sMF && (cudaStreamCreateWithFlags(&b->sMF, cudaStreamNonBlocking) != cudaSuccess ||
+			cudaStreamCreateWithFlags(&b->sGate, cudaStreamNonBlocking) != cudaSuccess)) {
+		snprintf(err, errlen, "backend streams: %s", cudaGetErrorString(cudaGetLastError()));
+		return LRZGPU_ECUDA;
 	}
-	const bool hc5 = cfgs[0].fastMode != 0; // one level per call: all blocks use the same finder
+	b->p = p;
+	b->sz = sz;
+	b->fb = p.level < 7 ? 32 : 64; // src/stream.c:455
+	lzma::Config cfg;
+	if (max_block_len < 1)
+		max_block_len = 1;
+	if (!lzma::make_config(p.level, sz.dict_size, b->fb, (uint64_t)max_block_len, cfg) || b->fb > lzma::kMfMaxFb) {
+		snprintf(err, errlen, "LZMA level %d / block of %lld bytes is not supported by the device encoder", p.level,
+			 (long long)max_block_len);
+		return LRZGPU_EUNSUPPORTED;
+	}
+	const bool hc5 = cfg.fastMode != 0;
 	const size_t minAvail = hc5 ? 5 : 4;
+	b->max_block = (size_t)max_block_len;
+	b->slot_bytes = align_up(lay_for(b->max_block, hc5, kPoolMul).end, 4096);
+	const uint32_t maxCount = b->max_block >= minAvail ? (uint32_t)(b->max_block - (minAvail - 1)) : 0;
 	const size_t scratch_bytes = align_up(lzma::mf_sort_scratch_bytes(maxCount), 256);
-	if (b->out.ensure(osum) != cudaSuccess || b->scratch.ensure(scratch_bytes) != cudaSuccess) {
-		snprintf(err, errlen, "out of device memory for LZMA payloads / sort scratch (%zu MiB)", (osum + scratch_bytes) >> 20);
+	const size_t out_bytes = (size_t)payload_bytes_upper + (size_t)payload_bytes_upper / 50 + (size_t)(max_blocks + 1) * 8192;
+	const size_t meta_bytes = (size_t)(max_blocks + 1) * (sizeof(LzmaJob) + sizeof(lzma::MfBlock) + sizeof(GateJob) + 16 + 1024);
+	if (b->out.ensure(out_bytes) != cudaSuccess || b->scratch.ensure(scratch_bytes) != cudaSuccess ||
+	    b->meta.ensure(meta_bytes) != cudaSuccess) {
+		snprintf(err, errlen, "out of device memory for LZMA payloads / sort scratch (%zu MiB)", (out_bytes + scratch_bytes) >> 20);
 		return LRZGPU_ENOMEM;
 	}
 	size_t free_b = 0, total_b = 0;
 	cudaMemGetInfo(&free_b, &total_b);
-	const size_t budget = free_b + b->work.cap > (2ull << 30) ? free_b + b->work.cap - (1ull << 30) : free_b + b->work.cap;
+	const size_t have = free_b + b->work.cap;
+	const size_t budget = have > (3ull << 30) ? have - (2ull << 30) : have / 2;
+	int64_t slots = (int64_t)(budget / b->slot_bytes);
+	if (slots > max_blocks)
+		slots = max_blocks;
+	if (slots < 1)
+		slots = 1;
+	if (b->work.ensure((size_t)slots * b->slot_bytes) != cudaSuccess) {
+		snprintf(err, errlen, "out of device memory for %lld LZMA block encoders (%zu MiB)", (long long)slots,
+			 ((size_t)slots * b->slot_bytes) >> 20);
+		return LRZGPU_ENOMEM;
+	}
+	b->nslots = (int)slots;
+	b->slots_used = 0;
+	b->out_used = b->meta_used = 0;
+	b->subs.clear();
+	b->groups.clear();
+	b->ev_next = 0;
+	if (cudaFuncSetAttribute(lzma_block_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(lzma::Enc)) != cudaSuccess) {
+		snprintf(err, errlen, "LZMA encoder state (%zu bytes) does not fit in shared memory", sizeof(lzma::Enc));
+		return LRZGPU_ECUDA;
+	}
+	b->active = true;
+	return LRZGPU_OK;
+}
 
-	struct Lay {
-		size_t son, c2, c3, sorted, ctl, rec, pool, end;
-		uint64_t poolCap;
-	};
-	size_t at = 0;
-	unsigned poolMul = 12; // uint32 of match-list pool per input byte; text needs ~6-9, raised on overflow
-	while (at < idx.size()) {
-		std::vector<Lay> lay;
-		size_t wsum = 0, first = at;
-		const auto t_wave = std::chrono::steady_clock::now();
-		for (; at < idx.size(); at++) {
-			const size_t n = (size_t)jobs[idx[at]].u_len, count = n >= minAvail ? n - (minAvail - 1) : 0;
-			Lay L;
-			size_t o = wsum;
-			L.son = o;
-			o += hc5 ? 256 : align_up(8 * (n + 2), 256); // the hash-chain finder keeps its links in `sorted`
-			L.c2 = o;
-			o += align_up(4 * count + 4, 256);
-			L.c3 = o;
-			o += align_up(4 * count + 4, 256);
-			L.sorted = o;
-			o += align_up(4 * count + 4, 256);
-			L.ctl = o; // cursor, overflow flag; zeroed together with rec
-			o += 256;
-			L.rec = o;
-			o += align_up(8 * n, 256);
-			L.pool = o;
-			L.poolCap = (uint64_t)poolMul * n + 65536;
-			o += align_up(4 * L.poolCap, 256);
-			L.end = o;
-			if (!lay.empty() && o > budget)
-				break;
-			lay.push_back(L);
-			wsum = o;
-		}
-		if (b->work.ensure(wsum) != cudaSuccess || b->jobs.ensure(lay.size() * (sizeof(LzmaJob) + sizeof(lzma::MfBlock) + 8) + 64) != cudaSuccess) {
-			snprintf(err, errlen, "out of device memory for %zu LZMA block encoders (%zu MiB)", lay.size(), wsum >> 20);
-			return LRZGPU_ENOMEM;
-		}
-		uint8_t *W = (uint8_t *)b->work.p;
-		std::vector<LzmaJob> lj(lay.size());
-		std::vector<lzma::MfBlock> mb(lay.size());
-		std::vector<uint64_t> seg(lay.size() + 1, 0);
-		for (size_t i = 0; i < lay.size(); i++) {
-			const BlockJob &bj = jobs[idx[first + i]];
-			const Lay &L = lay[i];
-			const lzma::Config &c = cfgs[first + i];
-			lzma::MfBlock &B = mb[i];
-			B.src = bj.d_src;
-			B.P.n = (uint32_t)bj.u_len;
-			B.P.fb = c.fb;
-			B.P.mc = c.mc;
-			B.P.hashMask = c.hashMask;
-			B.P.bigHash = c.bigHash;
-			B.P.historySize = c.historySize;
-			B.P.cyclicSize = c.cyclicSize;
-			B.P.hc5 = c.fastMode;
-			B.count = (size_t)bj.u_len >= minAvail ? (uint32_t)bj.u_len - (uint32_t)(minAvail - 1) : 0;
-			B.son = (uint32_t *)(W + L.son);
-			B.c2 = (uint32_t *)(W + L.c2);
-			B.c3 = (uint32_t *)(W + L.c3);
-			B.sorted = (uint32_t *)(W + L.sorted);
-			B.cursor = (unsigned long long *)(W + L.ctl);
-			B.overflow = (int *)(W + L.ctl + 8);
-			B.rec = (uint64_t *)(W + L.rec);
-			B.pool = (uint32_t *)(W + L.pool);
-			B.poolCap = L.poolCap;
-			seg[i + 1] = seg[i] + B.count;
-			LzmaJob &j = lj[i];
-			memset(&j, 0, sizeof(j));
-			j.src = bj.d_src;
-			j.n = (uint32_t)bj.u_len;
-			j.out = (uint8_t *)b->out.p + oofs[first + i];
-			j.outCap = (uint64_t)round_up_page((int64_t)((double)bj.u_len * 1.02), p.page_size);
-			j.rec = B.rec;
-			j.pool = B.pool;
-			j.cfg = c;
-			if (cudaMemsetAsync(W + L.ctl, 0, 256 + 8 * (size_t)bj.u_len, stream) != cudaSuccess)
-				return LRZGPU_ECUDA;
-			if (lzma::mf_prepare_block(B, b->scratch.p, stream, launches)) {
-				snprintf(err, errlen, "LZMA match finder sort: %s", cudaGetErrorString(cudaGetLastError()));
-				return LRZGPU_ECUDA;
-			}
-		}
-		// job table: [LzmaJob x m][MfBlock x m][segBase x (m + 1)]
-		uint8_t *J = (uint8_t *)b->jobs.p;
-		const size_t o_mb = lay.size() * sizeof(LzmaJob), o_seg = o_mb + lay.size() * sizeof(lzma::MfBlock);
-		if (cudaMemcpyAsync(J, lj.data(), o_mb, cudaMemcpyHostToDevice, stream) != cudaSuccess ||
-		    cudaMemcpyAsync(J + o_mb, mb.data(), lay.size() * sizeof(lzma::MfBlock), cudaMemcpyHostToDevice, stream) != cudaSuccess ||
-		    cudaMemcpyAsync(J + o_seg, seg.data(), seg.size() * 8, cudaMemcpyHostToDevice, stream) != cudaSuccess)
-			return LRZGPU_ECUDA;
-		if (lzma::mf_walk_launch((const lzma::MfBlock *)(J + o_mb), (int)lay.size(), (const uint64_t *)(J + o_seg), seg.back(),
-					 hc5, stream, launches)) {
-			snprintf(err, errlen, "LZMA match finder walk: %s", cudaGetErrorString(cudaGetLastError()));
+// Enqueue gate + match finder + parser for subs[first .. first + m) whose work arrays start at `bases[i]`.
+static int enqueue_group(BackendCtx *b, size_t first, size_t m, const std::vector<uint8_t *> &bases, unsigned poolMul,
+			 bool gate, cudaEvent_t ready, int64_t *launches, char *err, size_t errlen)
+{
+	AsyncGroup G;
+	G.first = first;
+	G.count = m;
+	G.gated = gate;
+	const size_t o_mb = m * sizeof(LzmaJob), o_seg = align_up(o_mb + m * sizeof(lzma::MfBlock), 8);
+	const size_t o_gate = align_up(o_seg + (m + 1) * 8, 8), total = align_up(o_gate + m * sizeof(GateJob), 256);
+	if (b->meta_used + total > b->meta.cap)
+		return 1; // drain first
+	G.meta_off = b->meta_used;
+	b->meta_used += total;
+	uint8_t *J = (uint8_t *)b->meta.p + G.meta_off;
+	// parser stream of this group: its kernel runs for the whole encode of the blocks, so every group that is
+	// in flight at the same time needs its own
+	const size_t gi = b->groups.size();
+	while (b->pstreams.size() <= gi) {
+		cudaStream_t s = nullptr;
+		if (cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking) != cudaSuccess) {
+			snprintf(err, errlen, "parser stream: %s", cudaGetErrorString(cudaGetLastError()));
 			return LRZGPU_ECUDA;
 		}
-		// pool overflow check before the parser consumes the lists
-		std::vector<int> ovf(lay.size(), 0);
-		for (size_t i = 0; i < lay.size(); i++)
-			if (cudaMemcpyAsync(&ovf[i], mb[i].overflow, 4, cudaMemcpyDeviceToHost, stream) != cudaSuccess)
-				return LRZGPU_ECUDA;
-		cudaError_t ce = cudaStreamSynchronize(stream);
-		if (ce != cudaSuccess) {
-			snprintf(err, errlen, "LZMA match finder failed: %s", cudaGetErrorString(ce));
+		b->pstreams.push_back(s);
+	}
+	G.ps = b->pstreams[gi];
+	cudaEvent_t evGate = nullptr, evMF = next_event(b);
+	if (!evMF)
+		return LRZGPU_ECUDA;
+	if (ready) {
+		if (cudaStreamWaitEvent(b->sMF, ready, 0) != cudaSuccess)
+			return LRZGPU_ECUDA;
+		if (gate && cudaStreamWaitEvent(b->sGate, ready, 0) != cudaSuccess)
+			return LRZGPU_ECUDA;
+	}
+	std::vector<LzmaJob> lj(m);
+	std::vector<lzma::MfBlock> mb(m);
+	std::vector<uint64_t> seg(m + 1, 0);
+	std::vector<GateJob> gj(m);
+	bool hc5 = false;
+	for (size_t i = 0; i < m; i++) {
+		AsyncSub &S = b->subs[first + i];
+		const BlockJob &bj = S.job;
+		const lzma::Config &c = S.cfg;
+		hc5 = c.fastMode != 0;
+		const size_t minAvail = hc5 ? 5 : 4;
+		const SlotLay L = lay_for((size_t)bj.u_len, hc5, poolMul);
+		uint8_t *W = bases[i];
+		lzma::MfBlock &B = mb[i];
+		B.src = bj.d_src;
+		B.P.n = (uint32_t)bj.u_len;
+		B.P.fb = c.fb;
+		B.P.mc = c.mc;
+		B.P.hashMask = c.hashMask;
+		B.P.bigHash = c.bigHash;
+		B.P.historySize = c.historySize;
+		B.P.cyclicSize = c.cyclicSize;
+		B.P.hc5 = c.fastMode;
+		B.count = (size_t)bj.u_len >= minAvail ? (uint32_t)bj.u_len - (uint32_t)(minAvail - 1) : 0;
+		B.son = (uint32_t *)(W + L.son);
+		B.c2 = (uint32_t *)(W + L.c2);
+		B.c3 = (uint32_t *)(W + L.c3);
+		B.sorted = (uint32_t *)(W + L.sorted);
+		B.cursor = (unsigned long long *)(W + L.ctl);
+		B.overflow = (int *)(W + L.ctl + 8);
+		B.rec = (uint64_t *)(W + L.rec);
+		B.pool = (uint32_t *)(W + L.pool);
+		B.poolCap = L.poolCap;
+		seg[i + 1] = seg[i] + B.count;
+		gj[i].src = bj.d_src;
+		gj[i].len = bj.u_len;
+		gj[i].result = 0;
+		LzmaJob &j = lj[i];
+		memset(&j, 0, sizeof(j));
+		j.src = bj.d_src;
+		j.n = (uint32_t)bj.u_len;
+		j.out = (uint8_t *)b->out.p + S.oofs;
+		j.outCap = (uint64_t)round_up_page((int64_t)((double)bj.u_len * 1.02), b->p.page_size);
+		j.rec = B.rec;
+		j.pool = B.pool;
+		j.cfg = c;
+		j.gate_result = gate ? &((GateJob *)(J + o_gate))[i].result : nullptr;
+		j.mf_overflow = B.overflow;
+		S.group = (int)gi;
+		S.index_in_group = (int)i;
+		if (cudaMemsetAsync(W + L.ctl, 0, 256 + 8 * (size_t)bj.u_len, b->sMF) != cudaSuccess)
+			return LRZGPU_ECUDA;
+		if (lzma::mf_prepare_block(B, b->scratch.p, b->sMF, launches)) {
+			snprintf(err, errlen, "LZMA match finder sort: %s", cudaGetErrorString(cudaGetLastError()));
 			return LRZGPU_ECUDA;
 		}
-		const auto t_mf = std::chrono::steady_clock::now();
-		bool any_ovf = false;
-		for (int v : ovf)
-			any_ovf = any_ovf || v;
-		if (any_ovf) { // redo this wave with a larger pool (worst case 2 * (fb - 3) + 4 words per position)
-			if (poolMul >= 2 * fb)
-				return LRZGPU_EINTERNAL;
-			poolMul = poolMul < 40 ? 40 : 2 * fb;
-			at = first;
-			continue;
-		}
-		if (cudaFuncSetAttribute(lzma_block_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(lzma::Enc)) != cudaSuccess) {
-			snprintf(err, errlen, "LZMA encoder state (%zu bytes) does not fit in shared memory", sizeof(lzma::Enc));
+	}
+	if (cudaMemcpyAsync(J, lj.data(), o_mb, cudaMemcpyHostToDevice, b->sMF) != cudaSuccess ||
+	    cudaMemcpyAsync(J + o_mb, mb.data(), m * sizeof(lzma::MfBlock), cudaMemcpyHostToDevice, b->sMF) != cudaSuccess ||
+	    cudaMemcpyAsync(J + o_seg, seg.data(), seg.size() * 8, cudaMemcpyHostToDevice, b->sMF) != cudaSuccess)
+		return LRZGPU_ECUDA;
+	if (gate) { // runs beside the match finder; the parser kernel reads the verdict on the device
+		evGate = next_event(b);
+		if (!evGate ||
+		    cudaMemcpyAsync(J + o_gate, gj.data(), m * sizeof(GateJob), cudaMemcpyHostToDevice, b->sGate) != cudaSuccess)
 			return LRZGPU_ECUDA;
-		}
-		lzma_block_kernel<<<(unsigned)lj.size(), 64, sizeof(lzma::Enc), stream>>>((LzmaJob *)J);
+		lz4_gate_kernel<<<(unsigned)m, 32, 0, b->sGate>>>((GateJob *)(J + o_gate), b->p.threshold);
 		if (launches)
 			(*launches)++;
-		if (cudaMemcpyAsync(lj.data(), J, o_mb, cudaMemcpyDeviceToHost, stream) != cudaSuccess)
+		if (cudaEventRecord(evGate, b->sGate) != cudaSuccess)
 			return LRZGPU_ECUDA;
-		ce = cudaStreamSynchronize(stream);
+	}
+	if (lzma::mf_walk_launch((const lzma::MfBlock *)(J + o_mb), (int)m, (const uint64_t *)(J + o_seg), seg.back(), hc5, b->sMF,
+				 launches)) {
+		snprintf(err, errlen, "LZMA match finder walk: %s", cudaGetErrorString(cudaGetLastError()));
+		return LRZGPU_ECUDA;
+	}
+	if (cudaEventRecord(evMF, b->sMF) != cudaSuccess || cudaStreamWaitEvent(G.ps, evMF, 0) != cudaSuccess ||
+	    (evGate && cudaStreamWaitEvent(G.ps, evGate, 0) != cudaSuccess))
+		return LRZGPU_ECUDA;
+	lzma_block_kernel<<<(unsigned)m, 64, sizeof(lzma::Enc), G.ps>>>((LzmaJob *)J);
+	if (launches)
+		(*launches)++;
+	if (cudaGetLastError() != cudaSuccess) {
+		snprintf(err, errlen, "LZMA kernel launch: %s", cudaGetErrorString(cudaGetLastError()));
+		return LRZGPU_ECUDA;
+	}
+	b->groups.push_back(G);
+	return LRZGPU_OK;
+}
+
+// Submit `n` blocks (u_len >= 64) as one group.  `ready`: event after which their bytes are in place (or null).
+// Returns 0, a negative error, or 1 when the work space is used up: drain, then submit again.
+int backend_async_submit(BackendCtx *b, const BlockJob *jobs, int n, cudaEvent_t ready, int64_t *launches, char *err,
+			 size_t errlen)
+{
+	if (!b->active || n <= 0)
+		return b->active ? LRZGPU_OK : LRZGPU_EINVAL;
+	if (b->slots_used + n > b->nslots)
+		return 1;
+	size_t osum = b->out_used;
+	std::vector<AsyncSub> add((size_t)n);
+	for (int i = 0; i < n; i++) {
+		AsyncSub &S = add[(size_t)i];
+		S.job = jobs[i];
+		S.job.c_type = LRZGPU_CTYPE_NONE;
+		S.job.c_len = jobs[i].u_len;
+		S.job.d_payload = jobs[i].d_src;
+		if ((size_t)jobs[i].u_len > b->max_block ||
+		    !lzma::make_config(b->p.level, b->sz.dict_size, b->fb, (uint64_t)jobs[i].u_len, S.cfg)) {
+			snprintf(err, errlen, "LZMA block of %lld bytes is not supported by the device encoder", (long long)jobs[i].u_len);
+			return LRZGPU_EUNSUPPORTED;
+		}
+		S.oofs = osum;
+		osum += align_up((size_t)round_up_page((int64_t)((double)jobs[i].u_len * 1.02), b->p.page_size), 256);
+	}
+	if (osum > b->out.cap) {
+		snprintf(err, errlen, "LZMA payload area exhausted");
+		return LRZGPU_EINTERNAL;
+	}
+	const size_t first = b->subs.size();
+	std::vector<uint8_t *> bases((size_t)n);
+	for (int i = 0; i < n; i++)
+		bases[(size_t)i] = (uint8_t *)b->work.p + (size_t)(b->slots_used + i) * b->slot_bytes;
+	b->subs.insert(b->subs.end(), add.begin(), add.end());
+	const int rc = enqueue_group(b, first, (size_t)n, bases, kPoolMul, b->p.threshold != 0, ready, launches, err, errlen);
+	if (rc) {
+		b->subs.resize(first);
+		return rc;
+	}
+	b->slots_used += n;
+	b->out_used = osum;
+	return LRZGPU_OK;
+}
+
+static int collect_groups(BackendCtx *b, std::vector<size_t> &redo, char *err, size_t errlen)
+{
+	for (const AsyncGroup &G : b->groups) {
+		cudaError_t ce = cudaStreamSynchronize(G.ps);
 		if (ce != cudaSuccess) {
 			snprintf(err, errlen, "LZMA kernel failed: %s", cudaGetErrorString(ce));
 			return LRZGPU_ECUDA;
 		}
-		if (getenv("LRZGPU_DEBUG")) {
-			const auto t_end = std::chrono::steady_clock::now();
-			fprintf(stderr, "[lrzgpu] lzma wave: %zu blocks, %llu positions, arena %zu MiB, match finder %.1f ms, parser %.1f ms\n",
-				lj.size(), (unsigned long long)seg.back(), wsum >> 20,
-				std::chrono::duration<double, std::milli>(t_mf - t_wave).count(),
-				std::chrono::duration<double, std::milli>(t_end - t_mf).count());
-		}
-		for (size_t i = 0; i < lj.size(); i++) {
-			BlockJob &bj = jobs[idx[first + i]];
+		std::vector<LzmaJob> lj(G.count);
+		if (cudaMemcpy(lj.data(), (uint8_t *)b->meta.p + G.meta_off, G.count * sizeof(LzmaJob), cudaMemcpyDeviceToHost) != cudaSuccess)
+			return LRZGPU_ECUDA;
+		for (size_t i = 0; i < G.count; i++) {
+			AsyncSub &S = b->subs[G.first + i];
+			S.done = true;
+			if (lj[i].skipped == 1)
+				continue; // LZ4_TEST (FLAG_THRESHOLD): incompressible blocks stay stored
+			if (lj[i].skipped == 2) {
+				S.done = false;
+				redo.push_back(G.first + i);
+				continue;
+			}
 			// src/stream.c:482-487: kept only when smaller; SZ_ERROR_OUTPUT_EOF leaves the block stored
-			if (!lj[i].overflow && (int64_t)lj[i].outLen < bj.u_len) {
-				bj.c_type = LRZGPU_CTYPE_LZMA;
-				bj.c_len = (int64_t)lj[i].outLen;
-				bj.d_payload = lj[i].out;
+			if (!lj[i].overflow && (int64_t)lj[i].outLen < S.job.u_len) {
+				S.job.c_type = LRZGPU_CTYPE_LZMA;
+				S.job.c_len = (int64_t)lj[i].outLen;
+				S.job.d_payload = lj[i].out;
 			}
 		}
 	}
+	b->groups.clear();
+	b->slots_used = 0;
+	b->meta_used = 0;
+	b->ev_next = 0;
+	return LRZGPU_OK;
+}
+
+// Wait for everything submitted so far; afterwards the work space is free again and backend_async_result()
+// answers for every submitted block.
+int backend_async_drain(BackendCtx *b, int64_t *launches, char *err, size_t errlen)
+{
+	if (!b->active)
+		return LRZGPU_EINVAL;
+	std::vector<size_t> redo;
+	int rc = collect_groups(b, redo, err, errlen);
+	if (rc)
+		return rc;
+	// blocks whose match lists did not fit the pool (worst case 2 * (fb - 3) + 4 words per position): again, one at
+	// a time, with a pool that cannot overflow
+	for (size_t k : redo) {
+		AsyncSub &S = b->subs[k];
+		const unsigned mul = 2 * b->fb + 8;
+		const SlotLay L = lay_for((size_t)S.job.u_len, S.cfg.fastMode != 0, mul);
+		if (b->big.ensure(L.end) != cudaSuccess) {
+			snprintf(err, errlen, "out of device memory for a %zu MiB LZMA match pool", L.end >> 20);
+			return LRZGPU_ENOMEM;
+		}
+		std::vector<uint8_t *> bases(1, (uint8_t *)b->big.p);
+		rc = enqueue_group(b, k, 1, bases, mul, false, nullptr, launches, err, errlen);
+		if (rc)
+			return rc < 0 ? rc : LRZGPU_EINTERNAL;
+		std::vector<size_t> again;
+		rc = collect_groups(b, again, err, errlen);
+		if (rc)
+			return rc;
+		if (!again.empty()) {
+			snprintf(err, errlen, "LZMA match pool overflow with the worst-case pool");
+			return LRZGPU_EINTERNAL;
+		}
+	}
+	return LRZGPU_OK;
+}
+
+int backend_async_count(const BackendCtx *b) { return (int)b->subs.size(); }
+
+const BlockJob *backend_async_result(const BackendCtx *b, int i)
+{
+	if (i < 0 || (size_t)i >= b->subs.size() || !b->subs[(size_t)i].done)
+		return nullptr;
+	return &b->subs[(size_t)i].job;
+}
+
+// All LZMA blocks of a chunk, synchronously: submit in as large groups as the work space takes, drain, repeat.
+static int run_lzma(BackendCtx *b, const lrzgpu_params &p, const lrzgpu_sizing_t &sz, std::vector<BlockJob> &jobs,
+		    const std::vector<int> &idx, cudaStream_t stream, int64_t *launches, char *err, size_t errlen)
+{
+	int64_t max_len = 0, sum = 0;
+	for (int i : idx) {
+		max_len = jobs[(size_t)i].u_len > max_len ? jobs[(size_t)i].u_len : max_len;
+		sum += jobs[(size_t)i].u_len;
+	}
+	if (cudaStreamSynchronize(stream) != cudaSuccess) // the blocks' bytes were produced on the caller's stream
+		return LRZGPU_ECUDA;
+	int rc = backend_async_begin(b, p, sz, max_len, (int64_t)idx.size(), sum, err, errlen);
+	if (rc)
+		return rc;
+	size_t at = 0;
+	while (at < idx.size()) {
+		size_t take = idx.size() - at;
+		if (take > (size_t)b->nslots)
+			take = (size_t)b->nslots;
+		std::vector<BlockJob> grp;
+		for (size_t k = 0; k < take; k++)
+			grp.push_back(jobs[(size_t)idx[at + k]]);
+		const auto t0 = std::chrono::steady_clock::now();
+		rc = backend_async_submit(b, grp.data(), (int)take, nullptr, launches, err, errlen);
+		if (rc == 1) {
+			snprintf(err, errlen, "LZMA work space exhausted on an empty pipeline");
+			rc = LRZGPU_EINTERNAL;
+		}
+		if (!rc)
+			rc = backend_async_drain(b, launches, err, errlen);
+		if (rc)
+			return rc;
+		if (getenv("LRZGPU_DEBUG"))
+			fprintf(stderr, "[lrzgpu] lzma wave: %zu blocks in %.1f ms\n", take,
+				std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count());
+		at += take;
+	}
+	for (size_t k = 0; k < idx.size(); k++) {
+		const BlockJob *r = backend_async_result(b, (int)k);
+		if (!r)
+			return LRZGPU_EINTERNAL;
+		BlockJob &bj = jobs[(size_t)idx[k]];
+		bj.c_type = r->c_type;
+		bj.c_len = r->c_len;
+		bj.d_payload = r->d_payload;
+	}
+	b->active = false;
 	return LRZGPU_OK;
 }
 
@@ -527,6 +773,33 @@ static int run_zstd(BackendCtx *b, std::vector<BlockJob> &jobs, const std::vecto
 	return LRZGPU_OK;
 }
 
+// lz4 gate of a list of blocks, synchronously (zstd path; the LZMA pipeline runs its gate on the device side)
+static int run_gate(BackendCtx *b, std::vector<BlockJob> &jobs, const std::vector<int> &idx, int threshold,
+		    std::vector<int> &pass, cudaStream_t stream, int64_t *launches)
+{
+	std::vector<GateJob> g(idx.size());
+	for (size_t i = 0; i < idx.size(); i++) {
+		g[i].src = jobs[idx[i]].d_src;
+		g[i].len = jobs[idx[i]].u_len;
+		g[i].result = 0;
+	}
+	if (b->jobs.ensure(g.size() * sizeof(GateJob)) != cudaSuccess)
+		return LRZGPU_ENOMEM;
+	if (cudaMemcpyAsync(b->jobs.p, g.data(), g.size() * sizeof(GateJob), cudaMemcpyHostToDevice, stream) != cudaSuccess)
+		return LRZGPU_ECUDA;
+	lz4_gate_kernel<<<(unsigned)g.size(), 32, 0, stream>>>((GateJob *)b->jobs.p, threshold);
+	if (launches)
+		(*launches)++;
+	if (cudaMemcpyAsync(g.data(), b->jobs.p, g.size() * sizeof(GateJob), cudaMemcpyDeviceToHost, stream) != cudaSuccess ||
+	    cudaStreamSynchronize(stream) != cudaSuccess)
+		return LRZGPU_ECUDA;
+	pass.clear();
+	for (size_t i = 0; i < idx.size(); i++)
+		if (g[i].result)
+			pass.push_back(idx[i]);
+	return LRZGPU_OK;
+}
+
 int backend_encode_blocks(BackendCtx *b, const lrzgpu_params &p, const lrzgpu_sizing_t &sz, std::vector<BlockJob> &jobs,
 			  int num_sms, cudaStream_t stream, int64_t *launches, char *err, size_t errlen)
 {
@@ -537,6 +810,8 @@ int backend_encode_blocks(BackendCtx *b, const lrzgpu_params &p, const lrzgpu_si
 			idx.push_back((int)i);
 	if (idx.empty())
 		return LRZGPU_OK;
+	if (p.backend == LRZGPU_BACKEND_LZMA) // gate (when on), match finder and parser of every block, pipelined
+		return run_lzma(b, p, sz, jobs, idx, stream, launches, err, errlen);
 	if (p.threshold) { // LZ4_TEST (FLAG_THRESHOLD): incompressible blocks stay stored
 		std::vector<int> pass;
 		int rc = run_gate(b, jobs, idx, p.threshold, pass, stream, launches);
@@ -548,8 +823,6 @@ int backend_encode_blocks(BackendCtx *b, const lrzgpu_params &p, const lrzgpu_si
 		if (idx.empty())
 			return LRZGPU_OK;
 	}
-	if (p.backend == LRZGPU_BACKEND_LZMA)
-		return run_lzma(b, p, sz, jobs, idx, stream, launches, err, errlen);
 	if (p.backend == LRZGPU_BACKEND_ZSTD) {
 		int rc = run_zstd(b, jobs, idx, stream, launches);
 		if (rc)

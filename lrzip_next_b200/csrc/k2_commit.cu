@@ -392,6 +392,7 @@ struct FastShared {
 	LaneEval ev[32];              // evaluation results of the batch, written by the 8-lane groups
 	long long eq_off[8][4][K2_MAXEQ]; // per warp and group: offsets of the equal-tag entries met on the walk
 	unsigned eslot[32][K2_MAXEQ];     // per candidate: the slots of those entries, in walk order (chain-cap victims)
+	unsigned wmask[4096];             // validation filter: bit l of wmask[slot >> 10] = lane l of the batch writes there
 	// batch evaluation command, written by the commit warp before barrier 1 (see k2_eval_worker)
 	long long cmd_tag_mask, cmd_better, cmd_end, cmd_last_match;
 	int cmd_nb, cmd_max_chain, cmd_exit, cmd_mode;
@@ -788,8 +789,8 @@ __device__ void group_eval_t(const uint8_t *__restrict__ buf, const HEntry *tab,
 	// table, so this group knows what its predecessor does and evaluates its own candidate on the table as the
 	// predecessor leaves it -- for the two common cases:
 	//   predecessor appends at the chain end E and E + 1 is empty: this candidate meets one more equal-tag entry
-	//     (the predecessor's, a tag miss unless the two windows really match) and appends at E + 1, or evicts when
-	//     that entry completes the chain;
+	//     (the predecessor's, a tag miss unless the two windows really match) and appends at E + 1 -- or replaces
+	//     that entry when it is already due for cleaning, or evicts when it completes the chain;
 	//   predecessor evicts from a full chain: the chain keeps its slots, this candidate evicts the next victim.
 	// The commit warp skips the predecessor's insert when it checks this lane's reads (L.twin).
 	bool tw = active && !cx && do_insert && cand_idx >= 1 && sh->qtag[cand_idx - 1] == t &&
@@ -806,7 +807,11 @@ __device__ void group_eval_t(const uint8_t *__restrict__ buf, const HEntry *tab,
 			cx = true; // the two windows may really match: the serial step decides
 		if (nm && twE) {
 			miss += 1;
-			if (round + 1 >= max_chain) {
+			if ((t & better) != better) {
+				// while the table is still filling (insert gate == lookup gate) the predecessor's entry itself is
+				// "due for cleaning anyway" (src/rzip.c:316-319): this candidate replaces it instead of walking on
+				kind = kProbeDue;
+			} else if (round + 1 >= max_chain) {
 				if (neq < K2_MAXEQ && max_chain <= K2_MAXEQ) {
 					if (gl == 0)
 						sh->eslot[cand_idx][neq] = sslot;
@@ -1282,43 +1287,66 @@ __device__ void k2_commit_segment_batched(WarpPrim &prim, FastShared *sh, ScanSt
 		// ---- ordered validation: cmask bit j = this lane read a slot that lane j (< lane) writes.
 		// Only the lanes up to the first stopper can commit in this round, so only they are checked: their
 		// writes are gathered (in lane order) into a shared list that every reader lane scans once.
+		// ---- ordered validation: a lane may commit only if it read no slot that an earlier lane of the batch
+		// writes.  Only lanes up to the first stopper can commit, and the batch ends at the first conflict, so all
+		// that is needed is the FIRST lane with a conflict.  Filter: writers mark the 1024-slot stretch of each
+		// write in a shared bit table, readers look up the stretches their probe ranges touch; the few lanes that
+		// meet an earlier writer's mark are then checked exactly, in lane order, by the whole warp at once (every
+		// earlier lane tests its own writes against the candidate's ranges).
 		unsigned cmask = 0;
 		{
 			const unsigned stop0 = __ballot_sync(FULL, lane < nb && stopper);
 			const int nv = stop0 ? __ffs(stop0) : nb;
-			constexpr unsigned NONE = 0xffffffffu;
 			const int myn = lane < nv ? nwt : 0;
-			// nearly every lane writes one slot (its insert) or two (and the sweep deletion it triggers): those
-			// travel by shuffle, one writer lane per step; deeper displacement chains take the extra loop below
-			const unsigned w0 = myn > 0 ? L.wslot[0] : NONE, w1 = myn > 1 ? L.wslot[1] : NONE;
-			const unsigned manym = __ballot_sync(FULL, myn > 2);
 			const int mynr = lane < nv ? L.nr : 0;
-			const unsigned rlo0 = L.rlo[0], rlen0 = L.rlen[0];
-			auto reads = [&](unsigned sl) {
-				bool hit = ((sl - rlo0) & hmask) < rlen0;
-				for (int q = 1; q < mynr; q++)
-					hit = hit || ((sl - L.rlo[q]) & hmask) < L.rlen[q];
-				return hit;
-			};
-			for (int i = 0; i + 1 < nv; i++) {
-				const unsigned a0 = __shfl_sync(FULL, w0, i), a1 = __shfl_sync(FULL, w1, i);
-				if (lane > i && mynr > 0) {
-					// a twin was evaluated on the table as its predecessor's insert leaves it
-					const bool skip0 = L.twin && i == lane - 1;
-					if ((a0 != NONE && !skip0 && reads(a0)) || (a1 != NONE && reads(a1)))
-						cmask |= 1u << i;
+			for (int w = 0; w < myn; w++)
+				atomicOr(&sh->wmask[L.wslot[w] >> 10], 1u << lane);
+			__syncwarp();
+			unsigned seen = 0;
+			for (int q = 0; q < mynr; q++) {
+				const unsigned b0 = L.rlo[q] >> 10, b1 = ((L.rlo[q] + L.rlen[q] - 1) & hmask) >> 10;
+				const unsigned nbk = (unsigned)(tsize >> 10);
+				for (unsigned bk = b0;; bk = (bk + 1 == nbk) ? 0 : bk + 1) {
+					seen |= sh->wmask[bk];
+					if (bk == b1)
+						break;
 				}
 			}
-			for (unsigned mm = manym; mm; mm &= mm - 1) {
-				const int i = __ffs(mm) - 1;
-				const int ni = __shfl_sync(FULL, myn, i);
+			unsigned F = __ballot_sync(FULL, (seen & lt) != 0);
+			__syncwarp();
+			for (int w = 0; w < myn; w++)
+				sh->wmask[L.wslot[w] >> 10] = 0;
+			const unsigned w0 = myn > 0 ? L.wslot[0] : 0, w1 = myn > 1 ? L.wslot[1] : 0;
+			int first_conf = 32;
+			while (F) {
+				const int f = __ffs(F) - 1;
+				F &= F - 1;
+				const int nrf = __shfl_sync(FULL, mynr, f), twf = __shfl_sync(FULL, L.twin, f);
+				bool hit = false;
 #pragma unroll
-				for (int w = 2; w < K2_MAXW + 1; w++) {
-					const unsigned a = __shfl_sync(FULL, L.wslot[w], i);
-					if (w < ni && lane > i && mynr > 0 && reads(a))
-						cmask |= 1u << i;
+				for (int q = 0; q < K2_MAXW; q++) {
+					if (q >= nrf)
+						break;
+					const unsigned lo = __shfl_sync(FULL, L.rlo[q], f), len = __shfl_sync(FULL, L.rlen[q], f);
+					if (lane < f) {
+						// a twin was evaluated on the table as its predecessor's insert leaves it
+						if (myn > 0 && !(twf && lane == f - 1) && ((w0 - lo) & hmask) < len)
+							hit = true;
+						if (myn > 1 && ((w1 - lo) & hmask) < len)
+							hit = true;
+						for (int w = 2; w < myn; w++)
+							if (((L.wslot[w] - lo) & hmask) < len)
+								hit = true;
+					}
+				}
+				if (__ballot_sync(FULL, hit)) {
+					first_conf = f;
+					break;
 				}
 			}
+			if (lane == first_conf)
+				cmask = 1;
+			__syncwarp();
 		}
 		dbg[13] += clock64() - cv0;
 		const long long cc0 = clock64();
@@ -1427,6 +1455,8 @@ k2_commit_kernel(const uint8_t *__restrict__ buf, ScanState *st, HEntry *tab, co
 	tab += (int64_t)blockIdx.x * tab_stride;
 	recs += (int64_t)blockIdx.x * rec_stride;
 	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+	for (int i = threadIdx.x; i < 4096; i += K2_THREADS)
+		sh.wmask[i] = 0;
 	if (threadIdx.x == 0) {
 		sh.prog.pos = st->scan_pos;
 		sh.prog.min_mask = st->min_mask;

@@ -290,12 +290,13 @@ __device__ __forceinline__ uint4 load16u_g(const uint8_t *p)
 }
 
 __global__ void __launch_bounds__(LIT_THREADS)
-k4_literals_kernel(const uint8_t *__restrict__ buf, const MatchRec *__restrict__ recs, int64_t n_rec, int64_t s1_len,
-		   uint8_t *__restrict__ s1)
+k4_literals_kernel(const uint8_t *__restrict__ buf, const MatchRec *__restrict__ recs, int64_t n_rec, int64_t s1_from,
+		   int64_t s1_len, uint8_t *__restrict__ s1)
 {
 	__shared__ int64_t s_range[2];
+	const int64_t first_tile = s1_from / LIT_TILE; // s1_from is a multiple of 16: tiles are re-done whole
 	const int64_t num_tiles = (s1_len + LIT_TILE - 1) / LIT_TILE;
-	for (int64_t t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+	for (int64_t t = first_tile + blockIdx.x; t < num_tiles; t += gridDim.x) {
 		const int64_t t0 = t * LIT_TILE;
 		const int64_t t1 = (t0 + LIT_TILE < s1_len) ? t0 + LIT_TILE : s1_len;
 		if (threadIdx.x < 2)
@@ -325,16 +326,16 @@ k4_literals_kernel(const uint8_t *__restrict__ buf, const MatchRec *__restrict__
 	}
 }
 
-int k4_literals_launch(const uint8_t *d_buf, const MatchRec *d_recs, int64_t n_rec, int64_t s1_len,
+int k4_literals_launch(const uint8_t *d_buf, const MatchRec *d_recs, int64_t n_rec, int64_t s1_from, int64_t s1_len,
 		       uint8_t *d_s1, int num_sms, cudaStream_t stream)
 {
-	if (s1_len <= 0 || n_rec <= 0)
+	if (s1_len <= s1_from || n_rec <= 0)
 		return 0;
-	int64_t tiles = (s1_len + LIT_TILE - 1) / LIT_TILE;
+	int64_t tiles = (s1_len + LIT_TILE - 1) / LIT_TILE - s1_from / LIT_TILE;
 	int64_t grid = (int64_t)num_sms * 8;
 	if (grid > tiles)
 		grid = tiles;
-	k4_literals_kernel<<<(unsigned)grid, LIT_THREADS, 0, stream>>>(d_buf, d_recs, n_rec, s1_len, d_s1);
+	k4_literals_kernel<<<(unsigned)grid, LIT_THREADS, 0, stream>>>(d_buf, d_recs, n_rec, s1_from, s1_len, d_s1);
 	return cudaGetLastError() == cudaSuccess ? 0 : -1;
 }
 

@@ -31,8 +31,9 @@ int crc32_launch(const uint8_t *d_buf, int64_t n, uint32_t *d_crc, int num_sms, 
 // Stream 0 (record headers, terminator, CRC) from the match records.
 int k4_headers_launch(const MatchRec *d_recs, int64_t n_rec, int chunk_bytes, const uint32_t *d_crc,
 		      uint8_t *d_s0, cudaStream_t stream);
-// Stream 1 (literal bytes) gathered from the chunk.
-int k4_literals_launch(const uint8_t *d_buf, const MatchRec *d_recs, int64_t n_rec, int64_t s1_len,
+// Stream 1 (literal bytes) gathered from the chunk: bytes [s1_from, s1_len) of the stream (whole tiles: bytes
+// before s1_from in its tile are written again with the same values), from the records [0, n_rec) known so far.
+int k4_literals_launch(const uint8_t *d_buf, const MatchRec *d_recs, int64_t n_rec, int64_t s1_from, int64_t s1_len,
 		       uint8_t *d_s1, int num_sms, cudaStream_t stream);
 // For each stream-0 block boundary j (byte offset (j+1)*bufsize), the number of stream-1 bytes that
 // had been written when that byte was written: decides the global flush order of blocks.

@@ -12,6 +12,7 @@
 #include <string.h>
 
 #include <chrono>
+#include <functional>
 #include <thread>
 #include <vector>
 
@@ -64,11 +65,15 @@ double now_ms()
 struct lrzgpu_ctx {
 	int device = 0, sms = 148;
 	char err[512] = { 0 };
-	cudaStream_t sA = nullptr, sB = nullptr, sC = nullptr, sD = nullptr;
+	cudaStream_t sA = nullptr, sB = nullptr, sC = nullptr, sD = nullptr, sE = nullptr;
 	cudaEvent_t evK1[2] = { nullptr, nullptr }, evK2[2] = { nullptr, nullptr }, evInit = nullptr, evCrc = nullptr;
 	DevBuf in, tab, state, cand[2], tc[2], recs, s0, s1, crc, w1;
 	ScanState *h_state = nullptr; // pinned, one per variant of the window being scanned
 	size_t h_state_cap = 0;
+	ScanState *h_snap = nullptr; // pinned, one per segment of a pipelined scan
+	size_t h_snap_cap = 0;
+	std::vector<cudaEvent_t> evSeg;
+	cudaEvent_t evLit = nullptr;
 	uint8_t *h_pin[2] = { nullptr, nullptr }; // pinned staging for the MD5 stream of device inputs
 	size_t h_pin_cap = 0;
 	BackendCtx *backend = nullptr;
@@ -142,8 +147,13 @@ void account_rzip(lrzgpu_stats *stats, const ChunkResult &res)
 // chunk from the given victim_round; nvar > 1 runs one commit per possible incoming value 0..nvar-1 of the
 // reference's cross-window counter (all-values speculation), each with its own table, state and
 // match records.  Leaves the match records in c->recs (variant v from res[v].rec_base).
+// `progress` (single-variant scans only) is called on the host after every segment with the scan state as of the
+// end of that segment -- match records [0, n_rec) and the stream lengths are final up to there -- while the
+// device goes on with the following segments: this is where the backend gets its blocks from early.
+using ScanProgress = std::function<int(const ScanState &)>;
+
 int rzip_scan_device(lrzgpu_ctx *c, const uint8_t *d_chunk, int64_t n, int rzip_level, int cb, int64_t victim_round,
-		     int nvar, std::vector<ChunkResult> &res, lrzgpu_stats *stats)
+		     int nvar, std::vector<ChunkResult> &res, lrzgpu_stats *stats, const ScanProgress *progress = nullptr)
 {
 	const double t0 = now_ms();
 	const RzipLevel &lv = kLevels[rzip_level];
@@ -180,6 +190,22 @@ int rzip_scan_device(lrzgpu_ctx *c, const uint8_t *d_chunk, int64_t n, int rzip_
 	c->launches += 1;
 
 	const int64_t nseg = (n + seg - 1) / seg;
+	const bool snap = progress && nvar == 1 && nseg > 1;
+	if (snap) { // one pinned snapshot of the scan state and one event per segment
+		if ((size_t)nseg > c->h_snap_cap) {
+			if (c->h_snap)
+				cudaFreeHost(c->h_snap);
+			c->h_snap = nullptr;
+			c->h_snap_cap = 0;
+			CU(c, cudaHostAlloc((void **)&c->h_snap, sizeof(ScanState) * (size_t)nseg, cudaHostAllocDefault));
+			c->h_snap_cap = (size_t)nseg;
+		}
+		while (c->evSeg.size() < (size_t)nseg) {
+			cudaEvent_t e = nullptr;
+			CU(c, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+			c->evSeg.push_back(e);
+		}
+	}
 	for (int64_t i = 0; i < nseg; i++) {
 		const int b = (int)(i & 1);
 		const int64_t lo = i * seg, hi = (lo + seg < n) ? lo + seg : n;
@@ -194,6 +220,20 @@ int rzip_scan_device(lrzgpu_ctx *c, const uint8_t *d_chunk, int64_t n, int rzip_
 			return fail(c, LRZGPU_ECUDA, "k2 launch: %s", cudaGetErrorString(cudaGetLastError()));
 		CU(c, cudaEventRecord(c->evK2[b], c->sA));
 		c->launches += 2;
+		if (snap) {
+			CU(c, cudaMemcpyAsync(c->h_snap + i, d_state, sizeof(ScanState), cudaMemcpyDeviceToHost, c->sA));
+			CU(c, cudaEventRecord(c->evSeg[(size_t)i], c->sA));
+		}
+	}
+	if (snap) {
+		for (int64_t i = 0; i + 1 < nseg; i++) { // the last segment's state is handled by the caller as the final one
+			CU(c, cudaEventSynchronize(c->evSeg[(size_t)i]));
+			if (c->h_snap[i].status != kStatusRunning)
+				break;
+			const int prc = (*progress)(c->h_snap[i]);
+			if (prc)
+				return prc;
+		}
 	}
 	CU(c, cudaMemcpyAsync(c->h_state, d_state, sizeof(ScanState) * (size_t)nvar, cudaMemcpyDeviceToHost, c->sA));
 	CU(c, cudaStreamSynchronize(c->sA));
@@ -222,15 +262,17 @@ int rzip_scan_device(lrzgpu_ctx *c, const uint8_t *d_chunk, int64_t n, int rzip_
 }
 
 // K4: stream 0 / stream 1 of one scanned variant into c->s0 / c->s1.
-int rzip_emit_device(lrzgpu_ctx *c, const uint8_t *d_chunk, int cb, const ChunkResult &res, lrzgpu_stats *stats)
+int rzip_emit_device(lrzgpu_ctx *c, const uint8_t *d_chunk, int cb, const ChunkResult &res, lrzgpu_stats *stats,
+		     int64_t s1_from = 0)
 {
 	const double t1 = now_ms();
 	const MatchRec *recs = (const MatchRec *)c->recs.p + res.rec_base;
 	CU(c, c->s0.ensure((size_t)res.s0_len + 64));
-	CU(c, c->s1.ensure((size_t)res.s1_len + 64));
+	if (!s1_from) // a pipelined chunk sized the buffer before the scan and already holds [0, s1_from)
+		CU(c, c->s1.ensure((size_t)res.s1_len + 64));
 	CU(c, cudaStreamWaitEvent(c->sA, c->evCrc, 0));
 	if (k4_headers_launch(recs, res.n_rec, cb, (const uint32_t *)c->crc.p, (uint8_t *)c->s0.p, c->sA) ||
-	    k4_literals_launch(d_chunk, recs, res.n_rec, res.s1_len, (uint8_t *)c->s1.p, c->sms, c->sA))
+	    k4_literals_launch(d_chunk, recs, res.n_rec, s1_from, res.s1_len, (uint8_t *)c->s1.p, c->sms, c->sA))
 		return fail(c, LRZGPU_ECUDA, "k4 launch: %s", cudaGetErrorString(cudaGetLastError()));
 	c->launches += 2;
 	uint32_t crc_acc = 0;
@@ -275,30 +317,9 @@ struct OutBuf {
 	}
 };
 
-// One chunk: rzip on the device, then blocks -> backend -> framed blob appended to `out`
-// (src/stream.c:1722-1821: chunk preamble, two initial stream headers, blocks with next_head patching).
-// Second half of a chunk: stream blocks -> backend -> framed blob, from the streams rzip left in c->s0 / c->s1.
-int finish_chunk_device(lrzgpu_ctx *c, const lrzgpu_params &p, const lrzgpu_sizing_t &sz, int64_t n, int eof, int cb,
-			const ChunkResult &res, OutBuf &out, lrzgpu_stats *stats);
-
-int compress_chunk_device(lrzgpu_ctx *c, const lrzgpu_params &p, const lrzgpu_sizing_t &sz, const uint8_t *d_chunk,
-			  int64_t n, int eof, int64_t *victim_round, OutBuf &out, lrzgpu_stats *stats)
+// Global flush order of the chunk's stream blocks (src/stream.c:2198-2216, 2253-2259) as jobs over c->s0 / c->s1.
+int plan_chunk_blocks(lrzgpu_ctx *c, const lrzgpu_sizing_t &sz, int cb, const ChunkResult &res, std::vector<BlockJob> &jobs)
 {
-	const int rzl = p.rzip_level ? p.rzip_level : p.level;
-	const int cb = chunk_bytes_for(n);
-	ChunkResult res;
-	int rc = rzip_chunk_device(c, d_chunk, n, rzl, cb, *victim_round, res, stats);
-	if (rc)
-		return rc;
-	*victim_round = res.st.victim_round;
-	return finish_chunk_device(c, p, sz, n, eof, cb, res, out, stats);
-}
-
-int finish_chunk_device(lrzgpu_ctx *c, const lrzgpu_params &p, const lrzgpu_sizing_t &sz, int64_t n, int eof, int cb,
-			const ChunkResult &res, OutBuf &out, lrzgpu_stats *stats)
-{
-	int rc = 0;
-	const double t0 = now_ms();
 	const int64_t nb0 = res.s0_len / sz.bufsize;
 	std::vector<int64_t> w1((size_t)nb0 + 1, 0);
 	if (nb0 > 0) {
@@ -311,8 +332,7 @@ int finish_chunk_device(lrzgpu_ctx *c, const lrzgpu_params &p, const lrzgpu_sizi
 	}
 	std::vector<BlockPlan> plan;
 	plan_blocks(res.s0_len, res.s1_len, sz.bufsize, w1.data(), plan);
-
-	std::vector<BlockJob> jobs(plan.size());
+	jobs.assign(plan.size(), BlockJob());
 	for (size_t i = 0; i < plan.size(); i++) {
 		jobs[i].d_src = (const uint8_t *)(plan[i].stream ? c->s1.p : c->s0.p) + plan[i].off;
 		jobs[i].u_len = plan[i].u_len;
@@ -321,13 +341,14 @@ int finish_chunk_device(lrzgpu_ctx *c, const lrzgpu_params &p, const lrzgpu_sizi
 		jobs[i].c_len = plan[i].u_len;
 		jobs[i].d_payload = jobs[i].d_src;
 	}
-	if (p.backend != LRZGPU_BACKEND_NONE) {
-		rc = backend_encode_blocks(c->backend, p, sz, jobs, c->sms, c->sA, &c->launches, c->err, sizeof(c->err));
-		if (rc)
-			return rc;
-	}
-	const double t1 = now_ms();
+	return LRZGPU_OK;
+}
 
+// The chunk's blob appended to `out` (src/stream.c:1722-1821: chunk preamble, two initial stream headers, blocks
+// in flush order with next_head patching); payloads come from the device.
+int frame_chunk(lrzgpu_ctx *c, const lrzgpu_params &p, int64_t n, int eof, int cb, const std::vector<BlockJob> &jobs,
+		OutBuf &out, lrzgpu_stats *stats)
+{
 	const int64_t hdr = 1 + 3 * cb;
 	int64_t total = 2 + cb + 2 * hdr;
 	for (auto &j : jobs)
@@ -369,12 +390,167 @@ int finish_chunk_device(lrzgpu_ctx *c, const lrzgpu_params &p, const lrzgpu_sizi
 	}
 	CU(c, cudaStreamSynchronize(c->sA));
 	out.len += total;
-	const double t2 = now_ms();
+	return LRZGPU_OK;
+}
+
+// Second half of a chunk: stream blocks -> backend -> framed blob, from the streams rzip left in c->s0 / c->s1.
+int finish_chunk_device(lrzgpu_ctx *c, const lrzgpu_params &p, const lrzgpu_sizing_t &sz, int64_t n, int eof, int cb,
+			const ChunkResult &res, OutBuf &out, lrzgpu_stats *stats)
+{
+	const double t0 = now_ms();
+	std::vector<BlockJob> jobs;
+	int rc = plan_chunk_blocks(c, sz, cb, res, jobs);
+	if (rc)
+		return rc;
+	if (p.backend != LRZGPU_BACKEND_NONE) {
+		rc = backend_encode_blocks(c->backend, p, sz, jobs, c->sms, c->sA, &c->launches, c->err, sizeof(c->err));
+		if (rc)
+			return rc;
+	}
+	const double t1 = now_ms();
+	rc = frame_chunk(c, p, n, eof, cb, jobs, out, stats);
+	if (rc)
+		return rc;
 	if (stats) {
 		stats->ms_backend += t1 - t0;
-		stats->ms_d2h += t2 - t1;
+		stats->ms_d2h += now_ms() - t1;
 	}
 	return LRZGPU_OK;
+}
+
+// One chunk with the LZMA backend running UNDER the rzip stage: every stream-1 block goes to the backend the
+// moment the scan has produced its last byte (the reference does the same: write_stream() flushes a full buffer to
+// a compthread, src/stream.c:2198-2216, 1836-1875), so that at the end of the scan only the blocks that were
+// still open -- the last full one, the two tails and stream 0 -- remain to be encoded.
+int compress_chunk_pipelined(lrzgpu_ctx *c, const lrzgpu_params &p, const lrzgpu_sizing_t &sz, const uint8_t *d_chunk,
+			     int64_t n, int eof, int64_t *victim_round, OutBuf &out, lrzgpu_stats *stats)
+{
+	const double t0 = now_ms();
+	const int rzl = p.rzip_level ? p.rzip_level : p.level;
+	const int cb = chunk_bytes_for(n);
+	const int64_t bs = sz.bufsize;
+	CU(c, c->s1.ensure((size_t)n + 64));
+	const int64_t max_blocks = n / bs + n / bs / 3 + 4; // stream 1 <= n bytes, stream 0 <= about n / 4
+	int rc = backend_async_begin(c->backend, p, sz, bs < n ? bs : n, max_blocks, n + n / 3 + (1 << 20), c->err, sizeof(c->err));
+	if (rc)
+		return rc;
+	int64_t s1_done = 0, blk1 = 0;
+	auto submit = [&](const BlockJob *jobs, int cnt, cudaEvent_t ready) -> int {
+		int r = backend_async_submit(c->backend, jobs, cnt, ready, &c->launches, c->err, sizeof(c->err));
+		if (r == 1) { // work space used up: wait for what is in flight (the scan goes on meanwhile), then go on
+			r = backend_async_drain(c->backend, &c->launches, c->err, sizeof(c->err));
+			if (!r)
+				r = backend_async_submit(c->backend, jobs, cnt, ready, &c->launches, c->err, sizeof(c->err));
+			if (r == 1)
+				r = fail(c, LRZGPU_EINTERNAL, "LZMA work space cannot hold %d blocks", cnt);
+		}
+		return r;
+	};
+	const ScanProgress progress = [&](const ScanState &st) -> int {
+		const int64_t full = st.s1_len / bs;
+		if (full <= blk1)
+			return 0;
+		// stream-1 bytes [s1_done, st.s1_len) from the records known so far, on a stream of their own (sA holds
+		// the rest of the scan)
+		if (k4_literals_launch(d_chunk, (const MatchRec *)c->recs.p, st.n_rec, s1_done, st.s1_len, (uint8_t *)c->s1.p, c->sms, c->sE))
+			return fail(c, LRZGPU_ECUDA, "k4 launch: %s", cudaGetErrorString(cudaGetLastError()));
+		c->launches += 1;
+		CU(c, cudaEventRecord(c->evLit, c->sE));
+		std::vector<BlockJob> jobs((size_t)(full - blk1));
+		for (int64_t k = blk1; k < full; k++) {
+			BlockJob &j = jobs[(size_t)(k - blk1)];
+			j.d_src = (const uint8_t *)c->s1.p + k * bs;
+			j.u_len = bs;
+			j.stream = 1;
+			j.c_type = kCtypeNone;
+			j.c_len = bs;
+			j.d_payload = j.d_src;
+		}
+		const int r = bs >= 64 ? submit(jobs.data(), (int)jobs.size(), c->evLit) : 0;
+		blk1 = full;
+		s1_done = st.s1_len;
+		return r;
+	};
+	std::vector<ChunkResult> all;
+	rc = rzip_scan_device(c, d_chunk, n, rzl, cb, *victim_round, 1, all, stats, &progress);
+	if (rc)
+		return rc;
+	const ChunkResult &res = all[0];
+	*victim_round = res.st.victim_round;
+	CU(c, cudaStreamSynchronize(c->sE));
+	rc = rzip_emit_device(c, d_chunk, cb, res, stats, s1_done);
+	if (rc)
+		return rc;
+	const double t1 = now_ms();
+	std::vector<BlockJob> jobs;
+	rc = plan_chunk_blocks(c, sz, cb, res, jobs);
+	if (rc)
+		return rc;
+	// the blocks the scan could not hand over: whatever of stream 1 was not complete at the last look, stream 0
+	std::vector<BlockJob> rest;
+	std::vector<int> early((size_t)blk1, -1), late;
+	for (size_t i = 0; i < jobs.size(); i++) {
+		const BlockJob &j = jobs[i];
+		const int64_t off = j.d_src - (const uint8_t *)(j.stream ? c->s1.p : c->s0.p);
+		if (j.stream == 1 && bs >= 64 && off / bs < blk1 && j.u_len == bs)
+			early[(size_t)(off / bs)] = (int)i;
+		else if (j.u_len >= 64) { // src/stream.c:1633
+			rest.push_back(j);
+			late.push_back((int)i);
+		}
+	}
+	const int n_early = backend_async_count(c->backend);
+	if (!rest.empty()) {
+		rc = submit(rest.data(), (int)rest.size(), nullptr);
+		if (rc)
+			return rc;
+	}
+	rc = backend_async_drain(c->backend, &c->launches, c->err, sizeof(c->err));
+	if (rc)
+		return rc;
+	if (n_early != (bs >= 64 ? blk1 : 0))
+		return fail(c, LRZGPU_EINTERNAL, "pipelined blocks out of step");
+	auto take = [&](int job, int sub) -> int {
+		const BlockJob *r = backend_async_result(c->backend, sub);
+		if (!r || job < 0)
+			return fail(c, LRZGPU_EINTERNAL, "missing result of a pipelined block");
+		jobs[(size_t)job].c_type = r->c_type;
+		jobs[(size_t)job].c_len = r->c_len;
+		jobs[(size_t)job].d_payload = r->d_payload;
+		return 0;
+	};
+	for (int k = 0; k < n_early; k++)
+		if ((rc = take(early[(size_t)k], k)))
+			return rc;
+	for (size_t k = 0; k < late.size(); k++)
+		if ((rc = take(late[k], n_early + (int)k)))
+			return rc;
+	const double t2 = now_ms();
+	rc = frame_chunk(c, p, n, eof, cb, jobs, out, stats);
+	if (rc)
+		return rc;
+	if (stats) {
+		stats->ms_backend += t2 - t1;
+		stats->ms_d2h += now_ms() - t2;
+	}
+	(void)t0;
+	return LRZGPU_OK;
+}
+
+// One chunk: rzip on the device, then blocks -> backend -> framed blob appended to `out`.
+int compress_chunk_device(lrzgpu_ctx *c, const lrzgpu_params &p, const lrzgpu_sizing_t &sz, const uint8_t *d_chunk,
+			  int64_t n, int eof, int64_t *victim_round, OutBuf &out, lrzgpu_stats *stats)
+{
+	if (p.backend == LRZGPU_BACKEND_LZMA && n > kSegment && !getenv("LRZGPU_NO_OVERLAP"))
+		return compress_chunk_pipelined(c, p, sz, d_chunk, n, eof, victim_round, out, stats);
+	const int rzl = p.rzip_level ? p.rzip_level : p.level;
+	const int cb = chunk_bytes_for(n);
+	ChunkResult res;
+	int rc = rzip_chunk_device(c, d_chunk, n, rzl, cb, *victim_round, res, stats);
+	if (rc)
+		return rc;
+	*victim_round = res.st.victim_round;
+	return finish_chunk_device(c, p, sz, n, eof, cb, res, out, stats);
 }
 
 // Upload a host buffer behind a zeroed front pad and in front of a zeroed tail pad.
@@ -448,10 +624,12 @@ int lrzgpu_create(int device, lrzgpu_ctx **out)
 	bool ok = cudaStreamCreateWithFlags(&c->sA, cudaStreamNonBlocking) == cudaSuccess &&
 		  cudaStreamCreateWithFlags(&c->sB, cudaStreamNonBlocking) == cudaSuccess &&
 		  cudaStreamCreateWithFlags(&c->sC, cudaStreamNonBlocking) == cudaSuccess &&
-		  cudaStreamCreateWithFlags(&c->sD, cudaStreamNonBlocking) == cudaSuccess;
+		  cudaStreamCreateWithFlags(&c->sD, cudaStreamNonBlocking) == cudaSuccess &&
+		  cudaStreamCreateWithFlags(&c->sE, cudaStreamNonBlocking) == cudaSuccess;
 	for (int i = 0; i < 2 && ok; i++)
 		ok = cudaEventCreateWithFlags(&c->evK1[i], cudaEventDisableTiming) == cudaSuccess &&
 		     cudaEventCreateWithFlags(&c->evK2[i], cudaEventDisableTiming) == cudaSuccess;
+	ok = ok && cudaEventCreateWithFlags(&c->evLit, cudaEventDisableTiming) == cudaSuccess;
 	ok = ok && cudaEventCreateWithFlags(&c->evInit, cudaEventDisableTiming) == cudaSuccess &&
 	     cudaEventCreateWithFlags(&c->evCrc, cudaEventDisableTiming) == cudaSuccess;
 	ok = ok && cudaHostAlloc((void **)&c->h_state, sizeof(ScanState), cudaHostAllocDefault) == cudaSuccess;
@@ -484,6 +662,12 @@ void lrzgpu_destroy(lrzgpu_ctx *c)
 		b->release();
 	if (c->h_state)
 		cudaFreeHost(c->h_state);
+	if (c->h_snap)
+		cudaFreeHost(c->h_snap);
+	for (cudaEvent_t e : c->evSeg)
+		cudaEventDestroy(e);
+	if (c->evLit)
+		cudaEventDestroy(c->evLit);
 	for (int i = 0; i < 2; i++) {
 		if (c->h_pin[i])
 			cudaFreeHost(c->h_pin[i]);
@@ -496,7 +680,7 @@ void lrzgpu_destroy(lrzgpu_ctx *c)
 		cudaEventDestroy(c->evInit);
 	if (c->evCrc)
 		cudaEventDestroy(c->evCrc);
-	cudaStream_t ss[] = { c->sA, c->sB, c->sC, c->sD };
+	cudaStream_t ss[] = { c->sA, c->sB, c->sC, c->sD, c->sE };
 	for (cudaStream_t s : ss)
 		if (s)
 			cudaStreamDestroy(s);

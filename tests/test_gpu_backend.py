@@ -87,3 +87,21 @@ def test_zstd_archive_decodes_with_reference(ctx):
     assert oracle.ref_test(got)
     assert oracle.ref_decompress(got) == d.tobytes()
     assert len(got) < d.size - (2 << 20)  # the zero run went through RLE blocks
+
+
+@pytest.mark.skipif(not oracle.have_ref(), reason="oracle/_ref not built")
+def test_pipelined_chunk_equals_plain_and_reference(ctx, monkeypatch):
+    """Chunks above one scan segment run the LZMA backend UNDER the rzip stage (blocks submitted as they fill,
+    gate verdicts read on the device).  Same bytes as the plain order, and as the reference: text blocks that
+    compress, random blocks the lz4 gate leaves stored, zero blocks, several blocks per stream."""
+    d = np.concatenate([datagen.generate("text", 22 << 20), RNG.integers(0, 256, 12 << 20, dtype=np.uint8),
+                        np.zeros(11 << 20, dtype=np.uint8), datagen.generate("text", 3 << 20)])
+    kw = dict(threads=8, processors=os.cpu_count() or 8)
+    p = make_params(backend=BACKEND_LZMA, **kw)
+    got, st = ctx.compress(d, p, want_stats=True)
+    assert st["blocks"] >= 5 and 0 < st["blocks_stored"] < st["blocks"]
+    monkeypatch.setenv("LRZGPU_NO_OVERLAP", "1")
+    plain = ctx.compress(d, p)
+    monkeypatch.delenv("LRZGPU_NO_OVERLAP")
+    assert got == plain
+    assert got == oracle.ref_compress(d, oracle.make_params(backend=oracle.BACKEND_LZMA, **kw))
