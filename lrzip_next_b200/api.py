@@ -80,6 +80,9 @@ def load_library():
     global _lib
     if _lib is not None:
         return _lib
+    # more hardware work queues than the default 8: the backend keeps one stream per group of blocks in flight
+    # (only read by the CUDA runtime when it creates its context, so it must be set before the first CUDA call)
+    os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
     path = lib_path()
     if not os.path.exists(path):
         raise LrzGpuError(-4, f"{path} is missing: run __graft_entry__.build() (there is no CPU fallback)")

@@ -259,7 +259,8 @@ struct AsyncGroup {
 	size_t first = 0, count = 0; // subs[first .. first + count)
 	size_t meta_off = 0;         // [LzmaJob x m][MfBlock x m][segBase x (m + 1)][GateJob x m] in BackendCtx::meta
 	cudaStream_t ps = nullptr;   // parser stream
-	bool gated = false;
+	cudaEvent_t evMF = nullptr, evGate = nullptr, evDone = nullptr;
+	bool gated = false, launched = false, finished = false;
 };
 
 struct BackendCtx {
@@ -278,6 +279,8 @@ struct BackendCtx {
 	size_t out_used = 0, meta_used = 0;
 	std::vector<AsyncSub> subs;
 	std::vector<AsyncGroup> groups; // enqueued since the last drain
+	size_t next_launch = 0;         // groups[next_launch ..) still wait for their parser kernel
+	int inflight = 0, inflight_max = 100; // blocks whose parser kernel is running
 };
 
 BackendCtx *backend_create() { return new BackendCtx(); }
@@ -390,6 +393,14 @@ int backend_async_begin(BackendCtx *b, const lrzgpu_params &p, const lrzgpu_sizi
 	b->subs.clear();
 	b->groups.clear();
 	b->ev_next = 0;
+	b->next_launch = 0;
+	b->inflight = 0;
+	{
+		int dev = 0, sms = 148;
+		cudaGetDevice(&dev);
+		cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+		b->inflight_max = sms > 48 ? sms - 24 : sms / 2; // one parser CTA per SM; the rest stays free for the scan
+	}
 	if (cudaFuncSetAttribute(lzma_block_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(lzma::Enc)) != cudaSuccess) {
 		snprintf(err, errlen, "LZMA encoder state (%zu bytes) does not fit in shared memory", sizeof(lzma::Enc));
 		return LRZGPU_ECUDA;
@@ -428,12 +439,8 @@ static int enqueue_group(BackendCtx *b, size_t first, size_t m, const std::vecto
 	cudaEvent_t evGate = nullptr, evMF = next_event(b);
 	if (!evMF)
 		return LRZGPU_ECUDA;
-	if (ready) {
-		if (cudaStreamWaitEvent(b->sMF, ready, 0) != cudaSuccess)
-			return LRZGPU_ECUDA;
-		if (gate && cudaStreamWaitEvent(b->sGate, ready, 0) != cudaSuccess)
-			return LRZGPU_ECUDA;
-	}
+	if (ready && cudaEventSynchronize(ready) != cudaSuccess) // see pump_groups: no device-side waits on these streams
+		return LRZGPU_ECUDA;
 	std::vector<LzmaJob> lj(m);
 	std::vector<lzma::MfBlock> mb(m);
 	std::vector<uint64_t> seg(m + 1, 0);
@@ -511,18 +518,68 @@ static int enqueue_group(BackendCtx *b, size_t first, size_t m, const std::vecto
 		snprintf(err, errlen, "LZMA match finder walk: %s", cudaGetErrorString(cudaGetLastError()));
 		return LRZGPU_ECUDA;
 	}
-	if (cudaEventRecord(evMF, b->sMF) != cudaSuccess || cudaStreamWaitEvent(G.ps, evMF, 0) != cudaSuccess ||
-	    (evGate && cudaStreamWaitEvent(G.ps, evGate, 0) != cudaSuccess))
+	if (cudaEventRecord(evMF, b->sMF) != cudaSuccess)
 		return LRZGPU_ECUDA;
-	lzma_block_kernel<<<(unsigned)m, 64, sizeof(lzma::Enc), G.ps>>>((LzmaJob *)J);
-	if (launches)
-		(*launches)++;
-	if (cudaGetLastError() != cudaSuccess) {
-		snprintf(err, errlen, "LZMA kernel launch: %s", cudaGetErrorString(cudaGetLastError()));
+	G.evMF = evMF;
+	G.evGate = evGate;
+	G.evDone = next_event(b);
+	if (!G.evDone)
 		return LRZGPU_ECUDA;
-	}
 	b->groups.push_back(G);
 	return LRZGPU_OK;
+}
+
+// Launch the parser kernels of the groups whose match finder (and gate) have finished.  The host does the
+// waiting: a parser stream that waited on the device would sit at the head of a hardware work queue it shares
+// with other streams (CUDA_DEVICE_MAX_CONNECTIONS, 8 by default) and hold up their launches -- the scan's
+// among them -- and so would a parser kernel that finds no SM with 135 KB of shared memory free, hence the cap
+// on blocks in flight.  wait = false: launch what is ready, return at once.
+static int pump_groups(BackendCtx *b, bool wait, int64_t *launches, char *err, size_t errlen)
+{
+	for (AsyncGroup &G : b->groups) // retire finished kernels
+		if (G.launched && !G.finished && cudaEventQuery(G.evDone) == cudaSuccess) {
+			G.finished = true;
+			b->inflight -= (int)G.count;
+		}
+	while (b->next_launch < b->groups.size()) {
+		AsyncGroup &G = b->groups[b->next_launch];
+		if (b->inflight > 0 && b->inflight + (int)G.count > b->inflight_max) {
+			if (!wait)
+				return LRZGPU_OK;
+			for (AsyncGroup &O : b->groups) // the oldest running group
+				if (O.launched && !O.finished) {
+					if (cudaEventSynchronize(O.evDone) != cudaSuccess)
+						return LRZGPU_ECUDA;
+					O.finished = true;
+					b->inflight -= (int)O.count;
+					break;
+				}
+			continue;
+		}
+		if (wait) {
+			if (cudaEventSynchronize(G.evMF) != cudaSuccess || (G.evGate && cudaEventSynchronize(G.evGate) != cudaSuccess)) {
+				snprintf(err, errlen, "LZMA match finder failed: %s", cudaGetErrorString(cudaGetLastError()));
+				return LRZGPU_ECUDA;
+			}
+		} else if (cudaEventQuery(G.evMF) != cudaSuccess || (G.evGate && cudaEventQuery(G.evGate) != cudaSuccess))
+			return LRZGPU_OK;
+		lzma_block_kernel<<<(unsigned)G.count, 64, sizeof(lzma::Enc), G.ps>>>((LzmaJob *)((uint8_t *)b->meta.p + G.meta_off));
+		if (launches)
+			(*launches)++;
+		if (cudaGetLastError() != cudaSuccess || cudaEventRecord(G.evDone, G.ps) != cudaSuccess) {
+			snprintf(err, errlen, "LZMA kernel launch: %s", cudaGetErrorString(cudaGetLastError()));
+			return LRZGPU_ECUDA;
+		}
+		G.launched = true;
+		b->inflight += (int)G.count;
+		b->next_launch++;
+	}
+	return LRZGPU_OK;
+}
+
+int backend_async_poll(BackendCtx *b, int64_t *launches, char *err, size_t errlen)
+{
+	return b->active ? pump_groups(b, false, launches, err, errlen) : LRZGPU_OK;
 }
 
 // Submit `n` blocks (u_len >= 64) as one group.  `ready`: event after which their bytes are in place (or null).
@@ -566,11 +623,14 @@ int backend_async_submit(BackendCtx *b, const BlockJob *jobs, int n, cudaEvent_t
 	}
 	b->slots_used += n;
 	b->out_used = osum;
-	return LRZGPU_OK;
+	return pump_groups(b, false, launches, err, errlen);
 }
 
-static int collect_groups(BackendCtx *b, std::vector<size_t> &redo, char *err, size_t errlen)
+static int collect_groups(BackendCtx *b, std::vector<size_t> &redo, int64_t *launches, char *err, size_t errlen)
 {
+	int prc = pump_groups(b, true, launches, err, errlen);
+	if (prc)
+		return prc;
 	for (const AsyncGroup &G : b->groups) {
 		cudaError_t ce = cudaStreamSynchronize(G.ps);
 		if (ce != cudaSuccess) {
@@ -599,6 +659,8 @@ static int collect_groups(BackendCtx *b, std::vector<size_t> &redo, char *err, s
 		}
 	}
 	b->groups.clear();
+	b->next_launch = 0;
+	b->inflight = 0;
 	b->slots_used = 0;
 	b->meta_used = 0;
 	b->ev_next = 0;
@@ -612,7 +674,7 @@ int backend_async_drain(BackendCtx *b, int64_t *launches, char *err, size_t errl
 	if (!b->active)
 		return LRZGPU_EINVAL;
 	std::vector<size_t> redo;
-	int rc = collect_groups(b, redo, err, errlen);
+	int rc = collect_groups(b, redo, launches, err, errlen);
 	if (rc)
 		return rc;
 	// blocks whose match lists did not fit the pool (worst case 2 * (fb - 3) + 4 words per position): again, one at
@@ -630,7 +692,7 @@ int backend_async_drain(BackendCtx *b, int64_t *launches, char *err, size_t errl
 		if (rc)
 			return rc < 0 ? rc : LRZGPU_EINTERNAL;
 		std::vector<size_t> again;
-		rc = collect_groups(b, again, err, errlen);
+		rc = collect_groups(b, again, launches, err, errlen);
 		if (rc)
 			return rc;
 		if (!again.empty()) {

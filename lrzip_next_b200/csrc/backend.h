@@ -35,6 +35,8 @@ int backend_async_begin(BackendCtx *b, const lrzgpu_params &p, const lrzgpu_sizi
 // 1 when the work space is used up (drain, then submit again).  Blocks must have u_len >= 64.
 int backend_async_submit(BackendCtx *b, const BlockJob *jobs, int n, cudaEvent_t ready, int64_t *launches, char *err,
 			 size_t errlen);
+// launch whatever has become ready since (never blocks); call it now and then while blocks are in flight
+int backend_async_poll(BackendCtx *b, int64_t *launches, char *err, size_t errlen);
 int backend_async_drain(BackendCtx *b, int64_t *launches, char *err, size_t errlen);
 int backend_async_count(const BackendCtx *b);
 const BlockJob *backend_async_result(const BackendCtx *b, int i); // null until drained

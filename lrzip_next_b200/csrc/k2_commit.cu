@@ -395,7 +395,7 @@ struct FastShared {
 	unsigned wmask[4096];             // validation filter: bit l of wmask[slot >> 10] = lane l of the batch writes there
 	// batch evaluation command, written by the commit warp before barrier 1 (see k2_eval_worker)
 	long long cmd_tag_mask, cmd_better, cmd_end, cmd_last_match;
-	int cmd_nb, cmd_max_chain, cmd_exit, cmd_mode;
+	int cmd_nb, cmd_max_chain, cmd_exit, cmd_mode, cmd_flags;
 	Progress prog;
 };
 
@@ -793,7 +793,7 @@ __device__ void group_eval_t(const uint8_t *__restrict__ buf, const HEntry *tab,
 	//     that entry when it is already due for cleaning, or evicts when it completes the chain;
 	//   predecessor evicts from a full chain: the chain keeps its slots, this candidate evicts the next victim.
 	// The commit warp skips the predecessor's insert when it checks this lane's reads (L.twin).
-	bool tw = active && !cx && do_insert && cand_idx >= 1 && sh->qtag[cand_idx - 1] == t &&
+	bool tw = active && !cx && do_insert && !(sh->cmd_flags & 1) && cand_idx >= 1 && sh->qtag[cand_idx - 1] == t &&
 		  !(cand_idx >= 2 && sh->qtag[cand_idx - 2] == t);
 	if (__any_sync(FULL, tw)) {
 		const bool twE = tw && kind == kProbeEmpty, twC = tw && kind == kProbeChain;
@@ -1312,7 +1312,7 @@ __device__ void k2_commit_segment_batched(WarpPrim &prim, FastShared *sh, ScanSt
 						break;
 				}
 			}
-			unsigned F = __ballot_sync(FULL, (seen & lt) != 0);
+			unsigned F = __ballot_sync(FULL, (seen & lt) != 0 || ((sh->cmd_flags & 2) && lane < nv && lane > 0));
 			__syncwarp();
 			for (int w = 0; w < myn; w++)
 				sh->wmask[L.wslot[w] >> 10] = 0;
@@ -1463,6 +1463,7 @@ k2_commit_kernel(const uint8_t *__restrict__ buf, ScanState *st, HEntry *tab, co
 		sh.prog.done = (st->status != kStatusRunning) ? 1 : 0;
 		sh.cmd_exit = 0;
 		sh.cmd_nb = 0;
+		sh.cmd_flags = st->flags;
 	}
 	__syncthreads();
 	const int64_t hmask = ((int64_t)1 << st->hash_bits) - 1;

@@ -300,6 +300,7 @@ inline void k2_init_state(ScanState *st, int64_t n, int rzip_level, int chunk_by
 	st->chunk_bytes = chunk_bytes;
 	st->rec_cap = rec_cap;
 	st->status = kStatusRunning;
+	st->flags = 0;
 }
 
 // ---------------------------------------------------------------------------------------------

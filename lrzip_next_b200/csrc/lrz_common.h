@@ -106,6 +106,8 @@ struct ScanState {
 	// 7 rank-shift restarts, 8 clock cycles in lane evaluation, 9 cycles in serial steps, 10 total cycles,
 	// 11 cycles in queue refill, 12 sweep scan + classify, 13 validation, 14 commit loop (incl. re-evaluations)
 	int64_t dbg[16];
+	int32_t flags;        // development switches of the commit kernel (LRZGPU_K2_FLAGS): 1 no twin evaluation, 2 exact
+	int32_t pad_;         // validation of every lane (no bit filter)
 };
 
 enum { kStatusRunning = 0, kStatusChunkDone = 2, kStatusRecOverflow = -1 };

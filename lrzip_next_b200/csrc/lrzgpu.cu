@@ -177,8 +177,11 @@ int rzip_scan_device(lrzgpu_ctx *c, const uint8_t *d_chunk, int64_t n, int rzip_
 		c->h_state_cap = (size_t)nvar;
 	}
 	ScanState *d_state = (ScanState *)c->state.p;
-	for (int v = 0; v < nvar; v++)
+	for (int v = 0; v < nvar; v++) {
 		k2_init_state(c->h_state + v, n, rzip_level, cb, nvar > 1 ? v : victim_round, rec_cap);
+		if (const char *fl = getenv("LRZGPU_K2_FLAGS"))
+			c->h_state[v].flags = atoi(fl);
+	}
 	CU(c, cudaMemcpyAsync(d_state, c->h_state, sizeof(ScanState) * (size_t)nvar, cudaMemcpyHostToDevice, c->sA));
 	CU(c, cudaMemsetAsync(c->tab.p, 0, tab_bytes * (size_t)nvar, c->sA)); // src/rzip.c:599-600
 	CU(c, cudaEventRecord(c->evInit, c->sA));
@@ -449,13 +452,13 @@ int compress_chunk_pipelined(lrzgpu_ctx *c, const lrzgpu_params &p, const lrzgpu
 	const ScanProgress progress = [&](const ScanState &st) -> int {
 		const int64_t full = st.s1_len / bs;
 		if (full <= blk1)
-			return 0;
+			return backend_async_poll(c->backend, &c->launches, c->err, sizeof(c->err));
 		// stream-1 bytes [s1_done, st.s1_len) from the records known so far, on a stream of their own (sA holds
 		// the rest of the scan)
 		if (k4_literals_launch(d_chunk, (const MatchRec *)c->recs.p, st.n_rec, s1_done, st.s1_len, (uint8_t *)c->s1.p, c->sms, c->sE))
 			return fail(c, LRZGPU_ECUDA, "k4 launch: %s", cudaGetErrorString(cudaGetLastError()));
 		c->launches += 1;
-		CU(c, cudaEventRecord(c->evLit, c->sE));
+		CU(c, cudaStreamSynchronize(c->sE)); // a millisecond; the backend's streams take no device-side waits
 		std::vector<BlockJob> jobs((size_t)(full - blk1));
 		for (int64_t k = blk1; k < full; k++) {
 			BlockJob &j = jobs[(size_t)(k - blk1)];
@@ -466,7 +469,7 @@ int compress_chunk_pipelined(lrzgpu_ctx *c, const lrzgpu_params &p, const lrzgpu
 			j.c_len = bs;
 			j.d_payload = j.d_src;
 		}
-		const int r = bs >= 64 ? submit(jobs.data(), (int)jobs.size(), c->evLit) : 0;
+		const int r = bs >= 64 ? submit(jobs.data(), (int)jobs.size(), nullptr) : 0;
 		blk1 = full;
 		s1_done = st.s1_len;
 		return r;
