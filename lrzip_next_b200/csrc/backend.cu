@@ -80,7 +80,7 @@ struct LzmaJob {
 	const uint64_t *rec;  // match lists of the data-parallel finder (lzma_mf.cu)
 	const uint32_t *pool;
 	lzma::Config cfg;
-	const int *gate_result; // lz4 gate verdict of this block (device), or null when the gate is off
+	int threshold;          // lz4 gate (lz4_compresses, src/stream.c:2325-2380): 0 = off
 	const int *mf_overflow; // the match finder ran out of pool for this block: encode it again with a larger one
 	uint64_t outLen;
 	int overflow;
@@ -131,37 +131,58 @@ __device__ void lzma_lookahead_warp(const lzma::Enc *e, const LzmaJob &j, const 
 	}
 }
 
-__global__ void __launch_bounds__(64, 1) lzma_block_kernel(LzmaJob *jobs)
+__global__ void __launch_bounds__(96, 1) lzma_block_kernel(LzmaJob *jobs)
 {
 	extern __shared__ __align__(16) uint8_t lzma_smem[];
-	__shared__ int done;
+	__shared__ uint32_t gate_table[4096];
+	__shared__ int done, gate_state;
 	lzma::Enc *e = reinterpret_cast<lzma::Enc *>(lzma_smem);
 	LzmaJob &j = jobs[blockIdx.x];
-	{ // verdicts of the stages that ran before, read on the device so that the host never waits for them
-		const int why = (j.gate_result && *j.gate_result == 0) ? 1 : (*j.mf_overflow ? 2 : 0);
-		if (why) { // uniform over the CTA
-			if (threadIdx.x == 0)
-				j.skipped = why;
-			return;
+	if (*j.mf_overflow) { // uniform over the CTA: the host encodes this block again with a larger pool
+		if (threadIdx.x == 0)
+			j.skipped = 2;
+		return;
+	}
+	if (threadIdx.x == 0) {
+		done = 0;
+		gate_state = 0;
+	}
+	__syncthreads();
+	if (threadIdx.x >= 64) {
+		// warp 2: the lz4 compressibility gate (LZ4_TEST) of this block, beside the encoder instead of in front of
+		// it.  lz4_compresses() is a serial LZ4 emulation: one lane.  A block it rejects costs the encoder the
+		// gate's run time (it gives up when it reads the verdict); every other block starts encoding at once.
+		if (threadIdx.x == 64) {
+			int v = 1;
+			if (j.threshold)
+				v = lz4s::gate(j.src, (int64_t)j.n, j.threshold, gate_table) ? 1 : 2;
+			__threadfence_block();
+			*(volatile int *)&gate_state = v;
 		}
+		return;
 	}
 	if (threadIdx.x >= 32) {
-		if (threadIdx.x == 32)
-			done = 0;
-		__syncthreads(); // the encoder state (e->pos) is initialised
+		asm volatile("bar.sync 1, 64;" ::: "memory"); // warps 0 and 1: the encoder state (e->pos) is initialised
 		lzma_lookahead_warp(e, j, &done);
 		return;
 	}
 	lzma::enc_init(e, j.cfg, j.src, j.n, j.out, j.outCap, nullptr, nullptr, nullptr, nullptr);
 	e->preRec = j.rec;
 	e->prePool = j.pool;
-	__syncthreads();
+	asm volatile("bar.sync 1, 64;" ::: "memory");
+	e->gateState = j.threshold ? &gate_state : nullptr;
+	__syncwarp();
 	const uint64_t len = lzma::enc_run(e);
 	__syncwarp();
+	int verdict = 1;
+	if (j.threshold) // a block shorter than the gate's run time: wait for the verdict
+		while ((verdict = *(volatile int *)&gate_state) == 0)
+			__nanosleep(500);
 	if (threadIdx.x == 0) {
 		done = 1;
 		j.outLen = len;
 		j.overflow = e->overflow;
+		j.skipped = verdict == 2 ? 1 : 0;
 	}
 }
 
@@ -259,8 +280,9 @@ struct AsyncGroup {
 	size_t first = 0, count = 0; // subs[first .. first + count)
 	size_t meta_off = 0;         // [LzmaJob x m][MfBlock x m][segBase x (m + 1)][GateJob x m] in BackendCtx::meta
 	cudaStream_t ps = nullptr;   // parser stream
-	cudaEvent_t evMF = nullptr, evGate = nullptr, evDone = nullptr;
-	bool gated = false, launched = false, finished = false;
+	cudaEvent_t evMF = nullptr, evDone = nullptr; // sorts done / parser done
+	uint64_t walk_total = 0;                       // positions of the group (grid of the tree walk)
+	bool hc5 = false, launched = false, finished = false;
 };
 
 struct BackendCtx {
@@ -387,6 +409,20 @@ int backend_async_begin(BackendCtx *b, const lrzgpu_params &p, const lrzgpu_sizi
 			 ((size_t)slots * b->slot_bytes) >> 20);
 		return LRZGPU_ENOMEM;
 	}
+	// streams and events of the groups are made now: nothing is created or freed while block encoders run
+	const size_t want_streams = (size_t)(max_blocks < 96 ? max_blocks : 96);
+	while (b->pstreams.size() < want_streams) {
+		cudaStream_t st = nullptr;
+		if (cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking) != cudaSuccess)
+			return LRZGPU_ECUDA;
+		b->pstreams.push_back(st);
+	}
+	while (b->events.size() < 2 * want_streams) {
+		cudaEvent_t ev = nullptr;
+		if (cudaEventCreateWithFlags(&ev, cudaEventDisableTiming) != cudaSuccess)
+			return LRZGPU_ECUDA;
+		b->events.push_back(ev);
+	}
 	b->nslots = (int)slots;
 	b->slots_used = 0;
 	b->out_used = b->meta_used = 0;
@@ -416,9 +452,8 @@ static int enqueue_group(BackendCtx *b, size_t first, size_t m, const std::vecto
 	AsyncGroup G;
 	G.first = first;
 	G.count = m;
-	G.gated = gate;
 	const size_t o_mb = m * sizeof(LzmaJob), o_seg = align_up(o_mb + m * sizeof(lzma::MfBlock), 8);
-	const size_t o_gate = align_up(o_seg + (m + 1) * 8, 8), total = align_up(o_gate + m * sizeof(GateJob), 256);
+	const size_t total = align_up(o_seg + (m + 1) * 8, 256);
 	if (b->meta_used + total > b->meta.cap)
 		return 1; // drain first
 	G.meta_off = b->meta_used;
@@ -436,7 +471,7 @@ static int enqueue_group(BackendCtx *b, size_t first, size_t m, const std::vecto
 		b->pstreams.push_back(s);
 	}
 	G.ps = b->pstreams[gi];
-	cudaEvent_t evGate = nullptr, evMF = next_event(b);
+	cudaEvent_t evMF = next_event(b);
 	if (!evMF)
 		return LRZGPU_ECUDA;
 	if (ready && cudaEventSynchronize(ready) != cudaSuccess) // see pump_groups: no device-side waits on these streams
@@ -444,7 +479,6 @@ static int enqueue_group(BackendCtx *b, size_t first, size_t m, const std::vecto
 	std::vector<LzmaJob> lj(m);
 	std::vector<lzma::MfBlock> mb(m);
 	std::vector<uint64_t> seg(m + 1, 0);
-	std::vector<GateJob> gj(m);
 	bool hc5 = false;
 	for (size_t i = 0; i < m; i++) {
 		AsyncSub &S = b->subs[first + i];
@@ -475,9 +509,6 @@ static int enqueue_group(BackendCtx *b, size_t first, size_t m, const std::vecto
 		B.pool = (uint32_t *)(W + L.pool);
 		B.poolCap = L.poolCap;
 		seg[i + 1] = seg[i] + B.count;
-		gj[i].src = bj.d_src;
-		gj[i].len = bj.u_len;
-		gj[i].result = 0;
 		LzmaJob &j = lj[i];
 		memset(&j, 0, sizeof(j));
 		j.src = bj.d_src;
@@ -487,7 +518,7 @@ static int enqueue_group(BackendCtx *b, size_t first, size_t m, const std::vecto
 		j.rec = B.rec;
 		j.pool = B.pool;
 		j.cfg = c;
-		j.gate_result = gate ? &((GateJob *)(J + o_gate))[i].result : nullptr;
+		j.threshold = gate ? b->p.threshold : 0;
 		j.mf_overflow = B.overflow;
 		S.group = (int)gi;
 		S.index_in_group = (int)i;
@@ -502,26 +533,11 @@ static int enqueue_group(BackendCtx *b, size_t first, size_t m, const std::vecto
 	    cudaMemcpyAsync(J + o_mb, mb.data(), m * sizeof(lzma::MfBlock), cudaMemcpyHostToDevice, b->sMF) != cudaSuccess ||
 	    cudaMemcpyAsync(J + o_seg, seg.data(), seg.size() * 8, cudaMemcpyHostToDevice, b->sMF) != cudaSuccess)
 		return LRZGPU_ECUDA;
-	if (gate) { // runs beside the match finder; the parser kernel reads the verdict on the device
-		evGate = next_event(b);
-		if (!evGate ||
-		    cudaMemcpyAsync(J + o_gate, gj.data(), m * sizeof(GateJob), cudaMemcpyHostToDevice, b->sGate) != cudaSuccess)
-			return LRZGPU_ECUDA;
-		lz4_gate_kernel<<<(unsigned)m, 32, 0, b->sGate>>>((GateJob *)(J + o_gate), b->p.threshold);
-		if (launches)
-			(*launches)++;
-		if (cudaEventRecord(evGate, b->sGate) != cudaSuccess)
-			return LRZGPU_ECUDA;
-	}
-	if (lzma::mf_walk_launch((const lzma::MfBlock *)(J + o_mb), (int)m, (const uint64_t *)(J + o_seg), seg.back(), hc5, b->sMF,
-				 launches)) {
-		snprintf(err, errlen, "LZMA match finder walk: %s", cudaGetErrorString(cudaGetLastError()));
-		return LRZGPU_ECUDA;
-	}
 	if (cudaEventRecord(evMF, b->sMF) != cudaSuccess)
 		return LRZGPU_ECUDA;
 	G.evMF = evMF;
-	G.evGate = evGate;
+	G.walk_total = seg.back();
+	G.hc5 = hc5;
 	G.evDone = next_event(b);
 	if (!G.evDone)
 		return LRZGPU_ECUDA;
@@ -529,7 +545,7 @@ static int enqueue_group(BackendCtx *b, size_t first, size_t m, const std::vecto
 	return LRZGPU_OK;
 }
 
-// Launch the parser kernels of the groups whose match finder (and gate) have finished.  The host does the
+// Launch the tree walk and the parser kernel of the groups whose sorts have finished.  The host does the
 // waiting: a parser stream that waited on the device would sit at the head of a hardware work queue it shares
 // with other streams (CUDA_DEVICE_MAX_CONNECTIONS, 8 by default) and hold up their launches -- the scan's
 // among them -- and so would a parser kernel that finds no SM with 135 KB of shared memory free, hence the cap
@@ -557,13 +573,23 @@ static int pump_groups(BackendCtx *b, bool wait, int64_t *launches, char *err, s
 			continue;
 		}
 		if (wait) {
-			if (cudaEventSynchronize(G.evMF) != cudaSuccess || (G.evGate && cudaEventSynchronize(G.evGate) != cudaSuccess)) {
-				snprintf(err, errlen, "LZMA match finder failed: %s", cudaGetErrorString(cudaGetLastError()));
+			if (cudaEventSynchronize(G.evMF) != cudaSuccess) {
+				snprintf(err, errlen, "LZMA match finder sorts failed: %s", cudaGetErrorString(cudaGetLastError()));
 				return LRZGPU_ECUDA;
 			}
-		} else if (cudaEventQuery(G.evMF) != cudaSuccess || (G.evGate && cudaEventQuery(G.evGate) != cudaSuccess))
+		} else if (cudaEventQuery(G.evMF) != cudaSuccess)
 			return LRZGPU_OK;
-		lzma_block_kernel<<<(unsigned)G.count, 64, sizeof(lzma::Enc), G.ps>>>((LzmaJob *)((uint8_t *)b->meta.p + G.meta_off));
+		// the tree walk's run time is that of the block's longest hash bucket (one thread per bucket) whatever the
+		// number of blocks in the launch: it goes on the group's own stream, so that the walks of successive
+		// groups overlap, and the parser kernel follows it in stream order
+		uint8_t *J = (uint8_t *)b->meta.p + G.meta_off;
+		const size_t o_mb = G.count * sizeof(LzmaJob), o_seg = align_up(o_mb + G.count * sizeof(lzma::MfBlock), 8);
+		if (lzma::mf_walk_launch((const lzma::MfBlock *)(J + o_mb), (int)G.count, (const uint64_t *)(J + o_seg), G.walk_total,
+					 G.hc5, G.ps, launches)) {
+			snprintf(err, errlen, "LZMA match finder walk: %s", cudaGetErrorString(cudaGetLastError()));
+			return LRZGPU_ECUDA;
+		}
+		lzma_block_kernel<<<(unsigned)G.count, 96, sizeof(lzma::Enc), G.ps>>>((LzmaJob *)J);
 		if (launches)
 			(*launches)++;
 		if (cudaGetLastError() != cudaSuccess || cudaEventRecord(G.evDone, G.ps) != cudaSuccess) {

@@ -1372,7 +1372,17 @@ __device__ void k2_commit_segment_batched(WarpPrim &prim, FastShared *sh, ScanSt
 				}
 			}
 			const bool mine = lane >= base && lane < k;
-			if (mine) {
+			// Two lanes of a batch never write the same slot -- except a twin, which may replace the entry its
+			// predecessor has just inserted (when that entry is due for cleaning, or is the victim of the eviction
+			// it completes): the twin's store has to land second.  A twin's predecessor is never a twin itself.
+			if (mine && !L.twin) {
+				for (int w = 0; w < L.nw; w++)
+					*reinterpret_cast<longlong2 *>(prim.tab + L.wslot[w]) = make_longlong2(L.woff[w], L.wtag[w]);
+				if (cl)
+					*reinterpret_cast<longlong2 *>(prim.tab + del) = make_longlong2(0, 0);
+			}
+			__syncwarp();
+			if (mine && L.twin) {
 				for (int w = 0; w < L.nw; w++)
 					*reinterpret_cast<longlong2 *>(prim.tab + L.wslot[w]) = make_longlong2(L.woff[w], L.wtag[w]);
 				if (cl)

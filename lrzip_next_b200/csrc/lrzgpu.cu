@@ -432,9 +432,15 @@ int compress_chunk_pipelined(lrzgpu_ctx *c, const lrzgpu_params &p, const lrzgpu
 	const int rzl = p.rzip_level ? p.rzip_level : p.level;
 	const int cb = chunk_bytes_for(n);
 	const int64_t bs = sz.bufsize;
+	// every device buffer is sized before the first block goes to the backend: cudaFree / cudaMalloc wait for the
+	// whole device, i.e. for block encoders that run for tens of seconds
+	const int64_t rec_max = n / kMinMatch + 8, pieces_max = n / 0xFFFF + rec_max;
+	const int64_t s0_max = (6 + cb) * pieces_max + 64;
 	CU(c, c->s1.ensure((size_t)n + 64));
-	const int64_t max_blocks = n / bs + n / bs / 3 + 4; // stream 1 <= n bytes, stream 0 <= about n / 4
-	int rc = backend_async_begin(c->backend, p, sz, bs < n ? bs : n, max_blocks, n + n / 3 + (1 << 20), c->err, sizeof(c->err));
+	CU(c, c->s0.ensure((size_t)s0_max));
+	CU(c, c->w1.ensure((size_t)(s0_max / bs + 2) * 8));
+	const int64_t max_blocks = n / bs + s0_max / bs + 4;
+	int rc = backend_async_begin(c->backend, p, sz, bs < n ? bs : n, max_blocks, n + s0_max + (1 << 20), c->err, sizeof(c->err));
 	if (rc)
 		return rc;
 	int64_t s1_done = 0, blk1 = 0;
@@ -624,11 +630,15 @@ int lrzgpu_create(int device, lrzgpu_ctx **out)
 	cudaDeviceProp prop;
 	if (cudaGetDeviceProperties(&prop, device) == cudaSuccess)
 		c->sms = prop.multiProcessorCount;
-	bool ok = cudaStreamCreateWithFlags(&c->sA, cudaStreamNonBlocking) == cudaSuccess &&
-		  cudaStreamCreateWithFlags(&c->sB, cudaStreamNonBlocking) == cudaSuccess &&
+	// the scan's streams outrank the backend's: while block encoders and match-finder kernels of earlier blocks
+	// fill the GPU, the next segment's tag scan and commit kernel must not queue behind their pending CTAs
+	int prio_lo = 0, prio_hi = 0;
+	cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
+	bool ok = cudaStreamCreateWithPriority(&c->sA, cudaStreamNonBlocking, prio_hi) == cudaSuccess &&
+		  cudaStreamCreateWithPriority(&c->sB, cudaStreamNonBlocking, prio_hi) == cudaSuccess &&
 		  cudaStreamCreateWithFlags(&c->sC, cudaStreamNonBlocking) == cudaSuccess &&
 		  cudaStreamCreateWithFlags(&c->sD, cudaStreamNonBlocking) == cudaSuccess &&
-		  cudaStreamCreateWithFlags(&c->sE, cudaStreamNonBlocking) == cudaSuccess;
+		  cudaStreamCreateWithPriority(&c->sE, cudaStreamNonBlocking, prio_hi) == cudaSuccess;
 	for (int i = 0; i < 2 && ok; i++)
 		ok = cudaEventCreateWithFlags(&c->evK1[i], cudaEventDisableTiming) == cudaSuccess &&
 		     cudaEventCreateWithFlags(&c->evK2[i], cudaEventDisableTiming) == cudaSuccess;

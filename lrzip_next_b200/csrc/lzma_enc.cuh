@@ -131,6 +131,10 @@ struct Enc {
 	// precomputed match lists (lzma_mf.cu): when preRec is set the serial finder above is not used
 	const uint64_t *preRec;
 	const uint32_t *prePool;
+	// lz4 compressibility gate running beside the encoder (device): 0 undecided, 1 compressible, 2 leave the
+	// block stored -- the encoder gives up as soon as it reads 2 (null: no gate)
+	const int *gateState;
+	int aborted;
 	uint32_t pos;       // position the match finder will hand out next
 	uint32_t cycPos;
 	uint32_t crc[256];
@@ -1412,6 +1416,8 @@ LZ_FN inline void enc_init(Enc *e, const Config &c, const uint8_t *src, uint32_t
 	e->lpMask = (0x100u << c.lp) - (0x100u >> c.lc);
 	e->preRec = nullptr;
 	e->prePool = nullptr;
+	e->gateState = nullptr;
+	e->aborted = 0;
 	e->hash2 = hash2;
 	e->hash3 = hash3;
 	e->hash4 = hash4;
@@ -1611,6 +1617,10 @@ LZ_FN inline uint64_t enc_run(Enc *e)
 				}
 				if (mf_avail(e) == 0)
 					break;
+				if (e->gateState && *(const volatile int *)e->gateState == 2) { // the same word for every lane
+					e->aborted = 1;
+					break;
+				}
 			}
 		}
 	}
