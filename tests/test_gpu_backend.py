@@ -94,8 +94,8 @@ def test_pipelined_chunk_equals_plain_and_reference(ctx, monkeypatch):
     """Chunks above one scan segment run the LZMA backend UNDER the rzip stage (blocks submitted as they fill,
     gate verdicts read on the device).  Same bytes as the plain order, and as the reference: text blocks that
     compress, random blocks the lz4 gate leaves stored, zero blocks, several blocks per stream."""
-    d = np.concatenate([datagen.generate("text", 22 << 20), RNG.integers(0, 256, 12 << 20, dtype=np.uint8),
-                        np.zeros(11 << 20, dtype=np.uint8), datagen.generate("text", 3 << 20)])
+    d = np.concatenate([datagen.generate("text", 18 << 20), RNG.integers(0, 256, 25 << 20, dtype=np.uint8),
+                        np.zeros(5 << 20, dtype=np.uint8), datagen.generate("text", 3 << 20)])
     kw = dict(threads=8, processors=os.cpu_count() or 8)
     p = make_params(backend=BACKEND_LZMA, **kw)
     got, st = ctx.compress(d, p, want_stats=True)
