@@ -10,8 +10,10 @@
 //
 // zstd: libzstd is not vendored by the reference and its source is not available here, so frames
 // byte-identical to ZSTD_compress(level 17) are out of reach ("parity unpinned").  What
-// is produced is a valid Zstandard frame (RFC 8878) of Raw and RLE blocks, which the reference's
-// ZSTD_decompress() accepts; blocks that do not shrink are stored, like the reference does.
+// is produced is a valid Zstandard frame (RFC 8878) of genuinely compressed blocks (zstd_enc.cuh: LZ
+// sequences from the same data-parallel match finder the LZMA backend uses, FSE-coded with the format's
+// predefined tables, Huffman literals), which the reference's ZSTD_decompress() accepts; a frame that is
+// not smaller than the block leaves the block stored, like the reference does.
 #include "backend.h"
 
 #include <stdio.h>
@@ -25,6 +27,7 @@
 #include "lz4_size.cuh"
 #include "lzma_enc.cuh"
 #include "lzma_mf.h"
+#include "zstd_enc.cuh"
 
 namespace lrz {
 
@@ -84,8 +87,97 @@ struct LzmaJob {
 	const int *mf_overflow; // the match finder ran out of pool for this block: encode it again with a larger one
 	uint64_t outLen;
 	int overflow;
-	int skipped;            // 1: gate said incompressible, 2: match-list pool overflow
+	int skipped;            // 1: gate said incompressible, 2: match-list pool overflow, 3: zstd frame not smaller
+	// zstd: per 128 KiB zstd block scratch carved from the match finder's arrays the walk no longer needs
+	zs::Seq *zseq;          // nzb x (kBlockMax / 3 + 2) sequences           (over `son`)
+	uint8_t *zlit;          // nzb x kBlockMax literal bytes                  (over `c2`)
+	uint8_t *zstage;        // nzb x (kBlockMax + 64) encoded block contents  (over `c3`)
+	uint32_t *zsize;        // [2 * nzb] (type << 28 | payload size), then offsets in the frame  (over `sorted`)
+	uint32_t nzb;
+	const int *gate_result; // zstd: verdict of the lz4 gate kernel that ran before (device), or null
 };
+
+constexpr uint32_t kZsSeqPerBlock = zs::kBlockMax / 3 + 2;
+constexpr uint32_t kZsStagePerBlock = zs::kBlockMax + 64;
+
+// zstd, step 1: every 128 KiB zstd block of every stream block, one warp each (lane 0 parses and codes: both are
+// serial bit-stream work; the blocks are the parallelism -- 80 per 10 MiB stream block).
+__global__ void __launch_bounds__(32) zstd_encode_kernel(LzmaJob *jobs, const zs::Tables *T, uint32_t fb)
+{
+	LzmaJob &j = jobs[blockIdx.y];
+	const uint32_t x = blockIdx.x;
+	if (x >= j.nzb)
+		return;
+	if ((j.gate_result && *j.gate_result == 0) || *j.mf_overflow)
+		return; // decided in the assemble kernel
+	const uint32_t lo = x * zs::kBlockMax, hi = lo + zs::kBlockMax < j.n ? lo + zs::kBlockMax : j.n, size = hi - lo;
+	int same = 1;
+	for (uint32_t i = lo + threadIdx.x; i < hi; i += 32)
+		if (j.src[i] != j.src[lo])
+			same = 0;
+	same = __all_sync(0xffffffffu, same);
+	if (threadIdx.x != 0)
+		return;
+	uint32_t v;
+	if (same && size > 1)
+		v = (1u << 28) | 1u; // RLE block
+	else {
+		const uint32_t cs = zs::encode_block(*T, j.src, j.n, lo, hi, j.rec, j.pool, fb, j.zseq + (size_t)x * kZsSeqPerBlock,
+						     j.zlit + (size_t)x * zs::kBlockMax, j.zstage + (size_t)x * kZsStagePerBlock,
+						     size + 64); // the last block's share of the scratch array is only that long
+		v = cs ? ((2u << 28) | cs) : size; // compressed, else raw
+	}
+	j.zsize[x] = v;
+}
+
+// zstd, step 2: frame header, block offsets, block headers and payloads of one stream block's frame.
+__global__ void __launch_bounds__(256) zstd_assemble_kernel(LzmaJob *jobs)
+{
+	LzmaJob &j = jobs[blockIdx.x];
+	__shared__ uint64_t total_s;
+	__shared__ int why_s;
+	uint32_t *off = j.zsize + j.nzb;
+	if (threadIdx.x == 0) {
+		int why = (j.gate_result && *j.gate_result == 0) ? 1 : (*j.mf_overflow ? 2 : 0);
+		uint64_t total = 0;
+		if (!why) {
+			uint8_t hdr[16];
+			const uint32_t hl = zs::frame_header(j.n, hdr);
+			total = hl;
+			for (uint32_t x = 0; x < j.nzb; x++) {
+				off[x] = (uint32_t)total;
+				total += 3 + (j.zsize[x] & 0x0FFFFFFFu);
+			}
+			if (total >= j.n || total > j.outCap) // src/stream.c:205-221: not smaller (or no room) => stays stored
+				why = 3;
+			else
+				for (uint32_t i = 0; i < hl; i++)
+					j.out[i] = hdr[i];
+		}
+		total_s = total;
+		why_s = why;
+		j.outLen = total;
+		j.skipped = why;
+		j.overflow = 0;
+	}
+	__syncthreads();
+	if (why_s)
+		return;
+	for (uint32_t x = 0; x < j.nzb; x++) {
+		const uint32_t v = j.zsize[x], type = v >> 28, payload = v & 0x0FFFFFFFu;
+		const uint32_t lo = x * zs::kBlockMax, size = (lo + zs::kBlockMax < j.n ? lo + zs::kBlockMax : j.n) - lo;
+		uint8_t *w = j.out + off[x];
+		if (threadIdx.x == 0) {
+			const uint32_t h = (uint32_t)(x == j.nzb - 1) | (type << 1) | ((type == 1 ? size : payload) << 3);
+			w[0] = (uint8_t)h;
+			w[1] = (uint8_t)(h >> 8);
+			w[2] = (uint8_t)(h >> 16);
+		}
+		const uint8_t *from = type == 2 ? j.zstage + (size_t)x * kZsStagePerBlock : j.src + lo;
+		for (uint32_t i = threadIdx.x; i < payload; i += 256)
+			w[3 + i] = from[i];
+	}
+}
 
 // K7b: optimal parser + range coder, one block per CTA, over the precomputed match lists.
 // The whole encoder state (probabilities, price tables, the 2048-cell parse table: 135 KB) lives in the
@@ -186,45 +278,6 @@ __global__ void __launch_bounds__(96, 1) lzma_block_kernel(LzmaJob *jobs)
 	}
 }
 
-// ---- zstd (Raw / RLE blocks) ----------------------------------------------------------------------
-constexpr int64_t kZstdBlock = 128 * 1024;
-
-// flags[c] = 1 when chunk c of the job is one repeated byte
-__global__ void __launch_bounds__(256) zstd_scan_kernel(const uint8_t *src, int64_t len, uint8_t *flags)
-{
-	const int64_t c = blockIdx.x;
-	const int64_t lo = c * kZstdBlock, hi = (lo + kZstdBlock < len) ? lo + kZstdBlock : len;
-	const uint8_t first = src[lo];
-	int same = 1;
-	for (int64_t i = lo + threadIdx.x; i < hi; i += 256)
-		if (src[i] != first)
-			same = 0;
-	same = __syncthreads_and(same);
-	if (threadIdx.x == 0)
-		flags[c] = (uint8_t)same;
-}
-
-// writes block c (header + payload) at out + offs[c]
-__global__ void __launch_bounds__(256) zstd_emit_kernel(const uint8_t *src, int64_t len, const uint8_t *flags,
-							 const int64_t *offs, int64_t nchunks, uint8_t *out)
-{
-	const int64_t c = blockIdx.x;
-	const int64_t lo = c * kZstdBlock, hi = (lo + kZstdBlock < len) ? lo + kZstdBlock : len, size = hi - lo;
-	uint8_t *w = out + offs[c];
-	const int rle = flags[c];
-	if (threadIdx.x == 0) {
-		const uint32_t hdr = (uint32_t)(c == nchunks - 1) | ((rle ? 1u : 0u) << 1) | ((uint32_t)size << 3);
-		w[0] = (uint8_t)hdr;
-		w[1] = (uint8_t)(hdr >> 8);
-		w[2] = (uint8_t)(hdr >> 16);
-		if (rle)
-			w[3] = src[lo];
-	}
-	if (!rle)
-		for (int64_t i = threadIdx.x; i < size; i += 256)
-			w[3 + i] = src[lo + i];
-}
-
 int64_t round_up_page(int64_t v, int page) { return v % page ? v + page - v % page : v; }
 
 } // namespace
@@ -282,11 +335,13 @@ struct AsyncGroup {
 	cudaStream_t ps = nullptr;   // parser stream
 	cudaEvent_t evMF = nullptr, evDone = nullptr; // sorts done / parser done
 	uint64_t walk_total = 0;                       // positions of the group (grid of the tree walk)
-	bool hc5 = false, launched = false, finished = false;
+	uint32_t max_nzb = 0;                          // zstd: most 128 KiB blocks in one stream block of the group
+	bool hc5 = false, gated = false, launched = false, finished = false;
 };
 
 struct BackendCtx {
-	DevBuf jobs, work, out, flags, offs, scratch, meta, big;
+	DevBuf jobs, work, out, flags, offs, scratch, meta, big, zs_tables;
+	bool zstd = false; // the chunk's backend (else LZMA)
 	cudaStream_t sMF = nullptr, sGate = nullptr;
 	std::vector<cudaStream_t> pstreams;
 	std::vector<cudaEvent_t> events;
@@ -311,7 +366,7 @@ void backend_destroy(BackendCtx *b)
 {
 	if (!b)
 		return;
-	DevBuf *bufs[] = { &b->jobs, &b->work, &b->out, &b->flags, &b->offs, &b->scratch, &b->meta, &b->big };
+	DevBuf *bufs[] = { &b->jobs, &b->work, &b->out, &b->flags, &b->offs, &b->scratch, &b->meta, &b->big, &b->zs_tables };
 	for (DevBuf *d : bufs)
 		d->release();
 	for (cudaStream_t s : b->pstreams)
@@ -358,9 +413,18 @@ int backend_async_begin(BackendCtx *b, const lrzgpu_params &p, const lrzgpu_sizi
 			int64_t max_blocks, int64_t payload_bytes_upper, char *err, size_t errlen)
 {
 	b->active = false;
-	if (p.backend != LRZGPU_BACKEND_LZMA) {
-		snprintf(err, errlen, "the block pipeline is the LZMA backend's");
+	if (p.backend != LRZGPU_BACKEND_LZMA && p.backend != LRZGPU_BACKEND_ZSTD) {
+		snprintf(err, errlen, "the block pipeline serves the LZMA and zstd backends");
 		return LRZGPU_EUNSUPPORTED;
+	}
+	b->zstd = p.backend == LRZGPU_BACKEND_ZSTD;
+	if (b->zstd && !b->zs_tables.p) { // the format's predefined FSE tables, built once on the host
+		zs::Tables T;
+		zs::build_tables(T);
+		if (b->zs_tables.ensure(sizeof(T)) != cudaSuccess || cudaMemcpy(b->zs_tables.p, &T, sizeof(T), cudaMemcpyHostToDevice) != cudaSuccess) {
+			snprintf(err, errlen, "zstd tables: %s", cudaGetErrorString(cudaGetLastError()));
+			return LRZGPU_ECUDA;
+		}
 	}
 	if (lzma::mf_init_tables()) {
 		snprintf(err, errlen, "LZMA match finder tables: %s", cudaGetErrorString(cudaGetLastError()));
@@ -373,11 +437,15 @@ int backend_async_begin(BackendCtx *b, const lrzgpu_params &p, const lrzgpu_sizi
 	}
 	b->p = p;
 	b->sz = sz;
-	b->fb = p.level < 7 ? 32 : 64; // src/stream.c:455
+	b->fb = (p.level < 7 && !b->zstd) ? 32 : 64; // src/stream.c:455
+	if (b->zstd) { // the match finder in its binary-tree form with a 32 MiB window, whatever the level
+		b->sz.dict_size = 1u << 25;
+		b->p.level = p.level < 5 ? 5 : p.level;
+	}
 	lzma::Config cfg;
 	if (max_block_len < 1)
 		max_block_len = 1;
-	if (!lzma::make_config(p.level, sz.dict_size, b->fb, (uint64_t)max_block_len, cfg) || b->fb > lzma::kMfMaxFb) {
+	if (!lzma::make_config(b->p.level, b->sz.dict_size, b->fb, (uint64_t)max_block_len, cfg) || b->fb > lzma::kMfMaxFb) {
 		snprintf(err, errlen, "LZMA level %d / block of %lld bytes is not supported by the device encoder", p.level,
 			 (long long)max_block_len);
 		return LRZGPU_EUNSUPPORTED;
@@ -453,7 +521,8 @@ static int enqueue_group(BackendCtx *b, size_t first, size_t m, const std::vecto
 	G.first = first;
 	G.count = m;
 	const size_t o_mb = m * sizeof(LzmaJob), o_seg = align_up(o_mb + m * sizeof(lzma::MfBlock), 8);
-	const size_t total = align_up(o_seg + (m + 1) * 8, 256);
+	const size_t o_gate = align_up(o_seg + (m + 1) * 8, 8);
+	const size_t total = align_up(o_gate + m * sizeof(GateJob), 256);
 	if (b->meta_used + total > b->meta.cap)
 		return 1; // drain first
 	G.meta_off = b->meta_used;
@@ -479,6 +548,7 @@ static int enqueue_group(BackendCtx *b, size_t first, size_t m, const std::vecto
 	std::vector<LzmaJob> lj(m);
 	std::vector<lzma::MfBlock> mb(m);
 	std::vector<uint64_t> seg(m + 1, 0);
+	std::vector<GateJob> gj(m);
 	bool hc5 = false;
 	for (size_t i = 0; i < m; i++) {
 		AsyncSub &S = b->subs[first + i];
@@ -520,6 +590,18 @@ static int enqueue_group(BackendCtx *b, size_t first, size_t m, const std::vecto
 		j.cfg = c;
 		j.threshold = gate ? b->p.threshold : 0;
 		j.mf_overflow = B.overflow;
+		if (b->zstd) {
+			j.outCap = (uint64_t)round_up_page(bj.u_len, b->p.page_size); // src/stream.c:169
+			j.nzb = (uint32_t)(((uint64_t)bj.u_len + zs::kBlockMax - 1) / zs::kBlockMax);
+			j.zseq = (zs::Seq *)(W + L.son);
+			j.zlit = W + L.c2;
+			j.zstage = W + L.c3;
+			j.zsize = (uint32_t *)(W + L.sorted);
+			j.gate_result = gate ? &((GateJob *)(J + o_gate))[i].result : nullptr;
+			gj[i].src = bj.d_src;
+			gj[i].len = bj.u_len;
+			gj[i].result = 0;
+		}
 		S.group = (int)gi;
 		S.index_in_group = (int)i;
 		if (cudaMemsetAsync(W + L.ctl, 0, 256 + 8 * (size_t)bj.u_len, b->sMF) != cudaSuccess)
@@ -531,13 +613,18 @@ static int enqueue_group(BackendCtx *b, size_t first, size_t m, const std::vecto
 	}
 	if (cudaMemcpyAsync(J, lj.data(), o_mb, cudaMemcpyHostToDevice, b->sMF) != cudaSuccess ||
 	    cudaMemcpyAsync(J + o_mb, mb.data(), m * sizeof(lzma::MfBlock), cudaMemcpyHostToDevice, b->sMF) != cudaSuccess ||
-	    cudaMemcpyAsync(J + o_seg, seg.data(), seg.size() * 8, cudaMemcpyHostToDevice, b->sMF) != cudaSuccess)
+	    cudaMemcpyAsync(J + o_seg, seg.data(), seg.size() * 8, cudaMemcpyHostToDevice, b->sMF) != cudaSuccess ||
+	    (b->zstd && cudaMemcpyAsync(J + o_gate, gj.data(), m * sizeof(GateJob), cudaMemcpyHostToDevice, b->sMF) != cudaSuccess))
 		return LRZGPU_ECUDA;
 	if (cudaEventRecord(evMF, b->sMF) != cudaSuccess)
 		return LRZGPU_ECUDA;
 	G.evMF = evMF;
 	G.walk_total = seg.back();
 	G.hc5 = hc5;
+	G.gated = gate;
+	for (size_t i = 0; i < m; i++)
+		if (lj[i].nzb > G.max_nzb)
+			G.max_nzb = lj[i].nzb;
 	G.evDone = next_event(b);
 	if (!G.evDone)
 		return LRZGPU_ECUDA;
@@ -589,9 +676,22 @@ static int pump_groups(BackendCtx *b, bool wait, int64_t *launches, char *err, s
 			snprintf(err, errlen, "LZMA match finder walk: %s", cudaGetErrorString(cudaGetLastError()));
 			return LRZGPU_ECUDA;
 		}
-		lzma_block_kernel<<<(unsigned)G.count, 96, sizeof(lzma::Enc), G.ps>>>((LzmaJob *)J);
-		if (launches)
-			(*launches)++;
+		if (b->zstd) {
+			const size_t o_gate = align_up(o_seg + (G.count + 1) * 8, 8);
+			if (G.gated) {
+				lz4_gate_kernel<<<(unsigned)G.count, 32, 0, G.ps>>>((GateJob *)(J + o_gate), b->p.threshold);
+				if (launches)
+					(*launches)++;
+			}
+			zstd_encode_kernel<<<dim3(G.max_nzb, (unsigned)G.count), 32, 0, G.ps>>>((LzmaJob *)J, (const zs::Tables *)b->zs_tables.p, b->fb);
+			zstd_assemble_kernel<<<(unsigned)G.count, 256, 0, G.ps>>>((LzmaJob *)J);
+			if (launches)
+				(*launches) += 2;
+		} else {
+			lzma_block_kernel<<<(unsigned)G.count, 96, sizeof(lzma::Enc), G.ps>>>((LzmaJob *)J);
+			if (launches)
+				(*launches)++;
+		}
 		if (cudaGetLastError() != cudaSuccess || cudaEventRecord(G.evDone, G.ps) != cudaSuccess) {
 			snprintf(err, errlen, "LZMA kernel launch: %s", cudaGetErrorString(cudaGetLastError()));
 			return LRZGPU_ECUDA;
@@ -627,7 +727,7 @@ int backend_async_submit(BackendCtx *b, const BlockJob *jobs, int n, cudaEvent_t
 		S.job.d_payload = jobs[i].d_src;
 		if ((size_t)jobs[i].u_len > b->max_block ||
 		    !lzma::make_config(b->p.level, b->sz.dict_size, b->fb, (uint64_t)jobs[i].u_len, S.cfg)) {
-			snprintf(err, errlen, "LZMA block of %lld bytes is not supported by the device encoder", (long long)jobs[i].u_len);
+			snprintf(err, errlen, "block of %lld bytes is not supported by the device encoder", (long long)jobs[i].u_len);
 			return LRZGPU_EUNSUPPORTED;
 		}
 		S.oofs = osum;
@@ -669,8 +769,8 @@ static int collect_groups(BackendCtx *b, std::vector<size_t> &redo, int64_t *lau
 		for (size_t i = 0; i < G.count; i++) {
 			AsyncSub &S = b->subs[G.first + i];
 			S.done = true;
-			if (lj[i].skipped == 1)
-				continue; // LZ4_TEST (FLAG_THRESHOLD): incompressible blocks stay stored
+			if (lj[i].skipped == 1 || lj[i].skipped == 3)
+				continue; // LZ4_TEST (FLAG_THRESHOLD): incompressible blocks stay stored; zstd frame not smaller
 			if (lj[i].skipped == 2) {
 				S.done = false;
 				redo.push_back(G.first + i);
@@ -678,7 +778,7 @@ static int collect_groups(BackendCtx *b, std::vector<size_t> &redo, int64_t *lau
 			}
 			// src/stream.c:482-487: kept only when smaller; SZ_ERROR_OUTPUT_EOF leaves the block stored
 			if (!lj[i].overflow && (int64_t)lj[i].outLen < S.job.u_len) {
-				S.job.c_type = LRZGPU_CTYPE_LZMA;
+				S.job.c_type = b->zstd ? LRZGPU_CTYPE_ZSTD : LRZGPU_CTYPE_LZMA;
 				S.job.c_len = (int64_t)lj[i].outLen;
 				S.job.d_payload = lj[i].out;
 			}
@@ -788,106 +888,6 @@ static int run_lzma(BackendCtx *b, const lrzgpu_params &p, const lrzgpu_sizing_t
 	return LRZGPU_OK;
 }
 
-static int run_zstd(BackendCtx *b, std::vector<BlockJob> &jobs, const std::vector<int> &idx, cudaStream_t stream,
-		    int64_t *launches)
-{
-	// layout of all frames in b->out
-	size_t osum = 0;
-	std::vector<size_t> oofs;
-	for (int i : idx) {
-		oofs.push_back(osum);
-		osum += align_up((size_t)jobs[i].u_len + 64, 256);
-	}
-	if (b->out.ensure(osum) != cudaSuccess)
-		return LRZGPU_ENOMEM;
-	for (size_t k = 0; k < idx.size(); k++) {
-		BlockJob &bj = jobs[idx[k]];
-		const int64_t n = bj.u_len, nchunks = (n + kZstdBlock - 1) / kZstdBlock;
-		if (b->flags.ensure((size_t)nchunks) != cudaSuccess || b->offs.ensure((size_t)nchunks * 8) != cudaSuccess)
-			return LRZGPU_ENOMEM;
-		zstd_scan_kernel<<<(unsigned)nchunks, 256, 0, stream>>>(bj.d_src, n, (uint8_t *)b->flags.p);
-		std::vector<uint8_t> flags((size_t)nchunks);
-		if (cudaMemcpyAsync(flags.data(), b->flags.p, (size_t)nchunks, cudaMemcpyDeviceToHost, stream) != cudaSuccess ||
-		    cudaStreamSynchronize(stream) != cudaSuccess)
-			return LRZGPU_ECUDA;
-		if (launches)
-			(*launches)++;
-		// frame header: magic, FHD (single segment, FCS size by value), FCS
-		uint8_t hdr[16];
-		int hl = 0;
-		hdr[hl++] = 0x28;
-		hdr[hl++] = 0xB5;
-		hdr[hl++] = 0x2F;
-		hdr[hl++] = 0xFD;
-		if (n < 256) {
-			hdr[hl++] = 0x20;
-			hdr[hl++] = (uint8_t)n;
-		} else if (n < 65536 + 256) {
-			hdr[hl++] = 0x60;
-			hdr[hl++] = (uint8_t)(n - 256);
-			hdr[hl++] = (uint8_t)((n - 256) >> 8);
-		} else if (n <= 0xFFFFFFFFll) {
-			hdr[hl++] = 0xA0;
-			for (int i = 0; i < 4; i++)
-				hdr[hl++] = (uint8_t)(n >> (8 * i));
-		} else {
-			hdr[hl++] = 0xE0;
-			for (int i = 0; i < 8; i++)
-				hdr[hl++] = (uint8_t)(n >> (8 * i));
-		}
-		std::vector<int64_t> offs((size_t)nchunks);
-		int64_t total = hl;
-		for (int64_t c = 0; c < nchunks; c++) {
-			const int64_t size = (c == nchunks - 1) ? n - c * kZstdBlock : kZstdBlock;
-			offs[(size_t)c] = total;
-			total += 3 + (flags[(size_t)c] ? 1 : size);
-		}
-		if (total >= n)
-			continue; // src/stream.c:215-221: not smaller => stays CTYPE_NONE
-		uint8_t *out = (uint8_t *)b->out.p + oofs[k];
-		if (cudaMemcpyAsync(out, hdr, (size_t)hl, cudaMemcpyHostToDevice, stream) != cudaSuccess ||
-		    cudaMemcpyAsync(b->offs.p, offs.data(), (size_t)nchunks * 8, cudaMemcpyHostToDevice, stream) != cudaSuccess)
-			return LRZGPU_ECUDA;
-		zstd_emit_kernel<<<(unsigned)nchunks, 256, 0, stream>>>(bj.d_src, n, (const uint8_t *)b->flags.p,
-									 (const int64_t *)b->offs.p, nchunks, out);
-		if (launches)
-			(*launches)++;
-		if (cudaStreamSynchronize(stream) != cudaSuccess)
-			return LRZGPU_ECUDA;
-		bj.c_type = LRZGPU_CTYPE_ZSTD;
-		bj.c_len = total;
-		bj.d_payload = out;
-	}
-	return LRZGPU_OK;
-}
-
-// lz4 gate of a list of blocks, synchronously (zstd path; the LZMA pipeline runs its gate on the device side)
-static int run_gate(BackendCtx *b, std::vector<BlockJob> &jobs, const std::vector<int> &idx, int threshold,
-		    std::vector<int> &pass, cudaStream_t stream, int64_t *launches)
-{
-	std::vector<GateJob> g(idx.size());
-	for (size_t i = 0; i < idx.size(); i++) {
-		g[i].src = jobs[idx[i]].d_src;
-		g[i].len = jobs[idx[i]].u_len;
-		g[i].result = 0;
-	}
-	if (b->jobs.ensure(g.size() * sizeof(GateJob)) != cudaSuccess)
-		return LRZGPU_ENOMEM;
-	if (cudaMemcpyAsync(b->jobs.p, g.data(), g.size() * sizeof(GateJob), cudaMemcpyHostToDevice, stream) != cudaSuccess)
-		return LRZGPU_ECUDA;
-	lz4_gate_kernel<<<(unsigned)g.size(), 32, 0, stream>>>((GateJob *)b->jobs.p, threshold);
-	if (launches)
-		(*launches)++;
-	if (cudaMemcpyAsync(g.data(), b->jobs.p, g.size() * sizeof(GateJob), cudaMemcpyDeviceToHost, stream) != cudaSuccess ||
-	    cudaStreamSynchronize(stream) != cudaSuccess)
-		return LRZGPU_ECUDA;
-	pass.clear();
-	for (size_t i = 0; i < idx.size(); i++)
-		if (g[i].result)
-			pass.push_back(idx[i]);
-	return LRZGPU_OK;
-}
-
 int backend_encode_blocks(BackendCtx *b, const lrzgpu_params &p, const lrzgpu_sizing_t &sz, std::vector<BlockJob> &jobs,
 			  int num_sms, cudaStream_t stream, int64_t *launches, char *err, size_t errlen)
 {
@@ -898,25 +898,8 @@ int backend_encode_blocks(BackendCtx *b, const lrzgpu_params &p, const lrzgpu_si
 			idx.push_back((int)i);
 	if (idx.empty())
 		return LRZGPU_OK;
-	if (p.backend == LRZGPU_BACKEND_LZMA) // gate (when on), match finder and parser of every block, pipelined
+	if (p.backend == LRZGPU_BACKEND_LZMA || p.backend == LRZGPU_BACKEND_ZSTD) // gate, match finder, block coder: pipelined
 		return run_lzma(b, p, sz, jobs, idx, stream, launches, err, errlen);
-	if (p.threshold) { // LZ4_TEST (FLAG_THRESHOLD): incompressible blocks stay stored
-		std::vector<int> pass;
-		int rc = run_gate(b, jobs, idx, p.threshold, pass, stream, launches);
-		if (rc) {
-			snprintf(err, errlen, "lz4 gate kernel failed: %s", cudaGetErrorString(cudaGetLastError()));
-			return rc;
-		}
-		idx.swap(pass);
-		if (idx.empty())
-			return LRZGPU_OK;
-	}
-	if (p.backend == LRZGPU_BACKEND_ZSTD) {
-		int rc = run_zstd(b, jobs, idx, stream, launches);
-		if (rc)
-			snprintf(err, errlen, "zstd backend failed: %s", cudaGetErrorString(cudaGetLastError()));
-		return rc;
-	}
 	snprintf(err, errlen, "backend %d is not supported", p.backend);
 	return LRZGPU_EUNSUPPORTED;
 }

@@ -550,7 +550,7 @@ int compress_chunk_pipelined(lrzgpu_ctx *c, const lrzgpu_params &p, const lrzgpu
 int compress_chunk_device(lrzgpu_ctx *c, const lrzgpu_params &p, const lrzgpu_sizing_t &sz, const uint8_t *d_chunk,
 			  int64_t n, int eof, int64_t *victim_round, OutBuf &out, lrzgpu_stats *stats)
 {
-	if (p.backend == LRZGPU_BACKEND_LZMA && n > kSegment && !getenv("LRZGPU_NO_OVERLAP"))
+	if ((p.backend == LRZGPU_BACKEND_LZMA || p.backend == LRZGPU_BACKEND_ZSTD) && n > kSegment && !getenv("LRZGPU_NO_OVERLAP"))
 		return compress_chunk_pipelined(c, p, sz, d_chunk, n, eof, victim_round, out, stats);
 	const int rzl = p.rzip_level ? p.rzip_level : p.level;
 	const int cb = chunk_bytes_for(n);

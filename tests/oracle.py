@@ -286,3 +286,40 @@ def lzma_block_fn(level: int, dict_size: int, threshold: int = 100):
             c_type[0] = 6
         return 0
     return fn
+
+
+def walk_blocks(archive: bytes):
+    """Block headers of a v0.14 archive in file order: [(chunk, ctype, c_len, u_len)] (SURVEY.md Appendix A:
+    21-byte magic, per chunk [cb][eof][chunk_size:cb], two initial stream headers, then blocks
+    [ctype][c_len:cb][u_len:cb][next_head:cb] + payload; 16-byte MD5 at the end)."""
+    out, pos, chunk = [], 21 + archive[20], 0
+    end = len(archive) - 16
+    while pos < end:
+        cb, eof = archive[pos], archive[pos + 1]
+        pos += 2 + cb
+        initial = pos
+        hdr = 1 + 3 * cb
+        pos += 2 * hdr
+        # blocks follow back to back until the chunk ends: the last block of stream 1 is physically last
+        # (src/lrzip.c:1276), so walk until both streams have seen a header with next_head == 0
+        open_streams = 2
+        heads = {}
+        for s in range(2):
+            nh = int.from_bytes(archive[initial + s * hdr + 1 + 2 * cb: initial + s * hdr + hdr], "little")
+            heads[initial + nh] = s
+        while open_streams and pos < end:
+            ctype = archive[pos]
+            c_len = int.from_bytes(archive[pos + 1:pos + 1 + cb], "little")
+            u_len = int.from_bytes(archive[pos + 1 + cb:pos + 1 + 2 * cb], "little")
+            nh = int.from_bytes(archive[pos + 1 + 2 * cb:pos + hdr], "little")
+            s = heads.pop(pos)
+            out.append((chunk, s, ctype, c_len, u_len))
+            if nh:
+                heads[initial + nh] = s
+            else:
+                open_streams -= 1
+            pos += hdr + c_len
+        chunk += 1
+        if eof:
+            break
+    return out

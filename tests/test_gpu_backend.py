@@ -105,3 +105,64 @@ def test_pipelined_chunk_equals_plain_and_reference(ctx, monkeypatch):
     monkeypatch.delenv("LRZGPU_NO_OVERLAP")
     assert got == plain
     assert got == oracle.ref_compress(d, oracle.make_params(backend=oracle.BACKEND_LZMA, **kw))
+
+
+def _libzstd():
+    import ctypes as C
+    try:
+        Z = C.CDLL("libzstd.so.1")
+    except OSError:
+        pytest.skip("system libzstd not present")
+    Z.ZSTD_decompress.restype = C.c_size_t
+    Z.ZSTD_decompress.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t]
+    Z.ZSTD_isError.restype = C.c_uint
+    Z.ZSTD_compress.restype = C.c_size_t
+    Z.ZSTD_compress.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_int]
+    return Z
+
+
+def test_zstd_blocks_are_compressed_frames_libzstd_decodes(ctx):
+    """zstd backend, block level.  PARITY UNPINNED for payload bytes (libzstd 1.5.5 is not vendored and its source
+    is absent): what is pinned is (a) every payload is a Zstandard frame libzstd decodes back to the block,
+    (b) the stored / compressed decision equals the reference's (lz4 gate + ZSTD_compress(17) + "not smaller =>
+    stored", src/stream.c:167-229), (c) the size delta against ZSTD_compress(level 17) is reported."""
+    import ctypes as C
+    Z = _libzstd()
+    p = make_params(level=7, backend=BACKEND_ZSTD, threads=8)
+    report = {}
+    for name, d in _inputs().items():
+        if len(d) < 64:
+            continue
+        got, ctype = ctx.block_compress(d, p)
+        n = len(d)
+        ref = C.create_string_buffer(n + n // 8 + 1024)
+        rs = Z.ZSTD_compress(ref, len(ref), d, n, 17)
+        ref_kept = bool(oracle.ref_lz4_gate(d, 100)) and not Z.ZSTD_isError(rs) and rs < n
+        if ctype == 10:
+            back = C.create_string_buffer(n + 16)
+            r = Z.ZSTD_decompress(back, len(back), got, len(got))
+            assert not Z.ZSTD_isError(r) and r == n and back.raw[:n] == d, name
+            assert len(got) < n
+        else:
+            assert ctype == 3 and got == d, name
+        assert (ctype == 10) == ref_kept, (name, ctype, rs, n)
+        report[name] = {"n": n, "ours": len(got), "zstd17": int(rs), "delta_pct": round(100.0 * (len(got) - rs) / rs, 1)}
+    print("zstd payload parity: UNPINNED; sizes vs ZSTD_compress(17):", report)
+    assert report["text"]["ours"] < 0.55 * report["text"]["n"]  # text is compressed for real now
+
+
+@pytest.mark.skipif(not oracle.have_ref(), reason="oracle/_ref not built")
+def test_zstd_c4_shaped_block_decisions_match_reference(ctx):
+    """C4 shape (random || zeros, -Z, gate on), scaled: per block, the same c_type and u_len as the reference's
+    archive (random blocks stay stored behind the lz4 gate, zero blocks become zstd frames), and the reference
+    decodes our archive."""
+    d = np.concatenate([RNG.integers(0, 256, 24 << 20, dtype=np.uint8), np.zeros(24 << 20, dtype=np.uint8)])
+    kw = dict(threads=8, processors=os.cpu_count() or 8)
+    got = ctx.compress(d, make_params(backend=BACKEND_ZSTD, **kw))
+    want = oracle.ref_compress(d, oracle.make_params(backend=oracle.BACKEND_ZSTD, **kw))
+    ours = [(c, s, t, u) for c, s, t, cl, u in oracle.walk_blocks(got)]
+    theirs = [(c, s, t, u) for c, s, t, cl, u in oracle.walk_blocks(want)]
+    assert ours == theirs
+    assert any(t == 3 for _, _, t, _ in ours) and any(t == 10 for _, _, t, _ in ours)
+    assert got[:21] == want[:21] and got[-16:] == want[-16:]
+    assert oracle.ref_decompress(got) == d.tobytes()
