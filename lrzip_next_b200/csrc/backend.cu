@@ -412,6 +412,9 @@ int backend_lz4_gate(BackendCtx *b, const uint8_t *d_src, int64_t len, int thres
 int backend_async_begin(BackendCtx *b, const lrzgpu_params &p, const lrzgpu_sizing_t &sz, int64_t max_block_len,
 			int64_t max_blocks, int64_t payload_bytes_upper, char *err, size_t errlen)
 {
+	if (b->active && !b->groups.empty()) // an abandoned chunk: its kernels still use the work space
+		cudaDeviceSynchronize();
+	b->groups.clear();
 	b->active = false;
 	if (p.backend != LRZGPU_BACKEND_LZMA && p.backend != LRZGPU_BACKEND_ZSTD) {
 		snprintf(err, errlen, "the block pipeline serves the LZMA and zstd backends");
@@ -902,6 +905,20 @@ int backend_encode_blocks(BackendCtx *b, const lrzgpu_params &p, const lrzgpu_si
 		return run_lzma(b, p, sz, jobs, idx, stream, launches, err, errlen);
 	snprintf(err, errlen, "backend %d is not supported", p.backend);
 	return LRZGPU_EUNSUPPORTED;
+}
+
+// Load this file's kernels now (CUDA loads a kernel's code at its first launch, and that load waits for every kernel
+// that is running -- block encoders run for tens of seconds).
+int backend_preload()
+{
+	cudaFuncAttributes a;
+	bool ok = true;
+	ok = ok && cudaFuncGetAttributes(&a, lz4_gate_kernel) == cudaSuccess;
+	ok = ok && cudaFuncGetAttributes(&a, lzma_block_kernel) == cudaSuccess;
+	ok = ok && cudaFuncGetAttributes(&a, zstd_assemble_kernel) == cudaSuccess;
+	ok = ok && cudaFuncGetAttributes(&a, zstd_encode_kernel) == cudaSuccess;
+	ok = ok && lzma::mf_preload() == 0;
+	return ok ? 0 : -1;
 }
 
 } // namespace lrz

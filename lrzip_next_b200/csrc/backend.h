@@ -21,6 +21,7 @@ struct BlockJob {
 struct BackendCtx; // opaque per-context scratch, owned by lrzgpu_ctx
 
 BackendCtx *backend_create();
+int backend_preload(); // load every backend kernel's code now
 void backend_destroy(BackendCtx *b);
 // Runs the lz4 gate (when threshold != 0) and the backend on every job with u_len >= 64
 // (src/stream.c:1633), synchronously on `stream`.  Jobs left stored keep c_type NONE / c_len u_len.

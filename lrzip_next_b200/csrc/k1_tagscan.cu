@@ -273,4 +273,14 @@ int k1_launch(const uint8_t *d_buf, int64_t n, int64_t pos_lo, int64_t pos_hi, i
 	return cudaGetLastError() == cudaSuccess ? 0 : -1;
 }
 
+// Load this file's kernels now (CUDA loads a kernel's code at its first launch, and that load waits for every kernel
+// that is running -- block encoders run for tens of seconds).
+int k1_preload()
+{
+	cudaFuncAttributes a;
+	bool ok = true;
+	ok = ok && cudaFuncGetAttributes(&a, k1_tagscan_kernel) == cudaSuccess;
+	return ok ? 0 : -1;
+}
+
 } // namespace lrz

@@ -1522,4 +1522,14 @@ int k2_launch(const uint8_t *d_buf, ScanState *d_state, HEntry *d_tab, const Can
 	return cudaGetLastError() == cudaSuccess ? 0 : -1;
 }
 
+// Load this file's kernels now (CUDA loads a kernel's code at its first launch, and that load waits for every kernel
+// that is running -- block encoders run for tens of seconds).
+int k2_preload()
+{
+	cudaFuncAttributes a;
+	bool ok = true;
+	ok = ok && cudaFuncGetAttributes(&a, k2_commit_kernel) == cudaSuccess;
+	return ok ? 0 : -1;
+}
+
 } // namespace lrz

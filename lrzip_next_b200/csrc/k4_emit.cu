@@ -381,4 +381,17 @@ int k4_flush_order_launch(const MatchRec *d_recs, int64_t n_rec, int chunk_bytes
 	return cudaGetLastError() == cudaSuccess ? 0 : -1;
 }
 
+// Load this file's kernels now (CUDA loads a kernel's code at its first launch, and that load waits for every kernel
+// that is running -- block encoders run for tens of seconds).
+int k4_preload()
+{
+	cudaFuncAttributes a;
+	bool ok = true;
+	ok = ok && cudaFuncGetAttributes(&a, crc32_kernel) == cudaSuccess;
+	ok = ok && cudaFuncGetAttributes(&a, k4_flush_order_kernel) == cudaSuccess;
+	ok = ok && cudaFuncGetAttributes(&a, k4_headers_kernel) == cudaSuccess;
+	ok = ok && cudaFuncGetAttributes(&a, k4_literals_kernel) == cudaSuccess;
+	return ok ? 0 : -1;
+}
+
 } // namespace lrz

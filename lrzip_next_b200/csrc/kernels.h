@@ -7,6 +7,9 @@ namespace lrz {
 
 // ---- K1 tag scan (k1_tagscan.cu) ------------------------------------------------------------
 int k1_init_tables();
+int k1_preload(); // load the kernels' code now (see k1_tagscan.cu)
+int k2_preload();
+int k4_preload();
 // Scan positions [pos_lo, pos_hi) (pos_lo tile-aligned, kTile = 512) of the n-byte chunk at d_buf (followed by at
 // least kInputPad readable bytes) and write the candidates with (tag & mask) == mask, tile-strided:
 // candidates of tile T (positions [T*512, (T+1)*512)) start at d_cand[(T - pos_lo/512) * 512].

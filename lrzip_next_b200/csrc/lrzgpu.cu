@@ -87,6 +87,8 @@ struct lrzgpu_ctx {
 		int eof = 0, cb = 0;
 		const uint8_t *d_chunk = nullptr;
 		bool selected = false; // streams emitted (always true after lrzgpu_chunk_begin)
+		bool pipelined = false; // lrzgpu_chunk_begin handed blocks to the backend during the scan
+		int64_t blk1 = 0;
 		std::vector<int64_t> v_s0, v_s1, v_nrec, v_base, v_out; // per variant, after lrzgpu_chunk_begin_all
 		std::vector<ScanState> v_st;
 	} pending;
@@ -425,12 +427,10 @@ int finish_chunk_device(lrzgpu_ctx *c, const lrzgpu_params &p, const lrzgpu_sizi
 // moment the scan has produced its last byte (the reference does the same: write_stream() flushes a full buffer to
 // a compthread, src/stream.c:2198-2216, 1836-1875), so that at the end of the scan only the blocks that were
 // still open -- the last full one, the two tails and stream 0 -- remain to be encoded.
-int compress_chunk_pipelined(lrzgpu_ctx *c, const lrzgpu_params &p, const lrzgpu_sizing_t &sz, const uint8_t *d_chunk,
-			     int64_t n, int eof, int64_t *victim_round, OutBuf &out, lrzgpu_stats *stats)
+int pipelined_scan(lrzgpu_ctx *c, const lrzgpu_params &p, const lrzgpu_sizing_t &sz, const uint8_t *d_chunk, int64_t n, int cb,
+		   int64_t *victim_round, ChunkResult &res_out, int64_t &blk1_out, lrzgpu_stats *stats)
 {
-	const double t0 = now_ms();
 	const int rzl = p.rzip_level ? p.rzip_level : p.level;
-	const int cb = chunk_bytes_for(n);
 	const int64_t bs = sz.bufsize;
 	// every device buffer is sized before the first block goes to the backend: cudaFree / cudaMalloc wait for the
 	// whole device, i.e. for block encoders that run for tens of seconds
@@ -444,17 +444,6 @@ int compress_chunk_pipelined(lrzgpu_ctx *c, const lrzgpu_params &p, const lrzgpu
 	if (rc)
 		return rc;
 	int64_t s1_done = 0, blk1 = 0;
-	auto submit = [&](const BlockJob *jobs, int cnt, cudaEvent_t ready) -> int {
-		int r = backend_async_submit(c->backend, jobs, cnt, ready, &c->launches, c->err, sizeof(c->err));
-		if (r == 1) { // work space used up: wait for what is in flight (the scan goes on meanwhile), then go on
-			r = backend_async_drain(c->backend, &c->launches, c->err, sizeof(c->err));
-			if (!r)
-				r = backend_async_submit(c->backend, jobs, cnt, ready, &c->launches, c->err, sizeof(c->err));
-			if (r == 1)
-				r = fail(c, LRZGPU_EINTERNAL, "LZMA work space cannot hold %d blocks", cnt);
-		}
-		return r;
-	};
 	const ScanProgress progress = [&](const ScanState &st) -> int {
 		const int64_t full = st.s1_len / bs;
 		if (full <= blk1)
@@ -475,7 +464,17 @@ int compress_chunk_pipelined(lrzgpu_ctx *c, const lrzgpu_params &p, const lrzgpu
 			j.c_len = bs;
 			j.d_payload = j.d_src;
 		}
-		const int r = bs >= 64 ? submit(jobs.data(), (int)jobs.size(), nullptr) : 0;
+		int r = 0;
+		if (bs >= 64) {
+			r = backend_async_submit(c->backend, jobs.data(), (int)jobs.size(), nullptr, &c->launches, c->err, sizeof(c->err));
+			if (r == 1) { // work space used up: wait for what is in flight (the scan goes on meanwhile), then go on
+				r = backend_async_drain(c->backend, &c->launches, c->err, sizeof(c->err));
+				if (!r)
+					r = backend_async_submit(c->backend, jobs.data(), (int)jobs.size(), nullptr, &c->launches, c->err, sizeof(c->err));
+				if (r == 1)
+					r = fail(c, LRZGPU_EINTERNAL, "LZMA work space cannot hold %d blocks", (int)jobs.size());
+			}
+		}
 		blk1 = full;
 		s1_done = st.s1_len;
 		return r;
@@ -484,15 +483,26 @@ int compress_chunk_pipelined(lrzgpu_ctx *c, const lrzgpu_params &p, const lrzgpu
 	rc = rzip_scan_device(c, d_chunk, n, rzl, cb, *victim_round, 1, all, stats, &progress);
 	if (rc)
 		return rc;
-	const ChunkResult &res = all[0];
-	*victim_round = res.st.victim_round;
+	res_out = all[0];
+	*victim_round = res_out.st.victim_round;
 	CU(c, cudaStreamSynchronize(c->sE));
-	rc = rzip_emit_device(c, d_chunk, cb, res, stats, s1_done);
+	rc = rzip_emit_device(c, d_chunk, cb, res_out, stats, s1_done);
 	if (rc)
 		return rc;
+	if (bs < 64)
+		blk1 = 0; // nothing was handed over
+	blk1_out = blk1;
+	return LRZGPU_OK;
+}
+
+// Second half of a pipelined chunk: the blocks the scan could not hand over, drain, framing.
+int pipelined_finish(lrzgpu_ctx *c, const lrzgpu_params &p, const lrzgpu_sizing_t &sz, int64_t n, int eof, int cb,
+		     const ChunkResult &res, int64_t blk1, OutBuf &out, lrzgpu_stats *stats)
+{
 	const double t1 = now_ms();
+	const int64_t bs = sz.bufsize;
 	std::vector<BlockJob> jobs;
-	rc = plan_chunk_blocks(c, sz, cb, res, jobs);
+	int rc = plan_chunk_blocks(c, sz, cb, res, jobs);
 	if (rc)
 		return rc;
 	// the blocks the scan could not hand over: whatever of stream 1 was not complete at the last look, stream 0
@@ -501,7 +511,7 @@ int compress_chunk_pipelined(lrzgpu_ctx *c, const lrzgpu_params &p, const lrzgpu
 	for (size_t i = 0; i < jobs.size(); i++) {
 		const BlockJob &j = jobs[i];
 		const int64_t off = j.d_src - (const uint8_t *)(j.stream ? c->s1.p : c->s0.p);
-		if (j.stream == 1 && bs >= 64 && off / bs < blk1 && j.u_len == bs)
+		if (j.stream == 1 && off / bs < blk1 && j.u_len == bs)
 			early[(size_t)(off / bs)] = (int)i;
 		else if (j.u_len >= 64) { // src/stream.c:1633
 			rest.push_back(j);
@@ -509,17 +519,28 @@ int compress_chunk_pipelined(lrzgpu_ctx *c, const lrzgpu_params &p, const lrzgpu
 		}
 	}
 	const int n_early = backend_async_count(c->backend);
-	if (!rest.empty()) {
-		rc = submit(rest.data(), (int)rest.size(), nullptr);
+	if (n_early != blk1)
+		return fail(c, LRZGPU_EINTERNAL, "pipelined blocks out of step");
+	size_t at = 0;
+	while (at < rest.size()) { // as many at a time as the work space takes
+		size_t take = rest.size() - at;
+		for (;;) {
+			rc = backend_async_submit(c->backend, rest.data() + at, (int)take, nullptr, &c->launches, c->err, sizeof(c->err));
+			if (rc != 1)
+				break;
+			if (take > 1)
+				take = (take + 1) / 2;
+			else if ((rc = backend_async_drain(c->backend, &c->launches, c->err, sizeof(c->err))))
+				break;
+		}
 		if (rc)
 			return rc;
+		at += take;
 	}
 	rc = backend_async_drain(c->backend, &c->launches, c->err, sizeof(c->err));
 	if (rc)
 		return rc;
-	if (n_early != (bs >= 64 ? blk1 : 0))
-		return fail(c, LRZGPU_EINTERNAL, "pipelined blocks out of step");
-	auto take = [&](int job, int sub) -> int {
+	auto take_result = [&](int job, int sub) -> int {
 		const BlockJob *r = backend_async_result(c->backend, sub);
 		if (!r || job < 0)
 			return fail(c, LRZGPU_EINTERNAL, "missing result of a pipelined block");
@@ -529,10 +550,10 @@ int compress_chunk_pipelined(lrzgpu_ctx *c, const lrzgpu_params &p, const lrzgpu
 		return 0;
 	};
 	for (int k = 0; k < n_early; k++)
-		if ((rc = take(early[(size_t)k], k)))
+		if ((rc = take_result(early[(size_t)k], k)))
 			return rc;
 	for (size_t k = 0; k < late.size(); k++)
-		if ((rc = take(late[k], n_early + (int)k)))
+		if ((rc = take_result(late[k], n_early + (int)k)))
 			return rc;
 	const double t2 = now_ms();
 	rc = frame_chunk(c, p, n, eof, cb, jobs, out, stats);
@@ -542,15 +563,31 @@ int compress_chunk_pipelined(lrzgpu_ctx *c, const lrzgpu_params &p, const lrzgpu
 		stats->ms_backend += t2 - t1;
 		stats->ms_d2h += now_ms() - t2;
 	}
-	(void)t0;
 	return LRZGPU_OK;
+}
+
+bool pipelined_ok(const lrzgpu_params &p, int64_t n)
+{
+	return (p.backend == LRZGPU_BACKEND_LZMA || p.backend == LRZGPU_BACKEND_ZSTD) && n > kSegment && !getenv("LRZGPU_NO_OVERLAP");
+}
+
+int compress_chunk_pipelined(lrzgpu_ctx *c, const lrzgpu_params &p, const lrzgpu_sizing_t &sz, const uint8_t *d_chunk,
+			     int64_t n, int eof, int64_t *victim_round, OutBuf &out, lrzgpu_stats *stats)
+{
+	const int cb = chunk_bytes_for(n);
+	ChunkResult res;
+	int64_t blk1 = 0;
+	int rc = pipelined_scan(c, p, sz, d_chunk, n, cb, victim_round, res, blk1, stats);
+	if (rc)
+		return rc;
+	return pipelined_finish(c, p, sz, n, eof, cb, res, blk1, out, stats);
 }
 
 // One chunk: rzip on the device, then blocks -> backend -> framed blob appended to `out`.
 int compress_chunk_device(lrzgpu_ctx *c, const lrzgpu_params &p, const lrzgpu_sizing_t &sz, const uint8_t *d_chunk,
 			  int64_t n, int eof, int64_t *victim_round, OutBuf &out, lrzgpu_stats *stats)
 {
-	if ((p.backend == LRZGPU_BACKEND_LZMA || p.backend == LRZGPU_BACKEND_ZSTD) && n > kSegment && !getenv("LRZGPU_NO_OVERLAP"))
+	if (pipelined_ok(p, n))
 		return compress_chunk_pipelined(c, p, sz, d_chunk, n, eof, victim_round, out, stats);
 	const int rzl = p.rzip_level ? p.rzip_level : p.level;
 	const int cb = chunk_bytes_for(n);
@@ -649,6 +686,7 @@ int lrzgpu_create(int device, lrzgpu_ctx **out)
 	if (ok)
 		c->h_state_cap = 1;
 	ok = ok && k1_init_tables() == 0 && k4_init_tables() == 0;
+	ok = ok && k1_preload() == 0 && k2_preload() == 0 && k4_preload() == 0 && backend_preload() == 0;
 	if (ok) {
 		c->backend = backend_create();
 		ok = c->backend != nullptr;
@@ -956,13 +994,20 @@ int lrzgpu_chunk_begin(lrzgpu_ctx *c, const lrzgpu_params *p, const lrzgpu_sizin
 	const int rzl = p->rzip_level ? p->rzip_level : p->level;
 	const int cb = chunk_bytes_for(n);
 	ChunkResult res;
-	rc = rzip_chunk_device(c, d_in, n, rzl, cb, *victim_round, res, stats);
+	int64_t blk1 = 0;
+	const bool pipe = pipelined_ok(*p, n);
+	if (pipe)
+		rc = pipelined_scan(c, *p, *sz, d_in, n, cb, victim_round, res, blk1, stats);
+	else
+		rc = rzip_chunk_device(c, d_in, n, rzl, cb, *victim_round, res, stats);
 	if (rc)
 		return rc;
 	*victim_round = res.st.victim_round;
 	lrzgpu_ctx::Pending &pd = c->pending;
 	pd.valid = true;
 	pd.selected = true;
+	pd.pipelined = pipe;
+	pd.blk1 = blk1;
 	pd.p = *p;
 	pd.sz = *sz;
 	pd.n = n;
@@ -1033,6 +1078,7 @@ int lrzgpu_chunk_begin_all(lrzgpu_ctx *c, const lrzgpu_params *p, const lrzgpu_s
 	lrzgpu_ctx::Pending &pd = c->pending;
 	pd.valid = true;
 	pd.selected = false;
+	pd.pipelined = false;
 	pd.p = *p;
 	pd.sz = *sz;
 	pd.n = n;
@@ -1115,8 +1161,11 @@ int lrzgpu_chunk_finish(lrzgpu_ctx *c, uint8_t **blob, int64_t *blob_len, lrzgpu
 	res.rec_base = c->pending.rec_base;
 	c->pending.valid = false;
 	OutBuf ob;
-	const int rc = finish_chunk_device(c, c->pending.p, c->pending.sz, c->pending.n, c->pending.eof, c->pending.cb, res, ob,
-					   stats);
+	const int rc = c->pending.pipelined
+			       ? pipelined_finish(c, c->pending.p, c->pending.sz, c->pending.n, c->pending.eof, c->pending.cb, res,
+						  c->pending.blk1, ob, stats)
+			       : finish_chunk_device(c, c->pending.p, c->pending.sz, c->pending.n, c->pending.eof, c->pending.cb, res, ob,
+						     stats);
 	if (rc) {
 		free(ob.p);
 		return rc;

@@ -375,5 +375,23 @@ int mf_walk_launch(const MfBlock *d_blocks, int nblocks, const uint64_t *d_segBa
 	return cudaGetLastError() == cudaSuccess ? 0 : -1;
 }
 
+// Load this file's kernels now (CUDA loads a kernel's code at its first launch, and that load waits for every kernel
+// that is running -- block encoders run for tens of seconds).
+int mf_preload()
+{
+	cudaFuncAttributes a;
+	bool ok = true;
+	ok = ok && cudaFuncGetAttributes(&a, mf_copy_kernel) == cudaSuccess;
+	ok = ok && cudaFuncGetAttributes(&a, mf_hc_kernel) == cudaSuccess;
+	ok = ok && cudaFuncGetAttributes(&a, mf_prev_kernel) == cudaSuccess;
+	ok = ok && cudaFuncGetAttributes(&a, mf_walk_kernel) == cudaSuccess;
+	ok = ok && cudaFuncGetAttributes(&a, rs_hist_kernel<true>) == cudaSuccess;
+	ok = ok && cudaFuncGetAttributes(&a, rs_hist_kernel<false>) == cudaSuccess;
+	ok = ok && cudaFuncGetAttributes(&a, rs_scan_kernel) == cudaSuccess;
+	ok = ok && cudaFuncGetAttributes(&a, rs_scatter_kernel<true>) == cudaSuccess;
+	ok = ok && cudaFuncGetAttributes(&a, rs_scatter_kernel<false>) == cudaSuccess;
+	return ok ? 0 : -1;
+}
+
 } // namespace lzma
 } // namespace lrz

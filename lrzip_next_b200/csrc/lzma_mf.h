@@ -28,6 +28,7 @@ struct MfBlock {
 };
 
 int mf_init_tables();
+int mf_preload();
 // scratch needed by mf_prepare_block for blocks of up to maxCount positions
 size_t mf_sort_scratch_bytes(uint32_t maxCount);
 // sorts + c2/c3 + bucket order of one block (stream-ordered; scratch may be reused by the next block)
