@@ -212,8 +212,12 @@ def main():
     # -p: stream blocks are limit/threads but never below 10 MiB (src/stream.c:1140-1348), and one block is
     # the unit of backend parallelism on both arms.  -p 160 gives the 10 MiB minimum for 1 GB at -m 600
     # (the reference itself reduces it to what fits its memory budget); it is passed to both arms.
-    threads = a.threads or max(cores, 160)
-    ram_units = 600  # -m 600 = 60 GB, pinned for both arms
+    # Both scale with the number of windows: the reference sizes blocks as file size / threads while the file is smaller
+    # than a sixth of the declared RAM, and caps the threads by that RAM (105 at -m 600), so that N windows at a fixed
+    # -p / -m would be cut into N-times larger blocks than one window is.  -p 160 N -m 600 N keeps the per-window
+    # block structure (10 MiB blocks, 101 per window) the same at every N; both arms get the same flags.
+    threads = a.threads or max(cores, 160) * nwin
+    ram_units = 600 * nwin  # -m 600 = 60 GB per window, pinned for both arms
     # the same per-GPU size at every N; N > 1 = N windows of that size (-w in units of 100 MiB)
     window = 0 if nwin == 1 else size // (100 * MiB)
     if nwin > 1 and size % (100 * MiB):
