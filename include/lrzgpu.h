@@ -9,6 +9,7 @@
  *   lrzgpu_compress / _file / _device   rzip_fd()            src/include/rzip.h:12, src/rzip.c:922
  *                                       + write_magic()      src/lrzip.c:131 (called from
  *                                                            compress_file(), src/lrzip.c:1549-1553)
+ *   lrzgpu_compress_multi               the same with the windows of the file dealt to several GPUs
  *   lrzgpu_compress_chunk               one pass of the chunk loop src/rzip.c:1041-1186
  *   lrzgpu_chunk_begin / _finish        (rzip_chunk :873 + close_stream_out, src/stream.c:2253); the two-call form
  *                                       splits it at the point where rzip_chunk returns
@@ -114,6 +115,16 @@ int lrzgpu_compress_file(lrzgpu_ctx *ctx, const lrzgpu_params *p, const char *in
  * computed by a host thread from a device->host stream of the input unless md5 is given. */
 int lrzgpu_compress_device(lrzgpu_ctx *ctx, const lrzgpu_params *p, const void *d_in, int64_t n,
 			   const uint8_t *md5_or_null, uint8_t **out, int64_t *out_len, lrzgpu_stats *stats);
+
+/* Whole file on several GPUs of one box from ONE process (what a patched lrzip-next would call; one-process-per-GPU
+ * callers use the chunk entry points below and gather the blobs themselves, lrzip_next_b200/multigpu.py).  The file's
+ * rzip windows (src/rzip.c:1041-1186; more than one window needs -w or a file larger than 2/3 of the RAM) are dealt to
+ * the contexts round-robin, ctxs[i mod nctx]; every window after the first is scanned for all values of the
+ * cross-window counter at once (lrzgpu_chunk_begin_all), so the windows run concurrently; blobs are appended in
+ * file order between magic and MD5.  Contexts should sit on distinct devices (the same device works, for tests).
+ * The archive is byte-identical to lrzgpu_compress() with the same parameters. */
+int lrzgpu_compress_multi(lrzgpu_ctx **ctxs, int nctx, const lrzgpu_params *p, const uint8_t *in, int64_t n,
+			  uint8_t **out, int64_t *out_len, lrzgpu_stats *stats);
 
 /* One chunk (window) -> its position-independent blob (chunk preamble, stream headers, blocks), the
  * unit that is sharded across GPUs.  chunk_bytes/eof as in src/rzip.c:1129-1143; victim_round carries

@@ -68,7 +68,7 @@ _lib = None
 
 EXPORTS = [
     "lrzgpu_create", "lrzgpu_destroy", "lrzgpu_last_error", "lrzgpu_free", "lrzgpu_version", "lrzgpu_sizing",
-    "lrzgpu_compress", "lrzgpu_compress_file", "lrzgpu_compress_device", "lrzgpu_compress_chunk",
+    "lrzgpu_compress", "lrzgpu_compress_file", "lrzgpu_compress_device", "lrzgpu_compress_multi", "lrzgpu_compress_chunk",
     "lrzgpu_chunk_begin", "lrzgpu_chunk_finish", "lrzgpu_victim_values", "lrzgpu_chunk_begin_all", "lrzgpu_chunk_select",
     "lrzgpu_rzip_chunk", "lrzgpu_tag_scan", "lrzgpu_crc32", "lrzgpu_block_compress", "lrzgpu_lz4_gate",
     "lrzgpu_k1_launch", "lrzgpu_crc32_launch", "lrzgpu_sm_count",
@@ -100,6 +100,7 @@ def load_library():
     L.lrzgpu_compress.argtypes = [vp, C.POINTER(Params), vp, i64, pvp, pi64, C.POINTER(Stats)]
     L.lrzgpu_compress_file.argtypes = [vp, C.POINTER(Params), C.c_char_p, C.c_char_p, C.POINTER(Stats)]
     L.lrzgpu_compress_device.argtypes = [vp, C.POINTER(Params), vp, i64, vp, pvp, pi64, C.POINTER(Stats)]
+    L.lrzgpu_compress_multi.argtypes = [pvp, C.c_int, C.POINTER(Params), vp, i64, pvp, pi64, C.POINTER(Stats)]
     L.lrzgpu_compress_chunk.argtypes = [vp, C.POINTER(Params), C.POINTER(Sizing), vp, i64, C.c_int, pi64, pvp, pi64,
                                         C.POINTER(Stats)]
     L.lrzgpu_chunk_begin.argtypes = [vp, C.POINTER(Params), C.POINTER(Sizing), vp, i64, C.c_int, pi64, C.POINTER(Stats)]
@@ -131,6 +132,20 @@ def sizing(params: Params, st_size: int) -> Sizing:
 def victim_values(params: Params) -> int:
     """Number of values the reference's cross-window counter can take (max_chain_len of the rzip level)."""
     return load_library().lrzgpu_victim_values(C.byref(params))
+
+
+def compress_multi(contexts, data, params: Params, want_stats: bool = False):
+    """lrzgpu_compress_multi: one process, several contexts (GPUs); windows dealt round-robin."""
+    L = load_library()
+    addr, n, keep = _ptr(data)
+    arr = (C.c_void_p * len(contexts))(*[c.handle for c in contexts])
+    out, ol, st = C.c_void_p(), C.c_int64(), Stats()
+    rc = L.lrzgpu_compress_multi(arr, len(contexts), C.byref(params), addr, n, C.byref(out), C.byref(ol), C.byref(st))
+    if rc:
+        raise LrzGpuError(rc, (L.lrzgpu_last_error(contexts[0].handle) or b"").decode())
+    res = C.string_at(out, ol.value)
+    L.lrzgpu_free(out)
+    return (res, st.as_dict()) if want_stats else res
 
 
 def chunk_bytes_for(n: int) -> int:

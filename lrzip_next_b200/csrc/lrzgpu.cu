@@ -12,7 +12,9 @@
 #include <string.h>
 
 #include <chrono>
+#include <condition_variable>
 #include <functional>
+#include <mutex>
 #include <thread>
 #include <vector>
 
@@ -1177,6 +1179,210 @@ int lrzgpu_chunk_finish(lrzgpu_ctx *c, uint8_t **blob, int64_t *blob_len, lrzgpu
 		stats->kernel_launches = c->launches - launches0;
 	}
 	return LRZGPU_OK;
+}
+
+int lrzgpu_compress_multi(lrzgpu_ctx **ctxs, int nctx, const lrzgpu_params *p, const uint8_t *in, int64_t n, uint8_t **out,
+			  int64_t *out_len, lrzgpu_stats *stats)
+{
+	if (!ctxs || nctx < 1 || !p || !in || n <= 0 || !out || !out_len)
+		return LRZGPU_EINVAL;
+	for (int i = 0; i < nctx; i++)
+		if (!ctxs[i])
+			return LRZGPU_EINVAL;
+	lrzgpu_ctx *c0 = ctxs[0];
+	if (nctx == 1)
+		return lrzgpu_compress(c0, p, in, n, out, out_len, stats);
+	lrzgpu_sizing_t sz;
+	int rc = compute_sizing(*p, n, sz);
+	if (rc)
+		return fail(c0, rc, "unsupported parameters");
+	const double t0 = now_ms();
+	struct Win {
+		int64_t off = 0, size = 0;
+		int eof = 0;
+		uint8_t *blob = nullptr;
+		int64_t blob_len = 0;
+		lrzgpu_stats st;
+	};
+	std::vector<Win> wins;
+	for (int64_t off = 0; off < n; off += sz.max_chunk) { // src/rzip.c:1041: the window loop as a static plan
+		Win w;
+		w.off = off;
+		w.size = sz.max_chunk < n - off ? sz.max_chunk : n - off;
+		w.eof = off + w.size == n;
+		memset(&w.st, 0, sizeof(w.st));
+		wins.push_back(w);
+	}
+	const size_t nw = wins.size();
+	// the true value of the cross-window counter after window i (src/rzip.c:308), handed from owner to owner
+	std::vector<int64_t> v_out(nw, -1);
+	std::mutex mu;
+	std::condition_variable cv;
+	std::vector<int> rcs((size_t)nctx, 0);
+	auto wait_for = [&](size_t i) -> int64_t { // value after window i; -2 when its owner failed
+		std::unique_lock<std::mutex> lk(mu);
+		cv.wait(lk, [&] { return v_out[i] != -1; });
+		return v_out[i];
+	};
+	auto publish = [&](size_t i, int64_t v) {
+		{
+			std::lock_guard<std::mutex> lk(mu);
+			v_out[i] = v;
+		}
+		cv.notify_all();
+	};
+	auto worker = [&](int k) {
+		lrzgpu_ctx *c = ctxs[k];
+		for (size_t i = (size_t)k; i < nw; i += (size_t)nctx) { // window i belongs to context i mod nctx
+			Win &w = wins[i];
+			lrzgpu_stats a, b, s3;
+			memset(&s3, 0, sizeof(s3));
+			int r;
+			int64_t v = 0;
+			std::vector<int64_t> table;
+			const int nval = lrzgpu_victim_values(p);
+			if (i == 0)
+				r = lrzgpu_chunk_begin(c, p, &sz, in + w.off, w.size, w.eof, &v, &a);
+			else {
+				table.resize((size_t)nval);
+				r = lrzgpu_chunk_begin_all(c, p, &sz, in + w.off, w.size, w.eof, table.data(), nval, &a);
+				if (r == LRZGPU_ENOMEM) { // the variants do not fit: wait for the predecessor instead
+					table.clear();
+					v = wait_for(i - 1);
+					r = v < 0 ? LRZGPU_EINTERNAL : lrzgpu_chunk_begin(c, p, &sz, in + w.off, w.size, w.eof, &v, &a);
+				} else if (!r) {
+					const int64_t vin = wait_for(i - 1);
+					r = vin < 0 ? LRZGPU_EINTERNAL : lrzgpu_chunk_select(c, vin, &s3);
+					v = r ? 0 : table[(size_t)vin];
+				}
+			}
+			publish(i, r ? -2 : v);
+			if (!r)
+				r = lrzgpu_chunk_finish(c, &w.blob, &w.blob_len, &b);
+			if (r) {
+				rcs[(size_t)k] = r;
+				for (size_t j = i + (size_t)nctx; j < nw; j += (size_t)nctx)
+					publish(j, -2); // nobody waits forever for a window that will not be scanned
+				return;
+			}
+			// the window's counters: scan (begin or begin_all + select) and backend
+			lrzgpu_stats &d = w.st;
+			const lrzgpu_stats *parts[3] = { &a, &s3, &b };
+			for (const lrzgpu_stats *q : parts) {
+				d.matches += q->matches;
+				d.match_bytes += q->match_bytes;
+				d.literals += q->literals;
+				d.literal_bytes += q->literal_bytes;
+				d.tag_hits += q->tag_hits;
+				d.tag_misses += q->tag_misses;
+				d.inserts += q->inserts;
+				d.lookups += q->lookups;
+				d.chain_evictions += q->chain_evictions;
+				d.sweeps += q->sweeps;
+				d.displacements += q->displacements;
+				d.chunks += q->chunks;
+				d.blocks += q->blocks;
+				d.blocks_stored += q->blocks_stored;
+				d.stream0_bytes += q->stream0_bytes;
+				d.stream1_bytes += q->stream1_bytes;
+				d.ms_h2d += q->ms_h2d;
+				d.ms_rzip += q->ms_rzip;
+				d.ms_emit += q->ms_emit;
+				d.ms_backend += q->ms_backend;
+				d.ms_d2h += q->ms_d2h;
+				d.kernel_launches += q->kernel_launches;
+				if (q->crc32)
+					d.crc32 = q->crc32;
+				if (q->chunks) {
+					d.hash_count = q->hash_count;
+					d.final_min_mask = q->final_min_mask;
+					d.final_tag_mask = q->final_tag_mask;
+				}
+			}
+		}
+	};
+	uint8_t md5[16];
+	double md5_ms = 0;
+	std::thread hasher([&] { // whole-file MD5 in file order, overlapped with the GPUs (src/rzip.c:1195-1218)
+		const double a = now_ms();
+		Md5 m;
+		for (int64_t o = 0; o < n; o += (64 << 20))
+			m.update(in + o, (size_t)((n - o < (64 << 20)) ? n - o : (64 << 20)));
+		m.final(md5);
+		md5_ms = now_ms() - a;
+	});
+	std::vector<std::thread> th;
+	for (int k = 0; k < nctx; k++)
+		th.emplace_back(worker, k);
+	for (auto &t : th)
+		t.join();
+	hasher.join();
+	rc = 0;
+	for (int k = 0; k < nctx && !rc; k++)
+		if (rcs[(size_t)k]) {
+			rc = rcs[(size_t)k];
+			if (ctxs[k] != c0)
+				snprintf(c0->err, sizeof(c0->err), "context %d: %s", k, ctxs[k]->err);
+		}
+	OutBuf ob;
+	if (!rc) {
+		int64_t total = 21 + 16;
+		for (const Win &w : wins)
+			total += w.blob_len;
+		if (ob.reserve(total))
+			rc = fail(c0, LRZGPU_ENOMEM, "out of host memory");
+	}
+	if (!rc) {
+		memset(ob.p, 0, 21);
+		ob.len = 21;
+		for (const Win &w : wins) {
+			memcpy(ob.p + ob.len, w.blob, (size_t)w.blob_len);
+			ob.len += w.blob_len;
+		}
+		memcpy(ob.p + ob.len, md5, 16);
+		ob.len += 16;
+		make_magic(ob.p, *p, sz, n);
+		*out = ob.p;
+		*out_len = ob.len;
+	} else
+		free(ob.p);
+	if (stats) {
+		memset(stats, 0, sizeof(*stats));
+		for (const Win &w : wins) {
+			stats->matches += w.st.matches;
+			stats->match_bytes += w.st.match_bytes;
+			stats->literals += w.st.literals;
+			stats->literal_bytes += w.st.literal_bytes;
+			stats->tag_hits += w.st.tag_hits;
+			stats->tag_misses += w.st.tag_misses;
+			stats->inserts += w.st.inserts;
+			stats->lookups += w.st.lookups;
+			stats->chain_evictions += w.st.chain_evictions;
+			stats->sweeps += w.st.sweeps;
+			stats->displacements += w.st.displacements;
+			stats->chunks += w.st.chunks;
+			stats->blocks += w.st.blocks;
+			stats->blocks_stored += w.st.blocks_stored;
+			stats->stream0_bytes += w.st.stream0_bytes;
+			stats->stream1_bytes += w.st.stream1_bytes;
+			stats->kernel_launches += w.st.kernel_launches;
+			stats->ms_h2d += w.st.ms_h2d;
+			stats->ms_d2h += w.st.ms_d2h;
+			if (w.st.ms_rzip > stats->ms_rzip)
+				stats->ms_rzip = w.st.ms_rzip;
+			if (w.st.ms_backend > stats->ms_backend)
+				stats->ms_backend = w.st.ms_backend;
+			stats->crc32 = w.st.crc32;
+			stats->hash_count = w.st.hash_count;
+			stats->final_min_mask = w.st.final_min_mask;
+			stats->final_tag_mask = w.st.final_tag_mask;
+		}
+		stats->ms_md5 = md5_ms;
+		stats->ms_total = now_ms() - t0;
+	}
+	for (Win &w : wins)
+		free(w.blob);
+	return rc;
 }
 
 int lrzgpu_rzip_chunk(lrzgpu_ctx *c, const uint8_t *in, int64_t n, int rzip_level, int chunk_bytes,

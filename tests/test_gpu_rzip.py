@@ -194,3 +194,19 @@ def test_all_values_speculation_equals_chunk_from_known_value(ctx):
     assert len(set(blobs.values())) > 1, "the input was meant to depend on the incoming counter"
     with pytest.raises(Exception):
         ctx.chunk_select(0)  # nothing pending any more
+
+
+def test_compress_multi_equals_single_context(ctx):
+    """lrzgpu_compress_multi (one process, windows dealt to several contexts, all-values speculation of the
+    cross-window counter) == lrzgpu_compress, on text whose windows DO consult the counter.  Two contexts on the
+    same device here; on a multi-GPU box they would sit on different devices."""
+    from lrzip_next_b200 import Context
+    from lrzip_next_b200.api import compress_multi
+    d = datagen.generate("text", 230 << 20)   # 3 windows of 100 / 100 / 30 MiB
+    p = make_params(backend=BACKEND_NONE, threads=1, window=1)
+    want, st1 = ctx.compress(d, p, want_stats=True)
+    with Context(0) as c2:
+        got, st = compress_multi([ctx, c2], d, p, want_stats=True)
+    assert got == want
+    assert st["chunks"] == 3 and st["chain_evictions"] == st1["chain_evictions"] > 0
+    assert st["lookups"] == st1["lookups"] and st["matches"] == st1["matches"]
