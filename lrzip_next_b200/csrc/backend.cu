@@ -189,13 +189,17 @@ __global__ void __launch_bounds__(256) zstd_assemble_kernel(LzmaJob *jobs)
 // cannot change the output; it only turns the parser's dependent HBM/L2 round trips into L1 hits.
 constexpr uint32_t kLzmaAhead = 6; // positions
 
-__device__ void lzma_lookahead_warp(const lzma::Enc *e, const LzmaJob &j, const volatile int *done)
+// Warp 1.  Besides pulling the far bytes towards L1 it STAGES the lists of the coming positions in a ring in
+// shared memory (lzma_enc.cuh: kLkSlots entries), together with the byte comparison of every pair's
+// MATCH : LIT : REP0 trial (LzmaEnc.c:1876-1893), so that the encoder warp finds both without touching HBM.
+// A staged entry is a cache: the encoder checks its tag and falls back to HBM, so nothing here can change the output.
+__device__ void lzma_lookahead_warp(const lzma::Enc *e, const LzmaJob &j, const volatile int *done, uint32_t *lkTag, uint32_t *lkData)
 {
 	const uint32_t lane = threadIdx.x & 31u;
 	const volatile uint32_t *ppos = &e->pos;
 	const uint8_t *src = j.src;
-	const uint32_t n = j.n;
-	uint32_t upto = 0; // positions <= upto (1-based, like e->pos) are already prefetched
+	const uint32_t n = j.n, fb = j.cfg.fb;
+	uint32_t upto = 0; // positions <= upto (1-based, like e->pos) are already staged
 	while (!*done) {
 		const uint32_t pos = *ppos;
 		uint32_t lo = pos + 1 > upto + 1 ? pos + 1 : upto + 1;
@@ -209,13 +213,39 @@ __device__ void lzma_lookahead_warp(const lzma::Enc *e, const LzmaJob &j, const 
 			const uint64_t rec = j.rec[i0];
 			const uint32_t nd = (uint32_t)rec & 1023u;
 			const uint32_t *lst = j.pool + (rec >> 10);
+			const bool stage = nd <= lzma::kLkMaxList;
+			uint32_t *b = lkData + (q & (lzma::kLkSlots - 1)) * lzma::kLkWords;
+			const uint32_t numAvail = n - i0; // what ReadMatchDistances will see at this position
+			const uint8_t *data = src + i0;
 			for (uint32_t k = lane; 2 * k < nd; k += 32) {
 				const uint32_t len = lst[2 * k], dist = lst[2 * k + 1];
+				uint32_t w = 0;
 				if (dist < i0) {
-					const uint8_t *far = src + i0 - dist - 1;
-					lzma::lz_prefetch(far);
-					lzma::lz_prefetch(far + len + 2);
+					const uint8_t *data2 = data - dist - 1;
+					lzma::lz_prefetch(data2);
+					uint32_t len2 = len + 3, limit = len + 1 + fb;
+					if (limit > numAvail)
+						limit = numAvail;
+					if (len2 <= limit && data[len2 - 2] == data2[len2 - 2] && data[len2 - 1] == data2[len2 - 1]) {
+						while (len2 < limit && data[len2] == data2[len2])
+							len2++;
+						w = 0x80000000u | len2;
+					}
 				}
+				if (stage) {
+					b[1 + 2 * k] = len;
+					b[2 + 2 * k] = dist;
+					b[1 + lzma::kLkMaxList + k] = w;
+				}
+			}
+			__syncwarp();
+			if (stage) {
+				if (lane == 0)
+					b[0] = nd;
+				__threadfence_block();
+				__syncwarp();
+				if (lane == 0)
+					*(volatile uint32_t *)(lkTag + (q & (lzma::kLkSlots - 1))) = q;
 			}
 		}
 		upto = hi;
@@ -223,11 +253,63 @@ __device__ void lzma_lookahead_warp(const lzma::Enc *e, const LzmaJob &j, const 
 	}
 }
 
-__global__ void __launch_bounds__(96, 1) lzma_block_kernel(LzmaJob *jobs)
+// Warp 3, one thread: the range arithmetic, carries and byte output for the (probability, bit) pairs the encoder
+// warp queues (lzma_enc.cuh: rc_bit with a queue).  Same bytes as the in-line coder: the queue preserves the order
+// of the binary decisions and carries the probability each one was coded with.
+__device__ void lzma_coder_thread(lzma::Enc *e, const volatile uint32_t *q, volatile uint32_t *tailPub, volatile uint32_t *headPub,
+				  volatile int *rcDone)
+{
+	uint32_t head = 0;
+	for (;;) {
+		const uint32_t tail = *tailPub;
+		if (head == tail) {
+			__nanosleep(50);
+			continue;
+		}
+		__threadfence_block();
+		bool flush = false;
+		while (head != tail) {
+			const uint32_t op = q[head & (lzma::kRcQ - 1)];
+			head++;
+			if (op == lzma::kRcFlush) {
+				flush = true;
+				break;
+			}
+			if (op & lzma::kRcDirect) {
+				uint32_t nbits = (op >> 26) & 31u;
+				const uint32_t value = op & 0x3FFFFFFu;
+				while (nbits--) {
+					e->range >>= 1;
+					if ((value >> nbits) & 1)
+						e->low += e->range;
+					lzma::rc_norm(e);
+				}
+			} else
+				lzma::rc_bit_value(e, op >> 1, op & 1u);
+		}
+		*headPub = head;
+		if (flush) {
+			for (int i = 0; i < 5; i++) // RangeEnc_FlushData; no end marker (writeEndMark = 0)
+				lzma::rc_shift_low(e);
+			__threadfence_block();
+			*rcDone = 1;
+			return;
+		}
+	}
+}
+
+// K7b kernel: one block per CTA, four warps.  Warp 0 is the encoder (optimal parser, probability model, symbol
+// decisions: lzma_enc.cuh, replicated scalar code with lane-split loops); warp 1 looks ahead and stages match lists;
+// warp 2 runs the lz4 compressibility gate beside it; one thread of warp 3 is the range coder.
+__global__ void __launch_bounds__(128, 1) lzma_block_kernel(LzmaJob *jobs)
 {
 	extern __shared__ __align__(16) uint8_t lzma_smem[];
 	__shared__ uint32_t gate_table[4096];
-	__shared__ int done, gate_state;
+	__shared__ uint32_t rc_queue[lzma::kRcQ];
+	__shared__ uint32_t lk_data[lzma::kLkSlots * lzma::kLkWords];
+	__shared__ uint32_t lk_tag[lzma::kLkSlots];
+	__shared__ uint32_t rc_tail_pub, rc_head_pub;
+	__shared__ int done, gate_state, rc_done;
 	lzma::Enc *e = reinterpret_cast<lzma::Enc *>(lzma_smem);
 	LzmaJob &j = jobs[blockIdx.x];
 	if (*j.mf_overflow) { // uniform over the CTA: the host encodes this block again with a larger pool
@@ -235,11 +317,33 @@ __global__ void __launch_bounds__(96, 1) lzma_block_kernel(LzmaJob *jobs)
 			j.skipped = 2;
 		return;
 	}
+	if (threadIdx.x < lzma::kLkSlots)
+		lk_tag[threadIdx.x] = 0; // no position 0: positions count from 1
 	if (threadIdx.x == 0) {
 		done = 0;
 		gate_state = 0;
+		rc_done = 0;
+		rc_tail_pub = rc_head_pub = 0;
 	}
 	__syncthreads();
+	if (threadIdx.x < 32) {
+		lzma::enc_init(e, j.cfg, j.src, j.n, j.out, j.outCap, nullptr, nullptr, nullptr, nullptr);
+		e->preRec = j.rec;
+		e->prePool = j.pool;
+		e->gateState = j.threshold ? &gate_state : nullptr;
+		e->lkTag = lk_tag;
+		e->lkData = lk_data;
+		e->rcQ = rc_queue;
+		e->rcTailPub = &rc_tail_pub;
+		e->rcHeadPub = &rc_head_pub;
+		e->rcDone = &rc_done;
+	}
+	__syncthreads(); // the encoder state is initialised: the helpers may read it
+	if (threadIdx.x >= 96) {
+		if (threadIdx.x == 96)
+			lzma_coder_thread(e, rc_queue, &rc_tail_pub, &rc_head_pub, &rc_done);
+		return;
+	}
 	if (threadIdx.x >= 64) {
 		// warp 2: the lz4 compressibility gate (LZ4_TEST) of this block, beside the encoder instead of in front of
 		// it.  lz4_compresses() is a serial LZ4 emulation: one lane.  A block it rejects costs the encoder the
@@ -254,16 +358,9 @@ __global__ void __launch_bounds__(96, 1) lzma_block_kernel(LzmaJob *jobs)
 		return;
 	}
 	if (threadIdx.x >= 32) {
-		asm volatile("bar.sync 1, 64;" ::: "memory"); // warps 0 and 1: the encoder state (e->pos) is initialised
-		lzma_lookahead_warp(e, j, &done);
+		lzma_lookahead_warp(e, j, &done, lk_tag, lk_data);
 		return;
 	}
-	lzma::enc_init(e, j.cfg, j.src, j.n, j.out, j.outCap, nullptr, nullptr, nullptr, nullptr);
-	e->preRec = j.rec;
-	e->prePool = j.pool;
-	asm volatile("bar.sync 1, 64;" ::: "memory");
-	e->gateState = j.threshold ? &gate_state : nullptr;
-	__syncwarp();
 	const uint64_t len = lzma::enc_run(e);
 	__syncwarp();
 	int verdict = 1;
@@ -273,7 +370,7 @@ __global__ void __launch_bounds__(96, 1) lzma_block_kernel(LzmaJob *jobs)
 	if (threadIdx.x == 0) {
 		done = 1;
 		j.outLen = len;
-		j.overflow = e->overflow;
+		j.overflow = *(volatile int *)&e->overflow;
 		j.skipped = verdict == 2 ? 1 : 0;
 	}
 }
@@ -691,7 +788,7 @@ static int pump_groups(BackendCtx *b, bool wait, int64_t *launches, char *err, s
 			if (launches)
 				(*launches) += 2;
 		} else {
-			lzma_block_kernel<<<(unsigned)G.count, 96, sizeof(lzma::Enc), G.ps>>>((LzmaJob *)J);
+			lzma_block_kernel<<<(unsigned)G.count, 128, sizeof(lzma::Enc), G.ps>>>((LzmaJob *)J);
 			if (launches)
 				(*launches)++;
 		}

@@ -699,16 +699,6 @@ __device__ void group_eval_t(const uint8_t *__restrict__ buf, const HEntry *tab,
 	bool stop = !do_insert, done = !active;
 	int kind = -1, round = 0, neq = 0;
 	int64_t occ_off = 0, occ_tag = 0;
-	if (P > 1 && active) {
-		// Inserted tags have all gate bits set, so a chain is about 2/3 * 2^bits slots long (bits = gate bits): ask
-		// for the whole expected span now, one 128-byte line (8 slots) per prefetch, spread over the group's lanes.
-		// The first step of the walk still waits for L2; the following steps then find their windows in L1
-		// instead of paying one L2 round trip each.
-		const int bits = __popcll(tag_mask);
-		const unsigned span = bits >= 9 ? 384u : ((2u << bits) / 3u + 16u); // 32 candidates x 48 lines stay inside L1
-		for (unsigned l = (unsigned)gl; l * 8u < span; l += (unsigned)G)
-			prefetch_l1(tab + ((h + l * 8u) & hmask));
-	}
 	while (__any_sync(FULL, !done)) {
 		HEntry ew[P];
 #pragma unroll

@@ -100,6 +100,20 @@ constexpr uint32_t kHash2Size = 1u << 10, kHash3Size = 1u << 16;
 
 typedef uint16_t Prob;
 
+// ---- helpers of the device build (one CTA per block: the encoder warp plus helper warps, backend.cu) ------------
+// Staged match lists: a look-ahead warp copies the lists of the next few positions from HBM into a small ring in
+// shared memory and, for every (len, dist) pair, already does the far-byte comparison of the MATCH : LIT : REP0
+// trial.  An entry is a pure cache: the encoder uses it when its tag says it holds the position it wants and
+// falls back to HBM otherwise, so the output never depends on the helper.
+constexpr uint32_t kLkSlots = 8;                  // ring entries (positions); the helper runs at most 6 ahead
+constexpr uint32_t kLkMaxList = 128;              // uint32 of one staged list (pairs of len, dist - 1)
+constexpr uint32_t kLkWords = 1 + kLkMaxList + kLkMaxList / 2; // count, list, per pair (twoBytesEqual << 31 | end)
+// Range-coder queue: the encoder warp updates the probabilities (the next prices depend on them) and queues
+// (probability, bit) for a coder thread that does the range arithmetic, carries and byte output on its own.
+constexpr uint32_t kRcQ = 4096;                   // queue entries (power of two)
+constexpr uint32_t kRcDirect = 0x80000000u;       // entry: direct bits, nbits << 26 | value
+constexpr uint32_t kRcFlush = 0xFFFFFFFFu;        // entry: end of the block
+
 struct LenProbs {
 	Prob low[kNumPosStatesMax << 4]; // per posState: 16 probs (choice bits live in low[0], low[8])
 	Prob high[kLenHigh];
@@ -135,6 +149,14 @@ struct Enc {
 	// block stored -- the encoder gives up as soon as it reads 2 (null: no gate)
 	const int *gateState;
 	int aborted;
+	// staged match lists / range-coder queue (null on the host and in tests of the plain path)
+	const uint32_t *lkTag;  // [kLkSlots] position (1-based, as e->pos) each ring entry holds
+	const uint32_t *lkData; // [kLkSlots][kLkWords]
+	int lkSlot;             // entry the current position's list was taken from, or -1
+	uint32_t *rcQ;          // [kRcQ]
+	uint32_t rcTail;        // entries queued so far (the encoder warp's private count)
+	uint32_t *rcTailPub, *rcHeadPub; // published counts (encoder -> coder, coder -> encoder)
+	int *rcDone;
 	uint32_t pos;       // position the match finder will hand out next
 	uint32_t cycPos;
 	uint32_t crc[256];
@@ -240,8 +262,36 @@ LZ_INL void rc_norm(Enc *e)
 	}
 }
 
+#if defined(__CUDA_ARCH__)
+LZ_INL void rcq_push(Enc *e, uint32_t v)
+{
+	e->rcQ[e->rcTail & (kRcQ - 1)] = v; // every lane stores the same word
+	e->rcTail++;
+}
+// make the entries queued so far visible to the coder thread; called once per symbol
+LZ_INL void rcq_publish(Enc *e)
+{
+	__threadfence_block();
+	*(volatile uint32_t *)e->rcTailPub = e->rcTail;
+}
+// room for one more symbol (a symbol queues fewer than 64 entries)
+LZ_INL void rcq_reserve(Enc *e)
+{
+	while (e->rcTail + 64 - *(volatile uint32_t *)e->rcHeadPub > kRcQ)
+		__nanosleep(100);
+}
+#endif
+
 LZ_INL void rc_bit(Enc *e, Prob *prob, uint32_t bit)
 {
+#if defined(__CUDA_ARCH__)
+	if (e->rcQ) {
+		const uint32_t q = *prob;
+		*prob = bit ? (Prob)(q - (q >> kMoveBits)) : (Prob)(q + ((kBitModelTotal - q) >> kMoveBits));
+		rcq_push(e, (q << 1) | bit);
+		return;
+	}
+#endif
 	const uint32_t p = *prob;
 	const uint32_t bound = (e->range >> 11) * p;
 	if (bit == 0) {
@@ -255,8 +305,28 @@ LZ_INL void rc_bit(Enc *e, Prob *prob, uint32_t bit)
 	rc_norm(e);
 }
 
+// The coder thread's side of rc_bit: the probability is the value the encoder saw, its update is already done.
+LZ_INL void rc_bit_value(Enc *e, uint32_t p, uint32_t bit)
+{
+	const uint32_t bound = (e->range >> 11) * p;
+	if (bit == 0)
+		e->range = bound;
+	else {
+		e->low += bound;
+		e->range -= bound;
+	}
+	rc_norm(e);
+}
+
 LZ_INL void rc_direct(Enc *e, uint32_t value, uint32_t nbits) // most significant bit first
 {
+#if defined(__CUDA_ARCH__)
+	if (e->rcQ) {
+		if (nbits)
+			rcq_push(e, kRcDirect | (nbits << 26) | value); // nbits <= 26, value < 2^26
+		return;
+	}
+#endif
 	while (nbits--) {
 		e->range >>= 1;
 		if ((value >> nbits) & 1)
@@ -623,6 +693,24 @@ LZ_FN inline uint32_t mf_get_matches(Enc *e, uint32_t *d)
 {
 	if (e->preRec) { // the data-parallel pre-pass already produced this position's list
 		const uint32_t i0 = e->pos - 1;
+#if defined(__CUDA_ARCH__)
+		if (e->lkTag) { // staged in shared memory by the look-ahead warp?  (the same word for every lane)
+			const uint32_t slot = e->pos & (kLkSlots - 1);
+			if (*(const volatile uint32_t *)(e->lkTag + slot) == e->pos) {
+				__threadfence_block();
+				const uint32_t *b = e->lkData + slot * kLkWords;
+				const uint32_t nd = b[0];
+				lz_sync();
+				LZ_PFOR(i, nd)
+					d[i] = b[1 + i];
+				lz_sync();
+				e->lkSlot = (int)slot;
+				e->pos++;
+				return nd;
+			}
+			e->lkSlot = -1;
+		}
+#endif
 		const uint64_t rec = e->preRec[i0];
 		const uint32_t nd = (uint32_t)rec & 1023u;
 		const uint32_t *s = e->prePool + (rec >> 10);
@@ -1059,7 +1147,9 @@ LZ_FN inline uint32_t get_optimum(Enc *e, uint32_t position)
 		}
 		numAvail = numAvailFull <= fb ? numAvailFull : fb;
 		// MATCH list clipped to what is available (LzmaEnc.c:1830-1838; independent of the REP section)
+		bool clipped = false;
 		if (numAvailFull >= 2 && newLen > numAvail) {
+			clipped = true;
 			newLen = numAvail;
 			for (numPairs = 0; newLen > matches[numPairs]; numPairs += 2) {
 			}
@@ -1076,15 +1166,28 @@ LZ_FN inline uint32_t get_optimum(Enc *e, uint32_t position)
 			} else {
 				// MATCH : LIT : REP_0 reach of pair k (LzmaEnc.c:1876-1893)
 				const uint32_t k = q - kNumReps, len = matches[2 * k];
-				const uint8_t *data2 = data - matches[2 * k + 1] - 1;
 				uint32_t len2 = len + 1, limit = len2 + fb, res = 0;
 				if (limit > numAvailFull)
 					limit = numAvailFull;
 				len2 += 2;
-				if (len2 <= limit && data[len2 - 2] == data2[len2 - 2] && data[len2 - 1] == data2[len2 - 1]) {
-					while (len2 < limit && data[len2] == data2[len2])
-						len2++;
-					res = len2 - len;
+#if defined(__CUDA_ARCH__)
+				if (e->lkSlot >= 0 && !clipped) {
+					// the look-ahead warp compared the bytes already, up to min(len + 1 + fb, numAvail): its end,
+					// cut at this position's own limit, is where the loop below would stop
+					const uint32_t w = e->lkData[(uint32_t)e->lkSlot * kLkWords + 1 + kLkMaxList + k];
+					if ((w >> 31) && len2 <= limit) {
+						const uint32_t end = (w & 0x7FFFFFFFu) < limit ? (w & 0x7FFFFFFFu) : limit;
+						res = end - len;
+					}
+				} else
+#endif
+				{
+					const uint8_t *data2 = data - matches[2 * k + 1] - 1;
+					if (len2 <= limit && data[len2 - 2] == data2[len2 - 2] && data[len2 - 1] == data2[len2 - 1]) {
+						while (len2 < limit && data[len2] == data2[len2])
+							len2++;
+						res = len2 - len;
+					}
 				}
 				e->xPairLen2[k] = res;
 			}
@@ -1418,6 +1521,13 @@ LZ_FN inline void enc_init(Enc *e, const Config &c, const uint8_t *src, uint32_t
 	e->prePool = nullptr;
 	e->gateState = nullptr;
 	e->aborted = 0;
+	e->lkTag = nullptr;
+	e->lkData = nullptr;
+	e->lkSlot = -1;
+	e->rcQ = nullptr;
+	e->rcTail = 0;
+	e->rcTailPub = e->rcHeadPub = nullptr;
+	e->rcDone = nullptr;
 	e->hash2 = hash2;
 	e->hash3 = hash3;
 	e->hash4 = hash4;
@@ -1527,6 +1637,10 @@ LZ_FN inline uint64_t enc_run(Enc *e)
 			const uint32_t posState = nowPos & e->pbMask;
 			uint32_t dist = e->backRes;
 			Prob *pm = &e->isMatch[e->state][posState];
+#if defined(__CUDA_ARCH__)
+			if (e->rcQ)
+				rcq_reserve(e);
+#endif
 			if (dist == kMarkLit) {
 				rc_bit(e, pm, 0);
 				const uint8_t *data = mf_cur(e) - e->additionalOffset;
@@ -1603,6 +1717,10 @@ LZ_FN inline uint64_t enc_run(Enc *e)
 					}
 				}
 			}
+#if defined(__CUDA_ARCH__)
+			if (e->rcQ)
+				rcq_publish(e);
+#endif
 			nowPos += len;
 			e->additionalOffset -= len;
 			if (e->additionalOffset == 0) {
@@ -1624,6 +1742,17 @@ LZ_FN inline uint64_t enc_run(Enc *e)
 			}
 		}
 	}
+#if defined(__CUDA_ARCH__)
+	if (e->rcQ) { // the coder thread flushes (RangeEnc_FlushData) and reports the length
+		rcq_reserve(e);
+		rcq_push(e, kRcFlush);
+		rcq_publish(e);
+		while (*(volatile int *)e->rcDone == 0)
+			__nanosleep(200);
+		__threadfence_block();
+		return *(volatile uint64_t *)&e->outPos;
+	}
+#endif
 	for (int i = 0; i < 5; i++) // RangeEnc_FlushData; no end marker (writeEndMark = 0)
 		rc_shift_low(e);
 	return e->outPos;
