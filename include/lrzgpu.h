@@ -15,6 +15,7 @@
  *                                       splits it at the point where rzip_chunk returns
  *   lrzgpu_chunk_begin_all / _select    the same window for every value of insert_hash()'s static victim_round
  *                                       (src/rzip.c:308), so that windows need not wait for their predecessor
+ *   lrzgpu_decompress                   runzip_fd()          src/runzip.c:372 (the inverse path, 8(f1))
  *   lrzgpu_rzip_chunk                   hash_search()        src/rzip.c:586 with the scan primitives
  *                                       full_tag/next_tag/match_len, lrzip_private.h:573-576
  *   lrzgpu_tag_scan                     single_full_tag()/single_next_tag()  src/rzip.c:385-416
@@ -154,6 +155,13 @@ int lrzgpu_victim_values(const lrzgpu_params *p);
 int lrzgpu_chunk_begin_all(lrzgpu_ctx *ctx, const lrzgpu_params *p, const lrzgpu_sizing_t *sz, const uint8_t *in, int64_t n,
 			   int eof, int64_t *victim_out, int nvalues, lrzgpu_stats *stats);
 int lrzgpu_chunk_select(lrzgpu_ctx *ctx, int64_t victim_in, lrzgpu_stats *stats);
+
+/* Decode (runzip_fd / runzip_chunk, src/runzip.c:261-470; block chains src/stream.c:1883-2016): a whole archive in
+ * host memory -> the original bytes (malloc'ed).  Container walk on the host; LZMA blocks (lzma_decompress_buf,
+ * src/stream.c:556-616) decoded on the device, one thread per block; stream 0 parsed into records and replayed on
+ * the device (literals scattered by all SMs, matches in order); chunk CRC-32 and the trailing MD5 are verified.
+ * Stored and LZMA blocks only (zstd and the other back ends: LRZGPU_EUNSUPPORTED); no encryption, no filters. */
+int lrzgpu_decompress(lrzgpu_ctx *ctx, const uint8_t *archive, int64_t archive_len, uint8_t **out, int64_t *out_len);
 
 /* rzip of one chunk -> stream 0 / stream 1 bytes (malloc'ed). */
 int lrzgpu_rzip_chunk(lrzgpu_ctx *ctx, const uint8_t *in, int64_t n, int rzip_level, int chunk_bytes,

@@ -70,7 +70,7 @@ EXPORTS = [
     "lrzgpu_create", "lrzgpu_destroy", "lrzgpu_last_error", "lrzgpu_free", "lrzgpu_version", "lrzgpu_sizing",
     "lrzgpu_compress", "lrzgpu_compress_file", "lrzgpu_compress_device", "lrzgpu_compress_multi", "lrzgpu_compress_chunk",
     "lrzgpu_chunk_begin", "lrzgpu_chunk_finish", "lrzgpu_victim_values", "lrzgpu_chunk_begin_all", "lrzgpu_chunk_select",
-    "lrzgpu_rzip_chunk", "lrzgpu_tag_scan", "lrzgpu_crc32", "lrzgpu_block_compress", "lrzgpu_lz4_gate",
+    "lrzgpu_decompress", "lrzgpu_rzip_chunk", "lrzgpu_tag_scan", "lrzgpu_crc32", "lrzgpu_block_compress", "lrzgpu_lz4_gate",
     "lrzgpu_k1_launch", "lrzgpu_crc32_launch", "lrzgpu_sm_count",
 ]
 
@@ -109,6 +109,7 @@ def load_library():
     L.lrzgpu_chunk_begin_all.argtypes = [vp, C.POINTER(Params), C.POINTER(Sizing), vp, i64, C.c_int, pi64, C.c_int,
                                          C.POINTER(Stats)]
     L.lrzgpu_chunk_select.argtypes = [vp, i64, C.POINTER(Stats)]
+    L.lrzgpu_decompress.argtypes = [vp, vp, i64, pvp, pi64]
     L.lrzgpu_rzip_chunk.argtypes = [vp, vp, i64, C.c_int, C.c_int, pi64, pvp, pi64, pvp, pi64, C.POINTER(Stats)]
     L.lrzgpu_tag_scan.argtypes = [vp, vp, i64, i64, i64, i64, vp, vp, i64, pi64]
     L.lrzgpu_crc32.argtypes = [vp, vp, i64, C.POINTER(C.c_uint32)]
@@ -236,6 +237,13 @@ class Context:
 
     def free(self, p):
         self._L.lrzgpu_free(p)
+
+    def decompress(self, archive) -> bytes:
+        """runzip_fd on the device: archive bytes -> original bytes (CRC and MD5 verified)."""
+        addr, n, keep = _ptr(archive)
+        out, ol = C.c_void_p(), C.c_int64()
+        self._check(self._L.lrzgpu_decompress(self._h, addr, n, C.byref(out), C.byref(ol)))
+        return self._take(out, ol.value)
 
     def compress_file(self, src: str, dst: str, params: Params) -> dict:
         st = Stats()

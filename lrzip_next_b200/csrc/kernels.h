@@ -43,4 +43,35 @@ int k4_literals_launch(const uint8_t *d_buf, const MatchRec *d_recs, int64_t n_r
 int k4_flush_order_launch(const MatchRec *d_recs, int64_t n_rec, int chunk_bytes, int64_t bufsize,
 			  int64_t n_bounds, int64_t *d_w1, cudaStream_t stream);
 
+// ---- decode side (unrzip.cu) -------------------------------------------------------
+struct DecLit {   // one literal record of stream 0: `len` bytes of stream 1 from lit_off go to out_off
+	int64_t out_off, lit_off, len;
+};
+struct DecMatch { // one match record: `len` bytes copied from `dist` back
+	int64_t out_off, len, dist;
+};
+struct DecSummary {
+	int64_t n_lit, n_match, out_len, lit_len;
+	uint32_t crc; // the chunk CRC stored behind the terminator
+	int32_t status; // 0 ok, < 0 malformed stream
+};
+struct LzmaDecJob {
+	const uint8_t *src;
+	int64_t c_len;
+	uint8_t *out;
+	int64_t u_len;
+	int64_t produced;
+	int32_t status;
+	int32_t pad;
+};
+// stream 0 -> literal / match records with their output offsets (one thread: a running sum over 3..3+cb byte records)
+int unrzip_parse_launch(const uint8_t *d_s0, int64_t s0_len, int cb, int64_t chunk_size, DecLit *d_lits, DecMatch *d_matches,
+			int64_t cap, DecSummary *d_sum, cudaStream_t stream);
+// literals scattered by all SMs, then the matches in record order by one CTA
+int unrzip_replay_launch(const uint8_t *d_s1, int64_t s1_len, const DecLit *d_lits, int64_t n_lit, const DecMatch *d_matches,
+			 int64_t n_match, uint8_t *d_out, int num_sms, cudaStream_t stream);
+size_t lzma_dec_prob_bytes(int njobs);
+int lzma_dec_launch(LzmaDecJob *d_jobs, int njobs, void *d_probs, cudaStream_t stream);
+int unrzip_preload();
+
 } // namespace lrz

@@ -688,7 +688,7 @@ int lrzgpu_create(int device, lrzgpu_ctx **out)
 	if (ok)
 		c->h_state_cap = 1;
 	ok = ok && k1_init_tables() == 0 && k4_init_tables() == 0;
-	ok = ok && k1_preload() == 0 && k2_preload() == 0 && k4_preload() == 0 && backend_preload() == 0;
+	ok = ok && k1_preload() == 0 && k2_preload() == 0 && k4_preload() == 0 && backend_preload() == 0 && unrzip_preload() == 0;
 	if (ok) {
 		c->backend = backend_create();
 		ok = c->backend != nullptr;
@@ -1382,6 +1382,176 @@ int lrzgpu_compress_multi(lrzgpu_ctx **ctxs, int nctx, const lrzgpu_params *p, c
 	}
 	for (Win &w : wins)
 		free(w.blob);
+	return rc;
+}
+
+// ---- decode: runzip_fd / runzip_chunk, src/runzip.c:261-470, on the device ---------------
+namespace {
+int64_t get_le(const uint8_t *p, int width)
+{
+	int64_t v = 0;
+	for (int i = 0; i < width; i++)
+		v |= (int64_t)p[i] << (8 * i);
+	return v;
+}
+struct ArcBlock {
+	int stream, ctype;
+	int64_t c_len, u_len, payload; // payload: offset in the archive
+};
+} // namespace
+
+int lrzgpu_decompress(lrzgpu_ctx *c, const uint8_t *arc, int64_t arc_len, uint8_t **out, int64_t *out_len)
+{
+	if (!c || !arc || !out || !out_len)
+		return LRZGPU_EINVAL;
+	cudaSetDevice(c->device);
+	// magic header, src/lrzip.c:131-208 (written) / 227-330 (read)
+	if (arc_len < 21 + 16 || memcmp(arc, "LRZI", 4) || arc[4] != 0)
+		return fail(c, LRZGPU_EINVAL, "not an lrzip-next archive");
+	if (arc[15] != 0 || arc[16] != 0)
+		return fail(c, LRZGPU_EUNSUPPORTED, "encrypted or filtered archives are not supported");
+	if (arc[14] != 1)
+		return fail(c, LRZGPU_EUNSUPPORTED, "only MD5 archives are supported (hash code %d)", arc[14]);
+	const int64_t st_size = get_le(arc + 6, 8);
+	int64_t pos = 21 + arc[20];
+	const int64_t end = arc_len - 16;
+	uint8_t *res = (uint8_t *)malloc((size_t)(st_size > 0 ? st_size : 1));
+	if (!res)
+		return fail(c, LRZGPU_ENOMEM, "out of host memory");
+	struct Guard { // every error path below returns through the CU macro or bail(): the buffer goes with it
+		uint8_t *p;
+		~Guard() { free(p); }
+	} guard{ res };
+	int64_t done = 0;
+	int rc = LRZGPU_OK;
+	auto bail = [&](int code, const char *msg) { return fail(c, code, "%s", msg); };
+	for (bool last = false; !last;) {
+		if (pos + 2 > end)
+			return bail(LRZGPU_EINVAL, "truncated archive (chunk header)");
+		const int cb = arc[pos], eof = arc[pos + 1];
+		if (cb < 1 || cb > 8 || pos + 2 + cb + 2 * (1 + 3 * cb) > end)
+			return bail(LRZGPU_EINVAL, "bad chunk header");
+		pos += 2 + cb; // the stored chunk size is not needed: the terminator ends the chunk
+		const int64_t initial = pos, hdr = 1 + 3 * cb;
+		std::vector<ArcBlock> blocks;
+		int64_t chunk_end = initial + 2 * hdr, total_u[2] = { 0, 0 };
+		for (int s = 0; s < 2; s++) { // follow the stream's chain of block headers (src/stream.c:1883-2016)
+			int64_t head = get_le(arc + initial + s * hdr + 1 + 2 * cb, cb);
+			while (head) {
+				const int64_t at = initial + head;
+				if (at < initial || at + hdr > end)
+					return bail(LRZGPU_EINVAL, "block header outside the archive");
+				ArcBlock b;
+				b.stream = s;
+				b.ctype = arc[at];
+				b.c_len = get_le(arc + at + 1, cb);
+				b.u_len = get_le(arc + at + 1 + cb, cb);
+				b.payload = at + hdr;
+				if (b.c_len < 0 || b.u_len < 0 || b.payload + b.c_len > end)
+					return bail(LRZGPU_EINVAL, "block payload outside the archive");
+				if (b.ctype != LRZGPU_CTYPE_NONE && b.ctype != LRZGPU_CTYPE_LZMA)
+					return bail(LRZGPU_EUNSUPPORTED, "only stored and LZMA blocks can be decoded on the device");
+				blocks.push_back(b);
+				total_u[s] += b.u_len;
+				if (b.payload + b.c_len > chunk_end)
+					chunk_end = b.payload + b.c_len;
+				head = get_le(arc + at + 1 + 2 * cb, cb);
+			}
+		}
+		// stream bytes on the device: stored blocks are copied in place, LZMA blocks decoded there
+		CU(c, c->s0.ensure((size_t)total_u[0] + 64));
+		CU(c, c->s1.ensure((size_t)total_u[1] + 64));
+		int64_t comp_bytes = 0;
+		std::vector<LzmaDecJob> jobs;
+		for (const ArcBlock &b : blocks)
+			if (b.ctype == LRZGPU_CTYPE_LZMA)
+				comp_bytes += (b.c_len + 15) & ~(int64_t)15;
+		CU(c, c->in.ensure((size_t)comp_bytes + 64));
+		int64_t so[2] = { 0, 0 }, co = 0;
+		for (const ArcBlock &b : blocks) {
+			uint8_t *dst = (uint8_t *)(b.stream ? c->s1.p : c->s0.p) + so[b.stream];
+			if (b.ctype == LRZGPU_CTYPE_NONE) {
+				if (b.c_len != b.u_len)
+					return bail(LRZGPU_EINVAL, "stored block with c_len != u_len");
+				if (b.u_len)
+					CU(c, cudaMemcpyAsync(dst, arc + b.payload, (size_t)b.u_len, cudaMemcpyHostToDevice, c->sA));
+			} else {
+				uint8_t *src = (uint8_t *)c->in.p + co;
+				CU(c, cudaMemcpyAsync(src, arc + b.payload, (size_t)b.c_len, cudaMemcpyHostToDevice, c->sA));
+				LzmaDecJob j;
+				memset(&j, 0, sizeof(j));
+				j.src = src;
+				j.c_len = b.c_len;
+				j.out = dst;
+				j.u_len = b.u_len;
+				jobs.push_back(j);
+				co += (b.c_len + 15) & ~(int64_t)15;
+			}
+			so[b.stream] += b.u_len;
+		}
+		if (!jobs.empty()) {
+			const size_t jb = jobs.size() * sizeof(LzmaDecJob);
+			CU(c, c->w1.ensure(jb));
+			CU(c, c->tab.ensure(lzma_dec_prob_bytes((int)jobs.size())));
+			CU(c, cudaMemcpyAsync(c->w1.p, jobs.data(), jb, cudaMemcpyHostToDevice, c->sA));
+			if (lzma_dec_launch((LzmaDecJob *)c->w1.p, (int)jobs.size(), c->tab.p, c->sA))
+				return bail(LRZGPU_ECUDA, "LZMA decoder launch failed");
+			c->launches++;
+			CU(c, cudaMemcpyAsync(jobs.data(), c->w1.p, jb, cudaMemcpyDeviceToHost, c->sA));
+			CU(c, cudaStreamSynchronize(c->sA));
+			for (const LzmaDecJob &j : jobs)
+				if (j.status || j.produced != j.u_len)
+					return bail(LRZGPU_EINVAL, "corrupt LZMA block");
+		}
+		// stream 0 -> records, then the replay into the chunk's bytes
+		const int64_t cap = total_u[0] / 3 + 2;
+		CU(c, c->recs.ensure((size_t)cap * (sizeof(DecLit) + sizeof(DecMatch)) + sizeof(DecSummary) + 64));
+		DecLit *d_lits = (DecLit *)c->recs.p;
+		DecMatch *d_matches = (DecMatch *)(d_lits + cap);
+		DecSummary *d_sum = (DecSummary *)(d_matches + cap);
+		const int64_t room = st_size - done;
+		if (unrzip_parse_launch((const uint8_t *)c->s0.p, total_u[0], cb, room, d_lits, d_matches, cap, d_sum, c->sA))
+			return bail(LRZGPU_ECUDA, "stream parse launch failed");
+		DecSummary sum;
+		CU(c, cudaMemcpyAsync(&sum, d_sum, sizeof(sum), cudaMemcpyDeviceToHost, c->sA));
+		CU(c, cudaStreamSynchronize(c->sA));
+		c->launches++;
+		if (sum.status || sum.lit_len != total_u[1] || sum.out_len > room)
+			return bail(LRZGPU_EINVAL, "corrupt rzip stream");
+		CU(c, c->cand[0].ensure((size_t)sum.out_len + kFrontPad + kInputPad));
+		uint8_t *d_out = (uint8_t *)c->cand[0].p + kFrontPad;
+		if (unrzip_replay_launch((const uint8_t *)c->s1.p, total_u[1], d_lits, sum.n_lit, d_matches, sum.n_match, d_out, c->sms, c->sA))
+			return bail(LRZGPU_ECUDA, "replay launch failed");
+		c->launches += 2;
+		// the chunk's CRC-32 (src/runzip.c:346-357)
+		CU(c, c->crc.ensure(16));
+		uint32_t crc_acc = 0;
+		if (sum.out_len > 0) {
+			if (crc32_launch(d_out, sum.out_len, (uint32_t *)c->crc.p, c->sms, c->sA))
+				return bail(LRZGPU_ECUDA, "crc32 launch failed");
+			c->launches++;
+			CU(c, cudaMemcpyAsync(&crc_acc, c->crc.p, 4, cudaMemcpyDeviceToHost, c->sA));
+		}
+		if (sum.out_len)
+			CU(c, cudaMemcpyAsync(res + done, d_out, (size_t)sum.out_len, cudaMemcpyDeviceToHost, c->sA));
+		CU(c, cudaStreamSynchronize(c->sA));
+		if (sum.out_len > 0 && (crc_acc ^ 0xffffffffu) != sum.crc)
+			return bail(LRZGPU_EINVAL, "chunk CRC mismatch");
+		done += sum.out_len;
+		pos = chunk_end;
+		last = eof != 0;
+	}
+	if (done != st_size || pos != end)
+		return bail(LRZGPU_EINVAL, "archive size does not match its header");
+	uint8_t md5[16];
+	Md5 m;
+	m.update(res, (size_t)done);
+	m.final(md5);
+	if (memcmp(md5, arc + end, 16))
+		return bail(LRZGPU_EINVAL, "MD5 mismatch");
+	guard.p = nullptr;
+	*out = res;
+	*out_len = done;
 	return rc;
 }
 
