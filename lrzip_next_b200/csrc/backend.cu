@@ -195,7 +195,7 @@ constexpr uint32_t kLzmaAhead = 6; // positions
 // A staged entry is a cache: the encoder checks its tag and falls back to HBM, so nothing here can change the output.
 __device__ void lzma_lookahead_warp(const lzma::Enc *e, const LzmaJob &j, const volatile int *done, uint32_t *lkTag, uint32_t *lkData)
 {
-	const uint32_t lane = threadIdx.x & 31u;
+	const uint32_t lane = threadIdx.x & 31u, grp = lane >> 3, sub = lane & 7u;
 	const volatile uint32_t *ppos = &e->pos;
 	const uint8_t *src = j.src;
 	const uint32_t n = j.n, fb = j.cfg.fb;
@@ -205,10 +205,14 @@ __device__ void lzma_lookahead_warp(const lzma::Enc *e, const LzmaJob &j, const 
 		uint32_t lo = pos + 1 > upto + 1 ? pos + 1 : upto + 1;
 		uint32_t hi = pos + kLzmaAhead < n ? pos + kLzmaAhead : n;
 		if (lo > hi) {
-			__nanosleep(200);
+			__nanosleep(100);
 			continue;
 		}
-		for (uint32_t q = lo; q <= hi; q++) {
+		if (hi > lo + 3)
+			hi = lo + 3;
+		// four positions in flight, eight lanes each: the dependent far loads (record -> list -> bytes) of the four overlap
+		const uint32_t q = lo + grp;
+		if (q <= hi) {
 			const uint32_t i0 = q - 1;
 			const uint64_t rec = j.rec[i0];
 			const uint32_t nd = (uint32_t)rec & 1023u;
@@ -217,7 +221,7 @@ __device__ void lzma_lookahead_warp(const lzma::Enc *e, const LzmaJob &j, const 
 			uint32_t *b = lkData + (q & (lzma::kLkSlots - 1)) * lzma::kLkWords;
 			const uint32_t numAvail = n - i0; // what ReadMatchDistances will see at this position
 			const uint8_t *data = src + i0;
-			for (uint32_t k = lane; 2 * k < nd; k += 32) {
+			for (uint32_t k = sub; 2 * k < nd; k += 8) {
 				const uint32_t len = lst[2 * k], dist = lst[2 * k + 1];
 				uint32_t w = 0;
 				if (dist < i0) {
@@ -236,17 +240,22 @@ __device__ void lzma_lookahead_warp(const lzma::Enc *e, const LzmaJob &j, const 
 					b[1 + 2 * k] = len;
 					b[2 + 2 * k] = dist;
 					b[1 + lzma::kLkMaxList + k] = w;
+					// distance by length: this pair serves the lengths above the previous pair's up to its own
+					uint32_t from = k ? lst[2 * k - 2] + 1 : 2;
+					for (; from <= len && from <= lzma::kMatchMax; from++)
+						b[lzma::kLkByLen + from] = dist;
 				}
 			}
-			__syncwarp();
-			if (stage) {
-				if (lane == 0)
-					b[0] = nd;
-				__threadfence_block();
-				__syncwarp();
-				if (lane == 0)
-					*(volatile uint32_t *)(lkTag + (q & (lzma::kLkSlots - 1))) = q;
-			}
+			if (stage && sub == 0)
+				b[0] = nd | ((nd ? lst[nd - 2] : 0u) << 16); // count, and the longest length (ReadMatchDistances' result)
+		}
+		__syncwarp();
+		__threadfence_block();
+		__syncwarp();
+		if (q <= hi && sub == 0) {
+			const uint32_t nd = (uint32_t)j.rec[q - 1] & 1023u;
+			if (nd <= lzma::kLkMaxList)
+				*(volatile uint32_t *)(lkTag + (q & (lzma::kLkSlots - 1))) = q;
 		}
 		upto = hi;
 		__syncwarp();
@@ -361,8 +370,27 @@ __global__ void __launch_bounds__(128, 1) lzma_block_kernel(LzmaJob *jobs)
 		lzma_lookahead_warp(e, j, &done, lk_tag, lk_data);
 		return;
 	}
+#if defined(LZ_PROF)
+	for (int i = 0; i < 24; i++)
+		e->prof[i] = e->profN[i] = 0;
+	e->profT = clock64();
+	const long long prof_t0 = e->profT;
+#endif
 	const uint64_t len = lzma::enc_run(e);
 	__syncwarp();
+#if defined(LZ_PROF)
+	if (threadIdx.x == 0) {
+		const long long tot = clock64() - prof_t0;
+		printf("[lzprof] n=%u total=%lld cyc (%.0f / byte)\n", j.n, tot, (double)tot / j.n);
+		for (int i = 0; i < 14; i++)
+			printf("[lzprof] s%-2d %6.2f%%  %12llu cyc  %10llu calls  %8.0f cyc/call\n", i, 100.0 * e->prof[i] / tot,
+			       (unsigned long long)e->prof[i], (unsigned long long)e->profN[i],
+			       e->profN[i] ? (double)e->prof[i] / e->profN[i] : 0.0);
+		printf("[lzprof] staged steps %llu, staged but not eligible %llu, not staged %llu, pos mismatch %llu\n",
+		       (unsigned long long)e->profN[14], (unsigned long long)e->profN[15], (unsigned long long)e->profN[16],
+		       (unsigned long long)e->profN[20]);
+	}
+#endif
 	int verdict = 1;
 	if (j.threshold) // a block shorter than the gate's run time: wait for the verdict
 		while ((verdict = *(volatile int *)&gate_state) == 0)

@@ -54,6 +54,14 @@ LZ_INL void lz_sync() { __syncwarp(); }
 LZ_INL uint32_t lz_ballot(bool p) { return __ballot_sync(0xffffffffu, p); }
 LZ_INL uint32_t lz_ffs(uint32_t m) { return (uint32_t)__ffs((int)m); }
 LZ_INL void lz_prefetch(const void *p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+LZ_INL uint32_t lz_ld_acquire(const uint32_t *p) // pairs with the helper warp's fence + tag store
+{
+	uint32_t v;
+	asm volatile("ld.acquire.cta.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+	return v;
+}
+LZ_INL uint32_t lz_shfl(uint32_t v, uint32_t src) { return __shfl_sync(0xffffffffu, v, (int)src); }
+LZ_INL uint32_t lz_sum(uint32_t v) { return __reduce_add_sync(0xffffffffu, v); }
 #else
 #define LZ_W 1u
 LZ_INL uint32_t lz_lane() { return 0; }
@@ -63,6 +71,12 @@ LZ_INL uint32_t lz_ffs(uint32_t m) { return m ? (uint32_t)__builtin_ffs((int)m) 
 LZ_INL void lz_prefetch(const void *) {}
 #endif
 #define LZ_PFOR(i, n) for (uint32_t i = lz_lane(); i < (uint32_t)(n); i += LZ_W)
+// Development aid (-DLZ_PROF): cycles of the encoder warp per section, printed at the end of the block.
+#if defined(LZ_PROF) && defined(__CUDA_ARCH__)
+#define LZ_T(i) do { const long long t_ = clock64(); e->prof[i] += (uint64_t)(t_ - e->profT); e->profN[i]++; e->profT = t_; } while (0)
+#else
+#define LZ_T(i) do { } while (0)
+#endif
 
 // First index in [from, limit] at which a and b differ (limit if they agree up to there); from <= limit.
 LZ_FN inline uint32_t lz_extend(const uint8_t *a, const uint8_t *b, uint32_t from, uint32_t limit)
@@ -107,7 +121,8 @@ typedef uint16_t Prob;
 // falls back to HBM otherwise, so the output never depends on the helper.
 constexpr uint32_t kLkSlots = 8;                  // ring entries (positions); the helper runs at most 6 ahead
 constexpr uint32_t kLkMaxList = 128;              // uint32 of one staged list (pairs of len, dist - 1)
-constexpr uint32_t kLkWords = 1 + kLkMaxList + kLkMaxList / 2; // count, list, per pair (twoBytesEqual << 31 | end)
+constexpr uint32_t kLkByLen = 1 + kLkMaxList + kLkMaxList / 2; // offset of the distance-by-length table (indexed by length)
+constexpr uint32_t kLkWords = kLkByLen + kMatchMax + 1; // count | longest << 16, list, per pair (twoBytesEqual << 31 | end), table
 // Range-coder queue: the encoder warp updates the probabilities (the next prices depend on them) and queues
 // (probability, bit) for a coder thread that does the range arithmetic, carries and byte output on its own.
 constexpr uint32_t kRcQ = 4096;                   // queue entries (power of two)
@@ -124,7 +139,7 @@ struct LenPrices {
 	uint32_t prices[kNumPosStatesMax][kLenTotal];
 };
 
-struct Opt {
+struct alignas(16) Opt {
 	uint32_t price;
 	uint16_t state;
 	uint16_t extra; // 0 normal, 1 LIT : MATCH, >1 MATCH(extra-1) : LIT : REP0(len)
@@ -190,6 +205,10 @@ struct Enc {
 	uint32_t xLit[8];
 	uint32_t xRepLen[kNumReps], xRepLen2[kNumReps];
 	uint32_t xPairLen2[kMatchMax + 2], xPairPrice[kMatchMax + 2];
+#if defined(LZ_PROF)
+	uint64_t prof[24], profN[24];
+	long long profT;
+#endif
 };
 
 // ---------------------------------------------------------------------------------------------------
@@ -699,7 +718,7 @@ LZ_FN inline uint32_t mf_get_matches(Enc *e, uint32_t *d)
 			if (*(const volatile uint32_t *)(e->lkTag + slot) == e->pos) {
 				__threadfence_block();
 				const uint32_t *b = e->lkData + slot * kLkWords;
-				const uint32_t nd = b[0];
+				const uint32_t nd = b[0] & 0xFFFFu; // the length of the last pair sits above
 				lz_sync();
 				LZ_PFOR(i, nd)
 					d[i] = b[1 + i];
@@ -943,6 +962,283 @@ LZ_FN inline void opt_match_cells(Enc *e, uint32_t base, uint32_t startLen, uint
 	lz_sync();
 }
 
+
+#if defined(__CUDA_ARCH__)
+LZ_INL void opt_set4(Opt *o, uint32_t price, uint32_t len, uint32_t dist, uint32_t extra)
+{
+	// one 16-byte store; the cell's state is rewritten when the parse reaches the cell, before anything reads it
+	*reinterpret_cast<uint4 *>(o) = make_uint4(price, extra << 16, len, dist);
+}
+
+// One position of GetOptimum's main loop (LzmaEnc.c:1545-1949) for the common case, written for the warp instead of
+// replicated: the position's match list, its distance-by-length table and the MATCH : LIT : REP_0 reaches are staged
+// in shared memory by the look-ahead warp (b), nothing is clipped (numAvailFull >= fb, longest match < fb) and there
+// are at most 32 pairs.  Lane k owns pair k; four groups of eight lanes compare the first eight bytes of the four
+// reps; lanes 0-7 price the literal's eight decisions; the cells a match reaches are spread over the lanes.  Same
+// decisions, same order of updates per cell as the loop below (which remains the general path and the host build).
+__device__ __forceinline__ void opt_step_staged(Enc *e, const uint32_t *b, uint32_t hdr, uint32_t pos, uint32_t numAvailFull,
+						uint32_t cur, uint32_t &last, uint32_t &position, uint32_t *reps,
+						const uint8_t *srcAll, uint32_t pbMask, uint32_t fb)
+{
+	const uint32_t lane = lz_lane(), grp = lane >> 3, sub = lane & 7u;
+	const uint32_t nd = hdr & 0xFFFFu, newLen = hdr >> 16, np = nd >> 1;
+	const uint8_t *data = srcAll + (pos - 1);
+	// ---- everything that does not depend on the parse table is requested first
+	uint32_t pLen = 0, pDist = 0, pW = 0;
+	if (lane < np) {
+		pLen = b[1 + 2 * lane];
+		pDist = b[2 + 2 * lane];
+		pW = b[1 + kLkMaxList + lane];
+	}
+	const uint32_t dSub = data[sub], prevByte = *(data - 1);
+	Opt *curOpt = &e->opt[cur], *nextOpt = curOpt + 1;
+	const uint4 c0 = *reinterpret_cast<const uint4 *>(curOpt); // price, state | extra << 16, len, dist
+	const uint4 n0 = *reinterpret_cast<const uint4 *>(nextOpt);
+	// what ReadMatchDistances leaves behind
+	e->additionalOffset++;
+	e->numAvail = e->n - (pos - 1);
+	e->pos = pos + 1;
+	LZ_T(2);
+	position++;
+	const uint32_t curPrice = c0.x, curLen = c0.z, curDist = c0.w, curExtra = c0.y >> 16;
+	uint32_t prev = cur - curLen, state;
+	if (curLen == 1) {
+		state = e->opt[prev].state;
+		state = curDist == 0 ? st_shortrep(state) : st_lit(state);
+	} else {
+		if (curExtra) {
+			prev -= curExtra;
+			state = 8;
+			if (curExtra == 1)
+				state = curDist < kNumReps ? 8 : 7;
+		} else {
+			state = e->opt[prev].state;
+			state = curDist < kNumReps ? st_rep(state) : st_match(state);
+		}
+		const uint4 pr = *reinterpret_cast<const uint4 *>(e->opt[prev].reps);
+		if (curDist < kNumReps) {
+			if (curDist == 0) {
+				reps[0] = pr.x;
+				reps[1] = pr.y;
+				reps[2] = pr.z;
+				reps[3] = pr.w;
+			} else if (curDist == 1) {
+				reps[0] = pr.y;
+				reps[1] = pr.x;
+				reps[2] = pr.z;
+				reps[3] = pr.w;
+			} else if (curDist == 2) {
+				reps[0] = pr.z;
+				reps[1] = pr.x;
+				reps[2] = pr.y;
+				reps[3] = pr.w;
+			} else {
+				reps[0] = pr.w;
+				reps[1] = pr.x;
+				reps[2] = pr.y;
+				reps[3] = pr.z;
+			}
+		} else {
+			reps[0] = curDist - kNumReps + 1;
+			reps[1] = pr.x;
+			reps[2] = pr.y;
+			reps[3] = pr.z;
+		}
+	}
+	curOpt->state = (uint16_t)state;
+	*reinterpret_cast<uint4 *>(curOpt->reps) = make_uint4(reps[0], reps[1], reps[2], reps[3]);
+	LZ_T(3);
+
+	// ---- bytes from far back, all in flight at once: group g compares the first eight bytes of rep g
+	uint32_t myRep = reps[0];
+	myRep = grp == 1 ? reps[1] : myRep;
+	myRep = grp == 2 ? reps[2] : myRep;
+	myRep = grp == 3 ? reps[3] : myRep;
+	const uint32_t rSub = (data - myRep)[sub];
+	const uint32_t eq = lz_ballot(rSub == dSub); // bit 8 g + i: byte i of rep g equals byte i here
+	const uint32_t curByte = lz_shfl(dSub, 0), matchByte = lz_shfl(rSub, 0);
+	uint32_t repMask = 0;
+	for (uint32_t q = 0; q < kNumReps; q++)
+		repMask |= ((eq >> (8 * q)) & 3u) == 3u ? 1u << q : 0u;
+	// MATCH : LIT : REP_0 reach of my pair (LzmaEnc.c:1876-1893), from the helper's byte comparison
+	uint32_t pL2 = 0;
+	if (lane < np) {
+		uint32_t limit = pLen + 1 + fb;
+		if (limit > numAvailFull)
+			limit = numAvailFull;
+		if ((pW >> 31) && pLen + 3 <= limit) {
+			const uint32_t end = (pW & 0x7FFFFFFFu) < limit ? (pW & 0x7FFFFFFFu) : limit;
+			pL2 = end - pLen;
+		}
+	}
+	LZ_T(4);
+
+	const uint32_t posState = position & pbMask;
+	uint32_t matchPrice, litPrice, repMatchPrice;
+	{
+		const uint32_t prob = e->isMatch[state][posState];
+		matchPrice = curPrice + price1(e, prob);
+		litPrice = curPrice + price0(e, prob);
+	}
+	const uint32_t probRep = e->isRep[state];
+	repMatchPrice = matchPrice + price1(e, probRep);
+	const uint32_t normalMatchPrice = matchPrice + price0(e, probRep);
+	uint32_t nPrice = n0.x, nLen = n0.z, nDist = n0.w;
+	bool nextIsLit = false;
+	if ((nPrice < kInfinity && matchByte == curByte) || litPrice > nPrice)
+		litPrice = 0;
+	else {
+		const Prob *probs = lit_probs(e, position, prevByte);
+		uint32_t v = 0;
+		if (lane < 8) {
+			const uint32_t node = (0x100u | curByte) >> (8 - lane), bit = (curByte >> (7 - lane)) & 1;
+			if (is_lit_state(state))
+				v = price_bit(e, probs[node], bit);
+			else {
+				const uint32_t offs = (((matchByte ^ curByte) >> (8 - lane)) == 0) ? 0x100u : 0u;
+				const uint32_t mb = ((matchByte >> (7 - lane)) & 1) << 8;
+				v = price_bit(e, probs[offs + (mb & offs) + node], bit);
+			}
+		}
+		litPrice += lz_sum(v);
+		if (litPrice < nPrice) {
+			opt_set4(nextOpt, litPrice, 1, kMarkLit, 0);
+			nPrice = litPrice;
+			nLen = 1;
+			nDist = kMarkLit;
+			nextIsLit = true;
+		}
+	}
+	// SHORT_REP
+	if (is_lit_state(state) && matchByte == curByte && repMatchPrice < nPrice && (nLen < 2 || nDist != 0)) {
+		const uint32_t shortRepPrice = repMatchPrice + price_short_rep(e, state, posState);
+		if (shortRepPrice < nPrice) {
+			opt_set4(nextOpt, shortRepPrice, 1, 0, 0);
+			nextIsLit = false;
+		}
+	}
+	LZ_T(5);
+
+	// LIT : REP_0 (bytes 1 and 2 behind rep0 equal; numAvailFull >= fb > 2)
+	if (!nextIsLit && litPrice != 0 && matchByte != curByte && (eq & 6u) == 6u) {
+		const uint8_t *data2 = data - reps[0];
+		uint32_t len, limit = fb + 1;
+		if (limit > numAvailFull)
+			limit = numAvailFull;
+		const uint32_t ne = ~eq & 0xF8u; // first of the bytes 3..7 that differs
+		if (ne)
+			len = lz_ffs(ne) - 1;
+		else
+			len = 8;
+		if (len > limit)
+			len = limit;
+		else if (!ne && limit > 8)
+			len = lz_extend(data2, data, 8, limit);
+		const uint32_t state2 = st_lit(state), posState2 = (position + 1) & pbMask;
+		const uint32_t price = litPrice + price_rep0(e, state2, posState2);
+		const uint32_t offset = cur + len;
+		if (last < offset)
+			last = offset;
+		len--;
+		const uint32_t price2 = price + len_price(&e->repLenPrices, posState2, len);
+		Opt *o = &e->opt[offset];
+		if (price2 < o->price)
+			opt_set4(o, price2, len, 0, 1);
+	}
+	uint32_t startLen = 2;
+	LZ_T(6);
+	// REP
+	for (uint32_t rm = repMask; rm; rm &= rm - 1) {
+		const uint32_t repIndex = lz_ffs(rm) - 1;
+		const uint8_t *data2 = data - reps[repIndex];
+		const uint32_t f = (eq >> (8 * repIndex)) & 0xFFu, nf = ~f & 0xFFu;
+		uint32_t len = nf ? lz_ffs(nf) - 1 : 8; // equal leading bytes among the first eight; numAvail = fb
+		if (len > fb)
+			len = fb;
+		else if (!nf && fb > 8)
+			len = lz_extend(data2, data, 8, fb);
+		if (last < cur + len)
+			last = cur + len;
+		uint32_t price = repMatchPrice + price_pure_rep(e, repIndex, state, posState);
+		opt_rep_cells(e, cur, 2, len, price, posState, repIndex);
+		if (repIndex == 0)
+			startLen = len + 1;
+		// REP : LIT : REP_0
+		uint32_t len2 = len + 1, limit = len2 + fb;
+		if (limit > numAvailFull)
+			limit = numAvailFull;
+		len2 += 2;
+		bool two;
+		if (len + 2 < 8)
+			two = ((f >> (len + 1)) & 3u) == 3u;
+		else
+			two = len2 <= limit && data[len2 - 2] == data2[len2 - 2] && data[len2 - 1] == data2[len2 - 1];
+		if (len2 <= limit && two) {
+			uint32_t state2 = st_rep(state), posState2 = (position + len) & pbMask;
+			price += len_price(&e->repLenPrices, posState, len) + price0(e, e->isMatch[state2][posState2]) +
+				 lit_price_matched(e, lit_probs(e, position + len, data[len - 1]), data[len], data2[len]);
+			state2 = 5; // kState_LitAfterRep
+			posState2 = (posState2 + 1) & pbMask;
+			price += price_rep0(e, state2, posState2);
+			len2 = lz_extend(data2, data, len2, limit);
+			len2 -= len;
+			const uint32_t offset = cur + len + len2;
+			if (last < offset)
+				last = offset;
+			len2--;
+			const uint32_t price2 = price + len_price(&e->repLenPrices, posState2, len2);
+			Opt *o = &e->opt[offset];
+			if (price2 < o->price)
+				opt_set4(o, price2, len2, repIndex, len + 1);
+		}
+	}
+	LZ_T(7);
+	// MATCH
+	if (newLen >= startLen) {
+		if (last < cur + newLen)
+			last = cur + newLen;
+		// MATCH : LIT : REP_0 of every pair that is long enough: priced by the pair's lane, applied in pair order
+		const bool tr = lane < np && pLen >= startLen && pL2 != 0;
+		const uint32_t trMask = lz_ballot(tr);
+		if (trMask) {
+			uint32_t tPrice = 0;
+			if (tr) {
+				const uint8_t *data2 = data - pDist - 1;
+				uint32_t price = match_price(e, normalMatchPrice, posState, pLen, pDist);
+				uint32_t state2 = st_match(state), posState2 = (position + pLen) & pbMask;
+				price += price0(e, e->isMatch[state2][posState2]);
+				price += lit_price_matched_1(e, lit_probs(e, position + pLen, data[pLen - 1]), data[pLen], data2[pLen]);
+				state2 = 4; // kState_LitAfterMatch
+				posState2 = (posState2 + 1) & pbMask;
+				price += price_rep0(e, state2, posState2);
+				tPrice = price + len_price(&e->repLenPrices, posState2, pL2 - 1);
+			}
+			for (uint32_t m = trMask; m; m &= m - 1) {
+				const uint32_t k = lz_ffs(m) - 1;
+				const uint32_t len = lz_shfl(pLen, k), l2 = lz_shfl(pL2, k), dist = lz_shfl(pDist, k), price2 = lz_shfl(tPrice, k);
+				const uint32_t offset = cur + len + l2;
+				if (last < offset)
+					last = offset;
+				Opt *o = &e->opt[offset];
+				if (price2 < o->price)
+					opt_set4(o, price2, l2 - 1, dist + kNumReps, len + 1);
+			}
+		}
+		LZ_T(8);
+		// the cells [cur + startLen, cur + newLen]: the shortest-distance pair that reaches each length (staged table)
+		for (uint32_t len = startLen + lane; len <= newLen; len += LZ_W) {
+			const uint32_t dist = b[kLkByLen + len];
+			const uint32_t price = match_price(e, normalMatchPrice, posState, len, dist);
+			Opt *o = &e->opt[cur + len];
+			if (price < o->price)
+				opt_set4(o, price, len, dist + kNumReps, 0);
+		}
+		LZ_T(9);
+	}
+	lz_sync();
+}
+#endif
+
 // GetOptimum (LzmaEnc.c:1219-1968).
 //
 // Order of updates: the reference interleaves, per position, "cell" updates (a rep or match of every
@@ -959,6 +1255,7 @@ LZ_FN inline uint32_t get_optimum(Enc *e, uint32_t position)
 	const uint32_t fb = e->fb;
 	{
 		uint32_t numAvail, numPairs, mainLen, repMaxIndex, i, posState, matchPrice, repMatchPrice;
+		LZ_T(0);
 		e->optCur = e->optEnd = 0;
 		if (e->additionalOffset == 0)
 			mainLen = read_matches(e, &numPairs);
@@ -1001,11 +1298,13 @@ LZ_FN inline uint32_t get_optimum(Enc *e, uint32_t position)
 			e->backRes = repMaxIndex;
 			const uint32_t len = repLens[repMaxIndex];
 			move_pos(e, len - 1);
+			LZ_T(11);
 			return len;
 		}
 		if (mainLen >= fb) {
 			e->backRes = matches[numPairs - 1] + kNumReps;
 			move_pos(e, mainLen - 1);
+			LZ_T(11);
 			return mainLen;
 		}
 		const uint8_t curByte = *data, matchByte = *(data - reps[0]);
@@ -1014,6 +1313,7 @@ LZ_FN inline uint32_t get_optimum(Enc *e, uint32_t position)
 			last = mainLen;
 		if (last < 2 && curByte != matchByte) {
 			e->backRes = kMarkLit;
+			LZ_T(11);
 			return 1;
 		}
 		e->opt[0].state = (uint16_t)e->state;
@@ -1036,6 +1336,7 @@ LZ_FN inline uint32_t get_optimum(Enc *e, uint32_t position)
 			}
 			if (last < 2) {
 				e->backRes = e->opt[1].dist;
+				LZ_T(11);
 				return 1;
 			}
 		}
@@ -1060,7 +1361,14 @@ LZ_FN inline uint32_t get_optimum(Enc *e, uint32_t position)
 			}
 		}
 		cur = 0;
+		LZ_T(1);
 	}
+#if defined(__CUDA_ARCH__)
+	// loop invariants the compiler cannot keep in registers by itself (every store into *e may alias them)
+	const uint32_t *const lkTag = e->lkTag, *const lkData = e->lkData;
+	const uint32_t nAll = e->n, pbMask = e->pbMask;
+	const uint8_t *const srcAll = e->src;
+#endif
 
 	for (;;) {
 		uint32_t numAvail, numAvailFull, newLen, numPairs, prev, state, posState, startLen;
@@ -1083,7 +1391,40 @@ LZ_FN inline uint32_t get_optimum(Enc *e, uint32_t position)
 			cur = best;
 			break;
 		}
+#if defined(__CUDA_ARCH__)
+		if (lkTag) {
+			// every iteration reads exactly one position: the finder stands two past `position` (1-based)
+			const uint32_t pos = position + 2, slot = pos & (kLkSlots - 1);
+			const uint32_t *b = lkData + slot * kLkWords;
+			const uint32_t availReal = nAll - (pos - 1);
+			uint32_t naf = kNumOpts - 1 - cur; // numAvailFull
+			if (naf > availReal)
+				naf = availReal;
+#if defined(LZ_PROF)
+			if (e->pos != pos)
+				e->profN[20]++;
+#endif
+			if (naf >= fb && naf >= 8 && lz_ld_acquire(lkTag + slot) == pos) {
+				const uint32_t hdr = b[0];
+				if ((hdr & 0xFFFFu) <= 64 && (hdr >> 16) < fb) {
+#if defined(LZ_PROF)
+					e->profN[14]++;
+#endif
+					opt_step_staged(e, b, hdr, pos, naf, cur, last, position, reps, srcAll, pbMask, fb);
+					continue;
+				}
+#if defined(LZ_PROF)
+				e->profN[15]++;
+#endif
+			}
+#if defined(LZ_PROF)
+			else
+				e->profN[16]++;
+#endif
+		}
+#endif
 		newLen = read_matches(e, &numPairs);
+		LZ_T(2);
 		if (newLen >= fb) {
 			e->numPairs = numPairs;
 			e->longestMatchLen = newLen;
@@ -1138,6 +1479,7 @@ LZ_FN inline uint32_t get_optimum(Enc *e, uint32_t position)
 		for (uint32_t i = 0; i < kNumReps; i++)
 			curOpt->reps[i] = reps[i];
 
+		LZ_T(3);
 		const uint8_t *data = mf_cur(e) - 1;
 		numAvailFull = e->numAvail;
 		{
@@ -1193,6 +1535,7 @@ LZ_FN inline uint32_t get_optimum(Enc *e, uint32_t position)
 			}
 		}
 		lz_sync();
+		LZ_T(4);
 
 		const uint8_t curByte = *data, matchByte = *(data - reps[0]);
 		posState = position & e->pbMask;
@@ -1224,6 +1567,7 @@ LZ_FN inline uint32_t get_optimum(Enc *e, uint32_t position)
 				nextIsLit = false;
 			}
 		}
+		LZ_T(5);
 		if (numAvailFull < 2)
 			continue;
 
@@ -1248,6 +1592,7 @@ LZ_FN inline uint32_t get_optimum(Enc *e, uint32_t position)
 			}
 		}
 		startLen = 2;
+		LZ_T(6);
 		// REP
 		for (uint32_t repIndex = 0; repIndex < kNumReps; repIndex++) {
 			if (e->xRepLen[repIndex] == 0)
@@ -1284,6 +1629,7 @@ LZ_FN inline uint32_t get_optimum(Enc *e, uint32_t position)
 					opt_set(o, price2, len2, repIndex, len + 1);
 			}
 		}
+		LZ_T(7);
 		// MATCH
 		if (newLen >= startLen) {
 			const uint32_t normalMatchPrice = matchPrice + price0(e, e->isRep[state]);
@@ -1320,14 +1666,18 @@ LZ_FN inline uint32_t get_optimum(Enc *e, uint32_t position)
 				if (price2 < o->price)
 					opt_set(o, price2, l2 - 1, matches[2 * k + 1] + kNumReps, len + 1);
 			}
+			LZ_T(8);
 			opt_match_cells(e, cur, startLen, newLen, normalMatchPrice, posState);
+			LZ_T(9);
 		}
 	}
 	lz_sync();
 	LZ_PFOR(q, last)
 		e->opt[1 + q].price = kInfinity;
 	lz_sync();
-	return backward(e, cur);
+	const uint32_t res_ = backward(e, cur);
+	LZ_T(10);
+	return res_;
 }
 
 // GetOptimumFast (LzmaEnc.c:1970-2098): levels 1-4.  No price tables; greedy with one position of look-ahead.
@@ -1721,6 +2071,7 @@ LZ_FN inline uint64_t enc_run(Enc *e)
 			if (e->rcQ)
 				rcq_publish(e);
 #endif
+			LZ_T(12);
 			nowPos += len;
 			e->additionalOffset -= len;
 			if (e->additionalOffset == 0) {
@@ -1733,6 +2084,7 @@ LZ_FN inline uint64_t enc_run(Enc *e)
 					e->repLenCounter = kRepLenCount;
 					len_update_prices(e, &e->repLenPrices, e->pbMask + 1, &e->repLenProbs);
 				}
+				LZ_T(13);
 				if (mf_avail(e) == 0)
 					break;
 				if (e->gateState && *(const volatile int *)e->gateState == 2) { // the same word for every lane
