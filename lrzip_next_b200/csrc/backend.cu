@@ -382,7 +382,7 @@ __global__ void __launch_bounds__(128, 1) lzma_block_kernel(LzmaJob *jobs)
 	if (threadIdx.x == 0) {
 		const long long tot = clock64() - prof_t0;
 		printf("[lzprof] n=%u total=%lld cyc (%.0f / byte)\n", j.n, tot, (double)tot / j.n);
-		for (int i = 0; i < 14; i++)
+		for (int i = 0; i < 20; i++)
 			printf("[lzprof] s%-2d %6.2f%%  %12llu cyc  %10llu calls  %8.0f cyc/call\n", i, 100.0 * e->prof[i] / tot,
 			       (unsigned long long)e->prof[i], (unsigned long long)e->profN[i],
 			       e->profN[i] ? (double)e->prof[i] / e->profN[i] : 0.0);

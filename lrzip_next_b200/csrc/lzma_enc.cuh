@@ -301,13 +301,47 @@ LZ_INL void rcq_reserve(Enc *e)
 }
 #endif
 
-LZ_INL void rc_bit(Enc *e, Prob *prob, uint32_t bit)
+// Device, queue mode: the binary decisions of ONE symbol are collected one per lane (which probability, which
+// bit: both follow from the symbol alone, never from a probability's value, and no probability is used twice
+// within a symbol), then rcw_commit lets every lane update its probability and queue its (probability, bit) entry
+// at once.  A symbol has at most 23 decisions (match: 2 + 10 length + 6 slot + 1 direct + 4 align).
+struct RcW {
+	Prob *p;
+	uint32_t v, cnt;
+	bool on;
+};
+
+LZ_INL void rcw_commit(Enc *e, RcW &w)
 {
 #if defined(__CUDA_ARCH__)
-	if (e->rcQ) {
-		const uint32_t q = *prob;
-		*prob = bit ? (Prob)(q - (q >> kMoveBits)) : (Prob)(q + ((kBitModelTotal - q) >> kMoveBits));
-		rcq_push(e, (q << 1) | bit);
+	if (!w.on)
+		return;
+	const uint32_t tail = e->rcTail;
+	if (lz_lane() < w.cnt) {
+		uint32_t ent = w.v;
+		if (w.p) {
+			const uint32_t q = *w.p;
+			*w.p = w.v ? (Prob)(q - (q >> kMoveBits)) : (Prob)(q + ((kBitModelTotal - q) >> kMoveBits));
+			ent = (q << 1) | w.v;
+		}
+		e->rcQ[(tail + lz_lane()) & (kRcQ - 1)] = ent;
+	}
+	e->rcTail = tail + w.cnt;
+	w.cnt = 0;
+	lz_sync();
+	rcq_publish(e);
+#endif
+}
+
+LZ_INL void rc_bit(Enc *e, RcW &w, Prob *prob, uint32_t bit)
+{
+#if defined(__CUDA_ARCH__)
+	if (w.on) { // decision number w.cnt of this symbol: lane w.cnt keeps it (rcw_commit)
+		if (lz_lane() == w.cnt) {
+			w.p = prob;
+			w.v = bit;
+		}
+		w.cnt++;
 		return;
 	}
 #endif
@@ -337,12 +371,17 @@ LZ_INL void rc_bit_value(Enc *e, uint32_t p, uint32_t bit)
 	rc_norm(e);
 }
 
-LZ_INL void rc_direct(Enc *e, uint32_t value, uint32_t nbits) // most significant bit first
+LZ_INL void rc_direct(Enc *e, RcW &w, uint32_t value, uint32_t nbits) // most significant bit first
 {
 #if defined(__CUDA_ARCH__)
-	if (e->rcQ) {
-		if (nbits)
-			rcq_push(e, kRcDirect | (nbits << 26) | value); // nbits <= 26, value < 2^26
+	if (w.on) {
+		if (nbits) {
+			if (lz_lane() == w.cnt) {
+				w.p = nullptr;
+				w.v = kRcDirect | (nbits << 26) | value; // nbits <= 26, value < 2^26
+			}
+			w.cnt++;
+		}
 		return;
 	}
 #endif
@@ -354,16 +393,16 @@ LZ_INL void rc_direct(Enc *e, uint32_t value, uint32_t nbits) // most significan
 	}
 }
 
-LZ_FN inline void lit_encode(Enc *e, Prob *probs, uint32_t sym)
+LZ_FN inline void lit_encode(Enc *e, RcW &w, Prob *probs, uint32_t sym)
 {
 	sym |= 0x100;
 	do {
-		rc_bit(e, probs + (sym >> 8), (sym >> 7) & 1);
+		rc_bit(e, w, probs + (sym >> 8), (sym >> 7) & 1);
 		sym <<= 1;
 	} while (sym < 0x10000);
 }
 
-LZ_FN inline void lit_encode_matched(Enc *e, Prob *probs, uint32_t sym, uint32_t matchByte)
+LZ_FN inline void lit_encode_matched(Enc *e, RcW &w, Prob *probs, uint32_t sym, uint32_t matchByte)
 {
 	uint32_t offs = 0x100;
 	sym |= 0x100;
@@ -373,44 +412,44 @@ LZ_FN inline void lit_encode_matched(Enc *e, Prob *probs, uint32_t sym, uint32_t
 		const uint32_t bit = (sym >> 7) & 1;
 		sym <<= 1;
 		offs &= ~(matchByte ^ sym);
-		rc_bit(e, prob, bit);
+		rc_bit(e, w, prob, bit);
 	} while (sym < 0x10000);
 }
 
-LZ_FN inline void rc_reverse(Enc *e, Prob *probs, uint32_t nbits, uint32_t sym)
+LZ_FN inline void rc_reverse(Enc *e, RcW &w, Prob *probs, uint32_t nbits, uint32_t sym)
 {
 	uint32_t m = 1;
 	do {
 		const uint32_t bit = sym & 1;
 		sym >>= 1;
-		rc_bit(e, probs + m, bit);
+		rc_bit(e, w, probs + m, bit);
 		m = (m << 1) | bit;
 	} while (--nbits);
 }
 
 // LenEnc_Encode (LzmaEnc.c:928-960)
-LZ_FN inline void len_encode(Enc *e, LenProbs *lp, uint32_t sym, uint32_t posState)
+LZ_FN inline void len_encode(Enc *e, RcW &w, LenProbs *lp, uint32_t sym, uint32_t posState)
 {
 	Prob *probs = lp->low;
 	if (sym >= kLenLow) {
-		rc_bit(e, probs, 1);
+		rc_bit(e, w, probs, 1);
 		probs += kLenLow;
 		if (sym >= kLenLow * 2) {
-			rc_bit(e, probs, 1);
-			lit_encode(e, lp->high, sym - kLenLow * 2);
+			rc_bit(e, w, probs, 1);
+			lit_encode(e, w, lp->high, sym - kLenLow * 2);
 			return;
 		}
 		sym -= kLenLow;
 	}
-	rc_bit(e, probs, 0);
+	rc_bit(e, w, probs, 0);
 	probs += posState << 4;
 	uint32_t bit = sym >> 2;
-	rc_bit(e, probs + 1, bit);
+	rc_bit(e, w, probs + 1, bit);
 	uint32_t m = 2 + bit;
 	bit = (sym >> 1) & 1;
-	rc_bit(e, probs + m, bit);
+	rc_bit(e, w, probs + m, bit);
 	m = (m << 1) + bit;
-	rc_bit(e, probs + m, sym & 1);
+	rc_bit(e, w, probs + m, sym & 1);
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -1954,6 +1993,13 @@ LZ_FN inline void enc_init(Enc *e, const Config &c, const uint8_t *src, uint32_t
 LZ_FN inline uint64_t enc_run(Enc *e)
 {
 	uint32_t nowPos = 0;
+	RcW w;
+	w.p = nullptr;
+	w.v = w.cnt = 0;
+	w.on = false;
+#if defined(__CUDA_ARCH__)
+	w.on = e->rcQ != nullptr;
+#endif
 	if (e->n == 0) {
 		for (int i = 0; i < 5; i++)
 			rc_shift_low(e);
@@ -1962,9 +2008,10 @@ LZ_FN inline uint64_t enc_run(Enc *e)
 	{
 		uint32_t numPairs;
 		read_matches(e, &numPairs);
-		rc_bit(e, &e->isMatch[0][0], 0);
+		rc_bit(e, w, &e->isMatch[0][0], 0);
 		const uint8_t curByte = *(mf_cur(e) - e->additionalOffset);
-		lit_encode(e, e->lit, curByte);
+		lit_encode(e, w, e->lit, curByte);
+		rcw_commit(e, w);
 		e->additionalOffset--;
 		nowPos++;
 	}
@@ -1991,33 +2038,34 @@ LZ_FN inline uint64_t enc_run(Enc *e)
 			if (e->rcQ)
 				rcq_reserve(e);
 #endif
+			LZ_T(17);
 			if (dist == kMarkLit) {
-				rc_bit(e, pm, 0);
+				rc_bit(e, w, pm, 0);
 				const uint8_t *data = mf_cur(e) - e->additionalOffset;
 				Prob *probs = (Prob *)lit_probs(e, nowPos, *(data - 1));
 				const uint32_t state = e->state;
 				e->state = st_lit(state);
 				if (is_lit_state(state))
-					lit_encode(e, probs, *data);
+					lit_encode(e, w, probs, *data);
 				else
-					lit_encode_matched(e, probs, *data, *(data - e->reps[0]));
+					lit_encode_matched(e, w, probs, *data, *(data - e->reps[0]));
 			} else {
-				rc_bit(e, pm, 1);
+				rc_bit(e, w, pm, 1);
 				if (dist < kNumReps) {
-					rc_bit(e, &e->isRep[e->state], 1);
+					rc_bit(e, w, &e->isRep[e->state], 1);
 					if (dist == 0) {
-						rc_bit(e, &e->isRepG0[e->state], 0);
-						rc_bit(e, &e->isRep0Long[e->state][posState], len != 1 ? 1 : 0);
+						rc_bit(e, w, &e->isRepG0[e->state], 0);
+						rc_bit(e, w, &e->isRep0Long[e->state][posState], len != 1 ? 1 : 0);
 						if (len == 1)
 							e->state = st_shortrep(e->state);
 					} else {
-						rc_bit(e, &e->isRepG0[e->state], 1);
+						rc_bit(e, w, &e->isRepG0[e->state], 1);
 						if (dist == 1) {
-							rc_bit(e, &e->isRepG1[e->state], 0);
+							rc_bit(e, w, &e->isRepG1[e->state], 0);
 							dist = e->reps[1];
 						} else {
-							rc_bit(e, &e->isRepG1[e->state], 1);
-							rc_bit(e, &e->isRepG2[e->state], dist - 2);
+							rc_bit(e, w, &e->isRepG1[e->state], 1);
+							rc_bit(e, w, &e->isRepG2[e->state], dist - 2);
 							if (dist == 2)
 								dist = e->reps[2];
 							else {
@@ -2030,14 +2078,14 @@ LZ_FN inline uint64_t enc_run(Enc *e)
 						e->reps[0] = dist;
 					}
 					if (len != 1) {
-						len_encode(e, &e->repLenProbs, len - kMatchMin, posState);
+						len_encode(e, w, &e->repLenProbs, len - kMatchMin, posState);
 						--e->repLenCounter;
 						e->state = st_rep(e->state);
 					}
 				} else {
-					rc_bit(e, &e->isRep[e->state], 0);
+					rc_bit(e, w, &e->isRep[e->state], 0);
 					e->state = st_match(e->state);
-					len_encode(e, &e->lenProbs, len - kMatchMin, posState);
+					len_encode(e, w, &e->lenProbs, len - kMatchMin, posState);
 					dist -= kNumReps;
 					e->reps[3] = e->reps[2];
 					e->reps[2] = e->reps[1];
@@ -2052,25 +2100,23 @@ LZ_FN inline uint64_t enc_run(Enc *e)
 							Prob *prob = probs + (sym >> 6);
 							const uint32_t bit = (sym >> 5) & 1;
 							sym <<= 1;
-							rc_bit(e, prob, bit);
+							rc_bit(e, w, prob, bit);
 						} while (sym < (1u << 12));
 					}
 					if (dist >= kStartPosModel) {
 						const uint32_t footer = (slot >> 1) - 1;
 						if (dist < kNumFullDist) {
 							const uint32_t base = (2 | (slot & 1)) << footer;
-							rc_reverse(e, e->posEnc + base, footer, dist);
+							rc_reverse(e, w, e->posEnc + base, footer, dist);
 						} else {
-							rc_direct(e, (dist & ((1u << footer) - 1)) >> kNumAlignBits, footer - kNumAlignBits);
-							rc_reverse(e, e->posAlign, kNumAlignBits, dist & kAlignMask);
+							rc_direct(e, w, (dist & ((1u << footer) - 1)) >> kNumAlignBits, footer - kNumAlignBits);
+							rc_reverse(e, w, e->posAlign, kNumAlignBits, dist & kAlignMask);
 						}
 					}
 				}
 			}
-#if defined(__CUDA_ARCH__)
-			if (e->rcQ)
-				rcq_publish(e);
-#endif
+			LZ_T(18);
+			rcw_commit(e, w);
 			LZ_T(12);
 			nowPos += len;
 			e->additionalOffset -= len;
