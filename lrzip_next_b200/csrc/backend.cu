@@ -193,8 +193,9 @@ constexpr uint32_t kLzmaAhead = 6; // positions
 // shared memory (lzma_enc.cuh: kLkSlots entries), together with the byte comparison of every pair's
 // MATCH : LIT : REP0 trial (LzmaEnc.c:1876-1893), so that the encoder warp finds both without touching HBM.
 // A staged entry is a cache: the encoder checks its tag and falls back to HBM, so nothing here can change the output.
-__device__ void lzma_lookahead_warp(const lzma::Enc *e, const LzmaJob &j, const volatile int *done, uint32_t *lkTag, uint32_t *lkData)
+__device__ void lzma_lookahead_warp(lzma::Enc *e, const LzmaJob &j, const volatile int *done)
 {
+	uint32_t *const lkData = e->lkRing;
 	const uint32_t lane = threadIdx.x & 31u, grp = lane >> 3, sub = lane & 7u;
 	const volatile uint32_t *ppos = &e->pos;
 	const uint8_t *src = j.src;
@@ -246,16 +247,17 @@ __device__ void lzma_lookahead_warp(const lzma::Enc *e, const LzmaJob &j, const 
 						b[lzma::kLkByLen + from] = dist;
 				}
 			}
-			if (stage && sub == 0)
-				b[0] = nd | ((nd ? lst[nd - 2] : 0u) << 16); // count, and the longest length (ReadMatchDistances' result)
 		}
 		__syncwarp();
 		__threadfence_block();
 		__syncwarp();
 		if (q <= hi && sub == 0) {
-			const uint32_t nd = (uint32_t)j.rec[q - 1] & 1023u;
-			if (nd <= lzma::kLkMaxList)
-				*(volatile uint32_t *)(lkTag + (q & (lzma::kLkSlots - 1))) = q;
+			const uint64_t rec = j.rec[q - 1];
+			const uint32_t nd = (uint32_t)rec & 1023u;
+			if (nd <= lzma::kLkMaxList) { // position, count and the longest length (ReadMatchDistances' result) in one store
+				const uint32_t hdr = nd | ((nd ? j.pool[(rec >> 10) + nd - 2] : 0u) << 16);
+				*reinterpret_cast<volatile uint64_t *>(&e->lkHead[q & (lzma::kLkSlots - 1)][0]) = (uint64_t)q | ((uint64_t)hdr << 32);
+			}
 		}
 		upto = hi;
 		__syncwarp();
@@ -265,9 +267,11 @@ __device__ void lzma_lookahead_warp(const lzma::Enc *e, const LzmaJob &j, const 
 // Warp 3, one thread: the range arithmetic, carries and byte output for the (probability, bit) pairs the encoder
 // warp queues (lzma_enc.cuh: rc_bit with a queue).  Same bytes as the in-line coder: the queue preserves the order
 // of the binary decisions and carries the probability each one was coded with.
-__device__ void lzma_coder_thread(lzma::Enc *e, const volatile uint32_t *q, volatile uint32_t *tailPub, volatile uint32_t *headPub,
-				  volatile int *rcDone)
+__device__ void lzma_coder_thread(lzma::Enc *e)
 {
+	const volatile uint32_t *q = e->rcQueue;
+	volatile uint32_t *tailPub = &e->rcTailPub, *headPub = &e->rcHeadPub;
+	volatile int *rcDone = &e->rcDone;
 	uint32_t head = 0;
 	for (;;) {
 		const uint32_t tail = *tailPub;
@@ -314,11 +318,7 @@ __global__ void __launch_bounds__(128, 1) lzma_block_kernel(LzmaJob *jobs)
 {
 	extern __shared__ __align__(16) uint8_t lzma_smem[];
 	__shared__ uint32_t gate_table[4096];
-	__shared__ uint32_t rc_queue[lzma::kRcQ];
-	__shared__ uint32_t lk_data[lzma::kLkSlots * lzma::kLkWords];
-	__shared__ uint32_t lk_tag[lzma::kLkSlots];
-	__shared__ uint32_t rc_tail_pub, rc_head_pub;
-	__shared__ int done, gate_state, rc_done;
+	__shared__ int done, gate_state;
 	lzma::Enc *e = reinterpret_cast<lzma::Enc *>(lzma_smem);
 	LzmaJob &j = jobs[blockIdx.x];
 	if (*j.mf_overflow) { // uniform over the CTA: the host encodes this block again with a larger pool
@@ -327,12 +327,10 @@ __global__ void __launch_bounds__(128, 1) lzma_block_kernel(LzmaJob *jobs)
 		return;
 	}
 	if (threadIdx.x < lzma::kLkSlots)
-		lk_tag[threadIdx.x] = 0; // no position 0: positions count from 1
+		e->lkHead[threadIdx.x][0] = e->lkHead[threadIdx.x][1] = 0; // no position 0: positions count from 1
 	if (threadIdx.x == 0) {
 		done = 0;
 		gate_state = 0;
-		rc_done = 0;
-		rc_tail_pub = rc_head_pub = 0;
 	}
 	__syncthreads();
 	if (threadIdx.x < 32) {
@@ -340,17 +338,12 @@ __global__ void __launch_bounds__(128, 1) lzma_block_kernel(LzmaJob *jobs)
 		e->preRec = j.rec;
 		e->prePool = j.pool;
 		e->gateState = j.threshold ? &gate_state : nullptr;
-		e->lkTag = lk_tag;
-		e->lkData = lk_data;
-		e->rcQ = rc_queue;
-		e->rcTailPub = &rc_tail_pub;
-		e->rcHeadPub = &rc_head_pub;
-		e->rcDone = &rc_done;
+		e->lkOn = e->rcOn = 1;
 	}
 	__syncthreads(); // the encoder state is initialised: the helpers may read it
 	if (threadIdx.x >= 96) {
 		if (threadIdx.x == 96)
-			lzma_coder_thread(e, rc_queue, &rc_tail_pub, &rc_head_pub, &rc_done);
+			lzma_coder_thread(e);
 		return;
 	}
 	if (threadIdx.x >= 64) {
@@ -367,7 +360,7 @@ __global__ void __launch_bounds__(128, 1) lzma_block_kernel(LzmaJob *jobs)
 		return;
 	}
 	if (threadIdx.x >= 32) {
-		lzma_lookahead_warp(e, j, &done, lk_tag, lk_data);
+		lzma_lookahead_warp(e, j, &done);
 		return;
 	}
 #if defined(LZ_PROF)
@@ -386,9 +379,7 @@ __global__ void __launch_bounds__(128, 1) lzma_block_kernel(LzmaJob *jobs)
 			printf("[lzprof] s%-2d %6.2f%%  %12llu cyc  %10llu calls  %8.0f cyc/call\n", i, 100.0 * e->prof[i] / tot,
 			       (unsigned long long)e->prof[i], (unsigned long long)e->profN[i],
 			       e->profN[i] ? (double)e->prof[i] / e->profN[i] : 0.0);
-		printf("[lzprof] staged steps %llu, staged but not eligible %llu, not staged %llu, pos mismatch %llu\n",
-		       (unsigned long long)e->profN[14], (unsigned long long)e->profN[15], (unsigned long long)e->profN[16],
-		       (unsigned long long)e->profN[20]);
+		printf("[lzprof] pos mismatch %llu\n", (unsigned long long)e->profN[20]);
 	}
 #endif
 	int verdict = 1;

@@ -165,13 +165,9 @@ struct Enc {
 	const int *gateState;
 	int aborted;
 	// staged match lists / range-coder queue (null on the host and in tests of the plain path)
-	const uint32_t *lkTag;  // [kLkSlots] position (1-based, as e->pos) each ring entry holds
-	const uint32_t *lkData; // [kLkSlots][kLkWords]
+	int lkOn, rcOn;         // the look-ahead warp / the coder thread are running (device product path only)
 	int lkSlot;             // entry the current position's list was taken from, or -1
-	uint32_t *rcQ;          // [kRcQ]
 	uint32_t rcTail;        // entries queued so far (the encoder warp's private count)
-	uint32_t *rcTailPub, *rcHeadPub; // published counts (encoder -> coder, coder -> encoder)
-	int *rcDone;
 	uint32_t pos;       // position the match finder will hand out next
 	uint32_t cycPos;
 	uint32_t crc[256];
@@ -209,6 +205,13 @@ struct Enc {
 	uint64_t prof[24], profN[24];
 	long long profT;
 #endif
+	// The helpers' structures live inside the encoder so that the encoder warp reaches them with plain shared-memory
+	// loads (through a pointer kept in the struct they become generic loads, which cost three times as much).
+	alignas(8) uint32_t lkHead[kLkSlots][2]; // {position (1-based, as e->pos) the entry holds, count | longest length << 16}
+	uint32_t lkRing[kLkSlots * kLkWords];
+	uint32_t rcQueue[kRcQ];
+	uint32_t rcTailPub, rcHeadPub; // published counts (encoder -> coder, coder -> encoder)
+	int rcDone;
 };
 
 // ---------------------------------------------------------------------------------------------------
@@ -230,6 +233,8 @@ LZ_INL uint32_t pos_slot(uint32_t d) // GetPosSlot (LzmaEnc.c:167-246): 2*log2 +
 	return 2 * b + ((d >> (b - 1)) & 1);
 }
 
+// a[i] for a four-element array kept in registers (a run-time index would push the array to local memory)
+LZ_INL uint32_t pick4(const uint32_t *a, uint32_t i) { return i == 0 ? a[0] : (i == 1 ? a[1] : (i == 2 ? a[2] : a[3])); }
 LZ_INL bool is_lit_state(uint32_t s) { return s < 7; }
 LZ_INL uint32_t st_lit(uint32_t s) { return s < 4 ? 0 : (s < 10 ? s - 3 : s - 6); }   // kLiteralNextStates
 LZ_INL uint32_t st_match(uint32_t s) { return s < 7 ? 7 : 10; }                         // kMatchNextStates
@@ -284,19 +289,19 @@ LZ_INL void rc_norm(Enc *e)
 #if defined(__CUDA_ARCH__)
 LZ_INL void rcq_push(Enc *e, uint32_t v)
 {
-	e->rcQ[e->rcTail & (kRcQ - 1)] = v; // every lane stores the same word
+	e->rcQueue[e->rcTail & (kRcQ - 1)] = v; // every lane stores the same word
 	e->rcTail++;
 }
 // make the entries queued so far visible to the coder thread; called once per symbol
 LZ_INL void rcq_publish(Enc *e)
 {
 	__threadfence_block();
-	*(volatile uint32_t *)e->rcTailPub = e->rcTail;
+	*(volatile uint32_t *)&e->rcTailPub = e->rcTail;
 }
 // room for one more symbol (a symbol queues fewer than 64 entries)
 LZ_INL void rcq_reserve(Enc *e)
 {
-	while (e->rcTail + 64 - *(volatile uint32_t *)e->rcHeadPub > kRcQ)
+	while (e->rcTail + 64 - *(volatile uint32_t *)&e->rcHeadPub > kRcQ)
 		__nanosleep(100);
 }
 #endif
@@ -306,7 +311,7 @@ LZ_INL void rcq_reserve(Enc *e)
 // within a symbol), then rcw_commit lets every lane update its probability and queue its (probability, bit) entry
 // at once.  A symbol has at most 23 decisions (match: 2 + 10 length + 6 slot + 1 direct + 4 align).
 struct RcW {
-	Prob *p;
+	uint32_t off; // the probability, as a byte offset inside the encoder (0: direct bits)
 	uint32_t v, cnt;
 	bool on;
 };
@@ -319,12 +324,13 @@ LZ_INL void rcw_commit(Enc *e, RcW &w)
 	const uint32_t tail = e->rcTail;
 	if (lz_lane() < w.cnt) {
 		uint32_t ent = w.v;
-		if (w.p) {
-			const uint32_t q = *w.p;
-			*w.p = w.v ? (Prob)(q - (q >> kMoveBits)) : (Prob)(q + ((kBitModelTotal - q) >> kMoveBits));
+		if (w.off) {
+			Prob *pp = reinterpret_cast<Prob *>(reinterpret_cast<char *>(e) + w.off);
+			const uint32_t q = *pp;
+			*pp = w.v ? (Prob)(q - (q >> kMoveBits)) : (Prob)(q + ((kBitModelTotal - q) >> kMoveBits));
 			ent = (q << 1) | w.v;
 		}
-		e->rcQ[(tail + lz_lane()) & (kRcQ - 1)] = ent;
+		e->rcQueue[(tail + lz_lane()) & (kRcQ - 1)] = ent;
 	}
 	e->rcTail = tail + w.cnt;
 	w.cnt = 0;
@@ -338,7 +344,7 @@ LZ_INL void rc_bit(Enc *e, RcW &w, Prob *prob, uint32_t bit)
 #if defined(__CUDA_ARCH__)
 	if (w.on) { // decision number w.cnt of this symbol: lane w.cnt keeps it (rcw_commit)
 		if (lz_lane() == w.cnt) {
-			w.p = prob;
+			w.off = (uint32_t)(reinterpret_cast<const char *>(prob) - reinterpret_cast<const char *>(e));
 			w.v = bit;
 		}
 		w.cnt++;
@@ -377,7 +383,7 @@ LZ_INL void rc_direct(Enc *e, RcW &w, uint32_t value, uint32_t nbits) // most si
 	if (w.on) {
 		if (nbits) {
 			if (lz_lane() == w.cnt) {
-				w.p = nullptr;
+				w.off = 0;
 				w.v = kRcDirect | (nbits << 26) | value; // nbits <= 26, value < 2^26
 			}
 			w.cnt++;
@@ -393,7 +399,7 @@ LZ_INL void rc_direct(Enc *e, RcW &w, uint32_t value, uint32_t nbits) // most si
 	}
 }
 
-LZ_FN inline void lit_encode(Enc *e, RcW &w, Prob *probs, uint32_t sym)
+LZ_INL void lit_encode(Enc *e, RcW &w, Prob *probs, uint32_t sym)
 {
 	sym |= 0x100;
 	do {
@@ -402,7 +408,7 @@ LZ_FN inline void lit_encode(Enc *e, RcW &w, Prob *probs, uint32_t sym)
 	} while (sym < 0x10000);
 }
 
-LZ_FN inline void lit_encode_matched(Enc *e, RcW &w, Prob *probs, uint32_t sym, uint32_t matchByte)
+LZ_INL void lit_encode_matched(Enc *e, RcW &w, Prob *probs, uint32_t sym, uint32_t matchByte)
 {
 	uint32_t offs = 0x100;
 	sym |= 0x100;
@@ -416,7 +422,7 @@ LZ_FN inline void lit_encode_matched(Enc *e, RcW &w, Prob *probs, uint32_t sym, 
 	} while (sym < 0x10000);
 }
 
-LZ_FN inline void rc_reverse(Enc *e, RcW &w, Prob *probs, uint32_t nbits, uint32_t sym)
+LZ_INL void rc_reverse(Enc *e, RcW &w, Prob *probs, uint32_t nbits, uint32_t sym)
 {
 	uint32_t m = 1;
 	do {
@@ -428,7 +434,7 @@ LZ_FN inline void rc_reverse(Enc *e, RcW &w, Prob *probs, uint32_t nbits, uint32
 }
 
 // LenEnc_Encode (LzmaEnc.c:928-960)
-LZ_FN inline void len_encode(Enc *e, RcW &w, LenProbs *lp, uint32_t sym, uint32_t posState)
+LZ_INL void len_encode(Enc *e, RcW &w, LenProbs *lp, uint32_t sym, uint32_t posState)
 {
 	Prob *probs = lp->low;
 	if (sym >= kLenLow) {
@@ -752,12 +758,12 @@ LZ_FN inline uint32_t mf_get_matches(Enc *e, uint32_t *d)
 	if (e->preRec) { // the data-parallel pre-pass already produced this position's list
 		const uint32_t i0 = e->pos - 1;
 #if defined(__CUDA_ARCH__)
-		if (e->lkTag) { // staged in shared memory by the look-ahead warp?  (the same word for every lane)
+		if (e->lkOn) { // staged in shared memory by the look-ahead warp?  (the same word for every lane)
 			const uint32_t slot = e->pos & (kLkSlots - 1);
-			if (*(const volatile uint32_t *)(e->lkTag + slot) == e->pos) {
+			if (*(const volatile uint32_t *)&e->lkHead[slot][0] == e->pos) {
 				__threadfence_block();
-				const uint32_t *b = e->lkData + slot * kLkWords;
-				const uint32_t nd = b[0] & 0xFFFFu; // the length of the last pair sits above
+				const uint32_t *b = e->lkRing + slot * kLkWords;
+				const uint32_t nd = *(const volatile uint32_t *)&e->lkHead[slot][1] & 0xFFFFu; // the longest length sits above
 				lz_sync();
 				LZ_PFOR(i, nd)
 					d[i] = b[1 + i];
@@ -1033,6 +1039,7 @@ __device__ __forceinline__ void opt_step_staged(Enc *e, const uint32_t *b, uint3
 	Opt *curOpt = &e->opt[cur], *nextOpt = curOpt + 1;
 	const uint4 c0 = *reinterpret_cast<const uint4 *>(curOpt); // price, state | extra << 16, len, dist
 	const uint4 n0 = *reinterpret_cast<const uint4 *>(nextOpt);
+	LZ_T(15);
 	// what ReadMatchDistances leaves behind
 	e->additionalOffset++;
 	e->numAvail = e->n - (pos - 1);
@@ -1189,7 +1196,7 @@ __device__ __forceinline__ void opt_step_staged(Enc *e, const uint32_t *b, uint3
 	// REP
 	for (uint32_t rm = repMask; rm; rm &= rm - 1) {
 		const uint32_t repIndex = lz_ffs(rm) - 1;
-		const uint8_t *data2 = data - reps[repIndex];
+		const uint8_t *data2 = data - pick4(reps, repIndex);
 		const uint32_t f = (eq >> (8 * repIndex)) & 0xFFu, nf = ~f & 0xFFu;
 		uint32_t len = nf ? lz_ffs(nf) - 1 : 8; // equal leading bytes among the first eight; numAvail = fb
 		if (len > fb)
@@ -1275,6 +1282,7 @@ __device__ __forceinline__ void opt_step_staged(Enc *e, const uint32_t *b, uint3
 		LZ_T(9);
 	}
 	lz_sync();
+	LZ_T(16);
 }
 #endif
 
@@ -1319,23 +1327,25 @@ LZ_FN inline uint32_t get_optimum(Enc *e, uint32_t position)
 		}
 		lz_sync();
 		repMaxIndex = 0;
-		for (i = 0; i < kNumReps; i++) {
+		uint32_t repMaxLen = 0; // repLens[repMaxIndex]
+		for (i = 0; i < kNumReps; i++)
 			repLens[i] = 0;
-			if (e->xRepLen[i] == 0)
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+		for (i = 0; i < kNumReps; i++) {
+			if (e->xRepLen[i] == 0 || repMaxLen == kMatchMax) // a rep of the maximum length is returned right away
 				continue;
 			const uint32_t len = lz_extend(data - reps[i], data, 2, numAvail);
 			repLens[i] = len;
-			if (len > repLens[repMaxIndex])
+			if (len > repMaxLen) {
 				repMaxIndex = i;
-			if (len == kMatchMax) {
-				for (uint32_t j = i + 1; j < kNumReps; j++)
-					repLens[j] = 0; // not read: this rep is >= fb and is returned right away
-				break;
+				repMaxLen = len;
 			}
 		}
-		if (repLens[repMaxIndex] >= fb) {
+		if (repMaxLen >= fb) {
 			e->backRes = repMaxIndex;
-			const uint32_t len = repLens[repMaxIndex];
+			const uint32_t len = repMaxLen;
 			move_pos(e, len - 1);
 			LZ_T(11);
 			return len;
@@ -1347,7 +1357,7 @@ LZ_FN inline uint32_t get_optimum(Enc *e, uint32_t position)
 			return mainLen;
 		}
 		const uint8_t curByte = *data, matchByte = *(data - reps[0]);
-		last = repLens[repMaxIndex];
+		last = repMaxLen;
 		if (last <= mainLen)
 			last = mainLen;
 		if (last < 2 && curByte != matchByte) {
@@ -1383,6 +1393,9 @@ LZ_FN inline uint32_t get_optimum(Enc *e, uint32_t position)
 		for (i = 0; i < kNumReps; i++)
 			e->opt[0].reps[i] = reps[i];
 
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
 		for (i = 0; i < kNumReps; i++) { // REP
 			const uint32_t repLen = repLens[i];
 			if (repLen < 2)
@@ -1404,7 +1417,7 @@ LZ_FN inline uint32_t get_optimum(Enc *e, uint32_t position)
 	}
 #if defined(__CUDA_ARCH__)
 	// loop invariants the compiler cannot keep in registers by itself (every store into *e may alias them)
-	const uint32_t *const lkTag = e->lkTag, *const lkData = e->lkData;
+	const bool lkOn = e->lkOn != 0;
 	const uint32_t nAll = e->n, pbMask = e->pbMask;
 	const uint8_t *const srcAll = e->src;
 #endif
@@ -1431,10 +1444,11 @@ LZ_FN inline uint32_t get_optimum(Enc *e, uint32_t position)
 			break;
 		}
 #if defined(__CUDA_ARCH__)
-		if (lkTag) {
+		LZ_T(19);
+		if (lkOn) {
 			// every iteration reads exactly one position: the finder stands two past `position` (1-based)
 			const uint32_t pos = position + 2, slot = pos & (kLkSlots - 1);
-			const uint32_t *b = lkData + slot * kLkWords;
+			const uint32_t *b = e->lkRing + slot * kLkWords;
 			const uint32_t availReal = nAll - (pos - 1);
 			uint32_t naf = kNumOpts - 1 - cur; // numAvailFull
 			if (naf > availReal)
@@ -1443,23 +1457,18 @@ LZ_FN inline uint32_t get_optimum(Enc *e, uint32_t position)
 			if (e->pos != pos)
 				e->profN[20]++;
 #endif
-			if (naf >= fb && naf >= 8 && lz_ld_acquire(lkTag + slot) == pos) {
-				const uint32_t hdr = b[0];
+			// one 8-byte load: the tag and the header the helper stored together after its fence; the entry's words
+			// are read after it (shared-memory loads of one warp are served in order)
+			const uint64_t head = *reinterpret_cast<const volatile uint64_t *>(&e->lkHead[slot][0]);
+			const uint32_t hdr = (uint32_t)(head >> 32);
+			if (naf >= fb && naf >= 8 && (uint32_t)head == pos) {
 				if ((hdr & 0xFFFFu) <= 64 && (hdr >> 16) < fb) {
-#if defined(LZ_PROF)
-					e->profN[14]++;
-#endif
+					LZ_T(14);
 					opt_step_staged(e, b, hdr, pos, naf, cur, last, position, reps, srcAll, pbMask, fb);
 					continue;
 				}
-#if defined(LZ_PROF)
-				e->profN[15]++;
-#endif
 			}
-#if defined(LZ_PROF)
-			else
-				e->profN[16]++;
-#endif
+
 		}
 #endif
 		newLen = read_matches(e, &numPairs);
@@ -1555,7 +1564,7 @@ LZ_FN inline uint32_t get_optimum(Enc *e, uint32_t position)
 				if (e->lkSlot >= 0 && !clipped) {
 					// the look-ahead warp compared the bytes already, up to min(len + 1 + fb, numAvail): its end,
 					// cut at this position's own limit, is where the loop below would stop
-					const uint32_t w = e->lkData[(uint32_t)e->lkSlot * kLkWords + 1 + kLkMaxList + k];
+					const uint32_t w = e->lkRing[(uint32_t)e->lkSlot * kLkWords + 1 + kLkMaxList + k];
 					if ((w >> 31) && len2 <= limit) {
 						const uint32_t end = (w & 0x7FFFFFFFu) < limit ? (w & 0x7FFFFFFFu) : limit;
 						res = end - len;
@@ -1636,7 +1645,7 @@ LZ_FN inline uint32_t get_optimum(Enc *e, uint32_t position)
 		for (uint32_t repIndex = 0; repIndex < kNumReps; repIndex++) {
 			if (e->xRepLen[repIndex] == 0)
 				continue;
-			const uint8_t *data2 = data - reps[repIndex];
+			const uint8_t *data2 = data - pick4(reps, repIndex);
 			const uint32_t len = lz_extend(data2, data, 2, numAvail);
 			if (last < cur + len)
 				last = cur + len;
@@ -1910,13 +1919,11 @@ LZ_FN inline void enc_init(Enc *e, const Config &c, const uint8_t *src, uint32_t
 	e->prePool = nullptr;
 	e->gateState = nullptr;
 	e->aborted = 0;
-	e->lkTag = nullptr;
-	e->lkData = nullptr;
+	e->lkOn = e->rcOn = 0;
 	e->lkSlot = -1;
-	e->rcQ = nullptr;
 	e->rcTail = 0;
-	e->rcTailPub = e->rcHeadPub = nullptr;
-	e->rcDone = nullptr;
+	e->rcTailPub = e->rcHeadPub = 0;
+	e->rcDone = 0;
 	e->hash2 = hash2;
 	e->hash3 = hash3;
 	e->hash4 = hash4;
@@ -1994,11 +2001,10 @@ LZ_FN inline uint64_t enc_run(Enc *e)
 {
 	uint32_t nowPos = 0;
 	RcW w;
-	w.p = nullptr;
-	w.v = w.cnt = 0;
+	w.off = w.v = w.cnt = 0;
 	w.on = false;
 #if defined(__CUDA_ARCH__)
-	w.on = e->rcQ != nullptr;
+	w.on = e->rcOn != 0;
 #endif
 	if (e->n == 0) {
 		for (int i = 0; i < 5; i++)
@@ -2035,7 +2041,7 @@ LZ_FN inline uint64_t enc_run(Enc *e)
 			uint32_t dist = e->backRes;
 			Prob *pm = &e->isMatch[e->state][posState];
 #if defined(__CUDA_ARCH__)
-			if (e->rcQ)
+			if (w.on)
 				rcq_reserve(e);
 #endif
 			LZ_T(17);
@@ -2141,11 +2147,11 @@ LZ_FN inline uint64_t enc_run(Enc *e)
 		}
 	}
 #if defined(__CUDA_ARCH__)
-	if (e->rcQ) { // the coder thread flushes (RangeEnc_FlushData) and reports the length
+	if (w.on) { // the coder thread flushes (RangeEnc_FlushData) and reports the length
 		rcq_reserve(e);
 		rcq_push(e, kRcFlush);
 		rcq_publish(e);
-		while (*(volatile int *)e->rcDone == 0)
+		while (*(volatile int *)&e->rcDone == 0)
 			__nanosleep(200);
 		__threadfence_block();
 		return *(volatile uint64_t *)&e->outPos;
