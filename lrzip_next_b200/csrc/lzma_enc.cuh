@@ -1995,6 +1995,173 @@ LZ_FN inline void enc_init(Enc *e, const Config &c, const uint8_t *src, uint32_t
 	len_update_prices(e, &e->repLenPrices, 1u << c.pb, &e->repLenProbs);
 }
 
+#if defined(__CUDA_ARCH__)
+// ---- one symbol, its binary decisions in closed form, one per lane (device, queue mode) ----------------------
+// Every decision of a symbol (which probability, which bit) follows from the symbol alone: decision i of a bit
+// tree uses the node reached by the i bits above it.  Lane j therefore works out decision j by itself instead of all
+// lanes walking the coder's loops; rcw_commit then applies the probability updates and queues the entries.
+LZ_INL uint32_t enc_off(const Enc *e, const void *p) { return (uint32_t)(reinterpret_cast<const char *>(p) - reinterpret_cast<const char *>(e)); }
+
+// decision j (0-based) of the 8-bit tree `probs` for symbol s (LitEnc_Encode, LzmaEnc.c:780-798)
+LZ_INL void sym_tree8(const Enc *e, const Prob *probs, uint32_t s, uint32_t j, uint32_t &off, uint32_t &v)
+{
+	off = enc_off(e, probs + ((0x100u | s) >> (8 - j)));
+	v = (s >> (7 - j)) & 1u;
+}
+
+// number of decisions of LenEnc_Encode for sym = len - 2 (LzmaEnc.c:928-960)
+LZ_INL uint32_t sym_len_count(uint32_t sym) { return sym < kLenLow ? 4u : (sym < 2 * kLenLow ? 5u : 10u); }
+
+LZ_INL void sym_len(const Enc *e, const LenProbs *lp, uint32_t sym, uint32_t posState, uint32_t j, uint32_t &off, uint32_t &v)
+{
+	const Prob *low = lp->low;
+	if (sym >= 2 * kLenLow) { // choice 1, choice2 1, eight bits of the high tree
+		if (j < 2) {
+			off = enc_off(e, low + (j ? kLenLow : 0));
+			v = 1;
+		} else
+			sym_tree8(e, lp->high, sym - 2 * kLenLow, j - 2, off, v);
+		return;
+	}
+	const uint32_t mid = sym >= kLenLow ? 1u : 0u; // choice (1), choice2 0 in front of a 3-bit tree / choice 0
+	if (j <= mid) {
+		off = enc_off(e, low + (j ? kLenLow : 0));
+		v = j < mid ? 1u : 0u;
+		return;
+	}
+	const uint32_t s3 = sym - (mid ? kLenLow : 0), d = j - mid - 1; // depth 0..2
+	const Prob *probs = low + (mid ? kLenLow : 0) + (posState << 4);
+	off = enc_off(e, probs + ((8u | s3) >> (3 - d)));
+	v = (s3 >> (2 - d)) & 1u;
+}
+
+// The whole symbol (len, dist as GetOptimum returns them: dist = kMarkLit literal, < kNumReps rep, else distance + 4).
+// Leaves lane j's decision in w and the decision count in w.cnt; updates state, reps and the counters exactly as the
+// serial coder below does.
+LZ_INL void enc_symbol_warp(Enc *e, RcW &w, uint32_t nowPos, uint32_t len, uint32_t dist)
+{
+	const uint32_t j = lz_lane(), posState = nowPos & e->pbMask, state = e->state;
+	uint32_t off = 0, v = 0, cnt;
+	if (dist == kMarkLit) {
+		const uint8_t *data = mf_cur(e) - e->additionalOffset;
+		const uint32_t cur = *data, prevByte = *(data - 1);
+		const Prob *probs = lit_probs(e, nowPos, prevByte);
+		cnt = 9;
+		if (j == 0) {
+			off = enc_off(e, &e->isMatch[state][posState]);
+			v = 0;
+		} else if (j < 9) {
+			const uint32_t i = j - 1;
+			if (is_lit_state(state))
+				sym_tree8(e, probs, cur, i, off, v);
+			else { // LitEnc_MatchedEncode (LzmaEnc.c:800-826): the match byte's bit picks the half while the bits above agree
+				const uint32_t mb = *(data - e->reps[0]);
+				const uint32_t offs = (((mb ^ cur) >> (8 - i)) == 0) ? 0x100u : 0u;
+				const uint32_t mbit = ((mb >> (7 - i)) & 1u) << 8;
+				off = enc_off(e, probs + (offs + (mbit & offs) + ((0x100u | cur) >> (8 - i))));
+				v = (cur >> (7 - i)) & 1u;
+			}
+		}
+		e->state = st_lit(state);
+	} else if (dist < kNumReps) {
+		// header: isMatch 1, isRep 1, isRepG0 ..., (isRep0Long | isRepG1, isRepG2)
+		const uint32_t nh = dist == 0 ? 4u : (dist == 1 ? 4u : 5u);
+		const uint32_t nl = len != 1 ? sym_len_count(len - kMatchMin) : 0u;
+		cnt = nh + nl;
+		if (j == 0) {
+			off = enc_off(e, &e->isMatch[state][posState]);
+			v = 1;
+		} else if (j == 1) {
+			off = enc_off(e, &e->isRep[state]);
+			v = 1;
+		} else if (j == 2) {
+			off = enc_off(e, &e->isRepG0[state]);
+			v = dist == 0 ? 0u : 1u;
+		} else if (j == 3) {
+			if (dist == 0) {
+				off = enc_off(e, &e->isRep0Long[state][posState]);
+				v = len != 1 ? 1u : 0u;
+			} else {
+				off = enc_off(e, &e->isRepG1[state]);
+				v = dist == 1 ? 0u : 1u;
+			}
+		} else if (j == 4 && dist >= 2) {
+			off = enc_off(e, &e->isRepG2[state]);
+			v = dist - 2;
+		} else if (j < cnt)
+			sym_len(e, &e->repLenProbs, len - kMatchMin, posState, j - nh, off, v);
+		if (dist != 0) {
+			const uint32_t r0 = e->reps[0], r1 = e->reps[1], r2 = e->reps[2], r3 = e->reps[3];
+			const uint32_t d = dist == 1 ? r1 : (dist == 2 ? r2 : r3);
+			if (dist == 3)
+				e->reps[3] = r2;
+			if (dist >= 2)
+				e->reps[2] = r1;
+			e->reps[1] = r0;
+			e->reps[0] = d;
+		}
+		if (len == 1)
+			e->state = st_shortrep(state);
+		else {
+			--e->repLenCounter;
+			e->state = st_rep(state);
+		}
+	} else {
+		const uint32_t d = dist - kNumReps, slot = pos_slot(d), nl = sym_len_count(len - kMatchMin);
+		const uint32_t footer = (slot >> 1) - 1; // meaningful for d >= kStartPosModel
+		const uint32_t nf = d < kStartPosModel ? 0u : (d < kNumFullDist ? footer : 1u + kNumAlignBits);
+		const uint32_t slotBase = 2 + nl, footBase = slotBase + 6;
+		cnt = footBase + nf;
+		if (j == 0) {
+			off = enc_off(e, &e->isMatch[state][posState]);
+			v = 1;
+		} else if (j == 1) {
+			off = enc_off(e, &e->isRep[state]);
+			v = 0;
+		} else if (j < slotBase)
+			sym_len(e, &e->lenProbs, len - kMatchMin, posState, j - 2, off, v);
+		else if (j < footBase) { // the slot's six bits, most significant first
+			const uint32_t i = j - slotBase;
+			const Prob *probs = e->posSlot[len < kNumLenToPos + 1 ? len - 2 : kNumLenToPos - 1];
+			off = enc_off(e, probs + ((64u | slot) >> (6 - i)));
+			v = (slot >> (5 - i)) & 1u;
+		} else if (j < cnt) {
+			uint32_t i = j - footBase;
+			const Prob *probs;
+			uint32_t sym = d;
+			bool direct = false;
+			if (d < kNumFullDist) // reverse bit tree over the footer bits
+				probs = e->posEnc + ((2u | (slot & 1u)) << footer);
+			else if (i == 0) {
+				direct = true;
+				probs = nullptr;
+			} else { // the four align bits, reverse tree
+				i--;
+				probs = e->posAlign;
+				sym = d & kAlignMask;
+			}
+			if (direct) {
+				off = 0;
+				v = kRcDirect | ((footer - kNumAlignBits) << 26) | ((d & ((1u << footer) - 1)) >> kNumAlignBits);
+			} else {
+				const uint32_t m = (1u << i) | (i ? (__brev(sym) >> (32 - i)) : 0u); // 1, then the i lower bits, lowest first
+				off = enc_off(e, probs + m);
+				v = (sym >> i) & 1u;
+			}
+		}
+		e->state = st_match(state);
+		e->reps[3] = e->reps[2];
+		e->reps[2] = e->reps[1];
+		e->reps[1] = e->reps[0];
+		e->reps[0] = d + 1;
+		e->matchPriceCount++;
+	}
+	w.off = off;
+	w.v = v;
+	w.cnt = cnt;
+}
+#endif
+
 // LzmaEnc_CodeOneBlock (LzmaEnc.c:2383-2680) run to the end of the block, then Flush (:2191-2200).
 // Returns the number of output bytes (valid when !e->overflow).
 LZ_FN inline uint64_t enc_run(Enc *e)
@@ -2045,6 +2212,11 @@ LZ_FN inline uint64_t enc_run(Enc *e)
 				rcq_reserve(e);
 #endif
 			LZ_T(17);
+#if defined(__CUDA_ARCH__)
+			if (w.on)
+				enc_symbol_warp(e, w, nowPos, len, dist);
+			else
+#endif
 			if (dist == kMarkLit) {
 				rc_bit(e, w, pm, 0);
 				const uint8_t *data = mf_cur(e) - e->additionalOffset;
