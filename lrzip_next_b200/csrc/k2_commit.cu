@@ -210,6 +210,17 @@ struct WarpPrim {
 			pos = c.x;
 			tag = c.y;
 		}
+		{
+			// The list is consumed front to back and, at a tight gate, a refill scans dozens of windows for a handful
+			// of keepers: pull the 8 KB behind this window towards L1 (a line per lane, twice) so that those windows
+			// do not each wait for L2 / HBM.
+			const Cand *pa = cand + tile * (int64_t)kTile + idx + 32 + lane * 8;
+			const Cand *lim = cand + num_tiles * (int64_t)kTile;
+			if (pa < lim)
+				asm volatile("prefetch.global.L1 [%0];" ::"l"(pa));
+			if (pa + 256 < lim)
+				asm volatile("prefetch.global.L1 [%0];" ::"l"(pa + 256));
+		}
 		idx += 32;
 		return true;
 	}
@@ -1259,6 +1270,13 @@ __device__ void k2_commit_segment_batched(WarpPrim &prim, FastShared *sh, ScanSt
 			__syncwarp();
 			if (found)
 				dmax = sh->dslot[found - 1];
+			{ // the sweep moves on from here in the next rounds: have the following 512 slots on their way
+				const int64_t k0 = (found ? (int64_t)dmax : r.clean_ptr) + 128 + lane * 8;
+				if (k0 < tsize)
+					prefetch_l1(prim.tab + k0);
+				if (k0 + 256 < tsize)
+					prefetch_l1(prim.tab + k0 + 256);
+			}
 		}
 		// flags of one lane after an evaluation: `stopper` = must go through the serial step
 		bool stopper = false;
@@ -1508,6 +1526,8 @@ k2_commit_kernel(const uint8_t *__restrict__ buf, ScanState *st, HEntry *tab, co
 	k2_bar(K2_BAR_GO); // releases the workers
 }
 
+static constexpr int kK2ReserveSmem = 64 * 1024;
+
 int k2_launch(const uint8_t *d_buf, ScanState *d_state, HEntry *d_tab, const Cand *d_cand,
 	      const uint32_t *d_tile_count, int64_t pos_lo, int64_t pos_hi, MatchRec *d_recs, bool last_segment,
 	      int nvar, int64_t tab_stride, int64_t rec_stride, cudaStream_t stream)
@@ -1517,7 +1537,10 @@ int k2_launch(const uint8_t *d_buf, ScanState *d_state, HEntry *d_tab, const Can
 		first_tile = pos_lo / kTile;
 		num_tiles = (pos_hi - 1) / kTile - first_tile + 1;
 	}
-	k2_commit_kernel<<<nvar, K2_THREADS, 0, stream>>>(d_buf, d_state, d_tab, d_cand, d_tile_count, first_tile, num_tiles,
+	// The commit CTA lives on L1: probe chains, candidate windows and the list are prefetched into it ahead of
+	// their use.  A block encoder (K7b: ~200 KB of shared memory) landing on the same SM would shrink that L1 to a
+	// fifth, so the commit CTA claims enough shared memory that no encoder CTA fits beside it.
+	k2_commit_kernel<<<nvar, K2_THREADS, kK2ReserveSmem, stream>>>(d_buf, d_state, d_tab, d_cand, d_tile_count, first_tile, num_tiles,
 							  pos_hi, d_recs, last_segment ? 1 : 0, tab_stride, rec_stride);
 	return cudaGetLastError() == cudaSuccess ? 0 : -1;
 }
@@ -1529,6 +1552,7 @@ int k2_preload()
 	cudaFuncAttributes a;
 	bool ok = true;
 	ok = ok && cudaFuncGetAttributes(&a, k2_commit_kernel) == cudaSuccess;
+	ok = ok && cudaFuncSetAttribute(k2_commit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kK2ReserveSmem) == cudaSuccess;
 	return ok ? 0 : -1;
 }
 
