@@ -222,6 +222,11 @@ __device__ void lzma_lookahead_warp(lzma::Enc *e, const LzmaJob &j, const volati
 			uint32_t *b = lkData + (q & (lzma::kLkSlots - 1)) * lzma::kLkWords;
 			const uint32_t numAvail = n - i0; // what ReadMatchDistances will see at this position
 			const uint8_t *data = src + i0;
+			if (sub < lzma::kNumReps) { // the bytes behind the reps, as they stand now (they seldom change from one cell to the next)
+				const uint32_t r = *(const volatile uint32_t *)&e->pubReps[sub];
+				if (r <= i0)
+					lzma::lz_prefetch(data - r);
+			}
 			for (uint32_t k = sub; 2 * k < nd; k += 8) {
 				const uint32_t len = lst[2 * k], dist = lst[2 * k + 1];
 				uint32_t w = 0;

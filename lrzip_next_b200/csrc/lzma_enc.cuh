@@ -207,6 +207,7 @@ struct Enc {
 #endif
 	// The helpers' structures live inside the encoder so that the encoder warp reaches them with plain shared-memory
 	// loads (through a pointer kept in the struct they become generic loads, which cost three times as much).
+	alignas(16) uint32_t pubReps[kNumReps]; // the reps of the cell the parser is at: the look-ahead warp prefetches behind them
 	alignas(8) uint32_t lkHead[kLkSlots][2]; // {position (1-based, as e->pos) the entry holds, count | longest length << 16}
 	uint32_t lkRing[kLkSlots * kLkWords];
 	uint32_t rcQueue[kRcQ];
@@ -1093,6 +1094,7 @@ __device__ __forceinline__ void opt_step_staged(Enc *e, const uint32_t *b, uint3
 	}
 	curOpt->state = (uint16_t)state;
 	*reinterpret_cast<uint4 *>(curOpt->reps) = make_uint4(reps[0], reps[1], reps[2], reps[3]);
+	*reinterpret_cast<uint4 *>(e->pubReps) = make_uint4(reps[0], reps[1], reps[2], reps[3]);
 	LZ_T(3);
 
 	// ---- bytes from far back, all in flight at once: group g compares the first eight bytes of rep g
@@ -1921,6 +1923,8 @@ LZ_FN inline void enc_init(Enc *e, const Config &c, const uint8_t *src, uint32_t
 	e->aborted = 0;
 	e->lkOn = e->rcOn = 0;
 	e->lkSlot = -1;
+	for (uint32_t i = 0; i < kNumReps; i++)
+		e->pubReps[i] = 1;
 	e->rcTail = 0;
 	e->rcTailPub = e->rcHeadPub = 0;
 	e->rcDone = 0;
