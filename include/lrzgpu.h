@@ -53,6 +53,13 @@ enum {
 /* c_type byte of a block header, src/include/lrzip_private.h:287-295 */
 enum { LRZGPU_CTYPE_NONE = 3, LRZGPU_CTYPE_LZMA = 6, LRZGPU_CTYPE_ZSTD = 10 };
 
+/* pre-compression filter of the stream-1 blocks (control->filter_flag, src/include/lrzip_private.h:389-397;
+ * applied in compthread, src/stream.c:1587-1628).  ARMT, IA64 and RISCV are not built: LRZGPU_EUNSUPPORTED. */
+enum {
+	LRZGPU_FILTER_NONE = 0, LRZGPU_FILTER_X86 = 1, LRZGPU_FILTER_ARM = 2, LRZGPU_FILTER_ARMT = 3, LRZGPU_FILTER_PPC = 4,
+	LRZGPU_FILTER_SPARC = 5, LRZGPU_FILTER_IA64 = 6, LRZGPU_FILTER_ARM64 = 7, LRZGPU_FILTER_RISCV = 8, LRZGPU_FILTER_DELTA = 128
+};
+
 /* backend selector (the reference's FLAG_NO_COMPRESS / default lzma / FLAG_ZSTD_COMPRESS) */
 enum { LRZGPU_BACKEND_NONE = 0, LRZGPU_BACKEND_LZMA = 1, LRZGPU_BACKEND_ZSTD = 4 };
 
@@ -70,6 +77,8 @@ typedef struct lrzgpu_params {
 	int threshold;    /* lz4 gate: 0 = off (-T), else percent (default 100) */
 	int nobemt;       /* --nobemt: with LZMA level >= 5 and threads > 1 the reference switches to the single-threaded
 			     bt4 finder (src/stream.c:456); not reproduced => LRZGPU_EUNSUPPORTED */
+	int filter;       /* LRZGPU_FILTER_* (--x86 --arm --arm64 --ppc --sparc --delta), 0 = none */
+	int delta;        /* --delta: the distance in bytes, 1..16 or a multiple of 16 up to 256 (control->delta) */
 } lrzgpu_params;
 
 typedef struct lrzgpu_sizing_t {

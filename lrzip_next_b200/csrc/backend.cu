@@ -85,6 +85,8 @@ struct LzmaJob {
 	lzma::Config cfg;
 	int threshold;          // lz4 gate (lz4_compresses, src/stream.c:2325-2380): 0 = off
 	const int *mf_overflow; // the match finder ran out of pool for this block: encode it again with a larger one
+	uint32_t wait_count;    // > 0: the tree walk runs beside this kernel; records [0, wait_count) carry a "final" bit
+	uint64_t pool_cap;      // uint32 in the pool (a record of an overflowed walk may point past it)
 	uint64_t outLen;
 	int overflow;
 	int skipped;            // 1: gate said incompressible, 2: match-list pool overflow, 3: zstd frame not smaller
@@ -200,6 +202,7 @@ __device__ void lzma_lookahead_warp(lzma::Enc *e, const LzmaJob &j, const volati
 	const volatile uint32_t *ppos = &e->pos;
 	const uint8_t *src = j.src;
 	const uint32_t n = j.n, fb = j.cfg.fb;
+	const bool live = j.wait_count != 0;
 	uint32_t upto = 0; // positions <= upto (1-based, like e->pos) are already staged
 	while (!*done) {
 		const uint32_t pos = *ppos;
@@ -213,9 +216,25 @@ __device__ void lzma_lookahead_warp(lzma::Enc *e, const LzmaJob &j, const volati
 			hi = lo + 3;
 		// four positions in flight, eight lanes each: the dependent far loads (record -> list -> bytes) of the four overlap
 		const uint32_t q = lo + grp;
+		uint64_t rec = 0;
+		bool ready = true;
 		if (q <= hi) {
+			if (live) { // the tree walk may not have reached this position yet
+				if (q - 1 < j.wait_count) {
+					rec = *(const volatile uint64_t *)(j.rec + (q - 1));
+					ready = (rec >> 63) != 0;
+				}
+			} else
+				rec = j.rec[q - 1];
+			rec &= ~lzma::kMfReady;
+		}
+		if (!__all_sync(0xffffffffu, ready)) {
+			__nanosleep(200);
+			continue;
+		}
+		const bool usable = q <= hi && (!live || (rec >> 10) + ((uint32_t)rec & 1023u) <= j.pool_cap);
+		if (usable) {
 			const uint32_t i0 = q - 1;
-			const uint64_t rec = j.rec[i0];
 			const uint32_t nd = (uint32_t)rec & 1023u;
 			const uint32_t *lst = j.pool + (rec >> 10);
 			const bool stage = nd <= lzma::kLkMaxList;
@@ -228,7 +247,8 @@ __device__ void lzma_lookahead_warp(lzma::Enc *e, const LzmaJob &j, const volati
 					lzma::lz_prefetch(data - r);
 			}
 			for (uint32_t k = sub; 2 * k < nd; k += 8) {
-				const uint32_t len = lst[2 * k], dist = lst[2 * k + 1];
+				// (beside a running walk the pool is read past L1: a cached line may predate a neighbouring list)
+				const uint32_t len = live ? __ldcg(lst + 2 * k) : lst[2 * k], dist = live ? __ldcg(lst + 2 * k + 1) : lst[2 * k + 1];
 				uint32_t w = 0;
 				if (dist < i0) {
 					const uint8_t *data2 = data - dist - 1;
@@ -247,7 +267,7 @@ __device__ void lzma_lookahead_warp(lzma::Enc *e, const LzmaJob &j, const volati
 					b[2 + 2 * k] = dist;
 					b[1 + lzma::kLkMaxList + k] = w;
 					// distance by length: this pair serves the lengths above the previous pair's up to its own
-					uint32_t from = k ? lst[2 * k - 2] + 1 : 2;
+					uint32_t from = k ? (live ? __ldcg(lst + 2 * k - 2) : lst[2 * k - 2]) + 1 : 2;
 					for (; from <= len && from <= lzma::kMatchMax; from++)
 						b[lzma::kLkByLen + from] = dist;
 				}
@@ -256,11 +276,11 @@ __device__ void lzma_lookahead_warp(lzma::Enc *e, const LzmaJob &j, const volati
 		__syncwarp();
 		__threadfence_block();
 		__syncwarp();
-		if (q <= hi && sub == 0) {
-			const uint64_t rec = j.rec[q - 1];
+		if (usable && sub == 0) {
 			const uint32_t nd = (uint32_t)rec & 1023u;
 			if (nd <= lzma::kLkMaxList) { // position, count and the longest length (ReadMatchDistances' result) in one store
-				const uint32_t hdr = nd | ((nd ? j.pool[(rec >> 10) + nd - 2] : 0u) << 16);
+				const uint32_t *lp = j.pool + (rec >> 10) + nd - 2;
+				const uint32_t hdr = nd | ((nd ? (live ? __ldcg(lp) : *lp) : 0u) << 16);
 				*reinterpret_cast<volatile uint64_t *>(&e->lkHead[q & (lzma::kLkSlots - 1)][0]) = (uint64_t)q | ((uint64_t)hdr << 32);
 			}
 		}
@@ -342,6 +362,9 @@ __global__ void __launch_bounds__(128, 1) lzma_block_kernel(LzmaJob *jobs)
 		lzma::enc_init(e, j.cfg, j.src, j.n, j.out, j.outCap, nullptr, nullptr, nullptr, nullptr);
 		e->preRec = j.rec;
 		e->prePool = j.pool;
+		e->preWait = j.wait_count;
+		e->prePoolCap = j.pool_cap;
+		e->mfOverflow = j.wait_count ? j.mf_overflow : nullptr;
 		e->gateState = j.threshold ? &gate_state : nullptr;
 		e->lkOn = e->rcOn = 1;
 	}
@@ -395,7 +418,7 @@ __global__ void __launch_bounds__(128, 1) lzma_block_kernel(LzmaJob *jobs)
 		done = 1;
 		j.outLen = len;
 		j.overflow = *(volatile int *)&e->overflow;
-		j.skipped = verdict == 2 ? 1 : 0;
+		j.skipped = verdict == 2 ? 1 : (*(volatile int *)&e->aborted == 2 ? 2 : 0);
 	}
 }
 
@@ -454,6 +477,8 @@ struct AsyncGroup {
 	size_t first = 0, count = 0; // subs[first .. first + count)
 	size_t meta_off = 0;         // [LzmaJob x m][MfBlock x m][segBase x (m + 1)][GateJob x m] in BackendCtx::meta
 	cudaStream_t ps = nullptr;   // parser stream
+	cudaStream_t ws = nullptr;   // tree-walk stream (LZMA levels 5-9: the walk runs beside the parser)
+	cudaEvent_t evWalk = nullptr;
 	cudaEvent_t evMF = nullptr, evDone = nullptr; // sorts done / parser done
 	uint64_t walk_total = 0;                       // positions of the group (grid of the tree walk)
 	uint32_t max_nzb = 0;                          // zstd: most 128 KiB blocks in one stream block of the group
@@ -464,7 +489,7 @@ struct BackendCtx {
 	DevBuf jobs, work, out, flags, offs, scratch, meta, big, zs_tables;
 	bool zstd = false; // the chunk's backend (else LZMA)
 	cudaStream_t sMF = nullptr, sGate = nullptr;
-	std::vector<cudaStream_t> pstreams;
+	std::vector<cudaStream_t> pstreams, wstreams;
 	std::vector<cudaEvent_t> events;
 	size_t ev_next = 0;
 	// state of the chunk being encoded
@@ -491,6 +516,8 @@ void backend_destroy(BackendCtx *b)
 	for (DevBuf *d : bufs)
 		d->release();
 	for (cudaStream_t s : b->pstreams)
+		cudaStreamDestroy(s);
+	for (cudaStream_t s : b->wstreams)
 		cudaStreamDestroy(s);
 	for (cudaEvent_t e : b->events)
 		cudaEventDestroy(e);
@@ -609,7 +636,13 @@ int backend_async_begin(BackendCtx *b, const lrzgpu_params &p, const lrzgpu_sizi
 			return LRZGPU_ECUDA;
 		b->pstreams.push_back(st);
 	}
-	while (b->events.size() < 2 * want_streams) {
+	while (b->wstreams.size() < want_streams) {
+		cudaStream_t st = nullptr;
+		if (cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking) != cudaSuccess)
+			return LRZGPU_ECUDA;
+		b->wstreams.push_back(st);
+	}
+	while (b->events.size() < 3 * want_streams) {
 		cudaEvent_t ev = nullptr;
 		if (cudaEventCreateWithFlags(&ev, cudaEventDisableTiming) != cudaSuccess)
 			return LRZGPU_ECUDA;
@@ -664,6 +697,18 @@ static int enqueue_group(BackendCtx *b, size_t first, size_t m, const std::vecto
 		b->pstreams.push_back(s);
 	}
 	G.ps = b->pstreams[gi];
+	while (b->wstreams.size() <= gi) {
+		cudaStream_t s = nullptr;
+		if (cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking) != cudaSuccess) {
+			snprintf(err, errlen, "walk stream: %s", cudaGetErrorString(cudaGetLastError()));
+			return LRZGPU_ECUDA;
+		}
+		b->wstreams.push_back(s);
+	}
+	G.ws = b->wstreams[gi];
+	G.evWalk = next_event(b);
+	if (!G.evWalk)
+		return LRZGPU_ECUDA;
 	cudaEvent_t evMF = next_event(b);
 	if (!evMF)
 		return LRZGPU_ECUDA;
@@ -714,6 +759,8 @@ static int enqueue_group(BackendCtx *b, size_t first, size_t m, const std::vecto
 		j.cfg = c;
 		j.threshold = gate ? b->p.threshold : 0;
 		j.mf_overflow = B.overflow;
+		j.pool_cap = B.poolCap;
+		j.wait_count = (!b->zstd && !hc5) ? B.count : 0; // the parser starts beside the tree walk (pump_groups)
 		if (b->zstd) {
 			j.outCap = (uint64_t)round_up_page(bj.u_len, b->p.page_size); // src/stream.c:169
 			j.nzb = (uint32_t)(((uint64_t)bj.u_len + zs::kBlockMax - 1) / zs::kBlockMax);
@@ -795,8 +842,12 @@ static int pump_groups(BackendCtx *b, bool wait, int64_t *launches, char *err, s
 		// groups overlap, and the parser kernel follows it in stream order
 		uint8_t *J = (uint8_t *)b->meta.p + G.meta_off;
 		const size_t o_mb = G.count * sizeof(LzmaJob), o_seg = align_up(o_mb + G.count * sizeof(lzma::MfBlock), 8);
+		// LZMA levels 5-9: the parser does not wait for the walk to end.  A record is final once its bucket's thread
+		// has passed the position, and the slowest bucket needs ~1 s for a block the parser needs ~10 s for, so the
+		// parser (look-ahead warp) only waits for the "final" bit of the records right in front of it.
+		const bool beside = !b->zstd && !G.hc5;
 		if (lzma::mf_walk_launch((const lzma::MfBlock *)(J + o_mb), (int)G.count, (const uint64_t *)(J + o_seg), G.walk_total,
-					 G.hc5, G.ps, launches)) {
+					 G.hc5, beside ? G.ws : G.ps, launches)) {
 			snprintf(err, errlen, "LZMA match finder walk: %s", cudaGetErrorString(cudaGetLastError()));
 			return LRZGPU_ECUDA;
 		}
@@ -815,6 +866,10 @@ static int pump_groups(BackendCtx *b, bool wait, int64_t *launches, char *err, s
 			lzma_block_kernel<<<(unsigned)G.count, 128, sizeof(lzma::Enc), G.ps>>>((LzmaJob *)J);
 			if (launches)
 				(*launches)++;
+			if (beside && (cudaEventRecord(G.evWalk, G.ws) != cudaSuccess || cudaStreamWaitEvent(G.ps, G.evWalk, 0) != cudaSuccess)) {
+				snprintf(err, errlen, "walk event: %s", cudaGetErrorString(cudaGetLastError()));
+				return LRZGPU_ECUDA;
+			}
 		}
 		if (cudaGetLastError() != cudaSuccess || cudaEventRecord(G.evDone, G.ps) != cudaSuccess) {
 			snprintf(err, errlen, "LZMA kernel launch: %s", cudaGetErrorString(cudaGetLastError()));

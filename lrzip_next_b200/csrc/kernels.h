@@ -70,6 +70,13 @@ int unrzip_parse_launch(const uint8_t *d_s0, int64_t s0_len, int cb, int64_t chu
 // literals scattered by all SMs, then the matches in record order by one CTA
 int unrzip_replay_launch(const uint8_t *d_s1, int64_t s1_len, const DecLit *d_lits, int64_t n_lit, const DecMatch *d_matches,
 			 int64_t n_match, uint8_t *d_out, int num_sms, cudaStream_t stream);
+// ---- pre-compression filters of the stream-1 blocks (filters.cu) -----------------------------------
+// Converts in place the stream blocks that make up s[from, to) (from is a multiple of the block size bs); `side` is
+// scratch of filter_side_bytes() bytes (Delta only).
+size_t filter_side_bytes(int filter, int64_t span, int64_t bs);
+int filter_blocks_launch(int filter, int delta, uint8_t *s, int64_t from, int64_t to, int64_t bs, uint8_t *side,
+			 cudaStream_t stream, int64_t *launches);
+int filter_preload();
 size_t lzma_dec_prob_bytes(int njobs);
 int lzma_dec_launch(LzmaDecJob *d_jobs, int njobs, void *d_probs, cudaStream_t stream);
 int unrzip_preload();

@@ -76,6 +76,27 @@ int compute_sizing(const lrzgpu_params &p, int64_t st_size, lrzgpu_sizing_t &o)
 		return LRZGPU_EUNSUPPORTED;
 	if (p.backend != LRZGPU_BACKEND_NONE && p.backend != LRZGPU_BACKEND_LZMA && p.backend != LRZGPU_BACKEND_ZSTD)
 		return LRZGPU_EUNSUPPORTED;
+	// filters (src/main.c:700-755): the Thumb, IA64 and RISC-V converters are not built; --delta takes 1..16 or a
+	// multiple of 16 up to 256
+	switch (p.filter) {
+	case LRZGPU_FILTER_NONE:
+	case LRZGPU_FILTER_X86:
+	case LRZGPU_FILTER_ARM:
+	case LRZGPU_FILTER_PPC:
+	case LRZGPU_FILTER_SPARC:
+	case LRZGPU_FILTER_ARM64:
+		break;
+	case LRZGPU_FILTER_DELTA:
+		if (p.delta < 1 || p.delta > 256 || (p.delta > 16 && p.delta % 16))
+			return LRZGPU_EINVAL;
+		break;
+	case LRZGPU_FILTER_ARMT:
+	case LRZGPU_FILTER_IA64:
+	case LRZGPU_FILTER_RISCV:
+		return LRZGPU_EUNSUPPORTED;
+	default:
+		return LRZGPU_EINVAL;
+	}
 	const bool stored = p.backend == LRZGPU_BACKEND_NONE, lzma = p.backend == LRZGPU_BACKEND_LZMA;
 	const int testbufs = stored ? 1 : 2;
 	const int64_t usable_ram = p.ramsize / 3; // setup_ram, src/util.c:179-188
@@ -181,6 +202,11 @@ void make_magic(uint8_t magic[21], const lrzgpu_params &p, const lrzgpu_sizing_t
 	magic[5] = 14;
 	put_le(magic + 6, st_size, 8);
 	magic[14] = 1; // MD5
+	// filter byte (src/lrzip.c:150-155): the flag, or 128 + the coded delta distance
+	if (p.filter == LRZGPU_FILTER_DELTA)
+		magic[16] = (uint8_t)(128 + (p.delta <= 16 ? p.delta : (p.delta >> 4) + 15));
+	else
+		magic[16] = (uint8_t)p.filter;
 	if (p.backend == LRZGPU_BACKEND_LZMA) {
 		magic[17] = 1;
 		magic[18] = (uint8_t)lzma2_prop_from_dic(sz.dict_size);

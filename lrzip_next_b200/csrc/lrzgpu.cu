@@ -69,7 +69,7 @@ struct lrzgpu_ctx {
 	char err[512] = { 0 };
 	cudaStream_t sA = nullptr, sB = nullptr, sC = nullptr, sD = nullptr, sE = nullptr;
 	cudaEvent_t evK1[2] = { nullptr, nullptr }, evK2[2] = { nullptr, nullptr }, evInit = nullptr, evCrc = nullptr;
-	DevBuf in, tab, state, cand[2], tc[2], recs, s0, s1, crc, w1;
+	DevBuf in, tab, state, cand[2], tc[2], recs, s0, s1, crc, w1, fside;
 	ScanState *h_state = nullptr; // pinned, one per variant of the window being scanned
 	size_t h_state_cap = 0;
 	ScanState *h_snap = nullptr; // pinned, one per segment of a pipelined scan
@@ -400,13 +400,29 @@ int frame_chunk(lrzgpu_ctx *c, const lrzgpu_params &p, int64_t n, int eof, int c
 	return LRZGPU_OK;
 }
 
+// The pre-compression filter of the stream-1 blocks that make up c->s1[from, to), in place (src/stream.c:1587-1628: the
+// first thing a compthread does to its block, whatever the backend).  c->fside must be sized already (Delta).
+int filter_stream1(lrzgpu_ctx *c, const lrzgpu_params &p, const lrzgpu_sizing_t &sz, int64_t from, int64_t to, cudaStream_t st)
+{
+	if (!p.filter || to <= from)
+		return LRZGPU_OK;
+	if (filter_blocks_launch(p.filter, p.delta, (uint8_t *)c->s1.p, from, to, sz.bufsize, (uint8_t *)c->fside.p, st, &c->launches))
+		return fail(c, LRZGPU_ECUDA, "filter launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+	CU(c, cudaStreamSynchronize(st));
+	return LRZGPU_OK;
+}
+
 // Second half of a chunk: stream blocks -> backend -> framed blob, from the streams rzip left in c->s0 / c->s1.
 int finish_chunk_device(lrzgpu_ctx *c, const lrzgpu_params &p, const lrzgpu_sizing_t &sz, int64_t n, int eof, int cb,
 			const ChunkResult &res, OutBuf &out, lrzgpu_stats *stats)
 {
 	const double t0 = now_ms();
 	std::vector<BlockJob> jobs;
-	int rc = plan_chunk_blocks(c, sz, cb, res, jobs);
+	CU(c, c->fside.ensure(filter_side_bytes(p.filter, res.s1_len, sz.bufsize) + 16));
+	int rc = filter_stream1(c, p, sz, 0, res.s1_len, c->sA);
+	if (rc)
+		return rc;
+	rc = plan_chunk_blocks(c, sz, cb, res, jobs);
 	if (rc)
 		return rc;
 	if (p.backend != LRZGPU_BACKEND_NONE) {
@@ -441,6 +457,7 @@ int pipelined_scan(lrzgpu_ctx *c, const lrzgpu_params &p, const lrzgpu_sizing_t 
 	CU(c, c->s1.ensure((size_t)n + 64));
 	CU(c, c->s0.ensure((size_t)s0_max));
 	CU(c, c->w1.ensure((size_t)(s0_max / bs + 2) * 8));
+	CU(c, c->fside.ensure(filter_side_bytes(p.filter, n, bs) + 16));
 	const int64_t max_blocks = n / bs + s0_max / bs + 4;
 	int rc = backend_async_begin(c->backend, p, sz, bs < n ? bs : n, max_blocks, n + s0_max + (1 << 20), c->err, sizeof(c->err));
 	if (rc)
@@ -456,6 +473,8 @@ int pipelined_scan(lrzgpu_ctx *c, const lrzgpu_params &p, const lrzgpu_sizing_t 
 			return fail(c, LRZGPU_ECUDA, "k4 launch: %s", cudaGetErrorString(cudaGetLastError()));
 		c->launches += 1;
 		CU(c, cudaStreamSynchronize(c->sE)); // a millisecond; the backend's streams take no device-side waits
+		if (int frc = filter_stream1(c, p, sz, blk1 * bs, full * bs, c->sE)) // the completed blocks, before anyone reads them
+			return frc;
 		std::vector<BlockJob> jobs((size_t)(full - blk1));
 		for (int64_t k = blk1; k < full; k++) {
 			BlockJob &j = jobs[(size_t)(k - blk1)];
@@ -489,6 +508,9 @@ int pipelined_scan(lrzgpu_ctx *c, const lrzgpu_params &p, const lrzgpu_sizing_t 
 	*victim_round = res_out.st.victim_round;
 	CU(c, cudaStreamSynchronize(c->sE));
 	rc = rzip_emit_device(c, d_chunk, cb, res_out, stats, s1_done);
+	if (rc)
+		return rc;
+	rc = filter_stream1(c, p, sz, blk1 * bs, res_out.s1_len, c->sA); // the blocks the scan did not complete
 	if (rc)
 		return rc;
 	if (bs < 64)
@@ -689,6 +711,7 @@ int lrzgpu_create(int device, lrzgpu_ctx **out)
 		c->h_state_cap = 1;
 	ok = ok && k1_init_tables() == 0 && k4_init_tables() == 0;
 	ok = ok && k1_preload() == 0 && k2_preload() == 0 && k4_preload() == 0 && backend_preload() == 0 && unrzip_preload() == 0;
+	ok = ok && filter_preload() == 0;
 	if (ok) {
 		c->backend = backend_create();
 		ok = c->backend != nullptr;
@@ -709,7 +732,7 @@ void lrzgpu_destroy(lrzgpu_ctx *c)
 	cudaDeviceSynchronize();
 	if (c->backend)
 		backend_destroy(c->backend);
-	DevBuf *bufs[] = { &c->in, &c->tab, &c->state, &c->cand[0], &c->cand[1], &c->tc[0], &c->tc[1], &c->recs, &c->s0, &c->s1,
+	DevBuf *bufs[] = { &c->fside, &c->in, &c->tab, &c->state, &c->cand[0], &c->cand[1], &c->tc[0], &c->tc[1], &c->recs, &c->s0, &c->s1,
 			   &c->crc, &c->w1 };
 	for (DevBuf *b : bufs)
 		b->release();

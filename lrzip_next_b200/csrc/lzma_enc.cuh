@@ -160,6 +160,11 @@ struct Enc {
 	// precomputed match lists (lzma_mf.cu): when preRec is set the serial finder above is not used
 	const uint64_t *preRec;
 	const uint32_t *prePool;
+	// the tree walk may still be running (device pipeline): records [0, preWait) carry a "final" bit to wait for, a
+	// record may point past the pool when the walk ran out of it (mfOverflow is set then and the block is redone)
+	uint32_t preWait;
+	uint64_t prePoolCap;
+	const int *mfOverflow;
 	// lz4 compressibility gate running beside the encoder (device): 0 undecided, 1 compressible, 2 leave the
 	// block stored -- the encoder gives up as soon as it reads 2 (null: no gate)
 	const int *gateState;
@@ -776,16 +781,31 @@ LZ_FN inline uint32_t mf_get_matches(Enc *e, uint32_t *d)
 			e->lkSlot = -1;
 		}
 #endif
-		const uint64_t rec = e->preRec[i0];
-		const uint32_t nd = (uint32_t)rec & 1023u;
+		uint64_t rec;
+		bool live = false; // the walk is (or may be) still writing: no cached loads
+#if defined(__CUDA_ARCH__)
+		if (e->preWait) {
+			live = true;
+			rec = 0;
+			if (i0 < e->preWait)
+				while (!((rec = *(const volatile uint64_t *)(e->preRec + i0)) >> 63))
+					__nanosleep(200);
+		} else
+#endif
+			rec = e->preRec[i0];
+		rec &= ~(1ull << 63);
+		uint32_t nd = (uint32_t)rec & 1023u;
+		if (live && (rec >> 10) + nd > e->prePoolCap)
+			nd = 0; // pool overflow: the block is abandoned at the next symbol
 		const uint32_t *s = e->prePool + (rec >> 10);
-		if (i0 + 6 < e->n) { // lists sit in the pool in bucket order: pull the ones needed next towards L1
-			lz_prefetch(e->prePool + (e->preRec[i0 + 3] >> 10));
-			lz_prefetch(e->preRec + i0 + 6);
-		}
 		lz_sync();
-		LZ_PFOR(i, nd)
+		LZ_PFOR(i, nd) {
+#if defined(__CUDA_ARCH__)
+			d[i] = live ? __ldcg(s + i) : s[i];
+#else
 			d[i] = s[i];
+#endif
+		}
 		lz_sync();
 		e->pos++;
 		return nd;
@@ -1919,6 +1939,9 @@ LZ_FN inline void enc_init(Enc *e, const Config &c, const uint8_t *src, uint32_t
 	e->lpMask = (0x100u << c.lp) - (0x100u >> c.lc);
 	e->preRec = nullptr;
 	e->prePool = nullptr;
+	e->preWait = 0;
+	e->prePoolCap = 0;
+	e->mfOverflow = nullptr;
 	e->gateState = nullptr;
 	e->aborted = 0;
 	e->lkOn = e->rcOn = 0;
@@ -2317,6 +2340,10 @@ LZ_FN inline uint64_t enc_run(Enc *e)
 					break;
 				if (e->gateState && *(const volatile int *)e->gateState == 2) { // the same word for every lane
 					e->aborted = 1;
+					break;
+				}
+				if (e->mfOverflow && *(const volatile int *)e->mfOverflow) { // the match finder ran out of pool under us
+					e->aborted = 2;
 					break;
 				}
 			}

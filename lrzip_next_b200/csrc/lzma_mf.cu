@@ -229,7 +229,10 @@ __global__ void __launch_bounds__(128) mf_walk_kernel(const MfBlock *__restrict_
 			} else
 				*B.overflow = 1;
 		}
-		B.rec[i] = (off << kMfCountBits) | nd;
+		// the block's parser may already be running and waiting for this very record (backend.cu): the list (or the
+		// overflow flag) must be visible before the record that announces it
+		__threadfence();
+		*(volatile uint64_t *)&B.rec[i] = kMfReady | (off << kMfCountBits) | nd;
 		prev = pos;
 		if (++s == count)
 			break;

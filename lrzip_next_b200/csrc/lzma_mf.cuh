@@ -38,6 +38,7 @@ namespace lzma {
 
 constexpr uint32_t kMfCountBits = 10; // per-position record = (pool offset << 10) | number of uint32 (<= 2*273+2)
 constexpr uint32_t kMfCountMask = (1u << kMfCountBits) - 1;
+constexpr uint64_t kMfReady = 1ull << 63; // set by the tree walk when a record is final (readers mask it off)
 
 struct MfParams {
 	uint32_t n;           // block length

@@ -558,7 +558,7 @@ ZS_FN inline void parse_block(const uint8_t *src, uint32_t n, uint32_t lo, uint3
 	auto best_at = [&](uint32_t p, uint32_t &len, uint32_t &dist) {
 		len = 0;
 		dist = 0;
-		const uint64_t r = rec[p];
+		const uint64_t r = rec[p] & ~(1ull << 63); // top bit: the tree walk's "final" mark
 		const uint32_t nd = (uint32_t)r & 1023u;
 		if (!nd)
 			return;

@@ -197,3 +197,40 @@ def test_device_decode_round_trips_and_reads_reference_archives(ctx):
     z = ctx.compress(datagen.generate("text", 200_000), make_params(backend=BACKEND_ZSTD, threads=8))
     with pytest.raises(Exception):
         ctx.decompress(z)  # zstd blocks are not decoded on the device (yet): an error, not garbage
+
+
+@pytest.mark.skipif(not oracle.have_ref(), reason="oracle/_ref not built")
+@pytest.mark.parametrize("flt,delta,flag,backend", [
+    (1, 0, "--x86", BACKEND_LZMA), (2, 0, "--arm", 0), (7, 0, "--arm64", BACKEND_LZMA), (4, 0, "--ppc", 0),
+    (5, 0, "--sparc", 0), (128, 1, "--delta=1", 0), (128, 4, "--delta=4", BACKEND_LZMA), (128, 48, "--delta=18", 0),
+])
+def test_filtered_archives_bit_identical_to_reference(ctx, flt, delta, flag, backend):
+    """Pre-compression filters (src/stream.c:1587-1628): stream-1 blocks are converted on the device
+    before the gate / backend; archives (filter byte in the magic, filtered stored blocks, LZMA over filtered bytes,
+    several blocks so that every block restarts the converter at 0) equal the reference binary's."""
+    rng = np.random.default_rng(flt + delta)
+    n = (25 if backend else 80) << 20  # LZMA: 3 blocks of one chunk; stored at -m1: 2 chunks x 3 blocks
+    d = rng.integers(0, 256, n, dtype=np.uint8)
+    # code-like: plant E8 calls and 4-byte aligned branch opcodes of several architectures, plus a compressible part
+    pos = (rng.integers(0, n // 4 - 2, n // 24) * 4).astype(np.int64)
+    d[pos + 3] = rng.choice(np.array([0xEB, 0x94, 0x97, 0x90], dtype=np.uint8), pos.size)
+    d[pos] = rng.choice(np.array([0x48, 0x4B, 0x40, 0x7F, 0xE8], dtype=np.uint8), pos.size)
+    d[5 << 20:9 << 20] = datagen.generate("text", 4 << 20)
+    d[12 << 20:13 << 20] = (np.arange(1 << 20) // 3 % 251).astype(np.uint8)  # a ramp: what Delta is for
+    kw = dict(threads=2 if backend else 1, processors=os.cpu_count() or 8)
+    if not backend:
+        kw["ramsize"] = 100 * 1048576  # -m1: two chunks, three blocks each
+    p = make_params(backend=backend, filter=flt, delta=delta, **kw)
+    got = ctx.compress(d, p)
+    op = oracle.make_params(backend=oracle.BACKEND_LZMA if backend else 0, **kw)
+    want = oracle.ref_compress(d, op, extra=(flag,))
+    assert got[16] == want[16] and got[16] != 0
+    assert got == want
+
+
+def test_unbuilt_filters_are_rejected(ctx):
+    for flt in (3, 6, 8, 77):
+        with pytest.raises(Exception):
+            ctx.compress(np.zeros(1000, dtype=np.uint8), make_params(filter=flt))
+    with pytest.raises(Exception):
+        ctx.compress(np.zeros(1000, dtype=np.uint8), make_params(filter=128, delta=17))

@@ -252,3 +252,84 @@ def test_zstd_block_encoder_frames_decode_with_libzstd():
         n, ours, theirs, blocks = report[name]
         assert blocks > 0 and ours < n * 0.6 and ours < theirs * 1.7, (name, report[name])
     assert report["zeros"][1] < 64 and report["random"][1] <= report["random"][0] + 32
+
+
+# ---- block filters: host build of filters.cuh against the reference's own converters ------------
+def _filter_libs():
+    subprocess.run(["make", "-s", "-C", os.path.join(HERE, "hostsim"), "libfilterhost.so"], check=True)
+    H = C.CDLL(os.path.join(HERE, "hostsim", "libfilterhost.so"))
+    H.hostsim_filter_block.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_int64]
+    R = C.CDLL(oracle.REF_LZMA)
+    for nm in ("ARM", "ARM64", "PPC", "SPARC"):
+        f = getattr(R, f"z7_BranchConv_{nm}_Enc")
+        f.argtypes, f.restype = [C.c_void_p, C.c_size_t, C.c_uint32], C.c_void_p
+    R.z7_BranchConvSt_X86_Enc.argtypes = [C.c_void_p, C.c_size_t, C.c_uint32, C.POINTER(C.c_uint32)]
+    R.z7_BranchConvSt_X86_Enc.restype = C.c_void_p
+    R.Delta_Init.argtypes = [C.c_void_p]
+    R.Delta_Encode.argtypes = [C.c_void_p, C.c_uint, C.c_void_p, C.c_size_t]
+    return H, R
+
+
+def _code_like(rng, kind, n):
+    """Random bytes with plausible branch instructions of the given architecture planted in them."""
+    d = rng.integers(0, 256, n, dtype=np.uint8)
+    if n < 32:
+        return d
+    m = n // 16
+    pos = (rng.integers(0, max(1, n // 4 - 2), m) * 4).astype(np.int64)
+    if kind == "ARM":
+        d[pos + 3] = 0xEB
+    elif kind == "ARM64":
+        h = m // 2
+        d[pos[:h] + 3] = (0x94 | rng.integers(0, 4, h)).astype(np.uint8)
+        d[pos[h:] + 3] = (0x90 | (rng.integers(0, 4, m - h) << 5)).astype(np.uint8)
+        d[pos[h:] + 2] = rng.choice(np.array([0, 0, 0xff, 0x0f, 0xf0, 0x1f, 0xe0], dtype=np.uint8), m - h)
+    elif kind == "PPC":
+        d[pos] = (0x48 | rng.integers(0, 4, m)).astype(np.uint8)
+        d[pos + 3] = (d[pos + 3] & 0xfc) | 1
+    elif kind == "SPARC":
+        sel = rng.integers(0, 2, m)
+        d[pos] = np.where(sel, 0x40, 0x7f).astype(np.uint8)
+        d[pos + 1] = np.where(sel, d[pos + 1] & 0x3f, d[pos + 1] | 0xc0).astype(np.uint8)
+    elif kind == "X86":
+        p1 = rng.integers(0, max(1, n - 6), m)
+        d[p1] = rng.choice(np.array([0xe8, 0xe9], dtype=np.uint8), m)
+        d[p1 + 4] = rng.choice(np.array([0, 0xff, 0, 0xff, 1, 0x80], dtype=np.uint8), m)
+        q = rng.integers(0, max(1, n - 12), m // 4)
+        for k in range(1, 4):  # runs of opcode-like bytes exercise the converter's state
+            d[q + k] = rng.choice(np.array([0xe8, 0xe9, 0x00, 0xff], dtype=np.uint8), m // 4)
+    return d
+
+
+@pytest.mark.skipif(not oracle.have_ref(), reason="oracle/_ref not built")
+def test_block_filters_match_the_reference_converters():
+    H, R = _filter_libs()
+    rng = np.random.default_rng(3)
+    ids = {"X86": 1, "ARM": 2, "PPC": 4, "SPARC": 5, "ARM64": 7}
+    for kind, fid in ids.items():
+        for n in (0, 1, 3, 4, 5, 7, 8, 64, 1000, 4099, 300_000):
+            for trial in range(3):
+                d = _code_like(rng, kind, n)
+                if trial == 2 and n:  # dense in opcode-like bytes
+                    d = np.where(rng.integers(0, 3, n) == 0, d, np.uint8(0xe8 if kind == "X86" else 0xff)).astype(np.uint8)
+                a, b = d.copy(), d.copy()
+                assert H.hostsim_filter_block(fid, 0, a.ctypes.data, n) == 0
+                if kind == "X86":
+                    st = C.c_uint32(0)
+                    R.z7_BranchConvSt_X86_Enc(b.ctypes.data, n, 0, C.byref(st))
+                else:
+                    getattr(R, f"z7_BranchConv_{kind}_Enc")(b.ctypes.data, n, 0)
+                assert np.array_equal(a, b), (kind, n, trial)
+                if n >= 1000 and trial == 0:
+                    assert (b != d).any(), (kind, "the planted instructions were not converted: the test has no teeth")
+    for delta in (1, 2, 3, 4, 15, 16, 32, 240, 256):
+        for n in (0, 1, 5, delta, delta + 1, 1000, 100_000):
+            d = rng.integers(0, 256, n, dtype=np.uint8)
+            a, b = d.copy(), d.copy()
+            assert H.hostsim_filter_block(128, delta, a.ctypes.data, n) == 0
+            st = (C.c_ubyte * 256)()
+            R.Delta_Init(st)
+            R.Delta_Encode(st, delta, b.ctypes.data, n)
+            assert np.array_equal(a, b), ("delta", delta, n)
+    for fid in (3, 6, 8):  # Thumb, IA64, RISC-V: not built, and said so
+        assert H.hostsim_filter_block(fid, 0, None, 0) != 0
