@@ -54,7 +54,7 @@ enum {
 enum { LRZGPU_CTYPE_NONE = 3, LRZGPU_CTYPE_LZMA = 6, LRZGPU_CTYPE_ZSTD = 10 };
 
 /* pre-compression filter of the stream-1 blocks (control->filter_flag, src/include/lrzip_private.h:389-397;
- * applied in compthread, src/stream.c:1587-1628).  ARMT, IA64 and RISCV are not built: LRZGPU_EUNSUPPORTED. */
+ * applied in compthread, src/stream.c:1587-1628).  RISCV is not built: LRZGPU_EUNSUPPORTED. */
 enum {
 	LRZGPU_FILTER_NONE = 0, LRZGPU_FILTER_X86 = 1, LRZGPU_FILTER_ARM = 2, LRZGPU_FILTER_ARMT = 3, LRZGPU_FILTER_PPC = 4,
 	LRZGPU_FILTER_SPARC = 5, LRZGPU_FILTER_IA64 = 6, LRZGPU_FILTER_ARM64 = 7, LRZGPU_FILTER_RISCV = 8, LRZGPU_FILTER_DELTA = 128
@@ -77,7 +77,7 @@ typedef struct lrzgpu_params {
 	int threshold;    /* lz4 gate: 0 = off (-T), else percent (default 100) */
 	int nobemt;       /* --nobemt: with LZMA level >= 5 and threads > 1 the reference switches to the single-threaded
 			     bt4 finder (src/stream.c:456); not reproduced => LRZGPU_EUNSUPPORTED */
-	int filter;       /* LRZGPU_FILTER_* (--x86 --arm --arm64 --ppc --sparc --delta), 0 = none */
+	int filter;       /* LRZGPU_FILTER_* (--x86 --arm --armt --arm64 --ppc --sparc --ia64 --delta), 0 = none */
 	int delta;        /* --delta: the distance in bytes, 1..16 or a multiple of 16 up to 256 (control->delta) */
 } lrzgpu_params;
 

@@ -36,13 +36,26 @@ __global__ void __launch_bounds__(256) filter_words_kernel(uint8_t *s, int64_t f
 	}
 }
 
-// x86: the converter's state runs through the whole block: one thread per block.
-__global__ void filter_x86_kernel(uint8_t *s, int64_t from, int64_t to, int64_t bs)
+// x86 and ARM Thumb: the scan's state runs through the whole block: one thread per block.
+__global__ void filter_serial_kernel(uint8_t *s, int64_t from, int64_t to, int64_t bs, int filter)
 {
 	if (threadIdx.x)
 		return;
 	const int64_t k = blockIdx.x;
-	flt::x86_encode(s + from + k * bs, (size_t)block_len(k, from, to, bs));
+	if (filter == flt::kX86)
+		flt::x86_encode(s + from + k * bs, (size_t)block_len(k, from, to, bs));
+	else
+		flt::armt_encode(s + from + k * bs, (size_t)block_len(k, from, to, bs));
+}
+
+// IA64: one thread per 16-byte bundle.
+__global__ void __launch_bounds__(256) filter_ia64_kernel(uint8_t *s, int64_t from, int64_t to, int64_t bs)
+{
+	const int64_t k = blockIdx.y;
+	uint8_t *b = s + from + k * bs;
+	const int64_t bundles = block_len(k, from, to, bs) >> 4;
+	for (int64_t w = (int64_t)blockIdx.x * 256 + threadIdx.x; w < bundles; w += (int64_t)gridDim.x * 256)
+		flt::ia64_bundle(b + 16 * w, (uint32_t)(16 * w));
 }
 
 // Delta in place, two passes so that no CTA reads bytes another CTA has already replaced: first every tile's `delta`
@@ -110,8 +123,15 @@ int filter_blocks_launch(int filter, int delta, uint8_t *s, int64_t from, int64_
 		filter_words_kernel<<<dim3(gx, (unsigned)nblk), 256, 0, stream>>>(s, from, to, bs, filter);
 		if (launches)
 			*launches += 1;
-	} else if (filter == flt::kX86) {
-		filter_x86_kernel<<<(unsigned)nblk, 32, 0, stream>>>(s, from, to, bs);
+	} else if (filter == flt::kX86 || filter == flt::kARMT) {
+		filter_serial_kernel<<<(unsigned)nblk, 32, 0, stream>>>(s, from, to, bs, filter);
+		if (launches)
+			*launches += 1;
+	} else if (filter == flt::kIA64) {
+		const int64_t bundles = (bs < to - from ? bs : to - from) >> 4;
+		unsigned gx = (unsigned)((bundles + 255) / 256);
+		gx = gx > 1184 ? 1184 : (gx ? gx : 1);
+		filter_ia64_kernel<<<dim3(gx, (unsigned)nblk), 256, 0, stream>>>(s, from, to, bs);
 		if (launches)
 			*launches += 1;
 	} else { // delta
@@ -131,7 +151,8 @@ int filter_preload()
 	cudaFuncAttributes a;
 	bool ok = true;
 	ok = ok && cudaFuncGetAttributes(&a, filter_words_kernel) == cudaSuccess;
-	ok = ok && cudaFuncGetAttributes(&a, filter_x86_kernel) == cudaSuccess;
+	ok = ok && cudaFuncGetAttributes(&a, filter_serial_kernel) == cudaSuccess;
+	ok = ok && cudaFuncGetAttributes(&a, filter_ia64_kernel) == cudaSuccess;
 	ok = ok && cudaFuncGetAttributes(&a, delta_save_kernel) == cudaSuccess;
 	ok = ok && cudaFuncGetAttributes(&a, delta_apply_kernel) == cudaSuccess;
 	return ok ? 0 : -1;

@@ -7,14 +7,18 @@
 //   --ppc       z7_BranchConv_PPC_Enc   src/lzma/C/Bra.c:158-195   "bl" (opcode 18, AA = 0, LK = 1), big endian
 //   --sparc     z7_BranchConv_SPARC_Enc src/lzma/C/Bra.c:202-257   "call" with a sign-extended 22-bit reach, big endian
 //   --x86       z7_BranchConvSt_X86_Enc src/lzma/C/Bra86.c         E8 / E9 rel32, the classic BCJ state machine
+//   --armt      z7_BranchConv_ARMT_Enc  src/lzma/C/Bra.c:260-338   Thumb BL pairs (F000 F800), 2-byte units
+//   --ia64      z7_BranchConv_IA64_Enc  src/lzma/C/BraIA64.c / Bra.c:343-420   br.call slots of 16-byte bundles
 //
 // The four RISC converters touch aligned 32-bit words independently of each other (a word's new value depends on the
 // word and on its offset only), so they are one thread per word; Delta is one thread per byte; the x86 converter
 // carries a few bits of state from byte to byte and is run by one thread per block (a stream block is 10 MiB: ~0.1 s,
-// beside a block encode of seconds).  ARM Thumb, IA64 and RISC-V are not built (LRZGPU_EUNSUPPORTED).
+// beside a block encode of seconds), and so is the Thumb converter (a converted pair hides the half-word after it from
+// the scan).  IA64 works on 16-byte bundles independently: one thread per bundle.  RISC-V is not built
+// (LRZGPU_EUNSUPPORTED).
 //
 // The converters are stated from the instruction formats; the CPU tests check them byte for byte against the
-// reference's own functions (oracle/_ref/liblzmaref.so exports them), the GPU tests against whole archives of the
+// reference's own functions (the test-side build of the reference's LZMA SDK exports them), the GPU tests against whole archives of the
 // reference binary.  Compiled for the device (product) and for the host (tests/hostsim only).
 #pragma once
 #include <stddef.h>
@@ -32,7 +36,7 @@ namespace flt {
 // magic byte 16 / control->filter_flag (src/include/lrzip_private.h:389-397)
 enum { kNone = 0, kX86 = 1, kARM = 2, kARMT = 3, kPPC = 4, kSPARC = 5, kIA64 = 6, kARM64 = 7, kRISCV = 8, kDelta = 128 };
 
-FLT_FN bool supported(int f) { return f == kNone || f == kX86 || f == kARM || f == kPPC || f == kSPARC || f == kARM64 || f == kDelta; }
+FLT_FN bool supported(int f) { return f == kNone || f == kX86 || f == kARM || f == kARMT || f == kPPC || f == kSPARC || f == kIA64 || f == kARM64 || f == kDelta; }
 FLT_FN bool wordwise(int f) { return f == kARM || f == kPPC || f == kSPARC || f == kARM64; }
 
 FLT_FN uint32_t bswap32(uint32_t v) { return (v >> 24) | ((v >> 8) & 0xff00u) | ((v << 8) & 0xff0000u) | (v << 24); }
@@ -157,6 +161,54 @@ FLT_FN void x86_encode(uint8_t *buf, size_t n)
 			if (x86_sign_byte(b))
 				mask |= 0x10;
 		}
+	}
+}
+
+// ARM Thumb: BL is a pair of half-words 11110 imm11(high) / 11111 imm11(low); the 22-bit field counts half-words from
+// the instruction after the pair's first half-word + 2 (i + 4).  After a converted pair the scan moves past it, so the
+// second half-word is never taken for the start of another pair: serial, in place, whole block.
+FLT_FN void armt_encode(uint8_t *buf, size_t n)
+{
+	for (size_t i = 0; i + 4 <= n; i += 2) {
+		if ((buf[i + 1] & 0xf8) != 0xf0 || (buf[i + 3] & 0xf8) != 0xf8)
+			continue;
+		uint32_t v = (((uint32_t)buf[i + 1] & 7) << 19) | ((uint32_t)buf[i] << 11) | (((uint32_t)buf[i + 3] & 7) << 8) | buf[i + 2];
+		v = ((v << 1) + (uint32_t)i + 4) >> 1;
+		buf[i + 1] = (uint8_t)(0xf0 | ((v >> 19) & 7));
+		buf[i] = (uint8_t)(v >> 11);
+		buf[i + 3] = (uint8_t)(0xf8 | ((v >> 8) & 7));
+		buf[i + 2] = (uint8_t)v;
+		i += 2;
+	}
+}
+
+// IA64: a 16-byte bundle = 5 template bits + three 41-bit slots; the template says which slots hold branch-unit
+// instructions.  A slot is converted when it is br.call-like (opcode 5, btype 0): its 21-bit immediate (20 bits at 13,
+// sign at 36), in bundles, becomes absolute.  Bundle-local.
+FLT_FN void ia64_bundle(uint8_t *b, uint32_t off)
+{
+	const uint32_t t = b[0] & 0x1f;
+	// slots holding a B unit, by template (10: MIB, 12: MBB, 16: BBB, 18: MMB, 1C: MFB; the odd twin of each ends a group)
+	const uint32_t mask = (t == 0x10 || t == 0x11 || t == 0x18 || t == 0x19 || t == 0x1c || t == 0x1d) ? 4u
+			      : ((t == 0x12 || t == 0x13) ? 6u : ((t == 0x16 || t == 0x17) ? 7u : 0u));
+	for (uint32_t slot = 0, bit = 5; slot < 3; slot++, bit += 41) {
+		if (!((mask >> slot) & 1))
+			continue;
+		const uint32_t bp = bit >> 3, br = bit & 7;
+		uint64_t ins = 0;
+		for (uint32_t j = 0; j < 6; j++)
+			ins |= (uint64_t)b[bp + j] << (8 * j);
+		uint64_t x = ins >> br;
+		if (((x >> 37) & 0xf) != 5 || ((x >> 9) & 7) != 0)
+			continue;
+		uint32_t v = (uint32_t)((x >> 13) & 0xfffff) | ((uint32_t)((x >> 36) & 1) << 20);
+		v = ((v << 4) + off) >> 4;
+		x &= ~((uint64_t)0x8fffff << 13);
+		x |= (uint64_t)(v & 0xfffff) << 13;
+		x |= (uint64_t)(v & 0x100000) << (36 - 20);
+		ins = (ins & (((uint64_t)1 << br) - 1)) | (x << br);
+		for (uint32_t j = 0; j < 6; j++)
+			b[bp + j] = (uint8_t)(ins >> (8 * j));
 	}
 }
 

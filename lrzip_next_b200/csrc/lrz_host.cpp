@@ -76,12 +76,13 @@ int compute_sizing(const lrzgpu_params &p, int64_t st_size, lrzgpu_sizing_t &o)
 		return LRZGPU_EUNSUPPORTED;
 	if (p.backend != LRZGPU_BACKEND_NONE && p.backend != LRZGPU_BACKEND_LZMA && p.backend != LRZGPU_BACKEND_ZSTD)
 		return LRZGPU_EUNSUPPORTED;
-	// filters (src/main.c:700-755): the Thumb, IA64 and RISC-V converters are not built; --delta takes 1..16 or a
-	// multiple of 16 up to 256
+	// filters (src/main.c:700-755): the RISC-V converter is not built; --delta takes 1..16 or a multiple of 16 up to 256
 	switch (p.filter) {
 	case LRZGPU_FILTER_NONE:
 	case LRZGPU_FILTER_X86:
 	case LRZGPU_FILTER_ARM:
+	case LRZGPU_FILTER_ARMT:
+	case LRZGPU_FILTER_IA64:
 	case LRZGPU_FILTER_PPC:
 	case LRZGPU_FILTER_SPARC:
 	case LRZGPU_FILTER_ARM64:
@@ -90,8 +91,6 @@ int compute_sizing(const lrzgpu_params &p, int64_t st_size, lrzgpu_sizing_t &o)
 		if (p.delta < 1 || p.delta > 256 || (p.delta > 16 && p.delta % 16))
 			return LRZGPU_EINVAL;
 		break;
-	case LRZGPU_FILTER_ARMT:
-	case LRZGPU_FILTER_IA64:
 	case LRZGPU_FILTER_RISCV:
 		return LRZGPU_EUNSUPPORTED;
 	default:

@@ -23,6 +23,12 @@ extern "C" int hostsim_filter_block(int filter, int delta, uint8_t *buf, int64_t
 		}
 	} else if (filter == flt::kX86)
 		flt::x86_encode(buf, (size_t)n);
+	else if (filter == flt::kARMT)
+		flt::armt_encode(buf, (size_t)n);
+	else if (filter == flt::kIA64) {
+		for (int64_t o = 0; o + 16 <= n; o += 16)
+			flt::ia64_bundle(buf + o, (uint32_t)o);
+	}
 	else if (filter == flt::kDelta) {
 		if (delta < 1 || delta > 256)
 			return -1;

@@ -202,7 +202,8 @@ def test_device_decode_round_trips_and_reads_reference_archives(ctx):
 @pytest.mark.skipif(not oracle.have_ref(), reason="oracle/_ref not built")
 @pytest.mark.parametrize("flt,delta,flag,backend", [
     (1, 0, "--x86", BACKEND_LZMA), (2, 0, "--arm", 0), (7, 0, "--arm64", BACKEND_LZMA), (4, 0, "--ppc", 0),
-    (5, 0, "--sparc", 0), (128, 1, "--delta=1", 0), (128, 4, "--delta=4", BACKEND_LZMA), (128, 48, "--delta=18", 0),
+    (5, 0, "--sparc", 0), (3, 0, "--armt", 0), (6, 0, "--ia64", 0),
+    (128, 1, "--delta=1", 0), (128, 4, "--delta=4", BACKEND_LZMA), (128, 48, "--delta=18", 0),
 ])
 def test_filtered_archives_bit_identical_to_reference(ctx, flt, delta, flag, backend):
     """Pre-compression filters (src/stream.c:1587-1628): stream-1 blocks are converted on the device
@@ -214,7 +215,8 @@ def test_filtered_archives_bit_identical_to_reference(ctx, flt, delta, flag, bac
     # code-like: plant E8 calls and 4-byte aligned branch opcodes of several architectures, plus a compressible part
     pos = (rng.integers(0, n // 4 - 2, n // 24) * 4).astype(np.int64)
     d[pos + 3] = rng.choice(np.array([0xEB, 0x94, 0x97, 0x90], dtype=np.uint8), pos.size)
-    d[pos] = rng.choice(np.array([0x48, 0x4B, 0x40, 0x7F, 0xE8], dtype=np.uint8), pos.size)
+    d[pos] = rng.choice(np.array([0x48, 0x4B, 0x40, 0x7F, 0xE8, 0x10, 0x16], dtype=np.uint8), pos.size)
+    d[pos + 1] = np.where(rng.integers(0, 3, pos.size) == 0, 0xF0 | (d[pos + 1] & 7), d[pos + 1]).astype(np.uint8)  # Thumb BL high half
     d[5 << 20:9 << 20] = datagen.generate("text", 4 << 20)
     d[12 << 20:13 << 20] = (np.arange(1 << 20) // 3 % 251).astype(np.uint8)  # a ramp: what Delta is for
     kw = dict(threads=2 if backend else 1, processors=os.cpu_count() or 8)
@@ -229,7 +231,7 @@ def test_filtered_archives_bit_identical_to_reference(ctx, flt, delta, flag, bac
 
 
 def test_unbuilt_filters_are_rejected(ctx):
-    for flt in (3, 6, 8, 77):
+    for flt in (8, 77):
         with pytest.raises(Exception):
             ctx.compress(np.zeros(1000, dtype=np.uint8), make_params(filter=flt))
     with pytest.raises(Exception):
