@@ -1044,7 +1044,7 @@ LZ_INL void opt_set4(Opt *o, uint32_t price, uint32_t len, uint32_t dist, uint32
 // decisions, same order of updates per cell as the loop below (which remains the general path and the host build).
 __device__ __forceinline__ void opt_step_staged(Enc *e, const uint32_t *b, uint32_t hdr, uint32_t pos, uint32_t numAvailFull,
 						uint32_t cur, uint32_t &last, uint32_t &position, uint32_t *reps,
-						const uint8_t *srcAll, uint32_t pbMask, uint32_t fb)
+						const uint8_t *srcAll, uint32_t pbMask, uint32_t fb, uint64_t &headNext)
 {
 	const uint32_t lane = lz_lane(), grp = lane >> 3, sub = lane & 7u;
 	const uint32_t nd = hdr & 0xFFFFu, newLen = hdr >> 16, np = nd >> 1;
@@ -1056,10 +1056,11 @@ __device__ __forceinline__ void opt_step_staged(Enc *e, const uint32_t *b, uint3
 		pDist = b[2 + 2 * lane];
 		pW = b[1 + kLkMaxList + lane];
 	}
-	const uint32_t dSub = data[sub], prevByte = *(data - 1);
+	const uint32_t dSub = data[sub], prevByte = *(data - 1), curByte = data[0];
 	Opt *curOpt = &e->opt[cur], *nextOpt = curOpt + 1;
 	const uint4 c0 = *reinterpret_cast<const uint4 *>(curOpt); // price, state | extra << 16, len, dist
 	const uint4 n0 = *reinterpret_cast<const uint4 *>(nextOpt);
+	const uint32_t statePrev1 = (curOpt - 1)->state; // the common predecessor (a literal or short rep): asked for before len is known
 	LZ_T(15);
 	// what ReadMatchDistances leaves behind
 	e->additionalOffset++;
@@ -1070,7 +1071,7 @@ __device__ __forceinline__ void opt_step_staged(Enc *e, const uint32_t *b, uint3
 	const uint32_t curPrice = c0.x, curLen = c0.z, curDist = c0.w, curExtra = c0.y >> 16;
 	uint32_t prev = cur - curLen, state;
 	if (curLen == 1) {
-		state = e->opt[prev].state;
+		state = statePrev1;
 		state = curDist == 0 ? st_shortrep(state) : st_lit(state);
 	} else {
 		if (curExtra) {
@@ -1124,7 +1125,7 @@ __device__ __forceinline__ void opt_step_staged(Enc *e, const uint32_t *b, uint3
 	myRep = grp == 3 ? reps[3] : myRep;
 	const uint32_t rSub = (data - myRep)[sub];
 	const uint32_t eq = lz_ballot(rSub == dSub); // bit 8 g + i: byte i of rep g equals byte i here
-	const uint32_t curByte = lz_shfl(dSub, 0), matchByte = lz_shfl(rSub, 0);
+	const uint32_t matchByte = lz_shfl(rSub, 0);
 	uint32_t repMask = 0;
 	for (uint32_t q = 0; q < kNumReps; q++)
 		repMask |= ((eq >> (8 * q)) & 3u) == 3u ? 1u << q : 0u;
@@ -1162,7 +1163,7 @@ __device__ __forceinline__ void opt_step_staged(Enc *e, const uint32_t *b, uint3
 			const uint32_t node = (0x100u | curByte) >> (8 - lane), bit = (curByte >> (7 - lane)) & 1;
 			if (is_lit_state(state))
 				v = price_bit(e, probs[node], bit);
-			else {
+			else { // after a match: the match byte's bits pick the half while the bits above agree
 				const uint32_t offs = (((matchByte ^ curByte) >> (8 - lane)) == 0) ? 0x100u : 0u;
 				const uint32_t mb = ((matchByte >> (7 - lane)) & 1) << 8;
 				v = price_bit(e, probs[offs + (mb & offs) + node], bit);
@@ -1303,6 +1304,9 @@ __device__ __forceinline__ void opt_step_staged(Enc *e, const uint32_t *b, uint3
 		}
 		LZ_T(9);
 	}
+	// the next position's ring entry, asked for now: the loop top finds it in a register (and asks again if the
+	// look-ahead warp had not got there yet)
+	headNext = *reinterpret_cast<const volatile uint64_t *>(&e->lkHead[(pos + 1) & (kLkSlots - 1)][0]);
 	lz_sync();
 	LZ_T(16);
 }
@@ -1440,6 +1444,7 @@ LZ_FN inline uint32_t get_optimum(Enc *e, uint32_t position)
 #if defined(__CUDA_ARCH__)
 	// loop invariants the compiler cannot keep in registers by itself (every store into *e may alias them)
 	const bool lkOn = e->lkOn != 0;
+	uint64_t headNext = 0; // ring head word read ahead by the previous staged step (position in the low half)
 	const uint32_t nAll = e->n, pbMask = e->pbMask;
 	const uint8_t *const srcAll = e->src;
 #endif
@@ -1481,12 +1486,14 @@ LZ_FN inline uint32_t get_optimum(Enc *e, uint32_t position)
 #endif
 			// one 8-byte load: the tag and the header the helper stored together after its fence; the entry's words
 			// are read after it (shared-memory loads of one warp are served in order)
-			const uint64_t head = *reinterpret_cast<const volatile uint64_t *>(&e->lkHead[slot][0]);
+			uint64_t head = headNext;
+			if ((uint32_t)head != pos)
+				head = *reinterpret_cast<const volatile uint64_t *>(&e->lkHead[slot][0]);
 			const uint32_t hdr = (uint32_t)(head >> 32);
 			if (naf >= fb && naf >= 8 && (uint32_t)head == pos) {
 				if ((hdr & 0xFFFFu) <= 64 && (hdr >> 16) < fb) {
 					LZ_T(14);
-					opt_step_staged(e, b, hdr, pos, naf, cur, last, position, reps, srcAll, pbMask, fb);
+					opt_step_staged(e, b, hdr, pos, naf, cur, last, position, reps, srcAll, pbMask, fb, headNext);
 					continue;
 				}
 			}
