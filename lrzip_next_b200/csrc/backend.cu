@@ -339,7 +339,7 @@ __device__ void lzma_coder_thread(lzma::Enc *e)
 // K7b kernel: one block per CTA, four warps.  Warp 0 is the encoder (optimal parser, probability model, symbol
 // decisions: lzma_enc.cuh, replicated scalar code with lane-split loops); warp 1 looks ahead and stages match lists;
 // warp 2 runs the lz4 compressibility gate beside it; one thread of warp 3 is the range coder.
-__global__ void __launch_bounds__(128, 1) lzma_block_kernel(LzmaJob *jobs)
+__global__ void __launch_bounds__(160, 1) lzma_block_kernel(LzmaJob *jobs)
 {
 	extern __shared__ __align__(16) uint8_t lzma_smem[];
 	__shared__ uint32_t gate_table[4096];
@@ -367,8 +367,21 @@ __global__ void __launch_bounds__(128, 1) lzma_block_kernel(LzmaJob *jobs)
 		e->mfOverflow = j.wait_count ? j.mf_overflow : nullptr;
 		e->gateState = j.threshold ? &gate_state : nullptr;
 		e->lkOn = e->rcOn = 1;
+		e->splitOn = 1;
 	}
 	__syncthreads(); // the encoder state is initialised: the helpers may read it
+#if defined(__CUDA_ARCH__) // (the helpers exist in the device pass only)
+	if (threadIdx.x >= 128) {
+		// warp 4: the rep / match half of every staged position, one position behind warp 0 (lzma_enc.cuh: opt_step_b)
+		for (;;) {
+			lzma::bar_wait(lzma::kBarGo);
+			if (*(volatile uint32_t *)&e->pkt.cmd == 0)
+				return;
+			lzma::opt_step_b(e);
+			lzma::bar_arrive(lzma::kBarDone);
+		}
+	}
+#endif
 	if (threadIdx.x >= 96) {
 		if (threadIdx.x == 96)
 			lzma_coder_thread(e);
@@ -399,6 +412,10 @@ __global__ void __launch_bounds__(128, 1) lzma_block_kernel(LzmaJob *jobs)
 #endif
 	const uint64_t len = lzma::enc_run(e);
 	__syncwarp();
+#if defined(__CUDA_ARCH__)
+	*(volatile uint32_t *)&e->pkt.cmd = 0; // warp 4 leaves
+	lzma::bar_arrive(lzma::kBarGo);
+#endif
 #if defined(LZ_PROF)
 	if (threadIdx.x == 0) {
 		const long long tot = clock64() - prof_t0;
@@ -863,7 +880,7 @@ static int pump_groups(BackendCtx *b, bool wait, int64_t *launches, char *err, s
 			if (launches)
 				(*launches) += 2;
 		} else {
-			lzma_block_kernel<<<(unsigned)G.count, 128, sizeof(lzma::Enc), G.ps>>>((LzmaJob *)J);
+			lzma_block_kernel<<<(unsigned)G.count, 160, sizeof(lzma::Enc), G.ps>>>((LzmaJob *)J);
 			if (launches)
 				(*launches)++;
 			if (beside && (cudaEventRecord(G.evWalk, G.ws) != cudaSuccess || cudaStreamWaitEvent(G.ps, G.evWalk, 0) != cudaSuccess)) {

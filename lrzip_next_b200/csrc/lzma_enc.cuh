@@ -119,7 +119,8 @@ typedef uint16_t Prob;
 // shared memory and, for every (len, dist) pair, already does the far-byte comparison of the MATCH : LIT : REP0
 // trial.  An entry is a pure cache: the encoder uses it when its tag says it holds the position it wants and
 // falls back to HBM otherwise, so the output never depends on the helper.
-constexpr uint32_t kLkSlots = 8;                  // ring entries (positions); the helper runs at most 6 ahead
+constexpr uint32_t kLkSlots = 16;                 // ring entries (positions); the helper runs at most 6 ahead of the parser,
+                                                  // whose second warp is up to two positions behind the first
 constexpr uint32_t kLkMaxList = 128;              // uint32 of one staged list (pairs of len, dist - 1)
 constexpr uint32_t kLkByLen = 1 + kLkMaxList + kLkMaxList / 2; // offset of the distance-by-length table (indexed by length)
 constexpr uint32_t kLkWords = kLkByLen + kMatchMax + 1; // count | longest << 16, list, per pair (twoBytesEqual << 31 | end), table
@@ -146,6 +147,14 @@ struct alignas(16) Opt {
 	uint32_t len;
 	uint32_t dist;
 	uint32_t reps[kNumReps];
+};
+
+// Hand-over of one position from the parser's first warp to its second (device product path, see opt_step_a / _b).
+struct StepPkt {
+	uint32_t cmd; // 1: a position, 0: leave
+	uint32_t cur, pos, position, naf, hdr, state, posState;
+	uint32_t reps[kNumReps];
+	uint32_t matchPrice, repMatchPrice, normalMatchPrice, litPrice, nextIsLit, curByte, matchByte, last;
 };
 
 // Everything one block encoder owns besides the match-finder arrays; lives in HBM (device) / heap (host).
@@ -212,6 +221,9 @@ struct Enc {
 #endif
 	// The helpers' structures live inside the encoder so that the encoder warp reaches them with plain shared-memory
 	// loads (through a pointer kept in the struct they become generic loads, which cost three times as much).
+	int splitOn;        // a second parser warp takes the rep / match half of every staged position (backend.cu)
+	uint32_t lastB;     // `last` as the second warp leaves it
+	alignas(16) StepPkt pkt;
 	alignas(16) uint32_t pubReps[kNumReps]; // the reps of the cell the parser is at: the look-ahead warp prefetches behind them
 	alignas(8) uint32_t lkHead[kLkSlots][2]; // {position (1-based, as e->pos) the entry holds, count | longest length << 16}
 	uint32_t lkRing[kLkSlots * kLkWords];
@@ -1310,6 +1322,317 @@ __device__ __forceinline__ void opt_step_staged(Enc *e, const uint32_t *b, uint3
 	lz_sync();
 	LZ_T(16);
 }
+// ---- the staged step on two warps ---------------------------------------------------------------------------------
+// The literal / short-rep half of position cur + 1 (cell's state and reps, prices, the literal's eight decisions) does
+// not depend on what the rep / match half of position cur writes -- matches reach cells cur + 2 and beyond -- except
+// for the final comparison with cell cur + 2.  So warp A runs the first half of every position and warp B the second,
+// one position behind: A works out position cur + 1 while B prices the reps and matches of position cur, waits for B,
+// does its two compare-and-store updates of cell cur + 2 and hands position cur + 1 to B.  Per cell the order of updates
+// is the reference's: everything of position cur (A's, then B's), then position cur + 1.  Named barriers 1 (a position
+// for B) and 2 (B is done) pair one arriving warp with one waiting warp (PTX producer / consumer form).
+LZ_INL void bar_arrive(int id) { asm volatile("bar.arrive %0, 64;" ::"r"(id) : "memory"); }
+LZ_INL void bar_wait(int id) { asm volatile("bar.sync %0, 64;" ::"r"(id) : "memory"); }
+constexpr int kBarGo = 1, kBarDone = 2;
+
+// A waits for B to finish the position it was given and takes over `last`.
+LZ_INL void split_drain(Enc *e, bool &pending, uint32_t &last)
+{
+	if (!pending)
+		return;
+	bar_wait(kBarDone);
+	pending = false;
+	last = *(volatile uint32_t *)&e->lastB;
+}
+
+__device__ __forceinline__ void opt_step_a(Enc *e, uint32_t hdr, uint32_t pos, uint32_t numAvailFull, uint32_t cur,
+					   uint32_t &last, uint32_t &position, uint32_t *reps, const uint8_t *srcAll,
+					   uint32_t pbMask, uint64_t &headNext, bool &pending)
+{
+	const uint32_t lane = lz_lane();
+	const uint8_t *data = srcAll + (pos - 1);
+	const uint32_t prevByte = *(data - 1), curByte = data[0];
+	Opt *curOpt = &e->opt[cur], *nextOpt = curOpt + 1;
+	const uint4 c0 = *reinterpret_cast<const uint4 *>(curOpt); // price, state | extra << 16, len, dist
+	const uint32_t statePrev1 = (curOpt - 1)->state;
+	// what ReadMatchDistances leaves behind
+	e->additionalOffset++;
+	e->numAvail = e->n - (pos - 1);
+	e->pos = pos + 1;
+	position++;
+	const uint32_t curPrice = c0.x, curLen = c0.z, curDist = c0.w, curExtra = c0.y >> 16;
+	uint32_t prev = cur - curLen, state;
+	if (curLen == 1) {
+		state = statePrev1;
+		state = curDist == 0 ? st_shortrep(state) : st_lit(state);
+	} else {
+		if (curExtra) {
+			prev -= curExtra;
+			state = 8;
+			if (curExtra == 1)
+				state = curDist < kNumReps ? 8 : 7;
+		} else {
+			state = e->opt[prev].state;
+			state = curDist < kNumReps ? st_rep(state) : st_match(state);
+		}
+		const uint4 pr = *reinterpret_cast<const uint4 *>(e->opt[prev].reps);
+		if (curDist < kNumReps) {
+			if (curDist == 0) {
+				reps[0] = pr.x;
+				reps[1] = pr.y;
+				reps[2] = pr.z;
+				reps[3] = pr.w;
+			} else if (curDist == 1) {
+				reps[0] = pr.y;
+				reps[1] = pr.x;
+				reps[2] = pr.z;
+				reps[3] = pr.w;
+			} else if (curDist == 2) {
+				reps[0] = pr.z;
+				reps[1] = pr.x;
+				reps[2] = pr.y;
+				reps[3] = pr.w;
+			} else {
+				reps[0] = pr.w;
+				reps[1] = pr.x;
+				reps[2] = pr.y;
+				reps[3] = pr.z;
+			}
+		} else {
+			reps[0] = curDist - kNumReps + 1;
+			reps[1] = pr.x;
+			reps[2] = pr.y;
+			reps[3] = pr.z;
+		}
+	}
+	curOpt->state = (uint16_t)state;
+	*reinterpret_cast<uint4 *>(curOpt->reps) = make_uint4(reps[0], reps[1], reps[2], reps[3]);
+	*reinterpret_cast<uint4 *>(e->pubReps) = make_uint4(reps[0], reps[1], reps[2], reps[3]);
+	const uint32_t matchByte = *(data - reps[0]);
+	const uint32_t posState = position & pbMask;
+	uint32_t matchPrice, litPrice, repMatchPrice;
+	{
+		const uint32_t prob = e->isMatch[state][posState];
+		matchPrice = curPrice + price1(e, prob);
+		litPrice = curPrice + price0(e, prob);
+	}
+	const uint32_t probRep = e->isRep[state];
+	repMatchPrice = matchPrice + price1(e, probRep);
+	const uint32_t normalMatchPrice = matchPrice + price0(e, probRep);
+	// the literal's eight decisions, priced whether or not the comparison below will want them: B is still busy
+	uint32_t litFull;
+	{
+		const Prob *probs = lit_probs(e, position, prevByte);
+		uint32_t v = 0;
+		if (lane < 8) {
+			const uint32_t node = (0x100u | curByte) >> (8 - lane), bit = (curByte >> (7 - lane)) & 1;
+			if (is_lit_state(state))
+				v = price_bit(e, probs[node], bit);
+			else {
+				const uint32_t offs = (((matchByte ^ curByte) >> (8 - lane)) == 0) ? 0x100u : 0u;
+				const uint32_t mb = ((matchByte >> (7 - lane)) & 1) << 8;
+				v = price_bit(e, probs[offs + (mb & offs) + node], bit);
+			}
+		}
+		litFull = litPrice + lz_sum(v);
+	}
+	const bool srCand = is_lit_state(state) && matchByte == curByte;
+	const uint32_t shortRepPrice = srCand ? repMatchPrice + price_short_rep(e, state, posState) : 0;
+	headNext = *reinterpret_cast<const volatile uint64_t *>(&e->lkHead[(pos + 1) & (kLkSlots - 1)][0]);
+
+	// ---- cell cur + 1 must now hold everything position cur - 1 wrote
+	split_drain(e, pending, last);
+	const uint4 n0 = *reinterpret_cast<const uint4 *>(nextOpt);
+	uint32_t nPrice = n0.x, nLen = n0.z, nDist = n0.w;
+	bool nextIsLit = false;
+	if ((nPrice < kInfinity && matchByte == curByte) || litPrice > nPrice)
+		litPrice = 0;
+	else {
+		litPrice = litFull;
+		if (litPrice < nPrice) {
+			opt_set4(nextOpt, litPrice, 1, kMarkLit, 0);
+			nPrice = litPrice;
+			nLen = 1;
+			nDist = kMarkLit;
+			nextIsLit = true;
+		}
+	}
+	// SHORT_REP
+	if (srCand && repMatchPrice < nPrice && (nLen < 2 || nDist != 0)) {
+		if (shortRepPrice < nPrice) {
+			opt_set4(nextOpt, shortRepPrice, 1, 0, 0);
+			nextIsLit = false;
+		}
+	}
+	// the rep / match half goes to warp B
+	StepPkt *k = &e->pkt;
+	*reinterpret_cast<uint4 *>(&k->cmd) = make_uint4(1u, cur, pos, position);
+	*reinterpret_cast<uint4 *>(&k->naf) = make_uint4(numAvailFull, hdr, state, posState);
+	*reinterpret_cast<uint4 *>(k->reps) = make_uint4(reps[0], reps[1], reps[2], reps[3]);
+	*reinterpret_cast<uint4 *>(&k->matchPrice) = make_uint4(matchPrice, repMatchPrice, normalMatchPrice, litPrice);
+	*reinterpret_cast<uint4 *>(&k->nextIsLit) = make_uint4(nextIsLit ? 1u : 0u, curByte, matchByte, last);
+	bar_arrive(kBarGo);
+	pending = true;
+}
+
+// Warp B: the rep / match half of the position in e->pkt (LzmaEnc.c:1700-1949).
+__device__ __forceinline__ void opt_step_b(Enc *e)
+{
+	const uint32_t lane = lz_lane(), grp = lane >> 3, sub = lane & 7u;
+	const StepPkt *k = &e->pkt;
+	const uint4 k0 = *reinterpret_cast<const uint4 *>(&k->cmd), k1 = *reinterpret_cast<const uint4 *>(&k->naf);
+	const uint4 k2 = *reinterpret_cast<const uint4 *>(k->reps), k3 = *reinterpret_cast<const uint4 *>(&k->matchPrice);
+	const uint4 k4 = *reinterpret_cast<const uint4 *>(&k->nextIsLit);
+	const uint32_t cur = k0.y, pos = k0.z, position = k0.w, numAvailFull = k1.x, hdr = k1.y, state = k1.z, posState = k1.w;
+	uint32_t reps[kNumReps] = { k2.x, k2.y, k2.z, k2.w };
+	const uint32_t repMatchPrice = k3.y, normalMatchPrice = k3.z, litPrice = k3.w;
+	const bool nextIsLit = k4.x != 0;
+	const uint32_t curByte = k4.y, matchByte = k4.z;
+	uint32_t last = k4.w;
+	const uint32_t fb = e->fb, pbMask = e->pbMask;
+	const uint32_t *b = e->lkRing + (pos & (kLkSlots - 1)) * kLkWords;
+	const uint32_t nd = hdr & 0xFFFFu, newLen = hdr >> 16, np = nd >> 1;
+	const uint8_t *data = e->src + (pos - 1);
+	uint32_t pLen = 0, pDist = 0, pW = 0;
+	if (lane < np) {
+		pLen = b[1 + 2 * lane];
+		pDist = b[2 + 2 * lane];
+		pW = b[1 + kLkMaxList + lane];
+	}
+	const uint32_t dSub = data[sub];
+	// ---- bytes from far back, all in flight at once: group g compares the first eight bytes of rep g
+	uint32_t myRep = reps[0];
+	myRep = grp == 1 ? reps[1] : myRep;
+	myRep = grp == 2 ? reps[2] : myRep;
+	myRep = grp == 3 ? reps[3] : myRep;
+	const uint32_t rSub = (data - myRep)[sub];
+	const uint32_t eq = lz_ballot(rSub == dSub); // bit 8 g + i: byte i of rep g equals byte i here
+	uint32_t repMask = 0;
+	for (uint32_t q = 0; q < kNumReps; q++)
+		repMask |= ((eq >> (8 * q)) & 3u) == 3u ? 1u << q : 0u;
+	uint32_t pL2 = 0;
+	if (lane < np) {
+		uint32_t limit = pLen + 1 + fb;
+		if (limit > numAvailFull)
+			limit = numAvailFull;
+		if ((pW >> 31) && pLen + 3 <= limit) {
+			const uint32_t end = (pW & 0x7FFFFFFFu) < limit ? (pW & 0x7FFFFFFFu) : limit;
+			pL2 = end - pLen;
+		}
+	}
+	// LIT : REP_0 (bytes 1 and 2 behind rep0 equal; numAvailFull >= fb > 2)
+	if (!nextIsLit && litPrice != 0 && matchByte != curByte && (eq & 6u) == 6u) {
+		const uint8_t *data2 = data - reps[0];
+		uint32_t len, limit = fb + 1;
+		if (limit > numAvailFull)
+			limit = numAvailFull;
+		const uint32_t ne = ~eq & 0xF8u; // first of the bytes 3..7 that differs
+		if (ne)
+			len = lz_ffs(ne) - 1;
+		else
+			len = 8;
+		if (len > limit)
+			len = limit;
+		else if (!ne && limit > 8)
+			len = lz_extend(data2, data, 8, limit);
+		const uint32_t state2 = st_lit(state), posState2 = (position + 1) & pbMask;
+		const uint32_t price = litPrice + price_rep0(e, state2, posState2);
+		const uint32_t offset = cur + len;
+		if (last < offset)
+			last = offset;
+		len--;
+		const uint32_t price2 = price + len_price(&e->repLenPrices, posState2, len);
+		Opt *o = &e->opt[offset];
+		if (price2 < o->price)
+			opt_set4(o, price2, len, 0, 1);
+	}
+	uint32_t startLen = 2;
+	// REP
+	for (uint32_t rm = repMask; rm; rm &= rm - 1) {
+		const uint32_t repIndex = lz_ffs(rm) - 1;
+		const uint8_t *data2 = data - pick4(reps, repIndex);
+		const uint32_t f = (eq >> (8 * repIndex)) & 0xFFu, nf = ~f & 0xFFu;
+		uint32_t len = nf ? lz_ffs(nf) - 1 : 8; // equal leading bytes among the first eight; numAvail = fb
+		if (len > fb)
+			len = fb;
+		else if (!nf && fb > 8)
+			len = lz_extend(data2, data, 8, fb);
+		if (last < cur + len)
+			last = cur + len;
+		uint32_t price = repMatchPrice + price_pure_rep(e, repIndex, state, posState);
+		opt_rep_cells(e, cur, 2, len, price, posState, repIndex);
+		if (repIndex == 0)
+			startLen = len + 1;
+		// REP : LIT : REP_0
+		uint32_t len2 = len + 1, limit = len2 + fb;
+		if (limit > numAvailFull)
+			limit = numAvailFull;
+		len2 += 2;
+		bool two;
+		if (len + 2 < 8)
+			two = ((f >> (len + 1)) & 3u) == 3u;
+		else
+			two = len2 <= limit && data[len2 - 2] == data2[len2 - 2] && data[len2 - 1] == data2[len2 - 1];
+		if (len2 <= limit && two) {
+			uint32_t state2 = st_rep(state), posState2 = (position + len) & pbMask;
+			price += len_price(&e->repLenPrices, posState, len) + price0(e, e->isMatch[state2][posState2]) +
+				 lit_price_matched(e, lit_probs(e, position + len, data[len - 1]), data[len], data2[len]);
+			state2 = 5; // kState_LitAfterRep
+			posState2 = (posState2 + 1) & pbMask;
+			price += price_rep0(e, state2, posState2);
+			len2 = lz_extend(data2, data, len2, limit);
+			len2 -= len;
+			const uint32_t offset = cur + len + len2;
+			if (last < offset)
+				last = offset;
+			len2--;
+			const uint32_t price2 = price + len_price(&e->repLenPrices, posState2, len2);
+			Opt *o = &e->opt[offset];
+			if (price2 < o->price)
+				opt_set4(o, price2, len2, repIndex, len + 1);
+		}
+	}
+	// MATCH
+	if (newLen >= startLen) {
+		if (last < cur + newLen)
+			last = cur + newLen;
+		// MATCH : LIT : REP_0 of every pair that is long enough: priced by the pair's lane, applied in pair order
+		const bool tr = lane < np && pLen >= startLen && pL2 != 0;
+		const uint32_t trMask = lz_ballot(tr);
+		if (trMask) {
+			uint32_t tPrice = 0;
+			if (tr) {
+				const uint8_t *data2 = data - pDist - 1;
+				uint32_t price = match_price(e, normalMatchPrice, posState, pLen, pDist);
+				uint32_t state2 = st_match(state), posState2 = (position + pLen) & pbMask;
+				price += price0(e, e->isMatch[state2][posState2]);
+				price += lit_price_matched_1(e, lit_probs(e, position + pLen, data[pLen - 1]), data[pLen], data2[pLen]);
+				state2 = 4; // kState_LitAfterMatch
+				posState2 = (posState2 + 1) & pbMask;
+				price += price_rep0(e, state2, posState2);
+				tPrice = price + len_price(&e->repLenPrices, posState2, pL2 - 1);
+			}
+			for (uint32_t m = trMask; m; m &= m - 1) {
+				const uint32_t k = lz_ffs(m) - 1;
+				const uint32_t len = lz_shfl(pLen, k), l2 = lz_shfl(pL2, k), dist = lz_shfl(pDist, k), price2 = lz_shfl(tPrice, k);
+				const uint32_t offset = cur + len + l2;
+				if (last < offset)
+					last = offset;
+				Opt *o = &e->opt[offset];
+				if (price2 < o->price)
+					opt_set4(o, price2, l2 - 1, dist + kNumReps, len + 1);
+			}
+		}
+		// the cells [cur + startLen, cur + newLen]: the shortest-distance pair that reaches each length (staged table)
+		for (uint32_t len = startLen + lane; len <= newLen; len += LZ_W) {
+			const uint32_t dist = b[kLkByLen + len];
+			const uint32_t price = match_price(e, normalMatchPrice, posState, len, dist);
+			Opt *o = &e->opt[cur + len];
+			if (price < o->price)
+				opt_set4(o, price, len, dist + kNumReps, 0);
+		}
+	}
+	*(volatile uint32_t *)&e->lastB = last;
+}
 #endif
 
 // GetOptimum (LzmaEnc.c:1219-1968).
@@ -1445,6 +1768,8 @@ LZ_FN inline uint32_t get_optimum(Enc *e, uint32_t position)
 	// loop invariants the compiler cannot keep in registers by itself (every store into *e may alias them)
 	const bool lkOn = e->lkOn != 0;
 	uint64_t headNext = 0; // ring head word read ahead by the previous staged step (position in the low half)
+	const bool splitOn = e->splitOn != 0;
+	bool pending = false;  // warp B is working on the previous position
 	const uint32_t nAll = e->n, pbMask = e->pbMask;
 	const uint8_t *const srcAll = e->src;
 #endif
@@ -1453,8 +1778,18 @@ LZ_FN inline uint32_t get_optimum(Enc *e, uint32_t position)
 		uint32_t numAvail, numAvailFull, newLen, numPairs, prev, state, posState, startLen;
 		uint32_t litPrice, matchPrice, repMatchPrice;
 		bool nextIsLit;
+#if defined(__CUDA_ARCH__)
+		if (++cur == last) {
+			split_drain(e, pending, last); // B may still be extending `last`
+			if (cur == last)
+				break;
+		}
+		if (cur >= kNumOpts - 64)
+			split_drain(e, pending, last);
+#else
 		if (++cur == last)
 			break;
+#endif
 		if (cur >= kNumOpts - 64) {
 			uint32_t best = cur, price = e->opt[cur].price;
 			for (uint32_t j = cur + 1; j <= last; j++) {
@@ -1493,12 +1828,15 @@ LZ_FN inline uint32_t get_optimum(Enc *e, uint32_t position)
 			if (naf >= fb && naf >= 8 && (uint32_t)head == pos) {
 				if ((hdr & 0xFFFFu) <= 64 && (hdr >> 16) < fb) {
 					LZ_T(14);
-					opt_step_staged(e, b, hdr, pos, naf, cur, last, position, reps, srcAll, pbMask, fb, headNext);
+					if (splitOn)
+						opt_step_a(e, hdr, pos, naf, cur, last, position, reps, srcAll, pbMask, headNext, pending);
+					else
+						opt_step_staged(e, b, hdr, pos, naf, cur, last, position, reps, srcAll, pbMask, fb, headNext);
 					continue;
 				}
 			}
-
 		}
+		split_drain(e, pending, last); // the general step below reads and writes the whole table
 #endif
 		newLen = read_matches(e, &numPairs);
 		LZ_T(2);
@@ -1748,6 +2086,9 @@ LZ_FN inline uint32_t get_optimum(Enc *e, uint32_t position)
 			LZ_T(9);
 		}
 	}
+#if defined(__CUDA_ARCH__)
+	split_drain(e, pending, last);
+#endif
 	lz_sync();
 	LZ_PFOR(q, last)
 		e->opt[1 + q].price = kInfinity;
@@ -1952,6 +2293,9 @@ LZ_FN inline void enc_init(Enc *e, const Config &c, const uint8_t *src, uint32_t
 	e->gateState = nullptr;
 	e->aborted = 0;
 	e->lkOn = e->rcOn = 0;
+	e->splitOn = 0;
+	e->lastB = 0;
+	e->pkt.cmd = 0;
 	e->lkSlot = -1;
 	for (uint32_t i = 0; i < kNumReps; i++)
 		e->pubReps[i] = 1;
