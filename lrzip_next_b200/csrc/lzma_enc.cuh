@@ -1348,9 +1348,9 @@ __device__ __forceinline__ void opt_step_a(Enc *e, uint32_t hdr, uint32_t pos, u
 					   uint32_t &last, uint32_t &position, uint32_t *reps, const uint8_t *srcAll,
 					   uint32_t pbMask, uint64_t &headNext, bool &pending)
 {
-	const uint32_t lane = lz_lane();
+	const uint32_t lane = lz_lane(), grp = lane >> 3, sub = lane & 7u;
 	const uint8_t *data = srcAll + (pos - 1);
-	const uint32_t prevByte = *(data - 1), curByte = data[0];
+	const uint32_t prevByte = *(data - 1), curByte = data[0], dSub = data[sub];
 	Opt *curOpt = &e->opt[cur], *nextOpt = curOpt + 1;
 	const uint4 c0 = *reinterpret_cast<const uint4 *>(curOpt); // price, state | extra << 16, len, dist
 	const uint32_t statePrev1 = (curOpt - 1)->state;
@@ -1407,7 +1407,13 @@ __device__ __forceinline__ void opt_step_a(Enc *e, uint32_t hdr, uint32_t pos, u
 	curOpt->state = (uint16_t)state;
 	*reinterpret_cast<uint4 *>(curOpt->reps) = make_uint4(reps[0], reps[1], reps[2], reps[3]);
 	*reinterpret_cast<uint4 *>(e->pubReps) = make_uint4(reps[0], reps[1], reps[2], reps[3]);
-	const uint32_t matchByte = *(data - reps[0]);
+	// bytes from far back, all in flight at once: group g compares the first eight bytes of rep g (warp B works from
+	// the resulting bits; the byte behind rep0 is the literal's match byte)
+	uint32_t myRep = reps[0];
+	myRep = grp == 1 ? reps[1] : myRep;
+	myRep = grp == 2 ? reps[2] : myRep;
+	myRep = grp == 3 ? reps[3] : myRep;
+	const uint32_t rSub = (data - myRep)[sub];
 	const uint32_t posState = position & pbMask;
 	uint32_t matchPrice, litPrice, repMatchPrice;
 	{
@@ -1418,6 +1424,8 @@ __device__ __forceinline__ void opt_step_a(Enc *e, uint32_t hdr, uint32_t pos, u
 	const uint32_t probRep = e->isRep[state];
 	repMatchPrice = matchPrice + price1(e, probRep);
 	const uint32_t normalMatchPrice = matchPrice + price0(e, probRep);
+	const uint32_t eq = lz_ballot(rSub == dSub); // bit 8 g + i: byte i of rep g equals byte i here
+	const uint32_t matchByte = lz_shfl(rSub, 0);
 	// the literal's eight decisions, priced whether or not the comparison below will want them: B is still busy
 	uint32_t litFull;
 	{
@@ -1469,7 +1477,8 @@ __device__ __forceinline__ void opt_step_a(Enc *e, uint32_t hdr, uint32_t pos, u
 	*reinterpret_cast<uint4 *>(&k->naf) = make_uint4(numAvailFull, hdr, state, posState);
 	*reinterpret_cast<uint4 *>(k->reps) = make_uint4(reps[0], reps[1], reps[2], reps[3]);
 	*reinterpret_cast<uint4 *>(&k->matchPrice) = make_uint4(matchPrice, repMatchPrice, normalMatchPrice, litPrice);
-	*reinterpret_cast<uint4 *>(&k->nextIsLit) = make_uint4(nextIsLit ? 1u : 0u, curByte, matchByte, last);
+	const bool litRep0 = !nextIsLit && litPrice != 0 && matchByte != curByte && (eq & 6u) == 6u; // LIT : REP_0 is worth a look
+	*reinterpret_cast<uint4 *>(&k->nextIsLit) = make_uint4(litRep0 ? 1u : 0u, eq, 0u, last);
 	bar_arrive(kBarGo);
 	pending = true;
 }
@@ -1477,7 +1486,7 @@ __device__ __forceinline__ void opt_step_a(Enc *e, uint32_t hdr, uint32_t pos, u
 // Warp B: the rep / match half of the position in e->pkt (LzmaEnc.c:1700-1949).
 __device__ __forceinline__ void opt_step_b(Enc *e)
 {
-	const uint32_t lane = lz_lane(), grp = lane >> 3, sub = lane & 7u;
+	const uint32_t lane = lz_lane();
 	const StepPkt *k = &e->pkt;
 	const uint4 k0 = *reinterpret_cast<const uint4 *>(&k->cmd), k1 = *reinterpret_cast<const uint4 *>(&k->naf);
 	const uint4 k2 = *reinterpret_cast<const uint4 *>(k->reps), k3 = *reinterpret_cast<const uint4 *>(&k->matchPrice);
@@ -1485,8 +1494,8 @@ __device__ __forceinline__ void opt_step_b(Enc *e)
 	const uint32_t cur = k0.y, pos = k0.z, position = k0.w, numAvailFull = k1.x, hdr = k1.y, state = k1.z, posState = k1.w;
 	uint32_t reps[kNumReps] = { k2.x, k2.y, k2.z, k2.w };
 	const uint32_t repMatchPrice = k3.y, normalMatchPrice = k3.z, litPrice = k3.w;
-	const bool nextIsLit = k4.x != 0;
-	const uint32_t curByte = k4.y, matchByte = k4.z;
+	const bool litRep0 = k4.x != 0;
+	const uint32_t eq = k4.y;
 	uint32_t last = k4.w;
 	const uint32_t fb = e->fb, pbMask = e->pbMask;
 	const uint32_t *b = e->lkRing + (pos & (kLkSlots - 1)) * kLkWords;
@@ -1498,14 +1507,6 @@ __device__ __forceinline__ void opt_step_b(Enc *e)
 		pDist = b[2 + 2 * lane];
 		pW = b[1 + kLkMaxList + lane];
 	}
-	const uint32_t dSub = data[sub];
-	// ---- bytes from far back, all in flight at once: group g compares the first eight bytes of rep g
-	uint32_t myRep = reps[0];
-	myRep = grp == 1 ? reps[1] : myRep;
-	myRep = grp == 2 ? reps[2] : myRep;
-	myRep = grp == 3 ? reps[3] : myRep;
-	const uint32_t rSub = (data - myRep)[sub];
-	const uint32_t eq = lz_ballot(rSub == dSub); // bit 8 g + i: byte i of rep g equals byte i here
 	uint32_t repMask = 0;
 	for (uint32_t q = 0; q < kNumReps; q++)
 		repMask |= ((eq >> (8 * q)) & 3u) == 3u ? 1u << q : 0u;
@@ -1520,7 +1521,7 @@ __device__ __forceinline__ void opt_step_b(Enc *e)
 		}
 	}
 	// LIT : REP_0 (bytes 1 and 2 behind rep0 equal; numAvailFull >= fb > 2)
-	if (!nextIsLit && litPrice != 0 && matchByte != curByte && (eq & 6u) == 6u) {
+	if (litRep0) {
 		const uint8_t *data2 = data - reps[0];
 		uint32_t len, limit = fb + 1;
 		if (limit > numAvailFull)
