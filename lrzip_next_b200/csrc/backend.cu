@@ -374,10 +374,23 @@ __global__ void __launch_bounds__(160, 1) lzma_block_kernel(LzmaJob *jobs)
 	if (threadIdx.x >= 128) {
 		// warp 4: the rep / match half of every staged position, one position behind warp 0 (lzma_enc.cuh: opt_step_b)
 		for (;;) {
+#if defined(LZ_PROF)
+			const long long w0 = clock64();
+#endif
 			lzma::bar_wait(lzma::kBarGo);
 			if (*(volatile uint32_t *)&e->pkt.cmd == 0)
 				return;
+#if defined(LZ_PROF)
+			const long long w1 = clock64();
+#endif
 			lzma::opt_step_b(e);
+#if defined(LZ_PROF)
+			if (threadIdx.x == 128) {
+				e->prof[22] += (uint64_t)(w1 - w0);
+				e->prof[23] += (uint64_t)(clock64() - w1);
+				e->profN[22]++;
+			}
+#endif
 			lzma::bar_arrive(lzma::kBarDone);
 		}
 	}
@@ -425,6 +438,9 @@ __global__ void __launch_bounds__(160, 1) lzma_block_kernel(LzmaJob *jobs)
 			       (unsigned long long)e->prof[i], (unsigned long long)e->profN[i],
 			       e->profN[i] ? (double)e->prof[i] / e->profN[i] : 0.0);
 		printf("[lzprof] pos mismatch %llu\n", (unsigned long long)e->profN[20]);
+		printf("[lzprof] warp A waits for B: %.0f cyc / position (%llu waits); warp B waits for A: %.0f, works: %.0f cyc / position\n",
+		       e->profN[21] ? (double)e->prof[21] / e->profN[21] : 0.0, (unsigned long long)e->profN[21],
+		       e->profN[22] ? (double)e->prof[22] / e->profN[22] : 0.0, e->profN[22] ? (double)e->prof[23] / e->profN[22] : 0.0);
 	}
 #endif
 	int verdict = 1;

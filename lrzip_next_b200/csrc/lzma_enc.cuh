@@ -1339,7 +1339,14 @@ LZ_INL void split_drain(Enc *e, bool &pending, uint32_t &last)
 {
 	if (!pending)
 		return;
+#if defined(LZ_PROF)
+	const long long w0_ = clock64();
+#endif
 	bar_wait(kBarDone);
+#if defined(LZ_PROF)
+	e->prof[21] += (uint64_t)(clock64() - w0_);
+	e->profN[21]++;
+#endif
 	pending = false;
 	last = *(volatile uint32_t *)&e->lastB;
 }
@@ -1358,6 +1365,7 @@ __device__ __forceinline__ void opt_step_a(Enc *e, uint32_t hdr, uint32_t pos, u
 	e->additionalOffset++;
 	e->numAvail = e->n - (pos - 1);
 	e->pos = pos + 1;
+	LZ_T(2);
 	position++;
 	const uint32_t curPrice = c0.x, curLen = c0.z, curDist = c0.w, curExtra = c0.y >> 16;
 	uint32_t prev = cur - curLen, state;
@@ -1414,6 +1422,7 @@ __device__ __forceinline__ void opt_step_a(Enc *e, uint32_t hdr, uint32_t pos, u
 	myRep = grp == 2 ? reps[2] : myRep;
 	myRep = grp == 3 ? reps[3] : myRep;
 	const uint32_t rSub = (data - myRep)[sub];
+	LZ_T(3);
 	const uint32_t posState = position & pbMask;
 	uint32_t matchPrice, litPrice, repMatchPrice;
 	{
@@ -1426,6 +1435,7 @@ __device__ __forceinline__ void opt_step_a(Enc *e, uint32_t hdr, uint32_t pos, u
 	const uint32_t normalMatchPrice = matchPrice + price0(e, probRep);
 	const uint32_t eq = lz_ballot(rSub == dSub); // bit 8 g + i: byte i of rep g equals byte i here
 	const uint32_t matchByte = lz_shfl(rSub, 0);
+	LZ_T(4);
 	// the literal's eight decisions, priced whether or not the comparison below will want them: B is still busy
 	uint32_t litFull;
 	{
@@ -1447,8 +1457,10 @@ __device__ __forceinline__ void opt_step_a(Enc *e, uint32_t hdr, uint32_t pos, u
 	const uint32_t shortRepPrice = srCand ? repMatchPrice + price_short_rep(e, state, posState) : 0;
 	headNext = *reinterpret_cast<const volatile uint64_t *>(&e->lkHead[(pos + 1) & (kLkSlots - 1)][0]);
 
+	LZ_T(5);
 	// ---- cell cur + 1 must now hold everything position cur - 1 wrote
 	split_drain(e, pending, last);
+	LZ_T(6);
 	const uint4 n0 = *reinterpret_cast<const uint4 *>(nextOpt);
 	uint32_t nPrice = n0.x, nLen = n0.z, nDist = n0.w;
 	bool nextIsLit = false;
@@ -1471,6 +1483,7 @@ __device__ __forceinline__ void opt_step_a(Enc *e, uint32_t hdr, uint32_t pos, u
 			nextIsLit = false;
 		}
 	}
+	LZ_T(7);
 	// the rep / match half goes to warp B
 	StepPkt *k = &e->pkt;
 	*reinterpret_cast<uint4 *>(&k->cmd) = make_uint4(1u, cur, pos, position);
@@ -1481,6 +1494,7 @@ __device__ __forceinline__ void opt_step_a(Enc *e, uint32_t hdr, uint32_t pos, u
 	*reinterpret_cast<uint4 *>(&k->nextIsLit) = make_uint4(litRep0 ? 1u : 0u, eq, 0u, last);
 	bar_arrive(kBarGo);
 	pending = true;
+	LZ_T(8);
 }
 
 // Warp B: the rep / match half of the position in e->pkt (LzmaEnc.c:1700-1949).
