@@ -16,6 +16,7 @@
  *   lrzgpu_chunk_begin_all / _select    the same window for every value of insert_hash()'s static victim_round
  *                                       (src/rzip.c:308), so that windows need not wait for their predecessor
  *   lrzgpu_decompress                   runzip_fd()          src/runzip.c:372 (the inverse path, 8(f1))
+ *   lrzgpu_info                         get_fileinfo()       src/lrzip.c:1069 (`-i`, 8(f4))
  *   lrzgpu_rzip_chunk                   hash_search()        src/rzip.c:586 with the scan primitives
  *                                       full_tag/next_tag/match_len, lrzip_private.h:573-576
  *   lrzgpu_tag_scan                     single_full_tag()/single_next_tag()  src/rzip.c:385-416
@@ -171,6 +172,41 @@ int lrzgpu_chunk_select(lrzgpu_ctx *ctx, int64_t victim_in, lrzgpu_stats *stats)
  * the device (literals scattered by all SMs, matches in order); chunk CRC-32 and the trailing MD5 are verified.
  * Stored and LZMA blocks only (zstd and the other back ends: LRZGPU_EUNSUPPORTED); no encryption, no filters. */
 int lrzgpu_decompress(lrzgpu_ctx *ctx, const uint8_t *archive, int64_t archive_len, uint8_t **out, int64_t *out_len);
+
+/* Archive walker (get_fileinfo, src/lrzip.c:1069-1459, what `lrzip-next -i [-vv]` prints): host only, no device.
+ * Walks magic, chunks, the two streams' block chains and the trailing MD5 of an archive in memory, fills `info`
+ * and, when `blocks` is given, up to `cap` block records in the order the reference lists them (per chunk: stream 0's
+ * chain, then stream 1's).  *nblocks receives the number of blocks in the archive.  LRZGPU_EINVAL on a malformed
+ * container, LRZGPU_EUNSUPPORTED for encrypted archives (their block headers are encrypted). */
+typedef struct lrzgpu_archive_info {
+	int major, minor;          /* magic bytes 4-5 */
+	int64_t expected_size;     /* magic bytes 6-13 (st_size) */
+	int hash_type;             /* magic byte 14: 1 = MD5 ... */
+	int encrypted;             /* magic byte 15 */
+	int filter, delta;         /* magic byte 16 decoded: LRZGPU_FILTER_*, delta distance */
+	int backend_code;          /* magic byte 17 & 15: 0 none, 1 lzma, 4 zstd, ... (src/lrzip.c:160-200) */
+	int backend_prop;          /* magic byte 18: lzma dictionary code / zstd level */
+	uint32_t lzma_dict_size;   /* decoded from backend_prop when backend_code == 1 */
+	int rzip_level, level;     /* magic byte 19 */
+	int64_t chunks, blocks;
+	int64_t stream_c_bytes[2]; /* compressed payload bytes per stream (sum of c_len) */
+	int64_t stream_u_bytes[2]; /* uncompressed bytes per stream (sum of u_len) */
+	int64_t blocks_by_ctype[16];
+	int64_t archive_bytes;
+	uint8_t md5[16];           /* trailing digest (hash_type == 1) */
+} lrzgpu_archive_info;
+
+typedef struct lrzgpu_block_info {
+	int64_t chunk;     /* 0-based */
+	int stream;        /* 0 or 1 */
+	int ctype;         /* LRZGPU_CTYPE_* and the reference's other codes */
+	int64_t c_len, u_len;
+	int64_t offset;    /* of the block header in the archive */
+	int64_t next_head; /* as stored (relative to the chunk's first stream header), 0 = last of its stream */
+} lrzgpu_block_info;
+
+int lrzgpu_info(const uint8_t *archive, int64_t archive_len, lrzgpu_archive_info *info, lrzgpu_block_info *blocks,
+		int64_t cap, int64_t *nblocks);
 
 /* rzip of one chunk -> stream 0 / stream 1 bytes (malloc'ed). */
 int lrzgpu_rzip_chunk(lrzgpu_ctx *ctx, const uint8_t *in, int64_t n, int rzip_level, int chunk_bytes,

@@ -58,6 +58,37 @@ def make_params(level=7, rzip_level=0, backend=BACKEND_NONE, threads=1, window=0
                   threshold, nobemt, filter, delta)
 
 
+class ArchiveInfo(C.Structure):
+    """lrzgpu_archive_info (include/lrzgpu.h): what `lrzip-next -i` reports."""
+    _fields_ = [("major", C.c_int), ("minor", C.c_int), ("expected_size", C.c_int64), ("hash_type", C.c_int),
+                ("encrypted", C.c_int), ("filter", C.c_int), ("delta", C.c_int), ("backend_code", C.c_int),
+                ("backend_prop", C.c_int), ("lzma_dict_size", C.c_uint32), ("rzip_level", C.c_int), ("level", C.c_int),
+                ("chunks", C.c_int64), ("blocks", C.c_int64), ("stream_c_bytes", C.c_int64 * 2),
+                ("stream_u_bytes", C.c_int64 * 2), ("blocks_by_ctype", C.c_int64 * 16), ("archive_bytes", C.c_int64),
+                ("md5", C.c_uint8 * 16)]
+
+
+class BlockInfo(C.Structure):
+    _fields_ = [("chunk", C.c_int64), ("stream", C.c_int), ("ctype", C.c_int), ("c_len", C.c_int64), ("u_len", C.c_int64),
+                ("offset", C.c_int64), ("next_head", C.c_int64)]
+
+
+def archive_info(archive: bytes):
+    """get_fileinfo (src/lrzip.c:1069) on an archive in memory: (ArchiveInfo, [BlockInfo]).  Host only."""
+    L = load_library()
+    L.lrzgpu_info.argtypes = [C.c_char_p, C.c_int64, C.POINTER(ArchiveInfo), C.POINTER(BlockInfo), C.c_int64,
+                              C.POINTER(C.c_int64)]
+    info, nb = ArchiveInfo(), C.c_int64()
+    rc = L.lrzgpu_info(archive, len(archive), C.byref(info), None, 0, C.byref(nb))
+    if rc:
+        raise LrzGpuError(f"lrzgpu_info: error {rc}")
+    arr = (BlockInfo * max(1, nb.value))()
+    rc = L.lrzgpu_info(archive, len(archive), C.byref(info), arr, nb.value, C.byref(nb))
+    if rc:
+        raise LrzGpuError(f"lrzgpu_info: error {rc}")
+    return info, list(arr[:nb.value])
+
+
 def lib_path() -> str:
     return os.path.join(_HERE, "liblrzgpu.so")
 
@@ -72,7 +103,7 @@ EXPORTS = [
     "lrzgpu_create", "lrzgpu_destroy", "lrzgpu_last_error", "lrzgpu_free", "lrzgpu_version", "lrzgpu_sizing",
     "lrzgpu_compress", "lrzgpu_compress_file", "lrzgpu_compress_device", "lrzgpu_compress_multi", "lrzgpu_compress_chunk",
     "lrzgpu_chunk_begin", "lrzgpu_chunk_finish", "lrzgpu_victim_values", "lrzgpu_chunk_begin_all", "lrzgpu_chunk_select",
-    "lrzgpu_decompress", "lrzgpu_rzip_chunk", "lrzgpu_tag_scan", "lrzgpu_crc32", "lrzgpu_block_compress", "lrzgpu_lz4_gate",
+    "lrzgpu_decompress", "lrzgpu_info", "lrzgpu_rzip_chunk", "lrzgpu_tag_scan", "lrzgpu_crc32", "lrzgpu_block_compress", "lrzgpu_lz4_gate",
     "lrzgpu_k1_launch", "lrzgpu_crc32_launch", "lrzgpu_sm_count",
 ]
 

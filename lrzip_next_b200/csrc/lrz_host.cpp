@@ -216,6 +216,99 @@ void make_magic(uint8_t magic[21], const lrzgpu_params &p, const lrzgpu_sizing_t
 	magic[19] = (uint8_t)((rzl << 4) + p.level);
 }
 
+// ---- archive walker (get_fileinfo, src/lrzip.c:1069-1459) -----------------------------------------------------------
+static int64_t get_le_w(const uint8_t *p, int width)
+{
+	int64_t v = 0;
+	for (int i = 0; i < width; i++)
+		v |= (int64_t)p[i] << (8 * i);
+	return v;
+}
+
+extern "C" int lrzgpu_info(const uint8_t *arc, int64_t len, lrzgpu_archive_info *info, lrzgpu_block_info *blocks, int64_t cap,
+			   int64_t *nblocks)
+{
+	if (!arc || !info || len < 21 + 16 || memcmp(arc, "LRZI", 4))
+		return LRZGPU_EINVAL;
+	memset(info, 0, sizeof(*info));
+	info->major = arc[4];
+	info->minor = arc[5];
+	info->expected_size = get_le_w(arc + 6, 8);
+	info->hash_type = arc[14];
+	info->encrypted = arc[15];
+	// filter byte (src/lrzip.c:323-340 for 0.13+ archives): 128 + coded distance = Delta, else the flag
+	if (arc[16] & 128) {
+		const int i = arc[16] & 127;
+		info->filter = LRZGPU_FILTER_DELTA;
+		info->delta = i <= 16 ? i : (i - 15) * 16;
+	} else
+		info->filter = arc[16];
+	info->backend_code = arc[17] & 15;
+	info->backend_prop = arc[18];
+	if (info->backend_code == 1) { // LZMA2-style dictionary code (src/lrzip.c:245-250): 2^(n/2 + 12), odd: x1.5
+		info->lzma_dict_size = lzma2_dic_from_prop(arc[18]);
+	}
+	info->rzip_level = arc[19] >> 4;
+	info->level = arc[19] & 15;
+	info->archive_bytes = len;
+	if (info->encrypted)
+		return LRZGPU_EUNSUPPORTED;
+	const int64_t tail = info->hash_type ? 16 : 0; // MD5; other digests of the reference are longer and not walked
+	if (info->hash_type > 1)
+		return LRZGPU_EUNSUPPORTED;
+	const int64_t end = len - tail;
+	int64_t pos = 21 + arc[20], nb = 0;
+	for (bool last = false; !last;) {
+		if (pos + 2 > end)
+			return LRZGPU_EINVAL;
+		const int cb = arc[pos], eof = arc[pos + 1];
+		const int64_t hdr = 1 + 3 * (int64_t)cb;
+		if (cb < 1 || cb > 8 || pos + 2 + cb + 2 * hdr > end)
+			return LRZGPU_EINVAL;
+		pos += 2 + cb;
+		const int64_t initial = pos;
+		int64_t chunk_end = initial + 2 * hdr;
+		for (int s = 0; s < 2; s++) {
+			int64_t head = get_le_w(arc + initial + s * hdr + 1 + 2 * cb, cb);
+			while (head) {
+				const int64_t at = initial + head;
+				if (at < initial || at + hdr > end)
+					return LRZGPU_EINVAL;
+				lrzgpu_block_info b;
+				b.chunk = info->chunks;
+				b.stream = s;
+				b.ctype = arc[at];
+				b.c_len = get_le_w(arc + at + 1, cb);
+				b.u_len = get_le_w(arc + at + 1 + cb, cb);
+				b.offset = at;
+				b.next_head = get_le_w(arc + at + 1 + 2 * cb, cb);
+				if (b.c_len < 0 || b.u_len < 0 || at + hdr + b.c_len > end)
+					return LRZGPU_EINVAL;
+				if (blocks && nb < cap)
+					blocks[nb] = b;
+				nb++;
+				info->stream_c_bytes[s] += b.c_len;
+				info->stream_u_bytes[s] += b.u_len;
+				info->blocks_by_ctype[b.ctype & 15]++;
+				if (at + hdr + b.c_len > chunk_end)
+					chunk_end = at + hdr + b.c_len;
+				head = b.next_head;
+			}
+		}
+		info->chunks++;
+		pos = chunk_end;
+		last = eof != 0;
+	}
+	if (pos != end)
+		return LRZGPU_EINVAL;
+	info->blocks = nb;
+	if (tail)
+		memcpy(info->md5, arc + end, 16);
+	if (nblocks)
+		*nblocks = nb;
+	return LRZGPU_OK;
+}
+
 // ---- MD5 ---------------------------------------------------------------------------------------
 Md5::Md5() : a(0x67452301u), b(0xefcdab89u), c(0x98badcfeu), d(0x10325476u), len(0), fill(0) {}
 

@@ -347,3 +347,68 @@ def test_block_filters_match_the_reference_converters():
             R.Delta_Encode(st, delta, b.ctypes.data, n)
             assert np.array_equal(a, b), ("delta", delta, n)
     assert H.hostsim_filter_block(8, 0, None, 0) != 0  # RISC-V: not built, and said so
+
+
+# ---- archive walker: lrzgpu_info against what `lrzip-next -i -vv` prints ---------------------
+def _ref_info(archive: bytes):
+    """Parse the reference's `-i -vv` listing: per-block rows and the totals."""
+    import re
+    import tempfile
+    env = dict(os.environ, LRZIP="NOCONFIG")
+    with tempfile.TemporaryDirectory(dir="/dev/shm" if os.path.isdir("/dev/shm") else None) as d:
+        a = os.path.join(d, "a.lrz")
+        with open(a, "wb") as fh:
+            fh.write(archive)
+        out = subprocess.run([oracle.REF_BIN, "-i", "-vv", a], env=env, capture_output=True, text=True)
+    text = out.stdout + out.stderr
+    blocks, chunk, stream = [], -1, 0
+    for ln in text.splitlines():
+        m = re.match(r"Rzip chunk:\s+(\d+)", ln)
+        if m:
+            chunk = int(m.group(1)) - 1
+        m = re.match(r"Stream:\s+(\d+)", ln)
+        if m:
+            stream = int(m.group(1))
+        m = re.match(r"(\d+)\t(\S+)\t\s*[\d.]+%\t\s*(\d+) /\s*(\d+)\s+(\d+) :\s+(\d+)", ln)
+        if m:
+            blocks.append((chunk, stream, m.group(2), int(m.group(3)), int(m.group(4)), int(m.group(5)), int(m.group(6))))
+    tot = {}
+    for key, pat in (("size", r"Decompressed file size:\s+(\d+)"), ("csize", r"Compressed file size:\s+(\d+)"),
+                     ("md5", r"MD5 Checksum: ([0-9a-f]{32})"), ("dict", r"Dictionary Size = (\d+)"),
+                     ("levels", r"Rzip Compression Level: (\d+), Lrzip-next Compression Level: (\d+)")):
+        m = re.search(pat, text)
+        tot[key] = m.groups() if m else None
+    return blocks, tot, text
+
+
+@pytest.mark.skipif(not oracle.have_ref(), reason="oracle/_ref not built")
+def test_archive_walker_matches_reference_info():
+    rng = np.random.default_rng(21)
+    names = {3: "none", 6: "lzma", 10: "zstd"}
+    cases = [
+        (rng.integers(0, 4, 3_000_000, dtype=np.uint8), oracle.make_params(backend=oracle.BACKEND_LZMA, threads=2), ()),
+        (np.concatenate([datagen.generate("text", 30 << 20), rng.integers(0, 256, 8 << 20, dtype=np.uint8)]),
+         oracle.make_params(backend=0, threads=1, ramsize=100 * 1048576), ()),            # 2 chunks, several stored blocks
+        (datagen.generate("trees", 4 << 20), oracle.make_params(backend=oracle.BACKEND_ZSTD, threads=2), ("--delta=3",)),
+    ]
+    for d, p, extra in cases:
+        arc = oracle.ref_compress(d, p, extra=extra)
+        info, blocks = api.archive_info(arc)
+        rblocks, tot, text = _ref_info(arc)
+        assert rblocks, text
+        assert [(b.chunk, b.stream, names.get(b.ctype, "?"), b.c_len, b.u_len, b.offset, b.next_head) for b in blocks] == rblocks
+        assert info.expected_size == d.size == int(tot["size"][0]) and info.archive_bytes == len(arc) == int(tot["csize"][0])
+        assert bytes(info.md5).hex() == tot["md5"][0]
+        assert (info.rzip_level, info.level) == tuple(int(x) for x in tot["levels"])
+        assert info.chunks == rblocks[-1][0] + 1 and info.blocks == len(rblocks)
+        assert info.stream_u_bytes[1] + info.stream_u_bytes[0] == sum(b[4] for b in rblocks)
+        if tot["dict"]:
+            assert info.lzma_dict_size == int(tot["dict"][0])
+        if extra:
+            assert (info.filter, info.delta) == (128, 3)
+    # a truncated or damaged container is an error, not a listing
+    L = api.load_library()
+    bad = bytearray(arc)
+    bad[30] ^= 0xff
+    with pytest.raises(Exception):
+        api.archive_info(bytes(bad[:len(bad) // 2]))
