@@ -80,6 +80,9 @@ typedef struct lrzgpu_params {
 			     bt4 finder (src/stream.c:456); not reproduced => LRZGPU_EUNSUPPORTED */
 	int filter;       /* LRZGPU_FILTER_* (--x86 --arm --armt --arm64 --ppc --sparc --ia64 --delta), 0 = none */
 	int delta;        /* --delta: the distance in bytes, 1..16 or a multiple of 16 up to 256 (control->delta) */
+	int stdin_mode;   /* reproduce `... | lrzip-next -o out`: the input's size is unknown while it is read, so every
+			     chunk is one mmap buffer of min(ramsize / 3, max_chunk) bytes (src/rzip.c:995-1013, 800-836) and the
+			     block size is derived from the first chunk alone; not with -U */
 } lrzgpu_params;
 
 typedef struct lrzgpu_sizing_t {

@@ -30,7 +30,7 @@ class Params(C.Structure):
     _fields_ = [("level", C.c_int), ("rzip_level", C.c_int), ("backend", C.c_int), ("threads", C.c_int),
                 ("window", C.c_int), ("unlimited", C.c_int), ("ramsize", C.c_int64), ("page_size", C.c_int),
                 ("processors", C.c_int), ("threshold", C.c_int), ("nobemt", C.c_int),
-                ("filter", C.c_int), ("delta", C.c_int)]
+                ("filter", C.c_int), ("delta", C.c_int), ("stdin_mode", C.c_int)]
 
 
 class Sizing(C.Structure):
@@ -53,9 +53,9 @@ class Stats(C.Structure):
 
 def make_params(level=7, rzip_level=0, backend=BACKEND_NONE, threads=1, window=0, unlimited=0,
                 ramsize=100 * 100 * 1048576, page_size=4096, processors=8, threshold=100, nobemt=0,
-                filter=0, delta=0) -> Params:
+                filter=0, delta=0, stdin_mode=0) -> Params:
     return Params(level, rzip_level, backend, threads, window, unlimited, ramsize, page_size, processors,
-                  threshold, nobemt, filter, delta)
+                  threshold, nobemt, filter, delta, stdin_mode)
 
 
 class ArchiveInfo(C.Structure):

@@ -61,8 +61,27 @@ static int64_t lzma_overhead_for(uint32_t dict) // src/util.c:130
 // Window policy src/rzip.c:995-1013 + 1046-1049, thread count src/stream.c:1090-1102, block size
 // src/stream.c:1169-1323 (evaluated once per archive with the first chunk's size as chunk_limit; the
 // test malloc of :1291-1306 is taken to succeed).
-int compute_sizing(const lrzgpu_params &p, int64_t st_size, lrzgpu_sizing_t &o)
+int compute_sizing(const lrzgpu_params &p, int64_t st_size_in, lrzgpu_sizing_t &o)
 {
+	int64_t st_size = st_size_in;
+	// STDIN (src/rzip.c:969-972, 1001-1013, mmap_stdin :800-836): the size is not known in advance.  Every chunk is one
+	// anonymous mmap of max_mmap = min(maxram, max_chunk) bytes filled from the pipe (the last one shrunk to what was
+	// read), and when the streams are opened control->st_size holds the bytes read so far = the first chunk.
+	int64_t stdin_chunk = 0;
+	if (p.stdin_mode) {
+		if (p.unlimited || p.ramsize <= 0 || p.page_size <= 0)
+			return LRZGPU_EUNSUPPORTED;
+		int64_t maxram = p.ramsize / 3; // setup_ram, src/util.c:179-188 (not STDOUT)
+		maxram -= maxram % p.page_size;
+		if (!maxram)
+			maxram = p.page_size;
+		const int64_t mc = p.window ? (int64_t)p.window * kChunkMultiple : p.ramsize / 3 * 2;
+		stdin_chunk = maxram < mc ? maxram : mc;
+		if (st_size >= stdin_chunk && st_size % stdin_chunk == 0)
+			return LRZGPU_EUNSUPPORTED; // the reference would append an empty chunk after the last full one
+		if (st_size > stdin_chunk)
+			st_size = stdin_chunk;
+	}
 	if (p.level < 1 || p.level > 9 || p.rzip_level < 0 || p.rzip_level > 9 || p.page_size <= 0 || p.threads < 1 ||
 	    p.ramsize <= 0)
 		return LRZGPU_EINVAL;
@@ -106,6 +125,8 @@ int compute_sizing(const lrzgpu_params &p, int64_t st_size, lrzgpu_sizing_t &o)
 		if (!max_chunk)
 			max_chunk = p.page_size;
 	}
+	if (stdin_chunk)
+		max_chunk = stdin_chunk;
 	int64_t chunk_limit = max_chunk < st_size ? max_chunk : st_size;
 	if (chunk_limit < p.page_size)
 		chunk_limit = p.page_size;

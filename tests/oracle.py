@@ -181,8 +181,9 @@ def ref_flags(params: Params):
     return f
 
 
-def ref_compress(data, params: Params, workdir: str | None = None, extra=()) -> bytes:
-    """Run the unmodified reference binary (oracle/_ref/lrzip-next) file -> file."""
+def ref_compress(data, params: Params, workdir: str | None = None, extra=(), via_stdin: bool = False) -> bytes:
+    """Run the unmodified reference binary (oracle/_ref/lrzip-next) file -> file, or pipe -> file (via_stdin: the
+    reference's STDIN mode, where the input's size is unknown while it is read)."""
     env = dict(os.environ, LRZIP="NOCONFIG")
     with tempfile.TemporaryDirectory(dir=workdir or ("/dev/shm" if os.path.isdir("/dev/shm") else None)) as d:
         src = os.path.join(d, "in.bin")
@@ -192,8 +193,13 @@ def ref_compress(data, params: Params, workdir: str | None = None, extra=()) -> 
                 fh.write(data)
         else:
             np.ascontiguousarray(data, dtype=np.uint8).tofile(src)
-        subprocess.run([REF_BIN, *ref_flags(params), *extra, "-o", dst, src], check=True, env=env,
-                       stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+        if via_stdin:
+            with open(src, "rb") as fin:
+                subprocess.run([REF_BIN, *ref_flags(params), *extra, "-o", dst], check=True, env=env, stdin=fin,
+                               stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+        else:
+            subprocess.run([REF_BIN, *ref_flags(params), *extra, "-o", dst, src], check=True, env=env,
+                           stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
         with open(dst, "rb") as fh:
             return fh.read()
 

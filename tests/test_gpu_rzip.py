@@ -210,3 +210,18 @@ def test_compress_multi_equals_single_context(ctx):
     assert got == want
     assert st["chunks"] == 3 and st["chain_evictions"] == st1["chain_evictions"] > 0
     assert st["lookups"] == st1["lookups"] and st["matches"] == st1["matches"]
+
+
+@pytest.mark.skipif(not oracle.have_ref(), reason="oracle/_ref not built")
+def test_stdin_mode_archive_bit_identical_to_reference_pipe_run(ctx):
+    """`cat f | lrzip-next -o out` (STDIN mode: chunks of one mmap buffer, the last one shrunk at EOF, block size from the
+    first chunk) against lrzgpu_params.stdin_mode = 1: three chunks, byte-identical; and the small-file
+    case where pipe and file runs coincide."""
+    d = datagen.generate("text", 80 << 20)
+    kw = dict(backend=0, threads=1, ramsize=100 * 1048576)
+    want = oracle.ref_compress(d, oracle.make_params(**kw), via_stdin=True)
+    got = ctx.compress(d, make_params(stdin_mode=1, **kw))
+    assert got == want
+    assert got != ctx.compress(d, make_params(**kw))  # the file -> file archive has two larger chunks
+    small = d[:20 << 20]
+    assert ctx.compress(small, make_params(stdin_mode=1, **kw)) == oracle.ref_compress(small, oracle.make_params(**kw), via_stdin=True)

@@ -412,3 +412,26 @@ def test_archive_walker_matches_reference_info():
     bad[30] ^= 0xff
     with pytest.raises(Exception):
         api.archive_info(bytes(bad[:len(bad) // 2]))
+
+
+@pytest.mark.skipif(not oracle.have_ref(), reason="oracle/_ref not built")
+def test_stdin_mode_sizing_matches_reference_pipe_run():
+    """STDIN chunk policy (src/rzip.c:969-1013, 800-836): `cat f | lrzip-next -o out` cuts the input into
+    mmap-buffer sized chunks (ramsize / 3) instead of 2/3-of-RAM windows; lrzgpu_sizing(stdin_mode=1) must predict the
+    chunk and block structure of the reference's pipe-made archive."""
+    d = datagen.generate("text", 80 << 20)
+    kw = dict(backend=0, threads=1, ramsize=100 * 1048576)
+    arc = oracle.ref_compress(d, oracle.make_params(**kw), via_stdin=True)
+    info, blocks = api.archive_info(arc)
+    sz = api.sizing(api.make_params(stdin_mode=1, **kw), d.size)
+    assert sz.max_chunk == 34951168  # 100 MiB / 3, rounded down to a page
+    nch = -(-d.size // sz.max_chunk)
+    assert info.chunks == nch == 3 and info.expected_size == d.size
+    per_chunk = [sum(b.u_len for b in blocks if b.chunk == c and b.stream == 1) for c in range(nch)]
+    s1_blocks = [sum(1 for b in blocks if b.chunk == c and b.stream == 1) for c in range(nch)]
+    assert s1_blocks == [-(-n // sz.bufsize) for n in per_chunk]
+    # the file -> file run of the same input uses 2/3-of-RAM windows: a different archive
+    sz_file = api.sizing(api.make_params(**kw), d.size)
+    assert sz_file.max_chunk > sz.max_chunk
+    with pytest.raises(Exception):
+        api.sizing(api.make_params(stdin_mode=1, unlimited=1, **kw), d.size)
