@@ -173,7 +173,8 @@ int lrzgpu_chunk_select(lrzgpu_ctx *ctx, int64_t victim_in, lrzgpu_stats *stats)
  * host memory -> the original bytes (malloc'ed).  Container walk on the host; LZMA blocks (lzma_decompress_buf,
  * src/stream.c:556-616) decoded on the device, one thread per block; stream 0 parsed into records and replayed on
  * the device (literals scattered by all SMs, matches in order); chunk CRC-32 and the trailing MD5 are verified.
- * Stored and LZMA blocks only (zstd and the other back ends: LRZGPU_EUNSUPPORTED); no encryption, no filters. */
+ * Stored and LZMA blocks only (zstd and the other back ends: LRZGPU_EUNSUPPORTED); filtered archives are unfiltered
+ * per stream-1 block (all filters but RISC-V); no encryption. */
 int lrzgpu_decompress(lrzgpu_ctx *ctx, const uint8_t *archive, int64_t archive_len, uint8_t **out, int64_t *out_len);
 
 /* Archive walker (get_fileinfo, src/lrzip.c:1069-1459, what `lrzip-next -i [-vv]` prints): host only, no device.

@@ -18,7 +18,7 @@ __device__ __forceinline__ int64_t block_len(int64_t k, int64_t from, int64_t to
 }
 
 // One thread per aligned 32-bit word of a block (the tail of 1-3 bytes is left alone, like the reference's size &= ~3).
-__global__ void __launch_bounds__(256) filter_words_kernel(uint8_t *s, int64_t from, int64_t to, int64_t bs, int filter)
+__global__ void __launch_bounds__(256) filter_words_kernel(uint8_t *s, int64_t from, int64_t to, int64_t bs, int filter, bool enc)
 {
 	const int64_t k = blockIdx.y;
 	uint8_t *b = s + from + k * bs;
@@ -26,7 +26,7 @@ __global__ void __launch_bounds__(256) filter_words_kernel(uint8_t *s, int64_t f
 	for (int64_t w = (int64_t)blockIdx.x * 256 + threadIdx.x; w < words; w += (int64_t)gridDim.x * 256) {
 		uint8_t *p = b + 4 * w; // a block starts at a multiple of the block size inside a 256-byte aligned buffer
 		const uint32_t v = (uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16) | ((uint32_t)p[3] << 24);
-		const uint32_t c = flt::conv_word(filter, v, (uint32_t)(4 * w));
+		const uint32_t c = flt::conv_word(filter, v, (uint32_t)(4 * w), enc);
 		if (c != v) {
 			p[0] = (uint8_t)c;
 			p[1] = (uint8_t)(c >> 8);
@@ -37,25 +37,42 @@ __global__ void __launch_bounds__(256) filter_words_kernel(uint8_t *s, int64_t f
 }
 
 // x86 and ARM Thumb: the scan's state runs through the whole block: one thread per block.
-__global__ void filter_serial_kernel(uint8_t *s, int64_t from, int64_t to, int64_t bs, int filter)
+__global__ void filter_serial_kernel(uint8_t *s, int64_t from, int64_t to, int64_t bs, int filter, bool enc)
 {
 	if (threadIdx.x)
 		return;
 	const int64_t k = blockIdx.x;
 	if (filter == flt::kX86)
-		flt::x86_encode(s + from + k * bs, (size_t)block_len(k, from, to, bs));
+		flt::x86_convert(s + from + k * bs, (size_t)block_len(k, from, to, bs), enc);
 	else
-		flt::armt_encode(s + from + k * bs, (size_t)block_len(k, from, to, bs));
+		flt::armt_convert(s + from + k * bs, (size_t)block_len(k, from, to, bs), enc);
+}
+
+// Delta, decode side (Delta_Decode): out[i] = in[i] + out[i - delta] is a running sum along each residue class
+// modulo delta: one thread per class and block.
+__global__ void delta_decode_kernel(uint8_t *s, int64_t from, int64_t to, int64_t bs, int delta)
+{
+	const int64_t k = blockIdx.x;
+	uint8_t *b = s + from + k * bs;
+	const int64_t n = block_len(k, from, to, bs);
+	const int r = threadIdx.x;
+	if (r >= delta)
+		return;
+	uint8_t acc = r < n ? b[r] : 0;
+	for (int64_t i = (int64_t)r + delta; i < n; i += delta) {
+		acc = (uint8_t)(acc + b[i]);
+		b[i] = acc;
+	}
 }
 
 // IA64: one thread per 16-byte bundle.
-__global__ void __launch_bounds__(256) filter_ia64_kernel(uint8_t *s, int64_t from, int64_t to, int64_t bs)
+__global__ void __launch_bounds__(256) filter_ia64_kernel(uint8_t *s, int64_t from, int64_t to, int64_t bs, bool enc)
 {
 	const int64_t k = blockIdx.y;
 	uint8_t *b = s + from + k * bs;
 	const int64_t bundles = block_len(k, from, to, bs) >> 4;
 	for (int64_t w = (int64_t)blockIdx.x * 256 + threadIdx.x; w < bundles; w += (int64_t)gridDim.x * 256)
-		flt::ia64_bundle(b + 16 * w, (uint32_t)(16 * w));
+		flt::ia64_bundle(b + 16 * w, (uint32_t)(16 * w), enc);
 }
 
 // Delta in place, two passes so that no CTA reads bytes another CTA has already replaced: first every tile's `delta`
@@ -104,7 +121,7 @@ size_t filter_side_bytes(int filter, int64_t span, int64_t bs)
 
 // Convert the stream blocks that make up s[from, to) in place (from is a block boundary).  side: filter_side_bytes().
 int filter_blocks_launch(int filter, int delta, uint8_t *s, int64_t from, int64_t to, int64_t bs, uint8_t *side,
-			 cudaStream_t stream, int64_t *launches)
+			 cudaStream_t stream, int64_t *launches, bool enc)
 {
 	if (filter == flt::kNone || to <= from)
 		return 0;
@@ -120,18 +137,24 @@ int filter_blocks_launch(int filter, int delta, uint8_t *s, int64_t from, int64_
 			gx = 1184; // 8 CTAs on each of 148 SMs, grid-stride
 		if (gx == 0)
 			gx = 1;
-		filter_words_kernel<<<dim3(gx, (unsigned)nblk), 256, 0, stream>>>(s, from, to, bs, filter);
+		filter_words_kernel<<<dim3(gx, (unsigned)nblk), 256, 0, stream>>>(s, from, to, bs, filter, enc);
 		if (launches)
 			*launches += 1;
 	} else if (filter == flt::kX86 || filter == flt::kARMT) {
-		filter_serial_kernel<<<(unsigned)nblk, 32, 0, stream>>>(s, from, to, bs, filter);
+		filter_serial_kernel<<<(unsigned)nblk, 32, 0, stream>>>(s, from, to, bs, filter, enc);
 		if (launches)
 			*launches += 1;
 	} else if (filter == flt::kIA64) {
 		const int64_t bundles = (bs < to - from ? bs : to - from) >> 4;
 		unsigned gx = (unsigned)((bundles + 255) / 256);
 		gx = gx > 1184 ? 1184 : (gx ? gx : 1);
-		filter_ia64_kernel<<<dim3(gx, (unsigned)nblk), 256, 0, stream>>>(s, from, to, bs);
+		filter_ia64_kernel<<<dim3(gx, (unsigned)nblk), 256, 0, stream>>>(s, from, to, bs, enc);
+		if (launches)
+			*launches += 1;
+	} else if (!enc) { // delta, decode side
+		if (delta < 1 || delta > kDeltaMax)
+			return -1;
+		delta_decode_kernel<<<(unsigned)nblk, 256, 0, stream>>>(s, from, to, bs, delta);
 		if (launches)
 			*launches += 1;
 	} else { // delta
@@ -154,6 +177,7 @@ int filter_preload()
 	ok = ok && cudaFuncGetAttributes(&a, filter_serial_kernel) == cudaSuccess;
 	ok = ok && cudaFuncGetAttributes(&a, filter_ia64_kernel) == cudaSuccess;
 	ok = ok && cudaFuncGetAttributes(&a, delta_save_kernel) == cudaSuccess;
+	ok = ok && cudaFuncGetAttributes(&a, delta_decode_kernel) == cudaSuccess;
 	ok = ok && cudaFuncGetAttributes(&a, delta_apply_kernel) == cudaSuccess;
 	return ok ? 0 : -1;
 }

@@ -43,20 +43,23 @@ FLT_FN uint32_t bswap32(uint32_t v) { return (v >> 24) | ((v >> 8) & 0xff00u) | 
 
 // ARM: 0xEB in the top byte = BL with condition "always".  Its 24-bit field counts words from the instruction two
 // ahead; the filter makes it the absolute word index of the target.
-FLT_FN uint32_t conv_arm(uint32_t w, uint32_t off)
+// (every converter below takes `enc`: true adds the position -- compress side -- false subtracts it again -- the
+// decode path, z7_BranchConv_*_Dec; the instruction test reads bits the conversion never changes)
+FLT_FN uint32_t conv_arm(uint32_t w, uint32_t off, bool enc)
 {
 	if ((w >> 24) != 0xEBu)
 		return w;
-	return ((w + ((off + 8) >> 2)) & 0x00ffffffu) | 0xEB000000u;
+	const uint32_t c = (off + 8) >> 2;
+	return ((enc ? w + c : w - c) & 0x00ffffffu) | 0xEB000000u;
 }
 
 // ARM64: BL (top six bits 100101, imm26 in words from the instruction itself) and ADRP (1 immlo 10000 immhi Rd: a
 // 21-bit page delta, converted only while it stays within +-2^17 pages so that data that merely looks like ADRP is
 // rarely touched).
-FLT_FN uint32_t conv_arm64(uint32_t w, uint32_t off)
+FLT_FN uint32_t conv_arm64(uint32_t w, uint32_t off, bool enc)
 {
 	if ((w & 0xfc000000u) == 0x94000000u)
-		return ((w + (off >> 2)) & 0x03ffffffu) | 0x94000000u;
+		return ((enc ? w + (off >> 2) : w - (off >> 2)) & 0x03ffffffu) | 0x94000000u;
 	if ((w & 0x9f000000u) != 0x90000000u)
 		return w;
 	const uint32_t flag = 1u << 20, mask = (1u << 24) - (flag << 1);
@@ -64,46 +67,47 @@ FLT_FN uint32_t conv_arm64(uint32_t w, uint32_t off)
 	if (v & mask)
 		return w;
 	uint32_t z = (v & 0xffffffe0u) | (v >> 26); // immhi (biased) : immlo, as a number shifted left by 3
-	z += (off >> 9) & ~7u;                      // + this instruction's page number, same scale
+	const uint32_t pg = (off >> 9) & ~7u;       // this instruction's page number, same scale
+	z = enc ? z + pg : z - pg;
 	v = (v & 0x1fu) | 0x90000000u | (z << 26);  // Rd, opcode, new immlo
 	v |= 0x00ffffe0u & ((z & ((flag << 1) - 1)) - flag); // new immhi, bias removed
 	return v;
 }
 
 // PowerPC: "bl target" = opcode 18 with AA = 0, LK = 1; LI (24 bits, in words) is relative to the instruction.
-FLT_FN uint32_t conv_ppc(uint32_t w, uint32_t off)
+FLT_FN uint32_t conv_ppc(uint32_t w, uint32_t off, bool enc)
 {
 	uint32_t v = bswap32(w);
 	if ((v & 0xfc000003u) != 0x48000001u)
 		return w;
-	v = ((v + off) & 0x03ffffffu) | 0x48000000u;
+	v = ((enc ? v + off : v - off) & 0x03ffffffu) | 0x48000000u;
 	return bswap32(v);
 }
 
 // SPARC: "call" = 01 + disp30 (words).  Converted when the displacement is a sign-extended 22-bit number, i.e. the
 // top ten bits are 01 00000000 or 01 11111111; the absolute target keeps that form (sign re-extended from bit 22).
-FLT_FN uint32_t conv_sparc(uint32_t w, uint32_t off)
+FLT_FN uint32_t conv_sparc(uint32_t w, uint32_t off, bool enc)
 {
 	uint32_t v = bswap32(w);
 	const uint32_t top = v >> 22;
 	if (top != 0x100u && top != 0x1ffu)
 		return w;
-	uint32_t d = ((v << 2) + off) >> 2;                       // absolute word index, 30 bits
+	uint32_t d = (enc ? (v << 2) + off : (v << 2) - off) >> 2; // absolute (or relative again) word index, 30 bits
 	d = (((0u - ((d >> 22) & 1u)) << 22) & 0x3fffffffu) | (d & 0x3fffffu) | 0x40000000u;
 	return bswap32(d);
 }
 
-FLT_FN uint32_t conv_word(int f, uint32_t w, uint32_t off)
+FLT_FN uint32_t conv_word(int f, uint32_t w, uint32_t off, bool enc = true)
 {
 	switch (f) {
 	case kARM:
-		return conv_arm(w, off);
+		return conv_arm(w, off, enc);
 	case kARM64:
-		return conv_arm64(w, off);
+		return conv_arm64(w, off, enc);
 	case kPPC:
-		return conv_ppc(w, off);
+		return conv_ppc(w, off, enc);
 	case kSPARC:
-		return conv_sparc(w, off);
+		return conv_sparc(w, off, enc);
 	default:
 		return w;
 	}
@@ -115,7 +119,7 @@ FLT_FN uint32_t conv_word(int f, uint32_t w, uint32_t off)
 // sign byte the value is folded once more so that the transform stays reversible.  In place, whole block, ip = 0.
 FLT_FN bool x86_sign_byte(uint32_t b) { return b == 0 || b == 0xff; }
 
-FLT_FN void x86_encode(uint8_t *buf, size_t n)
+FLT_FN void x86_convert(uint8_t *buf, size_t n, bool enc)
 {
 	if (n < 5)
 		return;
@@ -140,7 +144,7 @@ FLT_FN void x86_encode(uint8_t *buf, size_t n)
 		if (x86_sign_byte(b) && allowed && (mask >> 1) < 0x10) {
 			uint32_t src = (b << 24) | ((uint32_t)buf[i + 3] << 16) | ((uint32_t)buf[i + 2] << 8) | buf[i + 1], dest;
 			for (;;) {
-				dest = src + (uint32_t)(i + 5);
+				dest = enc ? src + (uint32_t)(i + 5) : src - (uint32_t)(i + 5);
 				if (mask == 0)
 					break;
 				const uint32_t m = mask >> 1, bit = m == 0 ? 0 : (m == 1 ? 1 : (m < 4 ? 2 : 3));
@@ -164,16 +168,18 @@ FLT_FN void x86_encode(uint8_t *buf, size_t n)
 	}
 }
 
+FLT_FN void x86_encode(uint8_t *buf, size_t n) { x86_convert(buf, n, true); }
+
 // ARM Thumb: BL is a pair of half-words 11110 imm11(high) / 11111 imm11(low); the 22-bit field counts half-words from
 // the instruction after the pair's first half-word + 2 (i + 4).  After a converted pair the scan moves past it, so the
 // second half-word is never taken for the start of another pair: serial, in place, whole block.
-FLT_FN void armt_encode(uint8_t *buf, size_t n)
+FLT_FN void armt_convert(uint8_t *buf, size_t n, bool enc)
 {
 	for (size_t i = 0; i + 4 <= n; i += 2) {
 		if ((buf[i + 1] & 0xf8) != 0xf0 || (buf[i + 3] & 0xf8) != 0xf8)
 			continue;
 		uint32_t v = (((uint32_t)buf[i + 1] & 7) << 19) | ((uint32_t)buf[i] << 11) | (((uint32_t)buf[i + 3] & 7) << 8) | buf[i + 2];
-		v = ((v << 1) + (uint32_t)i + 4) >> 1;
+		v = (enc ? (v << 1) + ((uint32_t)i + 4) : (v << 1) - ((uint32_t)i + 4)) >> 1;
 		buf[i + 1] = (uint8_t)(0xf0 | ((v >> 19) & 7));
 		buf[i] = (uint8_t)(v >> 11);
 		buf[i + 3] = (uint8_t)(0xf8 | ((v >> 8) & 7));
@@ -182,10 +188,12 @@ FLT_FN void armt_encode(uint8_t *buf, size_t n)
 	}
 }
 
+FLT_FN void armt_encode(uint8_t *buf, size_t n) { armt_convert(buf, n, true); }
+
 // IA64: a 16-byte bundle = 5 template bits + three 41-bit slots; the template says which slots hold branch-unit
 // instructions.  A slot is converted when it is br.call-like (opcode 5, btype 0): its 21-bit immediate (20 bits at 13,
 // sign at 36), in bundles, becomes absolute.  Bundle-local.
-FLT_FN void ia64_bundle(uint8_t *b, uint32_t off)
+FLT_FN void ia64_bundle(uint8_t *b, uint32_t off, bool enc = true)
 {
 	const uint32_t t = b[0] & 0x1f;
 	// slots holding a B unit, by template (10: MIB, 12: MBB, 16: BBB, 18: MMB, 1C: MFB; the odd twin of each ends a group)
@@ -202,7 +210,7 @@ FLT_FN void ia64_bundle(uint8_t *b, uint32_t off)
 		if (((x >> 37) & 0xf) != 5 || ((x >> 9) & 7) != 0)
 			continue;
 		uint32_t v = (uint32_t)((x >> 13) & 0xfffff) | ((uint32_t)((x >> 36) & 1) << 20);
-		v = ((v << 4) + off) >> 4;
+		v = (enc ? (v << 4) + off : (v << 4) - off) >> 4;
 		x &= ~((uint64_t)0x8fffff << 13);
 		x |= (uint64_t)(v & 0xfffff) << 13;
 		x |= (uint64_t)(v & 0x100000) << (36 - 20);

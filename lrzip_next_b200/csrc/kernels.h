@@ -75,7 +75,7 @@ int unrzip_replay_launch(const uint8_t *d_s1, int64_t s1_len, const DecLit *d_li
 // scratch of filter_side_bytes() bytes (Delta only).
 size_t filter_side_bytes(int filter, int64_t span, int64_t bs);
 int filter_blocks_launch(int filter, int delta, uint8_t *s, int64_t from, int64_t to, int64_t bs, uint8_t *side,
-			 cudaStream_t stream, int64_t *launches);
+			 cudaStream_t stream, int64_t *launches, bool enc = true); // enc false: the decode side's inverse
 int filter_preload();
 size_t lzma_dec_prob_bytes(int njobs);
 int lzma_dec_launch(LzmaDecJob *d_jobs, int njobs, void *d_probs, cudaStream_t stream);

@@ -1431,8 +1431,18 @@ int lrzgpu_decompress(lrzgpu_ctx *c, const uint8_t *arc, int64_t arc_len, uint8_
 	// magic header, src/lrzip.c:131-208 (written) / 227-330 (read)
 	if (arc_len < 21 + 16 || memcmp(arc, "LRZI", 4) || arc[4] != 0)
 		return fail(c, LRZGPU_EINVAL, "not an lrzip-next archive");
-	if (arc[15] != 0 || arc[16] != 0)
-		return fail(c, LRZGPU_EUNSUPPORTED, "encrypted or filtered archives are not supported");
+	if (arc[15] != 0)
+		return fail(c, LRZGPU_EUNSUPPORTED, "encrypted archives are not supported");
+	// filter byte (src/lrzip.c:323-340): 128 + coded distance = Delta, else the flag; undone per stream-1 block after
+	// the block is decompressed (src/stream.c:2082-2130)
+	int flt_id = arc[16], flt_delta = 0;
+	if (arc[16] & 128) {
+		const int i = arc[16] & 127;
+		flt_id = LRZGPU_FILTER_DELTA;
+		flt_delta = i <= 16 ? i : (i - 15) * 16;
+	}
+	if (flt_id == LRZGPU_FILTER_RISCV || (flt_id > LRZGPU_FILTER_RISCV && flt_id != LRZGPU_FILTER_DELTA))
+		return fail(c, LRZGPU_EUNSUPPORTED, "filter %d is not supported", flt_id);
 	if (arc[14] != 1)
 		return fail(c, LRZGPU_EUNSUPPORTED, "only MD5 archives are supported (hash code %d)", arc[14]);
 	const int64_t st_size = get_le(arc + 6, 8);
@@ -1525,6 +1535,22 @@ int lrzgpu_decompress(lrzgpu_ctx *c, const uint8_t *arc, int64_t arc_len, uint8_
 			for (const LzmaDecJob &j : jobs)
 				if (j.status || j.produced != j.u_len)
 					return bail(LRZGPU_EINVAL, "corrupt LZMA block");
+		}
+		if (flt_id) { // every stream-1 block was filtered on its own, from its position 0: all but the last are equally long
+			int64_t bs1 = 0, seen = 0;
+			bool uniform = true;
+			for (const ArcBlock &b : blocks)
+				if (b.stream == 1) {
+					if (!bs1)
+						bs1 = b.u_len;
+					else if (seen % bs1)
+						uniform = false; // a short block that is not the last one
+					seen += b.u_len;
+				}
+			if (!uniform)
+				return bail(LRZGPU_EUNSUPPORTED, "filtered archive with irregular stream-1 blocks");
+			if (bs1 && filter_blocks_launch(flt_id, flt_delta, (uint8_t *)c->s1.p, 0, total_u[1], bs1, nullptr, c->sA, &c->launches, false))
+				return bail(LRZGPU_ECUDA, "unfilter launch failed");
 		}
 		// stream 0 -> records, then the replay into the chunk's bytes
 		const int64_t cap = total_u[0] / 3 + 2;

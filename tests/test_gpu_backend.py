@@ -228,6 +228,7 @@ def test_filtered_archives_bit_identical_to_reference(ctx, flt, delta, flag, bac
     want = oracle.ref_compress(d, op, extra=(flag,))
     assert got[16] == want[16] and got[16] != 0
     assert got == want
+    assert ctx.decompress(want) == d.tobytes()  # the decode side undoes the filter per stream-1 block
 
 
 def test_unbuilt_filters_are_rejected(ctx):

@@ -259,14 +259,17 @@ def _filter_libs():
     subprocess.run(["make", "-s", "-C", os.path.join(HERE, "hostsim"), "libfilterhost.so"], check=True)
     H = C.CDLL(os.path.join(HERE, "hostsim", "libfilterhost.so"))
     H.hostsim_filter_block.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_int64]
+    H.hostsim_unfilter_block.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_int64]
     R = C.CDLL(oracle.REF_LZMA)
     for nm in ("ARM", "ARM64", "PPC", "SPARC", "ARMT", "IA64"):
-        f = getattr(R, f"z7_BranchConv_{nm}_Enc")
-        f.argtypes, f.restype = [C.c_void_p, C.c_size_t, C.c_uint32], C.c_void_p
-    R.z7_BranchConvSt_X86_Enc.argtypes = [C.c_void_p, C.c_size_t, C.c_uint32, C.POINTER(C.c_uint32)]
-    R.z7_BranchConvSt_X86_Enc.restype = C.c_void_p
+        for way in ("Enc", "Dec"):
+            f = getattr(R, f"z7_BranchConv_{nm}_{way}")
+            f.argtypes, f.restype = [C.c_void_p, C.c_size_t, C.c_uint32], C.c_void_p
+    for f in (R.z7_BranchConvSt_X86_Enc, R.z7_BranchConvSt_X86_Dec):
+        f.argtypes, f.restype = [C.c_void_p, C.c_size_t, C.c_uint32, C.POINTER(C.c_uint32)], C.c_void_p
     R.Delta_Init.argtypes = [C.c_void_p]
     R.Delta_Encode.argtypes = [C.c_void_p, C.c_uint, C.c_void_p, C.c_size_t]
+    R.Delta_Decode.argtypes = [C.c_void_p, C.c_uint, C.c_void_p, C.c_size_t]
     return H, R
 
 
@@ -335,6 +338,19 @@ def test_block_filters_match_the_reference_converters():
                 else:
                     getattr(R, f"z7_BranchConv_{kind}_Enc")(b.ctypes.data, n, 0)
                 assert np.array_equal(a, b), (kind, n, trial)
+                # the inverse converter (decode path): equal to the reference's decoder on ANY bytes, and a round trip
+                a, b = d.copy(), d.copy()
+                assert H.hostsim_unfilter_block(fid, 0, a.ctypes.data, n) == 0
+                if kind == "X86":
+                    st = C.c_uint32(0)
+                    R.z7_BranchConvSt_X86_Dec(b.ctypes.data, n, 0, C.byref(st))
+                else:
+                    getattr(R, f"z7_BranchConv_{kind}_Dec")(b.ctypes.data, n, 0)
+                assert np.array_equal(a, b), ("decode", kind, n, trial)
+                e = d.copy()
+                H.hostsim_filter_block(fid, 0, e.ctypes.data, n)
+                H.hostsim_unfilter_block(fid, 0, e.ctypes.data, n)
+                assert np.array_equal(e, d), ("round trip", kind, n, trial)
                 if n >= 1000 and trial == 0:
                     assert (b != d).any(), (kind, "the planted instructions were not converted: the test has no teeth")
     for delta in (1, 2, 3, 4, 15, 16, 32, 240, 256):
@@ -346,6 +362,12 @@ def test_block_filters_match_the_reference_converters():
             R.Delta_Init(st)
             R.Delta_Encode(st, delta, b.ctypes.data, n)
             assert np.array_equal(a, b), ("delta", delta, n)
+            a, b = d.copy(), d.copy()
+            assert H.hostsim_unfilter_block(128, delta, a.ctypes.data, n) == 0
+            st = (C.c_ubyte * 256)()
+            R.Delta_Init(st)
+            R.Delta_Decode(st, delta, b.ctypes.data, n)
+            assert np.array_equal(a, b), ("delta decode", delta, n)
     assert H.hostsim_filter_block(8, 0, None, 0) != 0  # RISC-V: not built, and said so
 
 
