@@ -695,6 +695,8 @@ int backend_async_begin(BackendCtx *b, const lrzgpu_params &p, const lrzgpu_sizi
 		cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
 		b->inflight_max = sms > 48 ? sms - 24 : sms / 2; // one parser CTA per SM; the rest stays free for the scan
 	}
+	if (const char *im = getenv("LRZGPU_INFLIGHT")) // development switch: cap on block encoders running at once
+		b->inflight_max = atoi(im) > 0 ? atoi(im) : b->inflight_max;
 	if (cudaFuncSetAttribute(lzma_block_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(lzma::Enc)) != cudaSuccess) {
 		snprintf(err, errlen, "LZMA encoder state (%zu bytes) does not fit in shared memory", sizeof(lzma::Enc));
 		return LRZGPU_ECUDA;
