@@ -181,6 +181,35 @@ __global__ void __launch_bounds__(256) mf_prev_kernel(const uint32_t *__restrict
 	c[V[s]] = (s > 0 && K[s - 1] == K[s]) ? V[s - 1] + 1 : 0;
 }
 
+// The sorted positions go to the block's `sorted` array, and every position that has a predecessor in its bucket gets
+// the length of its common prefix with that predecessor -- the first comparison of its tree insertion -- into its
+// (still unused) record: one thread per position instead of the bucket's thread (lzma_mf.cuh, kMfFirstValid).
+__global__ void __launch_bounds__(256) mf_first_kernel(const uint32_t *__restrict__ K, const uint32_t *__restrict__ V, uint32_t count,
+							const uint8_t *__restrict__ src, MfParams P, uint32_t *__restrict__ sorted,
+							uint64_t *__restrict__ rec)
+{
+	const uint32_t s = blockIdx.x * 256u + threadIdx.x;
+	if (s >= count)
+		return;
+	const uint32_t i = V[s];
+	sorted[s] = i;
+	if (s == 0)
+		return;
+	const uint32_t pi = V[s - 1], pos = i + 1, curMatch = pi + 1;
+	// the same bucket test as the walk's (mf_walk_kernel)
+	if (mf_hash4(c_crc, src + pi, P.hashMask, P.bigHash) != mf_hash4(c_crc, src + i, P.hashMask, P.bigHash))
+		return;
+	const uint32_t cmCheck = pos <= P.cyclicSize ? 0 : pos - P.cyclicSize;
+	if (cmCheck >= curMatch)
+		return; // outside the dictionary: the insertion does not look at it
+	const uint32_t avail = P.n - i, lenLimit = avail < P.fb ? avail : P.fb;
+	const uint8_t *a = src + pi, *b = src + i;
+	uint32_t len = 0;
+	while (len != lenLimit && a[len] == b[len])
+		len++;
+	rec[i] = kMfFirstValid | len;
+}
+
 __global__ void __launch_bounds__(256) mf_copy_kernel(const uint32_t *__restrict__ a, uint32_t count, uint32_t *__restrict__ b)
 {
 	const uint32_t s = blockIdx.x * 256u + threadIdx.x;
@@ -215,13 +244,60 @@ __global__ void __launch_bounds__(128) mf_walk_kernel(const MfBlock *__restrict_
 	const MfParams P = B.P;
 	uint32_t d[2 * kMfMaxFb + 6];
 	uint32_t prev = 0;
+	// A bucket of thousands of positions (a run of identical bytes is ONE bucket as long as the run) is a serial chain on
+	// this thread, so what every link of the chain would wait for is taken out of it once the bucket proves long:
+	//  * a full-length hit on the first candidate (known from the pre-pass) is GetMatchesSpec1's early exit -- record the
+	//    pair, take over the candidate's children -- and the candidate is the node this thread wrote one step ago: its
+	//    children are kept in registers instead of read back through L2;
+	//  * pool space is taken 512 words at a time instead of one atomic round trip per position;
+	//  * records are published 16 at a time behind one fence.
+	constexpr uint32_t kLongBucket = 256, kChunk = 512, kBatch = 16;
+	uint32_t steps = 0, cpos = 0, cp0 = 0, cp1 = 0;
+	uint64_t chunkOff = 0;
+	uint32_t chunkLeft = 0, nb = 0;
+	uint32_t bi[kBatch];
+	uint64_t bv[kBatch];
 	for (;;) {
 		const uint32_t pos = i + 1;
-		const uint32_t nbt = mf_bt_insert(src, P, B.son, pos, prev, d + 4);
+		const uint32_t r0 = (uint32_t)B.rec[i]; // the pre-pass's note about the first candidate (mf_first_kernel)
+		const uint32_t avail = P.n - i, lenLimit = avail < P.fb ? avail : P.fb;
+		uint32_t nbt;
+		if ((r0 & kMfFirstValid) && (r0 & 0xFFFFu) == lenLimit && P.mc) {
+			uint32_t p0, p1;
+			if (prev == cpos) {
+				p0 = cp0;
+				p1 = cp1;
+			} else {
+				p0 = B.son[(size_t)prev << 1];
+				p1 = B.son[((size_t)prev << 1) + 1];
+			}
+			B.son[(size_t)pos << 1] = p0;
+			B.son[((size_t)pos << 1) + 1] = p1;
+			d[4] = lenLimit;
+			d[5] = pos - prev - 1;
+			nbt = 2;
+			cpos = pos;
+			cp0 = p0;
+			cp1 = p1;
+		} else {
+			nbt = mf_bt_insert(src, P, B.son, pos, prev, d + 4, (r0 & kMfFirstValid) ? (r0 & 0xFFFFu) : kMfFirstNone);
+			cpos = 0;
+		}
 		const uint32_t nd = mf_mix(src, P, pos, B.c2[i], B.c3[i], d, nbt);
 		uint64_t off = 0;
 		if (nd) {
-			off = atomicAdd(B.cursor, (unsigned long long)nd);
+			if (steps < kLongBucket)
+				off = atomicAdd(B.cursor, (unsigned long long)nd);
+			else {
+				if (chunkLeft < nd) {
+					const uint32_t grab = nd > kChunk ? nd : kChunk;
+					chunkOff = atomicAdd(B.cursor, (unsigned long long)grab);
+					chunkLeft = grab;
+				}
+				off = chunkOff;
+				chunkOff += nd;
+				chunkLeft -= nd;
+			}
 			if (off + nd <= B.poolCap) {
 				uint32_t *w = B.pool + off;
 				for (uint32_t j = 0; j < nd; j++)
@@ -231,13 +307,32 @@ __global__ void __launch_bounds__(128) mf_walk_kernel(const MfBlock *__restrict_
 		}
 		// the block's parser may already be running and waiting for this very record (backend.cu): the list (or the
 		// overflow flag) must be visible before the record that announces it
-		__threadfence();
-		*(volatile uint64_t *)&B.rec[i] = kMfReady | (off << kMfCountBits) | nd;
+		const uint64_t rv = kMfReady | (off << kMfCountBits) | nd;
+		bool last = false;
 		prev = pos;
+		steps++;
 		if (++s == count)
-			break;
-		i = V[s];
-		if (mf_hash4(c_crc, src + i, P.hashMask, P.bigHash) != hv)
+			last = true;
+		else {
+			i = V[s];
+			if (mf_hash4(c_crc, src + i, P.hashMask, P.bigHash) != hv)
+				last = true;
+		}
+		if (steps <= kLongBucket) {
+			__threadfence();
+			*(volatile uint64_t *)&B.rec[pos - 1] = rv;
+		} else {
+			bi[nb] = pos - 1;
+			bv[nb] = rv;
+			nb++;
+		}
+		if (nb == kBatch || (last && nb)) {
+			__threadfence();
+			for (uint32_t j = 0; j < nb; j++)
+				*(volatile uint64_t *)&B.rec[bi[j]] = bv[j];
+			nb = 0;
+		}
+		if (last)
 			break;
 	}
 }
@@ -355,7 +450,7 @@ int mf_prepare_block(const MfBlock &B, void *scratch, cudaStream_t st, int64_t *
 	}
 	if (sort_by(B, KEY_H4, bits, bufs, hist, &K, &V, st, launches))
 		return -1;
-	mf_copy_kernel<<<grid, 256, 0, st>>>(V, count, B.sorted);
+	mf_first_kernel<<<grid, 256, 0, st>>>(K, V, count, B.src, B.P, B.sorted, B.rec);
 	if (launches)
 		*launches += 3;
 	return cudaGetLastError() == cudaSuccess ? 0 : -1;
@@ -385,6 +480,7 @@ int mf_preload()
 	cudaFuncAttributes a;
 	bool ok = true;
 	ok = ok && cudaFuncGetAttributes(&a, mf_copy_kernel) == cudaSuccess;
+	ok = ok && cudaFuncGetAttributes(&a, mf_first_kernel) == cudaSuccess;
 	ok = ok && cudaFuncGetAttributes(&a, mf_hc_kernel) == cudaSuccess;
 	ok = ok && cudaFuncGetAttributes(&a, mf_prev_kernel) == cudaSuccess;
 	ok = ok && cudaFuncGetAttributes(&a, mf_walk_kernel) == cudaSuccess;

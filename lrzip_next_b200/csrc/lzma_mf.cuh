@@ -39,6 +39,11 @@ namespace lzma {
 constexpr uint32_t kMfCountBits = 10; // per-position record = (pool offset << 10) | number of uint32 (<= 2*273+2)
 constexpr uint32_t kMfCountMask = (1u << kMfCountBits) - 1;
 constexpr uint64_t kMfReady = 1ull << 63; // set by the tree walk when a record is final (readers mask it off)
+// Before the walk reaches a position its record holds what a data-parallel pre-pass knows about it: the length of the
+// common prefix with the previous position of its bucket (the first candidate the tree insertion compares with), so
+// that a run of identical bytes -- one bucket, every insertion an immediate full-length hit -- costs the bucket's
+// thread no byte comparison at all.
+constexpr uint32_t kMfFirstValid = 1u << 16, kMfFirstNone = 0xFFFFFFFFu;
 
 struct MfParams {
 	uint32_t n;           // block length
@@ -88,7 +93,7 @@ MF_INL uint32_t mf_extend(const uint8_t *a, const uint8_t *b, uint32_t len, uint
 // as the BT thread calls it (LzFindMt.c:627-700).  Writes (len, dist-1) pairs with strictly increasing
 // len >= 4 to d and returns the number of uint32 written.  son is flat: node p at son[2p], son[2p+1].
 MF_FN inline uint32_t mf_bt_insert(const uint8_t *src, const MfParams &P, uint32_t *son, uint32_t pos, uint32_t curMatch,
-				   uint32_t *d)
+				   uint32_t *d, uint32_t firstLen = kMfFirstNone)
 {
 	const uint8_t *cur = src + (pos - 1);
 	const uint32_t avail = P.n - (pos - 1);
@@ -103,8 +108,18 @@ MF_FN inline uint32_t mf_bt_insert(const uint8_t *src, const MfParams &P, uint32
 			const uint8_t *pb = cur - delta;
 			uint32_t len = len0 < len1 ? len0 : len1;
 			const uint32_t pair0 = pair[0], pair1 = pair[1];
-			if (pb[len] == cur[len]) {
-				len = mf_extend(pb, cur, len + 1, lenLimit);
+			bool hit;
+			if (firstLen != kMfFirstNone) { // first candidate: its common prefix (from 0, capped at lenLimit) is known
+				hit = firstLen != 0;
+				if (hit)
+					len = firstLen;
+				firstLen = kMfFirstNone;
+			} else {
+				hit = pb[len] == cur[len];
+				if (hit)
+					len = mf_extend(pb, cur, len + 1, lenLimit);
+			}
+			if (hit) {
 				if (maxLen < len) {
 					maxLen = len;
 					d[nd++] = len;

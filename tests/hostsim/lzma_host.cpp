@@ -102,7 +102,17 @@ extern "C" int hostsim_lzma_encode_pre(const uint8_t *src, int64_t n, int level,
 			uint32_t prev = 0;
 			for (; s < count && h4(order[s]) == hv; s++) {
 				const uint32_t i = order[s], pos = i + 1;
-				const uint32_t nbt = mf_bt_insert(src, P, son.data(), pos, prev, d + 4);
+				// the device's pre-pass (mf_first_kernel): the common prefix with the bucket's previous position,
+				// worked out independently of the tree, handed to the insertion as its first comparison
+				uint32_t first = kMfFirstNone;
+				if (prev) {
+					const uint32_t cmCheck = pos <= P.cyclicSize ? 0 : pos - P.cyclicSize;
+					if (cmCheck < prev) {
+						const uint32_t avail = P.n - i, lenLimit = avail < P.fb ? avail : P.fb;
+						first = mf_extend(src + (prev - 1), src + i, 0, lenLimit);
+					}
+				}
+				const uint32_t nbt = mf_bt_insert(src, P, son.data(), pos, prev, d + 4, first);
 				const uint32_t nd = mf_mix(src, P, pos, c2[i], c3[i], d, nbt);
 				rec[i] = ((uint64_t)pool.size() << kMfCountBits) | nd;
 				pool.insert(pool.end(), d, d + nd);
