@@ -185,8 +185,6 @@ def test_device_decode_round_trips_and_reads_reference_archives(ctx):
         kw = dict(kw, processors=os.cpu_count() or 8)
         ours = ctx.compress(d, make_params(**kw))
         assert ctx.decompress(ours) == d.tobytes()
-        if kw["ramsize"] if "ramsize" in kw else True:
-            pass
         if kw.get("ramsize", 0) == 0:  # -m is in units of 100 MiB on the reference's command line
             theirs = oracle.ref_compress(d, oracle.make_params(**kw))
             assert ctx.decompress(theirs) == d.tobytes()
