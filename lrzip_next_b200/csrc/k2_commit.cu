@@ -17,7 +17,13 @@
 // of the batch writes, commits the conflict-free prefix and re-evaluates / serialises the rest, so
 // exactness rests on the serial step (k2_commit.cuh) and on the ordered validation alone.
 #include "k2_commit.cuh"
+#if defined(LRZ_SIMT_HOST) // tests/hostsim: this file compiled for the CPU, CUDA threads emulated as fibers (simt.h)
+#include "simt.h"
+#define K2_PREFETCH_L1(p) ((void)(p))
+#else
 #include "kernels.h"
+#define K2_PREFETCH_L1(p) asm volatile("prefetch.global.L1 [%0];" ::"l"(p))
+#endif
 
 namespace lrz {
 
@@ -217,9 +223,9 @@ struct WarpPrim {
 			const Cand *pa = cand + tile * (int64_t)kTile + idx + 32 + lane * 8;
 			const Cand *lim = cand + num_tiles * (int64_t)kTile;
 			if (pa < lim)
-				asm volatile("prefetch.global.L1 [%0];" ::"l"(pa));
+				K2_PREFETCH_L1(pa);
 			if (pa + 256 < lim)
-				asm volatile("prefetch.global.L1 [%0];" ::"l"(pa + 256));
+				K2_PREFETCH_L1(pa + 256);
 		}
 		idx += 32;
 		return true;
@@ -413,7 +419,11 @@ struct FastShared {
 // Named barriers of the commit CTA: all 8 warps meet at K2_BAR_GO when the commit warp has queued a batch
 // (or wants the workers to leave), and at K2_BAR_DONE when every warp has evaluated its four candidates.
 static constexpr int K2_BAR_GO = 1, K2_BAR_DONE = 2;
+#if defined(LRZ_SIMT_HOST)
+__device__ __forceinline__ void k2_bar(int id) { simt::bar_sync(id, 256); }
+#else
 __device__ __forceinline__ void k2_bar(int id) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(256) : "memory"); }
+#endif
 
 // ---- batched commit ---------------------------------------------------------------------------------
 // The reference's loop is serial, but consecutive candidates almost never interact: a candidate reads
@@ -428,7 +438,7 @@ __device__ __forceinline__ void k2_bar(int id) { asm volatile("bar.sync %0, %1;"
 // handed to the serial k2_step(), which is also used while a match is pending.  The batch therefore
 // never decides anything the serial code would decide differently.
 
-__device__ __forceinline__ void prefetch_l1(const void *p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+__device__ __forceinline__ void prefetch_l1(const void *p) { K2_PREFETCH_L1(p); }
 
 #ifdef K2_CROSSCHECK
 // Development aid: the original one-lane evaluator, kept as an in-kernel cross-check of group_eval_t.
@@ -1526,6 +1536,7 @@ k2_commit_kernel(const uint8_t *__restrict__ buf, ScanState *st, HEntry *tab, co
 	k2_bar(K2_BAR_GO); // releases the workers
 }
 
+#if !defined(LRZ_SIMT_HOST)
 static constexpr int kK2ReserveSmem = 64 * 1024;
 
 int k2_launch(const uint8_t *d_buf, ScanState *d_state, HEntry *d_tab, const Cand *d_cand,
@@ -1555,5 +1566,6 @@ int k2_preload()
 	ok = ok && cudaFuncSetAttribute(k2_commit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kK2ReserveSmem) == cudaSuccess;
 	return ok ? 0 : -1;
 }
+#endif // !LRZ_SIMT_HOST
 
 } // namespace lrz

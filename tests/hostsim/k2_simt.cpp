@@ -1,0 +1,92 @@
+// tests/hostsim/k2_simt.cpp -- TEST INFRASTRUCTURE ONLY.
+// The product's batched commit kernel (lrzip_next_b200/csrc/k2_commit.cu: commit warp + 7 evaluator warps, named
+// barriers, warp collectives) compiled as C++ and run under the SIMT emulator of simt.h, next to the scalar form of
+// the same control logic (k2_commit.cuh with ScalarPrim, itself pinned against the oracle).  `table_bits` overrides
+// the hash-table size of the rzip level so that every phase of a long scan -- table full, sweeps, gate tightening,
+// the narrow / wide evaluation modes -- is reached within a megabyte of input.
+#include "hostsim_common.h"
+
+#define LRZ_SIMT_HOST 1
+#include "../../lrzip_next_b200/csrc/k2_commit.cu"
+
+// mode 0: scalar primitives, one candidate after the other; mode 1: k2_commit_kernel under the emulator
+extern "C" int simt_rzip_chunk(const uint8_t *data, int64_t n, int rzip_level, int cb, int64_t *victim_round, int64_t seg,
+			       int table_bits, int flags, int mode, uint8_t **s0_out, int64_t *s0_len, uint8_t **s1_out,
+			       int64_t *s1_len, int64_t *stats /* [8] as hostsim_rzip_chunk */, int64_t *dbg /* [16] or null */)
+{
+	int64_t hi_tab[256];
+	make_hash_index(hi_tab);
+	// the layout the kernels see in HBM: 256 zero bytes in front, kInputPad behind (vector over-reads)
+	std::vector<uint8_t> padded((size_t)n + 256 + kInputPad + 64, 0);
+	uint8_t *buf = padded.data() + 256;
+	buf += (16 - ((uintptr_t)buf & 15)) & 15;
+	memcpy(buf, data, (size_t)n);
+	ScanState st;
+	const int64_t rec_cap = n / kMinMatch + 8;
+	k2_init_state(&st, n, rzip_level, cb, *victim_round, rec_cap);
+	if (table_bits) {
+		st.hash_bits = table_bits;
+		st.hash_limit = ((int64_t)1 << table_bits) / 3 * 2;
+	}
+	st.flags = flags;
+	std::vector<HEntry> tab((size_t)1 << st.hash_bits, HEntry{ 0, 0 });
+	std::vector<MatchRec> recs((size_t)rec_cap);
+	seg = (seg + kTile - 1) / kTile * kTile;
+	const int64_t nseg = (n + seg - 1) / seg;
+	int64_t mask_lag[2] = { st.min_mask, st.min_mask }; // K1(i) sees the mask as of the end of K2(i-2)
+	for (int64_t i = 0; i < nseg; i++) {
+		const int64_t lo = i * seg, hi = lo + seg < n ? lo + seg : n;
+		std::vector<Cand> cand;
+		std::vector<uint32_t> tc;
+		scalar_k1(buf, n, lo, hi, mask_lag[i & 1], hi_tab, cand, tc);
+		const int64_t first_tile = lo / kTile, num_tiles = (hi - 1) / kTile - lo / kTile + 1;
+		cand.resize(cand.size() + 1024, Cand{ 0, 0 }); // the list prefetch looks past the last tile
+		if (mode == 0) {
+			ScalarPrim prim;
+			prim.buf = buf;
+			prim.tab = tab.data();
+			prim.hmask = ((int64_t)1 << st.hash_bits) - 1;
+			prim.cand = cand.data();
+			prim.tile_count = tc.data();
+			prim.first_tile = first_tile;
+			prim.num_tiles = num_tiles;
+			prim.seg_hi = hi;
+			prim.tile = 0;
+			prim.idx = 0;
+			k2_commit_segment(prim, &st, recs.data(), i == nseg - 1);
+		} else {
+			const bool last = i == nseg - 1;
+			const bool ok = simt::run_block(K2_THREADS, 0, [&]() {
+				k2_commit_kernel(buf, &st, tab.data(), cand.data(), tc.data(), first_tile, num_tiles, hi, recs.data(),
+						 last ? 1 : 0, 0, 0);
+			});
+			if (!ok)
+				return -2;
+		}
+		mask_lag[i & 1] = st.min_mask;
+	}
+	if (dbg)
+		memcpy(dbg, st.dbg, sizeof(st.dbg));
+	if (st.status != kStatusChunkDone)
+		return st.status == -9 ? -9 : -1;
+	*victim_round = st.victim_round;
+	uint8_t *s0, *s1;
+	scalar_k4(buf, n, cb, st, recs, &s0, &s1);
+	*s0_out = s0;
+	*s0_len = st.s0_len;
+	*s1_out = s1;
+	*s1_len = st.s1_len;
+	if (stats) {
+		stats[0] = st.st_inserts;
+		stats[1] = st.st_lookups;
+		stats[2] = st.st_tag_hits;
+		stats[3] = st.st_tag_misses;
+		stats[4] = st.st_evictions;
+		stats[5] = st.st_sweeps;
+		stats[6] = st.hash_count;
+		stats[7] = st.min_mask;
+	}
+	return 0;
+}
+
+extern "C" void simt_free(void *p) { free(p); }

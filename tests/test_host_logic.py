@@ -58,6 +58,54 @@ def test_commit_control_logic_matches_oracle(hostsim, kind, n, level, seg):
     assert _commit(hostsim[0], d, level, seg) == (o0, o1, ovr)
 
 
+@pytest.fixture(scope="module")
+def k2simt():
+    subprocess.run(["make", "-s", "-C", os.path.join(HERE, "hostsim"), "libk2simt.so"], check=True)
+    S = C.CDLL(os.path.join(HERE, "hostsim", "libk2simt.so"))
+    S.simt_rzip_chunk.argtypes = [C.c_void_p, C.c_int64, C.c_int, C.c_int, C.POINTER(C.c_int64), C.c_int64, C.c_int, C.c_int,
+                                  C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_int64), C.POINTER(C.c_void_p),
+                                  C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
+    return S
+
+
+def _simt_commit(S, data, level, seg, table_bits, flags, mode, vr=0):
+    """mode 0: the scalar control logic; mode 1: k2_commit_kernel itself (256 emulated CUDA threads, tests/hostsim/simt.h)."""
+    data = np.ascontiguousarray(data, dtype=np.uint8)
+    v, s0, s1, l0, l1 = C.c_int64(vr), C.c_void_p(), C.c_void_p(), C.c_int64(), C.c_int64()
+    st, dbg = (C.c_int64 * 8)(), (C.c_int64 * 16)()
+    rc = S.simt_rzip_chunk(data.ctypes.data, data.size, level, oracle.chunk_bytes_for(data.size), C.byref(v), seg, table_bits,
+                           flags, mode, C.byref(s0), C.byref(l0), C.byref(s1), C.byref(l1), st, dbg)
+    assert rc == 0, f"rc {rc} dbg {list(dbg)}"
+    a, b = C.string_at(s0, l0.value), C.string_at(s1, l1.value)
+    S.simt_free(s0)
+    S.simt_free(s1)
+    return (a, b, v.value, list(st)), list(dbg)
+
+
+def _trees_small(n):
+    return datagen.gen_trees(n, copies=4, seed=3, edit_rate=0.005)
+
+
+# table_bits shrinks the hash table (0 = the level's own 64 MiB) so that a megabyte of input goes through table-full
+# sweeps, gate tightening and the wide evaluation modes; vr = incoming value of the cross-window counter
+@pytest.mark.parametrize("kind,n,level,seg,table_bits,flags,vr", [
+    ("text", 1 << 20, 7, 1 << 20, 13, 0, 0), ("text", 600_000, 7, 1 << 18, 0, 0, 5), ("trees", 2 << 20, 7, 1 << 20, 14, 0, 0),
+    ("trees", 1 << 20, 9, 1 << 19, 12, 0, 3), ("rep", 1 << 20, 7, 1 << 20, 12, 0, 0), ("mix", 1 << 20, 7, 12288, 12, 0, 0),
+    ("vm", 1 << 20, 7, 1 << 20, 13, 0, 0), ("text", 1 << 20, 3, 4096, 11, 0, 1), ("trees", 1 << 20, 7, 1 << 20, 14, 1, 0),
+    ("text", 300_000, 7, 1 << 20, 12, 2, 0), ("text", 100, 7, 4096, 0, 0, 0),
+])
+def test_batched_commit_kernel_under_simt_equals_scalar_logic(k2simt, kind, n, level, seg, table_bits, flags, vr):
+    d = _trees_small(n) if kind == "trees" else datagen.generate(kind, n)
+    want, _ = _simt_commit(k2simt, d, level, seg, table_bits, 0, 0, vr)
+    got, dbg = _simt_commit(k2simt, d, level, seg, table_bits, flags, 1, vr)
+    assert got == want
+    if table_bits == 0:  # the level's own table: the scalar logic is the oracle's
+        o0, o1, _, ovr = oracle.rzip_chunk(d, level, victim_round=vr)
+        assert (got[0], got[1], got[2]) == (o0, o1, ovr)
+    if n >= 300_000:
+        assert dbg[0] > 0 and dbg[1] > 0  # batch rounds ran and committed candidates
+
+
 def _lzma(Z, data, level, dic):
     n = len(data)
     cap = int(n * 1.02)
