@@ -103,8 +103,14 @@ struct Progress { // shared memory, written by the commit warp, polled by the he
 	volatile int done;
 };
 
+// Table slots written since the last batch evaluation (batch commits and serial steps alike): what a lane of that
+// evaluation must not have read if its result is to be used in a later round (see "resumed rounds" below).
+static constexpr int K2_WLOG = 192;
+
 struct WarpPrim {
 	Progress *prog;
+	unsigned *wlog = nullptr; // shared memory, K2_WLOG entries
+	int *wlog_n = nullptr;    // entries written; > K2_WLOG = overflow
 	const uint8_t *buf;
 	HEntry *tab;
 	int64_t hmask;
@@ -134,8 +140,15 @@ struct WarpPrim {
 	}
 	__device__ __forceinline__ void store_entry(int64_t slot, int64_t t, int64_t off)
 	{
-		if (lane == 0)
+		if (lane == 0) {
 			*reinterpret_cast<longlong2 *>(tab + slot) = make_longlong2(off, t);
+			if (wlog) {
+				const int k = *wlog_n;
+				if (k < K2_WLOG)
+					wlog[k] = (unsigned)slot;
+				*wlog_n = k + 1;
+			}
+		}
 		__syncwarp();
 	}
 	__device__ __forceinline__ void clear_entry(int64_t slot) { store_entry(slot, 0, 0); }
@@ -402,6 +415,7 @@ struct LaneEval {
 };
 
 static constexpr int K2_MAXEQ = 16; // equal-tag entries one candidate may meet in its chain
+static constexpr int K2_RESUME_MIN = 4; // a round without evaluation is worth its validation from this many lanes on
 
 struct FastShared {
 	long long qpos[64], qtag[64]; // queue of upcoming candidates that pass the current gate
@@ -410,6 +424,8 @@ struct FastShared {
 	long long eq_off[8][4][K2_MAXEQ]; // per warp and group: offsets of the equal-tag entries met on the walk
 	unsigned eslot[32][K2_MAXEQ];     // per candidate: the slots of those entries, in walk order (chain-cap victims)
 	unsigned wmask[4096];             // validation filter: bit l of wmask[slot >> 10] = lane l of the batch writes there
+	unsigned wlog[K2_WLOG];           // slots written since the last evaluation (WarpPrim::wlog)
+	int wlog_n;
 	// batch evaluation command, written by the commit warp before barrier 1 (see k2_eval_worker)
 	long long cmd_tag_mask, cmd_better, cmd_end, cmd_last_match;
 	int cmd_nb, cmd_max_chain, cmd_exit, cmd_mode, cmd_flags;
@@ -1040,6 +1056,23 @@ __device__ void k2_commit_segment_batched(WarpPrim &prim, FastShared *sh, ScanSt
 	int64_t n_disp = 0, n_evict = 0;
 	int64_t dbg[16] = { 0 };
 	const long long clk_start = clock64();
+	// ---- resumed rounds.  A batch usually ends at a candidate that needs the serial step (a match, mostly), long before
+	// its 32 evaluations are used up, and evaluating is two thirds of a round.  The results of the lanes behind that
+	// candidate stay in sh->ev: they are still what an evaluation on the current table would return as long as no
+	// slot they read has been written since -- by the lanes committed from that evaluation or by the serial steps in
+	// between, all of which go through the write log -- and the gates are the same.  (last_match only grows, which can
+	// only turn "could match" into "cannot": a lane evaluated as match-free stays match-free, and lanes that could
+	// match go to the serial step anyway.)  The next round then skips the evaluation: queue entry i takes the result in
+	// ev slot ev_base + i, is checked against the log on top of the usual in-batch validation, and a lane that fails
+	// ends the round and sends everything from it on into a fresh evaluation.
+	int ev_n = 0, ev_base = 0; // evaluated slots in sh->ev; queue entry 0 <-> slot ev_base
+	int64_t ev_tag_mask = 0, ev_min_mask = 0;
+	const bool resume_on = !(sh->cmd_flags & 4);
+	prim.wlog = sh->wlog;
+	prim.wlog_n = &sh->wlog_n;
+	if (lane == 0)
+		sh->wlog_n = 0;
+	__syncwarp();
 
 	// drop queue entries the scan has moved past or that fail the (possibly tightened) gate
 	auto filter_queue = [&]() {
@@ -1068,6 +1101,16 @@ __device__ void k2_commit_segment_batched(WarpPrim &prim, FastShared *sh, ScanSt
 			sh->qpos[d] = p1;
 			sh->qtag[d] = t1;
 		}
+		{ // evaluated entries keep their slots only if what was dropped is a prefix of the queue
+			const int qn_old = qn, removed = qn_old - (__popc(b0) + __popc(b1));
+			const unsigned long long keep = (unsigned long long)b0 | ((unsigned long long)b1 << 32);
+			const unsigned long long all = qn_old >= 64 ? ~0ull : ((1ull << qn_old) - 1);
+			const unsigned long long gone = removed >= 64 ? ~0ull : ((1ull << removed) - 1);
+			if (keep == (all & ~gone))
+				ev_base += removed;
+			else
+				ev_n = 0;
+		}
 		qn = __popc(b0) + __popc(b1);
 		__syncwarp();
 	};
@@ -1093,6 +1136,7 @@ __device__ void k2_commit_segment_batched(WarpPrim &prim, FastShared *sh, ScanSt
 			sh->qtag[lane + 32] = t1;
 		}
 		qn -= k;
+		ev_base += k;
 		__syncwarp();
 	};
 
@@ -1140,8 +1184,13 @@ __device__ void k2_commit_segment_batched(WarpPrim &prim, FastShared *sh, ScanSt
 			continue;
 		}
 
-		// ---- evaluate up to 32 candidates, one per lane, on the table as it stands
-		const int nb = qn < 32 ? qn : 32;
+		// ---- evaluate up to 32 candidates, one per lane, on the table as it stands -- or take up the unused results
+		// of the last evaluation
+		__syncwarp();
+		const bool resumed = resume_on && ev_n - ev_base >= K2_RESUME_MIN && ev_n - ev_base <= qn &&
+				     r.tag_mask == ev_tag_mask && r.min_mask == ev_min_mask && sh->wlog_n <= K2_WLOG;
+		const int nb = resumed ? ev_n - ev_base : (qn < 32 ? qn : 32);
+		const int eb = resumed ? ev_base : 0; // ev / eslot slot of lane 0
 		const int64_t better = (r.min_mask << 1) | 1;
 		int pf_lines;
 		{
@@ -1156,8 +1205,14 @@ __device__ void k2_commit_segment_batched(WarpPrim &prim, FastShared *sh, ScanSt
 		L.nw = L.nr = L.net = L.ins = L.miss = L.chain = L.twin = 0;
 		L.cx = false;
 		int64_t myp = 0, myt = 0;
-		dbg[0]++;
 		const long long ce0 = clock64();
+		if (resumed) {
+			dbg[7]++;
+			if (lane < nb)
+				L = sh->ev[eb + lane];
+			__syncwarp();
+		} else {
+		dbg[0]++;
 		if (lane < nb) { // pull each candidate's home line(s) and window bytes towards L1 before the passes
 			myp = sh->qpos[lane];
 			myt = sh->qtag[lane];
@@ -1168,6 +1223,7 @@ __device__ void k2_commit_segment_batched(WarpPrim &prim, FastShared *sh, ScanSt
 					prefetch_l1(prim.tab + ((hh + 8u * (unsigned)l) & hmask));
 		}
 		if (lane == 0) { // all 8 warps of the CTA evaluate four candidates each
+			sh->wlog_n = 0;
 			sh->cmd_tag_mask = r.tag_mask;
 			sh->cmd_better = better;
 			sh->cmd_end = c.end;
@@ -1182,6 +1238,10 @@ __device__ void k2_commit_segment_batched(WarpPrim &prim, FastShared *sh, ScanSt
 		if (lane < nb)
 			L = sh->ev[lane];
 		__syncwarp();
+		ev_n = nb;
+		ev_base = 0;
+		ev_tag_mask = r.tag_mask;
+		ev_min_mask = r.min_mask;
 #ifdef K2_CROSSCHECK
 		{ // development aid: the single-lane evaluator must agree with the cooperative one
 			bool bad = false;
@@ -1228,6 +1288,7 @@ __device__ void k2_commit_segment_batched(WarpPrim &prim, FastShared *sh, ScanSt
 			}
 		}
 #endif
+		} // fresh evaluation
 		dbg[8] += clock64() - ce0;
 		if (L.cx)
 			L.net = 0;
@@ -1239,7 +1300,7 @@ __device__ void k2_commit_segment_batched(WarpPrim &prim, FastShared *sh, ScanSt
 		const unsigned evm = __ballot_sync(FULL, evict);
 		if (evict) {
 			const int vi = (int)((r.victim_round + __popc(evm & lt)) % c.max_chain);
-			L.wslot[0] = sh->eslot[lane][vi];
+			L.wslot[0] = sh->eslot[eb + lane][vi];
 		}
 		const long long cs0 = clock64();
 		// sweep deletions (clean_one_from_hash): the k-th insert that overfills the table removes the
@@ -1372,6 +1433,25 @@ __device__ void k2_commit_segment_batched(WarpPrim &prim, FastShared *sh, ScanSt
 					break;
 				}
 			}
+			if (resumed) { // reads against everything written since the evaluation
+				const int nlog = sh->wlog_n;
+				bool hitw = false;
+				if (lane < nv) {
+					if (lane == 0 && L.twin)
+						hitw = true; // its predecessor is no longer the lane in front of it
+					for (int q = 0; q < L.nr && !hitw; q++) {
+						const unsigned lo = L.rlo[q], len = L.rlen[q];
+						for (int w = 0; w < nlog; w++)
+							if (((sh->wlog[w] - lo) & hmask) < len) {
+								hitw = true;
+								break;
+							}
+					}
+				}
+				const unsigned hw = __ballot_sync(FULL, hitw);
+				if (hw && __ffs(hw) - 1 < first_conf)
+					first_conf = __ffs(hw) - 1;
+			}
 			if (lane == first_conf)
 				cmask = 1;
 			__syncwarp();
@@ -1416,6 +1496,12 @@ __device__ void k2_commit_segment_batched(WarpPrim &prim, FastShared *sh, ScanSt
 				if (cl)
 					*reinterpret_cast<longlong2 *>(prim.tab + del) = make_longlong2(0, 0);
 			}
+			if (mine) { // everything a committed lane wrote goes into the log (nwt: inserts + its sweep deletion)
+				const int at = atomicAdd(&sh->wlog_n, nwt);
+				if (at + nwt <= K2_WLOG)
+					for (int w = 0; w < nwt; w++)
+						sh->wlog[at + w] = L.wslot[w];
+			}
 			__syncwarp();
 			if (k > base) {
 				const unsigned km = ((k >= 32) ? FULL : ((1u << k) - 1)) & ((base >= 32) ? 0u : (FULL << base));
@@ -1452,6 +1538,7 @@ __device__ void k2_commit_segment_batched(WarpPrim &prim, FastShared *sh, ScanSt
 			// lane k only conflicts with committed lanes (it read a slot one of them wrote): it and everything
 			// after it go into the next full-width batch, evaluated on the updated table
 			dbg[5]++;
+			ev_n = 0;
 			break;
 		}
 		if (base > 0) {

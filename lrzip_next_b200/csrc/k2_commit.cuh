@@ -196,28 +196,14 @@ LRZ_HD void k2_store_regs(ScanState *st, const CommitRegs &r, const CommitCounte
 	st->st_tag_misses += n.misses;
 }
 
-// One iteration of the reference's loop body at candidate (p, t): src/rzip.c:660-688.
-// Returns true when p must be examined again: a match is emitted at the first candidate p that lies
-// 31 positions past its start; when the match ends before p the reference's loop variable moves
-// BACKWARDS to the end of the match (src/rzip.c:685) and walks up to p again, so p itself is looked up
-// and inserted a second time (no other candidate can lie in between).
+// The second half of the loop body at candidate p, once its lookup (best match mlen / offset / reverse, 0 = none) and its
+// insert are done: keep the longer match, emit on GREAT_MATCH or 31 positions past the pending match's start
+// (src/rzip.c:673-688).  Touches no table slot.  Returns k2_step's `again`.
 template <class P>
-LRZ_HD bool k2_step(P &prim, ScanState *st, CommitRegs &r, const CommitConst &c, CommitCounters &n, MatchRec *recs,
-		    int64_t p, int64_t t, int &status)
+LRZ_HD bool k2_step_tail(P &prim, ScanState *st, CommitRegs &r, const CommitConst &c, MatchRec *recs, int64_t p,
+			 int64_t mlen, int64_t offset, int64_t reverse, int &status)
 {
-	int64_t mlen = 0, offset = 0, reverse = 0;
 	bool again = false;
-	r.p = p;
-	prim.publish(p, r.min_mask);
-	n.lookups++;
-	prim.lookup(t, p, c.end, r.last_match, mlen, offset, reverse, n.hits, n.misses);
-	if ((t & r.tag_mask) == r.tag_mask) {
-		n.inserts++;
-		r.hash_count++;
-		k2_insert(prim, st, r, t, p, c.max_chain);
-		if (r.hash_count > c.hash_limit)
-			r.tag_mask = k2_clean_one(prim, st, r, c.hash_bits);
-	}
 	if (mlen > r.cur_len) {
 		r.cur_p = p - reverse;
 		r.cur_len = mlen;
@@ -236,6 +222,30 @@ LRZ_HD bool k2_step(P &prim, ScanState *st, CommitRegs &r, const CommitConst &c,
 		prim.publish(r.p, r.min_mask);
 	}
 	return again;
+}
+
+// One iteration of the reference's loop body at candidate (p, t): src/rzip.c:660-688.
+// Returns true when p must be examined again: a match is emitted at the first candidate p that lies
+// 31 positions past its start; when the match ends before p the reference's loop variable moves
+// BACKWARDS to the end of the match (src/rzip.c:685) and walks up to p again, so p itself is looked up
+// and inserted a second time (no other candidate can lie in between).
+template <class P>
+LRZ_HD bool k2_step(P &prim, ScanState *st, CommitRegs &r, const CommitConst &c, CommitCounters &n, MatchRec *recs,
+		    int64_t p, int64_t t, int &status)
+{
+	int64_t mlen = 0, offset = 0, reverse = 0;
+	r.p = p;
+	prim.publish(p, r.min_mask);
+	n.lookups++;
+	prim.lookup(t, p, c.end, r.last_match, mlen, offset, reverse, n.hits, n.misses);
+	if ((t & r.tag_mask) == r.tag_mask) {
+		n.inserts++;
+		r.hash_count++;
+		k2_insert(prim, st, r, t, p, c.max_chain);
+		if (r.hash_count > c.hash_limit)
+			r.tag_mask = k2_clean_one(prim, st, r, c.hash_bits);
+	}
+	return k2_step_tail(prim, st, r, c, recs, p, mlen, offset, reverse, status);
 }
 
 // src/rzip.c:710-711 tail literal, :759-760 terminator + CRC
