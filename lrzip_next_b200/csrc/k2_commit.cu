@@ -411,6 +411,8 @@ struct LaneEval {
 	int nw, nr, net, ins, miss;
 	int chain; // the insert met max_chain_len equal-tag entries: the victim slot is chosen at commit time (eslot[])
 	int twin;  // evaluated as the second of two adjacent candidates with the same tag (see group_eval_t)
+	unsigned surv; // equal-tag entries (bit i = i-th met on the walk, offsets in eoff[]) that may give a match of >= 31
+		       // bytes: the commit warp measures them (match tail); everything else about the lane is batch work
 	bool cx;
 };
 
@@ -421,7 +423,7 @@ struct FastShared {
 	long long qpos[64], qtag[64]; // queue of upcoming candidates that pass the current gate
 	unsigned dslot[32];           // sweep deletions of the current batch, in order
 	LaneEval ev[32];              // evaluation results of the batch, written by the 8-lane groups
-	long long eq_off[8][4][K2_MAXEQ]; // per warp and group: offsets of the equal-tag entries met on the walk
+	long long eoff[32][K2_MAXEQ];     // per candidate: offsets of the equal-tag entries met on the walk
 	unsigned eslot[32][K2_MAXEQ];     // per candidate: the slots of those entries, in walk order (chain-cap victims)
 	unsigned wmask[4096];             // validation filter: bit l of wmask[slot >> 10] = lane l of the batch writes there
 	unsigned wlog[K2_WLOG];           // slots written since the last evaluation (WarpPrim::wlog)
@@ -715,7 +717,7 @@ __device__ void group_eval_t(const uint8_t *__restrict__ buf, const HEntry *tab,
 {
 	constexpr unsigned GM = (G == 32) ? 0xffffffffu : ((1u << G) - 1u);
 	const int g = lane / G, gl = lane % G;
-	long long *eq_list = sh->eq_off[warp][g];
+	long long *eq_list = sh->eoff[cand_idx >= 0 ? cand_idx : 0];
 	const unsigned gshift = (unsigned)(g * G);
 	const unsigned ltg = (1u << gl) - 1;
 	const bool active = cand_idx >= 0;
@@ -865,6 +867,8 @@ __device__ void group_eval_t(const uint8_t *__restrict__ buf, const HEntry *tab,
 	// ---- equal-tag entries: would any of them give a match?  (then the serial step must decide)
 	// One lane per entry dismisses the ones whose bytes differ at once (all loads in flight together);
 	// the rare survivors get the group-wide compare.
+	unsigned surv = 0;
+	const bool soft_on = !(sh->cmd_flags & 8);
 	for (int qb = 0; __any_sync(FULL, active && !cx && qb < neq); qb += G) {
 		const int q = qb + gl;
 		const bool have = active && !cx && q < neq;
@@ -880,13 +884,20 @@ __device__ void group_eval_t(const uint8_t *__restrict__ buf, const HEntry *tab,
 			const int64_t op = act ? eq_list[qb + b] : 0;
 			const bool cm = group_could_match(buf, p, op, end, last_match, act, gl < 8, gshift, gl & 7);
 			if (act) {
-				if (cm)
-					cx = true;
-				else
+				if (cm) {
+					if (soft_on)
+						surv |= 1u << (qb + b);
+					else
+						cx = true;
+				} else
 					miss++;
 			}
 		}
 	}
+	// a twin looked at the chain as it was BEFORE its predecessor's insert: if that insert evicts an entry, it may be one
+	// of the survivors.  All misses are the same count either way; anything else is for the serial step.
+	if (tw && surv)
+		cx = true;
 	if (active && gl == 0) {
 		R->rlo[0] = h;
 		R->rlen[0] = s + 1;
@@ -995,6 +1006,7 @@ __device__ void group_eval_t(const uint8_t *__restrict__ buf, const HEntry *tab,
 		R->miss = miss;
 		R->chain = (!cx && ins && nw == 1 && kind == kProbeChain) ? 1 : 0;
 		R->twin = (tw && !cx) ? 1 : 0;
+		R->surv = cx ? 0u : surv;
 		R->cx = cx;
 	}
 	__syncwarp();
@@ -1068,6 +1080,14 @@ __device__ void k2_commit_segment_batched(WarpPrim &prim, FastShared *sh, ScanSt
 	int ev_n = 0, ev_base = 0; // evaluated slots in sh->ev; queue entry 0 <-> slot ev_base
 	int64_t ev_tag_mask = 0, ev_min_mask = 0;
 	const bool resume_on = !(sh->cmd_flags & 4);
+	// ---- soft stoppers.  A candidate that may have a match -- equal-tag entries the evaluation could not dismiss -- or
+	// that triggers the emission of the pending match (31 positions past its start, src/rzip.c:678) still does nothing
+	// to the table but its own lookup + insert, which the batch commits like any other lane's.  What is left is the
+	// second half of the loop body: measure the surviving entries (match_len, with the current last_match), keep the
+	// longest, emit.  The commit warp does that right after committing the lane ("match tail") and ends the round there,
+	// because an emission moves the scan past candidates of the batch; the lanes behind it are taken up by a resumed
+	// round.  While a match is pending the candidates inside its 31 positions that cannot match are plain lanes.
+	const bool soft_on = !(sh->cmd_flags & 8);
 	prim.wlog = sh->wlog;
 	prim.wlog_n = &sh->wlog_n;
 	if (lane == 0)
@@ -1171,7 +1191,7 @@ __device__ void k2_commit_segment_batched(WarpPrim &prim, FastShared *sh, ScanSt
 		dbg[11] += clock64() - cr0;
 		if (qn == 0)
 			break;
-		if (r.cur_len > 0) { // a match is pending: strictly serial until it is emitted
+		if (r.cur_len > 0 && !soft_on) { // (development switch 8) a match is pending: strictly serial until it is emitted
 			const int64_t p = sh->qpos[0], t = sh->qtag[0];
 			pop_front(1);
 			const long long c0 = clock64();
@@ -1186,9 +1206,9 @@ __device__ void k2_commit_segment_batched(WarpPrim &prim, FastShared *sh, ScanSt
 
 		// ---- evaluate up to 32 candidates, one per lane, on the table as it stands -- or take up the unused results
 		// of the last evaluation
-		__syncwarp();
+		const int wlog_now = __shfl_sync(FULL, sh->wlog_n, 0); // one read for the warp: lane 0 resets it further down
 		const bool resumed = resume_on && ev_n - ev_base >= K2_RESUME_MIN && ev_n - ev_base <= qn &&
-				     r.tag_mask == ev_tag_mask && r.min_mask == ev_min_mask && sh->wlog_n <= K2_WLOG;
+				     r.tag_mask == ev_tag_mask && r.min_mask == ev_min_mask && wlog_now <= K2_WLOG;
 		const int nb = resumed ? ev_n - ev_base : (qn < 32 ? qn : 32);
 		const int eb = resumed ? ev_base : 0; // ev / eslot slot of lane 0
 		const int64_t better = (r.min_mask << 1) | 1;
@@ -1208,8 +1228,10 @@ __device__ void k2_commit_segment_batched(WarpPrim &prim, FastShared *sh, ScanSt
 		const long long ce0 = clock64();
 		if (resumed) {
 			dbg[7]++;
-			if (lane < nb)
+			if (lane < nb) {
 				L = sh->ev[eb + lane];
+				myp = sh->qpos[lane];
+			}
 			__syncwarp();
 		} else {
 		dbg[0]++;
@@ -1350,11 +1372,12 @@ __device__ void k2_commit_segment_batched(WarpPrim &prim, FastShared *sh, ScanSt
 			}
 		}
 		// flags of one lane after an evaluation: `stopper` = must go through the serial step
-		bool stopper = false;
+		bool stopper = false, soft = false;
 		unsigned del = 0;
 		int nwt = 0;
 		auto classify = [&]() {
 			stopper = L.cx;
+			soft = soft_on && lane < nb && !L.cx && (L.surv != 0 || (r.cur_len > 0 && myp >= r.cur_p + kMinMatch));
 			del = 0;
 			if (cl) {
 				if (crank >= found)
@@ -1384,7 +1407,7 @@ __device__ void k2_commit_segment_batched(WarpPrim &prim, FastShared *sh, ScanSt
 		// earlier lane tests its own writes against the candidate's ranges).
 		unsigned cmask = 0;
 		{
-			const unsigned stop0 = __ballot_sync(FULL, lane < nb && stopper);
+			const unsigned stop0 = __ballot_sync(FULL, lane < nb && (stopper || soft));
 			const int nv = stop0 ? __ffs(stop0) : nb;
 			const int myn = lane < nv ? nwt : 0;
 			const int mynr = lane < nv ? L.nr : 0;
@@ -1461,11 +1484,15 @@ __device__ void k2_commit_segment_batched(WarpPrim &prim, FastShared *sh, ScanSt
 
 		// ---- commit the longest prefix of lanes that neither need the serial step nor read a slot an earlier lane writes
 		int base = 0;
-		bool serial_next = false;
+		bool serial_next = false, tail = false;
 		const int64_t tag_mask0 = r.tag_mask;
 		for (;;) {
 			const unsigned stopm = __ballot_sync(FULL, lane >= base && lane < nb && (stopper || cmask != 0));
+			const unsigned softm = __ballot_sync(FULL, lane >= base && lane < nb && soft && !stopper && cmask == 0);
 			int k = stopm ? (__ffs(stopm) - 1) : nb;
+			const int sl = softm ? (__ffs(softm) - 1) : 32;
+			if (sl < k) // the first soft stopper commits with the lanes before it, then gets its match tail
+				k = sl + 1;
 			bool gate_cut = false;
 			if (r.tag_mask != better) { // the first sweep deletion of a phase tightens the insert gate:
 				const unsigned lo_m = (base >= 32) ? 0u : (FULL << base); // later lanes used the old gate
@@ -1528,6 +1555,10 @@ __device__ void k2_commit_segment_batched(WarpPrim &prim, FastShared *sh, ScanSt
 			base = k;
 			if (gate_cut)
 				dbg[6]++;
+			if (k == sl + 1) { // (a gate cut in front of it would have moved k)
+				tail = true;
+				break;
+			}
 			if (k >= nb || gate_cut || r.tag_mask != tag_mask0)
 				break;
 			if (__shfl_sync(FULL, (int)stopper, k)) {
@@ -1541,11 +1572,44 @@ __device__ void k2_commit_segment_batched(WarpPrim &prim, FastShared *sh, ScanSt
 			ev_n = 0;
 			break;
 		}
+		int64_t tail_p = 0, tail_t = 0;
+		if (tail) {
+			tail_p = sh->qpos[base - 1];
+			tail_t = sh->qtag[base - 1];
+		}
 		if (base > 0) {
 			prim.publish(r.p, r.min_mask);
 			pop_front(base);
 		}
 		dbg[14] += clock64() - cc0;
+		if (tail) { // match tail of the lane committed last: find_best_match's compares, then src/rzip.c:673-688
+			const long long c0 = clock64();
+			const int tl = base - 1;
+			unsigned sv = __shfl_sync(FULL, L.surv, tl);
+			int64_t mlen = 0, offset = 0, reverse = 0;
+			while (sv) {
+				const int b = __ffs(sv) - 1;
+				sv &= sv - 1;
+				const int64_t off = sh->eoff[eb + tl][b];
+				int64_t rev;
+				const int64_t len = prim.match_len(tail_p, off, c.end, r.last_match, rev);
+				if (len) {
+					if (len > mlen) {
+						mlen = len;
+						offset = off - rev;
+						reverse = rev;
+					}
+					n.hits++;
+				} else
+					n.misses++;
+			}
+			again = k2_step_tail(prim, st, r, c, recs, tail_p, mlen, offset, reverse, status);
+			again_p = tail_p;
+			again_t = tail_t;
+			dbg[9] += clock64() - c0;
+			dbg[15]++;
+			filter_queue();
+		}
 		if (serial_next) { // serial step for the candidate that needs it
 			const int64_t p = sh->qpos[0], t = sh->qtag[0];
 			pop_front(1);

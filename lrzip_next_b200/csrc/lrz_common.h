@@ -103,11 +103,12 @@ struct ScanState {
 	int64_t st_evictions, st_sweeps, st_displacements;
 	// commit-kernel bookkeeping: 0 batch rounds, 1 lanes committed in batches, 2 serial steps (pending match),
 	// 3 serial (needs serial logic), 4 serial (sweep wrap / window), 5 single-lane re-evaluations, 6 gate cuts,
-	// 7 rank-shift restarts, 8 clock cycles in lane evaluation, 9 cycles in serial steps, 10 total cycles,
-	// 11 cycles in queue refill, 12 sweep scan + classify, 13 validation, 14 commit loop (incl. re-evaluations)
+	// 7 resumed rounds (no evaluation), 8 clock cycles in lane evaluation, 9 cycles in serial steps and match tails,
+	// 10 total cycles, 11 cycles in queue refill, 12 sweep scan + classify, 13 validation, 14 commit loop, 15 match tails
 	int64_t dbg[16];
 	int32_t flags;        // development switches of the commit kernel (LRZGPU_K2_FLAGS): 1 no twin evaluation, 2 exact
-	int32_t pad_;         // validation of every lane (no bit filter)
+	int32_t pad_;         // validation of every lane (no bit filter), 4 no resumed rounds, 8 no soft stoppers (matches
+			      // and pending matches through the serial step)
 };
 
 enum { kStatusRunning = 0, kStatusChunkDone = 2, kStatusRecOverflow = -1 };

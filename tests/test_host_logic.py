@@ -93,9 +93,13 @@ def _trees_small(n):
     ("trees", 1 << 20, 9, 1 << 19, 12, 0, 3), ("rep", 1 << 20, 7, 1 << 20, 12, 0, 0), ("mix", 1 << 20, 7, 12288, 12, 0, 0),
     ("vm", 1 << 20, 7, 1 << 20, 13, 0, 0), ("text", 1 << 20, 3, 4096, 11, 0, 1), ("trees", 1 << 20, 7, 1 << 20, 14, 1, 0),
     ("text", 300_000, 7, 1 << 20, 12, 2, 0), ("text", 100, 7, 4096, 0, 0, 0),
+    # development switches: 4 no resumed rounds, 8 matches / pending matches through the serial step
+    ("trees", 1 << 20, 7, 1 << 20, 14, 4, 0), ("trees", 1 << 20, 7, 1 << 20, 14, 8, 0), ("trees", 1 << 20, 7, 1 << 20, 14, 12, 0),
+    ("trees8", 4 << 20, 7, 4 << 20, 15, 0, 0),  # an evicting twin with a surviving equal-tag entry (tar-like headers)
 ])
 def test_batched_commit_kernel_under_simt_equals_scalar_logic(k2simt, kind, n, level, seg, table_bits, flags, vr):
-    d = _trees_small(n) if kind == "trees" else datagen.generate(kind, n)
+    d = _trees_small(n) if kind == "trees" else (
+        datagen.gen_trees(n, copies=8, seed=3, edit_rate=0.005) if kind == "trees8" else datagen.generate(kind, n))
     want, _ = _simt_commit(k2simt, d, level, seg, table_bits, 0, 0, vr)
     got, dbg = _simt_commit(k2simt, d, level, seg, table_bits, flags, 1, vr)
     assert got == want
@@ -104,6 +108,10 @@ def test_batched_commit_kernel_under_simt_equals_scalar_logic(k2simt, kind, n, l
         assert (got[0], got[1], got[2]) == (o0, o1, ovr)
     if n >= 300_000:
         assert dbg[0] > 0 and dbg[1] > 0  # batch rounds ran and committed candidates
+    if kind.startswith("trees") and not flags & 4:
+        assert dbg[7] > 0  # rounds that took up the previous evaluation
+    if kind.startswith("trees") and not flags & 8:
+        assert dbg[15] > 0 and dbg[2] == 0  # match tails instead of serial steps
 
 
 def _lzma(Z, data, level, dic):
