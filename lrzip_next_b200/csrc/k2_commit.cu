@@ -1223,6 +1223,7 @@ __device__ void k2_commit_segment_batched(WarpPrim &prim, FastShared *sh, ScanSt
 		const int mode = k2_mode_for(r.tag_mask);
 		LaneEval L;
 		L.nw = L.nr = L.net = L.ins = L.miss = L.chain = L.twin = 0;
+		L.surv = 0;
 		L.cx = false;
 		int64_t myp = 0, myt = 0;
 		const long long ce0 = clock64();
