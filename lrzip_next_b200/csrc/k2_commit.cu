@@ -410,13 +410,15 @@ struct LaneEval {
 	unsigned rlo[K2_MAXW], rlen[K2_MAXW]; // probe ranges read (start slot, length), modulo the table size
 	int nw, nr, net, ins, miss;
 	int chain; // the insert met max_chain_len equal-tag entries: the victim slot is chosen at commit time (eslot[])
-	int twin;  // evaluated as the second of two adjacent candidates with the same tag (see group_eval_t)
+	int twin;  // evaluated on the table as the earlier same-tag candidates of the batch leave it (see group_eval_t)
+	unsigned twmask; // those candidates (bit = evaluation slot): their inserts are not conflicts for this lane
 	unsigned surv; // equal-tag entries (bit i = i-th met on the walk, offsets in eoff[]) that may give a match of >= 31
 		       // bytes: the commit warp measures them (match tail); everything else about the lane is batch work
 	bool cx;
 };
 
 static constexpr int K2_MAXEQ = 16; // equal-tag entries one candidate may meet in its chain
+static constexpr int K2_TWMAX = 7;  // same-tag candidates earlier in the batch that one candidate may build on
 static constexpr int K2_RESUME_MIN = 4; // a round without evaluation is worth its validation from this many lanes on
 
 struct FastShared {
@@ -731,13 +733,27 @@ __device__ void group_eval_t(const uint8_t *__restrict__ buf, const HEntry *tab,
 	int nw = 0, nr = 0, net = 0, miss = 0;
 	bool cx = false;
 
+	// ---- the candidates earlier in the batch that carry the same tag (they walk the same chain and insert into it)
+	unsigned pm = 0;
+	if (!(sh->cmd_flags & 1)) {
+		if (active && do_insert)
+			for (int i = gl; i < cand_idx; i += G)
+				if (sh->qtag[i] == t)
+					pm |= 1u << i;
+		for (int o = 1; o < G; o <<= 1)
+			pm |= __shfl_xor_sync(FULL, pm, o);
+	}
+	const int npred = __popc(pm);
+	// with one such predecessor that replaces a due entry, this candidate's insert stops at the NEXT stopping slot
+	const bool want2 = npred == 1 && (t & better) == better;
+
 	// ---- walk 1: the lookup chain [home, first empty slot], and on the way the insert target
 	const unsigned h = (unsigned)t & hmask;
 	const int my_ones = tz_ones(t);
-	unsigned s = 0, sslot = 0;
-	bool stop = !do_insert, done = !active;
-	int kind = -1, round = 0, neq = 0;
-	int64_t occ_off = 0, occ_tag = 0;
+	unsigned s = 0, sslot = 0, sslot2 = 0;
+	bool stop = !do_insert, done = !active, stop2 = false;
+	int kind = -1, round = 0, neq = 0, kind2 = -1, round2 = 0;
+	int64_t occ_off = 0, occ_tag = 0, occ2_off = 0, occ2_tag = 0;
 	while (__any_sync(FULL, !done)) {
 		HEntry ew[P];
 #pragma unroll
@@ -757,7 +773,7 @@ __device__ void group_eval_t(const uint8_t *__restrict__ buf, const HEntry *tab,
 				prefetch_l1(buf + e.offset);
 			// a window with nothing to act on (no empty slot, no equal tag, no insert target still wanted)
 			// only moves the cursor: the common case inside a long chain
-			if (!__any_sync(FULL, !done && (emp || eq || (!stop && (due || les))))) {
+			if (!__any_sync(FULL, !done && (emp || eq || ((!stop || (want2 && kind == kProbeDue && !stop2)) && (due || les))))) {
 				if (!done) {
 					s += G;
 					if (s >= K2_MAXWALK)
@@ -775,6 +791,7 @@ __device__ void group_eval_t(const uint8_t *__restrict__ buf, const HEntry *tab,
 			const int fs = sc ? __ffs(sc) - 1 : G;
 			const int src = (int)gshift + (fs % G);
 			const int64_t oo = __shfl_sync(FULL, e.offset, src), ot = __shfl_sync(FULL, e.tag, src);
+			bool just = false; // the first stopping slot lies in this window
 			if (!done) {
 				if (!stop) {
 					const unsigned before = valid & low_mask(fs);
@@ -789,6 +806,7 @@ __device__ void group_eval_t(const uint8_t *__restrict__ buf, const HEntry *tab,
 							cx = true;
 					} else if (sc) {
 						stop = true;
+						just = true;
 						sslot = (h + s + (unsigned)fs) & hmask;
 						kind = ((dm >> fs) & 1) ? kProbeDue : kProbeDisplace;
 						occ_off = oo;
@@ -798,6 +816,30 @@ __device__ void group_eval_t(const uint8_t *__restrict__ buf, const HEntry *tab,
 						sslot = (h + s + (unsigned)fe) & hmask;
 					}
 				}
+			}
+			if (__any_sync(FULL, !done && want2 && kind == kProbeDue && !stop2)) { // the second stopping slot
+				const bool need2 = !done && want2 && kind == kProbeDue && !stop2;
+				const unsigned from = just ? ~low_mask(fs + 1) : 0xffffffffu;
+				const unsigned sc2 = sc & from;
+				const int f2 = sc2 ? __ffs(sc2) - 1 : G;
+				const int src2 = (int)gshift + (f2 % G);
+				const int64_t oo2 = __shfl_sync(FULL, e.offset, src2), ot2 = __shfl_sync(FULL, e.tag, src2);
+				if (need2) {
+					round2 += __popc(qm & valid & from & low_mask(f2));
+					if (sc2) {
+						stop2 = true;
+						sslot2 = (h + s + (unsigned)f2) & hmask;
+						kind2 = ((dm >> f2) & 1) ? kProbeDue : kProbeDisplace;
+						occ2_off = oo2;
+						occ2_tag = ot2;
+					} else if (em) {
+						stop2 = true;
+						kind2 = kProbeEmpty;
+						sslot2 = (h + s + (unsigned)fe) & hmask;
+					}
+				}
+			}
+			if (!done) {
 				const unsigned eqv = qm & valid;
 				if (neq + __popc(eqv) > K2_MAXEQ)
 					cx = true;
@@ -822,46 +864,89 @@ __device__ void group_eval_t(const uint8_t *__restrict__ buf, const HEntry *tab,
 		}
 	}
 	__syncwarp();
-	// ---- twins.  The rolling tag is an XOR over the window, so positions p and p + 1 have the SAME tag whenever
-	// buf[p] == buf[p + 31] (about one position in 16 on text): the second of two such candidates reads exactly the
-	// chain the first one writes to, which used to end the batch at it.  Both walk the same chain from the same
-	// table, so this group knows what its predecessor does and evaluates its own candidate on the table as the
-	// predecessor leaves it -- for the two common cases:
-	//   predecessor appends at the chain end E and E + 1 is empty: this candidate meets one more equal-tag entry
-	//     (the predecessor's, a tag miss unless the two windows really match) and appends at E + 1 -- or replaces
-	//     that entry when it is already due for cleaning, or evicts when it completes the chain;
-	//   predecessor evicts from a full chain: the chain keeps its slots, this candidate evicts the next victim.
-	// The commit warp skips the predecessor's insert when it checks this lane's reads (L.twin).
-	bool tw = active && !cx && do_insert && !(sh->cmd_flags & 1) && cand_idx >= 1 && sh->qtag[cand_idx - 1] == t &&
-		  !(cand_idx >= 2 && sh->qtag[cand_idx - 2] == t);
+	// ---- same-tag predecessors ("twins").  The rolling tag is an XOR over the window, so positions p and p + 1 have the
+	// SAME tag whenever buf[p] == buf[p + 31] (about one position in 16 on text), repeated phrases give equal tags further
+	// apart, and runs give several in a row: a later one of such candidates reads exactly the chain the earlier ones write
+	// to, which used to end the batch at it.  All of them walk the same chain from the same table, so this group knows what
+	// its predecessors do and evaluates its own candidate on the table as they leave it:
+	//   they append at the chain end E, E + 1, ... (those slots are empty): this candidate meets that many more equal-tag
+	//     entries (tag misses unless the windows really match) and appends behind them; with ONE predecessor it may
+	//     instead replace that entry when it is already due for cleaning, or evict when it completes the chain;
+	//   they evict from a full chain: the chain keeps its slots, this candidate evicts the next victim;
+	//   the (one) predecessor replaces the first due entry of the chain: this candidate's insert goes to the next slot
+	//     that stops an insert (found on the same walk), or replaces the predecessor's entry when the tag itself is due.
+	// Anything else is left to the validation (a conflict).  The commit warp skips the predecessors' inserts when it checks
+	// this lane's reads (L.twmask); the other writes of those lanes, and every other lane's, are checked as usual.
+	bool tw = active && !cx && npred >= 1 && npred <= K2_TWMAX;
+	bool tw_evicts = false; // a predecessor may have removed one of the equal-tag entries this walk recorded
 	if (__any_sync(FULL, tw)) {
-		const bool twE = tw && kind == kProbeEmpty, twC = tw && kind == kProbeChain;
-		HEntry nx;
-		nx.offset = nx.tag = 1;
-		if (twE)
-			nx = ld_entry(tab + ((sslot + 1) & hmask));
-		const bool ok = twC || (twE && !(nx.offset | nx.tag));
-		const bool nm = ok && quick_no_match(buf, p, sh->qpos[cand_idx - 1], end, last_match);
-		if (ok && !nm)
-			cx = true; // the two windows may really match: the serial step decides
-		if (nm && twE) {
-			miss += 1;
-			if ((t & better) != better) {
-				// while the table is still filling (insert gate == lookup gate) the predecessor's entry itself is
-				// "due for cleaning anyway" (src/rzip.c:316-319): this candidate replaces it instead of walking on
-				kind = kProbeDue;
-			} else if (round + 1 >= max_chain) {
-				if (neq < K2_MAXEQ && max_chain <= K2_MAXEQ) {
-					if (gl == 0)
-						sh->eslot[cand_idx][neq] = sslot;
-					kind = kProbeChain;
-				} else
-					cx = true;
-			} else
-				sslot = (sslot + 1) & hmask;
-			s += 1; // the read range grows by the slot after the old chain end
+		int ip = -1; // lane k of the group looks at the k-th predecessor
+		if (tw && gl < npred) {
+			unsigned m = pm;
+			for (int k = 0; k < gl; k++)
+				m &= m - 1;
+			ip = __ffs(m) - 1;
 		}
-		tw = nm && !cx;
+		const bool maym = ip >= 0 && !quick_no_match(buf, p, sh->qpos[ip >= 0 ? ip : 0], end, last_match);
+		const bool anym = ((__ballot_sync(FULL, maym) >> gshift) & GM) != 0;
+		const bool twE = tw && kind == kProbeEmpty;
+		HEntry nx;
+		nx.offset = nx.tag = 0;
+		if (twE && gl < npred)
+			nx = ld_entry(tab + ((sslot + 1u + (unsigned)gl) & hmask));
+		const bool occupied = ((__ballot_sync(FULL, twE && gl < npred && (nx.offset | nx.tag) != 0) >> gshift) & GM) != 0;
+		if (tw) {
+			const bool tdue = (t & better) != better;
+			if (anym)
+				cx = true; // two of the windows may really match: the serial step decides
+			else if (kind == kProbeEmpty) {
+				if (occupied)
+					tw = false;
+				else if (tdue) {
+					// while the table is still filling (insert gate == lookup gate) the predecessor's entry itself is
+					// "due for cleaning anyway" (src/rzip.c:316-319): this candidate replaces it instead of walking on
+					if (npred == 1) {
+						miss += 1;
+						kind = kProbeDue;
+						s += 1;
+					} else
+						tw = false;
+				} else if (round + npred >= max_chain) {
+					if (npred == 1 && neq < K2_MAXEQ && max_chain <= K2_MAXEQ) {
+						if (gl == 0)
+							sh->eslot[cand_idx][neq] = sslot;
+						kind = kProbeChain;
+						miss += 1;
+						s += 1;
+						tw_evicts = true;
+					} else
+						tw = false;
+				} else {
+					miss += npred;
+					sslot = (sslot + (unsigned)npred) & hmask;
+					s += (unsigned)npred; // the read range grows by the slots behind the old chain end
+				}
+			} else if (kind == kProbeChain) {
+				tw_evicts = true;
+				if (npred >= max_chain)
+					tw = false;
+			} else if (kind == kProbeDue && npred == 1) {
+				if (tdue) { // replaces the predecessor's entry, which sits where the due entry was
+					if (occ_tag != t)
+						miss += 1;
+					tw_evicts = true;
+				} else if (stop2 && round + 1 + round2 < max_chain) {
+					miss += 1;
+					sslot = sslot2;
+					kind = kind2;
+					occ_off = occ2_off;
+					occ_tag = occ2_tag;
+				} else
+					tw = false;
+			} else
+				tw = false;
+		}
+		tw = tw && !cx;
 	}
 	__syncwarp();
 	// ---- equal-tag entries: would any of them give a match?  (then the serial step must decide)
@@ -896,7 +981,7 @@ __device__ void group_eval_t(const uint8_t *__restrict__ buf, const HEntry *tab,
 	}
 	// a twin looked at the chain as it was BEFORE its predecessor's insert: if that insert evicts an entry, it may be one
 	// of the survivors.  All misses are the same count either way; anything else is for the serial step.
-	if (tw && surv)
+	if (tw && tw_evicts && surv)
 		cx = true;
 	if (active && gl == 0) {
 		R->rlo[0] = h;
@@ -1006,6 +1091,7 @@ __device__ void group_eval_t(const uint8_t *__restrict__ buf, const HEntry *tab,
 		R->miss = miss;
 		R->chain = (!cx && ins && nw == 1 && kind == kProbeChain) ? 1 : 0;
 		R->twin = (tw && !cx) ? 1 : 0;
+		R->twmask = (tw && !cx) ? pm : 0u;
 		R->surv = cx ? 0u : surv;
 		R->cx = cx;
 	}
@@ -1223,7 +1309,7 @@ __device__ void k2_commit_segment_batched(WarpPrim &prim, FastShared *sh, ScanSt
 		const int mode = k2_mode_for(r.tag_mask);
 		LaneEval L;
 		L.nw = L.nr = L.net = L.ins = L.miss = L.chain = L.twin = 0;
-		L.surv = 0;
+		L.surv = L.twmask = 0;
 		L.cx = false;
 		int64_t myp = 0, myt = 0;
 		const long long ce0 = clock64();
@@ -1328,8 +1414,12 @@ __device__ void k2_commit_segment_batched(WarpPrim &prim, FastShared *sh, ScanSt
 		const long long cs0 = clock64();
 		// sweep deletions (clean_one_from_hash): the k-th insert that overfills the table removes the
 		// k-th entry, in table order from tag_clean_ptr, that lacks the next-stricter mask
+		// (only the lanes up to the first candidate that ends the round can commit: the sweep is scanned for them alone)
+		const unsigned pre_stop = __ballot_sync(FULL, lane < nb && (L.cx || (soft_on && (L.surv != 0 ||
+							  (r.cur_len > 0 && myp >= r.cur_p + kMinMatch)))));
+		const int nv0 = pre_stop ? __ffs(pre_stop) : nb;
 		const unsigned netm = __ballot_sync(FULL, L.net != 0);
-		bool cl = L.net && (r.hash_count + __popc(netm & (lt | (1u << lane))) > c.hash_limit);
+		bool cl = lane < nv0 && L.net && (r.hash_count + __popc(netm & (lt | (1u << lane))) > c.hash_limit);
 		const unsigned clm = __ballot_sync(FULL, cl);
 		const int ncl = __popc(clm), crank = __popc(clm & lt);
 		int found = 0;
@@ -1434,7 +1524,8 @@ __device__ void k2_commit_segment_batched(WarpPrim &prim, FastShared *sh, ScanSt
 			while (F) {
 				const int f = __ffs(F) - 1;
 				F &= F - 1;
-				const int nrf = __shfl_sync(FULL, mynr, f), twf = __shfl_sync(FULL, L.twin, f);
+				const int nrf = __shfl_sync(FULL, mynr, f);
+				const unsigned twf = __shfl_sync(FULL, L.twmask, f); // same-tag predecessors, by evaluation slot
 				bool hit = false;
 #pragma unroll
 				for (int q = 0; q < K2_MAXW; q++) {
@@ -1442,8 +1533,8 @@ __device__ void k2_commit_segment_batched(WarpPrim &prim, FastShared *sh, ScanSt
 						break;
 					const unsigned lo = __shfl_sync(FULL, L.rlo[q], f), len = __shfl_sync(FULL, L.rlen[q], f);
 					if (lane < f) {
-						// a twin was evaluated on the table as its predecessor's insert leaves it
-						if (myn > 0 && !(twf && lane == f - 1) && ((w0 - lo) & hmask) < len)
+						// a twin was evaluated on the table as its predecessors' inserts leave it
+						if (myn > 0 && !((twf >> (eb + lane)) & 1) && ((w0 - lo) & hmask) < len)
 							hit = true;
 						if (myn > 1 && ((w1 - lo) & hmask) < len)
 							hit = true;
@@ -1461,8 +1552,8 @@ __device__ void k2_commit_segment_batched(WarpPrim &prim, FastShared *sh, ScanSt
 				const int nlog = sh->wlog_n;
 				bool hitw = false;
 				if (lane < nv) {
-					if (lane == 0 && L.twin)
-						hitw = true; // its predecessor is no longer the lane in front of it
+					if (L.twmask & low_mask(eb))
+						hitw = true; // a predecessor it was evaluated behind is no longer part of the batch
 					for (int q = 0; q < L.nr && !hitw; q++) {
 						const unsigned lo = L.rlo[q], len = L.rlen[q];
 						for (int w = 0; w < nlog; w++)

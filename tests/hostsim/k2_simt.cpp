@@ -12,7 +12,8 @@
 // mode 0: scalar primitives, one candidate after the other; mode 1: k2_commit_kernel under the emulator
 extern "C" int simt_rzip_chunk(const uint8_t *data, int64_t n, int rzip_level, int cb, int64_t *victim_round, int64_t seg,
 			       int table_bits, int flags, int mode, uint8_t **s0_out, int64_t *s0_len, uint8_t **s1_out,
-			       int64_t *s1_len, int64_t *stats /* [8] as hostsim_rzip_chunk */, int64_t *dbg /* [16] or null */)
+			       int64_t *s1_len, int64_t *stats /* [10]: [8] as hostsim_rzip_chunk, hash of the final table, records */,
+			       int64_t *dbg /* [16] or null */)
 {
 	int64_t hi_tab[256];
 	make_hash_index(hi_tab);
@@ -67,6 +68,12 @@ extern "C" int simt_rzip_chunk(const uint8_t *data, int64_t n, int rzip_level, i
 	}
 	if (dbg)
 		memcpy(dbg, st.dbg, sizeof(st.dbg));
+	if (const char *path = getenv("K2_SIMT_TABLE_DUMP")) { // debugging aid: the final hash table
+		if (FILE *f = fopen(path, "wb")) {
+			fwrite(tab.data(), sizeof(HEntry), tab.size(), f);
+			fclose(f);
+		}
+	}
 	if (st.status != kStatusChunkDone)
 		return st.status == -9 ? -9 : -1;
 	*victim_round = st.victim_round;
@@ -85,6 +92,13 @@ extern "C" int simt_rzip_chunk(const uint8_t *data, int64_t n, int rzip_level, i
 		stats[5] = st.st_sweeps;
 		stats[6] = st.hash_count;
 		stats[7] = st.min_mask;
+		uint64_t hsh = 1469598103934665603ull; // the final hash table itself: a misplaced entry shows here first
+		for (const HEntry &e : tab) {
+			hsh = (hsh ^ (uint64_t)e.offset) * 1099511628211ull;
+			hsh = (hsh ^ (uint64_t)e.tag) * 1099511628211ull;
+		}
+		stats[8] = (int64_t)hsh;
+		stats[9] = st.n_rec;
 	}
 	return 0;
 }

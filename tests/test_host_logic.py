@@ -72,7 +72,7 @@ def _simt_commit(S, data, level, seg, table_bits, flags, mode, vr=0):
     """mode 0: the scalar control logic; mode 1: k2_commit_kernel itself (256 emulated CUDA threads, tests/hostsim/simt.h)."""
     data = np.ascontiguousarray(data, dtype=np.uint8)
     v, s0, s1, l0, l1 = C.c_int64(vr), C.c_void_p(), C.c_void_p(), C.c_int64(), C.c_int64()
-    st, dbg = (C.c_int64 * 8)(), (C.c_int64 * 16)()
+    st, dbg = (C.c_int64 * 10)(), (C.c_int64 * 16)()
     rc = S.simt_rzip_chunk(data.ctypes.data, data.size, level, oracle.chunk_bytes_for(data.size), C.byref(v), seg, table_bits,
                            flags, mode, C.byref(s0), C.byref(l0), C.byref(s1), C.byref(l1), st, dbg)
     assert rc == 0, f"rc {rc} dbg {list(dbg)}"

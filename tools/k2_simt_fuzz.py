@@ -33,7 +33,7 @@ def lib():
 def run(d, level, seg, bits, flags, mode, vr):
     S = lib()
     v, s0, s1, l0, l1 = C.c_int64(vr), C.c_void_p(), C.c_void_p(), C.c_int64(), C.c_int64()
-    st, dbg = (C.c_int64 * 8)(), (C.c_int64 * 16)()
+    st, dbg = (C.c_int64 * 10)(), (C.c_int64 * 16)()
     rc = S.simt_rzip_chunk(d.ctypes.data, d.size, level, 4, C.byref(v), seg, bits, flags, mode, C.byref(s0), C.byref(l0),
                            C.byref(s1), C.byref(l1), st, dbg)
     if rc:
@@ -85,7 +85,8 @@ def one(args):
     seed, max_kib = args
     rng = np.random.default_rng(seed)
     n = int(rng.integers(200, max_kib * 1024))
-    d = make_data(rng, n)
+    d = make_data(rng, n) if rng.integers(0, 3) else __import__('lrzip_next_b200.datagen', fromlist=['x']).gen_text_blocks(
+        n + 4096, seed=int(rng.integers(0, 1 << 30)))[:n]
     level = int(rng.choice([1, 3, 5, 6, 7, 7, 7, 8, 9]))
     bits = int(rng.integers(8, 16))
     seg = int(rng.choice([4096, 12288, 1 << 16, 1 << 18, 1 << 22]))
