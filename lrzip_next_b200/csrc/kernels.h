@@ -79,6 +79,9 @@ int filter_blocks_launch(int filter, int delta, uint8_t *s, int64_t from, int64_
 int filter_preload();
 size_t lzma_dec_prob_bytes(int njobs);
 int lzma_dec_launch(LzmaDecJob *d_jobs, int njobs, void *d_probs, cudaStream_t stream);
+// zstd frames (CTYPE_ZSTD blocks): same job record, `d_work` = zstd_dec_work_bytes(njobs) bytes of scratch
+size_t zstd_dec_work_bytes(int njobs);
+int zstd_dec_launch(LzmaDecJob *d_jobs, int njobs, void *d_work, cudaStream_t stream);
 int unrzip_preload();
 
 } // namespace lrz

@@ -1482,8 +1482,8 @@ int lrzgpu_decompress(lrzgpu_ctx *c, const uint8_t *arc, int64_t arc_len, uint8_
 				b.payload = at + hdr;
 				if (b.c_len < 0 || b.u_len < 0 || b.payload + b.c_len > end)
 					return bail(LRZGPU_EINVAL, "block payload outside the archive");
-				if (b.ctype != LRZGPU_CTYPE_NONE && b.ctype != LRZGPU_CTYPE_LZMA)
-					return bail(LRZGPU_EUNSUPPORTED, "only stored and LZMA blocks can be decoded on the device");
+				if (b.ctype != LRZGPU_CTYPE_NONE && b.ctype != LRZGPU_CTYPE_LZMA && b.ctype != LRZGPU_CTYPE_ZSTD)
+					return bail(LRZGPU_EUNSUPPORTED, "only stored, LZMA and zstd blocks can be decoded on the device");
 				blocks.push_back(b);
 				total_u[s] += b.u_len;
 				if (b.payload + b.c_len > chunk_end)
@@ -1495,9 +1495,9 @@ int lrzgpu_decompress(lrzgpu_ctx *c, const uint8_t *arc, int64_t arc_len, uint8_
 		CU(c, c->s0.ensure((size_t)total_u[0] + 64));
 		CU(c, c->s1.ensure((size_t)total_u[1] + 64));
 		int64_t comp_bytes = 0;
-		std::vector<LzmaDecJob> jobs;
+		std::vector<LzmaDecJob> jobs, zjobs;
 		for (const ArcBlock &b : blocks)
-			if (b.ctype == LRZGPU_CTYPE_LZMA)
+			if (b.ctype != LRZGPU_CTYPE_NONE)
 				comp_bytes += (b.c_len + 15) & ~(int64_t)15;
 		CU(c, c->in.ensure((size_t)comp_bytes + 64));
 		int64_t so[2] = { 0, 0 }, co = 0;
@@ -1517,7 +1517,7 @@ int lrzgpu_decompress(lrzgpu_ctx *c, const uint8_t *arc, int64_t arc_len, uint8_
 				j.c_len = b.c_len;
 				j.out = dst;
 				j.u_len = b.u_len;
-				jobs.push_back(j);
+				(b.ctype == LRZGPU_CTYPE_LZMA ? jobs : zjobs).push_back(j);
 				co += (b.c_len + 15) & ~(int64_t)15;
 			}
 			so[b.stream] += b.u_len;
@@ -1535,6 +1535,20 @@ int lrzgpu_decompress(lrzgpu_ctx *c, const uint8_t *arc, int64_t arc_len, uint8_
 			for (const LzmaDecJob &j : jobs)
 				if (j.status || j.produced != j.u_len)
 					return bail(LRZGPU_EINVAL, "corrupt LZMA block");
+		}
+		if (!zjobs.empty()) { // zstd frames: one thread per frame, frames side by side
+			const size_t jb = zjobs.size() * sizeof(LzmaDecJob);
+			CU(c, c->w1.ensure(jb));
+			CU(c, c->tab.ensure(zstd_dec_work_bytes((int)zjobs.size())));
+			CU(c, cudaMemcpyAsync(c->w1.p, zjobs.data(), jb, cudaMemcpyHostToDevice, c->sA));
+			if (zstd_dec_launch((LzmaDecJob *)c->w1.p, (int)zjobs.size(), c->tab.p, c->sA))
+				return bail(LRZGPU_ECUDA, "zstd decoder launch failed");
+			c->launches++;
+			CU(c, cudaMemcpyAsync(zjobs.data(), c->w1.p, jb, cudaMemcpyDeviceToHost, c->sA));
+			CU(c, cudaStreamSynchronize(c->sA));
+			for (const LzmaDecJob &j : zjobs)
+				if (j.status || j.produced != j.u_len)
+					return bail(LRZGPU_EINVAL, "corrupt zstd block");
 		}
 		if (flt_id) { // every stream-1 block was filtered on its own, from its position 0: all but the last are equally long
 			int64_t bs1 = 0, seen = 0;

@@ -6,6 +6,7 @@
 //                                              overlap: the reference replicates min(len, dist) bytes at a time)
 //   lzma_decompress_buf src/stream.c:556-616 -> LzmaUncompress -> LzmaDec (src/lzma/C/LzmaDec.c): raw LZMA
 //                                              stream, lc3 lp0 pb2, known output size, no end marker
+//   zstd_decompress_buf src/stream.c:1989-2010 -> ZSTD_decompress: one RFC 8878 frame per block (zstd_dec.cuh)
 //
 // The replay is a gather once the record offsets are known: one thread walks stream 0 and writes, per record,
 // where its bytes go (a running sum -- the only serial part, 3 to 3+cb bytes per record); every literal byte is
@@ -13,6 +14,7 @@
 // replayed in record order by one CTA, each copy spread over its threads (a copy that overlaps itself reads
 // periodically from the dist bytes before it, so it is parallel as well).
 #include "kernels.h"
+#include "zstd_dec.cuh"
 
 namespace lrz {
 
@@ -346,6 +348,19 @@ __global__ void lzma_dec_kernel(LzmaDecJob *jobs, int njobs, uint16_t *prob_aren
 	j.produced = pos;
 }
 
+// One zstd frame per job (the payload of a CTYPE_ZSTD stream block), one thread per frame, one frame per CTA so that
+// the frames of a chunk spread over the SMs (zstd_dec.cuh).
+__global__ void zstd_dec_kernel(LzmaDecJob *jobs, int njobs, zd::Work *work)
+{
+	const int b = blockIdx.x;
+	if (b >= njobs || threadIdx.x)
+		return;
+	LzmaDecJob &j = jobs[b];
+	const int64_t r = zd::decode_frame(j.src, j.c_len, j.out, j.u_len, work + b);
+	j.status = r < 0 ? (int32_t)r : 0;
+	j.produced = r < 0 ? 0 : r;
+}
+
 } // namespace
 
 int unrzip_parse_launch(const uint8_t *d_s0, int64_t s0_len, int cb, int64_t chunk_size, DecLit *d_lits, DecMatch *d_matches,
@@ -379,6 +394,16 @@ int lzma_dec_launch(LzmaDecJob *d_jobs, int njobs, void *d_probs, cudaStream_t s
 	return cudaGetLastError() == cudaSuccess ? 0 : -1;
 }
 
+size_t zstd_dec_work_bytes(int njobs) { return (size_t)njobs * sizeof(zd::Work); }
+
+int zstd_dec_launch(LzmaDecJob *d_jobs, int njobs, void *d_work, cudaStream_t stream)
+{
+	if (njobs <= 0)
+		return 0;
+	zstd_dec_kernel<<<(unsigned)njobs, 32, 0, stream>>>(d_jobs, njobs, (zd::Work *)d_work);
+	return cudaGetLastError() == cudaSuccess ? 0 : -1;
+}
+
 int unrzip_preload()
 {
 	cudaFuncAttributes a;
@@ -386,6 +411,7 @@ int unrzip_preload()
 	ok = ok && cudaFuncGetAttributes(&a, lit_scatter_kernel) == cudaSuccess;
 	ok = ok && cudaFuncGetAttributes(&a, match_replay_kernel) == cudaSuccess;
 	ok = ok && cudaFuncGetAttributes(&a, lzma_dec_kernel) == cudaSuccess;
+	ok = ok && cudaFuncGetAttributes(&a, zstd_dec_kernel) == cudaSuccess;
 	return ok ? 0 : -1;
 }
 

@@ -192,9 +192,19 @@ def test_device_decode_round_trips_and_reads_reference_archives(ctx):
     bad[len(bad) // 2] ^= 0x40
     with pytest.raises(Exception):
         ctx.decompress(bytes(bad))
-    z = ctx.compress(datagen.generate("text", 200_000), make_params(backend=BACKEND_ZSTD, threads=8))
-    with pytest.raises(Exception):
-        ctx.decompress(z)  # zstd blocks are not decoded on the device (yet): an error, not garbage
+    # zstd blocks (one RFC 8878 frame per stream block, csrc/zstd_dec.cuh): our own frames and libzstd's level-17 ones
+    # written by the reference binary, compressed and stored blocks mixed (C4 shape)
+    for d in (datagen.generate("text", 2_500_000), datagen.generate("randzero", 24 << 20),
+              np.concatenate([datagen.generate("rep", 3 << 20, block=1 << 17), datagen.generate("text", 1 << 20)])):
+        kw = dict(backend=BACKEND_ZSTD, threads=8, processors=os.cpu_count() or 8)
+        z = ctx.compress(d, make_params(**kw))
+        assert ctx.decompress(z) == d.tobytes()
+        theirs = oracle.ref_compress(d, oracle.make_params(**kw))
+        assert ctx.decompress(theirs) == d.tobytes()
+        bad = bytearray(theirs)
+        bad[len(bad) // 3] ^= 0x10
+        with pytest.raises(Exception):
+            ctx.decompress(bytes(bad))
 
 
 @pytest.mark.skipif(not oracle.have_ref(), reason="oracle/_ref not built")

@@ -274,6 +274,65 @@ def _zstd_libs():
     return L, Z
 
 
+def test_zstd_frame_decoder_reads_libzstd_and_our_own_frames():
+    """The decode path's zstd frame decoder (csrc/zstd_dec.cuh, host build): frames made by the system's libzstd at
+    levels 1 .. 22 (raw / RLE / compressed blocks, Huffman literals with direct and FSE-compressed weights, one and
+    four streams, treeless literals, predefined / RLE / FSE / repeat sequence tables, repeat offsets, multi-block frames)
+    and by the product's own block encoder come back byte-identical; damaged frames are refused, not mis-decoded."""
+    import ctypes as C
+    L, Z = _zstd_libs()
+    here = os.path.join(os.path.dirname(os.path.abspath(__file__)), "hostsim")
+    D = C.CDLL(os.path.join(here, "libzstddechost.so"))
+    D.hostsim_zstd_decode.restype = C.c_int64
+    D.hostsim_zstd_decode.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64]
+    rng = np.random.default_rng(1)
+    cases = {
+        "text": datagen.gen_text(1_000_000), "small": datagen.gen_text(3000), "rep": datagen.gen_rep(2_000_000, block=1 << 16),
+        "zeros": np.zeros(500_000, dtype=np.uint8), "random": rng.integers(0, 256, 300_000, dtype=np.uint8),
+        "trees": datagen.gen_trees(3_000_000, copies=4), "vm": datagen.gen_vm(2_000_000),
+        "few": rng.integers(0, 3, 400_000, dtype=np.uint8), "empty": np.zeros(0, dtype=np.uint8),
+        "one": np.array([65], dtype=np.uint8), "mix": datagen.gen_mix(1_500_000),
+    }
+
+    def decode(frame, n):
+        out = np.zeros(n + 8, dtype=np.uint8)
+        r = D.hostsim_zstd_decode(frame.ctypes.data, frame.size, out.ctypes.data, n)
+        return r, out[:n]
+
+    for name, d in cases.items():
+        d = np.ascontiguousarray(d)
+        for level in (1, 3, 7, 12, 17, 19, 22):
+            buf = np.zeros(d.size + d.size // 8 + 1024, dtype=np.uint8)
+            sz = Z.ZSTD_compress(buf.ctypes.data, buf.size, d.ctypes.data, d.size, level)
+            assert not Z.ZSTD_isError(sz)
+            r, back = decode(buf[:sz].copy(), d.size)
+            assert r == d.size and np.array_equal(back, d), (name, level, r)
+        if d.size:  # the product's own frames
+            buf = np.zeros(d.size + d.size // 8 + 1024, dtype=np.uint8)
+            nc = C.c_int64()
+            sz = L.hostsim_zstd_compress(d.ctypes.data, d.size, 7, 1 << 25, buf.ctypes.data, buf.size, C.byref(nc))
+            assert sz > 0
+            r, back = decode(buf[:sz].copy(), d.size)
+            assert r == d.size and np.array_equal(back, d), (name, "own", r)
+    # damage: truncation and bit flips either fail or, at worst, produce different bytes -- never the original length
+    # with a success code AND the right bytes... a wrong payload is caught by the container's CRC / MD5; what must not
+    # happen is a crash or an out-of-bounds write (the output buffer is exactly n bytes + 8 guard bytes)
+    d = np.ascontiguousarray(cases["text"][:200_000])
+    buf = np.zeros(d.size + 1024, dtype=np.uint8)
+    sz = Z.ZSTD_compress(buf.ctypes.data, buf.size, d.ctypes.data, d.size, 17)
+    good = buf[:sz].copy()
+    assert decode(good[:sz // 2].copy(), d.size)[0] < 0
+    refused = 0
+    for k in range(200):
+        bad = good.copy()
+        bad[int(rng.integers(4, sz))] ^= 1 << int(rng.integers(0, 8))
+        out = np.full(d.size + 8, 0xAB, dtype=np.uint8)
+        r = D.hostsim_zstd_decode(bad.ctypes.data, bad.size, out.ctypes.data, d.size)
+        assert (out[d.size:] == 0xAB).all()
+        refused += r < 0 or not np.array_equal(out[:d.size], d)
+    assert refused >= 190
+
+
 def test_zstd_block_encoder_frames_decode_with_libzstd():
     import ctypes as C
     L, Z = _zstd_libs()
