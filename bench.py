@@ -136,9 +136,16 @@ class RefRunner:
     """The unmodified reference binary, file -> file on tmpfs, wall clock around the whole run
     (test/speedtest.sh:87-99 of the reference times the same way)."""
 
-    def __init__(self):
+    def __init__(self, need_bytes: int = 0):
         self.ref = os.path.join(ROOT, "oracle", "_ref", "lrzip-next")
-        self.dir = tempfile.mkdtemp(dir="/dev/shm" if os.path.isdir("/dev/shm") else None)
+        # tmpfs when it can hold the input, the warm-up file and the archive; else the default temporary directory
+        shm = "/dev/shm" if os.path.isdir("/dev/shm") else None
+        if shm and need_bytes:
+            import shutil
+            if shutil.disk_usage(shm).free < int(2.3 * need_bytes) + (256 << 20):
+                shm = None
+        self.dir = tempfile.mkdtemp(dir=shm)
+        self.tmpfs = shm is not None
         self.files = set()
 
     def available(self) -> bool:
@@ -234,7 +241,7 @@ def main():
     if a.impl == "reference":
         if rank != 0:
             return
-        rr = RefRunner()
+        rr = RefRunner(total)
         if not rr.available():
             emit({"impl": "reference", "unavailable": "oracle/_ref/lrzip-next was not built"})
             return
@@ -267,7 +274,8 @@ def main():
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
             "config": config,
             "cpu_baseline": {"value": v, "unit": "MB/s", "cores": min(threads, cores), "kind": "reference",
-                             "sample": f"the full workload ({total // MiB} MiB), lrzip-next {' '.join(flags)}, file -> file on tmpfs"},
+                             "sample": f"the full workload ({total // MiB} MiB), lrzip-next {' '.join(flags)}, file -> file on "
+                                       f"{'tmpfs' if rr.tmpfs else 'the temporary directory (tmpfs too small)'}"},
             "e2e": {"value": v, "unit": "MB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "ratio": total / osz if osz else None, "archive_bytes": osz, "archive_sha256": sha,
             "step_seconds": times, "wall_s": elapsed()})

@@ -9,13 +9,14 @@
 //   --x86       z7_BranchConvSt_X86_Enc src/lzma/C/Bra86.c         E8 / E9 rel32, the classic BCJ state machine
 //   --armt      z7_BranchConv_ARMT_Enc  src/lzma/C/Bra.c:260-338   Thumb BL pairs (F000 F800), 2-byte units
 //   --ia64      z7_BranchConv_IA64_Enc  src/lzma/C/BraIA64.c / Bra.c:343-420   br.call slots of 16-byte bundles
+//   --riscv     z7_BranchConv_RISCV_Enc src/lzma/C/Bra.c:423-720   JAL (rd = ra / t0) and AUIPC + I/S-type pairs
 //
 // The four RISC converters touch aligned 32-bit words independently of each other (a word's new value depends on the
 // word and on its offset only), so they are one thread per word; Delta is one thread per byte; the x86 converter
 // carries a few bits of state from byte to byte and is run by one thread per block (a stream block is 10 MiB: ~0.1 s,
 // beside a block encode of seconds), and so is the Thumb converter (a converted pair hides the half-word after it from
-// the scan).  IA64 works on 16-byte bundles independently: one thread per bundle.  RISC-V is not built
-// (LRZGPU_EUNSUPPORTED).
+// the scan).  IA64 works on 16-byte bundles independently: one thread per bundle.  RISC-V (JAL, AUIPC pairs) moves
+// 4, 6 or 8 bytes ahead depending on what it finds, so it is serial per block like x86.
 //
 // The converters are stated from the instruction formats; the CPU tests check them byte for byte against the
 // reference's own functions (the test-side build of the reference's LZMA SDK exports them), the GPU tests against whole archives of the
@@ -36,7 +37,8 @@ namespace flt {
 // magic byte 16 / control->filter_flag (src/include/lrzip_private.h:389-397)
 enum { kNone = 0, kX86 = 1, kARM = 2, kARMT = 3, kPPC = 4, kSPARC = 5, kIA64 = 6, kARM64 = 7, kRISCV = 8, kDelta = 128 };
 
-FLT_FN bool supported(int f) { return f == kNone || f == kX86 || f == kARM || f == kARMT || f == kPPC || f == kSPARC || f == kIA64 || f == kARM64 || f == kDelta; }
+FLT_FN bool supported(int f) { return f == kNone || f == kX86 || f == kARM || f == kARMT || f == kPPC || f == kSPARC || f == kIA64 || f == kARM64 || f == kRISCV || f == kDelta; }
+FLT_FN bool serial(int f) { return f == kX86 || f == kARMT || f == kRISCV; } // the scan's state runs through the block
 FLT_FN bool wordwise(int f) { return f == kARM || f == kPPC || f == kSPARC || f == kARM64; }
 
 FLT_FN uint32_t bswap32(uint32_t v) { return (v >> 24) | ((v >> 8) & 0xff00u) | ((v << 8) & 0xff0000u) | (v << 24); }
@@ -189,6 +191,110 @@ FLT_FN void armt_convert(uint8_t *buf, size_t n, bool enc)
 }
 
 FLT_FN void armt_encode(uint8_t *buf, size_t n) { armt_convert(buf, n, true); }
+
+// RISC-V.  Instructions start on 2-byte boundaries; two kinds are converted (everything little endian on the way in):
+//   JAL with rd = x1 (ra) or x5 (t0): byte 0 = 0xEF and bits 8, 10, 11 clear.  Its J-type immediate (a byte offset,
+//     bits 20..1 scattered over the instruction) becomes the absolute position and is laid out high bits first over
+//     the top nibble of byte 1, byte 2, byte 3.
+//   AUIPC rd, hi20 followed by a 32-bit instruction that uses rd as rs1 (I/S-type: `addi`, loads, `jalr`, ...), rd
+//     other than x0 / x2: the pair's target hi20 + sext(lo12) becomes absolute and goes, big endian, into the second
+//     word; the first word becomes an "AUIPC x2" carrying the second instruction's low 20 bits.  A REAL "AUIPC x2"
+//     in the input that looks like such a carrier (immediate bits 13:12 set, top five bits not all in {0, 2}) is
+//     rotated together with the following word so that the two cases stay apart: decoding is exact.
+// The scan moves 2 bytes past a rejected JAL, 4 past a converted JAL or a plain AUIPC x0/x2, 6 past an AUIPC without a
+// partner, 8 past a converted pair; the last 6 bytes of the (even-sized) block are never examined.
+FLT_FN uint32_t rv_le32(const uint8_t *p) { return (uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16) | ((uint32_t)p[3] << 24); }
+FLT_FN void rv_put_le32(uint8_t *p, uint32_t v)
+{
+	p[0] = (uint8_t)v;
+	p[1] = (uint8_t)(v >> 8);
+	p[2] = (uint8_t)(v >> 16);
+	p[3] = (uint8_t)(v >> 24);
+}
+FLT_FN uint32_t rv_be32(const uint8_t *p) { return ((uint32_t)p[0] << 24) | ((uint32_t)p[1] << 16) | ((uint32_t)p[2] << 8) | p[3]; }
+FLT_FN void rv_put_be32(uint8_t *p, uint32_t v)
+{
+	p[0] = (uint8_t)(v >> 24);
+	p[1] = (uint8_t)(v >> 16);
+	p[2] = (uint8_t)(v >> 8);
+	p[3] = (uint8_t)v;
+}
+// second instruction of a pair: a 32-bit encoding (low bits 11) whose rs1 field is `rd`
+FLT_FN bool rv_uses_rd(uint32_t second, uint32_t rd) { return (second & 3) == 3 && ((second >> 15) & 31) == rd; }
+// "AUIPC x2" that reads as a carrier: immediate bits 13:12 set and a top-five-bits value outside {0, 2}
+FLT_FN bool rv_carrier_like(uint32_t w) { return ((w >> 12) & 3) == 3 && ((w >> 27) & 0x1d) != 0; }
+
+FLT_FN void riscv_convert(uint8_t *buf, size_t n, bool enc)
+{
+	n &= ~(size_t)1;
+	if (n <= 6)
+		return;
+	const size_t lim = n - 6;
+	size_t i = 0;
+	while (i < lim) {
+		uint8_t *p = buf + i;
+		const uint32_t op = p[0] & 0x7f;
+		if (op != 0x6f && op != 0x17) {
+			i += 2;
+			continue;
+		}
+		const uint32_t pc = (uint32_t)i;
+		if (op == 0x6f) { // JAL
+			if (p[0] != 0xef || (p[1] & 0x0d) != 0) {
+				i += 2;
+				continue;
+			}
+			if (enc) {
+				const uint32_t w = rv_le32(p);
+				uint32_t t = ((w >> 11) & 0x100000u) | ((w >> 20) & 0x7feu) | ((w >> 9) & 0x800u) | (w & 0xff000u);
+				t += pc;
+				p[1] = (uint8_t)(((t >> 13) & 0xf0) | (p[1] & 0x0f));
+				p[2] = (uint8_t)(t >> 9);
+				p[3] = (uint8_t)(t >> 1);
+			} else {
+				uint32_t t = ((uint32_t)(p[1] & 0xf0) << 13) | ((uint32_t)p[2] << 9) | ((uint32_t)p[3] << 1);
+				t -= pc;
+				const uint32_t w = (uint32_t)p[0] | ((uint32_t)(p[1] & 0x0f) << 8) | ((t << 11) & 0x80000000u) |
+						   ((t << 20) & 0x7fe00000u) | ((t << 9) & 0x100000u) | (t & 0xff000u);
+				rv_put_le32(p, w);
+			}
+			i += 4;
+			continue;
+		}
+		// AUIPC
+		const uint32_t w = rv_le32(p), rd = (w >> 7) & 31, second = rv_le32(p + 4);
+		if (rd != 0 && rd != 2) {
+			if (!rv_uses_rd(second, rd)) {
+				i += 6;
+				continue;
+			}
+			if (enc) { // a real pair -> carrier + absolute target
+				const uint32_t target = (w & 0xfffff000u) + (uint32_t)((int32_t)second >> 20) + pc;
+				rv_put_le32(p, (second << 12) | 0x117u);
+				rv_put_be32(p + 4, target);
+			} else { // the rotated form of a real "AUIPC x2" that looked like a carrier: rotate back
+				rv_put_le32(p, (second << 12) | 0x117u);
+				rv_put_le32(p + 4, (w & 0xfffff000u) | (second >> 20));
+			}
+			i += 8;
+			continue;
+		}
+		if (rd == 2 && rv_carrier_like(w)) {
+			const uint32_t top = w >> 27;
+			if (enc) { // keep it apart from the carriers: rotate it with the word behind it
+				rv_put_le32(p, (top << 7) + 0x17u + (second & 0xfffff000u));
+				rv_put_le32(p + 4, (w >> 12) | (second << 20));
+			} else { // a carrier: rebuild the pair
+				const uint32_t target = rv_be32(p + 4) - pc;
+				rv_put_le32(p, (top << 7) + 0x17u + ((target + 0x800u) & 0xfffff000u));
+				rv_put_le32(p + 4, (w >> 12) | (target << 20));
+			}
+			i += 8;
+			continue;
+		}
+		i += 4;
+	}
+}
 
 // IA64: a 16-byte bundle = 5 template bits + three 41-bit slots; the template says which slots hold branch-unit
 // instructions.  A slot is converted when it is br.call-like (opcode 5, btype 0): its 21-bit immediate (20 bits at 13,
