@@ -36,7 +36,7 @@ __global__ void __launch_bounds__(256) filter_words_kernel(uint8_t *s, int64_t f
 	}
 }
 
-// x86 and ARM Thumb: the scan's state runs through the whole block: one thread per block.
+// x86, ARM Thumb and RISC-V: the scan's state runs through the whole block: one thread per block.
 __global__ void filter_serial_kernel(uint8_t *s, int64_t from, int64_t to, int64_t bs, int filter, bool enc)
 {
 	if (threadIdx.x)
@@ -44,6 +44,8 @@ __global__ void filter_serial_kernel(uint8_t *s, int64_t from, int64_t to, int64
 	const int64_t k = blockIdx.x;
 	if (filter == flt::kX86)
 		flt::x86_convert(s + from + k * bs, (size_t)block_len(k, from, to, bs), enc);
+	else if (filter == flt::kRISCV)
+		flt::riscv_convert(s + from + k * bs, (size_t)block_len(k, from, to, bs), enc);
 	else
 		flt::armt_convert(s + from + k * bs, (size_t)block_len(k, from, to, bs), enc);
 }
@@ -140,7 +142,7 @@ int filter_blocks_launch(int filter, int delta, uint8_t *s, int64_t from, int64_
 		filter_words_kernel<<<dim3(gx, (unsigned)nblk), 256, 0, stream>>>(s, from, to, bs, filter, enc);
 		if (launches)
 			*launches += 1;
-	} else if (filter == flt::kX86 || filter == flt::kARMT) {
+	} else if (flt::serial(filter)) {
 		filter_serial_kernel<<<(unsigned)nblk, 32, 0, stream>>>(s, from, to, bs, filter, enc);
 		if (launches)
 			*launches += 1;

@@ -105,13 +105,12 @@ int compute_sizing(const lrzgpu_params &p, int64_t st_size_in, lrzgpu_sizing_t &
 	case LRZGPU_FILTER_PPC:
 	case LRZGPU_FILTER_SPARC:
 	case LRZGPU_FILTER_ARM64:
+	case LRZGPU_FILTER_RISCV:
 		break;
 	case LRZGPU_FILTER_DELTA:
 		if (p.delta < 1 || p.delta > 256 || (p.delta > 16 && p.delta % 16))
 			return LRZGPU_EINVAL;
 		break;
-	case LRZGPU_FILTER_RISCV:
-		return LRZGPU_EUNSUPPORTED;
 	default:
 		return LRZGPU_EINVAL;
 	}

@@ -1441,7 +1441,7 @@ int lrzgpu_decompress(lrzgpu_ctx *c, const uint8_t *arc, int64_t arc_len, uint8_
 		flt_id = LRZGPU_FILTER_DELTA;
 		flt_delta = i <= 16 ? i : (i - 15) * 16;
 	}
-	if (flt_id == LRZGPU_FILTER_RISCV || (flt_id > LRZGPU_FILTER_RISCV && flt_id != LRZGPU_FILTER_DELTA))
+	if (flt_id > LRZGPU_FILTER_RISCV && flt_id != LRZGPU_FILTER_DELTA)
 		return fail(c, LRZGPU_EUNSUPPORTED, "filter %d is not supported", flt_id);
 	if (arc[14] != 1)
 		return fail(c, LRZGPU_EUNSUPPORTED, "only MD5 archives are supported (hash code %d)", arc[14]);

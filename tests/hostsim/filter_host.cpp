@@ -25,6 +25,8 @@ extern "C" int hostsim_filter_block(int filter, int delta, uint8_t *buf, int64_t
 		flt::x86_encode(buf, (size_t)n);
 	else if (filter == flt::kARMT)
 		flt::armt_encode(buf, (size_t)n);
+	else if (filter == flt::kRISCV)
+		flt::riscv_convert(buf, (size_t)n, true);
 	else if (filter == flt::kIA64) {
 		for (int64_t o = 0; o + 16 <= n; o += 16)
 			flt::ia64_bundle(buf + o, (uint32_t)o);
@@ -58,6 +60,8 @@ extern "C" int hostsim_unfilter_block(int filter, int delta, uint8_t *buf, int64
 		flt::x86_convert(buf, (size_t)n, false);
 	else if (filter == flt::kARMT)
 		flt::armt_convert(buf, (size_t)n, false);
+	else if (filter == flt::kRISCV)
+		flt::riscv_convert(buf, (size_t)n, false);
 	else if (filter == flt::kIA64) {
 		for (int64_t o = 0; o + 16 <= n; o += 16)
 			flt::ia64_bundle(buf + o, (uint32_t)o, false);

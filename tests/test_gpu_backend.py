@@ -239,8 +239,36 @@ def test_filtered_archives_bit_identical_to_reference(ctx, flt, delta, flag, bac
     assert ctx.decompress(want) == d.tobytes()  # the decode side undoes the filter per stream-1 block
 
 
+@pytest.mark.skipif(not oracle.have_ref(), reason="oracle/_ref not built")
+def test_riscv_filtered_archive_bit_identical_to_reference(ctx):
+    """--riscv (z7_BranchConv_RISCV_Enc, src/lzma/C/Bra.c:423-720): JAL ra / t0 and AUIPC pairs planted on 2-byte
+    boundaries, two chunks of three stored blocks; archive equal to the reference binary's, decoded back on the device."""
+    rng = np.random.default_rng(88)
+    n = 80 << 20
+    d = rng.integers(0, 256, n, dtype=np.uint8)
+    pos = (rng.integers(0, n // 2 - 8, n // 40) * 2).astype(np.int64)
+    k = pos.size // 2
+    d[pos[:k]] = 0xEF
+    d[pos[:k] + 1] = (d[pos[:k] + 1] & 0xF0) | rng.choice(np.array([0, 2], dtype=np.uint8), k)
+    rd = rng.integers(1, 32, pos.size - k).astype(np.uint8)
+    d[pos[k:]] = 0x17 | ((rd & 1) << 7)
+    d[pos[k:] + 1] = (d[pos[k:] + 1] & 0xF0) | (rd >> 1)
+    d[pos[k:] + 4] |= 3                                             # a 32-bit second instruction ...
+    d[pos[k:] + 5] = (d[pos[k:] + 5] & 0x7F) | ((rd & 1) << 7)      # ... whose rs1 is the AUIPC's rd
+    d[pos[k:] + 6] = (d[pos[k:] + 6] & 0xF0) | (rd >> 1)
+    d[5 << 20:9 << 20] = datagen.generate("text", 4 << 20)
+    kw = dict(threads=1, processors=os.cpu_count() or 8, ramsize=100 * 1048576)
+    got = ctx.compress(d, make_params(backend=0, filter=8, **kw))
+    want = oracle.ref_compress(d, oracle.make_params(backend=0, **kw), extra=("--riscv",))
+    assert got[16] == want[16] == 8
+    assert got == want
+    plain = oracle.ref_compress(d, oracle.make_params(backend=0, **kw))
+    assert sum(a != b for a, b in zip(want[:4 << 20], plain[:4 << 20])) > 1000  # the converter did convert
+    assert ctx.decompress(want) == d.tobytes()
+
+
 def test_unbuilt_filters_are_rejected(ctx):
-    for flt in (8, 77):
+    for flt in (9, 77):
         with pytest.raises(Exception):
             ctx.compress(np.zeros(1000, dtype=np.uint8), make_params(filter=flt))
     with pytest.raises(Exception):
