@@ -55,7 +55,8 @@ enum {
 enum { LRZGPU_CTYPE_NONE = 3, LRZGPU_CTYPE_LZMA = 6, LRZGPU_CTYPE_ZSTD = 10 };
 
 /* pre-compression filter of the stream-1 blocks (control->filter_flag, src/include/lrzip_private.h:389-397;
- * applied in compthread, src/stream.c:1587-1628).  RISCV is not built: LRZGPU_EUNSUPPORTED. */
+ * applied in compthread, src/stream.c:1587-1628).  All of them are built (RISC-V: z7_BranchConv_RISCV_Enc,
+ * src/lzma/C/Bra.c:423-720). */
 enum {
 	LRZGPU_FILTER_NONE = 0, LRZGPU_FILTER_X86 = 1, LRZGPU_FILTER_ARM = 2, LRZGPU_FILTER_ARMT = 3, LRZGPU_FILTER_PPC = 4,
 	LRZGPU_FILTER_SPARC = 5, LRZGPU_FILTER_IA64 = 6, LRZGPU_FILTER_ARM64 = 7, LRZGPU_FILTER_RISCV = 8, LRZGPU_FILTER_DELTA = 128
@@ -78,7 +79,7 @@ typedef struct lrzgpu_params {
 	int threshold;    /* lz4 gate: 0 = off (-T), else percent (default 100) */
 	int nobemt;       /* --nobemt: with LZMA level >= 5 and threads > 1 the reference switches to the single-threaded
 			     bt4 finder (src/stream.c:456); not reproduced => LRZGPU_EUNSUPPORTED */
-	int filter;       /* LRZGPU_FILTER_* (--x86 --arm --armt --arm64 --ppc --sparc --ia64 --delta), 0 = none */
+	int filter;       /* LRZGPU_FILTER_* (--x86 --arm --armt --arm64 --ppc --sparc --ia64 --riscv --delta), 0 = none */
 	int delta;        /* --delta: the distance in bytes, 1..16 or a multiple of 16 up to 256 (control->delta) */
 	int stdin_mode;   /* reproduce `... | lrzip-next -o out`: the input's size is unknown while it is read, so every
 			     chunk is one mmap buffer of min(ramsize / 3, max_chunk) bytes (src/rzip.c:995-1013, 800-836) and the
@@ -173,8 +174,9 @@ int lrzgpu_chunk_select(lrzgpu_ctx *ctx, int64_t victim_in, lrzgpu_stats *stats)
  * host memory -> the original bytes (malloc'ed).  Container walk on the host; LZMA blocks (lzma_decompress_buf,
  * src/stream.c:556-616) decoded on the device, one thread per block; stream 0 parsed into records and replayed on
  * the device (literals scattered by all SMs, matches in order); chunk CRC-32 and the trailing MD5 are verified.
- * Stored and LZMA blocks only (zstd and the other back ends: LRZGPU_EUNSUPPORTED); filtered archives are unfiltered
- * per stream-1 block (all filters but RISC-V); no encryption. */
+ * zstd blocks (zstd_decompress_buf, src/stream.c:1989-2010) are decoded on the device too, one thread per frame.
+ * Stored, LZMA and zstd blocks (the other back ends: LRZGPU_EUNSUPPORTED); filtered archives are unfiltered per
+ * stream-1 block (every filter of the reference); no encryption. */
 int lrzgpu_decompress(lrzgpu_ctx *ctx, const uint8_t *archive, int64_t archive_len, uint8_t **out, int64_t *out_len);
 
 /* Archive walker (get_fileinfo, src/lrzip.c:1069-1459, what `lrzip-next -i [-vv]` prints): host only, no device.
