@@ -1100,7 +1100,7 @@ __device__ void group_eval_t(const uint8_t *__restrict__ buf, const HEntry *tab,
 
 // This warp's share of a batch of nb candidates (warp 0..7): four candidates at once, 8 lanes each, so that
 // their table walks and their far-byte compares overlap; tighter gates get more windows in flight per step.
-__device__ void k2_eval_share(const uint8_t *__restrict__ buf, const HEntry *tab, unsigned hmask, FastShared *sh, int nb, int mode,
+__device__ __noinline__ void k2_eval_share(const uint8_t *__restrict__ buf, const HEntry *tab, unsigned hmask, FastShared *sh, int nb, int mode,
 			      int64_t tag_mask, int64_t better, int max_chain, int64_t end, int64_t last_match, int lane, int warp)
 {
 	const int ci = warp * 4 + (lane >> 3);
