@@ -103,4 +103,81 @@ extern "C" int simt_rzip_chunk(const uint8_t *data, int64_t n, int rzip_level, i
 	return 0;
 }
 
+// All-values speculation of the cross-window counter (lrzgpu_chunk_begin_all): the kernel as a grid of `nvar` CTAs, CTA v
+// starting from victim_round = v with its own state, table and record array (blockIdx.x strides).  Per variant:
+// out[v * 6 ..] = status, outgoing victim_round, records, stream-0 length, stream-1 length, hash of the final table.
+extern "C" int simt_rzip_chunk_variants(const uint8_t *data, int64_t n, int rzip_level, int cb, int nvar, int64_t seg,
+					int table_bits, int flags, int mode, int64_t *out)
+{
+	int64_t hi_tab[256];
+	make_hash_index(hi_tab);
+	std::vector<uint8_t> padded((size_t)n + 256 + kInputPad + 64, 0);
+	uint8_t *buf = padded.data() + 256;
+	buf += (16 - ((uintptr_t)buf & 15)) & 15;
+	memcpy(buf, data, (size_t)n);
+	const int64_t rec_cap = n / kMinMatch + 8;
+	std::vector<ScanState> st((size_t)nvar);
+	for (int v = 0; v < nvar; v++) {
+		k2_init_state(&st[(size_t)v], n, rzip_level, cb, v, rec_cap);
+		if (table_bits) {
+			st[(size_t)v].hash_bits = table_bits;
+			st[(size_t)v].hash_limit = ((int64_t)1 << table_bits) / 3 * 2;
+		}
+		st[(size_t)v].flags = flags;
+	}
+	const int64_t tab_stride = (int64_t)1 << st[0].hash_bits, loosest = st[0].min_mask; // the level's initial gate
+	std::vector<HEntry> tab((size_t)(tab_stride * nvar), HEntry{ 0, 0 });
+	std::vector<MatchRec> recs((size_t)(rec_cap * nvar));
+	seg = (seg + kTile - 1) / kTile * kTile;
+	const int64_t nseg = (n + seg - 1) / seg;
+	for (int64_t i = 0; i < nseg; i++) {
+		const int64_t lo = i * seg, hi = lo + seg < n ? lo + seg : n;
+		std::vector<Cand> cand;
+		std::vector<uint32_t> tc;
+		scalar_k1(buf, n, lo, hi, loosest, hi_tab, cand, tc); // one list for all variants, made with the loosest gate
+		const int64_t first_tile = lo / kTile, num_tiles = (hi - 1) / kTile - lo / kTile + 1;
+		cand.resize(cand.size() + 1024, Cand{ 0, 0 });
+		for (int v = 0; v < nvar; v++) {
+			if (mode == 0) {
+				ScalarPrim prim;
+				prim.buf = buf;
+				prim.tab = tab.data() + v * tab_stride;
+				prim.hmask = tab_stride - 1;
+				prim.cand = cand.data();
+				prim.tile_count = tc.data();
+				prim.first_tile = first_tile;
+				prim.num_tiles = num_tiles;
+				prim.seg_hi = hi;
+				prim.tile = 0;
+				prim.idx = 0;
+				k2_commit_segment(prim, &st[(size_t)v], recs.data() + v * rec_cap, i == nseg - 1);
+			} else {
+				const bool last = i == nseg - 1;
+				if (!simt::run_block(K2_THREADS, (unsigned)v, [&]() {
+					    k2_commit_kernel(buf, st.data(), tab.data(), cand.data(), tc.data(), first_tile, num_tiles, hi,
+							     recs.data(), last ? 1 : 0, tab_stride, rec_cap);
+				    }))
+					return -2;
+			}
+		}
+	}
+	for (int v = 0; v < nvar; v++) {
+		const ScanState &s = st[(size_t)v];
+		uint64_t hsh = 1469598103934665603ull;
+		for (int64_t k = 0; k < tab_stride; k++) {
+			const HEntry &e = tab[(size_t)(v * tab_stride + k)];
+			hsh = (hsh ^ (uint64_t)e.offset) * 1099511628211ull;
+			hsh = (hsh ^ (uint64_t)e.tag) * 1099511628211ull;
+		}
+		int64_t *o = out + v * 6;
+		o[0] = s.status;
+		o[1] = s.victim_round;
+		o[2] = s.n_rec;
+		o[3] = s.s0_len;
+		o[4] = s.s1_len;
+		o[5] = (int64_t)hsh;
+	}
+	return 0;
+}
+
 extern "C" void simt_free(void *p) { free(p); }

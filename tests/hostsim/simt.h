@@ -27,6 +27,7 @@
 #define __forceinline__ inline __attribute__((always_inline))
 #define __shared__ static
 #define __launch_bounds__(...)
+#define __noinline__ __attribute__((noinline))
 
 struct longlong2 {
 	long long x, y;

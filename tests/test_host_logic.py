@@ -114,6 +114,30 @@ def test_batched_commit_kernel_under_simt_equals_scalar_logic(k2simt, kind, n, l
         assert dbg[15] > 0 and dbg[2] == 0  # match tails instead of serial steps
 
 
+def test_commit_kernel_grid_of_counter_variants_under_simt(k2simt):
+    """lrzgpu_chunk_begin_all's launch shape: k2_commit_kernel as a grid of max_chain_len CTAs, CTA v starting from
+    victim_round = v on its own state / table / records (blockIdx.x strides), all reading one candidate list made with
+    the loosest gate.  Every variant must end exactly where the scalar logic started from the same value ends; on data that
+    saturates equal-tag chains the variants really differ."""
+    blk = np.frombuffer(b"abcdefg" * 5, dtype=np.uint8)
+    d = np.tile(blk, 90_000 // blk.size + 1)[:90_000].copy()
+    rnd = np.random.default_rng(5).integers(0, 256, size=d.size // 8, dtype=np.uint8)
+    d[::8] ^= (rnd & 1)  # many equal windows, few long matches (as tests/test_gpu_rzip.py::test_rzip_victim_round_carried)
+    d = np.concatenate([d, datagen.generate("text", 110_000)])
+    S = k2simt
+    S.simt_rzip_chunk_variants.argtypes = [C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int64, C.c_int, C.c_int,
+                                           C.c_int, C.POINTER(C.c_int64)]
+    nvar = 6  # rzip level 6: max_chain_len 6
+    outs = []
+    for mode in (0, 1):
+        o = (C.c_int64 * (6 * nvar))()
+        assert S.simt_rzip_chunk_variants(d.ctypes.data, d.size, 6, 4, nvar, 1 << 16, 11, 0, mode, o) == 0
+        outs.append([tuple(o[6 * v:6 * v + 6]) for v in range(nvar)])
+    assert outs[0] == outs[1]
+    assert all(r[0] == 2 for r in outs[1])                 # kStatusChunkDone
+    assert len({r[5] for r in outs[1]}) > 1                # the incoming counter value matters on this input
+
+
 def _lzma(Z, data, level, dic):
     n = len(data)
     cap = int(n * 1.02)
