@@ -85,8 +85,11 @@ def one(args):
     seed, max_kib = args
     rng = np.random.default_rng(seed)
     n = int(rng.integers(200, max_kib * 1024))
-    d = make_data(rng, n) if rng.integers(0, 3) else __import__('lrzip_next_b200.datagen', fromlist=['x']).gen_text_blocks(
-        n + 4096, seed=int(rng.integers(0, 1 << 30)))[:n]
+    if rng.integers(0, 3):
+        d = make_data(rng, n)
+    else:  # plain text: the sweeps, gate tightening and same-tag runs of the headline workload
+        from lrzip_next_b200 import datagen
+        d = datagen.gen_text(n, seed=int(rng.integers(0, 1 << 30)))
     level = int(rng.choice([1, 3, 5, 6, 7, 7, 7, 8, 9]))
     bits = int(rng.integers(8, 16))
     seg = int(rng.choice([4096, 12288, 1 << 16, 1 << 18, 1 << 22]))
