@@ -451,12 +451,14 @@ __device__ __forceinline__ void k2_bar(int id) { asm volatile("bar.sync %0, %1;"
 // evaluates up to 32 queued candidates at once, ONE PER LANE, against the table as it stands at the
 // start of the batch, and then validates in order that no candidate read a slot written (inserted into
 // or swept) by an earlier candidate of the same batch.  The longest conflict-free prefix is committed
-// with exactly the effects the serial loop would have had; the first candidate that needs anything
-// beyond the simple cases -- a real match (anything that touches the pending-match / emit logic), an
-// equal-tag chain reaching max_chain_len (victim_round), a displacement chain deeper than 3, a sweep
-// that wraps (mask promotion), a write inside the stretch of table the sweep is about to visit -- is
-// handed to the serial k2_step(), which is also used while a match is pending.  The batch therefore
-// never decides anything the serial code would decide differently.
+// with exactly the effects the serial loop would have had.  A candidate that may match, or that triggers the
+// emission of the pending match, is committed with that prefix too -- its lookup and insert are batch work -- and
+// then gets the second half of the loop body from the commit warp (the "match tail", see soft stoppers below).
+// The first candidate that needs anything beyond these cases -- more equal-tag entries than the walk records, a
+// displacement chain deeper than 3, a sweep that wraps (mask promotion), a write inside the stretch of table the
+// sweep is about to visit -- is handed to the serial k2_step().  Chain-cap evictions (victim_round) are ranked
+// inside the batch.  The batch therefore never decides anything the serial code would decide differently;
+// tests/hostsim runs this very kernel on the CPU (simt.h) against the scalar form of the logic.
 
 __device__ __forceinline__ void prefetch_l1(const void *p) { K2_PREFETCH_L1(p); }
 

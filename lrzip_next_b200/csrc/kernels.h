@@ -1,6 +1,11 @@
 // kernels.h -- host launchers of the sm_100a kernels (one .cu file per kernel family).
 #pragma once
+#if defined(LRZ_SIMT_HOST) // tests/hostsim: kernels compiled for the CPU under the SIMT emulator (simt.h)
+#include "simt.h"
+typedef void *cudaStream_t;
+#else
 #include <cuda_runtime.h>
+#endif
 #include "lrz_common.h"
 
 namespace lrz {

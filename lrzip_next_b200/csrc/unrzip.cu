@@ -363,6 +363,7 @@ __global__ void zstd_dec_kernel(LzmaDecJob *jobs, int njobs, zd::Work *work)
 
 } // namespace
 
+#if !defined(LRZ_SIMT_HOST) // (the emulator calls the kernels directly)
 int unrzip_parse_launch(const uint8_t *d_s0, int64_t s0_len, int cb, int64_t chunk_size, DecLit *d_lits, DecMatch *d_matches,
 			int64_t cap, DecSummary *d_sum, cudaStream_t stream)
 {
@@ -414,5 +415,6 @@ int unrzip_preload()
 	ok = ok && cudaFuncGetAttributes(&a, zstd_dec_kernel) == cudaSuccess;
 	return ok ? 0 : -1;
 }
+#endif // !LRZ_SIMT_HOST
 
 } // namespace lrz

@@ -81,7 +81,7 @@ struct BarSync {
 
 struct Block {
 	int nthreads = 0, cur = 0;
-	Dim tidx{ 0, 0, 0 }, bidx{ 0, 0, 0 };
+	Dim tidx{ 0, 0, 0 }, bidx{ 0, 0, 0 }, bdim{ 1, 1, 1 }, gdim{ 1, 1, 1 };
 	void *sched_sp = nullptr;
 	std::vector<Fiber> fibers;
 	std::vector<WarpSync> warps;
@@ -139,11 +139,14 @@ static void fiber_main()
 }
 
 // Runs `kernel` as one block of `nthreads` threads with blockIdx.x = block_x.  Returns false on a deadlock.
-static inline bool run_block(int nthreads, unsigned block_x, std::function<void()> kernel, size_t stack_bytes = 256 << 10)
+static inline bool run_block(int nthreads, unsigned block_x, std::function<void()> kernel, size_t stack_bytes = 256 << 10,
+			     unsigned grid_x = 1)
 {
 	Block blk;
 	blk.nthreads = nthreads;
 	blk.bidx.x = block_x;
+	blk.bdim.x = (unsigned)nthreads;
+	blk.gdim.x = grid_x;
 	blk.fibers.resize((size_t)nthreads);
 	blk.warps.resize((size_t)(nthreads + 31) / 32);
 	blk.entry = std::move(kernel);
@@ -189,10 +192,21 @@ static inline bool run_block(int nthreads, unsigned block_x, std::function<void(
 	return ok;
 }
 
+// A one-dimensional grid, block after block (blocks of a grid do not synchronise with each other).
+static inline bool run_grid(unsigned grid_x, int nthreads, std::function<void()> kernel, size_t stack_bytes = 64 << 10)
+{
+	for (unsigned b = 0; b < grid_x; b++)
+		if (!run_block(nthreads, b, kernel, stack_bytes, grid_x))
+			return false;
+	return true;
+}
+
 } // namespace simt
 
 #define threadIdx (simt::B->tidx)
 #define blockIdx (simt::B->bidx)
+#define blockDim (simt::B->bdim)
+#define gridDim (simt::B->gdim)
 
 static inline unsigned __ballot_sync(unsigned, bool pred)
 {

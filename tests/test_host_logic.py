@@ -138,6 +138,62 @@ def test_commit_kernel_grid_of_counter_variants_under_simt(k2simt):
     assert len({r[5] for r in outs[1]}) > 1                # the incoming counter value matters on this input
 
 
+@pytest.fixture(scope="module")
+def unrzip_simt():
+    subprocess.run(["make", "-s", "-C", os.path.join(HERE, "hostsim"), "libunrzipsimt.so"], check=True)
+    U = C.CDLL(os.path.join(HERE, "hostsim", "libunrzipsimt.so"))
+    U.simt_unrzip_chunk.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int, C.c_int64, C.c_void_p,
+                                    C.POINTER(C.c_int64), C.POINTER(C.c_uint32)]
+    U.simt_block_decode.restype = C.c_int64
+    U.simt_block_decode.argtypes = [C.c_int, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64]
+    return U
+
+
+@pytest.mark.parametrize("kind,n,level,cb", [("text", 400_000, 7, 4), ("rep", 1 << 20, 7, 4), ("mix", 600_000, 7, 5),
+                                             ("vm", 800_000, 9, 4), ("trees", 700_000, 7, 4), ("text", 40, 7, 4)])
+def test_decode_kernels_under_simt_replay_the_oracle_streams(unrzip_simt, kind, n, level, cb):
+    """The decode kernels themselves (csrc/unrzip.cu: stream-0 parser, literal scatter over a grid, match replay by one
+    1024-thread CTA incl. self-overlapping copies) on the CPU: the oracle's streams of a chunk come back as the chunk,
+    with the CRC the stream carries; a damaged stream 0 is refused."""
+    d = _trees_small(n) if kind == "trees" else datagen.generate(kind, n)
+    d = np.ascontiguousarray(d)
+    s0, s1, _, _ = oracle.rzip_chunk(d, level, chunk_bytes=cb)
+    out = np.zeros(d.size + 64, dtype=np.uint8)
+    ol, crc = C.c_int64(), C.c_uint32()
+    rc = unrzip_simt.simt_unrzip_chunk(s0, len(s0), s1, len(s1), cb, d.size, out.ctypes.data, C.byref(ol), C.byref(crc))
+    assert rc == 0 and ol.value == d.size
+    assert np.array_equal(out[:d.size], d)
+    import zlib
+    assert crc.value == zlib.crc32(d.tobytes())
+    if len(s0) > 40:
+        bad = bytearray(s0)
+        bad[-5] ^= 0xFF  # the terminator's length field: no longer a terminator
+        rc = unrzip_simt.simt_unrzip_chunk(bytes(bad), len(bad), s1, len(s1), cb, d.size, out.ctypes.data, C.byref(ol),
+                                           C.byref(crc))
+        assert rc != 0
+
+
+@pytest.mark.skipif(not oracle.have_ref(), reason="oracle/_ref not built")
+def test_lzma_and_zstd_decode_kernels_under_simt(unrzip_simt):
+    """lzma_dec_kernel on payloads of the reference's own LzmaCompress (levels 5-9, as lzma_compress_buf stores them) and
+    zstd_dec_kernel on libzstd frames, both as the product launches them (a job record per block)."""
+    for level, dic in ((5, 1 << 24), (7, 1 << 25), (9, 1 << 26)):
+        for d in (datagen.generate("text", 300_000), datagen.generate("rep", 400_000, block=1 << 14),
+                  np.zeros(100_000, dtype=np.uint8), datagen.generate("vm", 300_000)):
+            d = np.ascontiguousarray(d)
+            z = oracle.ref_lzma_block(d.tobytes(), level, dic)
+            out = np.zeros(d.size + 8, dtype=np.uint8)
+            r = unrzip_simt.simt_block_decode(0, z, len(z), out.ctypes.data, d.size)
+            assert r == d.size and np.array_equal(out[:d.size], d), (level, r)
+    _, Z = _zstd_libs()
+    d = np.ascontiguousarray(datagen.generate("text", 500_000))
+    buf = np.zeros(d.size + 1024, dtype=np.uint8)
+    sz = Z.ZSTD_compress(buf.ctypes.data, buf.size, d.ctypes.data, d.size, 17)
+    out = np.zeros(d.size + 8, dtype=np.uint8)
+    assert unrzip_simt.simt_block_decode(1, buf.ctypes.data, sz, out.ctypes.data, d.size) == d.size
+    assert np.array_equal(out[:d.size], d)
+
+
 def _lzma(Z, data, level, dic):
     n = len(data)
     cap = int(n * 1.02)
