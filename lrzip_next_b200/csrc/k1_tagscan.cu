@@ -28,7 +28,9 @@
 //     share); ballot, 16 B store per surviving lane at the warp's running count.
 #include "kernels.h"
 
+#if !defined(LRZ_SIMT_HOST)
 #include <cuda_runtime.h>
+#endif
 
 namespace lrz {
 
@@ -49,6 +51,28 @@ static constexpr int K1_OFF_BAR = ((K1_OFF_IN + K1_SMEM_IN + 15) / 16) * 16;
 static constexpr int K1_SMEM = K1_OFF_BAR + 32;
 static_assert(kTile == 512, "one candidate tile per warp and step");
 
+#if defined(LRZ_SIMT_HOST)
+// tests/hostsim (simt.h): an mbarrier is a phase bit, a bulk copy completes the moment it is issued
+__device__ __forceinline__ void mbar_init(uint64_t *bar, unsigned) { *bar = 0; }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *, unsigned) {}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, unsigned parity)
+{
+	while ((*(volatile uint64_t *)bar & 1) == parity)
+		simt::yield();
+}
+__device__ __forceinline__ void tma_load_1d(void *dst, const void *src, unsigned bytes, uint64_t *bar)
+{
+	memcpy(dst, src, bytes);
+	*bar ^= 1;
+}
+__device__ __forceinline__ void st_cand(Cand *dst, uint32_t plo, uint32_t phi, uint32_t tlo, uint32_t thi)
+{
+	dst->pos = (int64_t)(((uint64_t)phi << 32) | plo);
+	dst->tag = (int64_t)(((uint64_t)thi << 32) | tlo);
+}
+#define K1_FENCE_MBAR_INIT() ((void)0)
+#else
+#define K1_FENCE_MBAR_INIT() asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory")
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
 __device__ __forceinline__ void mbar_init(uint64_t *bar, unsigned count)
@@ -79,6 +103,7 @@ __device__ __forceinline__ void st_cand(Cand *dst, uint32_t plo, uint32_t phi, u
 {
 	asm volatile("st.global.cs.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(dst), "r"(plo), "r"(phi), "r"(tlo), "r"(thi) : "memory");
 }
+#endif
 
 __device__ __forceinline__ uint64_t shfl_up64(uint64_t v, int d)
 {
@@ -130,7 +155,11 @@ k1_tagscan_kernel(const uint8_t *__restrict__ buf, int64_t n, int64_t pos_lo, in
 		  const ScanState *__restrict__ state, int nstates, Cand *__restrict__ cand, uint32_t *__restrict__ tile_count,
 		  int64_t first_tile, int64_t num_tiles, int64_t first_step, int64_t num_steps)
 {
+#if defined(LRZ_SIMT_HOST)
+	uint8_t *smem = simt::dyn_smem();
+#else
 	extern __shared__ __align__(128) uint8_t smem[];
+#endif
 	uint64_t *tab = reinterpret_cast<uint64_t *>(smem);                // tab[b * 16 + (lane & 15)]
 	uint64_t *z = reinterpret_cast<uint64_t *>(smem + K1_OFF_Z);       // padded warp-relative running XORs
 	uint8_t *in = smem + K1_OFF_IN;
@@ -163,7 +192,7 @@ k1_tagscan_kernel(const uint8_t *__restrict__ buf, int64_t n, int64_t pos_lo, in
 	if (tid == 0) {
 		mbar_init(&bar[0], 1);
 		mbar_init(&bar[1], 1);
-		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+		K1_FENCE_MBAR_INIT();
 	}
 	__syncthreads();
 
@@ -248,12 +277,19 @@ int k1_init_tables()
 {
 	int64_t hi[256];
 	make_hash_index(hi);
+#if defined(LRZ_SIMT_HOST)
+	memcpy(c_hash_index, hi, sizeof(hi));
+	return 0;
+#else
 	cudaError_t e = cudaMemcpyToSymbol(c_hash_index, hi, sizeof(hi));
 	if (e != cudaSuccess)
 		return -1;
 	e = cudaFuncSetAttribute(k1_tagscan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, K1_SMEM);
 	return e == cudaSuccess ? 0 : -1;
+#endif
 }
+
+#if !defined(LRZ_SIMT_HOST) // launchers: the emulator (tests/hostsim) calls the kernel directly
 
 int k1_launch(const uint8_t *d_buf, int64_t n, int64_t pos_lo, int64_t pos_hi, int64_t mask,
 	      const ScanState *d_state, int nstates, Cand *d_cand, uint32_t *d_tile_count, int num_sms, cudaStream_t stream)
@@ -282,5 +318,6 @@ int k1_preload()
 	ok = ok && cudaFuncGetAttributes(&a, k1_tagscan_kernel) == cudaSuccess;
 	return ok ? 0 : -1;
 }
+#endif // !LRZ_SIMT_HOST
 
 } // namespace lrz

@@ -74,7 +74,11 @@ __device__ __forceinline__ uint32_t d_xpow_bytes(int64_t nbytes)
 __global__ void __launch_bounds__(CRC_THREADS)
 crc32_kernel(const uint8_t *__restrict__ buf, int64_t n, uint32_t *__restrict__ acc)
 {
+#if defined(LRZ_SIMT_HOST)
+	uint8_t *smem = simt::dyn_smem();
+#else
 	extern __shared__ __align__(16) uint8_t smem[];
+#endif
 	uint32_t *tab = reinterpret_cast<uint32_t *>(smem);                   // tab[b * 32 + lane]
 	uint32_t *data = reinterpret_cast<uint32_t *>(smem + CRC_SMEM_TABLE); // piece l at word l * 33
 	uint32_t *red = reinterpret_cast<uint32_t *>(smem + CRC_SMEM_TABLE + CRC_SMEM_DATA);
@@ -180,11 +184,14 @@ int k4_init_tables()
 	    cudaMemcpyToSymbol(c_x2n, x2n, sizeof(x2n)) != cudaSuccess ||
 	    cudaMemcpyToSymbol(c_piece_shift, shift, sizeof(shift)) != cudaSuccess)
 		return -1;
+#if !defined(LRZ_SIMT_HOST)
 	if (cudaFuncSetAttribute(crc32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, CRC_SMEM) != cudaSuccess)
 		return -1;
+#endif
 	return 0;
 }
 
+#if !defined(LRZ_SIMT_HOST) // launchers: the emulator (tests/hostsim) calls the kernels directly
 int crc32_launch(const uint8_t *d_buf, int64_t n, uint32_t *d_crc, int num_sms, cudaStream_t stream)
 {
 	if (cudaMemsetAsync(d_crc, 0, sizeof(uint32_t), stream) != cudaSuccess)
@@ -198,6 +205,7 @@ int crc32_launch(const uint8_t *d_buf, int64_t n, uint32_t *d_crc, int num_sms, 
 	crc32_kernel<<<(unsigned)grid, CRC_THREADS, CRC_SMEM, stream>>>(d_buf, n, d_crc);
 	return cudaGetLastError() == cudaSuccess ? 0 : -1;
 }
+#endif
 
 // ------------------------------------------------------------------------------------------------
 // Stream 0: one warp per record, lanes stride over the record's 0xFFFF-byte pieces.
@@ -244,6 +252,7 @@ k4_headers_kernel(const MatchRec *__restrict__ recs, int64_t n_rec, int cb, cons
 	}
 }
 
+#if !defined(LRZ_SIMT_HOST)
 int k4_headers_launch(const MatchRec *d_recs, int64_t n_rec, int chunk_bytes, const uint32_t *d_crc,
 		      uint8_t *d_s0, cudaStream_t stream)
 {
@@ -255,6 +264,7 @@ int k4_headers_launch(const MatchRec *d_recs, int64_t n_rec, int chunk_bytes, co
 	k4_headers_kernel<<<(unsigned)blocks, 256, 0, stream>>>(d_recs, n_rec, chunk_bytes, d_crc, d_s0);
 	return cudaGetLastError() == cudaSuccess ? 0 : -1;
 }
+#endif
 
 // ------------------------------------------------------------------------------------------------
 // Stream 1: output-driven gather.  Each thread owns 16 consecutive output bytes (aligned 16-byte
@@ -326,6 +336,7 @@ k4_literals_kernel(const uint8_t *__restrict__ buf, const MatchRec *__restrict__
 	}
 }
 
+#if !defined(LRZ_SIMT_HOST)
 int k4_literals_launch(const uint8_t *d_buf, const MatchRec *d_recs, int64_t n_rec, int64_t s1_from, int64_t s1_len,
 		       uint8_t *d_s1, int num_sms, cudaStream_t stream)
 {
@@ -338,6 +349,7 @@ int k4_literals_launch(const uint8_t *d_buf, const MatchRec *d_recs, int64_t n_r
 	k4_literals_kernel<<<(unsigned)grid, LIT_THREADS, 0, stream>>>(d_buf, d_recs, n_rec, s1_from, s1_len, d_s1);
 	return cudaGetLastError() == cudaSuccess ? 0 : -1;
 }
+#endif
 
 // ------------------------------------------------------------------------------------------------
 // Flush order (src/stream.c:2198-2216 write_stream flushes a stream buffer the moment it is full;
@@ -371,6 +383,7 @@ __global__ void k4_flush_order_kernel(const MatchRec *__restrict__ recs, int64_t
 	w1[j] = written;
 }
 
+#if !defined(LRZ_SIMT_HOST)
 int k4_flush_order_launch(const MatchRec *d_recs, int64_t n_rec, int chunk_bytes, int64_t bufsize,
 			  int64_t n_bounds, int64_t *d_w1, cudaStream_t stream)
 {
@@ -393,5 +406,6 @@ int k4_preload()
 	ok = ok && cudaFuncGetAttributes(&a, k4_literals_kernel) == cudaSuccess;
 	return ok ? 0 : -1;
 }
+#endif // !LRZ_SIMT_HOST
 
 } // namespace lrz

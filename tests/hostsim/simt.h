@@ -29,9 +29,24 @@
 #define __launch_bounds__(...)
 #define __noinline__ __attribute__((noinline))
 
+#define __align__(n) __attribute__((aligned(n)))
+#define __constant__ static
+
 struct longlong2 {
 	long long x, y;
 };
+struct uint4 {
+	unsigned x, y, z, w;
+};
+static inline uint4 make_uint4(unsigned x, unsigned y, unsigned z, unsigned w)
+{
+	uint4 v;
+	v.x = x;
+	v.y = y;
+	v.z = z;
+	v.w = w;
+	return v;
+}
 static inline longlong2 make_longlong2(long long x, long long y)
 {
 	longlong2 v;
@@ -88,6 +103,7 @@ struct Block {
 	BarSync bars[16];
 	std::function<void()> entry;
 	unsigned long long collectives = 0;
+	std::vector<uint8_t> dyn_smem; // `extern __shared__` of the kernel
 };
 
 static Block *B = nullptr;
@@ -99,6 +115,14 @@ static inline void block_on(const volatile unsigned *p, unsigned v)
 	f.wait_val = v;
 	simt_switch(&f.sp, B->sched_sp);
 	f.wait_on = nullptr;
+}
+
+// gives the other threads a turn (a polling loop must call it: scheduling is cooperative)
+static inline void yield()
+{
+	Fiber &f = B->fibers[(size_t)B->cur];
+	f.wait_on = nullptr;
+	simt_switch(&f.sp, B->sched_sp);
 }
 
 // every lane of the calling warp deposits v; returns the 32 deposited values
@@ -140,9 +164,10 @@ static void fiber_main()
 
 // Runs `kernel` as one block of `nthreads` threads with blockIdx.x = block_x.  Returns false on a deadlock.
 static inline bool run_block(int nthreads, unsigned block_x, std::function<void()> kernel, size_t stack_bytes = 256 << 10,
-			     unsigned grid_x = 1)
+			     unsigned grid_x = 1, size_t dyn_smem_bytes = 0)
 {
 	Block blk;
+	blk.dyn_smem.assign(dyn_smem_bytes + 256, 0xCD); // uninitialised on the device: a pattern, not zeros
 	blk.nthreads = nthreads;
 	blk.bidx.x = block_x;
 	blk.bdim.x = (unsigned)nthreads;
@@ -193,12 +218,18 @@ static inline bool run_block(int nthreads, unsigned block_x, std::function<void(
 }
 
 // A one-dimensional grid, block after block (blocks of a grid do not synchronise with each other).
-static inline bool run_grid(unsigned grid_x, int nthreads, std::function<void()> kernel, size_t stack_bytes = 64 << 10)
+static inline bool run_grid(unsigned grid_x, int nthreads, std::function<void()> kernel, size_t stack_bytes = 64 << 10,
+			    size_t dyn_smem_bytes = 0)
 {
 	for (unsigned b = 0; b < grid_x; b++)
-		if (!run_block(nthreads, b, kernel, stack_bytes, grid_x))
+		if (!run_block(nthreads, b, kernel, stack_bytes, grid_x, dyn_smem_bytes))
 			return false;
 	return true;
+}
+static inline uint8_t *dyn_smem() // 128-byte aligned
+{
+	uint8_t *p = B->dyn_smem.data();
+	return p + ((128 - ((uintptr_t)p & 127)) & 127);
 }
 
 } // namespace simt
@@ -243,6 +274,17 @@ static inline T __shfl_xor_sync(unsigned, T val, int lane_mask)
 	return r;
 }
 template <class T>
+static inline T __shfl_up_sync(unsigned, T val, unsigned delta)
+{
+	uint64_t raw = 0;
+	memcpy(&raw, &val, sizeof(T));
+	const int lane = simt::B->cur & 31;
+	const uint64_t *v = simt::warp_exchange(raw);
+	T r;
+	memcpy(&r, &v[lane >= (int)delta ? lane - (int)delta : lane], sizeof(T));
+	return r;
+}
+template <class T>
 static inline T __shfl_down_sync(unsigned, T val, unsigned delta)
 {
 	uint64_t raw = 0;
@@ -261,6 +303,22 @@ static inline int __ffs(int v) { return __builtin_ffs(v); }
 static inline int __ffsll(long long v) { return __builtin_ffsll(v); }
 static inline int __clzll(long long v) { return v ? __builtin_clzll((unsigned long long)v) : 64; }
 static inline long long clock64() { return 0; }
+template <class T>
+static inline T __ldcs(const T *p) { return *p; }
+static inline unsigned __funnelshift_r(unsigned lo, unsigned hi, unsigned sh) // low 32 bits of (hi:lo) >> (sh & 31)
+{
+	sh &= 31;
+	return sh ? (lo >> sh) | (hi << (32 - sh)) : lo;
+}
+static inline unsigned atomicXor(unsigned *p, unsigned v)
+{
+	const unsigned o = *p;
+	*p = o ^ v;
+	return o;
+}
+// the few runtime calls that kernel files make next to their kernels (table set-up)
+enum { cudaSuccess = 0 };
+#define cudaMemcpyToSymbol(sym, src, bytes) (memcpy((void *)&(sym), (src), (bytes)), cudaSuccess)
 static inline unsigned atomicOr(unsigned *p, unsigned v)
 {
 	const unsigned o = *p;

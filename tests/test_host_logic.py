@@ -114,6 +114,45 @@ def test_batched_commit_kernel_under_simt_equals_scalar_logic(k2simt, kind, n, l
         assert dbg[15] > 0 and dbg[2] == 0  # match tails instead of serial steps
 
 
+@pytest.mark.parametrize("kind,n,level,seg", [
+    ("text", 300_000, 7, 1 << 18), ("rep", 1 << 20, 7, 1 << 20), ("mix", 700_000, 7, 12288), ("trees", 600_000, 9, 1 << 18),
+    ("vm", 500_000, 7, 100_000), ("text", 200_000, 3, 4096), ("text", 40, 7, 4096), ("text", 31, 7, 4096), ("text", 32, 7, 4096),
+    ("text", 4096 + 31, 7, 4096),
+])
+def test_every_kernel_of_the_rzip_stage_under_simt_equals_oracle(k2simt, kind, n, level, seg):
+    """The rzip stage's device code end to end on the CPU: K1 (k1_tagscan.cu, its TMA copies as memcpys), K2
+    (k2_commit.cu, 256 threads), the chunk CRC and K4's header / literal kernels (k4_emit.cu), each run under the SIMT
+    emulator with the product's block shapes, segment by segment -- streams and outgoing counter equal the oracle's."""
+    d = _trees_small(n) if kind == "trees" else datagen.generate(kind, n)
+    got, _ = _simt_commit(k2simt, d, level, seg, 0, 0, 3)
+    o0, o1, _, ovr = oracle.rzip_chunk(d, level)
+    assert (got[0], got[1], got[2]) == (o0, o1, ovr)
+
+
+@pytest.mark.parametrize("kind,n,mask,lo,hi", [("text", 300_000, 1, 0, 300_000), ("rep", 1 << 19, 1, 0, 1 << 19),
+                                               ("text", 70_000, 15, 0, 70_000), ("text", 100_000, 0, 0, 100_000),
+                                               ("text", 40, 1, 0, 40), ("text", 31, 1, 0, 31),
+                                               ("text", 200_000, 3, 65536, 150_016)])
+def test_tag_scan_kernel_under_simt_matches_full_tag(k2simt, kind, n, mask, lo, hi):
+    """K1 alone (as tests/test_gpu_rzip.py::test_tag_scan_matches_full_tag does on the GPU): positions and tags of every
+    candidate against the reference's definition, tag(p) = XOR of hash_index over bytes p .. p + 30 (src/rzip.c:385-416)."""
+    d = np.ascontiguousarray(datagen.generate(kind, n))
+    k2simt.simt_tag_scan.restype = C.c_int64
+    k2simt.simt_tag_scan.argtypes = [C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p]
+    pos = np.zeros(max(1, hi - lo), dtype=np.int64)
+    tag = np.zeros(max(1, hi - lo), dtype=np.int64)
+    k = k2simt.simt_tag_scan(d.ctypes.data, n, lo, hi, mask, pos.ctypes.data, tag.ctypes.data)
+    assert k >= 0
+    hidx = oracle.hash_index()
+    x = np.concatenate(([0], np.bitwise_xor.accumulate(hidx[d])))
+    end = n - 31
+    p = np.arange(max(lo, 1), min(hi, end + 1)) if end >= 1 else np.arange(0)
+    t = x[p + 31] ^ x[p] if p.size else p
+    keep = (t & mask) == mask if p.size else np.zeros(0, dtype=bool)
+    assert k == int(keep.sum())
+    assert np.array_equal(pos[:k], p[keep]) and np.array_equal(tag[:k], t[keep])
+
+
 def test_commit_kernel_grid_of_counter_variants_under_simt(k2simt):
     """lrzgpu_chunk_begin_all's launch shape: k2_commit_kernel as a grid of max_chain_len CTAs, CTA v starting from
     victim_round = v on its own state / table / records (blockIdx.x strides), all reading one candidate list made with
