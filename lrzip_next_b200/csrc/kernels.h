@@ -2,9 +2,18 @@
 #pragma once
 #if defined(LRZ_SIMT_HOST) // tests/hostsim: kernels compiled for the CPU under the SIMT emulator (simt.h)
 #include "simt.h"
-typedef void *cudaStream_t;
 #else
 #include <cuda_runtime.h>
+#endif
+// A kernel launch that the emulator can take over (host orchestration that is worth running in the CPU tests as it is):
+// on the device exactly `kernel<<<grid, block, smem, stream>>>(args...)`.
+#if !defined(LRZ_LAUNCH)
+#if defined(LRZ_SIMT_HOST)
+#define LRZ_LAUNCH(grid, block, smem, stream, kernel, ...) \
+	((void)(stream), (void)simt::run_grid((unsigned)(grid), (int)(block), [&]() { kernel(__VA_ARGS__); }, 64 << 10, (size_t)(smem)))
+#else
+#define LRZ_LAUNCH(grid, block, smem, stream, kernel, ...) kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__)
+#endif
 #endif
 #include "lrz_common.h"
 

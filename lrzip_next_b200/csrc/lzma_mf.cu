@@ -400,13 +400,13 @@ static int sort_by(const MfBlock &B, int kind, int bits, uint32_t *bufs[4], uint
 	uint32_t *ki = nullptr, *vi = nullptr, *ko = bufs[0], *vo = bufs[1];
 	for (int shift = 0, pass = 0; shift < bits; shift += 8, pass++) {
 		if (pass == 0) {
-			rs_hist_kernel<true><<<tiles, RS_THREADS, 0, st>>>(nullptr, ks, count, shift, hist, tiles);
-			rs_scan_kernel<<<1, 1024, 0, st>>>(hist, 256 * tiles);
-			rs_scatter_kernel<true><<<tiles, RS_THREADS, 0, st>>>(nullptr, nullptr, ks, count, shift, hist, tiles, ko, vo);
+			LRZ_LAUNCH(tiles, RS_THREADS, 0, st, rs_hist_kernel<true>, nullptr, ks, count, shift, hist, tiles);
+			LRZ_LAUNCH(1, 1024, 0, st, rs_scan_kernel, hist, 256 * tiles);
+			LRZ_LAUNCH(tiles, RS_THREADS, 0, st, rs_scatter_kernel<true>, nullptr, nullptr, ks, count, shift, hist, tiles, ko, vo);
 		} else {
-			rs_hist_kernel<false><<<tiles, RS_THREADS, 0, st>>>(ki, ks, count, shift, hist, tiles);
-			rs_scan_kernel<<<1, 1024, 0, st>>>(hist, 256 * tiles);
-			rs_scatter_kernel<false><<<tiles, RS_THREADS, 0, st>>>(ki, vi, ks, count, shift, hist, tiles, ko, vo);
+			LRZ_LAUNCH(tiles, RS_THREADS, 0, st, rs_hist_kernel<false>, ki, ks, count, shift, hist, tiles);
+			LRZ_LAUNCH(1, 1024, 0, st, rs_scan_kernel, hist, 256 * tiles);
+			LRZ_LAUNCH(tiles, RS_THREADS, 0, st, rs_scatter_kernel<false>, ki, vi, ks, count, shift, hist, tiles, ko, vo);
 		}
 		if (launches)
 			*launches += 3;
@@ -433,24 +433,24 @@ int mf_prepare_block(const MfBlock &B, void *scratch, cudaStream_t st, int64_t *
 	uint32_t *K, *V;
 	if (sort_by(B, KEY_H2, 10, bufs, hist, &K, &V, st, launches))
 		return -1;
-	mf_prev_kernel<<<grid, 256, 0, st>>>(K, V, count, B.c2);
+	LRZ_LAUNCH(grid, 256, 0, st, mf_prev_kernel, K, V, count, B.c2);
 	if (sort_by(B, KEY_H3, 16, bufs, hist, &K, &V, st, launches))
 		return -1;
-	mf_prev_kernel<<<grid, 256, 0, st>>>(K, V, count, B.c3);
+	LRZ_LAUNCH(grid, 256, 0, st, mf_prev_kernel, K, V, count, B.c3);
 	int bits = 0;
 	while (bits < 32 && (B.P.hashMask >> bits))
 		bits++;
 	if (B.P.hc5) { // hash chains: the predecessor in the 5-byte-hash order IS the chain link (son[])
 		if (sort_by(B, KEY_H5, bits, bufs, hist, &K, &V, st, launches))
 			return -1;
-		mf_prev_kernel<<<grid, 256, 0, st>>>(K, V, count, B.sorted);
+		LRZ_LAUNCH(grid, 256, 0, st, mf_prev_kernel, K, V, count, B.sorted);
 		if (launches)
 			*launches += 3;
 		return cudaGetLastError() == cudaSuccess ? 0 : -1;
 	}
 	if (sort_by(B, KEY_H4, bits, bufs, hist, &K, &V, st, launches))
 		return -1;
-	mf_first_kernel<<<grid, 256, 0, st>>>(K, V, count, B.src, B.P, B.sorted, B.rec);
+	LRZ_LAUNCH(grid, 256, 0, st, mf_first_kernel, K, V, count, B.src, B.P, B.sorted, B.rec);
 	if (launches)
 		*launches += 3;
 	return cudaGetLastError() == cudaSuccess ? 0 : -1;
@@ -465,9 +465,9 @@ int mf_walk_launch(const MfBlock *d_blocks, int nblocks, const uint64_t *d_segBa
 	if (grid > 0x7fffffffull)
 		return -1;
 	if (hc5)
-		mf_hc_kernel<<<(unsigned)grid, 128, 0, st>>>(d_blocks, nblocks, d_segBase);
+		LRZ_LAUNCH((unsigned)grid, 128, 0, st, mf_hc_kernel, d_blocks, nblocks, d_segBase);
 	else
-		mf_walk_kernel<<<(unsigned)grid, 128, 0, st>>>(d_blocks, nblocks, d_segBase);
+		LRZ_LAUNCH((unsigned)grid, 128, 0, st, mf_walk_kernel, d_blocks, nblocks, d_segBase);
 	if (launches)
 		*launches += 1;
 	return cudaGetLastError() == cudaSuccess ? 0 : -1;
@@ -475,6 +475,7 @@ int mf_walk_launch(const MfBlock *d_blocks, int nblocks, const uint64_t *d_segBa
 
 // Load this file's kernels now (CUDA loads a kernel's code at its first launch, and that load waits for every kernel
 // that is running -- block encoders run for tens of seconds).
+#if !defined(LRZ_SIMT_HOST)
 int mf_preload()
 {
 	cudaFuncAttributes a;
@@ -491,6 +492,7 @@ int mf_preload()
 	ok = ok && cudaFuncGetAttributes(&a, rs_scatter_kernel<false>) == cudaSuccess;
 	return ok ? 0 : -1;
 }
+#endif
 
 } // namespace lzma
 } // namespace lrz

@@ -1,6 +1,6 @@
 // lzma_mf.h -- host interface of the data-parallel LZMA match finder (lzma_mf.cu).
 #pragma once
-#include <cuda_runtime.h>
+#include "kernels.h" // cuda_runtime.h (or the emulator's stand-ins, tests/hostsim) and LRZ_LAUNCH
 #include <stddef.h>
 #include <stdint.h>
 

@@ -318,6 +318,29 @@ static inline unsigned atomicXor(unsigned *p, unsigned v)
 }
 // the few runtime calls that kernel files make next to their kernels (table set-up)
 enum { cudaSuccess = 0 };
+typedef void *cudaStream_t;
+static inline int cudaGetLastError() { return cudaSuccess; }
+static inline void __threadfence() {}
+static inline unsigned atomicAdd(unsigned *p, unsigned v)
+{
+	const unsigned o = *p;
+	*p = o + v;
+	return o;
+}
+static inline unsigned long long atomicAdd(unsigned long long *p, unsigned long long v)
+{
+	const unsigned long long o = *p;
+	*p = o + v;
+	return o;
+}
+static inline unsigned __match_any_sync(unsigned, unsigned val) // lanes of the warp holding the same value
+{
+	const uint64_t *v = simt::warp_exchange(val);
+	unsigned m = 0;
+	for (int i = 0; i < 32; i++)
+		m |= (unsigned)((unsigned)v[i] == val) << i;
+	return m;
+}
 #define cudaMemcpyToSymbol(sym, src, bytes) (memcpy((void *)&(sym), (src), (bytes)), cudaSuccess)
 static inline unsigned atomicOr(unsigned *p, unsigned v)
 {

@@ -251,6 +251,38 @@ def _lzma_pre(Z, data, level, dic):
     return (None if (rc != 0 or ol.value >= n) else out.raw[:ol.value]), pw.value
 
 
+@pytest.mark.skipif(not oracle.have_ref(), reason="oracle/_ref not built")
+@pytest.mark.parametrize("level,dic", [(7, 1 << 25), (5, 1 << 24), (9, 1 << 26), (3, 1 << 20), (1, 1 << 16)])
+def test_match_finder_kernels_under_simt_give_the_reference_payload(level, dic):
+    """K7a itself on the CPU: lzma_mf.cu's radix-sort, predecessor and tree-walk / hash-chain kernels, launched by the
+    product's own orchestration (mf_prepare_block, mf_walk_launch) through the SIMT emulator; the block is then encoded
+    by the host build of the encoder over those match lists and must equal the reference's LzmaCompress byte for byte
+    (a run of zeros goes through the long-bucket path of the walk: one bucket, thousands of insertions)."""
+    subprocess.run(["make", "-s", "-C", os.path.join(HERE, "hostsim"), "liblzmamfsimt.so"], check=True)
+    M = C.CDLL(os.path.join(HERE, "hostsim", "liblzmamfsimt.so"))
+    M.simt_lzma_encode_mf.argtypes = [C.c_void_p, C.c_int64, C.c_int, C.c_uint32, C.c_uint32, C.c_void_p, C.c_int64,
+                                      C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
+    rng = np.random.default_rng(2)
+    cases = {"text": datagen.generate("text", 200_000), "zeros": np.zeros(50_000, dtype=np.uint8),
+             "rep": datagen.generate("rep", 300_000, block=1 << 13), "random": rng.integers(0, 256, 60_000, dtype=np.uint8),
+             "tiny": datagen.generate("text", 100), "vm": datagen.generate("vm", 250_000),
+             "mixed": np.concatenate([datagen.generate("text", 80_000), np.zeros(30_000, dtype=np.uint8),
+                                      datagen.generate("text", 80_000)])}
+    for name, d in cases.items():
+        d = np.ascontiguousarray(d)
+        out = np.zeros(int(d.size * 1.1) + 4096, dtype=np.uint8)
+        ol, pw = C.c_int64(), C.c_int64()
+        rc = M.simt_lzma_encode_mf(d.ctypes.data, d.size, level, dic, 32 if level < 7 else 64, out.ctypes.data, out.size,
+                                   C.byref(ol), C.byref(pw))
+        assert rc == 0, (name, rc)
+        ref = oracle.ref_lzma_block(d.tobytes(), level, dic)
+        if ref is None:  # the reference leaves the block stored: our payload is not smaller either
+            assert ol.value >= d.size, name
+        else:
+            assert bytes(out[:ol.value]) == ref, (name, level)
+            assert pw.value > 0 or d.size < 8
+
+
 def test_lzma_bucketwise_match_finder_equals_serial(hostsim):
     """The data-parallel pre-pass (positions grouped by hash, one bucket at a time) must hand the encoder
     exactly what the serial two-thread finder does -- including when the block is longer than the
