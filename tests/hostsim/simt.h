@@ -7,7 +7,10 @@
 // sequentially consistent, and a collective that not every lane of a warp reaches is reported as a deadlock.
 //
 // Restrictions (all met by the kernels built with it): full-warp masks only, block size a multiple of 32, all lanes
-// of a warp leave the kernel together, no spin-waiting on memory.
+// of a warp leave the kernel together, polling loops must call __nanosleep / simt::yield.  Lanes run one after the other
+// between collectives, so a kernel whose lanes execute REPLICATED scalar code on shared state in lockstep (every lane
+// doing `state->x++` and relying on the warp doing it once: K7b, lzma_enc.cuh) cannot be emulated -- tried, and that is
+// why the LZMA parser's device-only paths stay covered by the GPU tests alone.
 // The product never includes this header: a kernel source opts in with `#if defined(LRZ_SIMT_HOST)`.
 #pragma once
 #include <stdint.h>
@@ -151,6 +154,16 @@ static inline void bar_sync(int id, int count)
 		b.gen = g + 1;
 	} else
 		block_on(&b.gen, g);
+}
+
+// bar.arrive: counts towards the barrier without waiting for it (the producer half of a producer / consumer pair)
+static inline void bar_arrive(int id, int count)
+{
+	BarSync &b = B->bars[id];
+	if (++b.arrived == count) {
+		b.arrived = 0;
+		b.gen++;
+	}
 }
 
 static void fiber_main()
@@ -303,6 +316,26 @@ static inline int __ffs(int v) { return __builtin_ffs(v); }
 static inline int __ffsll(long long v) { return __builtin_ffsll(v); }
 static inline int __clzll(long long v) { return v ? __builtin_clzll((unsigned long long)v) : 64; }
 static inline long long clock64() { return 0; }
+static inline void __nanosleep(unsigned) { simt::yield(); }
+static inline void __threadfence_block() {}
+template <class T>
+static inline T __ldcg(const T *p) { return *(const volatile T *)p; }
+static inline unsigned __brev(unsigned v)
+{
+	unsigned r = 0;
+	for (int i = 0; i < 32; i++)
+		r |= ((v >> i) & 1u) << (31 - i);
+	return r;
+}
+static inline int __clz(int v) { return v ? __builtin_clz((unsigned)v) : 32; }
+static inline unsigned __reduce_add_sync(unsigned, unsigned val)
+{
+	const uint64_t *v = simt::warp_exchange(val);
+	unsigned s = 0;
+	for (int i = 0; i < 32; i++)
+		s += (unsigned)v[i];
+	return s;
+}
 template <class T>
 static inline T __ldcs(const T *p) { return *p; }
 static inline unsigned __funnelshift_r(unsigned lo, unsigned hi, unsigned sh) // low 32 bits of (hi:lo) >> (sh & 31)
