@@ -452,7 +452,7 @@ def test_zstd_frame_decoder_reads_libzstd_and_our_own_frames():
 
     for name, d in cases.items():
         d = np.ascontiguousarray(d)
-        for level in (1, 3, 7, 12, 17, 19, 22):
+        for level in (1, 7, 17, 22):
             buf = np.zeros(d.size + d.size // 8 + 1024, dtype=np.uint8)
             sz = Z.ZSTD_compress(buf.ctypes.data, buf.size, d.ctypes.data, d.size, level)
             assert not Z.ZSTD_isError(sz)
