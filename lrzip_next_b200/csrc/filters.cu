@@ -94,7 +94,11 @@ __global__ void __launch_bounds__(256) delta_save_kernel(const uint8_t *s, int64
 __global__ void __launch_bounds__(256) delta_apply_kernel(uint8_t *s, int64_t from, int64_t to, int64_t bs, int delta,
 							  int tiles_per_block, const uint8_t *side)
 {
+#if defined(LRZ_SIMT_HOST)
+	uint8_t *tile = simt::dyn_smem();
+#else
 	extern __shared__ uint8_t tile[]; // delta saved bytes, then the tile
+#endif
 	const int64_t k = blockIdx.y, t = blockIdx.x;
 	const int64_t len = block_len(k, from, to, bs), t0 = t * kDeltaTile;
 	if (t0 >= len)
@@ -139,38 +143,39 @@ int filter_blocks_launch(int filter, int delta, uint8_t *s, int64_t from, int64_
 			gx = 1184; // 8 CTAs on each of 148 SMs, grid-stride
 		if (gx == 0)
 			gx = 1;
-		filter_words_kernel<<<dim3(gx, (unsigned)nblk), 256, 0, stream>>>(s, from, to, bs, filter, enc);
+		LRZ_LAUNCH(dim3(gx, (unsigned)nblk), 256, 0, stream, filter_words_kernel, s, from, to, bs, filter, enc);
 		if (launches)
 			*launches += 1;
 	} else if (flt::serial(filter)) {
-		filter_serial_kernel<<<(unsigned)nblk, 32, 0, stream>>>(s, from, to, bs, filter, enc);
+		LRZ_LAUNCH((unsigned)nblk, 32, 0, stream, filter_serial_kernel, s, from, to, bs, filter, enc);
 		if (launches)
 			*launches += 1;
 	} else if (filter == flt::kIA64) {
 		const int64_t bundles = (bs < to - from ? bs : to - from) >> 4;
 		unsigned gx = (unsigned)((bundles + 255) / 256);
 		gx = gx > 1184 ? 1184 : (gx ? gx : 1);
-		filter_ia64_kernel<<<dim3(gx, (unsigned)nblk), 256, 0, stream>>>(s, from, to, bs, enc);
+		LRZ_LAUNCH(dim3(gx, (unsigned)nblk), 256, 0, stream, filter_ia64_kernel, s, from, to, bs, enc);
 		if (launches)
 			*launches += 1;
 	} else if (!enc) { // delta, decode side
 		if (delta < 1 || delta > kDeltaMax)
 			return -1;
-		delta_decode_kernel<<<(unsigned)nblk, 256, 0, stream>>>(s, from, to, bs, delta);
+		LRZ_LAUNCH((unsigned)nblk, 256, 0, stream, delta_decode_kernel, s, from, to, bs, delta);
 		if (launches)
 			*launches += 1;
 	} else { // delta
 		if (delta < 1 || delta > kDeltaMax || !side)
 			return -1;
 		const int tpb = (int)((bs + kDeltaTile - 1) / kDeltaTile);
-		delta_save_kernel<<<dim3((unsigned)tpb, (unsigned)nblk), 256, 0, stream>>>(s, from, to, bs, delta, tpb, side);
-		delta_apply_kernel<<<dim3((unsigned)tpb, (unsigned)nblk), 256, kDeltaTile + kDeltaMax, stream>>>(s, from, to, bs, delta, tpb, side);
+		LRZ_LAUNCH(dim3((unsigned)tpb, (unsigned)nblk), 256, 0, stream, delta_save_kernel, s, from, to, bs, delta, tpb, side);
+		LRZ_LAUNCH(dim3((unsigned)tpb, (unsigned)nblk), 256, kDeltaTile + kDeltaMax, stream, delta_apply_kernel, s, from, to, bs, delta, tpb, side);
 		if (launches)
 			*launches += 2;
 	}
 	return cudaGetLastError() == cudaSuccess ? 0 : -1;
 }
 
+#if !defined(LRZ_SIMT_HOST)
 int filter_preload()
 {
 	cudaFuncAttributes a;
@@ -183,5 +188,7 @@ int filter_preload()
 	ok = ok && cudaFuncGetAttributes(&a, delta_apply_kernel) == cudaSuccess;
 	return ok ? 0 : -1;
 }
+
+#endif
 
 } // namespace lrz

@@ -10,7 +10,7 @@
 #if !defined(LRZ_LAUNCH)
 #if defined(LRZ_SIMT_HOST)
 #define LRZ_LAUNCH(grid, block, smem, stream, kernel, ...) \
-	((void)(stream), (void)simt::run_grid((unsigned)(grid), (int)(block), [&]() { kernel(__VA_ARGS__); }, 64 << 10, (size_t)(smem)))
+	((void)(stream), (void)simt::run_grid(dim3(grid), (int)(block), [&]() { kernel(__VA_ARGS__); }, 64 << 10, (size_t)(smem)))
 #else
 #define LRZ_LAUNCH(grid, block, smem, stream, kernel, ...) kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__)
 #endif

@@ -35,6 +35,10 @@
 #define __align__(n) __attribute__((aligned(n)))
 #define __constant__ static
 
+struct dim3 {
+	unsigned x, y, z;
+	dim3(unsigned x_ = 1, unsigned y_ = 1, unsigned z_ = 1) : x(x_), y(y_), z(z_) {}
+};
 struct longlong2 {
 	long long x, y;
 };
@@ -177,9 +181,11 @@ static void fiber_main()
 
 // Runs `kernel` as one block of `nthreads` threads with blockIdx.x = block_x.  Returns false on a deadlock.
 static inline bool run_block(int nthreads, unsigned block_x, std::function<void()> kernel, size_t stack_bytes = 256 << 10,
-			     unsigned grid_x = 1, size_t dyn_smem_bytes = 0)
+			     unsigned grid_x = 1, size_t dyn_smem_bytes = 0, unsigned block_y = 0, unsigned grid_y = 1)
 {
 	Block blk;
+	blk.bidx.y = block_y;
+	blk.gdim.y = grid_y;
 	blk.dyn_smem.assign(dyn_smem_bytes + 256, 0xCD); // uninitialised on the device: a pattern, not zeros
 	blk.nthreads = nthreads;
 	blk.bidx.x = block_x;
@@ -231,12 +237,13 @@ static inline bool run_block(int nthreads, unsigned block_x, std::function<void(
 }
 
 // A one-dimensional grid, block after block (blocks of a grid do not synchronise with each other).
-static inline bool run_grid(unsigned grid_x, int nthreads, std::function<void()> kernel, size_t stack_bytes = 64 << 10,
+static inline bool run_grid(dim3 grid, int nthreads, std::function<void()> kernel, size_t stack_bytes = 64 << 10,
 			    size_t dyn_smem_bytes = 0)
 {
-	for (unsigned b = 0; b < grid_x; b++)
-		if (!run_block(nthreads, b, kernel, stack_bytes, grid_x, dyn_smem_bytes))
-			return false;
+	for (unsigned by = 0; by < grid.y; by++)
+		for (unsigned b = 0; b < grid.x; b++)
+			if (!run_block(nthreads, b, kernel, stack_bytes, grid.x, dyn_smem_bytes, by, grid.y))
+				return false;
 	return true;
 }
 static inline uint8_t *dyn_smem() // 128-byte aligned

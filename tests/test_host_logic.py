@@ -659,6 +659,50 @@ def test_block_filters_match_the_reference_converters():
     assert H.hostsim_filter_block(9, 0, None, 0) != 0  # no such filter
 
 
+def test_filter_kernels_under_simt_match_reference_converters_per_block():
+    """filters.cu's kernels through the product's own filter_blocks_launch (SIMT emulator): a stretch of three stream
+    blocks, the last one short, every block converted from its own position 0 -- byte-equal to the reference's converter
+    applied block by block, and undone by the decode-side launch."""
+    H, R = _filter_libs()
+    subprocess.run(["make", "-s", "-C", os.path.join(HERE, "hostsim"), "libfilterssimt.so"], check=True)
+    F = C.CDLL(os.path.join(HERE, "hostsim", "libfilterssimt.so"))
+    F.simt_filter_blocks.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_int64, C.c_int64, C.c_int]
+    rng = np.random.default_rng(11)
+    bs, n = 40_000, 40_000 * 2 + 12_345
+    ids = {"X86": 1, "ARM": 2, "ARMT": 3, "PPC": 4, "SPARC": 5, "IA64": 6, "ARM64": 7, "RISCV": 8}
+
+    def ref_block(kind, blk, delta=0):
+        b = blk.copy()
+        if kind == "X86":
+            st = C.c_uint32(0)
+            R.z7_BranchConvSt_X86_Enc(b.ctypes.data, b.size, 0, C.byref(st))
+        elif kind == "DELTA":
+            st = (C.c_ubyte * 256)()
+            R.Delta_Init(st)
+            R.Delta_Encode(st, delta, b.ctypes.data, b.size)
+        else:
+            getattr(R, f"z7_BranchConv_{kind}_Enc")(b.ctypes.data, b.size, 0)
+        return b
+
+    for kind, fid in ids.items():
+        d = _code_like(rng, kind, n)
+        want = np.concatenate([ref_block(kind, np.ascontiguousarray(d[o:o + bs])) for o in range(0, n, bs)])
+        got = d.copy()
+        assert F.simt_filter_blocks(fid, 0, got.ctypes.data, n, bs, 1) == 0
+        assert np.array_equal(got, want), kind
+        assert (got != d).any(), kind
+        assert F.simt_filter_blocks(fid, 0, got.ctypes.data, n, bs, 0) == 0
+        assert np.array_equal(got, d), (kind, "decode")
+    for delta in (1, 3, 16, 48, 256):
+        d = rng.integers(0, 256, n, dtype=np.uint8)
+        want = np.concatenate([ref_block("DELTA", np.ascontiguousarray(d[o:o + bs]), delta) for o in range(0, n, bs)])
+        got = d.copy()
+        assert F.simt_filter_blocks(128, delta, got.ctypes.data, n, bs, 1) == 0
+        assert np.array_equal(got, want), ("delta", delta)
+        assert F.simt_filter_blocks(128, delta, got.ctypes.data, n, bs, 0) == 0
+        assert np.array_equal(got, d), ("delta decode", delta)
+
+
 # ---- archive walker (SURVEY.md 8(f4)): lrzgpu_info against what `lrzip-next -i -vv` prints ---------------------
 def _ref_info(archive: bytes):
     """Parse the reference's `-i -vv` listing: per-block rows and the totals."""
