@@ -14,7 +14,9 @@
 // sequences from the same data-parallel match finder the LZMA backend uses, FSE-coded with the format's
 // predefined tables, Huffman literals), which the reference's ZSTD_decompress() accepts; a frame that is
 // not smaller than the block leaves the block stored, like the reference does.
+#if !defined(LRZ_SIMT_HOST) // (tests/hostsim builds the kernels of this file for the SIMT emulator, not the pipeline)
 #include "backend.h"
+#endif
 
 #include <stdio.h>
 #include <stdlib.h>
@@ -33,6 +35,7 @@ namespace lrz {
 
 namespace {
 
+#if !defined(LRZ_SIMT_HOST)
 struct DevBuf {
 	void *p = nullptr;
 	size_t cap = 0;
@@ -57,6 +60,7 @@ struct DevBuf {
 		cap = 0;
 	}
 };
+#endif
 
 // ---- lz4 gate -------------------------------------------------------------------------------------
 struct GateJob {
@@ -341,7 +345,11 @@ __device__ void lzma_coder_thread(lzma::Enc *e)
 // warp 2 runs the lz4 compressibility gate beside it; one thread of warp 3 is the range coder.
 __global__ void __launch_bounds__(160, 1) lzma_block_kernel(LzmaJob *jobs)
 {
+#if defined(LRZ_SIMT_HOST)
+	uint8_t *lzma_smem = simt::dyn_smem();
+#else
 	extern __shared__ __align__(16) uint8_t lzma_smem[];
+#endif
 	__shared__ uint32_t gate_table[4096];
 	__shared__ int done, gate_state;
 	lzma::Enc *e = reinterpret_cast<lzma::Enc *>(lzma_smem);
@@ -459,6 +467,7 @@ int64_t round_up_page(int64_t v, int page) { return v % page ? v + page - v % pa
 
 } // namespace
 
+#if !defined(LRZ_SIMT_HOST)
 // ---- LZMA pipeline ------------------------------------------------------------------------------------
 // Blocks are SUBMITTED (lz4 gate, match finder, parser enqueued on the backend's own streams, no host wait)
 // and later DRAINED (wait, read verdicts and lengths).  The rzip stage submits stream-1 blocks while it is
@@ -1131,5 +1140,6 @@ int backend_preload()
 	ok = ok && lzma::mf_preload() == 0;
 	return ok ? 0 : -1;
 }
+#endif // !LRZ_SIMT_HOST
 
 } // namespace lrz

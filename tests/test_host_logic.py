@@ -484,6 +484,52 @@ def test_zstd_frame_decoder_reads_libzstd_and_our_own_frames():
     assert refused >= 190
 
 
+def test_zstd_kernels_under_simt_make_frames_libzstd_decodes():
+    """K6's kernels themselves on the CPU (SIMT emulator): zstd_encode_kernel per 128 KiB zstd block over the match lists
+    of K7a's kernels, zstd_assemble_kernel for the frame -- the frame decodes with the system's libzstd and with the
+    product's own decoder, is as long as what the host build of the same encoder assembles, and an incompressible block is
+    reported as "stays stored" (src/stream.c:215-221)."""
+    import ctypes as C
+    L, Z = _zstd_libs()
+    here = os.path.join(os.path.dirname(os.path.abspath(__file__)), "hostsim")
+    K = C.CDLL(os.path.join(here, "libzstdkernelssimt.so"))
+    K.simt_zstd_frame.restype = C.c_int64
+    K.simt_zstd_frame.argtypes = [C.c_void_p, C.c_int64, C.c_int, C.c_uint32, C.c_void_p, C.c_int64, C.POINTER(C.c_int),
+                                  C.POINTER(C.c_int64)]
+    D = C.CDLL(os.path.join(here, "libzstddechost.so"))
+    D.hostsim_zstd_decode.restype = C.c_int64
+    D.hostsim_zstd_decode.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64]
+    rng = np.random.default_rng(3)
+    cases = {
+        "text": datagen.gen_text(300_000), "edge": datagen.gen_text(131072 * 2 + 1), "zeros": np.zeros(200_000, dtype=np.uint8),
+        "lowent": rng.integers(0, 3, 150_000, dtype=np.uint8), "rep": datagen.gen_rep(300_000, block=1 << 14),
+        "mix": np.concatenate([datagen.gen_text(150_000), rng.integers(0, 256, 40_000, dtype=np.uint8),
+                               np.zeros(140_000, dtype=np.uint8)]), "small": datagen.gen_text(3000),
+    }
+    for name, d in cases.items():
+        d = np.ascontiguousarray(d)
+        n = d.size
+        out = np.zeros(n + n // 8 + 1024, dtype=np.uint8)
+        why, nc = C.c_int(), C.c_int64()
+        sz = K.simt_zstd_frame(d.ctypes.data, n, 7, 1 << 25, out.ctypes.data, n, C.byref(why), C.byref(nc))  # outCap = n
+        assert sz > 0 and why.value == 0, (name, sz, why.value)
+        back = np.zeros(n + 16, dtype=np.uint8)
+        r = Z.ZSTD_decompress(back.ctypes.data, back.size, out.ctypes.data, sz)
+        assert not Z.ZSTD_isError(r) and r == n and np.array_equal(back[:n], d), name
+        back[:] = 0
+        assert D.hostsim_zstd_decode(out.ctypes.data, sz, back.ctypes.data, n) == n and np.array_equal(back[:n], d), name
+        host = np.zeros(n + n // 8 + 1024, dtype=np.uint8)
+        hc = C.c_int64()
+        hs = L.hostsim_zstd_compress(d.ctypes.data, n, 7, 1 << 25, host.ctypes.data, host.size, C.byref(hc))
+        # (the host build's own frame assembly may choose RLE where the kernel writes a 1-byte raw block: same sizes)
+        assert hs == sz and hc.value == nc.value, (name, hs, sz)
+    d = np.ascontiguousarray(rng.integers(0, 256, 200_000, dtype=np.uint8))
+    out = np.zeros(d.size + 1024, dtype=np.uint8)
+    why, nc = C.c_int(), C.c_int64()
+    assert K.simt_zstd_frame(d.ctypes.data, d.size, 7, 1 << 25, out.ctypes.data, d.size, C.byref(why), C.byref(nc)) == 0
+    assert why.value == 3  # the frame is not smaller than the block: it stays stored
+
+
 def test_zstd_block_encoder_frames_decode_with_libzstd():
     import ctypes as C
     L, Z = _zstd_libs()
